@@ -1,0 +1,175 @@
+"""jrl_walkgen_b200 - B200-native batched backend for jrl-walkgen's ZMP pattern-generation hot path.
+
+The product is ``libwalkgen_b200.so`` (hand-written CUDA for sm_100a behind the C ABI in
+``include/walkgen_b200.h``) plus the C++ class mirror in ``jrl_walkgen_b200/host/``.  This Python
+package is a thin numpy-facing driver over the C ABI used by ``tests/`` and ``bench.py``; it holds
+no algorithmic code and has no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import (MODE_WITH_INITIALPOS, MODE_WITHOUT_INITIALPOS, WG_MEM_DEVICE, WG_MEM_HOST,
+                    PreviewGains, WalkgenError)
+
+__all__ = ["Context", "PreviewPlan", "preview_gains", "WalkgenError", "device_count",
+           "MODE_WITH_INITIALPOS", "MODE_WITHOUT_INITIALPOS", "WG_MEM_HOST", "WG_MEM_DEVICE"]
+
+
+def device_count() -> int:
+    return _capi.load().wg_device_count()
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, DeviceBuffer):
+        return C.c_void_p(a.ptr)
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def preview_gains(T=0.005, preview_time=1.6, zc=0.814, mode=MODE_WITHOUT_INITIALPOS) -> PreviewGains:
+    """Host Riccati solve: PreviewControl::ComputeOptimalWeights (PreviewControl.cpp:198-322)."""
+    g = PreviewGains()
+    rc = _capi.load().wg_preview_gains(T, preview_time, zc, mode, C.byref(g))
+    if rc != 0:
+        raise WalkgenError(rc, "wg_preview_gains")
+    return g
+
+
+class DeviceBuffer:
+    """A device allocation owned by a Context (plain pointer + size)."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        ctx._check(ctx.lib.wg_malloc_device(ctx.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.wg_memcpy_h2d(self.ctx.h, self.ptr, arr.ctypes.data, arr.nbytes))
+        self.ctx.sync()
+        return self
+
+    def download(self, dtype, shape):
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.wg_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes))
+        self.ctx.sync()
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.wg_free_device(self.ctx.h, self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One per GPU (wg_ctx).  Raises WalkgenError(WG_ERR_NO_DEVICE) when there is no GPU."""
+
+    def __init__(self, device=0):
+        self.lib = _capi.load()
+        h = C.c_void_p()
+        rc = self.lib.wg_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise WalkgenError(rc, "wg_ctx_create: no usable CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise WalkgenError(rc, self.lib.wg_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.wg_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self._check(self.lib.wg_sync(self.h))
+
+    def alloc(self, nbytes) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr) -> DeviceBuffer:
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, max(arr.nbytes, 8)).upload(arr)
+
+    def pinned(self, shape, dtype=np.float64):
+        """numpy view on pinned host memory (kept alive by the returned array's base)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self.lib.wg_malloc_pinned(self.h, max(n, 8), C.byref(p)))
+        buf = (C.c_char * max(n, 8)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return arr
+
+    def timer_start(self):
+        self._check(self.lib.wg_timer_start(self.h))
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.wg_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launches(self) -> int:
+        return self.lib.wg_launch_count(self.h)
+
+    def reset_launches(self):
+        self.lib.wg_launch_count_reset(self.h)
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.wg_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    # ---- Kajita preview control ---------------------------------------------------------
+    def preview_set_gains(self, gains: PreviewGains):
+        self._check(self.lib.wg_preview_set_gains(self.h, C.byref(gains)))
+        self.gains = gains
+
+    def preview_plan(self, offsets) -> "PreviewPlan":
+        return PreviewPlan(self, offsets)
+
+    def preview_one_iteration(self, x, y, sx, sy, window_xy, simulation=True):
+        """PreviewControl::OneIterationOfPreview for one instance (host buffers)."""
+        x = np.array(x, dtype=np.float64)
+        y = np.array(y, dtype=np.float64)
+        w = np.ascontiguousarray(window_xy, dtype=np.float64)
+        csx, csy, zx, zy = C.c_double(sx), C.c_double(sy), C.c_double(), C.c_double()
+        D = _capi.c_double_p
+        rc = self.lib.wg_preview_one_iteration(self.h, x.ctypes.data_as(D), y.ctypes.data_as(D), C.byref(csx),
+                                               C.byref(csy), w.ctypes.data_as(D), w.shape[0], C.byref(zx),
+                                               C.byref(zy), int(simulation))
+        self._check(rc)
+        return x, y, csx.value, csy.value, zx.value, zy.value
+
+
+class PreviewPlan:
+    def __init__(self, ctx: Context, offsets):
+        self.ctx = ctx
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.B = len(self.offsets) - 1
+        h = C.c_void_p()
+        ctx._check(ctx.lib.wg_preview_plan_create(ctx.h, self.B, self.offsets.ctypes.data_as(_capi.c_i64_p),
+                                                  C.byref(h)))
+        self.h = h
+        self.total_steps = ctx.lib.wg_preview_plan_total_steps(h)
+        self.total_samples = ctx.lib.wg_preview_plan_total_samples(h)
+
+    def run(self, zmpref_xy, state, com_out=None, zmp_out=None, simulation=True, mem=WG_MEM_HOST):
+        self.ctx._check(self.ctx.lib.wg_preview_run_batch(self.ctx.h, self.h, mem, _ptr(zmpref_xy), _ptr(state),
+                                                          _ptr(com_out), _ptr(zmp_out), int(simulation)))
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.wg_preview_plan_destroy(self.h)
+            self.h = None

@@ -1,0 +1,242 @@
+"""Kajita2003 preview control: oracle pins (CPU) and CUDA-vs-oracle parity (GPU).
+
+Reference: PreviewControl::ComputeOptimalWeights / OneIterationOfPreview
+(src/PreviewControl/PreviewControl.cpp:198-374), OptimalControllerSolver::ComputeWeights
+(src/PreviewControl/OptimalControllerSolver.cpp:200-352).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+# Gains shipped by the reference in src/data/PreviewControlParameters.ini (zc 0.814, T 5 ms, 1.6 s),
+# 5 significant digits: a sanity pin at ~1e-4 relative.
+INI_KX = (72719.0, 21550.0, 177.01)
+INI_KS = 618.7
+INI_F012 = (618.7, 777.51, 952.26)
+
+TOL_COM = 1e-9   # m; north_star asks for 1e-6 m - we test three orders tighter
+
+
+def synth_walk(rng, L):
+    """Piecewise-constant ZMP reference resembling a footstep sequence."""
+    z = np.zeros((L, 2))
+    k = 0
+    x = 0.0
+    side = 1.0
+    while k < L:
+        n = int(rng.integers(120, 200))
+        z[k:k + n, 0] = x
+        z[k:k + n, 1] = side * 0.095
+        x += rng.uniform(0.05, 0.25)
+        side = -side
+        k += n
+    return z
+
+
+def test_oracle_gains_match_reference_ini():
+    g = ol.OracleGains(0.005, 1.6, 0.814, 1)
+    assert g.NL == 320
+    assert np.allclose(g.Kx, INI_KX, rtol=2e-4)
+    assert abs(g.Ks - INI_KS) / INI_KS < 2e-4
+    assert np.allclose(g.F[:3], INI_F012, rtol=2e-4)
+
+
+@pytest.mark.parametrize("T,Tp,zc,mode,R", [(0.005, 1.6, 0.814, 1, 1e-6), (0.005, 1.6, 0.807709, 1, 1e-6),
+                                              (0.01, 1.6, 0.814, 0, 1e-5)])
+def test_oracle_gains_match_scipy_dare(T, Tp, zc, mode, R):
+    """TestRiccatiEquation's two configurations (tests/TestRiccatiEquation.cpp) against an independent
+    DARE solver."""
+    from scipy.linalg import solve_discrete_are
+    g = ol.OracleGains(T, Tp, zc, mode)
+    A = np.array([[1, T, T * T / 2], [0, 1, T], [0, 0, 1.0]])
+    B = np.array([[T ** 3 / 6], [T * T / 2], [T]])
+    Cm = np.array([[1, 0, -zc / 9.81]])
+    if mode == 1:
+        Ax = np.zeros((4, 4)); Ax[0, 0] = 1; Ax[0, 1:] = Cm @ A; Ax[1:, 1:] = A
+        bx = np.vstack([Cm @ B, B]); cx = np.array([[1, 0, 0, 0.0]])
+    else:
+        Ax, bx, cx = A, B, Cm
+    P = solve_discrete_are(Ax, bx, cx.T @ cx, np.array([[R]]))
+    la = 1.0 / (R + bx.T @ P @ bx)
+    K = (la * bx.T @ P @ Ax).ravel()
+    rec = P @ cx.T if mode == 1 else cx.T.copy()
+    Ac = (Ax - bx @ K[None, :]).T
+    F = []
+    for _ in range(g.NL):
+        F.append((la * bx.T @ rec).item())
+        rec = Ac @ rec
+    F = np.array(F)
+    assert np.abs(F - g.F).max() <= 1e-9 * np.abs(F).max()
+    assert abs(K[0] - g.Ks) <= 1e-9 * abs(K[0])
+    kx = K[1:] if mode == 1 else K
+    assert np.allclose(kx, g.Kx, rtol=1e-9)
+
+
+def test_product_gains_match_oracle():
+    """wg_preview_gains is host code (SDA Riccati) - runs without a GPU."""
+    import jrl_walkgen_b200 as wg
+    for (T, Tp, zc, mode) in [(0.005, 1.6, 0.814, 1), (0.005, 1.6, 0.807709, 1), (0.01, 1.6, 0.814, 0),
+                              (0.005, 0.8, 0.75, 1)]:
+        g = wg.preview_gains(T, Tp, zc, mode)
+        o = ol.OracleGains(T, Tp, zc, mode)
+        assert g.NL == o.NL
+        F = np.array(g.F[:g.NL])
+        assert np.abs(F - o.F).max() <= 1e-9 * np.abs(o.F).max()
+        assert abs(g.Ks - o.Ks) <= 1e-9 * abs(o.Ks)
+        assert np.allclose(np.array(g.Kx[:]), o.Kx, rtol=1e-9)
+        assert np.allclose(np.array(g.A[:]), o.A) and np.allclose(np.array(g.B[:]), o.B)
+
+
+def test_oracle_step_equals_run():
+    """oracle_preview_run is oracle_preview_step iterated (FIFO popped once per tick)."""
+    g = ol.OracleGains()
+    rng = np.random.default_rng(0)
+    z = synth_walk(rng, 400)
+    st = np.zeros(8)
+    com, zmp, steps = ol.oracle_preview_batch(g, [0, 400], z, st)
+    assert steps == 81
+    x = np.zeros(3); y = np.zeros(3); sx = C.c_double(0); sy = C.c_double(0)
+    zx = C.c_double(); zy = C.c_double()
+    for k in range(81):
+        rc = ol.oracle().oracle_preview_step(ol.dptr(g.A), ol.dptr(g.B), ol.dptr(g.C), ol.dptr(g.Kx), g.Ks,
+                                             ol.dptr(g.F), g.NL, ol.dptr(x), ol.dptr(y), C.byref(sx), C.byref(sy),
+                                             ol.dptr(z[k:]), 400 - k, C.byref(zx), C.byref(zy), 1)
+        assert rc == 0
+        assert np.array_equal(com[k, :3], x) and np.array_equal(com[k, 3:], y)
+        assert zmp[k, 0] == zx.value and zmp[k, 1] == zy.value
+    # window under-filled -> error, as the reference LTHROWs (PreviewControl.cpp:341-344)
+    rc = ol.oracle().oracle_preview_step(ol.dptr(g.A), ol.dptr(g.B), ol.dptr(g.C), ol.dptr(g.Kx), g.Ks,
+                                         ol.dptr(g.F), g.NL, ol.dptr(x), ol.dptr(y), C.byref(sx), C.byref(sy),
+                                         ol.dptr(z), 319, C.byref(zx), C.byref(zy), 1)
+    assert rc == -1
+
+
+def test_oracle_tracks_constant_reference():
+    """Property: with a constant ZMP reference the controller converges to CoM = ZMP = reference."""
+    g = ol.OracleGains()
+    z = np.tile(np.array([[0.3, -0.1]]), (4000, 1))
+    st = np.zeros(8)
+    com, zmp, steps = ol.oracle_preview_batch(g, [0, 4000], z, st)
+    assert abs(com[steps - 1, 0] - 0.3) < 1e-6 and abs(com[steps - 1, 3] + 0.1) < 1e-6
+    assert abs(zmp[steps - 1, 0] - 0.3) < 1e-6 and abs(zmp[steps - 1, 1] + 0.1) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU parity
+# ------------------------------------------------------------------------------------------------
+def _run_gpu(ctx, gains, offsets, z, st0, simulation=True, mem_device=False):
+    import jrl_walkgen_b200 as wg
+    ctx.preview_set_gains(gains)
+    plan = ctx.preview_plan(offsets)
+    n = int(offsets[-1])
+    st = st0.copy()
+    com = np.full((max(n, 1), 6), np.nan)
+    zmp = np.full((max(n, 1), 2), np.nan)
+    if mem_device:
+        dz = ctx.to_device(z if n else np.zeros(2)); ds = ctx.to_device(st)
+        dc = ctx.to_device(com); dzo = ctx.to_device(zmp)
+        plan.run(dz, ds, dc, dzo, simulation, mem=wg.WG_MEM_DEVICE)
+        ctx.sync()
+        st = ds.download(np.float64, st.shape); com = dc.download(np.float64, com.shape)
+        zmp = dzo.download(np.float64, zmp.shape)
+        for b in (dz, ds, dc, dzo):
+            b.free()
+    else:
+        plan.run(z, st, com, zmp, simulation)
+    steps = plan.total_steps
+    plan.destroy()
+    return com, zmp, st, steps
+
+
+def _valid_rows(offsets, NL):
+    rows = []
+    for b in range(len(offsets) - 1):
+        L = offsets[b + 1] - offsets[b]
+        rows.extend(range(offsets[b], offsets[b] + max(0, L - NL + 1)))
+    return np.array(rows, dtype=np.int64)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mem_device", [False, True])
+def test_gpu_preview_matches_oracle_ragged(ctx, mem_device):
+    import jrl_walkgen_b200 as wg
+    rng = np.random.default_rng(1)
+    gains = wg.preview_gains(0.005, 1.6, 0.807709, 1)
+    og = ol.OracleGains(0.005, 1.6, 0.807709, 1)
+    # ragged lengths incl. edge cases: shorter than the window (0 steps), exactly NL (1 step),
+    # tile boundaries of the FIR kernel (1024 outputs per block)
+    lens = [3362 + 640, 319, 320, 321, 320 + 1023, 320 + 1024, 320 + 1025, 0, 2500, 5000, 640]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    z = np.concatenate([synth_walk(rng, L) for L in lens if L > 0])
+    st0 = rng.normal(scale=0.01, size=(len(lens), 8))
+    com, zmp, st, steps = _run_gpu(ctx, gains, offsets, z, st0, True, mem_device)
+    st_o = st0.copy()
+    com_o, zmp_o, steps_o = ol.oracle_preview_batch(og, offsets, z, st_o)
+    assert steps == steps_o
+    rows = _valid_rows(offsets, 320)
+    assert np.abs(com[rows] - com_o[rows])[:, [0, 3]].max() < TOL_COM
+    assert np.abs(zmp[rows] - zmp_o[rows]).max() < 1e-8
+    assert np.allclose(st[:, :6], st_o[:, :6], atol=1e-8)
+    assert np.allclose(st, st_o, rtol=1e-7, atol=1e-8)
+    # rows past a trajectory's last step are untouched
+    mask = np.ones(len(com), bool); mask[rows] = False
+    assert np.isnan(com[mask]).all()
+
+
+@pytest.mark.gpu
+def test_gpu_preview_no_simulation_flag(ctx):
+    import jrl_walkgen_b200 as wg
+    rng = np.random.default_rng(2)
+    gains = wg.preview_gains(); og = ol.OracleGains()
+    offsets = np.array([0, 900, 2000], dtype=np.int64)
+    z = np.concatenate([synth_walk(rng, 900), synth_walk(rng, 1100)])
+    st0 = rng.normal(scale=0.01, size=(2, 8))
+    com, zmp, st, _ = _run_gpu(ctx, gains, offsets, z, st0, simulation=False)
+    st_o = st0.copy()
+    com_o, zmp_o, _ = ol.oracle_preview_batch(og, offsets, z, st_o, simulation=False)
+    rows = _valid_rows(offsets, 320)
+    assert np.abs(com[rows] - com_o[rows]).max() < 1e-7
+    assert np.array_equal(st[:, 6:], st0[:, 6:])  # integrators untouched when Simulation=false
+
+
+@pytest.mark.gpu
+def test_gpu_preview_one_iteration_and_window_error(ctx):
+    import jrl_walkgen_b200 as wg
+    rng = np.random.default_rng(3)
+    gains = wg.preview_gains(); og = ol.OracleGains()
+    ctx.preview_set_gains(gains)
+    z = synth_walk(rng, 320)
+    x0 = rng.normal(scale=0.01, size=3); y0 = rng.normal(scale=0.01, size=3)
+    x, y, sx, sy, zx, zy = ctx.preview_one_iteration(x0, y0, 0.01, -0.02, z)
+    st = np.concatenate([x0, y0, [0.01, -0.02]])
+    com_o, zmp_o, _ = ol.oracle_preview_batch(og, [0, 320], z, st)
+    assert np.allclose(x, st[:3], atol=1e-10) and np.allclose(y, st[3:6], atol=1e-10)
+    assert abs(sx - st[6]) < 1e-9 and abs(sy - st[7]) < 1e-9
+    assert abs(zx - zmp_o[0, 0]) < 1e-9 and abs(zy - zmp_o[0, 1]) < 1e-9
+    with pytest.raises(wg.WalkgenError) as ei:
+        ctx.preview_one_iteration(x0, y0, 0.0, 0.0, z[:319])
+    assert ei.value.code == -6  # WG_ERR_WINDOW <-> LTHROW at PreviewControl.cpp:341-344
+
+
+@pytest.mark.gpu
+def test_gpu_preview_linearity_full_size(ctx):
+    """Size-independent property at BASELINE config-2 scale (4096 walks): the map
+    (zmpref, state0) -> outputs is linear, so run(a)+run(b) == run(a+b)."""
+    import jrl_walkgen_b200 as wg
+    rng = np.random.default_rng(4)
+    gains = wg.preview_gains()
+    B = 4096
+    lens = rng.integers(2800, 4600, size=B)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = int(offsets[-1])
+    za = rng.normal(scale=0.1, size=(n, 2)); zb = rng.normal(scale=0.1, size=(n, 2))
+    sa = rng.normal(scale=0.01, size=(B, 8)); sb = rng.normal(scale=0.01, size=(B, 8))
+    ca, _, fa, _ = _run_gpu(ctx, gains, offsets, za, sa)
+    cb, _, fb, _ = _run_gpu(ctx, gains, offsets, zb, sb)
+    cs, _, fs, _ = _run_gpu(ctx, gains, offsets, za + zb, sa + sb)
+    rows = _valid_rows(offsets, 320)[::97]
+    assert np.abs(ca[rows] + cb[rows] - cs[rows])[:, [0, 3]].max() < 1e-9
+    assert np.abs(fa + fb - fs)[:, :6].max() < 1e-8
