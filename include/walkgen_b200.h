@@ -113,7 +113,8 @@ int64_t wg_preview_plan_total_samples(const wg_preview_plan *plan); /* offsets[B
  *                                           x, y, sxzmp, syzmp of OneIterationOfPreview
  *   com_out   : [total_samples][6]  out     row offsets[b]+k = (x,dx,ddx,y,dy,ddy) after step k
  *   zmp_out   : [total_samples][2]  out     row offsets[b]+k = (zmpx2, zmpy2) of step k
- *                                           (rows past a trajectory's last step are left untouched)
+ *                                           (rows past a trajectory's last step: left untouched with
+ *                                           WG_MEM_DEVICE, zero with WG_MEM_HOST)
  *   simulation: the `Simulation` flag (accumulate sxzmp += zmpref - zmp, PreviewControl.cpp:363-367)
  * com_out / zmp_out may be NULL. */
 int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *plan, int mem, const double *zmpref_xy,

@@ -452,8 +452,14 @@ int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double
   const size_t ns = (size_t)pl->total_samples;
   if (!pl->d_zmp) WG_CUDA(ctx, cudaMalloc(&pl->d_zmp, sizeof(double) * 2 * std::max<size_t>(1, ns)));
   if (!pl->d_state) WG_CUDA(ctx, cudaMalloc(&pl->d_state, sizeof(double) * 8 * pl->B));
-  if (com_out && !pl->d_com) WG_CUDA(ctx, cudaMalloc(&pl->d_com, sizeof(double) * 6 * std::max<size_t>(1, ns)));
-  if (zmp_out && !pl->d_zmpout) WG_CUDA(ctx, cudaMalloc(&pl->d_zmpout, sizeof(double) * 2 * std::max<size_t>(1, ns)));
+  if (com_out && !pl->d_com) {  // zero once: rows past a trajectory's last step read back as 0 in host mode
+    WG_CUDA(ctx, cudaMalloc(&pl->d_com, sizeof(double) * 6 * std::max<size_t>(1, ns)));
+    WG_CUDA(ctx, cudaMemsetAsync(pl->d_com, 0, sizeof(double) * 6 * std::max<size_t>(1, ns), ctx->stream));
+  }
+  if (zmp_out && !pl->d_zmpout) {
+    WG_CUDA(ctx, cudaMalloc(&pl->d_zmpout, sizeof(double) * 2 * std::max<size_t>(1, ns)));
+    WG_CUDA(ctx, cudaMemsetAsync(pl->d_zmpout, 0, sizeof(double) * 2 * std::max<size_t>(1, ns), ctx->stream));
+  }
   WG_CUDA(ctx, cudaMemcpyAsync(pl->d_zmp, zmpref_xy, sizeof(double) * 2 * ns, cudaMemcpyHostToDevice, ctx->stream));
   WG_CUDA(ctx, cudaMemcpyAsync(pl->d_state, state, sizeof(double) * 8 * pl->B, cudaMemcpyHostToDevice, ctx->stream));
   int rc = preview_launch(ctx, pl, pl->d_zmp, pl->d_state, com_out ? pl->d_com : nullptr,
