@@ -126,6 +126,75 @@ int wg_preview_one_iteration(wg_ctx *ctx, double *x, double *y, double *sxzmp, d
                              const double *window_xy, int n_available, double *zmpx2, double *zmpy2,
                              int simulation);
 
+/* ------------------------------------------------------------------------------------------------
+ * Herdt2010 velocity-referenced QP (N = 16 previewed samples of T = 0.1 s)
+ *   replaces GeneratorVelRef::build_invariant_part / update_problem / build_constraints
+ *                (src/ZMPRefTrajectoryGeneration/generator-vel-ref.cpp:588-674, :285-474, :555-584)
+ *            RelativeFeetInequalities::set_vertices / compute_linear_system
+ *                (src/Mathematics/relative-feet-inequalities.cpp:186-234, :265-319)
+ *            QPProblem::add_term_to / solve          (src/ZMPRefTrajectoryGeneration/qp-problem.cpp:411-547, :246-407)
+ *            ql0001_ / ql0002_                       (src/Mathematics/qld.cpp:378-2090)
+ *            LinearizedInvertedPendulum2D::Interpolation / OneIteration
+ *                (src/PreviewControl/LinearizedInvertedPendulum2D.cpp:157-264)
+ * ---------------------------------------------------------------------------------------------- */
+#define WG_HERDT_N 16            /* QP_N_, ZMPVelocityReferencedQP.cpp:65                        */
+#define WG_HERDT_MAX_STEPS 2     /* previewed steps ns in {0,1,2} for StepPeriod = 8 samples     */
+#define WG_HERDT_MAX_VARS (2 * WG_HERDT_N + 2 * WG_HERDT_MAX_STEPS)            /* 36 */
+#define WG_HERDT_MAX_ROWS (1 + 4 * WG_HERDT_N + 5 * WG_HERDT_MAX_STEPS)        /* 75: dummy row + CoP + feet */
+
+enum { WG_LEFT = 0, WG_RIGHT = 1 };  /* foot_type_e, privatepgtypes.hh:47-50 */
+enum { WG_SS = 0, WG_DS = 1 };       /* PhaseType,   privatepgtypes.hh:65-68 */
+
+/* Generator + robot constants (one set per context). */
+typedef struct wg_herdt_params {
+  double T;                 /* QP sampling period, 0.1          (ZMPVelocityReferencedQP.cpp:63)   */
+  double com_height;        /* QP model height, 0.814           (ZMPVelocityReferencedQP.cpp:103)  */
+  double w_jerk;            /* JERK_MIN weight 1e-5             (ZMPVelocityReferencedQP.cpp:118)  */
+  double w_vel;             /* INSTANT_VELOCITY weight 1.0      (ZMPVelocityReferencedQP.cpp:116)  */
+  double w_cop;             /* COP_CENTERING weight 1e-6        (ZMPVelocityReferencedQP.cpp:117)  */
+  double cop_half_x;        /* 0.5*sole_length - SecurityMarginX (FootHalfSize.cpp:62-68)          */
+  double cop_half_y;        /* 0.5*sole_width  - SecurityMarginY                                   */
+  double ds_feet_distance;  /* DSFeetDistance_ 0.2              (relative-feet-inequalities.cpp:45) */
+  double foot_hull_x[5];    /* LeftFPosEdgesX_                  (relative-feet-inequalities.cpp:51) */
+  double foot_hull_y[5];    /* LeftFPosEdgesY_ (right = -left)  (relative-feet-inequalities.cpp:52) */
+  double lipm_T;            /* control period for the 5 ms interpolation, 0.005                    */
+} wg_herdt_params;
+
+/* Defaults of the reference for a sole of (length, width) metres and margins 0.04 m. */
+void wg_herdt_default_params(double sole_length, double sole_width, wg_herdt_params *out);
+
+/* Everything GeneratorVelRef reads when it assembles one QP (one instance):
+ * IntermedData_->State().CoM, Ref.Global.{X,Y}_vec and Solution_.SupportStates_deq[0..N]. */
+typedef struct wg_herdt_qp_input {
+  double com_x[3], com_y[3];                       /* (c, dc, ddc) per axis                          */
+  double ref_x[WG_HERDT_N], ref_y[WG_HERDT_N];     /* velocity reference in the global frame         */
+  double sup_x[WG_HERDT_N + 1];                    /* support_state_t::X   [0] = current, [i] = previewed */
+  double sup_y[WG_HERDT_N + 1];                    /* support_state_t::Y                             */
+  double sup_yaw[WG_HERDT_N + 1];                  /* support_state_t::Yaw                           */
+  int8_t sup_foot[WG_HERDT_N + 1];                 /* WG_LEFT / WG_RIGHT                             */
+  int8_t sup_phase[WG_HERDT_N + 1];                /* WG_SS / WG_DS                                  */
+  int8_t sup_step[WG_HERDT_N + 1];                 /* support_state_t::StepNumber                    */
+  int8_t sup_changed[WG_HERDT_N + 1];              /* support_state_t::StateChanged                  */
+  int8_t pad_[4];
+} wg_herdt_qp_input;                               /* 784 bytes */
+
+/* solution_t as filled by QPProblem::solve (qp-problem.cpp:281-293) plus the first 0.1 s of CoM/ZMP. */
+typedef struct wg_herdt_qp_output {
+  double x[WG_HERDT_MAX_VARS];      /* Solution_vec: jerk_x[16], jerk_y[16], foot_x[ns], foot_y[ns]       */
+  double lagr[WG_HERDT_MAX_ROWS + 1]; /* ConstrLagr_vec; row 0 is the reference's all-zero dummy row      */
+  double com_next_x[3], com_next_y[3]; /* CoM_ after OneIteration(x[0], x[N]) (LIPM2D.cpp:230-264)        */
+  int32_t n_vars;                   /* 2N + 2ns                                                           */
+  int32_t n_rows;                   /* m_ = 1 + 4N + 5ns (incl. dummy row)                                */
+  int32_t fail;                     /* 0 ok (QLD ifail convention: >0 failure)                            */
+  int32_t iterations;               /* active-set changes (adds + drops)                                  */
+} wg_herdt_qp_output;
+
+int wg_herdt_set_params(wg_ctx *ctx, const wg_herdt_params *params);
+
+/* Build and solve B independent QPs.  in/out are arrays of B structs (host or device per `mem`). */
+int wg_herdt_qp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_herdt_qp_input *in,
+                            wg_herdt_qp_output *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,127 @@
+"""ctypes access to the Herdt part of the oracle (oracle/oracle_herdt.cpp).  TEST INFRASTRUCTURE."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N = 16
+MAX_VARS = 36
+MAX_ROWS = 75
+
+
+class HerdtParams(C.Structure):
+    _fields_ = [("T", C.c_double), ("com_height", C.c_double), ("w_jerk", C.c_double), ("w_vel", C.c_double),
+                ("w_cop", C.c_double), ("cop_half_x", C.c_double), ("cop_half_y", C.c_double),
+                ("ds_feet_distance", C.c_double), ("foot_hull_x", C.c_double * 5), ("foot_hull_y", C.c_double * 5),
+                ("lipm_T", C.c_double)]
+
+
+QP_INPUT_DTYPE = np.dtype([
+    ("com_x", "f8", 3), ("com_y", "f8", 3), ("ref_x", "f8", N), ("ref_y", "f8", N),
+    ("sup_x", "f8", N + 1), ("sup_y", "f8", N + 1), ("sup_yaw", "f8", N + 1),
+    ("sup_foot", "i1", N + 1), ("sup_phase", "i1", N + 1), ("sup_step", "i1", N + 1), ("sup_changed", "i1", N + 1),
+    ("pad_", "i1", 4)])
+QP_OUTPUT_DTYPE = np.dtype([
+    ("x", "f8", MAX_VARS), ("lagr", "f8", MAX_ROWS + 1), ("com_next_x", "f8", 3), ("com_next_y", "f8", 3),
+    ("n_vars", "i4"), ("n_rows", "i4"), ("fail", "i4"), ("iterations", "i4")])
+assert QP_INPUT_DTYPE.itemsize == 784 and QP_OUTPUT_DTYPE.itemsize == 960
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        L.oracle_herdt_set_ref_lib.argtypes = [C.c_char_p]
+        L.oracle_herdt_have_ref_qld.restype = C.c_int
+        L.oracle_herdt_default_params.argtypes = [C.c_double, C.c_double, C.POINTER(HerdtParams)]
+        L.oracle_herdt_build_qp.argtypes = [C.POINTER(HerdtParams), C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_herdt_solve_qp.argtypes = [C.POINTER(HerdtParams), C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_herdt_solve_qp.restype = C.c_int
+        L.oracle_herdt_solve_qp_batch.argtypes = [C.POINTER(HerdtParams), C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_herdt_solve_qp_batch.restype = C.c_long
+        L.oracle_herdt_sim_new.restype = C.c_void_p
+        L.oracle_herdt_sim_new.argtypes = [C.POINTER(HerdtParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_int]
+        L.oracle_herdt_sim_delete.argtypes = [C.c_void_p]
+        L.oracle_herdt_sim_set_robot.argtypes = [C.c_void_p] + [C.c_double] * 5
+        L.oracle_herdt_sim_set_initial_support.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.oracle_herdt_sim_set_vel_ref.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.oracle_herdt_sim_steps_before_stop.argtypes = [C.c_void_p, C.c_uint]
+        L.oracle_herdt_sim_stoppg.argtypes = [C.c_void_p]
+        L.oracle_herdt_sim_tick.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_herdt_sim_tick.restype = C.c_int
+        L.oracle_herdt_sim_num_qp.argtypes = [C.c_void_p]
+        L.oracle_herdt_sim_last_fail.argtypes = [C.c_void_p]
+        L.oracle_herdt_sim_get_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_herdt_sim_get_log.restype = C.c_int
+        ref = os.path.join(ROOT, "oracle", "_ref", "libwalkgen_ref.so")
+        if os.path.exists(ref):
+            L.oracle_herdt_set_ref_lib(ref.encode())
+        _lib = L
+    return _lib
+
+
+def default_params(sole_length=0.25, sole_width=0.14):
+    """Sole 0.25 x 0.14 m: fitted from the reference's datref."""
+    p = HerdtParams()
+    lib().oracle_herdt_default_params(sole_length, sole_width, C.byref(p))
+    return p
+
+
+class Sim:
+    """Closed-loop TestHerdt2010 harness around the oracle."""
+
+    def __init__(self, params=None, com0=(0.0316055, 0.0, 0.7116911), lf0=(0.0, 0.09, 0.0), rf0=(0.0, -0.09, 0.0),
+                 zmp0=(0.0, 0.0, 0.0), textbook=False, logging=False):
+        self.p = params or default_params()
+        a = [np.array(v, dtype=np.float64) for v in (com0, lf0, rf0, zmp0)]
+        self.h = lib().oracle_herdt_sim_new(C.byref(self.p), *[v.ctypes.data for v in a], int(textbook), int(logging))
+        self.row = np.zeros(37)
+
+    def initial_support(self, x, y, yaw):
+        lib().oracle_herdt_sim_set_initial_support(self.h, x, y, yaw)
+
+    def vel_ref(self, x, y, yaw):
+        lib().oracle_herdt_sim_set_vel_ref(self.h, x, y, yaw)
+
+    def steps_before_stop(self, n):
+        lib().oracle_herdt_sim_steps_before_stop(self.h, n)
+
+    def stoppg(self):
+        lib().oracle_herdt_sim_stoppg(self.h)
+
+    def tick(self):
+        rc = lib().oracle_herdt_sim_tick(self.h, self.row.ctypes.data)
+        return rc, self.row.copy()
+
+    def log(self):
+        n = lib().oracle_herdt_sim_num_qp(self.h)
+        ins = np.zeros(n, dtype=QP_INPUT_DTYPE)
+        x = np.zeros((n, MAX_VARS)); u = np.zeros((n, MAX_ROWS + 1)); meta = np.zeros((n, 3), dtype=np.int32)
+        k = lib().oracle_herdt_sim_get_log(self.h, ins.ctypes.data, x.ctypes.data, u.ctypes.data, meta.ctypes.data, n)
+        return ins[:k], x[:k], u[:k], meta[:k]
+
+    def close(self):
+        if self.h:
+            lib().oracle_herdt_sim_delete(self.h)
+            self.h = None
+
+
+def run_online_script(nticks, events, initial_support=None, **kw):
+    """TestHerdt2010 OnLine: tests/TestHerdt2010.cpp:66-90 (start) and :232-244 (events).  `events` maps the tick
+    index (m_OneStep.NbOfIt at the time generateEvent() runs) to a callable(sim)."""
+    sim = Sim(**kw)
+    sim.steps_before_stop(2)
+    if initial_support is not None:
+        sim.initial_support(*initial_support)
+    rows = np.zeros((nticks, 37))
+    for it in range(nticks):
+        rc, row = sim.tick()
+        rows[it] = row
+        if it in events:
+            events[it](sim)
+    return sim, rows
