@@ -1,20 +1,8 @@
+#!/bin/bash
+# Round-1 GPU session A: parity tests, bench line, ncu launch list + full capture of the preview kernels.
+mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-cat > /tmp/pv.py <<'PY'
-import numpy as np, time, sys
-sys.path.insert(0,'.')
-import jrl_walkgen_b200 as wg
-ctx = wg.Context(0)
-g = wg.preview_gains(); ctx.preview_set_gains(g)
-rng = np.random.default_rng(0)
-B=4096
-lens = rng.integers(2800,4600,size=B)
-off = np.concatenate([[0],np.cumsum(lens)]).astype(np.int64)
-n=int(off[-1])
-z = rng.normal(size=(n,2))
-plan = ctx.preview_plan(off)
-dz = ctx.to_device(z); ds = ctx.to_device(np.zeros((B,8))); dc = ctx.alloc(n*48); dzo = ctx.alloc(n*16)
-for i in range(3): plan.run(dz, ds, dc, dzo, True, mem=wg.WG_MEM_DEVICE)
-ctx.sync()
-PY
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_preview_v1.csv python /tmp/pv.py > gpurun_out/ncu.log 2>&1
-tail -8 gpurun_out/launches_preview_v1.csv
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r1_v1.json 2> gpurun_out/bench_r1_v1.err; tail -c 3000 gpurun_out/bench_r1_v1.json; tail -5 gpurun_out/bench_r1_v1.err
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1_v1.csv python bench.py --steps 2 --warmup 1 --cpu-seconds 0.5 > gpurun_out/ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:preview_ -s 6 -c 2 -o gpurun_out/prof_preview_v1 python bench.py --steps 2 --warmup 1 --cpu-seconds 0.5 > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out

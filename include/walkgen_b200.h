@@ -62,6 +62,14 @@ int wg_timer_stop_ms(wg_ctx *ctx, float *ms);       /* records, synchronises, re
 /* Number of kernels this library launched on this context since creation / last reset. */
 long long wg_launch_count(wg_ctx *ctx);
 void wg_launch_count_reset(wg_ctx *ctx);
+/* Per-kernel CUDA-event profiler on the context stream.  Between wg_prof_begin(capacity = max number of
+ * kernel launches to record) and wg_prof_end every kernel this library launches is bracketed by an event
+ * pair; wg_prof_get returns the launch count and the summed duration of one kernel id:
+ *   0 preview FIR, 1 preview recursion, 2 Herdt QP solve, 3 Herdt MPC step, 4 PLDP solve, 5 OptCholesky,
+ *   6 preview fused. */
+int wg_prof_begin(wg_ctx *ctx, int capacity);
+int wg_prof_end(wg_ctx *ctx);                        /* synchronises the stream and accumulates      */
+int wg_prof_get(wg_ctx *ctx, int kernel_id, long long *launches, double *total_ms);
 /* FP64 FMA peak micro-benchmark (register-resident DFMA chains on every SM): TFLOP/s. */
 int wg_measure_fp64_peak(wg_ctx *ctx, double *tflops);
 

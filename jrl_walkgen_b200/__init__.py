@@ -126,6 +126,20 @@ class Context:
     def reset_launches(self):
         self.lib.wg_launch_count_reset(self.h)
 
+    def prof_begin(self, capacity):
+        self._check(self.lib.wg_prof_begin(self.h, int(capacity)))
+
+    def prof_end(self):
+        """-> {kernel_id: (launches, total_ms)} for the kernels that ran since prof_begin."""
+        self._check(self.lib.wg_prof_end(self.h))
+        out = {}
+        for kid in range(8):
+            n = C.c_longlong(); ms = C.c_double()
+            self._check(self.lib.wg_prof_get(self.h, kid, C.byref(n), C.byref(ms)))
+            if n.value:
+                out[kid] = (n.value, ms.value)
+        return out
+
     def fp64_peak_tflops(self) -> float:
         v = C.c_double()
         self._check(self.lib.wg_measure_fp64_peak(self.h, C.byref(v)))

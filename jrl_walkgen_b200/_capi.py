@@ -74,6 +74,9 @@ SIGNATURES = {
     "wg_timer_stop_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "wg_launch_count": (C.c_longlong, [C.c_void_p]),
     "wg_launch_count_reset": (None, [C.c_void_p]),
+    "wg_prof_begin": (C.c_int, [C.c_void_p, C.c_int]),
+    "wg_prof_end": (C.c_int, [C.c_void_p]),
+    "wg_prof_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), c_double_p]),
     "wg_measure_fp64_peak": (C.c_int, [C.c_void_p, c_double_p]),
     "wg_preview_gains": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(PreviewGains)]),
     "wg_preview_set_gains": (C.c_int, [C.c_void_p, C.POINTER(PreviewGains)]),

@@ -427,13 +427,17 @@ static int preview_launch(wg_ctx *ctx, wg_preview_plan *pl, const double *d_zmp,
     attr_set = true;
   }
   if (smem > 64 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the FIR tile");
+  wg_prof_start(ctx, WG_K_PREVIEW_FIR);
   preview_fir_kernel<<<pl->n_tiles, FIR_THREADS, smem, ctx->stream>>>(
       pl->d_tiles, pl->d_offsets, reinterpret_cast<const double2 *>(d_zmp), pl->d_fir);
+  wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   const int threads = 64, blocks = (2 * pl->B + threads - 1) / threads;
+  wg_prof_start(ctx, WG_K_PREVIEW_RECUR);
   preview_recur_kernel<<<blocks, threads, 0, ctx->stream>>>(
       pl->B, pl->d_offsets, reinterpret_cast<const double2 *>(d_zmp), pl->d_fir, d_state, d_com, d_zmpout,
       simulation);
+  wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;
 }

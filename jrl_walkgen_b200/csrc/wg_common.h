@@ -4,13 +4,29 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "../../include/walkgen_b200.h"
 
 #define WG_VERSION ((0 << 16) | (1 << 8) | 0)
 
 struct wg_preview_consts;  // preview.cu
 
+// Kernel ids of the per-kernel CUDA-event profiler (wg_prof_*): bench.py reads the average launch
+// duration of each kernel over the timed region from these.
+enum { WG_K_PREVIEW_FIR = 0, WG_K_PREVIEW_RECUR = 1, WG_K_HERDT_QP = 2, WG_K_HERDT_MPC = 3, WG_K_PLDP = 4,
+       WG_K_OPTCHOL = 5, WG_K_PREVIEW_FUSED = 6, WG_K_COUNT = 8 };
+
+struct wg_prof_state {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  std::vector<int> kid;          // kernel id of pair i
+  size_t used = 0;               // pairs recorded since wg_prof_begin
+  long long launches[WG_K_COUNT] = {0};
+  double total_ms[WG_K_COUNT] = {0};
+};
+
 struct wg_ctx {
+  wg_prof_state prof;
   int device = -1;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
@@ -50,6 +66,22 @@ inline int wg_fail(wg_ctx *ctx, int code, const char *what, cudaError_t e = cuda
     cudaError_t e__ = cudaGetLastError();                                    \
     if (e__ != cudaSuccess) return wg_fail((ctx), WG_ERR_CUDA, "kernel launch", e__); \
   } while (0)
+
+// Bracket a kernel launch with profiler events (no-ops unless wg_prof_begin was called).
+inline void wg_prof_start(wg_ctx *ctx, int kid)
+{
+  wg_prof_state &p = ctx->prof;
+  if (!p.on || 2 * (p.used + 1) > p.ev.size()) return;
+  p.kid[p.used] = kid;
+  cudaEventRecord(p.ev[2 * p.used], ctx->stream);
+}
+inline void wg_prof_stop(wg_ctx *ctx)
+{
+  wg_prof_state &p = ctx->prof;
+  if (!p.on || 2 * (p.used + 1) > p.ev.size()) return;
+  cudaEventRecord(p.ev[2 * p.used + 1], ctx->stream);
+  p.used++;
+}
 
 struct wg_device_guard {
   int prev = -1;

@@ -42,6 +42,7 @@ int wg_ctx_destroy(wg_ctx *ctx)
   wg_herdt_release(ctx);
   wg_pldp_release(ctx);
   if (ctx->d_previewF) cudaFree(ctx->d_previewF);
+  for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -120,6 +121,45 @@ int wg_timer_stop_ms(wg_ctx *ctx, float *ms)
   WG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   WG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
   WG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return WG_OK;
+}
+
+int wg_prof_begin(wg_ctx *ctx, int capacity)
+{
+  if (!ctx || capacity < 0) return WG_ERR_INVALID;
+  wg_device_guard g(ctx->device);
+  wg_prof_state &p = ctx->prof;
+  while (p.ev.size() < 2 * (size_t)capacity) {
+    cudaEvent_t e;
+    WG_CUDA(ctx, cudaEventCreate(&e));
+    p.ev.push_back(e);
+  }
+  p.kid.assign(p.ev.size() / 2, 0);
+  p.used = 0;
+  for (int k = 0; k < WG_K_COUNT; ++k) { p.launches[k] = 0; p.total_ms[k] = 0.0; }
+  p.on = true;
+  return WG_OK;
+}
+int wg_prof_end(wg_ctx *ctx)
+{
+  if (!ctx) return WG_ERR_INVALID;
+  wg_device_guard g(ctx->device);
+  wg_prof_state &p = ctx->prof;
+  p.on = false;
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < p.used; ++i) {
+    float ms = 0.f;
+    WG_CUDA(ctx, cudaEventElapsedTime(&ms, p.ev[2 * i], p.ev[2 * i + 1]));
+    p.launches[p.kid[i]]++;
+    p.total_ms[p.kid[i]] += ms;
+  }
+  return WG_OK;
+}
+int wg_prof_get(wg_ctx *ctx, int kernel_id, long long *launches, double *total_ms)
+{
+  if (!ctx || kernel_id < 0 || kernel_id >= WG_K_COUNT) return WG_ERR_INVALID;
+  if (launches) *launches = ctx->prof.launches[kernel_id];
+  if (total_ms) *total_ms = ctx->prof.total_ms[kernel_id];
   return WG_OK;
 }
 

@@ -19,6 +19,8 @@
  */
 #include <cmath>
 #include <cstring>
+#include <deque>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -287,6 +289,71 @@ int oracle_preview_step_1d_wrap(const double *A, const double *B, const double *
   *zmp_out = z;
   if (simulation) *s += (zmp[lindex] - z);
   return 0;
+}
+
+
+/* CPU-baseline driver (bench.py cpu_baseline / --impl reference): the reference's data layout and call
+ * pattern - a std::deque of 48-byte ZMPPosition records (pgtypes.hh:90-104) read through operator[] at
+ * lindex + i (PreviewControl.cpp:346-356) and popped once per tick by the caller
+ * (ZMPPreviewControlWithMultiBodyZMP.cpp:437-438) - one walking problem per thread, `nthreads` host threads.
+ * Results are identical to oracle_preview_run_batch (same statement order). */
+struct RefZmpPosition { double px, py, pz, theta, time; int stepType; };
+
+static void preview_walk_deque(const double *A, const double *B, const double *C, const double *Kx, double Ks,
+                               const double *F, int NL, const double *zmpref_xy, int L, double *state,
+                               double *com_out, double *zmp_out, int simulation)
+{
+  std::deque<RefZmpPosition> fifo;
+  for (int k = 0; k < L; ++k) {
+    RefZmpPosition z = {zmpref_xy[2 * (size_t)k], zmpref_xy[2 * (size_t)k + 1], 0.0, 0.0, 0.005 * k, 0};
+    fifo.push_back(z);
+  }
+  double *x = state, *y = state + 3, *sx = state + 6, *sy = state + 7;
+  int k = 0;
+  while ((int)fifo.size() >= NL) {
+    const unsigned lindex = 0;
+    double rx = 0.0, ry = 0.0;
+    for (int i = 0; i < 3; ++i) { rx += Kx[i] * x[i]; ry += Kx[i] * y[i]; }
+    double ux = -rx + Ks * (*sx), uy = -ry + Ks * (*sy);
+    for (int i = 0; i < NL; ++i) ux += F[i] * fifo[lindex + i].px;
+    for (int i = 0; i < NL; ++i) uy += F[i] * fifo[lindex + i].py;
+    double xn[3], yn[3];
+    for (int i = 0; i < 3; ++i) {
+      double t = 0.0, v = 0.0;
+      for (int j = 0; j < 3; ++j) { t += A[i * 3 + j] * x[j]; v += A[i * 3 + j] * y[j]; }
+      xn[i] = t + ux * B[i]; yn[i] = v + uy * B[i];
+    }
+    for (int i = 0; i < 3; ++i) { x[i] = xn[i]; y[i] = yn[i]; }
+    double zx = 0.0, zy = 0.0;
+    for (int i = 0; i < 3; ++i) { zx += C[i] * x[i]; zy += C[i] * y[i]; }
+    if (simulation) { *sx += fifo[lindex].px - zx; *sy += fifo[lindex].py - zy; }
+    if (com_out) { double *c = com_out + 6 * (size_t)k; c[0] = x[0]; c[1] = x[1]; c[2] = x[2]; c[3] = y[0]; c[4] = y[1]; c[5] = y[2]; }
+    if (zmp_out) { zmp_out[2 * (size_t)k] = zx; zmp_out[2 * (size_t)k + 1] = zy; }
+    fifo.pop_front();
+    ++k;
+  }
+}
+
+long oracle_preview_run_batch_mt(const double *A, const double *B, const double *C, const double *Kx,
+                                 double Ks, const double *F, int NL, int nb, const long long *offsets,
+                                 const double *zmpref_xy, double *state, double *com_out, double *zmp_out,
+                                 int simulation, int nthreads)
+{
+  if (nthreads < 1) nthreads = 1;
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([=]() {
+      for (int b = t; b < nb; b += nthreads) {
+        long long o = offsets[b];
+        int L = (int)(offsets[b + 1] - o);
+        preview_walk_deque(A, B, C, Kx, Ks, F, NL, zmpref_xy + 2 * o, L, state + 8 * (size_t)b,
+                           com_out ? com_out + 6 * o : nullptr, zmp_out ? zmp_out + 2 * o : nullptr, simulation);
+      }
+    });
+  for (auto &t : th) t.join();
+  long total = 0;
+  for (int b = 0; b < nb; ++b) { long long L = offsets[b + 1] - offsets[b]; if (L >= NL) total += (long)(L - NL + 1); }
+  return total;
 }
 
 } /* extern "C" */

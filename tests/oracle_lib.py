@@ -27,6 +27,8 @@ def oracle():
         _ora.oracle_preview_run.argtypes = [D, D, D, D, C.c_double, D, C.c_int, D, C.c_int, D, D, D, C.c_int]
         _ora.oracle_preview_run_batch.restype = C.c_long
         _ora.oracle_preview_run_batch.argtypes = [D, D, D, D, C.c_double, D, C.c_int, C.c_int, I64, D, D, D, D, C.c_int]
+        _ora.oracle_preview_run_batch_mt.restype = C.c_long
+        _ora.oracle_preview_run_batch_mt.argtypes = _ora.oracle_preview_run_batch.argtypes + [C.c_int]
         _ora.oracle_preview_step.restype = C.c_int
         _ora.oracle_preview_step.argtypes = [D, D, D, D, C.c_double, D, C.c_int, D, D, D, D, D, C.c_int, D, D, C.c_int]
         _ora.oracle_preview_step_1d_wrap.restype = C.c_int
@@ -57,13 +59,20 @@ class OracleGains:
         self.Ks = ks.value
 
 
-def oracle_preview_batch(g, offsets, zmpref_xy, state, simulation=True, want_out=True):
-    """Run the oracle over a ragged batch; returns (com, zmp) with the product's row indexing."""
+def oracle_preview_batch(g, offsets, zmpref_xy, state, simulation=True, want_out=True, threads=0, out=None):
+    """Run the oracle over a ragged batch; returns (com, zmp) with the product's row indexing.
+    threads > 0 selects the reference-layout (deque of ZMPPosition) multi-threaded CPU-baseline driver."""
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n = int(offsets[-1])
-    com = np.zeros((n, 6)) if want_out else None
-    zmp = np.zeros((n, 2)) if want_out else None
-    steps = oracle().oracle_preview_run_batch(dptr(g.A), dptr(g.B), dptr(g.C), dptr(g.Kx), g.Ks, dptr(g.F), g.NL,
-                                              len(offsets) - 1, offsets.ctypes.data_as(I64), dptr(zmpref_xy),
-                                              dptr(state), dptr(com), dptr(zmp), int(simulation))
+    if out is not None:
+        com, zmp = out
+    else:
+        com = np.zeros((n, 6)) if want_out else None
+        zmp = np.zeros((n, 2)) if want_out else None
+    args = [dptr(g.A), dptr(g.B), dptr(g.C), dptr(g.Kx), g.Ks, dptr(g.F), g.NL, len(offsets) - 1,
+            offsets.ctypes.data_as(I64), dptr(zmpref_xy), dptr(state), dptr(com), dptr(zmp), int(simulation)]
+    if threads > 0:
+        steps = oracle().oracle_preview_run_batch_mt(*args, int(threads))
+    else:
+        steps = oracle().oracle_preview_run_batch(*args)
     return com, zmp, steps
