@@ -13,9 +13,12 @@ import numpy as np
 
 from . import _capi
 from ._capi import (MODE_WITH_INITIALPOS, MODE_WITHOUT_INITIALPOS, WG_MEM_DEVICE, WG_MEM_HOST,
-                    PreviewGains, WalkgenError)
+                    HerdtParams, PreviewGains, WalkgenError)
 
-__all__ = ["Context", "PreviewPlan", "preview_gains", "WalkgenError", "device_count",
+QP_INPUT_DTYPE, QP_OUTPUT_DTYPE = _capi.herdt_dtypes()
+
+__all__ = ["Context", "PreviewPlan", "preview_gains", "herdt_default_params", "HerdtParams", "QP_INPUT_DTYPE",
+           "QP_OUTPUT_DTYPE", "WalkgenError", "device_count",
            "MODE_WITH_INITIALPOS", "MODE_WITHOUT_INITIALPOS", "WG_MEM_HOST", "WG_MEM_DEVICE"]
 
 
@@ -30,6 +33,14 @@ def _ptr(a):
         return C.c_void_p(a.ptr)
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(C.c_void_p)
+
+
+def herdt_default_params(sole_length=0.25, sole_width=0.14) -> HerdtParams:
+    """Constants of ZMPVelocityReferencedQP's ctor (ZMPVelocityReferencedQP.cpp:61-118) for a given sole size
+    (the reference reads it from the robot model; 0.25 x 0.14 m is the sample robot's, fitted from the datref)."""
+    p = HerdtParams()
+    _capi.load().wg_herdt_default_params(sole_length, sole_width, C.byref(p))
+    return p
 
 
 def preview_gains(T=0.005, preview_time=1.6, zc=0.814, mode=MODE_WITHOUT_INITIALPOS) -> PreviewGains:
@@ -165,6 +176,24 @@ class Context:
                                                C.byref(zy), int(simulation))
         self._check(rc)
         return x, y, csx.value, csy.value, zx.value, zy.value
+
+
+    # ---- Herdt2010 velocity-referenced QP ----------------------------------------------------
+    def herdt_set_params(self, params: HerdtParams = None):
+        self.herdt_params = params or herdt_default_params()
+        self._check(self.lib.wg_herdt_set_params(self.h, C.byref(self.herdt_params)))
+
+    def herdt_qp_solve(self, inputs, outputs=None, mem=WG_MEM_HOST, count=None):
+        """wg_herdt_qp_solve_batch.  Host mode: numpy arrays of QP_INPUT_DTYPE -> QP_OUTPUT_DTYPE."""
+        if mem == WG_MEM_HOST:
+            inputs = np.ascontiguousarray(inputs, dtype=QP_INPUT_DTYPE)
+            B = len(inputs)
+            if outputs is None:
+                outputs = np.zeros(B, dtype=QP_OUTPUT_DTYPE)
+            self._check(self.lib.wg_herdt_qp_solve_batch(self.h, mem, B, inputs.ctypes.data, outputs.ctypes.data))
+            return outputs
+        self._check(self.lib.wg_herdt_qp_solve_batch(self.h, mem, int(count), _ptr(inputs), _ptr(outputs)))
+        return outputs
 
 
 class PreviewPlan:

@@ -54,6 +54,40 @@ class PreviewGains(C.Structure):
     ]
 
 
+class HerdtParams(C.Structure):
+    """Mirror of wg_herdt_params."""
+    _fields_ = [("T", C.c_double), ("com_height", C.c_double), ("w_jerk", C.c_double), ("w_vel", C.c_double),
+                ("w_cop", C.c_double), ("cop_half_x", C.c_double), ("cop_half_y", C.c_double),
+                ("ds_feet_distance", C.c_double), ("foot_hull_x", C.c_double * 5), ("foot_hull_y", C.c_double * 5),
+                ("lipm_T", C.c_double)]
+
+
+HERDT_N = 16
+HERDT_MAX_VARS = 36
+HERDT_MAX_ROWS = 75
+
+
+def _np():
+    import numpy as np
+    return np
+
+
+def herdt_dtypes():
+    """numpy mirrors of wg_herdt_qp_input (784 B) and wg_herdt_qp_output (960 B)."""
+    np = _np()
+    N = HERDT_N
+    qin = np.dtype([
+        ("com_x", "f8", 3), ("com_y", "f8", 3), ("ref_x", "f8", N), ("ref_y", "f8", N),
+        ("sup_x", "f8", N + 1), ("sup_y", "f8", N + 1), ("sup_yaw", "f8", N + 1),
+        ("sup_foot", "i1", N + 1), ("sup_phase", "i1", N + 1), ("sup_step", "i1", N + 1),
+        ("sup_changed", "i1", N + 1), ("pad_", "i1", 4)])
+    qout = np.dtype([
+        ("x", "f8", HERDT_MAX_VARS), ("lagr", "f8", HERDT_MAX_ROWS + 1), ("com_next_x", "f8", 3),
+        ("com_next_y", "f8", 3), ("n_vars", "i4"), ("n_rows", "i4"), ("fail", "i4"), ("iterations", "i4")])
+    assert qin.itemsize == 784 and qout.itemsize == 960
+    return qin, qout
+
+
 # name -> (restype, argtypes); also the list checked against include/walkgen_b200.h by the tests
 SIGNATURES = {
     "wg_version": (C.c_int, []),
@@ -88,6 +122,9 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_int]),
     "wg_preview_one_iteration": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                            c_double_p, C.c_int, c_double_p, c_double_p, C.c_int]),
+    "wg_herdt_default_params": (None, [C.c_double, C.c_double, C.POINTER(HerdtParams)]),
+    "wg_herdt_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtParams)]),
+    "wg_herdt_qp_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

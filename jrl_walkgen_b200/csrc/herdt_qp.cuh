@@ -1,0 +1,476 @@
+// herdt_qp.cuh - warp-per-instance Herdt2010 QP assembly + dual active-set solve (device code).
+//
+// Replaces, for one instance per warp, GeneratorVelRef::update_problem / build_constraints
+// (src/ZMPRefTrajectoryGeneration/generator-vel-ref.cpp:285-674), RelativeFeetInequalities
+// (src/Mathematics/relative-feet-inequalities.cpp:89-319), QPProblem::solve (qp-problem.cpp:246-407) and
+// ql0001_/ql0002_ (src/Mathematics/qld.cpp:378-2090).
+//
+// B200-first formulation (DESIGN.md "Herdt QP kernel").  The reference assembles a dense 36x36 Hessian and a
+// 75x36 constraint matrix and hands them to QLD, which factorises the Hessian for every solve.  Here nothing
+// dense is ever assembled.  The unknowns are x = [jx(16) jy(16) fx(ns) fy(ns)] and
+//   * the Hessian is block-diagonal over the two axes with the SAME block  Qx = [[Qc, Cx],[Cx', E]],
+//     Qc = a I + b Uv'Uv + c Uz'Uz constant, Cx = -c Uz'V, E = c V'V diagonal (V = step-selection matrix);
+//   * every inequality row has the form  a_k * PX[kappa] + b_k * PY[kappa] + d_k >= 0  where the "points"
+//     P[kappa] (16 CoP-minus-support offsets + ns relative foot placements) are affine in x with the same
+//     coefficient vector theta_kappa for both axes.
+// Hence the Gram matrix of the rows in the metric of H^-1 - the only thing a dual active-set method needs - is
+//   N_k' H^-1 N_l = (a_k a_l + b_k b_l) * Gamma(kappa_k, kappa_l),   Gamma = theta' Qx^-1 theta   (18 x 18),
+// with Gamma = G + t' S^-1 t, G = Uz Qc^-1 Uz' a constant 16x16 matrix and S the ns x ns Schur complement of
+// the foot block.  The Goldfarb-Idnani iteration then runs entirely in "point space": the primal iterate is
+// the 2 x 18 point coordinates, the dual iterate the multipliers of the <= 32 active rows, and the only
+// factorisation is the inverse Cholesky factor T of the active Gram matrix, grown by one row per added
+// constraint and shrunk by Givens rotations per dropped one (the batched analogue of OptCholesky's
+// row-incremental update, src/Mathematics/OptCholesky.cpp:123-223).  Everything lives in shared memory.
+#pragma once
+#include "wg_common.h"
+
+namespace herdt {
+
+constexpr int N = WG_HERDT_N;        // 16
+constexpr int NPTS = N + 2;          // 18 points
+constexpr int MAXM = 4 * N + 10;     // 74 real rows
+constexpr int QMAX = 32;             // active-set capacity (one lane per active row)
+constexpr int TRI = QMAX * (QMAX + 1) / 2;
+
+// Constants of one (T, h, weights) parameter set, computed once on the host in extended precision.
+struct Consts {
+  double K1[N][N];    // Qc^-1 Uz'
+  double G[N][N];     // Uz Qc^-1 Uz'
+  double K3[N][N];    // Qc^-1 Uv'
+  double K4[N][3];    // K3 Sv
+  double Sz[N][3];    // CoP state matrix (rigid-body-system.cpp:425-431)
+  double uz[N];       // Uz is Toeplitz: Uz(i,j) = uz[i-j], j <= i
+  double uz2[N];      // squared Euclidean norm of row i of Uz
+  double Qc[N][N];    // kept for residual checks
+  wg_herdt_params P;
+};
+
+// Per-warp shared-memory workspace.
+struct Work {
+  wg_herdt_qp_input in;            // 784 B
+  double PX[NPTS + 2], PY[NPTS + 2];
+  double Gam[NPTS][NPTS];
+  double a[MAXM + 2], b[MAXM + 2], d[MAXM + 2], inrm[MAXM + 2];
+  double T[TRI];
+  double u[QMAX], gv[QMAX], w[QMAX], ca[QMAX + 1], cb[QMAX + 1];
+  double theta[NPTS][2], sigma[NPTS][2];
+  double g[2][N], j0[2][N], Z[2][N], jr[2][N];
+  double f0[2][2], ff[2][2];
+  double wpt[2][NPTS + 2];
+  int W[QMAX], cpt[QMAX + 1];
+};
+
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+__device__ __forceinline__ int row_point(int k) { return k < 4 * N ? (k >> 2) : N + (k - 4 * N) / 5; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double half_sum(double v)  // sum over the 16 lanes of a half warp
+{
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// argmin with deterministic tie-break (lower index wins)
+__device__ __forceinline__ void warp_argmin(double &v, int &idx)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+// RelativeFeetInequalities::set_vertices + convex_hull_t::rotate + compute_linear_system for one hull
+// (relative-feet-inequalities.cpp:186-234, 265-319; privatepgtypes.cpp:152-180).
+__device__ inline void hull_rows(const wg_herdt_params &P, int foot, int phase, double yaw, bool cop, int sign_foot,
+                                 double *A, double *B, double *D)
+{
+  double X[5], Y[5];
+  int nv;
+  if (cop) {
+    nv = 4;
+    const double hw = P.cop_half_x, hh = P.cop_half_y, hhds = P.cop_half_y + P.ds_feet_distance * 0.5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double lx = (j < 2) ? 1.0 : -1.0;
+      const double lyL = (j == 0 || j == 3) ? 1.0 : -1.0;
+      X[j] = lx * hw;
+      if (foot == WG_LEFT) Y[j] = (phase == WG_DS) ? lyL * hhds - P.ds_feet_distance * 0.5 : lyL * hh;
+      else Y[j] = (phase == WG_DS) ? -lyL * hhds + P.ds_feet_distance * 0.5 : -lyL * hh;
+    }
+    X[4] = Y[4] = 0.0;
+  } else {
+    nv = 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { X[j] = P.foot_hull_x[j]; Y[j] = (foot == WG_LEFT) ? P.foot_hull_y[j] : -P.foot_hull_y[j]; }
+  }
+  double sn, cs;
+  sincos(yaw, &sn, &cs);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const double xo = X[j], yo = Y[j];
+    X[j] = xo * cs - yo * sn;
+    Y[j] = xo * sn + yo * cs;
+  }
+  const double sg = (sign_foot == WG_LEFT) ? 1.0 : -1.0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    if (i < nv) {
+      const int k = (i + 1 == nv) ? 0 : i + 1;
+      const double dx = Y[i] - Y[k], dy = X[k] - X[i], dc = dx * X[i] + dy * Y[i];
+      A[i] = sg * dx; B[i] = sg * dy; D[i] = sg * dc;
+    }
+  }
+}
+
+// Points from a primal iterate (jerks in jr[axis][16], foot placements in ff[axis][2]):
+//   P[i]   = -(Uz j)_i + (V f)_i - (Sz c)_i + Vc_i      (generator-vel-ref.cpp:394-447, rows of the CoP constraints)
+//   P[N+s] = -(Vf f)_s + Vcf_s                            (generator-vel-ref.cpp:450-474)
+__device__ inline void points_from_primal(Work &s, const Consts &C, const double (*jr)[N], const double (*ff)[2],
+                                          int ns, const double Vf[2][2], const double Vcf[2][2], double *outX,
+                                          double *outY, int lane)
+{
+  const int axis = lane >> 4, i = lane & 15;
+  double acc = 0.0;
+  for (int k = 0; k <= i; ++k) acc = fma(C.uz[i - k], jr[axis][k], acc);
+  const int sn = s.in.sup_step[i + 1];
+  const double sel = (sn > 0) ? ff[axis][sn - 1] : (axis ? s.in.sup_y[i + 1] : s.in.sup_x[i + 1]);
+  const double p = -acc + sel - s.Z[axis][i];
+  (axis ? outY : outX)[i] = p;
+  if (i < ns) {
+    double v = Vcf[axis][i];
+    for (int r = 0; r < ns; ++r) v -= Vf[i][r] * ff[axis][r];
+    (axis ? outY : outX)[N + i] = v;
+  }
+  __syncwarp();
+}
+
+struct Result {
+  int n_vars, n_rows, fail, iterations;
+};
+
+// Build and solve the QP of the instance in s.in.  On return s.jr / s.ff hold the solution, s.u / s.W / q the
+// multipliers of the active rows.  All 32 lanes of the warp must call.
+__device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_out)
+{
+  const wg_herdt_params &P = C.P;
+  const int axis = lane >> 4, i = lane & 15;
+  const double wv = P.w_vel, wc = P.w_cop;
+  const int ns = s.in.sup_step[N];
+  Result res;
+  res.n_vars = 2 * N + 2 * ns; res.n_rows = 1 + 4 * N + 5 * ns; res.fail = 0; res.iterations = 0;
+  q_out = 0;
+  if (ns < 0 || ns > WG_HERDT_MAX_STEPS) { res.fail = 100; return res; }
+  const int m = 4 * N + 5 * ns, npts = N + ns;
+  const int sn_i = s.in.sup_step[i + 1];
+  const double *com = axis ? s.in.com_y : s.in.com_x;
+  const double *ref = axis ? s.in.ref_y : s.in.ref_x;
+
+  // ---- selection matrices of the previewed feet (generator-vel-ref.cpp:138-208), redundantly on every lane
+  double Vf[2][2] = {{0, 0}, {0, 0}}, Vcf[2][2] = {{0, 0}, {0, 0}};   // Vcf[axis][s]
+  for (int ii = 0; ii < N; ++ii) {
+    const int k = ii + 1, sn = s.in.sup_step[k];
+    if (sn == 1 && s.in.sup_changed[k] && s.in.sup_phase[k] == WG_SS) {
+      Vcf[0][0] = s.in.sup_x[k - 1]; Vcf[1][0] = s.in.sup_y[k - 1]; Vf[0][0] = 1.0;
+    } else if (sn == 2) {
+      Vf[1][0] = -1.0; Vf[1][1] = 1.0;
+    }
+  }
+
+  // ---- unconstrained optimum: g = Qc^-1 pj,  pj = wv Uv'(Sv c - ref)
+  {
+    double acc = C.K4[i][0] * com[0] + C.K4[i][1] * com[1] + C.K4[i][2] * com[2];
+    for (int k = 0; k < N; ++k) acc = fma(-C.K3[i][k], ref[k], acc);
+    s.g[axis][i] = wv * acc;
+    s.Z[axis][i] = C.Sz[i][0] * com[0] + C.Sz[i][1] * com[1] + C.Sz[i][2] * com[2];
+  }
+  __syncwarp();
+  double zh;
+  {
+    double h = 0.0;
+    for (int k = 0; k <= i; ++k) h = fma(C.uz[i - k], s.g[axis][k], h);
+    zh = s.Z[axis][i] - h;
+  }
+  // GV[i][s] = sum_{k in step s} G[i][k]
+  double GV0 = 0.0, GV1 = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const int snk = s.in.sup_step[k + 1];
+    const double gk = C.G[i][k];
+    if (snk == 1) GV0 += gk;
+    else if (snk == 2) GV1 += gk;
+  }
+  const double rhs0 = -wc * half_sum(sn_i == 1 ? zh : 0.0);
+  const double rhs1 = -wc * half_sum(sn_i == 2 ? zh : 0.0);
+  const double cnt0 = half_sum(sn_i == 1 ? 1.0 : 0.0), cnt1 = half_sum(sn_i == 2 ? 1.0 : 0.0);
+  const double V00 = half_sum(sn_i == 1 ? GV0 : 0.0), V01 = half_sum(sn_i == 1 ? GV1 : 0.0);
+  const double V11 = half_sum(sn_i == 2 ? GV1 : 0.0);
+  double Si00 = 0.0, Si01 = 0.0, Si11 = 0.0;
+  if (ns == 1) {
+    Si00 = 1.0 / (wc * cnt0 - wc * wc * V00);
+  } else if (ns == 2) {
+    const double S00 = wc * cnt0 - wc * wc * V00, S01 = -wc * wc * V01, S11 = wc * cnt1 - wc * wc * V11;
+    const double det = S00 * S11 - S01 * S01;
+    Si00 = S11 / det; Si01 = -S01 / det; Si11 = S00 / det;
+  }
+  const double tau0 = Si00 * rhs0 + Si01 * rhs1, tau1 = Si01 * rhs0 + Si11 * rhs1;
+  if (i < 2) s.f0[axis][i] = (i < ns) ? -(i == 0 ? tau0 : tau1) : 0.0;
+  {
+    const double vt = (sn_i == 1) ? tau0 : (sn_i == 2 ? tau1 : 0.0);
+    double acc = 0.0;
+    for (int k = 0; k < N; ++k) acc = fma(C.K1[i][k], __shfl_sync(0xffffffffu, vt, (axis << 4) + k), acc);
+    s.j0[axis][i] = -s.g[axis][i] - wc * acc;
+  }
+  // theta / sigma
+  if (axis == 0) {
+    const double t0 = (sn_i == 1 ? 1.0 : 0.0) - wc * GV0, t1 = (sn_i == 2 ? 1.0 : 0.0) - wc * GV1;
+    s.theta[i][0] = (ns > 0) ? t0 : 0.0; s.theta[i][1] = (ns > 1) ? t1 : 0.0;
+  } else if (i < 2) {
+    s.theta[N + i][0] = -Vf[i][0]; s.theta[N + i][1] = -Vf[i][1];
+  }
+  __syncwarp();
+  if (lane < NPTS) {
+    const double t0 = s.theta[lane][0], t1 = s.theta[lane][1];
+    s.sigma[lane][0] = Si00 * t0 + Si01 * t1;
+    s.sigma[lane][1] = Si01 * t0 + Si11 * t1;
+  }
+  __syncwarp();
+  for (int e = lane; e < NPTS * NPTS; e += 32) {
+    const int k = e / NPTS, l = e - k * NPTS;
+    double v = s.sigma[k][0] * s.theta[l][0] + s.sigma[k][1] * s.theta[l][1];
+    if (k < N && l < N) v += C.G[k][l];
+    s.Gam[k][l] = v;
+  }
+  points_from_primal(s, C, s.j0, s.f0, ns, Vf, Vcf, s.PX, s.PY, lane);
+
+  // ---- inequality rows (a, b, d) and their inverse Euclidean norms
+  if (lane < N) {
+    const int k = lane + 1;
+    int src = 0;
+    for (int kk = 1; kk <= k; ++kk)
+      if (s.in.sup_changed[kk]) src = kk;
+    double A[5], B[5], D[5];
+    hull_rows(P, s.in.sup_foot[src], s.in.sup_phase[src], s.in.sup_yaw[src], true, s.in.sup_foot[k], A, B, D);
+    const double th2 = C.uz2[lane] + (sn_i > 0 ? 1.0 : 0.0);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = 4 * lane + e;
+      s.a[row] = A[e]; s.b[row] = B[e]; s.d[row] = D[e];
+      const double n2 = (A[e] * A[e] + B[e] * B[e]) * th2;
+      s.inrm[row] = n2 > 0.0 ? rsqrt(n2) : 0.0;
+    }
+  } else if (lane < N + ns) {
+    const int st = lane - N;
+    int kf = -1;
+    for (int kk = 1; kk <= N; ++kk)
+      if (s.in.sup_changed[kk] && s.in.sup_step[kk] == st + 1 && s.in.sup_phase[kk] != WG_DS) kf = kk;
+    double A[5] = {0, 0, 0, 0, 0}, B[5] = {0, 0, 0, 0, 0}, D[5] = {0, 0, 0, 0, 0};
+    if (kf > 0)
+      hull_rows(P, s.in.sup_foot[kf - 1], s.in.sup_phase[kf - 1], s.in.sup_yaw[kf - 1], false, s.in.sup_foot[kf], A, B, D);
+    const double th2 = Vf[st][0] * Vf[st][0] + Vf[st][1] * Vf[st][1];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const int row = 4 * N + 5 * st + e;
+      s.a[row] = A[e]; s.b[row] = B[e]; s.d[row] = D[e];
+      const double n2 = (A[e] * A[e] + B[e] * B[e]) * th2;
+      s.inrm[row] = n2 > 0.0 ? rsqrt(n2) : 0.0;
+    }
+  }
+  __syncwarp();
+
+  // ---- dual active-set iterations
+  const double tol = 1e-12;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  int q = 0;
+  unsigned actbits = 0;    // bit t: row lane + 32 t is active
+  int refinements = 0;
+  const int maxit = 40 * (m + 2 * N + 4);
+  bool done = false;
+  while (!done) {
+    // most violated row, normalised by its Euclidean norm (the pivoting rule of qld.cpp:1255-1331)
+    double best = INF;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int k = lane + 32 * t;
+      if (k < m && !((actbits >> t) & 1u)) {
+        const int kp = row_point(k);
+        const double sv = (s.a[k] * s.PX[kp] + s.b[k] * s.PY[kp] + s.d[k]) * s.inrm[k];
+        if (sv < best) { best = sv; bi = k; }
+      }
+    }
+    warp_argmin(best, bi);
+    if (!(best < -tol)) {
+      // ---- converged on the incremental points: recover the primal solution from the multipliers, then
+      // refine the multipliers so that the active rows hold on points recomputed from that solution
+      // (x = x0 + H^-1 N u goes through the precomputed inverse; one or two Newton steps on the dual,
+      // du = -(N'H^-1 N)^-1 s_active = -T'T s_active, remove its rounding error)
+      for (int pass = 0;; ++pass) {
+        if (lane < NPTS) {
+          double wx = 0.0, wy = 0.0;
+          for (int j = 0; j < q; ++j)
+            if (s.cpt[j] == lane) { const int k = s.W[j]; wx = fma(s.u[j], s.a[k], wx); wy = fma(s.u[j], s.b[k], wy); }
+          s.wpt[0][lane] = wx; s.wpt[1][lane] = wy;
+        }
+        __syncwarp();
+        double sg0 = 0.0, sg1 = 0.0;
+        for (int k = 0; k < npts; ++k) {
+          const double wk = s.wpt[axis][k];
+          sg0 = fma(s.sigma[k][0], wk, sg0); sg1 = fma(s.sigma[k][1], wk, sg1);
+        }
+        {
+          double acc = 0.0;
+          for (int k = 0; k < N; ++k) {
+            const int snk = s.in.sup_step[k + 1];
+            const double corr = (snk == 1) ? sg0 : (snk == 2 ? sg1 : 0.0);
+            acc = fma(C.K1[i][k], s.wpt[axis][k] - wc * corr, acc);
+          }
+          s.jr[axis][i] = s.j0[axis][i] - acc;
+          if (i < 2) s.ff[axis][i] = (i < ns) ? s.f0[axis][i] + (i == 0 ? sg0 : sg1) : 0.0;
+        }
+        __syncwarp();
+        points_from_primal(s, C, s.jr, s.ff, ns, Vf, Vcf, s.PX, s.PY, lane);
+        double sj = 0.0, vj = 0.0;
+        if (lane < q) {
+          const int k = s.W[lane], kp = s.cpt[lane];
+          sj = s.a[k] * s.PX[kp] + s.b[k] * s.PY[kp] + s.d[k];
+          vj = fabs(sj) * s.inrm[k];
+        }
+        double vmax = vj;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (!(vmax > 1e-14) || pass >= 3) break;
+        s.gv[lane] = sj;
+        __syncwarp();
+        double wi_ = 0.0;
+        if (lane < q) {
+          const double *Tr = s.T + tri(lane);
+          for (int j = 0; j <= lane; ++j) wi_ = fma(Tr[j], s.gv[j], wi_);
+        }
+        s.w[lane] = wi_;
+        __syncwarp();
+        if (lane < q) {
+          double rj = 0.0;
+          for (int r = lane; r < q; ++r) rj = fma(s.T[tri(r) + lane], s.w[r], rj);
+          s.u[lane] -= rj;
+        }
+        __syncwarp();
+      }
+      // re-evaluate the inactive rows on those points
+      double worst = INF; int wi = 0x7fffffff;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int k = lane + 32 * t;
+        if (k < m && !((actbits >> t) & 1u)) {
+          const int kp = row_point(k);
+          const double sv = (s.a[k] * s.PX[kp] + s.b[k] * s.PY[kp] + s.d[k]) * s.inrm[k];
+          if (sv < worst) { worst = sv; wi = k; }
+        }
+      }
+      warp_argmin(worst, wi);
+      if (!(worst < -tol) || refinements >= 3) { done = true; break; }
+      ++refinements;
+      best = worst; bi = wi;
+    }
+    const int p = bi;
+    const int pp = row_point(p);
+    const double ap = s.a[p], bp = s.b[p];
+    const double Mpp = (ap * ap + bp * bp) * s.Gam[pp][pp];
+    double up = 0.0;
+    while (true) {
+      if (++res.iterations > maxit) { res.fail = 1; done = true; break; }   // QLD ifail 1: too many iterations
+      if (q >= QMAX) { res.fail = 3; done = true; break; }                  // active-set capacity exhausted
+      // gv_j = N_Wj' H^-1 N_p
+      double gvj = 0.0;
+      if (lane < q) { const int k = s.W[lane]; gvj = (s.a[k] * ap + s.b[k] * bp) * s.Gam[s.cpt[lane]][pp]; }
+      s.gv[lane] = gvj;
+      __syncwarp();
+      double wi_ = 0.0;
+      if (lane < q) {
+        const double *Tr = s.T + tri(lane);
+        for (int j = 0; j <= lane; ++j) wi_ = fma(Tr[j], s.gv[j], wi_);
+      }
+      s.w[lane] = wi_;
+      __syncwarp();
+      double rj = 0.0;
+      if (lane < q)
+        for (int r = lane; r < q; ++r) rj = fma(s.T[tri(r) + lane], s.w[r], rj);
+      const double delta = Mpp - warp_sum(wi_ * wi_);
+      // step lengths
+      double t1 = INF; int l = 0x7fffffff;
+      if (lane < q && rj > 0.0) { t1 = s.u[lane] / rj; l = lane; }
+      warp_argmin(t1, l);
+      const double sp = ap * s.PX[pp] + bp * s.PY[pp] + s.d[p];
+      const double t2 = (delta > 1e-13 * Mpp) ? -sp / delta : INF;
+      const double tt = fmin(t1, t2);
+      if (!(tt < INF)) { res.fail = 2; done = true; break; }   // infeasible (QLD ifail 2 family)
+      // direction in point space and step
+      if (lane < q) { const int k = s.W[lane]; s.ca[lane] = -rj * s.a[k]; s.cb[lane] = -rj * s.b[k]; }
+      if (lane == q) { s.ca[q] = ap; s.cb[q] = bp; s.cpt[q] = pp; }
+      __syncwarp();
+      if (lane < npts) {
+        double dx = 0.0, dy = 0.0;
+        for (int j = 0; j <= q; ++j) {
+          const double gm = s.Gam[lane][s.cpt[j]];
+          dx = fma(gm, s.ca[j], dx); dy = fma(gm, s.cb[j], dy);
+        }
+        s.PX[lane] = fma(tt, dx, s.PX[lane]);
+        s.PY[lane] = fma(tt, dy, s.PY[lane]);
+      }
+      if (lane < q) s.u[lane] = fma(-tt, rj, s.u[lane]);
+      up += tt;
+      __syncwarp();
+      if (t2 <= t1) {
+        // full step: row p becomes active; append a row to T (inverse Cholesky factor of the active Gram matrix)
+        const double dd = sqrt(delta);
+        if (lane < q) s.T[tri(q) + lane] = -rj / dd;
+        if (lane == q) { s.T[tri(q) + q] = 1.0 / dd; s.W[q] = p; s.u[q] = up; }
+        if ((p & 31) == lane) actbits |= 1u << (p >> 5);
+        ++q;
+        __syncwarp();
+        break;
+      }
+      // partial step: multiplier l reached zero -> drop row l.  Rotate rows (l, r), r > l, so that column l
+      // vanishes below row l, then delete row and column l.
+      {
+        const int kl = s.W[l];
+        if ((kl & 31) == lane) actbits &= ~(1u << (kl >> 5));
+        double rowl = (lane <= l) ? s.T[tri(l) + lane] : 0.0;
+        __syncwarp();
+        for (int r = l + 1; r < q; ++r) {
+          const double x2 = (lane <= r) ? s.T[tri(r) + lane] : 0.0;
+          const double p1 = __shfl_sync(0xffffffffu, rowl, l), p2 = __shfl_sync(0xffffffffu, x2, l);
+          const double hyp = sqrt(p1 * p1 + p2 * p2);
+          const double c_ = p1 / hyp, s_ = p2 / hyp;
+          const double nl = c_ * rowl + s_ * x2, nr = c_ * x2 - s_ * rowl;
+          rowl = nl;
+          __syncwarp();
+          if (lane < l) s.T[tri(r - 1) + lane] = nr;
+          else if (lane > l && lane <= r) s.T[tri(r - 1) + lane - 1] = nr;
+          __syncwarp();
+        }
+        const int Wn = (lane > l && lane < q) ? s.W[lane] : 0;
+        const int cn = (lane > l && lane < q) ? s.cpt[lane] : 0;
+        const double un = (lane > l && lane < q) ? s.u[lane] : 0.0;
+        __syncwarp();
+        if (lane > l && lane < q) { s.W[lane - 1] = Wn; s.cpt[lane - 1] = cn; s.u[lane - 1] = un; }
+        --q;
+        __syncwarp();
+      }
+    }
+  }
+  if (res.fail) {  // no solution: report the unconstrained optimum, as a caller-visible placeholder
+    s.jr[axis][i] = s.j0[axis][i];
+    if (i < 2) s.ff[axis][i] = s.f0[axis][i];
+    __syncwarp();
+  }
+  q_out = q;
+  return res;
+}
+
+}  // namespace herdt

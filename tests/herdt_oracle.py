@@ -10,22 +10,9 @@ MAX_VARS = 36
 MAX_ROWS = 75
 
 
-class HerdtParams(C.Structure):
-    _fields_ = [("T", C.c_double), ("com_height", C.c_double), ("w_jerk", C.c_double), ("w_vel", C.c_double),
-                ("w_cop", C.c_double), ("cop_half_x", C.c_double), ("cop_half_y", C.c_double),
-                ("ds_feet_distance", C.c_double), ("foot_hull_x", C.c_double * 5), ("foot_hull_y", C.c_double * 5),
-                ("lipm_T", C.c_double)]
+from jrl_walkgen_b200._capi import HerdtParams, herdt_dtypes  # plain struct mirrors (no compute)
 
-
-QP_INPUT_DTYPE = np.dtype([
-    ("com_x", "f8", 3), ("com_y", "f8", 3), ("ref_x", "f8", N), ("ref_y", "f8", N),
-    ("sup_x", "f8", N + 1), ("sup_y", "f8", N + 1), ("sup_yaw", "f8", N + 1),
-    ("sup_foot", "i1", N + 1), ("sup_phase", "i1", N + 1), ("sup_step", "i1", N + 1), ("sup_changed", "i1", N + 1),
-    ("pad_", "i1", 4)])
-QP_OUTPUT_DTYPE = np.dtype([
-    ("x", "f8", MAX_VARS), ("lagr", "f8", MAX_ROWS + 1), ("com_next_x", "f8", 3), ("com_next_y", "f8", 3),
-    ("n_vars", "i4"), ("n_rows", "i4"), ("fail", "i4"), ("iterations", "i4")])
-assert QP_INPUT_DTYPE.itemsize == 784 and QP_OUTPUT_DTYPE.itemsize == 960
+QP_INPUT_DTYPE, QP_OUTPUT_DTYPE = herdt_dtypes()
 
 _lib = None
 
