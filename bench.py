@@ -258,7 +258,7 @@ def run_cuda(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         fp64_peak = ctx.fp64_peak_tflops()
-        names = {0: "preview_fir_kernel", 1: "preview_recur_kernel", 6: "preview_fused_kernel"}
+        names = {6: "preview_fused_kernel", 2: "herdt_qp_kernel", 3: "herdt_mpc_kernel", 4: "pldp_kernel"}
         kern = {names.get(k, str(k)): {"launches": v[0], "avg_ms": v[1] / v[0]} for k, v in prof.items()}
         dom = max(kern.items(), key=lambda kv: kv[1]["avg_ms"] * kv[1]["launches"])
         dom_name, dom_ms = dom[0], dom[1]["avg_ms"]

@@ -7,18 +7,23 @@
 //
 // B200-first restructuring.  The reference evaluates, per 5 ms tick and per axis,
 //     u = -Kx.x + Ks.s + sum_{i<NL} F[i] * p[k+i]          (640 MACs through a deque of 48-byte structs)
-// and then the 3-state update.  The preview sum does not depend on the state, so it is a FIR filter
-// of the ZMP reference and is separated from the recursion:
-//   kernel 1  preview_fir_kernel   : fir[k] = sum_i F[i] p[k+i] for every step of every trajectory.
-//             This is >94% of the flops (1280 of 1360 per step).  Each thread produces R=8 consecutive
-//             outputs for both axes from a register-resident sliding window: per tap it issues ONE
-//             128-bit shared-memory load and 16 DFMAs, so the FP64 pipe (64 DFMA/clk/SM), not the LSU,
-//             is the limiter.  The ZMP tile is staged once per block in shared memory (coalesced
-//             128-bit global loads) with a 9/8 padding so that the stride-8 per-thread windows are
-//             bank-conflict free.  HBM traffic is the streaming minimum (each sample read once per
-//             tile + 30% halo, fir written once).
-//   kernel 2  preview_recur_kernel : the 4-state (x, dx, ddx, s) recursion, one thread per
-//             (trajectory, axis), in the reference's statement order.
+// and then the 3-state update.  One kernel, preview_fused_kernel, does all of it; one CTA owns one
+// trajectory and walks it in tiles of 1024 ticks:
+//   (1) FIR.  The preview sum does not depend on the state, so it is a FIR filter of the ZMP reference
+//       (>94% of the flops: 1280 of 1360 per step).  Each thread produces R=8 consecutive outputs for
+//       both axes from a register-resident sliding window: per tap it issues ONE 128-bit shared-memory
+//       load and 16 DFMAs, so the FP64 pipe (64 DFMA/clk/SM), not the LSU, is the limiter.  The ZMP tile
+//       is staged once per tile in shared memory (coalesced 128-bit global loads) with a 9/8 padding so
+//       that the stride-8 per-thread windows are bank-conflict free.
+//   (2) Recursion as a scan.  Per axis the controller is the linear recurrence X' = M X + g_k on the
+//       4-state X = (x, dx, ddx, s) with a CONSTANT closed-loop matrix M (spectral radius 0.983), so the
+//       serial chain of the reference is replaced by: every thread runs its 8 ticks from a zero state
+//       (thread 0: from the carried state) in the reference's statement order; a Kogge-Stone scan over the
+//       128 threads combines them with the constant matrices M^(8 d), d = 1..32 (warp shuffles inside a warp,
+//       one shared-memory exchange of the four warp totals across warps); every thread then re-runs its 8 ticks from its true start state and
+//       emits CoM and ZMP.  The last tick's state is carried to the next tile in shared memory.
+// The FIR result never goes to HBM: traffic is the streaming minimum (16 B in per tick + the NL-sample
+// halo once per tile, 64 B out).
 //
 #include "wg_common.h"
 #include <vector>
@@ -206,140 +211,281 @@ extern "C" int wg_preview_gains(double T, double preview_time, double zc, int mo
 // ---------------------------------------------------------------------------------------------
 // Device side
 // ---------------------------------------------------------------------------------------------
-constexpr int FIR_R = 8;                      // outputs per thread
+constexpr int FIR_R = 8;                      // ticks per thread
 constexpr int FIR_THREADS = 128;
-constexpr int FIR_TILE = FIR_R * FIR_THREADS; // outputs per block
+constexpr int FIR_TILE = FIR_R * FIR_THREADS; // ticks per tile
+constexpr int SCAN_LEVELS = 6;                // M^(8 d), d = 1, 2, 4, ..., 32 threads
 
 struct PreviewConsts {
   double A[9], B[3], C[3], Kx[3], Ks;
   int NL, NLpad;
+  // P[sim][l] = M_sim^(FIR_R * 2^l), row-major 4x4; M_sim is the closed-loop one-tick matrix of the
+  // 4-state (x, dx, ddx, s) with (sim = 1) or without (sim = 0) the integrated-error update.
+  double P[2][SCAN_LEVELS][16];
 };
 __constant__ PreviewConsts c_pc;
 __constant__ double c_F[WG_PREVIEW_MAX_NL + 8];
-
-struct FirTile { int traj; int start; };      // outputs [start, start+FIR_TILE) of trajectory traj
 
 struct wg_preview_plan {
   wg_ctx *ctx;
   int B;
   int NL;
   int64_t total_samples, total_steps;
-  int n_tiles;
   int64_t *d_offsets;
-  FirTile *d_tiles;
-  double2 *d_fir;      // [total_samples]
+  int *d_order;        // trajectories sorted by decreasing length (longest CTAs are scheduled first)
   // staging buffers for WG_MEM_HOST calls
   double *d_zmp, *d_state, *d_com, *d_zmpout;
 };
 
 __device__ __forceinline__ int pad9(int e) { return e + (e >> 3); }
 
-// fir[o+k] = sum_{i<NL} F[i] * p[o+k+i]  for k in the tile, both axes.
-__global__ void __launch_bounds__(FIR_THREADS)
-preview_fir_kernel(const FirTile *__restrict__ tiles, const int64_t *__restrict__ offsets,
-                   const double2 *__restrict__ p, double2 *__restrict__ fir)
+// One tick of OneIterationOfPreview for one axis, in the reference's statement order
+// (PreviewControl.cpp:346-367): u, x <- A x + B u, zmp = C x, s += p - zmp.
+struct Axis {
+  double x0, x1, x2, s;
+};
+template <bool SIM>
+__device__ __forceinline__ double preview_tick(Axis &a, double f, double pk)
 {
-  extern __shared__ double2 sp[];             // padded tile of (px,py)
-  const FirTile tile = tiles[blockIdx.x];
-  const int64_t o = offsets[tile.traj];
-  const int L = (int)(offsets[tile.traj + 1] - o);
-  const int NL = c_pc.NL, NLpad = c_pc.NLpad;
-  const int nsteps = L - NL + 1;
-  const int span = FIR_TILE + NLpad;           // samples needed by this tile
-  const double2 *src = p + o + tile.start;
-  const int avail = L - tile.start;            // samples that exist from tile.start on
-  for (int e = threadIdx.x; e < span; e += FIR_THREADS) {
-    double2 v = make_double2(0.0, 0.0);
-    if (e < avail) v = __ldg(src + e);
-    sp[pad9(e)] = v;
-  }
-  __syncthreads();
-
-  const int t = threadIdx.x;
-  double ax[FIR_R], ay[FIR_R], wx[FIR_R], wy[FIR_R];
-#pragma unroll
-  for (int r = 0; r < FIR_R; ++r) {
-    ax[r] = 0.0; ay[r] = 0.0;
-    double2 v = sp[pad9(FIR_R * t + r)];
-    wx[r] = v.x; wy[r] = v.y;
-  }
-  // window invariant at tap j: w[(j+r) % 8] holds p[8t + r + j]
-  const double2 *wp = sp + pad9(FIR_R * t + FIR_R);   // next sample to enter the window
-  for (int jj = 0; jj < NLpad; jj += FIR_R) {
-#pragma unroll
-    for (int u = 0; u < FIR_R; ++u) {
-      const double f = c_F[jj + u];
-#pragma unroll
-      for (int r = 0; r < FIR_R; ++r) {
-        ax[r] = fma(f, wx[(u + r) % FIR_R], ax[r]);
-        ay[r] = fma(f, wy[(u + r) % FIR_R], ay[r]);
-      }
-      double2 v = wp[u];                        // p[8t + 8 + jj + u]; 8-aligned group => no pad inside
-      wx[u] = v.x; wy[u] = v.y;
-    }
-    wp += FIR_R + 1;                            // 8 samples + 1 padding slot
-  }
-  const int k0 = tile.start + FIR_R * t;
-  double2 *dst = fir + o + k0;
-#pragma unroll
-  for (int r = 0; r < FIR_R; ++r)
-    if (k0 + r < nsteps) dst[r] = make_double2(ax[r], ay[r]);
+  double r = c_pc.Kx[0] * a.x0;
+  r = fma(c_pc.Kx[1], a.x1, r);
+  r = fma(c_pc.Kx[2], a.x2, r);
+  const double u = fma(c_pc.Ks, a.s, -r) + f;
+  // A = [[1,T,T^2/2],[0,1,T],[0,0,1]]
+  const double n0 = fma(c_pc.A[2], a.x2, fma(c_pc.A[1], a.x1, a.x0));
+  const double n1 = fma(c_pc.A[5], a.x2, a.x1);
+  a.x0 = fma(u, c_pc.B[0], n0);
+  a.x1 = fma(u, c_pc.B[1], n1);
+  a.x2 = fma(u, c_pc.B[2], a.x2);
+  const double z = fma(c_pc.C[2], a.x2, fma(c_pc.C[1], a.x1, c_pc.C[0] * a.x0));
+  if (SIM) a.s += (pk - z);
+  return z;
 }
 
-// One thread per (trajectory, axis): the recursion of OneIterationOfPreview in statement order.
-__global__ void __launch_bounds__(64)
-preview_recur_kernel(int B, const int64_t *__restrict__ offsets, const double2 *__restrict__ p,
-                     const double2 *__restrict__ fir, double *__restrict__ state,
-                     double *__restrict__ com, double *__restrict__ zmp, int simulation)
+__device__ __forceinline__ void scan_combine(Axis &c, const double *__restrict__ P, double n0, double n1, double n2,
+                                             double n3)
 {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = tid >> 1, axis = tid & 1;
-  if (b >= B) return;
+  c.x0 = fma(P[0], n0, fma(P[1], n1, fma(P[2], n2, fma(P[3], n3, c.x0))));
+  c.x1 = fma(P[4], n0, fma(P[5], n1, fma(P[6], n2, fma(P[7], n3, c.x1))));
+  c.x2 = fma(P[8], n0, fma(P[9], n1, fma(P[10], n2, fma(P[11], n3, c.x2))));
+  c.s = fma(P[12], n0, fma(P[13], n1, fma(P[14], n2, fma(P[15], n3, c.s))));
+}
+
+template <bool SIM>
+__global__ void __launch_bounds__(FIR_THREADS, 5)
+preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ offsets,
+                     const double2 *__restrict__ p, double *__restrict__ state, double *__restrict__ com,
+                     double *__restrict__ zmp)
+{
+  extern __shared__ double2 sp[];             // padded tile of (px,py), then the scan exchange area
+  __shared__ double s_x[FIR_THREADS][8];      // scan exchange (x axis 0..3, y axis 4..7)
+  __shared__ double s_carry[8];
+  const int b = order[blockIdx.x];
   const int64_t o = offsets[b];
   const int L = (int)(offsets[b + 1] - o);
-  const int nsteps = L - c_pc.NL + 1;
+  const int NL = c_pc.NL, NLpad = c_pc.NLpad;
+  const int nsteps = L - NL + 1;
   if (nsteps <= 0) return;
-  const double A01 = c_pc.A[1], A02 = c_pc.A[2], A12 = c_pc.A[5];
-  const double B0 = c_pc.B[0], B1 = c_pc.B[1], B2 = c_pc.B[2];
-  const double C0 = c_pc.C[0], C1 = c_pc.C[1], C2 = c_pc.C[2];
-  const double K0 = c_pc.Kx[0], K1 = c_pc.Kx[1], K2 = c_pc.Kx[2], Ks = c_pc.Ks;
-  double *st = state + 8 * (size_t)b;
-  double x0 = st[3 * axis + 0], x1 = st[3 * axis + 1], x2 = st[3 * axis + 2], s = st[6 + axis];
-  const double *pf = reinterpret_cast<const double *>(fir + o) + axis;
-  const double *pp = reinterpret_cast<const double *>(p + o) + axis;
-  double *pc = com ? com + 6 * o + 3 * axis : nullptr;
-  double *pz = zmp ? zmp + 2 * o + axis : nullptr;
-#pragma unroll 4
-  for (int k = 0; k < nsteps; ++k) {
-    const double f = __ldg(pf + 2 * (size_t)k);
-    const double pk = __ldg(pp + 2 * (size_t)k);
-    double r = K0 * x0;
-    r = fma(K1, x1, r);
-    r = fma(K2, x2, r);
-    double u = fma(Ks, s, -r) + f;
-    // x = A x + u B   (A = [[1,T,T^2/2],[0,1,T],[0,0,1]])
-    double n0 = fma(A02, x2, fma(A01, x1, x0));
-    double n1 = fma(A12, x2, x1);
-    x0 = fma(u, B0, n0);
-    x1 = fma(u, B1, n1);
-    x2 = fma(u, B2, x2);
-    double z = fma(C2, x2, fma(C1, x1, C0 * x0));
-    if (simulation) s += (pk - z);
-    if (pc) { pc[6 * (size_t)k] = x0; pc[6 * (size_t)k + 1] = x1; pc[6 * (size_t)k + 2] = x2; }
-    if (pz) pz[2 * (size_t)k] = z;
+  const int t = threadIdx.x, lane = t & 31;
+  const int span = FIR_TILE + NLpad;           // samples one tile needs
+  if (t < 8) s_carry[t] = state[8 * (size_t)b + t];   // {x,dx,ddx,y,dy,ddy,sx,sy}
+  const double(*Pm)[16] = c_pc.P[SIM ? 1 : 0];
+
+  for (int start = 0; start < nsteps; start += FIR_TILE) {
+    __syncthreads();
+    const double2 *src = p + o + start;
+    const int avail = L - start;               // samples that exist from `start` on
+    for (int e = t; e < span; e += FIR_THREADS) {
+      double2 v = make_double2(0.0, 0.0);
+      if (e < avail) v = __ldg(src + e);
+      sp[pad9(e)] = v;
+    }
+    __syncthreads();
+
+    // ---- (1) FIR: ax[r], ay[r] = sum_i F[i] p[start + 8t + r + i]
+    double ax[FIR_R], ay[FIR_R], wx[FIR_R], wy[FIR_R];
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r) {
+      ax[r] = 0.0; ay[r] = 0.0;
+      double2 v = sp[pad9(FIR_R * t + r)];
+      wx[r] = v.x; wy[r] = v.y;
+    }
+    // window invariant at tap j: w[(j+r) % 8] holds p[8t + r + j]
+    const double2 *wp = sp + pad9(FIR_R * t + FIR_R);   // next sample to enter the window
+    for (int jj = 0; jj < NLpad; jj += FIR_R) {
+#pragma unroll
+      for (int u = 0; u < FIR_R; ++u) {
+        const double f = c_F[jj + u];
+#pragma unroll
+        for (int r = 0; r < FIR_R; ++r) {
+          ax[r] = fma(f, wx[(u + r) % FIR_R], ax[r]);
+          ay[r] = fma(f, wy[(u + r) % FIR_R], ay[r]);
+        }
+        double2 v = wp[u];                        // p[8t + 8 + jj + u]; 8-aligned group => no pad inside
+        wx[u] = v.x; wy[u] = v.y;
+      }
+      wp += FIR_R + 1;                            // 8 samples + 1 padding slot
+    }
+    // the ZMP reference of the thread's own ticks (the `ZMPPositions[lindex]` of the error integrator) is
+    // re-read from the tile in both passes below rather than kept in registers across the scan
+    const double2 *own = sp + pad9(FIR_R * t);
+
+    // ---- (2a) local pass from a zero state (thread 0: from the carried state)
+    Axis cx, cy;
+    if (t == 0) {
+      cx.x0 = s_carry[0]; cx.x1 = s_carry[1]; cx.x2 = s_carry[2]; cx.s = s_carry[6];
+      cy.x0 = s_carry[3]; cy.x1 = s_carry[4]; cy.x2 = s_carry[5]; cy.s = s_carry[7];
+    } else {
+      cx.x0 = cx.x1 = cx.x2 = cx.s = 0.0;
+      cy.x0 = cy.x1 = cy.x2 = cy.s = 0.0;
+    }
+    const Axis inx = cx, iny = cy;
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r) {
+      const double2 pk = own[r];
+      preview_tick<SIM>(cx, ax[r], pk.x);
+      preview_tick<SIM>(cy, ay[r], pk.y);
+    }
+    // ---- (2b) Kogge-Stone scan over threads: c_t += M^(8d) c_{t-d}
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      const int d = 1 << l;
+      const double a0 = __shfl_up_sync(0xffffffffu, cx.x0, d), a1 = __shfl_up_sync(0xffffffffu, cx.x1, d);
+      const double a2 = __shfl_up_sync(0xffffffffu, cx.x2, d), a3 = __shfl_up_sync(0xffffffffu, cx.s, d);
+      const double b0 = __shfl_up_sync(0xffffffffu, cy.x0, d), b1 = __shfl_up_sync(0xffffffffu, cy.x1, d);
+      const double b2 = __shfl_up_sync(0xffffffffu, cy.x2, d), b3 = __shfl_up_sync(0xffffffffu, cy.s, d);
+      if (lane >= d) {
+        scan_combine(cx, Pm[l], a0, a1, a2, a3);
+        scan_combine(cy, Pm[l], b0, b1, b2, b3);
+      }
+    }
+    // The shuffle levels give a scan segmented per warp.  Carry across warps: T_w = total of warp w (lane 31),
+    // state entering warp w: W_w = M^256 W_{w-1} + T_{w-1}, W_0 = 0 (the carried tile state is inside thread 0's
+    // local pass); lane j then adds M^(8 (j+1)) W_w, built from the bits of j+1 with the same constant matrices.
+    if (lane == 31) {
+      double *n = s_x[t >> 5];
+      n[0] = cx.x0; n[1] = cx.x1; n[2] = cx.x2; n[3] = cx.s;
+      n[4] = cy.x0; n[5] = cy.x1; n[6] = cy.x2; n[7] = cy.s;
+    }
+    __syncthreads();
+    {
+      const int w = t >> 5;
+      Axis vx, vy;
+      vx.x0 = vx.x1 = vx.x2 = vx.s = 0.0;
+      vy.x0 = vy.x1 = vy.x2 = vy.s = 0.0;
+      for (int v = 0; v < w; ++v) {        // W_{v+1} = M^256 W_v + T_v
+        const double *n = s_x[v];
+        Axis nx, ny;
+        nx.x0 = n[0]; nx.x1 = n[1]; nx.x2 = n[2]; nx.s = n[3];
+        ny.x0 = n[4]; ny.x1 = n[5]; ny.x2 = n[6]; ny.s = n[7];
+        scan_combine(nx, Pm[5], vx.x0, vx.x1, vx.x2, vx.s);
+        scan_combine(ny, Pm[5], vy.x0, vy.x1, vy.x2, vy.s);
+        vx = nx; vy = ny;
+      }
+      if (w > 0) {
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          if (((lane + 1) >> l) & 1) {
+            Axis zx, zy;
+            zx.x0 = zx.x1 = zx.x2 = zx.s = 0.0;
+            zy.x0 = zy.x1 = zy.x2 = zy.s = 0.0;
+            scan_combine(zx, Pm[l], vx.x0, vx.x1, vx.x2, vx.s);
+            scan_combine(zy, Pm[l], vy.x0, vy.x1, vy.x2, vy.s);
+            vx = zx; vy = zy;
+          }
+        }
+        cx.x0 += vx.x0; cx.x1 += vx.x1; cx.x2 += vx.x2; cx.s += vx.s;
+        cy.x0 += vy.x0; cy.x1 += vy.x1; cy.x2 += vy.x2; cy.s += vy.s;
+      }
+    }
+    __syncthreads();
+    // ---- (2c) true start state of this thread = inclusive result of thread t-1
+    s_x[t][0] = cx.x0; s_x[t][1] = cx.x1; s_x[t][2] = cx.x2; s_x[t][3] = cx.s;
+    s_x[t][4] = cy.x0; s_x[t][5] = cy.x1; s_x[t][6] = cy.x2; s_x[t][7] = cy.s;
+    __syncthreads();
+    Axis sx = inx, sy = iny;
+    if (t > 0) {
+      const double *n = s_x[t - 1];
+      sx.x0 = n[0]; sx.x1 = n[1]; sx.x2 = n[2]; sx.s = n[3];
+      sy.x0 = n[4]; sy.x1 = n[5]; sy.x2 = n[6]; sy.s = n[7];
+    }
+    // ---- (2d) final pass: emit CoM / ZMP of the valid ticks
+    const int k0 = start + FIR_R * t;
+    const int last = min(start + FIR_TILE, nsteps) - 1;   // last valid tick of this tile
+    double *pc = com ? com + 6 * (o + k0) : nullptr;
+    double *pz = zmp ? zmp + 2 * (o + k0) : nullptr;
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r) {
+      if (k0 + r <= last) {
+        const double2 pk = own[r];
+        const double zx = preview_tick<SIM>(sx, ax[r], pk.x);
+        const double zy = preview_tick<SIM>(sy, ay[r], pk.y);
+        if (pc) {
+          double2 *q = reinterpret_cast<double2 *>(pc + 6 * r);
+          q[0] = make_double2(sx.x0, sx.x1);
+          q[1] = make_double2(sx.x2, sy.x0);
+          q[2] = make_double2(sy.x1, sy.x2);
+        }
+        if (pz) *reinterpret_cast<double2 *>(pz + 2 * r) = make_double2(zx, zy);
+        if (k0 + r == last) {
+          s_carry[0] = sx.x0; s_carry[1] = sx.x1; s_carry[2] = sx.x2; s_carry[6] = sx.s;
+          s_carry[3] = sy.x0; s_carry[4] = sy.x1; s_carry[5] = sy.x2; s_carry[7] = sy.s;
+        }
+      }
+    }
   }
-  st[3 * axis + 0] = x0; st[3 * axis + 1] = x1; st[3 * axis + 2] = x2; st[6 + axis] = s;
+  __syncthreads();
+  if (t < 8) state[8 * (size_t)b + t] = s_carry[t];
 }
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
+namespace {
+
+// Closed-loop one-tick matrix of the 4-state (x, dx, ddx, s) and its powers M^(8 2^l), in extended precision.
+void scan_matrices(const wg_preview_gains_t &g, bool sim, double (*P)[16])
+{
+  typedef long double LD;
+  LD M[4][4];
+  for (int j = 0; j < 4; ++j) {
+    LD x[3] = {0, 0, 0}, s = 0;
+    if (j < 3) x[j] = 1; else s = 1;
+    const LD u = (LD)g.Ks * s - ((LD)g.Kx[0] * x[0] + (LD)g.Kx[1] * x[1] + (LD)g.Kx[2] * x[2]);
+    LD n[3];
+    for (int i = 0; i < 3; ++i)
+      n[i] = (LD)g.A[3 * i] * x[0] + (LD)g.A[3 * i + 1] * x[1] + (LD)g.A[3 * i + 2] * x[2] + (LD)g.B[i] * u;
+    const LD z = (LD)g.C[0] * n[0] + (LD)g.C[1] * n[1] + (LD)g.C[2] * n[2];
+    for (int i = 0; i < 3; ++i) M[i][j] = n[i];
+    M[3][j] = sim ? s - z : s;
+  }
+  auto square = [](LD X[4][4]) {
+    LD Y[4][4];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        LD a = 0;
+        for (int k = 0; k < 4; ++k) a += X[i][k] * X[k][j];
+        Y[i][j] = a;
+      }
+    std::memcpy(X, Y, sizeof Y);
+  };
+  for (int r = 1; r < FIR_R; r <<= 1) square(M);   // M^FIR_R (FIR_R is a power of two)
+  for (int l = 0; l < SCAN_LEVELS; ++l) {
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) P[l][4 * i + j] = (double)M[i][j];
+    square(M);
+  }
+}
+
+}  // namespace
+
 extern "C" {
 
 int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *g)
 {
   if (!ctx || !g || g->NL <= 0 || g->NL > WG_PREVIEW_MAX_NL) return WG_ERR_INVALID;
   wg_device_guard guard(ctx->device);
+  static_assert((FIR_R & (FIR_R - 1)) == 0, "FIR_R must be a power of two");
   PreviewConsts pc;
   std::memcpy(pc.A, g->A, sizeof pc.A);
   std::memcpy(pc.B, g->B, sizeof pc.B);
@@ -348,6 +494,8 @@ int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *g)
   pc.Ks = g->Ks;
   pc.NL = g->NL;
   pc.NLpad = (g->NL + FIR_R - 1) / FIR_R * FIR_R;
+  scan_matrices(*g, false, pc.P[0]);
+  scan_matrices(*g, true, pc.P[1]);
   std::vector<double> F(WG_PREVIEW_MAX_NL + 8, 0.0);
   std::copy(g->F, g->F + g->NL, F.begin());
   WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -365,31 +513,30 @@ int wg_preview_plan_create(wg_ctx *ctx, int B, const int64_t *offsets, wg_previe
   wg_device_guard guard(ctx->device);
   *out = nullptr;
   const int NL = ctx->preview_gains.NL;
-  std::vector<FirTile> tiles;
+  if (B > 0 && offsets[0] != 0) return wg_fail(ctx, WG_ERR_INVALID, "offsets[0] must be 0");
   int64_t total_steps = 0;
+  std::vector<int> order(B);
   for (int b = 0; b < B; ++b) {
-    int64_t L = offsets[b + 1] - offsets[b];
+    const int64_t L = offsets[b + 1] - offsets[b];
     if (L < 0 || L > 0x3fffffff) return wg_fail(ctx, WG_ERR_INVALID, "offsets must be non-decreasing");
-    int nsteps = (int)L - NL + 1;
-    if (nsteps <= 0) continue;
-    total_steps += nsteps;
-    for (int s = 0; s < nsteps; s += FIR_TILE) tiles.push_back(FirTile{b, s});
+    if (L >= NL) total_steps += L - NL + 1;
+    order[b] = b;
   }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return offsets[a + 1] - offsets[a] > offsets[b + 1] - offsets[b];
+  });
   wg_preview_plan *pl = new (std::nothrow) wg_preview_plan();
   if (!pl) return WG_ERR_ALLOC;
   std::memset(pl, 0, sizeof *pl);
   pl->ctx = ctx; pl->B = B; pl->NL = NL;
-  pl->total_samples = B > 0 ? offsets[B] - offsets[0] : 0;
+  pl->total_samples = B > 0 ? offsets[B] : 0;
   pl->total_steps = total_steps;
-  pl->n_tiles = (int)tiles.size();
-  if (B > 0 && offsets[0] != 0) { delete pl; return wg_fail(ctx, WG_ERR_INVALID, "offsets[0] must be 0"); }
   cudaError_t e = cudaMalloc(&pl->d_offsets, sizeof(int64_t) * (B + 1));
-  if (e == cudaSuccess) e = cudaMalloc(&pl->d_tiles, sizeof(FirTile) * std::max<size_t>(1, tiles.size()));
-  if (e == cudaSuccess) e = cudaMalloc(&pl->d_fir, sizeof(double2) * std::max<int64_t>(1, pl->total_samples));
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_order, sizeof(int) * std::max(1, B));
   if (e == cudaSuccess && B > 0)
     e = cudaMemcpyAsync(pl->d_offsets, offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && !tiles.empty())
-    e = cudaMemcpyAsync(pl->d_tiles, tiles.data(), sizeof(FirTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && B > 0)
+    e = cudaMemcpyAsync(pl->d_order, order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     wg_fail(ctx, WG_ERR_CUDA, "wg_preview_plan_create", e);
@@ -405,7 +552,7 @@ int wg_preview_plan_destroy(wg_preview_plan *pl)
   if (!pl) return WG_OK;
   wg_device_guard guard(pl->ctx->device);
   cudaStreamSynchronize(pl->ctx->stream);
-  cudaFree(pl->d_offsets); cudaFree(pl->d_tiles); cudaFree(pl->d_fir);
+  cudaFree(pl->d_offsets); cudaFree(pl->d_order);
   cudaFree(pl->d_zmp); cudaFree(pl->d_state); cudaFree(pl->d_com); cudaFree(pl->d_zmpout);
   delete pl;
   return WG_OK;
@@ -417,26 +564,23 @@ int64_t wg_preview_plan_total_samples(const wg_preview_plan *pl) { return pl ? p
 static int preview_launch(wg_ctx *ctx, wg_preview_plan *pl, const double *d_zmp, double *d_state,
                           double *d_com, double *d_zmpout, int simulation)
 {
-  if (pl->n_tiles == 0) return WG_OK;
+  if (pl->total_steps == 0) return WG_OK;
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
   const int span = FIR_TILE + NLpad;
   const size_t smem = sizeof(double2) * (size_t)(span + (span >> 3) + 2);
+  if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the FIR tile");
   static bool attr_set = false;
   if (!attr_set) {
-    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  if (smem > 64 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the FIR tile");
-  wg_prof_start(ctx, WG_K_PREVIEW_FIR);
-  preview_fir_kernel<<<pl->n_tiles, FIR_THREADS, smem, ctx->stream>>>(
-      pl->d_tiles, pl->d_offsets, reinterpret_cast<const double2 *>(d_zmp), pl->d_fir);
-  wg_prof_stop(ctx);
-  WG_LAUNCHED(ctx);
-  const int threads = 64, blocks = (2 * pl->B + threads - 1) / threads;
-  wg_prof_start(ctx, WG_K_PREVIEW_RECUR);
-  preview_recur_kernel<<<blocks, threads, 0, ctx->stream>>>(
-      pl->B, pl->d_offsets, reinterpret_cast<const double2 *>(d_zmp), pl->d_fir, d_state, d_com, d_zmpout,
-      simulation);
+  const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
+  wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
+  if (simulation)
+    preview_fused_kernel<true><<<pl->B, FIR_THREADS, smem, ctx->stream>>>(pl->d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
+  else
+    preview_fused_kernel<false><<<pl->B, FIR_THREADS, smem, ctx->stream>>>(pl->d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;
