@@ -162,6 +162,144 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# Herdt2010 leg (BASELINE configs[2]: 16 384 random velocity references on one B200)
+# ------------------------------------------------------------------------------------------------
+HERDT_WORKLOAD = "herdt2010_qp_16384_random_velocity_refs_N16"
+
+
+def herdt_flop_model(n, m, iters):
+    """flops of the reference algorithm for one solve (assembly + Cholesky + active-set iterations)."""
+    return 1.2e4 + (2.0 / 3.0) * n ** 3 + iters * (2.0 * m * n + 6.0 * n * n)
+
+
+def _cpu_qld_worker(args):
+    import ctypes as C
+    import herdt_oracle as ho
+    ins_bytes, n, seconds = args
+    ins = np.frombuffer(ins_bytes, dtype=ho.QP_INPUT_DTYPE)
+    p = ho.default_params()
+    out = np.zeros(n, dtype=ho.QP_OUTPUT_DTYPE)
+    done = 0
+    t0 = time.perf_counter()
+    while True:
+        ho.lib().oracle_herdt_solve_qp_batch(C.byref(p), n, ins.ctypes.data, out.ctypes.data, 0)
+        done += n
+        if time.perf_counter() - t0 >= seconds:
+            break
+    return done, time.perf_counter() - t0, int((out["fail"] != 0).sum())
+
+
+def cpu_herdt_rate(qin, seconds=5.0, procs=None):
+    """The reference's own QLD (oracle/_ref object code) + the oracle's restated assembly, one PROCESS per core
+    (QLD keeps its locals static, qld.cpp:403-412: threads are unsafe), each on its own slice of the inputs."""
+    import multiprocessing as mp
+    import herdt_oracle as ho
+    procs = procs or host_cores()
+    kind = "reference" if ho.lib().oracle_herdt_have_ref_qld() == 1 else "port"
+    per = max(64, min(512, len(qin) // procs))
+    jobs = [(qin[(i * per) % max(1, len(qin) - per):][:per].tobytes(), per, seconds) for i in range(procs)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_cpu_qld_worker, jobs)
+    total = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return {"value": total / wall, "unit": "QP solves/s", "cores": procs, "kind": kind,
+            "sample": f"{procs} processes x {per} captured closed-loop QPs repeated for {seconds:.0f} s "
+                      f"({total} solves): oracle assembly (generator-vel-ref.cpp restated) + "
+                      + ("the reference's own ql0001_ object code" if kind == "reference" else "textbook solver"),
+            "us_per_solve_per_core": 1e6 * wall * procs / total, "failures": sum(r[2] for r in res)}
+
+
+def herdt_leg(ctx, wg, args, rank, fp64_peak, want_cpu):
+    import ctypes as C
+    B = args.herdt_instances
+    rng = np.random.default_rng([7, rank])
+    v = np.column_stack([rng.uniform(-0.2, 0.3, B), rng.uniform(-0.15, 0.15, B), rng.uniform(-0.2, 0.2, B)])
+    ctx.herdt_set_params()
+    ctx.herdt_mpc_set_params()
+    d_st = ctx.herdt_mpc_init(B, device=True)
+    d_v = ctx.to_device(v)
+    d_qin = ctx.alloc(B * wg.QP_INPUT_DTYPE.itemsize)
+    d_out = ctx.alloc(B * wg.QP_OUTPUT_DTYPE.itemsize)
+    d_flush = ctx.alloc(256 << 20)
+    lib, h = ctx.lib, ctx.h
+    ST, QI = wg.MPC_STATE_DTYPE.itemsize, wg.QP_INPUT_DTYPE.itemsize
+
+    def mpc(off, n, periods, qin=False):
+        ctx._check(lib.wg_herdt_mpc_run_batch(h, wg.WG_MEM_DEVICE, n, periods, C.c_void_p(d_st.ptr + off * ST),
+                                              C.c_void_p(d_v.ptr + off * 24), None, None,
+                                              C.c_void_p(d_qin.ptr + off * QI) if qin else None))
+
+    # warm-up rollout: 16 slices advanced by 40..55 periods so that the batch covers every phase of the step cycle
+    sl = (B + 15) // 16
+    for j in range(16):
+        a = j * sl
+        n = min(sl, B - a)
+        if n > 0:
+            mpc(a, n, 40 + j)
+    ctx.sync()
+    # ---- closed loop: K launches of `periods` QP periods over the whole batch
+    periods = args.herdt_periods
+    for _ in range(2):
+        mpc(0, B, periods)
+    ctx.sync()
+    ctx.prof_begin(2 * args.steps + 8)
+    for _ in range(args.steps):
+        mpc(0, B, periods)
+    prof = ctx.prof_end()
+    mpc_ms = prof[3][1] / prof[3][0]
+    mpc_rate = B * periods / (mpc_ms * 1e-3)
+    # ---- open loop on the captured QP inputs of the last period (device resident, L2 flushed between launches)
+    mpc(0, B, 1, qin=True)
+    ctx.sync()
+    for _ in range(3):
+        ctx.herdt_qp_solve(d_qin, d_out, mem=wg.WG_MEM_DEVICE, count=B)
+    ctx.sync()
+    ctx.prof_begin(2 * args.steps + 8)
+    for _ in range(args.steps):
+        ctx._check(lib.wg_memset_device(h, d_flush.ptr, 0, 256 << 20))
+        ctx.herdt_qp_solve(d_qin, d_out, mem=wg.WG_MEM_DEVICE, count=B)
+    prof = ctx.prof_end()
+    qp_ms = prof[2][1] / prof[2][0]
+    qp_rate = B / (qp_ms * 1e-3)
+    out = d_out.download(wg.QP_OUTPUT_DTYPE, (B,))
+    qin = d_qin.download(wg.QP_INPUT_DTYPE, (B,))
+    st = d_st.download(wg.MPC_STATE_DTYPE, (B,))
+    iters = out["iterations"].astype(np.float64)
+    flops = float(np.sum(herdt_flop_model(out["n_vars"].astype(np.float64), out["n_rows"].astype(np.float64), iters)))
+    ach = flops / (qp_ms * 1e-3) / 1e12
+    # ---- end to end: host records in, host records out through the C ABI
+    pin_in = ctx.pinned((B,), wg.QP_INPUT_DTYPE); pin_in[:] = qin
+    pin_out = ctx.pinned((B,), wg.QP_OUTPUT_DTYPE)
+    for _ in range(2):
+        ctx.herdt_qp_solve(pin_in, pin_out)
+    n_e2e = max(3, min(args.steps, 10))
+    te = time.perf_counter()
+    for _ in range(n_e2e):
+        ctx.herdt_qp_solve(pin_in, pin_out)
+    e2e_s = time.perf_counter() - te
+    res = {"workload": HERDT_WORKLOAD, "instances": B,
+           "qp_solves_per_s": qp_rate, "qp_ms_per_launch": qp_ms,
+           "closed_loop_qp_solves_per_s": mpc_rate, "closed_loop_ms_per_launch": mpc_ms,
+           "closed_loop_periods_per_launch": periods,
+           "iterations_mean": float(iters.mean()), "iterations_max": int(iters.max()),
+           "n_prw_steps_hist": [int((qin["sup_step"][:, 16] == k).sum()) for k in range(3)],
+           "failures": int((out["fail"] != 0).sum()), "closed_loop_failures": int(st["fail_count"].sum()),
+           "roofline": {"kernel": "herdt_qp_kernel", "bound": "fp64", "achieved": ach, "peak": fp64_peak,
+                        "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                        "algorithmic_flop_per_solve_mean": flops / B,
+                        "note": "flop model of the reference algorithm (SURVEY 8d) with the measured active-set "
+                                "iteration counts; the kernel is latency/divergence bound, not pipe bound"},
+           "e2e": {"value": B * n_e2e / e2e_s, "unit": "QP solves/s", "h2d_bytes_per_step": int(qin.nbytes),
+                   "d2h_bytes_per_step": int(out.nbytes), "api": "wg_herdt_qp_solve_batch(WG_MEM_HOST), pinned host records"}}
+    if want_cpu:
+        res["cpu_baseline"] = cpu_herdt_rate(qin, seconds=max(2.0, args.cpu_seconds / 2))
+    for b in (d_st, d_v, d_qin, d_out, d_flush):
+        b.free()
+    return res, {"herdt_qp_kernel": {"launches": args.steps, "avg_ms": qp_ms},
+                 "herdt_mpc_kernel": {"launches": args.steps, "avg_ms": mpc_ms}}
+
+
 def run_cuda(args):
     rank, local_rank, world = dist_env()
     import jrl_walkgen_b200 as wg
@@ -247,6 +385,22 @@ def run_cuda(args):
     ms_per_step = ms_total / args.steps
     value = total_steps_all / (ms_per_step * 1e-3)
     e2e_value = total_steps_all * e2e_steps / e2e_s
+    for b_ in (dz, ds, dcom, dzmp):
+        b_.free()
+    launches_preview = launches
+    herdt = herdt_kern = None
+    if not args.no_herdt:
+        fp64_peak_all = ctx.fp64_peak_tflops()
+        ctx.reset_launches()
+        herdt, herdt_kern = herdt_leg(ctx, wg, args, rank, fp64_peak_all, want_cpu=(rank == 0 and world == 1))
+        if dist is not None:
+            import torch
+            t = torch.tensor([1.0 / herdt["qp_solves_per_s"], 1.0 / herdt["closed_loop_qp_solves_per_s"]],
+                             dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)          # slowest rank
+            herdt["qp_solves_per_s"] = world / float(t[0])
+            herdt["closed_loop_qp_solves_per_s"] = world / float(t[1])
+            herdt["instances"] = herdt["instances"] * world
 
     if rank == 0:
         # roofline of the dominant kernel (largest share of the timed region)
@@ -258,6 +412,7 @@ def run_cuda(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         fp64_peak = ctx.fp64_peak_tflops()
+        launches = launches_preview
         names = {6: "preview_fused_kernel", 2: "herdt_qp_kernel", 3: "herdt_mpc_kernel", 4: "pldp_kernel"}
         kern = {names.get(k, str(k)): {"launches": v[0], "avg_ms": v[1] / v[0]} for k, v in prof.items()}
         dom = max(kern.items(), key=lambda kv: kv[1]["avg_ms"] * kv[1]["launches"])
@@ -278,7 +433,7 @@ def run_cuda(args):
                     "algorithmic_flop_per_step": fl}
         roof["hbm_frac_streaming_minimum"] = BYTES_PER_STEP * steps_per_pass / (ms_per_step * 1e-3) / 1e9 / hbm_peak
         cpu = None
-        if world == 1 or True:
+        if world == 1:
             subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
             cpu = cpu_preview_rate(offsets, z, seconds=args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -287,7 +442,8 @@ def run_cuda(args):
                 "config": {"workload": WORKLOAD, "walks_per_gpu": B, "NL": 320, "T": 0.005,
                            "preview_steps_per_pass_per_gpu": steps_per_pass,
                            "l2": "inputs+outputs per pass (%.2f GB) exceed the 126 MB L2" % ((n * 80) / 1e9)},
-                "roofline": roof, "kernels": kern, "fp64_peak_tflops_measured": fp64_peak,
+                "roofline": roof, "kernels": dict(kern, **(herdt_kern or {})), "fp64_peak_tflops_measured": fp64_peak,
+                "herdt": herdt,
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "passes": e2e_steps, "api": "wg_preview_run_batch(WG_MEM_HOST), pinned host buffers"},
@@ -307,6 +463,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--walks", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--herdt-instances", type=int, default=16384)
+    ap.add_argument("--herdt-periods", type=int, default=10)
+    ap.add_argument("--no-herdt", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

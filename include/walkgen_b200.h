@@ -203,6 +203,114 @@ int wg_herdt_set_params(wg_ctx *ctx, const wg_herdt_params *params);
 int wg_herdt_qp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_herdt_qp_input *in,
                             wg_herdt_qp_output *out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Herdt2010 closed loop: the whole ZMPVelocityReferencedQP::OnLine cycle on the device, batched
+ *   replaces ZMPVelocityReferencedQP::InitOnLine / OnLine      (ZMPVelocityReferencedQP.cpp:213-319, :324-458)
+ *            SupportFSM::update_vel_reference / set_support_state (src/PreviewControl/SupportFSM.cpp:58-153)
+ *            GeneratorVelRef::preview_support_states / compute_global_reference (generator-vel-ref.cpp:71-134, :212-229)
+ *            OrientationsPreview::preview_orientations / interpolate_trunk_orientation (OrientationsPreview.cpp:80-418)
+ *            LinearizedInvertedPendulum2D::Interpolation / OneIteration (LinearizedInvertedPendulum2D.cpp:157-264)
+ *            OnLineFootTrajectoryGeneration::interpolate_feet_positions (OnLineFootTrajectoryGeneration.cpp:51-346)
+ *            the 5 ms deques popped by CoMAndFootOnlyStrategy::OneGlobalStepOfControl (CoMAndFootOnlyStrategy.cpp:56-124)
+ * One "step" is one QP period (QP_T_ = 0.1 s = 20 control ticks): FSM + orientation preview + QP build and
+ * solve + 20 interpolated CoM / ZMP / feet samples.  Every instance carries its own state, so B instances
+ * advance independently (different velocity references, phases, stop commands).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct wg_herdt_mpc_params {
+  double Ts;                /* m_SamplingPeriod 0.005            (ZMPVelocityReferencedQP.cpp:64)  */
+  double time_buffer;       /* TimeBuffer_ 0.04                  (:62)                             */
+  double step_period;       /* SupportFSM StepPeriod 0.8         (:77)                             */
+  double ds_period;         /* DSPeriod 1e9                      (:78)                             */
+  double dsss_period;       /* DSSSPeriod 0.8                    (:79)                             */
+  double t_single;          /* :singlesupporttime (TestHerdt2010: 0.7)                             */
+  double t_double;          /* :doublesupporttime (TestHerdt2010: 0.1)                             */
+  double step_height;       /* 0.05                              (rigid-body-system.cpp:66)        */
+  double hip_lower[2];      /* hip-yaw joint limits [left, right] (OrientationsPreview.cpp:48-66)  */
+  double hip_upper[2];
+  double foot_vel_limit;    /* |upperVelocityBound| of the hip yaw joint (:67-68)                  */
+  double hip_acc_limit;     /* uaLimitHipYaw_ 0.1                (:71)                             */
+  double feet_cross_limit;  /* uLimitFeet_ 5 deg                 (:73)                             */
+  int32_t nb_steps_ssds;    /* SupportFSM NbStepsSSDS 2 (:80); :numberstepsbeforestop overrides    */
+  int32_t pad_;
+} wg_herdt_mpc_params;
+
+void wg_herdt_mpc_default_params(wg_herdt_mpc_params *out);
+
+/* One 5 ms foot sample: the fields of FootAbsolutePosition this path writes (pgtypes.hh:141-170).
+ * theta in degrees as in the reference; omega/omega2 are identically 0 on this path (:omega 0.0). */
+typedef struct wg_herdt_foot_sample {
+  double x, y, z, theta;
+  double dx, dy, dz, dtheta;
+  double ddx, ddy;
+} wg_herdt_foot_sample;                /* 80 bytes */
+
+/* One 5 ms output row: what one tick pops from the four deques. */
+typedef struct wg_herdt_tick {
+  double com_x[3], com_y[3];           /* COMState x[0..2], y[0..2]                                   */
+  double com_z, yaw, dyaw;             /* COMState z[0], yaw[0], yaw[1]                               */
+  double zmp_x, zmp_y;                 /* ZMPPosition px, py (world frame)                            */
+  double pad_;
+  wg_herdt_foot_sample left, right;
+} wg_herdt_tick;                       /* 256 bytes */
+
+#define WG_HERDT_TICKS_PER_STEP 20     /* QP_T_ / m_SamplingPeriod */
+
+/* Per-instance persistent state of ZMPVelocityReferencedQP and its helpers (plain data; the host may
+ * read and edit it between calls, e.g. new_ref for Reference(), ending_phase for :stoppg). */
+typedef struct wg_herdt_mpc_state {
+  double clock;                        /* PGI m_InternalClock                                         */
+  double upper_time_limit;             /* UpperTimeLimitToUpdate_                                     */
+  double time_to_stop;                 /* m_TimeToStopOnLineMode                                      */
+  double new_ref[3];                   /* NewVelRef_ (dx, dy, dyaw): set by Reference()               */
+  double ref[3];                       /* VelRef_.Local after SupportFSM::update_vel_reference        */
+  double com_x[3], com_y[3];           /* CoM_ (LIPM state at the QP instants)                        */
+  double com_height;                   /* m_ComHeight of the LIPM (start height, NOT the QP's 0.814)  */
+  double trunk_yaw[3];                 /* OrientPrw_ TrunkState_.yaw                                  */
+  double trunk_t_yaw[2];               /* TrunkStateT_.yaw[0..1]                                      */
+  double support_time_passed;          /* OrientationsPreview::SupportTimePassed_                     */
+  double sup_time_limit, sup_start_time, sup_x, sup_y, sup_yaw;   /* IntermedData_->SupportState()    */
+  double poly_z[5];                    /* swing-height quartic, reset on support change               */
+  double com_front[6];                 /* FinalCOMTraj_deq[0]: x[0..2], y[0..2]                       */
+  double com_back[11];                 /* the not-yet-emitted last CoM/ZMP sample (wg_herdt_tick[0..10]) */
+  wg_herdt_foot_sample foot[2][3];     /* [left,right][deque index 0, size-2, size-1]                 */
+  int32_t sup_phase, sup_foot, sup_steps_left, sup_step_number, sup_nb_instants, sup_changed;
+  int32_t in_translation, in_rotation, post_rotation, steps_after_rotation, fsm_support_foot;
+  int32_t online_mode, ending_phase, running, nb_steps_ssds;
+  int32_t qp_count, fail_count, last_fail;
+  int64_t iterations_total;            /* active-set changes summed over all QPs of this instance     */
+} wg_herdt_mpc_state;
+
+/* Summary of one QP period (optional output). */
+typedef struct wg_herdt_mpc_step {
+  double time;                         /* clock at which the QP was solved                            */
+  double com_x[3], com_y[3];           /* CoM_ after the period                                       */
+  double jerk_x, jerk_y;               /* applied jerk (Solution_vec[0], [N])                         */
+  double next_foot_x, next_foot_y;     /* first previewed foot placement (0 when none)                */
+  double sup_x, sup_y, sup_yaw;        /* current support frame                                       */
+  int32_t sup_foot, sup_phase, n_prw_steps, fail;
+  int32_t iterations, n_active, pad_[2];
+} wg_herdt_mpc_step;                   /* 144 bytes */
+
+int wg_herdt_mpc_set_params(wg_ctx *ctx, const wg_herdt_mpc_params *params);
+
+/* InitOnLine for B instances.  init9 = {com x, y, z, left foot x, y, theta(deg), right foot x, y, theta(deg)};
+ * instance b reads init9 + b*init_stride (init_stride = 0 broadcasts one start configuration; the array is a
+ * HOST pointer).  `states` is host or device memory per `mem`.  The 8 buffered start samples
+ * (TimeBuffer_/m_SamplingPeriod) of the deques are implied by the state. */
+int wg_herdt_mpc_init(wg_ctx *ctx, int mem, int B, const double *init9, int init_stride,
+                      wg_herdt_mpc_state *states);
+
+/* Advance every instance by `nsteps` QP periods.
+ *   vel_ref : [B][3] or NULL   new (dx, dy, dyaw) written to new_ref before the first period
+ *   ticks   : [B][nsteps*20] or NULL  the rows popped at ticks 7+20k .. 26+20k of each period k (the sample a
+ *             period inherits at the back of the deques, final only now, then its first 19 new samples)
+ *   steps   : [B][nsteps] or NULL     per-period summaries
+ *   qp_in   : [B] or NULL             the QP input of each instance's LAST period (workload capture)
+ * Instances whose on-line mode ended (:stoppg + preview horizon elapsed) are left untouched. */
+int wg_herdt_mpc_run_batch(wg_ctx *ctx, int mem, int B, int nsteps, wg_herdt_mpc_state *states,
+                           const double *vel_ref, wg_herdt_tick *ticks, wg_herdt_mpc_step *steps,
+                           wg_herdt_qp_input *qp_in);
+
 #ifdef __cplusplus
 }
 #endif

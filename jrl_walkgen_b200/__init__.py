@@ -13,11 +13,14 @@ import numpy as np
 
 from . import _capi
 from ._capi import (MODE_WITH_INITIALPOS, MODE_WITHOUT_INITIALPOS, WG_MEM_DEVICE, WG_MEM_HOST,
-                    HerdtParams, PreviewGains, WalkgenError)
+                    HerdtMpcParams, HerdtParams, PreviewGains, WalkgenError)
 
 QP_INPUT_DTYPE, QP_OUTPUT_DTYPE = _capi.herdt_dtypes()
+FOOT_DTYPE, TICK_DTYPE, MPC_STATE_DTYPE, MPC_STEP_DTYPE = _capi.herdt_mpc_dtypes()
+TICKS_PER_STEP = _capi.HERDT_TICKS_PER_STEP
 
-__all__ = ["Context", "PreviewPlan", "preview_gains", "herdt_default_params", "HerdtParams", "QP_INPUT_DTYPE",
+__all__ = ["Context", "PreviewPlan", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
+           "FOOT_DTYPE", "TICK_DTYPE", "MPC_STATE_DTYPE", "MPC_STEP_DTYPE", "TICKS_PER_STEP", "QP_INPUT_DTYPE",
            "QP_OUTPUT_DTYPE", "WalkgenError", "device_count",
            "MODE_WITH_INITIALPOS", "MODE_WITHOUT_INITIALPOS", "WG_MEM_HOST", "WG_MEM_DEVICE"]
 
@@ -40,6 +43,13 @@ def herdt_default_params(sole_length=0.25, sole_width=0.14) -> HerdtParams:
     (the reference reads it from the robot model; 0.25 x 0.14 m is the sample robot's, fitted from the datref)."""
     p = HerdtParams()
     _capi.load().wg_herdt_default_params(sole_length, sole_width, C.byref(p))
+    return p
+
+
+def herdt_mpc_default_params() -> HerdtMpcParams:
+    """Constants of ZMPVelocityReferencedQP's ctor and the TestHerdt2010 script (step timing 0.7/0.1 s)."""
+    p = HerdtMpcParams()
+    _capi.load().wg_herdt_mpc_default_params(C.byref(p))
     return p
 
 
@@ -194,6 +204,46 @@ class Context:
             return outputs
         self._check(self.lib.wg_herdt_qp_solve_batch(self.h, mem, int(count), _ptr(inputs), _ptr(outputs)))
         return outputs
+
+
+    # ---- Herdt2010 closed loop -----------------------------------------------------------------
+    def herdt_mpc_set_params(self, params: HerdtMpcParams = None):
+        if not hasattr(self, "herdt_params"):
+            self.herdt_set_params()
+        self.herdt_mpc_params = params or herdt_mpc_default_params()
+        self._check(self.lib.wg_herdt_mpc_set_params(self.h, C.byref(self.herdt_mpc_params)))
+
+    def herdt_mpc_init(self, B, init9=(0.0316055, 0.0, 0.7116911, 0.0, 0.09, 0.0, 0.0, -0.09, 0.0), device=False):
+        """InitOnLine for B instances -> host array of MPC_STATE_DTYPE, or a DeviceBuffer when device=True.
+        init9: one start configuration (broadcast) or an array [B][9]."""
+        init = np.ascontiguousarray(init9, dtype=np.float64)
+        stride = 0 if init.ndim == 1 else 9
+        assert init.size == 9 or init.shape == (B, 9)
+        if device:
+            buf = self.alloc(B * MPC_STATE_DTYPE.itemsize)
+            self._check(self.lib.wg_herdt_mpc_init(self.h, WG_MEM_DEVICE, B, init.ctypes.data, stride, buf.ptr))
+            return buf
+        states = np.zeros(B, dtype=MPC_STATE_DTYPE)
+        self._check(self.lib.wg_herdt_mpc_init(self.h, WG_MEM_HOST, B, init.ctypes.data, stride, states.ctypes.data))
+        return states
+
+    def herdt_mpc_run(self, states, nsteps, vel_ref=None, ticks=False, steps=False, qp_in=False):
+        """wg_herdt_mpc_run_batch on host arrays: advances `states` in place; returns (ticks, steps, qp_in)
+        arrays for the outputs requested (else None)."""
+        assert states.dtype == MPC_STATE_DTYPE and states.flags["C_CONTIGUOUS"]
+        B = len(states)
+        ref = None if vel_ref is None else np.ascontiguousarray(np.broadcast_to(vel_ref, (B, 3)), dtype=np.float64)
+        t = np.zeros((B, nsteps * TICKS_PER_STEP), dtype=TICK_DTYPE) if ticks else None
+        s = np.zeros((B, nsteps), dtype=MPC_STEP_DTYPE) if steps else None
+        q = np.zeros(B, dtype=QP_INPUT_DTYPE) if qp_in else None
+        self._check(self.lib.wg_herdt_mpc_run_batch(self.h, WG_MEM_HOST, B, int(nsteps), states.ctypes.data, _ptr(ref),
+                                                    _ptr(t), _ptr(s), _ptr(q)))
+        return t, s, q
+
+    def herdt_mpc_run_device(self, d_states, B, nsteps, d_vel_ref=None, d_ticks=None, d_steps=None, d_qp_in=None):
+        """Device-resident form (asynchronous on the context stream)."""
+        self._check(self.lib.wg_herdt_mpc_run_batch(self.h, WG_MEM_DEVICE, int(B), int(nsteps), _ptr(d_states),
+                                                    _ptr(d_vel_ref), _ptr(d_ticks), _ptr(d_steps), _ptr(d_qp_in)))
 
 
 class PreviewPlan:

@@ -62,7 +62,17 @@ class HerdtParams(C.Structure):
                 ("lipm_T", C.c_double)]
 
 
+class HerdtMpcParams(C.Structure):
+    """Mirror of wg_herdt_mpc_params."""
+    _fields_ = [("Ts", C.c_double), ("time_buffer", C.c_double), ("step_period", C.c_double),
+                ("ds_period", C.c_double), ("dsss_period", C.c_double), ("t_single", C.c_double),
+                ("t_double", C.c_double), ("step_height", C.c_double), ("hip_lower", C.c_double * 2),
+                ("hip_upper", C.c_double * 2), ("foot_vel_limit", C.c_double), ("hip_acc_limit", C.c_double),
+                ("feet_cross_limit", C.c_double), ("nb_steps_ssds", C.c_int32), ("pad_", C.c_int32)]
+
+
 HERDT_N = 16
+HERDT_TICKS_PER_STEP = 20
 HERDT_MAX_VARS = 36
 HERDT_MAX_ROWS = 75
 
@@ -86,6 +96,32 @@ def herdt_dtypes():
         ("com_next_y", "f8", 3), ("n_vars", "i4"), ("n_rows", "i4"), ("fail", "i4"), ("iterations", "i4")])
     assert qin.itemsize == 784 and qout.itemsize == 960
     return qin, qout
+
+
+def herdt_mpc_dtypes():
+    """numpy mirrors of wg_herdt_foot_sample, wg_herdt_tick (256 B), wg_herdt_mpc_state, wg_herdt_mpc_step (144 B)."""
+    np = _np()
+    foot = np.dtype([("x", "f8"), ("y", "f8"), ("z", "f8"), ("theta", "f8"), ("dx", "f8"), ("dy", "f8"),
+                     ("dz", "f8"), ("dtheta", "f8"), ("ddx", "f8"), ("ddy", "f8")])
+    tick = np.dtype([("com_x", "f8", 3), ("com_y", "f8", 3), ("com_z", "f8"), ("yaw", "f8"), ("dyaw", "f8"),
+                     ("zmp_x", "f8"), ("zmp_y", "f8"), ("pad_", "f8"), ("left", foot), ("right", foot)])
+    state = np.dtype([
+        ("clock", "f8"), ("upper_time_limit", "f8"), ("time_to_stop", "f8"), ("new_ref", "f8", 3), ("ref", "f8", 3),
+        ("com_x", "f8", 3), ("com_y", "f8", 3), ("com_height", "f8"), ("trunk_yaw", "f8", 3),
+        ("trunk_t_yaw", "f8", 2), ("support_time_passed", "f8"), ("sup_time_limit", "f8"),
+        ("sup_start_time", "f8"), ("sup_x", "f8"), ("sup_y", "f8"), ("sup_yaw", "f8"), ("poly_z", "f8", 5),
+        ("com_front", "f8", 6), ("com_back", "f8", 11), ("foot", foot, (2, 3)),
+        ("sup_phase", "i4"), ("sup_foot", "i4"), ("sup_steps_left", "i4"), ("sup_step_number", "i4"),
+        ("sup_nb_instants", "i4"), ("sup_changed", "i4"), ("in_translation", "i4"), ("in_rotation", "i4"),
+        ("post_rotation", "i4"), ("steps_after_rotation", "i4"), ("fsm_support_foot", "i4"),
+        ("online_mode", "i4"), ("ending_phase", "i4"), ("running", "i4"), ("nb_steps_ssds", "i4"),
+        ("qp_count", "i4"), ("fail_count", "i4"), ("last_fail", "i4"), ("iterations_total", "i8")])
+    step = np.dtype([("time", "f8"), ("com_x", "f8", 3), ("com_y", "f8", 3), ("jerk_x", "f8"), ("jerk_y", "f8"),
+                     ("next_foot_x", "f8"), ("next_foot_y", "f8"), ("sup_x", "f8"), ("sup_y", "f8"),
+                     ("sup_yaw", "f8"), ("sup_foot", "i4"), ("sup_phase", "i4"), ("n_prw_steps", "i4"),
+                     ("fail", "i4"), ("iterations", "i4"), ("n_active", "i4"), ("pad_", "i4", 2)])
+    assert foot.itemsize == 80 and tick.itemsize == 256 and step.itemsize == 144 and state.itemsize == 952
+    return foot, tick, state, step
 
 
 # name -> (restype, argtypes); also the list checked against include/walkgen_b200.h by the tests
@@ -125,6 +161,11 @@ SIGNATURES = {
     "wg_herdt_default_params": (None, [C.c_double, C.c_double, C.POINTER(HerdtParams)]),
     "wg_herdt_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtParams)]),
     "wg_herdt_qp_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wg_herdt_mpc_default_params": (None, [C.POINTER(HerdtMpcParams)]),
+    "wg_herdt_mpc_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtMpcParams)]),
+    "wg_herdt_mpc_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "wg_herdt_mpc_run_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

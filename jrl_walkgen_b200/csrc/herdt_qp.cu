@@ -137,7 +137,7 @@ herdt_qp_kernel(int B, const Consts *__restrict__ Cp, const wg_herdt_qp_input *_
     }
     for (int e = lane; e < WG_HERDT_MAX_ROWS + 1; e += 32) o.lagr[e] = 0.0;
     __syncwarp();
-    if (lane < q && !r.fail) o.lagr[1 + s.W[lane]] = s.u[lane];
+    for (int j = lane; j < q && !r.fail; j += 32) o.lagr[1 + s.W[j]] = s.u[j];
     if (lane < 6) {
       // LinearizedInvertedPendulum2D::OneIteration with T = QP period (LinearizedInvertedPendulum2D.cpp:230-264)
       const int ax = lane / 3, c = lane % 3;

@@ -29,7 +29,7 @@ namespace herdt {
 constexpr int N = WG_HERDT_N;        // 16
 constexpr int NPTS = N + 2;          // 18 points
 constexpr int MAXM = 4 * N + 10;     // 74 real rows
-constexpr int QMAX = 32;             // active-set capacity (one lane per active row)
+constexpr int QMAX = 40;             // active-set capacity (> n = 36 independent rows; two slots per lane)
 constexpr int TRI = QMAX * (QMAX + 1) / 2;
 
 // Constants of one (T, h, weights) parameter set, computed once on the host in extended precision.
@@ -283,7 +283,8 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
   }
   __syncwarp();
 
-  // ---- dual active-set iterations
+  // ---- dual active-set iterations.  Active row j lives in slot j / 32 of lane j % 32 (QMAX = 40 > n = 36, the
+  // largest number of linearly independent rows).
   const double tol = 1e-12;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   int q = 0;
@@ -335,29 +336,40 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         }
         __syncwarp();
         points_from_primal(s, C, s.jr, s.ff, ns, Vf, Vcf, s.PX, s.PY, lane);
-        double sj = 0.0, vj = 0.0;
-        if (lane < q) {
-          const int k = s.W[lane], kp = s.cpt[lane];
-          sj = s.a[k] * s.PX[kp] + s.b[k] * s.PY[kp] + s.d[k];
-          vj = fabs(sj) * s.inrm[k];
+        double vmax = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int j = lane + 32 * sl;
+          if (j < q) {
+            const int k = s.W[j], kp = s.cpt[j];
+            const double sj = s.a[k] * s.PX[kp] + s.b[k] * s.PY[kp] + s.d[k];
+            s.gv[j] = sj;
+            vmax = fmax(vmax, fabs(sj) * s.inrm[k]);
+          }
         }
-        double vmax = vj;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         if (!(vmax > 1e-14) || pass >= 3) break;
-        s.gv[lane] = sj;
         __syncwarp();
-        double wi_ = 0.0;
-        if (lane < q) {
-          const double *Tr = s.T + tri(lane);
-          for (int j = 0; j <= lane; ++j) wi_ = fma(Tr[j], s.gv[j], wi_);
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int j = lane + 32 * sl;
+          if (j < q) {
+            const double *Tr = s.T + tri(j);
+            double wv_ = 0.0;
+            for (int e = 0; e <= j; ++e) wv_ = fma(Tr[e], s.gv[e], wv_);
+            s.w[j] = wv_;
+          }
         }
-        s.w[lane] = wi_;
         __syncwarp();
-        if (lane < q) {
-          double rj = 0.0;
-          for (int r = lane; r < q; ++r) rj = fma(s.T[tri(r) + lane], s.w[r], rj);
-          s.u[lane] -= rj;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int j = lane + 32 * sl;
+          if (j < q) {
+            double rj = 0.0;
+            for (int r = j; r < q; ++r) rj = fma(s.T[tri(r) + j], s.w[r], rj);
+            s.u[j] -= rj;
+          }
         }
         __syncwarp();
       }
@@ -386,32 +398,55 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
       if (++res.iterations > maxit) { res.fail = 1; done = true; break; }   // QLD ifail 1: too many iterations
       if (q >= QMAX) { res.fail = 3; done = true; break; }                  // active-set capacity exhausted
       // gv_j = N_Wj' H^-1 N_p
-      double gvj = 0.0;
-      if (lane < q) { const int k = s.W[lane]; gvj = (s.a[k] * ap + s.b[k] * bp) * s.Gam[s.cpt[lane]][pp]; }
-      s.gv[lane] = gvj;
-      __syncwarp();
-      double wi_ = 0.0;
-      if (lane < q) {
-        const double *Tr = s.T + tri(lane);
-        for (int j = 0; j <= lane; ++j) wi_ = fma(Tr[j], s.gv[j], wi_);
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int j = lane + 32 * sl;
+        if (j < q) { const int k = s.W[j]; s.gv[j] = (s.a[k] * ap + s.b[k] * bp) * s.Gam[s.cpt[j]][pp]; }
       }
-      s.w[lane] = wi_;
       __syncwarp();
-      double rj = 0.0;
-      if (lane < q)
-        for (int r = lane; r < q; ++r) rj = fma(s.T[tri(r) + lane], s.w[r], rj);
-      const double delta = Mpp - warp_sum(wi_ * wi_);
+      double wsq = 0.0;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int j = lane + 32 * sl;
+        if (j < q) {
+          const double *Tr = s.T + tri(j);
+          double wv_ = 0.0;
+          for (int e = 0; e <= j; ++e) wv_ = fma(Tr[e], s.gv[e], wv_);
+          s.w[j] = wv_;
+          wsq = fma(wv_, wv_, wsq);
+        }
+      }
+      __syncwarp();
+      double rj[2] = {0.0, 0.0};
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int j = lane + 32 * sl;
+        if (j < q)
+          for (int r = j; r < q; ++r) rj[sl] = fma(s.T[tri(r) + j], s.w[r], rj[sl]);
+      }
+      const double delta = Mpp - warp_sum(wsq);
       // step lengths
       double t1 = INF; int l = 0x7fffffff;
-      if (lane < q && rj > 0.0) { t1 = s.u[lane] / rj; l = lane; }
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int j = lane + 32 * sl;
+        if (j < q && rj[sl] > 0.0) {
+          const double tj = s.u[j] / rj[sl];
+          if (tj < t1) { t1 = tj; l = j; }
+        }
+      }
       warp_argmin(t1, l);
       const double sp = ap * s.PX[pp] + bp * s.PY[pp] + s.d[p];
       const double t2 = (delta > 1e-13 * Mpp) ? -sp / delta : INF;
       const double tt = fmin(t1, t2);
       if (!(tt < INF)) { res.fail = 2; done = true; break; }   // infeasible (QLD ifail 2 family)
       // direction in point space and step
-      if (lane < q) { const int k = s.W[lane]; s.ca[lane] = -rj * s.a[k]; s.cb[lane] = -rj * s.b[k]; }
-      if (lane == q) { s.ca[q] = ap; s.cb[q] = bp; s.cpt[q] = pp; }
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int j = lane + 32 * sl;
+        if (j < q) { const int k = s.W[j]; s.ca[j] = -rj[sl] * s.a[k]; s.cb[j] = -rj[sl] * s.b[k]; }
+      }
+      if (lane == 0) { s.ca[q] = ap; s.cb[q] = bp; s.cpt[q] = pp; }
       __syncwarp();
       if (lane < npts) {
         double dx = 0.0, dy = 0.0;
@@ -422,14 +457,22 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         s.PX[lane] = fma(tt, dx, s.PX[lane]);
         s.PY[lane] = fma(tt, dy, s.PY[lane]);
       }
-      if (lane < q) s.u[lane] = fma(-tt, rj, s.u[lane]);
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int j = lane + 32 * sl;
+        if (j < q) s.u[j] = fma(-tt, rj[sl], s.u[j]);
+      }
       up += tt;
       __syncwarp();
       if (t2 <= t1) {
         // full step: row p becomes active; append a row to T (inverse Cholesky factor of the active Gram matrix)
         const double dd = sqrt(delta);
-        if (lane < q) s.T[tri(q) + lane] = -rj / dd;
-        if (lane == q) { s.T[tri(q) + q] = 1.0 / dd; s.W[q] = p; s.u[q] = up; }
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int j = lane + 32 * sl;
+          if (j < q) s.T[tri(q) + j] = -rj[sl] / dd;
+        }
+        if (lane == 0) { s.T[tri(q) + q] = 1.0 / dd; s.W[q] = p; s.u[q] = up; }
         if ((p & 31) == lane) actbits |= 1u << (p >> 5);
         ++q;
         __syncwarp();
@@ -440,25 +483,48 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
       {
         const int kl = s.W[l];
         if ((kl & 31) == lane) actbits &= ~(1u << (kl >> 5));
-        double rowl = (lane <= l) ? s.T[tri(l) + lane] : 0.0;
+        double rowl[2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int j = lane + 32 * sl;
+          rowl[sl] = (j <= l) ? s.T[tri(l) + j] : 0.0;
+        }
         __syncwarp();
         for (int r = l + 1; r < q; ++r) {
-          const double x2 = (lane <= r) ? s.T[tri(r) + lane] : 0.0;
-          const double p1 = __shfl_sync(0xffffffffu, rowl, l), p2 = __shfl_sync(0xffffffffu, x2, l);
+          double x2[2];
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const int j = lane + 32 * sl;
+            x2[sl] = (j <= r) ? s.T[tri(r) + j] : 0.0;
+          }
+          const double p1 = __shfl_sync(0xffffffffu, (l >> 5) ? rowl[1] : rowl[0], l & 31);
+          const double p2 = __shfl_sync(0xffffffffu, (l >> 5) ? x2[1] : x2[0], l & 31);
           const double hyp = sqrt(p1 * p1 + p2 * p2);
           const double c_ = p1 / hyp, s_ = p2 / hyp;
-          const double nl = c_ * rowl + s_ * x2, nr = c_ * x2 - s_ * rowl;
-          rowl = nl;
           __syncwarp();
-          if (lane < l) s.T[tri(r - 1) + lane] = nr;
-          else if (lane > l && lane <= r) s.T[tri(r - 1) + lane - 1] = nr;
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const int j = lane + 32 * sl;
+            const double nl = c_ * rowl[sl] + s_ * x2[sl], nr = c_ * x2[sl] - s_ * rowl[sl];
+            rowl[sl] = nl;
+            if (j < l) s.T[tri(r - 1) + j] = nr;
+            else if (j > l && j <= r) s.T[tri(r - 1) + j - 1] = nr;
+          }
           __syncwarp();
         }
-        const int Wn = (lane > l && lane < q) ? s.W[lane] : 0;
-        const int cn = (lane > l && lane < q) ? s.cpt[lane] : 0;
-        const double un = (lane > l && lane < q) ? s.u[lane] : 0.0;
+        int Wn[2], cn[2]; double un[2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int j = lane + 32 * sl;
+          const bool mv = (j > l && j < q);
+          Wn[sl] = mv ? s.W[j] : 0; cn[sl] = mv ? s.cpt[j] : 0; un[sl] = mv ? s.u[j] : 0.0;
+        }
         __syncwarp();
-        if (lane > l && lane < q) { s.W[lane - 1] = Wn; s.cpt[lane - 1] = cn; s.u[lane - 1] = un; }
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int j = lane + 32 * sl;
+          if (j > l && j < q) { s.W[j - 1] = Wn[sl]; s.cpt[j - 1] = cn[sl]; s.u[j - 1] = un[sl]; }
+        }
         --q;
         __syncwarp();
       }

@@ -278,7 +278,7 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
                      double *__restrict__ zmp)
 {
   extern __shared__ double2 sp[];             // padded tile of (px,py), then the scan exchange area
-  __shared__ double s_x[FIR_THREADS][8];      // scan exchange (x axis 0..3, y axis 4..7)
+  __shared__ double s_tot[FIR_THREADS / 32][8];   // warp totals of the scan (x axis 0..3, y axis 4..7)
   __shared__ double s_carry[8];
   const int b = order[blockIdx.x];
   const int64_t o = offsets[b];
@@ -363,18 +363,20 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
     // state entering warp w: W_w = M^256 W_{w-1} + T_{w-1}, W_0 = 0 (the carried tile state is inside thread 0's
     // local pass); lane j then adds M^(8 (j+1)) W_w, built from the bits of j+1 with the same constant matrices.
     if (lane == 31) {
-      double *n = s_x[t >> 5];
+      double *n = s_tot[t >> 5];
       n[0] = cx.x0; n[1] = cx.x1; n[2] = cx.x2; n[3] = cx.s;
       n[4] = cy.x0; n[5] = cy.x1; n[6] = cy.x2; n[7] = cy.s;
     }
     __syncthreads();
+    // ---- (2c) true start state of this thread = inclusive result of thread t-1
+    Axis sx, sy;
     {
       const int w = t >> 5;
-      Axis vx, vy;
+      Axis vx, vy;                         // W_w, the state entering this warp
       vx.x0 = vx.x1 = vx.x2 = vx.s = 0.0;
       vy.x0 = vy.x1 = vy.x2 = vy.s = 0.0;
       for (int v = 0; v < w; ++v) {        // W_{v+1} = M^256 W_v + T_v
-        const double *n = s_x[v];
+        const double *n = s_tot[v];
         Axis nx, ny;
         nx.x0 = n[0]; nx.x1 = n[1]; nx.x2 = n[2]; nx.s = n[3];
         ny.x0 = n[4]; ny.x1 = n[5]; ny.x2 = n[6]; ny.s = n[7];
@@ -382,6 +384,7 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
         scan_combine(ny, Pm[5], vy.x0, vy.x1, vy.x2, vy.s);
         vx = nx; vy = ny;
       }
+      const Axis wx_in = vx, wy_in = vy;
       if (w > 0) {
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
@@ -397,17 +400,14 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
         cx.x0 += vx.x0; cx.x1 += vx.x1; cx.x2 += vx.x2; cx.s += vx.s;
         cy.x0 += vy.x0; cy.x1 += vy.x1; cy.x2 += vy.x2; cy.s += vy.s;
       }
-    }
-    __syncthreads();
-    // ---- (2c) true start state of this thread = inclusive result of thread t-1
-    s_x[t][0] = cx.x0; s_x[t][1] = cx.x1; s_x[t][2] = cx.x2; s_x[t][3] = cx.s;
-    s_x[t][4] = cy.x0; s_x[t][5] = cy.x1; s_x[t][6] = cy.x2; s_x[t][7] = cy.s;
-    __syncthreads();
-    Axis sx = inx, sy = iny;
-    if (t > 0) {
-      const double *n = s_x[t - 1];
-      sx.x0 = n[0]; sx.x1 = n[1]; sx.x2 = n[2]; sx.s = n[3];
-      sy.x0 = n[4]; sy.x1 = n[5]; sy.x2 = n[6]; sy.s = n[7];
+      sx.x0 = __shfl_up_sync(0xffffffffu, cx.x0, 1); sx.x1 = __shfl_up_sync(0xffffffffu, cx.x1, 1);
+      sx.x2 = __shfl_up_sync(0xffffffffu, cx.x2, 1); sx.s = __shfl_up_sync(0xffffffffu, cx.s, 1);
+      sy.x0 = __shfl_up_sync(0xffffffffu, cy.x0, 1); sy.x1 = __shfl_up_sync(0xffffffffu, cy.x1, 1);
+      sy.x2 = __shfl_up_sync(0xffffffffu, cy.x2, 1); sy.s = __shfl_up_sync(0xffffffffu, cy.s, 1);
+      if (lane == 0) {
+        if (w == 0) { sx = inx; sy = iny; }
+        else { sx = wx_in; sy = wy_in; }
+      }
     }
     // ---- (2d) final pass: emit CoM / ZMP of the valid ticks
     const int k0 = start + FIR_R * t;
@@ -427,11 +427,11 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
           q[2] = make_double2(sy.x1, sy.x2);
         }
         if (pz) *reinterpret_cast<double2 *>(pz + 2 * r) = make_double2(zx, zy);
-        if (k0 + r == last) {
-          s_carry[0] = sx.x0; s_carry[1] = sx.x1; s_carry[2] = sx.x2; s_carry[6] = sx.s;
-          s_carry[3] = sy.x0; s_carry[4] = sy.x1; s_carry[5] = sy.x2; s_carry[7] = sy.s;
-        }
       }
+    }
+    if (k0 <= last && last < k0 + FIR_R) {   // the thread that ran the tile's last valid tick carries the state
+      s_carry[0] = sx.x0; s_carry[1] = sx.x1; s_carry[2] = sx.x2; s_carry[6] = sx.s;
+      s_carry[3] = sy.x0; s_carry[4] = sy.x1; s_carry[5] = sy.x2; s_carry[7] = sy.s;
     }
   }
   __syncthreads();

@@ -39,6 +39,8 @@ struct wg_ctx {
   double *d_previewF = nullptr;  // device copy of F padded with zeros
   // Herdt constants (herdt_qp.cu)
   void *herdt = nullptr;
+  // Herdt closed loop (herdt_mpc.cu)
+  void *herdt_mpc = nullptr;
   // PLDP constants (pldp.cu)
   void *pldp = nullptr;
 };

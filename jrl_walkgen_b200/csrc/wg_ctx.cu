@@ -2,6 +2,7 @@
 #include "wg_common.h"
 
 extern void wg_herdt_release(wg_ctx *ctx);
+extern void wg_herdt_mpc_release(wg_ctx *ctx);
 extern void wg_pldp_release(wg_ctx *ctx);
 
 extern "C" {
@@ -39,6 +40,7 @@ int wg_ctx_destroy(wg_ctx *ctx)
   if (!ctx) return WG_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  wg_herdt_mpc_release(ctx);
   wg_herdt_release(ctx);
   wg_pldp_release(ctx);
   if (ctx->d_previewF) cudaFree(ctx->d_previewF);
