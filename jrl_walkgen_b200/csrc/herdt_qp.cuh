@@ -52,7 +52,7 @@ struct Work {
   double Gam[NPTS][NPTS];
   double a[MAXM + 2], b[MAXM + 2], d[MAXM + 2], inrm[MAXM + 2];
   double T[TRI];
-  double u[QMAX], gv[QMAX], w[QMAX], ca[QMAX + 1], cb[QMAX + 1];
+  double u[QMAX], gv[QMAX], w[QMAX], r[QMAX], ca[QMAX + 1], cb[QMAX + 1];
   double theta[NPTS][2], sigma[NPTS][2];
   double g[2][N], j0[2][N], Z[2][N], jr[2][N];
   double f0[2][2], ff[2][2];
@@ -88,7 +88,7 @@ __device__ __forceinline__ void warp_argmin(double &v, int &idx)
 
 // RelativeFeetInequalities::set_vertices + convex_hull_t::rotate + compute_linear_system for one hull
 // (relative-feet-inequalities.cpp:186-234, 265-319; privatepgtypes.cpp:152-180).
-__device__ inline void hull_rows(const wg_herdt_params &P, int foot, int phase, double yaw, bool cop, int sign_foot,
+static __device__ __noinline__ void hull_rows(const wg_herdt_params &P, int foot, int phase, double yaw, bool cop, int sign_foot,
                                  double *A, double *B, double *D)
 {
   double X[5], Y[5];
@@ -132,7 +132,7 @@ __device__ inline void hull_rows(const wg_herdt_params &P, int foot, int phase, 
 // Points from a primal iterate (jerks in jr[axis][16], foot placements in ff[axis][2]):
 //   P[i]   = -(Uz j)_i + (V f)_i - (Sz c)_i + Vc_i      (generator-vel-ref.cpp:394-447, rows of the CoP constraints)
 //   P[N+s] = -(Vf f)_s + Vcf_s                            (generator-vel-ref.cpp:450-474)
-__device__ inline void points_from_primal(Work &s, const Consts &C, const double (*jr)[N], const double (*ff)[2],
+static __device__ __noinline__ void points_from_primal(Work &s, const Consts &C, const double (*jr)[N], const double (*ff)[2],
                                           int ns, const double Vf[2][2], const double Vcf[2][2], double *outX,
                                           double *outY, int lane)
 {
@@ -283,8 +283,9 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
   }
   __syncwarp();
 
-  // ---- dual active-set iterations.  Active row j lives in slot j / 32 of lane j % 32 (QMAX = 40 > n = 36, the
-  // largest number of linearly independent rows).
+  // ---- dual active-set iterations.  Per-row quantities of the active set (<= QMAX = 40 > n = 36 independent rows)
+  // live in shared memory and are processed lane-strided (j = lane, lane + 32); the loops are kept rolled on purpose:
+  // the iteration body has to stay resident in the instruction cache.
   const double tol = 1e-12;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   int q = 0;
@@ -296,7 +297,7 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
     // most violated row, normalised by its Euclidean norm (the pivoting rule of qld.cpp:1255-1331)
     double best = INF;
     int bi = 0x7fffffff;
-#pragma unroll
+#pragma unroll 1
     for (int t = 0; t < 3; ++t) {
       const int k = lane + 32 * t;
       if (k < m && !((actbits >> t) & 1u)) {
@@ -311,21 +312,25 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
       // refine the multipliers so that the active rows hold on points recomputed from that solution
       // (x = x0 + H^-1 N u goes through the precomputed inverse; one or two Newton steps on the dual,
       // du = -(N'H^-1 N)^-1 s_active = -T'T s_active, remove its rounding error)
+#pragma unroll 1
       for (int pass = 0;; ++pass) {
         if (lane < NPTS) {
           double wx = 0.0, wy = 0.0;
+#pragma unroll 1
           for (int j = 0; j < q; ++j)
             if (s.cpt[j] == lane) { const int k = s.W[j]; wx = fma(s.u[j], s.a[k], wx); wy = fma(s.u[j], s.b[k], wy); }
           s.wpt[0][lane] = wx; s.wpt[1][lane] = wy;
         }
         __syncwarp();
         double sg0 = 0.0, sg1 = 0.0;
+#pragma unroll 1
         for (int k = 0; k < npts; ++k) {
           const double wk = s.wpt[axis][k];
           sg0 = fma(s.sigma[k][0], wk, sg0); sg1 = fma(s.sigma[k][1], wk, sg1);
         }
         {
           double acc = 0.0;
+#pragma unroll 4
           for (int k = 0; k < N; ++k) {
             const int snk = s.in.sup_step[k + 1];
             const double corr = (snk == 1) ? sg0 : (snk == 2 ? sg1 : 0.0);
@@ -337,45 +342,38 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         __syncwarp();
         points_from_primal(s, C, s.jr, s.ff, ns, Vf, Vcf, s.PX, s.PY, lane);
         double vmax = 0.0;
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int j = lane + 32 * sl;
-          if (j < q) {
-            const int k = s.W[j], kp = s.cpt[j];
-            const double sj = s.a[k] * s.PX[kp] + s.b[k] * s.PY[kp] + s.d[k];
-            s.gv[j] = sj;
-            vmax = fmax(vmax, fabs(sj) * s.inrm[k]);
-          }
+#pragma unroll 1
+        for (int j = lane; j < q; j += 32) {
+          const int k = s.W[j], kp = s.cpt[j];
+          const double sj = s.a[k] * s.PX[kp] + s.b[k] * s.PY[kp] + s.d[k];
+          s.gv[j] = sj;
+          vmax = fmax(vmax, fabs(sj) * s.inrm[k]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         if (!(vmax > 1e-14) || pass >= 3) break;
         __syncwarp();
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int j = lane + 32 * sl;
-          if (j < q) {
-            const double *Tr = s.T + tri(j);
-            double wv_ = 0.0;
-            for (int e = 0; e <= j; ++e) wv_ = fma(Tr[e], s.gv[e], wv_);
-            s.w[j] = wv_;
-          }
+#pragma unroll 1
+        for (int j = lane; j < q; j += 32) {
+          const double *Tr = s.T + tri(j);
+          double wv_ = 0.0;
+#pragma unroll 4
+          for (int e = 0; e <= j; ++e) wv_ = fma(Tr[e], s.gv[e], wv_);
+          s.w[j] = wv_;
         }
         __syncwarp();
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int j = lane + 32 * sl;
-          if (j < q) {
-            double rj = 0.0;
-            for (int r = j; r < q; ++r) rj = fma(s.T[tri(r) + j], s.w[r], rj);
-            s.u[j] -= rj;
-          }
+#pragma unroll 1
+        for (int j = lane; j < q; j += 32) {
+          double rj = 0.0;
+#pragma unroll 4
+          for (int r = j; r < q; ++r) rj = fma(s.T[tri(r) + j], s.w[r], rj);
+          s.u[j] -= rj;
         }
         __syncwarp();
       }
       // re-evaluate the inactive rows on those points
       double worst = INF; int wi = 0x7fffffff;
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < 3; ++t) {
         const int k = lane + 32 * t;
         if (k < m && !((actbits >> t) & 1u)) {
@@ -394,62 +392,65 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
     const double ap = s.a[p], bp = s.b[p];
     const double Mpp = (ap * ap + bp * bp) * s.Gam[pp][pp];
     double up = 0.0;
+#pragma unroll 1
     while (true) {
       if (++res.iterations > maxit) { res.fail = 1; done = true; break; }   // QLD ifail 1: too many iterations
       if (q >= QMAX) { res.fail = 3; done = true; break; }                  // active-set capacity exhausted
       // gv_j = N_Wj' H^-1 N_p
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int j = lane + 32 * sl;
-        if (j < q) { const int k = s.W[j]; s.gv[j] = (s.a[k] * ap + s.b[k] * bp) * s.Gam[s.cpt[j]][pp]; }
+#pragma unroll 1
+      for (int j = lane; j < q; j += 32) {
+        const int k = s.W[j];
+        s.gv[j] = (s.a[k] * ap + s.b[k] * bp) * s.Gam[s.cpt[j]][pp];
       }
       __syncwarp();
       double wsq = 0.0;
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int j = lane + 32 * sl;
-        if (j < q) {
-          const double *Tr = s.T + tri(j);
-          double wv_ = 0.0;
-          for (int e = 0; e <= j; ++e) wv_ = fma(Tr[e], s.gv[e], wv_);
-          s.w[j] = wv_;
-          wsq = fma(wv_, wv_, wsq);
-        }
+#pragma unroll 1
+      for (int j = lane; j < q; j += 32) {
+        const double *Tr = s.T + tri(j);
+        double w0 = 0.0, w1 = 0.0;
+        int e = 0;
+#pragma unroll 2
+        for (; e + 1 <= j; e += 2) { w0 = fma(Tr[e], s.gv[e], w0); w1 = fma(Tr[e + 1], s.gv[e + 1], w1); }
+        if (e <= j) w0 = fma(Tr[e], s.gv[e], w0);
+        const double wv_ = w0 + w1;
+        s.w[j] = wv_;
+        wsq = fma(wv_, wv_, wsq);
       }
       __syncwarp();
-      double rj[2] = {0.0, 0.0};
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int j = lane + 32 * sl;
-        if (j < q)
-          for (int r = j; r < q; ++r) rj[sl] = fma(s.T[tri(r) + j], s.w[r], rj[sl]);
-      }
-      const double delta = Mpp - warp_sum(wsq);
-      // step lengths
       double t1 = INF; int l = 0x7fffffff;
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int j = lane + 32 * sl;
-        if (j < q && rj[sl] > 0.0) {
-          const double tj = s.u[j] / rj[sl];
+#pragma unroll 1
+      for (int j = lane; j < q; j += 32) {
+        double r0 = 0.0, r1 = 0.0;
+        int r = j;
+#pragma unroll 2
+        for (; r + 1 < q; r += 2) { r0 = fma(s.T[tri(r) + j], s.w[r], r0); r1 = fma(s.T[tri(r + 1) + j], s.w[r + 1], r1); }
+        if (r < q) r0 = fma(s.T[tri(r) + j], s.w[r], r0);
+        const double rj = r0 + r1;
+        s.r[j] = rj;
+        if (rj > 0.0) {
+          const double tj = s.u[j] / rj;
           if (tj < t1) { t1 = tj; l = j; }
         }
       }
+      const double delta = Mpp - warp_sum(wsq);
       warp_argmin(t1, l);
       const double sp = ap * s.PX[pp] + bp * s.PY[pp] + s.d[p];
       const double t2 = (delta > 1e-13 * Mpp) ? -sp / delta : INF;
       const double tt = fmin(t1, t2);
       if (!(tt < INF)) { res.fail = 2; done = true; break; }   // infeasible (QLD ifail 2 family)
       // direction in point space and step
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int j = lane + 32 * sl;
-        if (j < q) { const int k = s.W[j]; s.ca[j] = -rj[sl] * s.a[k]; s.cb[j] = -rj[sl] * s.b[k]; }
+#pragma unroll 1
+      for (int j = lane; j < q; j += 32) {
+        const int k = s.W[j];
+        const double rj = s.r[j];
+        s.ca[j] = -rj * s.a[k]; s.cb[j] = -rj * s.b[k];
+        s.u[j] = fma(-tt, rj, s.u[j]);
       }
       if (lane == 0) { s.ca[q] = ap; s.cb[q] = bp; s.cpt[q] = pp; }
       __syncwarp();
       if (lane < npts) {
         double dx = 0.0, dy = 0.0;
+#pragma unroll 2
         for (int j = 0; j <= q; ++j) {
           const double gm = s.Gam[lane][s.cpt[j]];
           dx = fma(gm, s.ca[j], dx); dy = fma(gm, s.cb[j], dy);
@@ -457,76 +458,56 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         s.PX[lane] = fma(tt, dx, s.PX[lane]);
         s.PY[lane] = fma(tt, dy, s.PY[lane]);
       }
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int j = lane + 32 * sl;
-        if (j < q) s.u[j] = fma(-tt, rj[sl], s.u[j]);
-      }
       up += tt;
       __syncwarp();
       if (t2 <= t1) {
         // full step: row p becomes active; append a row to T (inverse Cholesky factor of the active Gram matrix)
-        const double dd = sqrt(delta);
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int j = lane + 32 * sl;
-          if (j < q) s.T[tri(q) + j] = -rj[sl] / dd;
-        }
-        if (lane == 0) { s.T[tri(q) + q] = 1.0 / dd; s.W[q] = p; s.u[q] = up; }
+        const double idd = rsqrt(delta);
+#pragma unroll 1
+        for (int j = lane; j < q; j += 32) s.T[tri(q) + j] = -s.r[j] * idd;
+        if (lane == 0) { s.T[tri(q) + q] = idd; s.W[q] = p; s.u[q] = up; }
         if ((p & 31) == lane) actbits |= 1u << (p >> 5);
         ++q;
         __syncwarp();
         break;
       }
       // partial step: multiplier l reached zero -> drop row l.  Rotate rows (l, r), r > l, so that column l
-      // vanishes below row l, then delete row and column l.
+      // vanishes below row l, then delete row and column l.  s.w holds the rotating copy of row l.
       {
         const int kl = s.W[l];
         if ((kl & 31) == lane) actbits &= ~(1u << (kl >> 5));
-        double rowl[2];
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int j = lane + 32 * sl;
-          rowl[sl] = (j <= l) ? s.T[tri(l) + j] : 0.0;
-        }
+#pragma unroll 1
+        for (int j = lane; j < q; j += 32) s.w[j] = (j <= l) ? s.T[tri(l) + j] : 0.0;
         __syncwarp();
+#pragma unroll 1
         for (int r = l + 1; r < q; ++r) {
-          double x2[2];
-#pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            const int j = lane + 32 * sl;
-            x2[sl] = (j <= r) ? s.T[tri(r) + j] : 0.0;
-          }
-          const double p1 = __shfl_sync(0xffffffffu, (l >> 5) ? rowl[1] : rowl[0], l & 31);
-          const double p2 = __shfl_sync(0xffffffffu, (l >> 5) ? x2[1] : x2[0], l & 31);
-          const double hyp = sqrt(p1 * p1 + p2 * p2);
-          const double c_ = p1 / hyp, s_ = p2 / hyp;
+          const double *Tr = s.T + tri(r);
+          const double p1 = s.w[l], p2 = Tr[l];
+          const double ih = rsqrt(p1 * p1 + p2 * p2);
+          const double c_ = p1 * ih, s_ = p2 * ih;
           __syncwarp();
-#pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            const int j = lane + 32 * sl;
-            const double nl = c_ * rowl[sl] + s_ * x2[sl], nr = c_ * x2[sl] - s_ * rowl[sl];
-            rowl[sl] = nl;
-            if (j < l) s.T[tri(r - 1) + j] = nr;
-            else if (j > l && j <= r) s.T[tri(r - 1) + j - 1] = nr;
+          double *Tn = s.T + tri(r - 1);
+#pragma unroll 1
+          for (int j = lane; j <= r; j += 32) {
+            const double x1 = s.w[j], x2 = Tr[j];
+            s.w[j] = c_ * x1 + s_ * x2;
+            const double nr = c_ * x2 - s_ * x1;
+            if (j < l) Tn[j] = nr;
+            else if (j > l) Tn[j - 1] = nr;
           }
           __syncwarp();
         }
-        int Wn[2], cn[2]; double un[2];
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int j = lane + 32 * sl;
+#pragma unroll 1
+        for (int base = 0; base < q; base += 32) {
+          const int j = base + lane;
           const bool mv = (j > l && j < q);
-          Wn[sl] = mv ? s.W[j] : 0; cn[sl] = mv ? s.cpt[j] : 0; un[sl] = mv ? s.u[j] : 0.0;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int j = lane + 32 * sl;
-          if (j > l && j < q) { s.W[j - 1] = Wn[sl]; s.cpt[j - 1] = cn[sl]; s.u[j - 1] = un[sl]; }
+          const int Wn = mv ? s.W[j] : 0, cn = mv ? s.cpt[j] : 0;
+          const double un = mv ? s.u[j] : 0.0;
+          __syncwarp();
+          if (mv) { s.W[j - 1] = Wn; s.cpt[j - 1] = cn; s.u[j - 1] = un; }
+          __syncwarp();
         }
         --q;
-        __syncwarp();
       }
     }
   }
