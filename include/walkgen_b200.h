@@ -65,8 +65,7 @@ void wg_launch_count_reset(wg_ctx *ctx);
 /* Per-kernel CUDA-event profiler on the context stream.  Between wg_prof_begin(capacity = max number of
  * kernel launches to record) and wg_prof_end every kernel this library launches is bracketed by an event
  * pair; wg_prof_get returns the launch count and the summed duration of one kernel id:
- *   0 preview FIR, 1 preview recursion, 2 Herdt QP solve, 3 Herdt MPC step, 4 PLDP solve, 5 OptCholesky,
- *   6 preview fused. */
+ *   2 Herdt QP solve, 3 Herdt closed-loop periods, 4 PLDP solve, 5 OptCholesky, 6 preview (fused FIR + scan). */
 int wg_prof_begin(wg_ctx *ctx, int capacity);
 int wg_prof_end(wg_ctx *ctx);                        /* synchronises the stream and accumulates      */
 int wg_prof_get(wg_ctx *ctx, int kernel_id, long long *launches, double *total_ms);
@@ -310,6 +309,74 @@ int wg_herdt_mpc_init(wg_ctx *ctx, int mem, int B, const double *init9, int init
 int wg_herdt_mpc_run_batch(wg_ctx *ctx, int mem, int B, int nsteps, wg_herdt_mpc_state *states,
                            const double *vel_ref, wg_herdt_tick *ticks, wg_herdt_mpc_step *steps,
                            wg_herdt_qp_input *qp_in);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dimitrov PLDP solver and OptCholesky, batched (QP_N = 16: control vector of 2N = 32 entries)
+ *   replaces PLDPSolver::PLDPSolver / SolveProblem / ComputeInitialSolution / ComputeProjectedDescentDirection /
+ *            ComputeAlpha / StoreCurrentZMPSolution   (src/Mathematics/PLDPSolver.cpp:56-135, :287-1032)
+ *            OptCholesky::AddActiveConstraint(s) / UpdateCholeskyMatrixNormal / UpdateCholeskyMatrixFortran /
+ *            ComputeNormalCholeskyOnANormal / ComputeInverseCholeskyNormal (src/Mathematics/OptCholesky.cpp:78-302)
+ * ---------------------------------------------------------------------------------------------- */
+#define WG_PLDP_CARDU 16                 /* m_CardV = QP_N                                          */
+#define WG_PLDP_NVAR (2 * WG_PLDP_CARDU)  /* 32                                                      */
+
+/* Constants the PLDPSolver ctor borrows (PLDPSolver.hh:48-52): iPu, Px, Pu are CardU x CardU, CardU x 3, CardU x CardU
+ * row-major host arrays.  (iLQ is only read by the reference's debug dumps and is not needed.) */
+int wg_pldp_set_constants(wg_ctx *ctx, int card_u, const double *iPu, const double *Px, const double *Pu);
+
+/* Hot-start memory of one solver instance: m_PreviouslyActivatedConstraints and m_PreviousZMPSolution. */
+typedef struct wg_pldp_state {
+  double prev_zmp[WG_PLDP_NVAR];
+  int32_t prev_active[WG_PLDP_NVAR];
+  int32_t n_prev;
+  int32_t pad_;
+} wg_pldp_state;
+
+typedef struct wg_pldp_info {
+  int32_t rc;          /* return value of SolveProblem: 0, or -1 when X[0] / X[CardU] is NaN or Inf (PLDPSolver.cpp:955-964) */
+  int32_t status;      /* 0 ok; 1 start point violated a constraint by more than m_tol ("PB ON constraint", :611-616);
+                          2 negative step length (the reference calls exit(0), :822-828); 3 active-set capacity;
+                          4 iteration cap reached (stands in for the 1.3 ms wall-clock cap, :890-900)                 */
+  int32_t iterations;  /* m_ItNb                                                                                       */
+  int32_t n_active;
+  int32_t active[WG_PLDP_NVAR];   /* m_ActivatedConstraints in activation order, -1 padded                             */
+} wg_pldp_info;
+
+/* Arguments of B calls of PLDPSolver::SolveProblem (PLDPSolver.hh:60-68), one per instance b.  All pointers live in
+ * the memory space given by `mem`. */
+typedef struct wg_pldp_batch {
+  const double *D;        /* [B][32]  CstPartOfTheCostFunction                                                    */
+  const int32_t *m;       /* [B]      NbOfConstraints                                                             */
+  const double *DPu;      /* instance b at DPu + b*dpu_stride: LinearPartOfConstraints, column-major with leading
+                             dimension m[b]+1 (element (r,c) at r + c*(m[b]+1)), 32 columns                       */
+  long long dpu_stride;
+  const double *DPx;      /* instance b at DPx + b*dpx_stride: CstPartOfConstraints [m[b]]                        */
+  long long dpx_stride;
+  const double *ZMPRef;   /* [B][32]                                                                              */
+  const double *XkYk;     /* [B][6]   (x, dx, ddx, y, dy, ddy)                                                    */
+  double *X;              /* [B][32]  out                                                                         */
+  const int32_t *similar; /* [B][similar_stride] SimilarConstraints, or NULL (the reuse is bit-neutral)           */
+  long long similar_stride;
+  const int32_t *n_removed; /* [B] NumberOfRemovedConstraints, or NULL (0)                                        */
+  const int32_t *starting;  /* [B] StartingSequence, or NULL (true)                                               */
+  wg_pldp_state *hot;     /* [B] in/out hot-start memory, or NULL                                                 */
+  int32_t hot_start;      /* m_HotStart (the reference hard-codes true, PLDPSolver.cpp:65)                        */
+  int32_t max_iterations; /* <= 0: 128                                                                            */
+  wg_pldp_info *info;     /* [B] out, or NULL                                                                     */
+} wg_pldp_batch;
+
+int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *batch);
+
+/* OptCholesky, B instances: compute rows k0..k1-1 of L for the active rows rows[b][0..k1) of A_b (rows 0..k0-1 of L
+ * must already be there: this is AddActiveConstraint called k1-k0 times).  mode 1 = MODE_FORTRAN (A column-major,
+ * leading dimension nb_constraints+1), mode 0 = MODE_NORMAL (A row-major, card_u columns).  L is row-major with leading
+ * dimension nb_max, as the storage SetL() hands to the reference. */
+int wg_optcholesky_add_rows_batch(wg_ctx *ctx, int mem, int B, int mode, int nb_max, int card_u, int nb_constraints,
+                                  const double *A, long long a_stride, const int32_t *rows, int rows_stride, int k0,
+                                  int k1, double *L, long long l_stride);
+/* ComputeNormalCholeskyOnANormal (A: [B][n][n] row-major, may be NULL to keep L) and, when iL != NULL,
+ * ComputeInverseCholeskyNormal on the leading inv_size x inv_size block. */
+int wg_optcholesky_full_batch(wg_ctx *ctx, int mem, int B, int n, const double *A, double *L, double *iL, int inv_size);
 
 #ifdef __cplusplus
 }

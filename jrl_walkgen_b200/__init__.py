@@ -18,9 +18,10 @@ from ._capi import (MODE_WITH_INITIALPOS, MODE_WITHOUT_INITIALPOS, WG_MEM_DEVICE
 QP_INPUT_DTYPE, QP_OUTPUT_DTYPE = _capi.herdt_dtypes()
 FOOT_DTYPE, TICK_DTYPE, MPC_STATE_DTYPE, MPC_STEP_DTYPE = _capi.herdt_mpc_dtypes()
 TICKS_PER_STEP = _capi.HERDT_TICKS_PER_STEP
+PLDP_STATE_DTYPE, PLDP_INFO_DTYPE = _capi.pldp_dtypes()
 
 __all__ = ["Context", "PreviewPlan", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
-           "FOOT_DTYPE", "TICK_DTYPE", "MPC_STATE_DTYPE", "MPC_STEP_DTYPE", "TICKS_PER_STEP", "QP_INPUT_DTYPE",
+           "PLDP_STATE_DTYPE", "PLDP_INFO_DTYPE", "FOOT_DTYPE", "TICK_DTYPE", "MPC_STATE_DTYPE", "MPC_STEP_DTYPE", "TICKS_PER_STEP", "QP_INPUT_DTYPE",
            "QP_OUTPUT_DTYPE", "WalkgenError", "device_count",
            "MODE_WITH_INITIALPOS", "MODE_WITHOUT_INITIALPOS", "WG_MEM_HOST", "WG_MEM_DEVICE"]
 
@@ -244,6 +245,58 @@ class Context:
         """Device-resident form (asynchronous on the context stream)."""
         self._check(self.lib.wg_herdt_mpc_run_batch(self.h, WG_MEM_DEVICE, int(B), int(nsteps), _ptr(d_states),
                                                     _ptr(d_vel_ref), _ptr(d_ticks), _ptr(d_steps), _ptr(d_qp_in)))
+
+
+    # ---- Dimitrov PLDP / OptCholesky ------------------------------------------------------------
+    def pldp_set_constants(self, iPu, Px, Pu):
+        """The arrays the PLDPSolver ctor borrows (PLDPSolver.hh:48-52), CardU = 16."""
+        iPu, Px, Pu = (np.ascontiguousarray(a, dtype=np.float64) for a in (iPu, Px, Pu))
+        D = _capi.c_double_p
+        self._check(self.lib.wg_pldp_set_constants(self.h, iPu.shape[0], iPu.ctypes.data_as(D), Px.ctypes.data_as(D),
+                                                   Pu.ctypes.data_as(D)))
+
+    def pldp_solve(self, pb, hot=None, hot_start=True, starting=None, n_removed=None, similar=None, max_iterations=0,
+                   mem=WG_MEM_HOST, B=None, X=None, info=None):
+        """wg_pldp_solve_batch.  pb: dict with D [B][32], m [B] int32, DPu [B][dpu_stride], DPx [B][dpx_stride],
+        ZMPRef [B][32], XkYk [B][6], dpu_stride, dpx_stride (numpy arrays, or DeviceBuffers with mem=WG_MEM_DEVICE).
+        Returns (X, info)."""
+        if mem == WG_MEM_HOST:
+            B = len(pb["m"])
+            X = np.zeros((B, 32)) if X is None else X
+            info = np.zeros(B, dtype=PLDP_INFO_DTYPE) if info is None else info
+        keep = [np.ascontiguousarray(pb[k]) if mem == WG_MEM_HOST else pb[k] for k in ("D", "m", "DPu", "DPx", "ZMPRef", "XkYk")]
+        opt = [None if a is None else (np.ascontiguousarray(a, dtype=np.int32) if mem == WG_MEM_HOST else a)
+               for a in (similar, n_removed, starting)]
+        def vp(a):
+            p = _ptr(a)
+            return None if p is None else p.value
+        b = _capi.PldpBatch(D=vp(keep[0]), m=vp(keep[1]), DPu=vp(keep[2]), dpu_stride=int(pb["dpu_stride"]),
+                            DPx=vp(keep[3]), dpx_stride=int(pb["dpx_stride"]), ZMPRef=vp(keep[4]), XkYk=vp(keep[5]),
+                            X=vp(X), similar=vp(opt[0]),
+                            similar_stride=0 if opt[0] is None or mem != WG_MEM_HOST else opt[0].shape[1],
+                            n_removed=vp(opt[1]), starting=vp(opt[2]), hot=vp(hot), hot_start=int(bool(hot_start)),
+                            max_iterations=int(max_iterations), info=vp(info))
+        self._check(self.lib.wg_pldp_solve_batch(self.h, mem, int(B), C.byref(b)))
+        return X, info
+
+    def optcholesky_add_rows(self, A, rows, L, mode, nb_max, card_u, nb_constraints, k0, k1):
+        """OptCholesky::AddActiveConstraint for rows[:, k0:k1] of every instance (host arrays; L updated in place)."""
+        A = np.ascontiguousarray(A, dtype=np.float64); rows = np.ascontiguousarray(rows, dtype=np.int32)
+        assert L.flags["C_CONTIGUOUS"] and L.dtype == np.float64
+        B = A.shape[0]
+        self._check(self.lib.wg_optcholesky_add_rows_batch(self.h, WG_MEM_HOST, B, mode, nb_max, card_u, nb_constraints,
+                                                           A.ctypes.data, A[0].size, rows.ctypes.data, rows.shape[1],
+                                                           k0, k1, L.ctypes.data, L[0].size))
+        return L
+
+    def optcholesky_full(self, A, inverse=True):
+        """ComputeNormalCholeskyOnANormal (+ ComputeInverseCholeskyNormal(1)) for A [B][n][n] -> (L, iL)."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        B, n, _ = A.shape
+        L = np.zeros_like(A); iL = np.zeros_like(A) if inverse else None
+        self._check(self.lib.wg_optcholesky_full_batch(self.h, WG_MEM_HOST, B, n, A.ctypes.data, L.ctypes.data,
+                                                       None if iL is None else iL.ctypes.data, n))
+        return L, iL
 
 
 class PreviewPlan:

@@ -71,6 +71,24 @@ class HerdtMpcParams(C.Structure):
                 ("feet_cross_limit", C.c_double), ("nb_steps_ssds", C.c_int32), ("pad_", C.c_int32)]
 
 
+class PldpBatch(C.Structure):
+    """Mirror of wg_pldp_batch."""
+    _fields_ = [("D", C.c_void_p), ("m", C.c_void_p), ("DPu", C.c_void_p), ("dpu_stride", C.c_longlong),
+                ("DPx", C.c_void_p), ("dpx_stride", C.c_longlong), ("ZMPRef", C.c_void_p), ("XkYk", C.c_void_p),
+                ("X", C.c_void_p), ("similar", C.c_void_p), ("similar_stride", C.c_longlong),
+                ("n_removed", C.c_void_p), ("starting", C.c_void_p), ("hot", C.c_void_p), ("hot_start", C.c_int32),
+                ("max_iterations", C.c_int32), ("info", C.c_void_p)]
+
+
+def pldp_dtypes():
+    """numpy mirrors of wg_pldp_state (392 B) and wg_pldp_info (144 B)."""
+    np = _np()
+    state = np.dtype([("prev_zmp", "f8", 32), ("prev_active", "i4", 32), ("n_prev", "i4"), ("pad_", "i4")])
+    info = np.dtype([("rc", "i4"), ("status", "i4"), ("iterations", "i4"), ("n_active", "i4"), ("active", "i4", 32)])
+    assert state.itemsize == 392 and info.itemsize == 144
+    return state, info
+
+
 HERDT_N = 16
 HERDT_TICKS_PER_STEP = 20
 HERDT_MAX_VARS = 36
@@ -161,6 +179,13 @@ SIGNATURES = {
     "wg_herdt_default_params": (None, [C.c_double, C.c_double, C.POINTER(HerdtParams)]),
     "wg_herdt_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtParams)]),
     "wg_herdt_qp_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wg_pldp_set_constants": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]),
+    "wg_pldp_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(PldpBatch)]),
+    "wg_optcholesky_add_rows_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_longlong]),
+    "wg_optcholesky_full_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int]),
     "wg_herdt_mpc_default_params": (None, [C.POINTER(HerdtMpcParams)]),
     "wg_herdt_mpc_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtMpcParams)]),
     "wg_herdt_mpc_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

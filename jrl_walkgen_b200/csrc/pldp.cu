@@ -1,3 +1,535 @@
-// pldp.cu - placeholder (filled in below in the same round)
+// pldp.cu - batched Dimitrov PLDP solver and OptCholesky for sm_100a.
+//
+// Replaces PLDPSolver::SolveProblem and its helpers (src/Mathematics/PLDPSolver.cpp:287-1007) and
+// OptCholesky (src/Mathematics/OptCholesky.cpp:92-302) for whole batches of independent problems.
+//
+// One warp owns one problem.  The control vector has 2N = 32 entries = one per lane, so the iterate V_k, the
+// descent direction c, the projected direction d live in registers (one double per lane) and move with shuffles;
+// the Cholesky factor of E E^T (at most 32 x 32: PLDP never drops a constraint and E has 32 columns) is packed in
+// shared memory.  The constraint matrix (m+1) x 32, column-major exactly as the reference receives it, is read
+// from global memory / L2 by "row per lane" loops (consecutive lanes read consecutive rows: coalesced).
+//
+// Arithmetic follows the reference statement by statement with NON-fused multiplies and adds (__dmul_rn/__dadd_rn)
+// in the reference's summation order throughout, so that on identical inputs the iterates, the step lengths and therefore the
+// sequence of activated constraints are the same as the reference's x86-64 object code (which has no FMA
+// contraction at -O3 without -march).  Differences by design: the wall-clock cap of 1.3 ms (PLDPSolver.cpp:69,
+// :890-900) becomes an iteration cap, and the paths on which the reference calls exit(0) (:822-828) or prints
+// return a status instead.
 #include "wg_common.h"
-void wg_pldp_release(wg_ctx *) {}
+#include <vector>
+#include <cmath>
+
+namespace {
+
+constexpr int PLDP_N = 16;            // m_CardV
+constexpr int PLDP_U = 2 * PLDP_N;    // 32 = warp size
+constexpr int PLDP_KMAX = 32;         // active-set capacity (= number of columns of E)
+constexpr int PLDP_WARPS = 4;
+
+struct PldpConsts {
+  double iPu[PLDP_N * PLDP_N];        // row-major as handed to the PLDPSolver ctor
+  double Px[PLDP_N * 3];
+  double Pu[PLDP_N * PLDP_N];
+  double iPuPx[PLDP_U * 6];           // PLDPSolver::PrecomputeiPuPx (PLDPSolver.cpp:264-285)
+};
+
+struct PldpHost {
+  PldpConsts h;
+  PldpConsts *d = nullptr;
+  bool ready = false;
+  // staging for WG_MEM_HOST calls
+  void *buf[10] = {nullptr};
+  size_t cap[10] = {0};
+};
+
+struct PldpWarp {
+  double L[PLDP_KMAX * (PLDP_KMAX + 1) / 2];   // packed lower triangle, row i at i(i+1)/2
+  double prev_zmp[PLDP_U];
+  int active[PLDP_KMAX];
+};
+
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// OptCholesky::UpdateCholeskyMatrixFortran (OptCholesky.cpp:171-223): row `i` of L for the active rows act[0..i].
+// Lane j computes M(i,j) = A_act[i] . A_act[j] in the reference's order and then the forward recurrence
+// L(i,j) = (M(i,j) - sum_{k<j} L(i,k) L(j,k)) / L(j,j), with the L(i,k) broadcast as they become final.
+__device__ void chol_add_row(double *L, const int *act, int i, const double *__restrict__ A, int ld, int lane)
+{
+  double r = 0.0;
+  if (lane <= i) {
+    const double *ri = A + act[i], *rj = A + act[lane];
+#pragma unroll 4
+    for (int k = 0; k < PLDP_U; ++k) r = add(r, mul(ri[(size_t)k * ld], rj[(size_t)k * ld]));
+  }
+  double lij = 0.0;
+  for (int j = 0; j <= i; ++j) {
+    // lane j finalises L(i,j)
+    if (lane == j) lij = (j != i) ? r / L[tri(j) + j] : sqrt(r);
+    const double v = bcast(lij, j);
+    // for the diagonal (lane == i) the second factor is the new row itself, i.e. the value just finalised
+    if (lane > j && lane <= i) r = add(r, -mul(v, (lane == i) ? v : L[tri(lane) + j]));
+  }
+  if (lane <= i) L[tri(i) + lane] = lij;
+  __syncwarp();
+}
+
+// One instance per warp.
+__global__ void __launch_bounds__(PLDP_WARPS * 32)
+pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__ D, const int *__restrict__ mvec,
+            const double *__restrict__ DPu, long long dpu_stride, const double *__restrict__ DPx, long long dpx_stride,
+            const double *__restrict__ ZMPRef, const double *__restrict__ XkYk, double *__restrict__ X,
+            const int *__restrict__ similar, long long similar_stride, const int *__restrict__ nremoved,
+            const int *__restrict__ starting, wg_pldp_state *__restrict__ hot, int hot_start, int max_iter,
+            double tol, wg_pldp_info *__restrict__ info)
+{
+  __shared__ PldpWarp ws[PLDP_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PldpConsts &C = *Cp;
+  PldpWarp &w = ws[warp];
+  constexpr int N = PLDP_N;
+  for (int b = blockIdx.x * PLDP_WARPS + warp; b < B; b += gridDim.x * PLDP_WARPS) {
+    const int m = mvec[b];
+    const int ld = m + 1;
+    const double *A = DPu + (size_t)b * dpu_stride;
+    const double *bv = DPx + (size_t)b * dpx_stride;
+    const int *sim = similar ? similar + (size_t)b * similar_stride : nullptr;
+    const bool start = starting ? starting[b] != 0 : true;
+    const double Dl = D[(size_t)b * PLDP_U + lane];
+    const double *zr = ZMPRef + (size_t)b * PLDP_U;
+    const double *xk = XkYk + (size_t)b * 6;
+    int status = 0;
+    (void)sim;   // A_j = -A_i reuse (PLDPSolver.cpp:570-590) gives bit-identical products; all rows are computed directly
+
+    // ---- ComputeInitialSolution (PLDPSolver.cpp:287-340): lane = i (x part) or i + N (y part)
+    const int ii = lane & (N - 1), ax = lane >> 4;
+    if (hot && hot_start && !start) w.prev_zmp[lane] = hot[b].prev_zmp[lane];
+    __syncwarp();
+    double Vk = 0.0;
+    {
+      const double *ipx = C.iPuPx + lane * 6 + 3 * ax;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Vk = add(Vk, -mul(ipx[j], xk[3 * ax + j]));
+      if (hot && hot_start && !start) {
+        for (int j = 0; j < N - 1; ++j) Vk = add(Vk, mul(C.iPu[j * N + ii], w.prev_zmp[j + 1 + N * ax]));
+        Vk = add(Vk, mul(C.iPu[(N - 1) * N + ii], zr[N - 1 + N * ax]));
+      } else {
+        for (int j = 0; j < N; ++j) Vk = add(Vk, mul(C.iPu[j * N + ii], zr[j + N * ax]));
+      }
+    }
+    // ---- hot start: re-activate the constraints kept from the previous solve (PLDPSolver.cpp:763-778)
+    int k = 0;
+    if (hot && hot_start) {
+      const int np = hot[b].n_prev;
+      const int nr = nremoved ? nremoved[b] : 0;
+      for (int i = 0; i < np && k < PLDP_KMAX; ++i) {
+        const int idx = hot[b].prev_active[i] - nr;
+        if (idx >= 0 && idx < m) {
+          if (lane == 0) w.active[k] = idx;
+          __syncwarp();
+          chol_add_row(w.L, w.active, k, A, ld, lane);
+          ++k;
+        }
+      }
+    }
+    // activity flags of the rows this lane owns (rows lane, lane+32, lane+64, lane+96)
+    unsigned mine = 0;
+    for (int i = 0; i < k; ++i) { const int r = w.active[i]; if ((r & 31) == lane) mine |= 1u << (r >> 5); }
+    int kproj = 0;         // size of the active set at the last projection (v2 is defined for lanes < kproj)
+
+    double v2 = 0.0;       // lane i < k holds v2[i] of the last projection
+    int it = 0;
+    bool cont = true;
+    while (cont) {
+      // ---- step 1: c = -D - Vk (PLDPSolver.cpp:805-807)
+      const double c = add(-Dl, -Vk);
+      // ---- step 2: ComputeProjectedDescentDirection (PLDPSolver.cpp:404-532)
+      // v1 = E c : lane li owns active row li
+      double v1 = 0.0;
+      {
+        const double *row = A + ((lane < k) ? w.active[lane] : 0);
+#pragma unroll 4
+        for (int j = 0; j < PLDP_U; ++j) {
+          const double cj = bcast(c, j);
+          if (lane < k) v1 = add(v1, mul(row[(size_t)j * ld], cj));
+        }
+      }
+      // forward substitution L y = v1 (:342-365): y[i] += -L(i,k) y[k] in k order, then / L(i,i) (skipped when 0)
+      double y = v1;
+      for (int i = 0; i < k; ++i) {
+        if (lane == i) { const double dg = w.L[tri(i) + i]; if (dg != 0.0) y = y / dg; }
+        const double yi = bcast(y, i);
+        if (lane > i && lane < k) y = add(y, -mul(w.L[tri(lane) + i], yi));
+      }
+      // backward substitution L^T v2 = y (:367-400): v2[i] = (y[i] - sum_{k'=i+1}^{k-1} L(k',i) v2[k']) / L(i,i), the
+      // sum taken in INCREASING k' as the reference does.  Lane k' forms its product in parallel; only the ordered
+      // additions are serial (the products and the shuffles are off the dependency chain).
+      v2 = y;
+      for (int i = k - 1; i >= 0; --i) {
+        const double p = (lane > i && lane < k) ? mul(w.L[tri(lane) + i], v2) : 0.0;
+        double acc = bcast(v2, i);
+        for (int kk = i + 1; kk < k; ++kk) acc = add(acc, -bcast(p, kk));
+        acc = acc / w.L[tri(i) + i];
+        if (lane == i) v2 = acc;
+      }
+      kproj = k;
+      // d = c - E^T v2 (:509-518): lane li, sequential over the active rows
+      double d = c;
+      for (int j = 0; j < k; ++j) {
+        const double vj = bcast(v2, j);
+        d = add(d, -mul(A[w.active[j] + (size_t)lane * ld], vj));
+      }
+      // ---- step 3: ComputeAlpha (:534-653): rows lane, lane+32, ... ; running minimum in row order
+      double alpha = 10000000.0;
+      int cand = -1;
+      {
+        double best = 10000000.0; int besti = 0x7fffffff;
+        for (int s = 0; s * 32 < m; ++s) {
+          const int li = lane + 32 * s;
+          double t1 = 0.0, t2 = 0.0;
+          const bool mineok = (li < m) && !((mine >> s) & 1u);
+          const double *row = A + (li < m ? li : 0);
+#pragma unroll 4
+          for (int j = 0; j < PLDP_U; ++j) {
+            const double dj = bcast(d, j);
+            if (mineok) t1 = add(t1, mul(row[(size_t)j * ld], dj));
+          }
+          const unsigned neg = __ballot_sync(0xffffffffu, mineok && t1 < 0.0);
+          if (neg) {
+            t2 = mineok ? -bv[li < m ? li : 0] : 0.0;
+#pragma unroll 4
+            for (int j = 0; j < PLDP_U; ++j) {
+              const double vj = bcast(Vk, j);
+              if (mineok && t1 < 0.0) t2 = add(t2, -mul(row[(size_t)j * ld], vj));
+            }
+            if (mineok && t1 < 0.0) {
+              if (t2 > tol) status = 1;                // "PB ON constraint": the start point violates row li
+              else if (t2 > 0.0) t2 = -tol;
+              const double la = t2 / t1;
+              if (la < best) { best = la; besti = li; }
+            }
+          }
+        }
+        // the reference keeps the FIRST row (in index order) that attains the minimum
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+          if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (best < alpha) { alpha = best; if (alpha < 1.0) cand = besti; }
+#ifdef PLDP_DEBUG
+        if (b == 0 && lane == 0) printf("gpu it %d k %d alpha %.17g cand %d\n", it, k, alpha, cand);
+#endif
+      }
+      status = __reduce_max_sync(0xffffffffu, status);
+      if (alpha >= 1.0) { alpha = 1.0; cont = false; }
+      if (alpha < 0.0) { status = 2; cont = false; }     // the reference calls exit(0) here (:822-828)
+      // ---- new solution (:830-834)
+      if (status != 2) Vk = add(Vk, mul(alpha, d));
+      if (cont) {
+        if (k >= PLDP_KMAX || cand < 0) { status = 3; cont = false; }
+        else {
+          if (lane == 0) w.active[k] = cand;
+          if ((cand & 31) == lane) mine |= 1u << (cand >> 5);
+          __syncwarp();
+          chol_add_row(w.L, w.active, k, A, ld, lane);
+          ++k;
+        }
+      }
+      ++it;
+      if (it >= max_iter && cont) { cont = false; status = status ? status : 4; }   // stands in for the 1.3 ms cap
+    }
+    // ---- results
+    X[(size_t)b * PLDP_U + lane] = Vk;
+    const double x0 = bcast(Vk, 0), xn = bcast(Vk, N);
+    int rc = 0;
+    if (isnan(x0) || isnan(xn) || isinf(x0) || isinf(xn)) rc = -1;   // PLDPSolver.cpp:955-964
+    if (hot && hot_start) {
+      // keep the rows whose multiplier is negative (:909-920) and store the ZMP solution (:1009-1032)
+      const unsigned keep = __ballot_sync(0xffffffffu, lane < kproj && v2 < 0.0);
+      if (lane < kproj && v2 < 0.0) hot[b].prev_active[__popc(keep & ((1u << lane) - 1u))] = w.active[lane];
+      if (lane == 0) hot[b].n_prev = __popc(keep);
+      double z = 0.0;
+      for (int j = 0; j < N; ++j) z = add(z, mul(C.Pu[j * N + ii], bcast(Vk, j + N * ax)));
+#pragma unroll
+      for (int j = 0; j < 3; ++j) z = add(z, mul(C.Px[ii * 3 + j], xk[3 * ax + j]));
+      hot[b].prev_zmp[lane] = z;
+    }
+    if (info) {
+      if (lane == 0) { info[b].rc = rc; info[b].status = status; info[b].iterations = it; info[b].n_active = k; }
+      info[b].active[lane] = (lane < k) ? w.active[lane] : -1;
+    }
+    __syncwarp();
+  }
+}
+
+// OptCholesky batched: rows k0..k-1 of L for the active rows `rows` of each instance's A.
+//   mode 1 (MODE_FORTRAN): A column-major, element (r, c) at A[r + c (nb_constraints + 1)]  (OptCholesky.cpp:171-223)
+//   mode 0 (MODE_NORMAL):  A row-major,    element (r, c) at A[r card_u + c]                 (OptCholesky.cpp:123-169)
+// L is row-major with leading dimension nb_max (the caller-owned storage the reference writes into).
+__global__ void __launch_bounds__(128)
+optchol_kernel(int B, int mode, int nb_max, int card_u, int nb_constraints, const double *__restrict__ A,
+               long long a_stride, const int *__restrict__ rows, int rows_stride, int k0, int k1,
+               double *__restrict__ Lout, long long l_stride)
+{
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 4 + warp; b < B; b += gridDim.x * 4) {
+    const double *Ab = A + (size_t)b * a_stride;
+    const int *act = rows + (size_t)b * rows_stride;
+    double *L = Lout + (size_t)b * l_stride;
+    const long long rs = mode ? 1 : card_u, cs = mode ? (nb_constraints + 1) : 1;
+    for (int i = k0; i < k1; ++i) {
+      const double *ri = Ab + (size_t)act[i] * rs;
+      // columns j = 0..i, 32 at a time; the recurrence over j is sequential, lane (j % 32) finalises L(i,j)
+      for (int j = 0; j <= i; ++j) {
+        const double *rj = Ab + (size_t)act[j] * rs;
+        // M(i,j) in the reference's order, then r -= L(i,k) L(j,k) for k < j: one lane does the serial sum
+        // (bit-faithful); different (i,j) pairs cannot run ahead because of the recurrence on L(i,k<j).
+        if (lane == 0) {
+          double r = 0.0;
+          for (int c = 0; c < card_u; ++c) r = add(r, mul(ri[c * cs], rj[c * cs]));
+          const double *Li = L + (size_t)i * nb_max, *Lj = L + (size_t)j * nb_max;
+          for (int kk = 0; kk < j; ++kk) r = add(r, -mul(Li[kk], Lj[kk]));
+          L[(size_t)i * nb_max + j] = (j != i) ? r / Lj[j] : sqrt(r);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ComputeNormalCholeskyOnANormal (OptCholesky.cpp:225-259) + ComputeInverseCholeskyNormal (:261-302), one warp each.
+__global__ void __launch_bounds__(128)
+optchol_full_kernel(int B, int n, const double *__restrict__ A, double *__restrict__ Lout, double *__restrict__ iLout,
+                    int inv_size)
+{
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 4 + warp; b < B; b += gridDim.x * 4) {
+    const double *Ab = A ? A + (size_t)b * n * n : nullptr;
+    double *L = Lout + (size_t)b * n * n;
+    double *iL = iLout ? iLout + (size_t)b * n * n : nullptr;
+    if (Ab) {
+      for (int i = 0; i < n; ++i) {
+        for (int j = 0; j <= i; ++j) {
+          if (lane == 0) {
+            double r = Ab[(size_t)i * n + j];
+            for (int kk = 0; kk < j; ++kk) r = add(r, -mul(L[(size_t)i * n + kk], L[(size_t)j * n + kk]));
+            L[(size_t)i * n + j] = (j != i) ? r / L[(size_t)j * n + j] : sqrt(r);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (iL) {
+      // columns lj are independent of each other: lane-strided over lj, serial down the column as the reference
+      for (int lj = inv_size - 1 - lane; lj >= 0; lj -= 32) {
+        const double inv = 1 / L[(size_t)lj * n + lj];
+        iL[(size_t)lj * n + lj] = inv;
+      }
+      __syncwarp();
+      // iL(li,lj) = -iL(lj,lj) * sum_{lk=lj+1..} iL(li,lk) L(lk,lj): needs iL(li, lk>lj) -> process lj descending
+      for (int lj = inv_size - 1; lj >= 0; --lj) {
+        const double inv = iL[(size_t)lj * n + lj];
+        for (int li = lj + 1 + lane; li < inv_size; li += 32) {
+          double r = 0.0;
+          for (int lk = lj + 1; lk < inv_size; ++lk) r = add(r, mul(iL[(size_t)li * n + lk], L[(size_t)lk * n + lj]));
+          iL[(size_t)li * n + lj] = mul(-inv, r);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+PldpHost *pldp_of(wg_ctx *ctx)
+{
+  if (!ctx->pldp) ctx->pldp = new PldpHost();
+  return static_cast<PldpHost *>(ctx->pldp);
+}
+
+int ensure(wg_ctx *ctx, PldpHost *p, int slot, size_t bytes)
+{
+  if (p->cap[slot] >= bytes) return WG_OK;
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(p->buf[slot]);
+  p->buf[slot] = nullptr; p->cap[slot] = 0;
+  WG_CUDA(ctx, cudaMalloc(&p->buf[slot], bytes ? bytes : 8));
+  p->cap[slot] = bytes;
+  return WG_OK;
+}
+
+int grid_for(wg_ctx *ctx, int B, int warps) { int g = (B + warps - 1) / warps; int cap = ctx->sm_count * 8; return g < cap ? (g > 0 ? g : 1) : cap; }
+
+}  // namespace
+
+void wg_pldp_release(wg_ctx *ctx)
+{
+  if (!ctx->pldp) return;
+  PldpHost *p = static_cast<PldpHost *>(ctx->pldp);
+  cudaFree(p->d);
+  for (void *b : p->buf) cudaFree(b);
+  delete p;
+  ctx->pldp = nullptr;
+}
+
+extern "C" {
+
+int wg_pldp_set_constants(wg_ctx *ctx, int card_u, const double *iPu, const double *Px, const double *Pu)
+{
+  if (!ctx || !iPu || !Px || !Pu) return WG_ERR_INVALID;
+  if (card_u != PLDP_N) return wg_fail(ctx, WG_ERR_INVALID, "PLDP kernels are built for CardU = 16 (QP_N of the reference)");
+  wg_device_guard guard(ctx->device);
+  PldpHost *p = pldp_of(ctx);
+  const int N = PLDP_N;
+  std::memcpy(p->h.iPu, iPu, sizeof p->h.iPu);
+  std::memcpy(p->h.Px, Px, sizeof p->h.Px);
+  std::memcpy(p->h.Pu, Pu, sizeof p->h.Pu);
+  // PLDPSolver::PrecomputeiPuPx, PLDPSolver.cpp:264-285 (same summation order)
+  std::memset(p->h.iPuPx, 0, sizeof p->h.iPuPx);
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < N; ++k) {
+        const double tmp = iPu[k * N + i] * Px[k * 3 + j];
+        p->h.iPuPx[i * 6 + j] += tmp;
+        p->h.iPuPx[(i + N) * 6 + j + 3] += tmp;
+      }
+  if (!p->d) WG_CUDA(ctx, cudaMalloc(&p->d, sizeof(PldpConsts)));
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  WG_CUDA(ctx, cudaMemcpy(p->d, &p->h, sizeof(PldpConsts), cudaMemcpyHostToDevice));
+  p->ready = true;
+  return WG_OK;
+}
+
+int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
+{
+  if (!ctx || !pb || B < 0) return WG_ERR_INVALID;
+  PldpHost *p = pldp_of(ctx);
+  if (!p->ready) return wg_fail(ctx, WG_ERR_NOT_READY, "wg_pldp_set_constants not called");
+  if (B == 0) return WG_OK;
+  if (!pb->D || !pb->m || !pb->DPu || !pb->DPx || !pb->ZMPRef || !pb->XkYk || !pb->X) return WG_ERR_INVALID;
+  if (pb->dpu_stride <= 0 || pb->dpx_stride <= 0) return WG_ERR_INVALID;
+  wg_device_guard guard(ctx->device);
+  const int max_iter = pb->max_iterations > 0 ? pb->max_iterations : 4 * PLDP_KMAX;
+  const double tol = 1e-8;   // m_tol, PLDPSolver.cpp:66
+  wg_pldp_batch d = *pb;
+  if (mem == WG_MEM_HOST) {
+    const size_t nb = (size_t)B;
+    struct Item { int slot; const void *src; size_t bytes; const void **dst; };
+    const Item in[] = {
+        {0, pb->D, sizeof(double) * PLDP_U * nb, (const void **)&d.D},
+        {1, pb->m, sizeof(int) * nb, (const void **)&d.m},
+        {2, pb->DPu, sizeof(double) * (size_t)pb->dpu_stride * nb, (const void **)&d.DPu},
+        {3, pb->DPx, sizeof(double) * (size_t)pb->dpx_stride * nb, (const void **)&d.DPx},
+        {4, pb->ZMPRef, sizeof(double) * PLDP_U * nb, (const void **)&d.ZMPRef},
+        {5, pb->XkYk, sizeof(double) * 6 * nb, (const void **)&d.XkYk},
+        {6, pb->similar, pb->similar ? sizeof(int) * (size_t)pb->similar_stride * nb : 0, (const void **)&d.similar},
+        {7, pb->n_removed, pb->n_removed ? sizeof(int) * nb : 0, (const void **)&d.n_removed},
+        {8, pb->starting, pb->starting ? sizeof(int) * nb : 0, (const void **)&d.starting}};
+    for (const Item &it : in) {
+      if (!it.src) continue;
+      int rc = ensure(ctx, p, it.slot, it.bytes);
+      if (rc != WG_OK) return rc;
+      WG_CUDA(ctx, cudaMemcpyAsync(p->buf[it.slot], it.src, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
+      *it.dst = p->buf[it.slot];
+    }
+    // outputs + hot-start state share one allocation: X | info | hot
+    const size_t ox = 0, oi = ox + sizeof(double) * PLDP_U * nb, oh = oi + sizeof(wg_pldp_info) * nb;
+    const size_t total = oh + sizeof(wg_pldp_state) * nb;
+    int rc = ensure(ctx, p, 9, total);
+    if (rc != WG_OK) return rc;
+    char *base = static_cast<char *>(p->buf[9]);
+    d.X = reinterpret_cast<double *>(base + ox);
+    d.info = pb->info ? reinterpret_cast<wg_pldp_info *>(base + oi) : nullptr;
+    d.hot = pb->hot ? reinterpret_cast<wg_pldp_state *>(base + oh) : nullptr;
+    if (pb->hot) WG_CUDA(ctx, cudaMemcpyAsync(d.hot, pb->hot, sizeof(wg_pldp_state) * nb, cudaMemcpyHostToDevice, ctx->stream));
+  } else if (mem != WG_MEM_DEVICE) {
+    return WG_ERR_INVALID;
+  }
+  wg_prof_start(ctx, WG_K_PLDP);
+  pldp_kernel<<<grid_for(ctx, B, PLDP_WARPS), PLDP_WARPS * 32, 0, ctx->stream>>>(
+      B, p->d, d.D, d.m, d.DPu, d.dpu_stride, d.DPx, d.dpx_stride, d.ZMPRef, d.XkYk, d.X, d.similar, d.similar_stride,
+      d.n_removed, d.starting, d.hot, pb->hot_start, max_iter, tol, d.info);
+  wg_prof_stop(ctx);
+  WG_LAUNCHED(ctx);
+  if (mem == WG_MEM_HOST) {
+    const size_t nb = (size_t)B;
+    WG_CUDA(ctx, cudaMemcpyAsync(pb->X, d.X, sizeof(double) * PLDP_U * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pb->info) WG_CUDA(ctx, cudaMemcpyAsync(pb->info, d.info, sizeof(wg_pldp_info) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pb->hot) WG_CUDA(ctx, cudaMemcpyAsync(pb->hot, d.hot, sizeof(wg_pldp_state) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return WG_OK;
+}
+
+int wg_optcholesky_add_rows_batch(wg_ctx *ctx, int mem, int B, int mode, int nb_max, int card_u, int nb_constraints,
+                                  const double *A, long long a_stride, const int *rows, int rows_stride, int k0, int k1,
+                                  double *L, long long l_stride)
+{
+  if (!ctx || B < 0 || nb_max <= 0 || card_u <= 0 || k0 < 0 || k1 < k0 || k1 > nb_max || (mode != 0 && mode != 1))
+    return WG_ERR_INVALID;
+  if (B == 0 || k1 == k0) return WG_OK;
+  if (!A || !rows || !L || rows_stride < k1) return WG_ERR_INVALID;   // UpdateCholeskyMatrix* returns -1 on null A / L
+  wg_device_guard guard(ctx->device);
+  PldpHost *p = pldp_of(ctx);
+  const double *dA = A; const int *drows = rows; double *dL = L;
+  const size_t nb = (size_t)B;
+  if (mem == WG_MEM_HOST) {
+    int rc;
+    if ((rc = ensure(ctx, p, 2, sizeof(double) * (size_t)a_stride * nb)) != WG_OK) return rc;
+    if ((rc = ensure(ctx, p, 6, sizeof(int) * (size_t)rows_stride * nb)) != WG_OK) return rc;
+    if ((rc = ensure(ctx, p, 9, sizeof(double) * (size_t)l_stride * nb)) != WG_OK) return rc;
+    WG_CUDA(ctx, cudaMemcpyAsync(p->buf[2], A, sizeof(double) * (size_t)a_stride * nb, cudaMemcpyHostToDevice, ctx->stream));
+    WG_CUDA(ctx, cudaMemcpyAsync(p->buf[6], rows, sizeof(int) * (size_t)rows_stride * nb, cudaMemcpyHostToDevice, ctx->stream));
+    WG_CUDA(ctx, cudaMemcpyAsync(p->buf[9], L, sizeof(double) * (size_t)l_stride * nb, cudaMemcpyHostToDevice, ctx->stream));
+    dA = static_cast<const double *>(p->buf[2]); drows = static_cast<const int *>(p->buf[6]); dL = static_cast<double *>(p->buf[9]);
+  } else if (mem != WG_MEM_DEVICE) {
+    return WG_ERR_INVALID;
+  }
+  wg_prof_start(ctx, WG_K_OPTCHOL);
+  optchol_kernel<<<grid_for(ctx, B, 4), 128, 0, ctx->stream>>>(B, mode, nb_max, card_u, nb_constraints, dA, a_stride, drows,
+                                                               rows_stride, k0, k1, dL, l_stride);
+  wg_prof_stop(ctx);
+  WG_LAUNCHED(ctx);
+  if (mem == WG_MEM_HOST) {
+    WG_CUDA(ctx, cudaMemcpyAsync(L, dL, sizeof(double) * (size_t)l_stride * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return WG_OK;
+}
+
+int wg_optcholesky_full_batch(wg_ctx *ctx, int mem, int B, int n, const double *A, double *L, double *iL, int inv_size)
+{
+  if (!ctx || B < 0 || n <= 0 || !L || inv_size < 0 || inv_size > n) return WG_ERR_INVALID;
+  if (B == 0) return WG_OK;
+  wg_device_guard guard(ctx->device);
+  PldpHost *p = pldp_of(ctx);
+  const size_t bytes = sizeof(double) * (size_t)n * n * B;
+  const double *dA = A; double *dL = L, *diL = iL;
+  if (mem == WG_MEM_HOST) {
+    int rc;
+    if ((rc = ensure(ctx, p, 2, bytes)) != WG_OK) return rc;
+    if ((rc = ensure(ctx, p, 9, 2 * bytes)) != WG_OK) return rc;
+    if (A) WG_CUDA(ctx, cudaMemcpyAsync(p->buf[2], A, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    dL = static_cast<double *>(p->buf[9]); diL = iL ? dL + (size_t)n * n * B : nullptr;
+    WG_CUDA(ctx, cudaMemcpyAsync(dL, L, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (iL) WG_CUDA(ctx, cudaMemcpyAsync(diL, iL, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    dA = A ? static_cast<const double *>(p->buf[2]) : nullptr;
+  } else if (mem != WG_MEM_DEVICE) {
+    return WG_ERR_INVALID;
+  }
+  wg_prof_start(ctx, WG_K_OPTCHOL);
+  optchol_full_kernel<<<grid_for(ctx, B, 4), 128, 0, ctx->stream>>>(B, n, dA, dL, diL, inv_size);
+  wg_prof_stop(ctx);
+  WG_LAUNCHED(ctx);
+  if (mem == WG_MEM_HOST) {
+    WG_CUDA(ctx, cudaMemcpyAsync(L, dL, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (iL) WG_CUDA(ctx, cudaMemcpyAsync(iL, diL, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return WG_OK;
+}
+
+}  // extern "C"

@@ -68,3 +68,133 @@ def preview_batch(B, seed=0):
     lens = np.array([len(w) for w in walks], dtype=np.int64)
     offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     return offsets, np.ascontiguousarray(np.concatenate(walks, axis=0))
+
+
+# ------------------------------------------------------------------------------------------------
+# Config 4 - "Dimitrov ZMPQPWithConstraint PLDPSolver/OptCholesky batched: 16,384 constrained CoP QPs"
+# ------------------------------------------------------------------------------------------------
+class DimitrovConstants:
+    """Constants of ZMPConstrainedQPFastFormulation in PLDP mode (N = 16, T = 0.1 s, zc = 0.80, alpha = 200,
+    beta = 1000: src/ZMPRefTrajectoryGeneration/ZMPConstrainedQPFastFormulation.cpp:87-96), following
+    InitializeMatrixPbConstants (:158-246), BuildingConstantPartOfTheObjectiveFunction (:512-614, including the
+    `lterm2 = alpha * VPu^T` term of which only the diagonal reaches the Cholesky factor, :525-533 and :390-418)
+    and BuildingConstantPartOfConstraintMatrices (:616-680).  Workload data, not product code."""
+
+    def __init__(self, N=16, T=0.1, zc=0.80, alpha=200.0, beta=1000.0):
+        self.N, self.T, self.zc = N, T, zc
+        i = np.arange(N)[:, None]; j = np.arange(N)[None, :]
+        d = i - j
+        low = j <= i
+        PPu = np.where(low, (1 + 3 * d + 3 * d * d) * T ** 3 / 6.0, 0.0)
+        VPu = np.where(low, (2 * d + 1) * T * T * 0.5, 0.0)
+        PPx = np.column_stack([np.ones(N), (i[:, 0] + 1) * T, (i[:, 0] + 1) ** 2 * T * T * 0.5])
+        VPx = np.column_stack([np.zeros(N), np.ones(N), (i[:, 0] + 1) * T])
+        Q = np.eye(N) + beta * PPu.T @ PPu + alpha * np.diag(np.diag(VPu))
+        LQ = np.linalg.cholesky(Q)
+        iLQ = np.linalg.inv(LQ)
+        self.iLQ = iLQ
+        self.OptB = iLQ @ (alpha * VPu.T @ VPx + beta * PPu.T @ PPx)        # N x 3 per axis
+        self.OptC = iLQ @ (beta * PPu.T)                                   # N x N per axis
+        PuT = np.where(j >= i, (1 + 3 * (j - i) + 3 * (j - i) ** 2) * T ** 3 / 6.0 - T * zc / 9.81, 0.0)  # ptPu[k*N+i], k<=i
+        self.Pu = np.ascontiguousarray(iLQ @ PuT)                           # m_Pu = iLQ * Pu'
+        self.iPu = np.ascontiguousarray(np.linalg.inv(self.Pu))
+        self.Px = np.ascontiguousarray(np.column_stack([np.ones(N), (i[:, 0] + 1) * T,
+                                                        (i[:, 0] + 1) ** 2 * T * T * 0.5 - zc / 9.81]))
+
+
+def _support_polygons(rng, N, T, count=None):
+    """Per previewed sample: (centre, rows (a0, a1, b) with a.p + b >= 0 inside).  Single support: the rectangle of
+    the support foot (4 rows); double support: a hexagon around both feet (6 rows)."""
+    hx, hy = 0.085, 0.03                       # ConstraintOnX/Y = 0.04 inside a 0.25 x 0.14 sole
+    t0 = rng.uniform(0.0, 1.6)
+    step = rng.uniform(0.05, 0.25)
+    yaw = rng.uniform(-0.3, 0.3)
+    c, s = np.cos(yaw), np.sin(yaw)
+    out = []
+    for i in range(count or N):
+        t = t0 + i * T
+        k = int(t // 0.8)                       # step index
+        ph = t - 0.8 * k
+        side = 1.0 if k % 2 == 0 else -1.0
+        fx, fy = k * step, side * 0.095
+        if ph < 0.1 and k > 0:                  # double support between step k-1 and k
+            px, py = (k - 0.5) * step, 0.0
+            ex, ey = hx + 0.5 * step, hy + 0.095
+            normals = [(1, 0, ex), (-1, 0, ex), (0, 1, ey), (0, -1, ey), (0.6, 0.8, 0.9 * (0.6 * ex + 0.8 * ey)),
+                       (-0.6, -0.8, 0.9 * (0.6 * ex + 0.8 * ey))]
+        else:
+            px, py = fx, fy
+            normals = [(1, 0, hx), (-1, 0, hx), (0, 1, hy), (0, -1, hy)]
+        cx, cy = c * px - s * py, s * px + c * py
+        rows = []
+        for (nx, ny, h) in normals:             # inward normal -n rotated by yaw: -n.(p - centre) + h >= 0
+            ax, ay = -(c * nx - s * ny), -(s * nx + c * ny)
+            rows.append((ax, ay, h - ax * cx - ay * cy))
+        out.append(((cx, cy), rows))
+    return out
+
+
+def pldp_problem_from(K: DimitrovConstants, polys, xk):
+    """One call of PLDPSolver::SolveProblem as ZMPConstrainedQPFastFormulation prepares it (:759-1022, :1250-1258)
+    for the N support polygons `polys` and the LIPM state xk:
+    -> dict(D[32], m, DPu[(m+1)*32] column-major, DPx[m], ZMPRef[32], XkYk[6], n_first = rows of the first sample)."""
+    N = K.N
+    m = sum(len(r) for _, r in polys)
+    zref = np.zeros(2 * N)
+    DPu = np.zeros((2 * N, m + 1))              # column-major storage: DPu[c, r] is element (r, c)
+    DPx = np.zeros(m)
+    r = 0
+    for i, (cen, rows) in enumerate(polys):
+        zref[i], zref[i + N] = cen
+        zx = xk[0] * K.Px[i, 0] + xk[1] * K.Px[i, 1] + xk[2] * K.Px[i, 2]
+        zy = xk[3] * K.Px[i, 0] + xk[4] * K.Px[i, 1] + xk[5] * K.Px[i, 2]
+        for (a0, a1, b) in rows:
+            DPx[r] = zx * a0 + zy * a1 + b
+            DPu[:N, r] = a0 * K.Pu[:, i]
+            DPu[N:, r] = a1 * K.Pu[:, i]
+            r += 1
+    D = np.concatenate([K.OptB @ xk[:3] - K.OptC @ zref[:N], K.OptB @ xk[3:] - K.OptC @ zref[N:]])
+    return {"D": D, "m": m, "DPu": DPu.ravel(), "DPx": DPx, "ZMPRef": zref, "XkYk": np.array(xk, dtype=np.float64),
+            "n_first": len(polys[0][1])}
+
+
+def pldp_problem(K: DimitrovConstants, rng):
+    """A random stand-alone problem: random walk phase and a LIPM state near the first support centre."""
+    polys = _support_polygons(rng, K.N, K.T)
+    xk = np.zeros(6)
+    c0 = polys[0][0]
+    xk[0] = c0[0] + rng.uniform(-0.02, 0.02); xk[3] = c0[1] + rng.uniform(-0.02, 0.02)
+    xk[1] = rng.uniform(-0.1, 0.3); xk[4] = rng.uniform(-0.2, 0.2)
+    xk[2] = rng.uniform(-0.5, 0.5); xk[5] = rng.uniform(-0.5, 0.5)
+    return pldp_problem_from(K, polys, xk)
+
+
+def pldp_advance(K: DimitrovConstants, xk, X):
+    """The receding-horizon step of ZMPConstrainedQPFastFormulation (:1363-1397): jerk = (iLQ^T X)[0], [N]; LIPM
+    OneIteration with T = 0.1 (LinearizedInvertedPendulum2D.cpp:230-264)."""
+    N, T = K.N, K.T
+    jx = float(K.iLQ[:, 0] @ X[:N]); jy = float(K.iLQ[:, 0] @ X[N:])
+    A = np.array([[1.0, T, T * T / 2.0], [0.0, 1.0, T], [0.0, 0.0, 1.0]]); B = np.array([T ** 3 / 6.0, T * T / 2.0, T])
+    return np.concatenate([A @ xk[:3] + B * jx, A @ xk[3:] + B * jy])
+
+
+def pldp_pack(K, probs):
+    """Pack a list of problems for wg_pldp_solve_batch (common strides = the maxima)."""
+    B = len(probs)
+    mmax = max(p["m"] for p in probs)
+    dpu_stride = (mmax + 1) * 2 * K.N
+    out = {"D": np.stack([p["D"] for p in probs]), "m": np.array([p["m"] for p in probs], dtype=np.int32),
+           "DPu": np.zeros((B, dpu_stride)), "DPx": np.zeros((B, mmax)),
+           "ZMPRef": np.stack([p["ZMPRef"] for p in probs]), "XkYk": np.stack([p["XkYk"] for p in probs]),
+           "dpu_stride": dpu_stride, "dpx_stride": mmax}
+    for b, p in enumerate(probs):
+        out["DPu"][b, :len(p["DPu"])] = p["DPu"]
+        out["DPx"][b, :p["m"]] = p["DPx"]
+    return out
+
+
+def pldp_batch(B, seed=0, K=None):
+    """Config 4: B independent PLDP problems packed for wg_pldp_solve_batch."""
+    K = K or DimitrovConstants()
+    probs = [pldp_problem(K, np.random.default_rng([seed, 4, b])) for b in range(B)]
+    return K, pldp_pack(K, probs)
