@@ -300,6 +300,111 @@ def herdt_leg(ctx, wg, args, rank, fp64_peak, want_cpu):
                  "herdt_mpc_kernel": {"launches": args.steps, "avg_ms": mpc_ms}}
 
 
+# ------------------------------------------------------------------------------------------------
+# Dimitrov PLDP leg (BASELINE configs[3]: 16 384 constrained CoP QPs)
+# ------------------------------------------------------------------------------------------------
+PLDP_WORKLOAD = "dimitrov_pldp_16384_constrained_cop_qps_N16"
+
+
+def _cpu_pldp_worker(args):
+    import ctypes as C
+    import pldp_oracle as po
+    from jrl_walkgen_b200 import workloads
+    blob, n, seconds = args
+    K = workloads.DimitrovConstants()
+    pb = {k: (np.frombuffer(v[0], dtype=v[1]).reshape(v[2]) if isinstance(v, tuple) else v) for k, v in blob.items()}
+    L = po.lib()
+    L.oracle_pldp_solve_batch.restype = C.c_long
+    X = np.zeros((n, 32)); its = np.zeros(n, dtype=np.int32)
+    done = 0; fails = 0
+    t0 = time.perf_counter()
+    while True:
+        fails = L.oracle_pldp_solve_batch(C.c_int(16), C.c_void_p(K.iPu.ctypes.data), C.c_void_p(K.Px.ctypes.data),
+                                          C.c_void_p(K.Pu.ctypes.data), C.c_int(n), C.c_void_p(pb["D"].ctypes.data),
+                                          C.c_void_p(pb["m"].ctypes.data), C.c_void_p(pb["DPu"].ctypes.data),
+                                          C.c_long(int(pb["dpu_stride"])), C.c_void_p(pb["DPx"].ctypes.data),
+                                          C.c_long(int(pb["dpx_stride"])), C.c_void_p(pb["ZMPRef"].ctypes.data),
+                                          C.c_void_p(pb["XkYk"].ctypes.data), C.c_void_p(X.ctypes.data),
+                                          C.c_void_p(its.ctypes.data))
+        done += n
+        if time.perf_counter() - t0 >= seconds:
+            break
+    return done, time.perf_counter() - t0, int(fails)
+
+
+def cpu_pldp_rate(pb, seconds=5.0, procs=None):
+    """Oracle port of PLDPSolver::SolveProblem (bitwise equal to the reference's object code, tests/test_pldp_oracle.py;
+    the port is used because a reference solver object cannot be reused across unrelated problems: its hot start would
+    re-activate the previous problem's constraints), cold start, one process per core."""
+    import multiprocessing as mp
+    procs = procs or host_cores()
+    n = min(256, len(pb["m"]))
+    jobs = []
+    for i in range(procs):
+        a = (i * n) % max(1, len(pb["m"]) - n)
+        blob = {k: ((np.ascontiguousarray(v[a:a + n]).tobytes(), v.dtype, (n,) + v.shape[1:]) if isinstance(v, np.ndarray) else v)
+                for k, v in pb.items()}
+        jobs.append((blob, n, seconds))
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_cpu_pldp_worker, jobs)
+    total = sum(r[0] for r in res); wall = max(r[1] for r in res)
+    return {"value": total / wall, "unit": "PLDP solves/s", "cores": procs, "kind": "port",
+            "sample": f"{procs} processes x {n} problems repeated for {seconds:.0f} s ({total} solves), cold start, "
+                      "oracle port of PLDPSolver::SolveProblem (bitwise pinned to the reference object code)",
+            "us_per_solve_per_core": 1e6 * wall * procs / total, "failures": sum(r[2] for r in res)}
+
+
+def pldp_leg(ctx, wg, args, rank, fp64_peak, want_cpu):
+    from jrl_walkgen_b200 import workloads
+    B = args.pldp_instances
+    distinct = min(B, 2048)
+    K, small = workloads.pldp_batch(distinct, seed=100 + rank)
+    reps = -(-B // distinct)
+    pb = {k: (np.tile(v, (reps,) + (1,) * (v.ndim - 1))[:B] if isinstance(v, np.ndarray) else v) for k, v in small.items()}
+    ctx.pldp_set_constants(K.iPu, K.Px, K.Pu)
+    dev = {k: (ctx.to_device(v) if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    dX = ctx.alloc(B * 32 * 8); dinfo = ctx.alloc(B * wg.PLDP_INFO_DTYPE.itemsize)
+    for _ in range(3):
+        ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=B, X=dX, info=dinfo)
+    ctx.sync()
+    ctx.prof_begin(args.steps + 4)
+    for _ in range(args.steps):
+        ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=B, X=dX, info=dinfo)
+    prof = ctx.prof_end()
+    ms = prof[4][1] / prof[4][0]
+    info = dinfo.download(wg.PLDP_INFO_DTYPE, (B,))
+    it = info["iterations"].astype(np.float64); k = info["n_active"].astype(np.float64); m = pb["m"].astype(np.float64)
+    u = 32.0
+    # SURVEY 8d: F = 2u^2 (v0) + I (2 k u 2 + 2 k^2 + 2 m u) + sum_k (2 k u + k^2); k averaged as k_final / 2 over the run
+    flops = float(np.sum(2 * u * u + it * (4 * (k / 2) * u + 2 * (k / 2) ** 2 + 2 * m * u) + k * (k * u + k * k / 3)))
+    ach = flops / (ms * 1e-3) / 1e12
+    # end to end with host buffers
+    n_e2e = max(2, min(args.steps, 5))
+    ctx.pldp_solve(pb)
+    te = time.perf_counter()
+    for _ in range(n_e2e):
+        ctx.pldp_solve(pb)
+    e2e_s = time.perf_counter() - te
+    h2d = sum(v.nbytes for v in pb.values() if isinstance(v, np.ndarray))
+    res = {"workload": PLDP_WORKLOAD, "instances": B, "distinct_problems": distinct,
+           "pldp_solves_per_s": B / (ms * 1e-3), "ms_per_launch": ms,
+           "iterations_mean": float(it.mean()), "iterations_max": int(it.max()), "active_mean": float(k.mean()),
+           "constraints_mean": float(m.mean()), "failures": int(((info["rc"] != 0) | (info["status"] != 0)).sum()),
+           "roofline": {"kernel": "pldp_kernel", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                        "frac": ach / fp64_peak, "traffic": None, "algorithmic_flop_per_solve_mean": flops / B,
+                        "note": "non-fused FP64 in the reference's serial summation order (bitwise parity): latency "
+                                "bound by design; constraint matrix re-read from L2 every iteration"},
+           "e2e": {"value": B * n_e2e / e2e_s, "unit": "PLDP solves/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(B * (256 + wg.PLDP_INFO_DTYPE.itemsize)),
+                   "api": "wg_pldp_solve_batch(WG_MEM_HOST)"}}
+    if want_cpu:
+        res["cpu_baseline"] = cpu_pldp_rate(small, seconds=max(2.0, args.cpu_seconds / 2))
+    for v in list(dev.values()) + [dX, dinfo]:
+        if hasattr(v, "free"):
+            v.free()
+    return res, {"pldp_kernel": {"launches": args.steps, "avg_ms": ms}}
+
+
 def run_cuda(args):
     rank, local_rank, world = dist_env()
     import jrl_walkgen_b200 as wg
@@ -401,6 +506,16 @@ def run_cuda(args):
             herdt["qp_solves_per_s"] = world / float(t[0])
             herdt["closed_loop_qp_solves_per_s"] = world / float(t[1])
             herdt["instances"] = herdt["instances"] * world
+    pldp = None
+    if not args.no_pldp:
+        pldp, pldp_kern = pldp_leg(ctx, wg, args, rank, ctx.fp64_peak_tflops(), want_cpu=(rank == 0 and world == 1))
+        herdt_kern = dict(herdt_kern or {}, **pldp_kern)
+        if dist is not None:
+            import torch
+            t = torch.tensor([1.0 / pldp["pldp_solves_per_s"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pldp["pldp_solves_per_s"] = world / float(t[0])
+            pldp["instances"] = pldp["instances"] * world
 
     if rank == 0:
         # roofline of the dominant kernel (largest share of the timed region)
@@ -443,7 +558,7 @@ def run_cuda(args):
                            "preview_steps_per_pass_per_gpu": steps_per_pass,
                            "l2": "inputs+outputs per pass (%.2f GB) exceed the 126 MB L2" % ((n * 80) / 1e9)},
                 "roofline": roof, "kernels": dict(kern, **(herdt_kern or {})), "fp64_peak_tflops_measured": fp64_peak,
-                "herdt": herdt,
+                "herdt": herdt, "pldp": pldp,
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "passes": e2e_steps, "api": "wg_preview_run_batch(WG_MEM_HOST), pinned host buffers"},
@@ -466,6 +581,8 @@ def main():
     ap.add_argument("--herdt-instances", type=int, default=16384)
     ap.add_argument("--herdt-periods", type=int, default=10)
     ap.add_argument("--no-herdt", action="store_true")
+    ap.add_argument("--pldp-instances", type=int, default=16384)
+    ap.add_argument("--no-pldp", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,7 +56,7 @@ __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(
 // OptCholesky::UpdateCholeskyMatrixFortran (OptCholesky.cpp:171-223): row `i` of L for the active rows act[0..i].
 // Lane j computes M(i,j) = A_act[i] . A_act[j] in the reference's order and then the forward recurrence
 // L(i,j) = (M(i,j) - sum_{k<j} L(i,k) L(j,k)) / L(j,j), with the L(i,k) broadcast as they become final.
-__device__ void chol_add_row(double *L, const int *act, int i, const double *__restrict__ A, int ld, int lane)
+__device__ void chol_add_row(double *L, const int *act, int i, const double *A, int ld, int lane)
 {
   double r = 0.0;
   if (lane <= i) {
@@ -83,9 +83,10 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
             const double *__restrict__ ZMPRef, const double *__restrict__ XkYk, double *__restrict__ X,
             const int *__restrict__ similar, long long similar_stride, const int *__restrict__ nremoved,
             const int *__restrict__ starting, wg_pldp_state *__restrict__ hot, int hot_start, int max_iter,
-            double tol, wg_pldp_info *__restrict__ info)
+            double tol, wg_pldp_info *__restrict__ info, int a_cap)
 {
   __shared__ PldpWarp ws[PLDP_WARPS];
+  extern __shared__ __align__(16) double sA[];   // a_cap doubles per warp: the instance's constraint matrix (0: read it from L2)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const PldpConsts &C = *Cp;
   PldpWarp &w = ws[warp];
@@ -94,14 +95,30 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
     const int m = mvec[b];
     const int ld = m + 1;
     const double *A = DPu + (size_t)b * dpu_stride;
+    if (a_cap > 0 && ld * PLDP_U <= a_cap) {
+      // stage the (m+1) x 32 column-major matrix once: every iteration re-reads all of it
+      double *dst = sA + (size_t)warp * a_cap;
+      const int n = ld * PLDP_U;
+      __syncwarp();
+      if ((((size_t)A) & 15) == 0) {
+        const double2 *src2 = reinterpret_cast<const double2 *>(A);
+        double2 *dst2 = reinterpret_cast<double2 *>(dst);
+        for (int e = lane; e < (n >> 1); e += 32) dst2[e] = __ldg(src2 + e);
+        if ((n & 1) && lane == 0) dst[n - 1] = A[n - 1];
+      } else {
+        for (int e = lane; e < n; e += 32) dst[e] = A[e];
+      }
+      __syncwarp();
+      A = dst;
+    }
     const double *bv = DPx + (size_t)b * dpx_stride;
-    const int *sim = similar ? similar + (size_t)b * similar_stride : nullptr;
     const bool start = starting ? starting[b] != 0 : true;
     const double Dl = D[(size_t)b * PLDP_U + lane];
     const double *zr = ZMPRef + (size_t)b * PLDP_U;
     const double *xk = XkYk + (size_t)b * 6;
     int status = 0;
-    (void)sim;   // A_j = -A_i reuse (PLDPSolver.cpp:570-590) gives bit-identical products; all rows are computed directly
+    // `similar` is accepted for interface parity only: the A_j = -A_i reuse (PLDPSolver.cpp:570-590) yields products
+    // bit-identical to computing every row directly, which is what the lanes do
 
     // ---- ComputeInitialSolution (PLDPSolver.cpp:287-340): lane = i (x part) or i + N (y part)
     const int ii = lane & (N - 1), ax = lane >> 4;
@@ -220,9 +237,6 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
           if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
         }
         if (best < alpha) { alpha = best; if (alpha < 1.0) cand = besti; }
-#ifdef PLDP_DEBUG
-        if (b == 0 && lane == 0) printf("gpu it %d k %d alpha %.17g cand %d\n", it, k, alpha, cand);
-#endif
       }
       status = __reduce_max_sync(0xffffffffu, status);
       if (alpha >= 1.0) { alpha = 1.0; cont = false; }
@@ -448,10 +462,22 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
   } else if (mem != WG_MEM_DEVICE) {
     return WG_ERR_INVALID;
   }
+  // shared-memory copy of each instance's constraint matrix when it fits (dpu_stride bounds (m+1)*32)
+  int a_cap = (int)((pb->dpu_stride + 1) & ~1LL);
+  size_t smem = sizeof(double) * (size_t)a_cap * PLDP_WARPS;
+  if (smem > 200 * 1024) { a_cap = 0; smem = 0; }
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    WG_CUDA(ctx, cudaFuncSetAttribute(pldp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  int grid = (B + PLDP_WARPS - 1) / PLDP_WARPS;
+  const int per_sm = smem ? (int)((227 * 1024) / (smem + sizeof(PldpWarp) * PLDP_WARPS + 1024)) : 8;
+  if (grid > ctx->sm_count * (per_sm > 0 ? per_sm : 1)) grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);
   wg_prof_start(ctx, WG_K_PLDP);
-  pldp_kernel<<<grid_for(ctx, B, PLDP_WARPS), PLDP_WARPS * 32, 0, ctx->stream>>>(
+  pldp_kernel<<<grid, PLDP_WARPS * 32, smem, ctx->stream>>>(
       B, p->d, d.D, d.m, d.DPu, d.dpu_stride, d.DPx, d.dpx_stride, d.ZMPRef, d.XkYk, d.X, d.similar, d.similar_stride,
-      d.n_removed, d.starting, d.hot, pb->hot_start, max_iter, tol, d.info);
+      d.n_removed, d.starting, d.hot, pb->hot_start, max_iter, tol, d.info, a_cap);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   if (mem == WG_MEM_HOST) {

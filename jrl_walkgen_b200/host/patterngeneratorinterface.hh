@@ -1,0 +1,2 @@
+// patterngeneratorinterface.hh - same header name as the reference; the declarations live in walkgen_host.hh
+#include "walkgen_host.hh"

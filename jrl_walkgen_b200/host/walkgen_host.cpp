@@ -1,0 +1,569 @@
+// walkgen_host.cpp - implementation of the host-side class mirror (walkgen_host.hh) over the C ABI.
+// No algorithm lives here: every numerical result comes from libwalkgen_b200's CUDA kernels.
+#include "walkgen_host.hh"
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+
+namespace walkgen_b200 {
+
+wg_ctx *default_context()
+{
+  static wg_ctx *ctx = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ctx) {
+    const char *dev = std::getenv("WG_DEVICE");
+    const int rc = wg_ctx_create(dev ? std::atoi(dev) : 0, &ctx);
+    if (rc != WG_OK || !ctx) {
+      ctx = nullptr;
+      throw std::runtime_error("walkgen_b200: no usable CUDA device (there is no CPU fallback)");
+    }
+  }
+  return ctx;
+}
+
+static void check(int rc, const char *what)
+{
+  if (rc != WG_OK) throw std::runtime_error(std::string("walkgen_b200: ") + what + ": " + wg_last_error(default_context()));
+}
+
+}  // namespace walkgen_b200
+
+using walkgen_b200::check;
+using walkgen_b200::default_context;
+
+namespace PatternGeneratorJRL {
+
+// ---------------------------------------------------------------------------------------------
+// SimplePlugin / SimplePluginManager
+// ---------------------------------------------------------------------------------------------
+SimplePlugin::~SimplePlugin()
+{
+  if (m_SimplePluginManager) m_SimplePluginManager->UnregisterPlugin(this);
+}
+bool SimplePlugin::RegisterMethod(std::string &MethodName)
+{
+  return m_SimplePluginManager ? m_SimplePluginManager->RegisterMethod(MethodName, this) : false;
+}
+bool SimplePluginManager::RegisterMethod(std::string &MethodName, SimplePlugin *aSP)
+{
+  m_SimplePlugins.insert(std::pair<std::string, SimplePlugin *>(MethodName, aSP));
+  return true;
+}
+void SimplePluginManager::UnregisterPlugin(SimplePlugin *aSP)
+{
+  for (auto it = m_SimplePlugins.begin(); it != m_SimplePlugins.end();) {
+    if (it->second == aSP) it = m_SimplePlugins.erase(it);
+    else ++it;
+  }
+}
+bool SimplePluginManager::CallMethod(std::string &MethodName, std::istringstream &istrm)
+{
+  // the rest of the buffer is handed, from its start, to every plugin registered under the name
+  std::string rest;
+  std::getline(istrm, rest, '\0');
+  bool found = false;
+  auto range = m_SimplePlugins.equal_range(MethodName);
+  std::vector<SimplePlugin *> targets;
+  for (auto it = range.first; it != range.second; ++it) targets.push_back(it->second);
+  for (SimplePlugin *sp : targets) {
+    if (!sp) continue;
+    std::istringstream iss(rest);
+    sp->CallMethod(MethodName, iss);
+    found = true;
+  }
+  return found;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PreviewControl
+// ---------------------------------------------------------------------------------------------
+static const PreviewControl *g_gains_owner = nullptr;   // whose gains are loaded in the context
+
+PreviewControl::PreviewControl(SimplePluginManager *lSPM, unsigned int defaultMode, bool computeWeightsAutomatically)
+    : SimplePlugin(lSPM), m_SamplingPeriod(0.0), m_PreviewControlTime(0.0), m_Zc(0.0), m_Coherent(false),
+      m_AutoComputeWeights(computeWeightsAutomatically), m_DefaultWeightComputationMode(defaultMode),
+      m_SizeOfPreviewWindow(0)
+{
+  std::memset(&m_Gains, 0, sizeof m_Gains);
+  std::string names[3] = {":samplingperiod", ":previewcontroltime", ":comheight"};
+  for (auto &n : names) RegisterMethod(n);
+}
+PreviewControl::~PreviewControl()
+{
+  if (g_gains_owner == this) g_gains_owner = nullptr;
+}
+void PreviewControl::SetSamplingPeriod(double v)
+{
+  if (m_SamplingPeriod != v) m_Coherent = false;
+  m_SamplingPeriod = v;
+  if (m_AutoComputeWeights) ComputeOptimalWeights(m_DefaultWeightComputationMode);
+}
+void PreviewControl::SetPreviewControlTime(double v)
+{
+  if (m_PreviewControlTime != v) m_Coherent = false;
+  m_PreviewControlTime = v;
+  if (m_AutoComputeWeights) ComputeOptimalWeights(m_DefaultWeightComputationMode);
+}
+void PreviewControl::SetHeightOfCoM(double v)
+{
+  if (m_Zc != v) m_Coherent = false;
+  m_Zc = v;
+  if (m_AutoComputeWeights) ComputeOptimalWeights(m_DefaultWeightComputationMode);
+}
+void PreviewControl::ComputeOptimalWeights(unsigned int mode)
+{
+  // the reference solves the Riccati equation whatever the parameters; incomplete parameter sets (the plugin
+  // commands arrive one by one) simply leave the object incoherent here
+  if (!(m_SamplingPeriod > 0.0) || !(m_PreviewControlTime > 0.0) || !(m_Zc > 0.0)) return;
+  if (wg_preview_gains(m_SamplingPeriod, m_PreviewControlTime, m_Zc, (int)mode, &m_Gains) != WG_OK) return;
+  m_SizeOfPreviewWindow = (unsigned)m_Gains.NL;
+  m_Coherent = true;
+  if (g_gains_owner == this) g_gains_owner = nullptr;   // force a reload
+}
+void PreviewControl::CallMethod(std::string &Method, std::istringstream &strm)
+{
+  double v;
+  if (Method == ":samplingperiod") { if (strm.good()) { strm >> v; SetSamplingPeriod(v); } }
+  else if (Method == ":previewcontroltime") { if (strm.good()) { strm >> v; SetPreviewControlTime(v); } }
+  else if (Method == ":comheight") { if (strm.good()) { strm >> v; SetHeightOfCoM(v); } }
+  else if (Method == ":computeweightsofpreview") {
+    std::string initialpos;
+    if (strm.good()) {
+      strm >> initialpos;
+      if (initialpos == "withinitialpos") ComputeOptimalWeights(OptimalControllerSolver::MODE_WITH_INITIALPOS);
+      else if (initialpos == "withoutinitialpos") ComputeOptimalWeights(OptimalControllerSolver::MODE_WITHOUT_INITIALPOS);
+    }
+  }
+}
+static void load_gains(const PreviewControl *pc, const wg_preview_gains_t &g)
+{
+  if (g_gains_owner != pc) {
+    check(wg_preview_set_gains(default_context(), &g), "wg_preview_set_gains");
+    g_gains_owner = pc;
+  }
+}
+int PreviewControl::OneIterationOfPreview(MAL_MATRIX(&x, double), MAL_MATRIX(&y, double), double &sxzmp, double &syzmp,
+                                          std::deque<ZMPPosition> &ZMPPositions, unsigned int lindex, double &zmpx2,
+                                          double &zmpy2, bool Simulation)
+{
+  if (!m_Coherent) throw std::runtime_error("PreviewControl: weights not computed");
+  if (ZMPPositions.size() < m_SizeOfPreviewWindow || ZMPPositions.size() - lindex < m_SizeOfPreviewWindow)
+    throw std::runtime_error("ZMPPositions.size()<m_SizeOfPreviewWindow:");   // LTHROW, PreviewControl.cpp:341-344
+  load_gains(this, m_Gains);
+  std::vector<double> w(2 * (size_t)m_SizeOfPreviewWindow);
+  for (unsigned i = 0; i < m_SizeOfPreviewWindow; ++i) {
+    w[2 * i] = ZMPPositions[lindex + i].px;
+    w[2 * i + 1] = ZMPPositions[lindex + i].py;
+  }
+  double xs[3] = {x(0, 0), x(1, 0), x(2, 0)}, ys[3] = {y(0, 0), y(1, 0), y(2, 0)};
+  check(wg_preview_one_iteration(default_context(), xs, ys, &sxzmp, &syzmp, w.data(), (int)m_SizeOfPreviewWindow, &zmpx2,
+                                 &zmpy2, Simulation ? 1 : 0), "wg_preview_one_iteration");
+  for (int i = 0; i < 3; ++i) { x(i, 0) = xs[i]; y(i, 0) = ys[i]; }
+  return 0;
+}
+int PreviewControl::run1d(walkgen_b200::Matrix &x, double &sxzmp, const std::vector<double> &window, double &zmpx2,
+                          bool Simulation)
+{
+  load_gains(this, m_Gains);
+  std::vector<double> w(2 * window.size(), 0.0);
+  for (size_t i = 0; i < window.size(); ++i) w[2 * i] = window[i];
+  double xs[3] = {x(0, 0), x(1, 0), x(2, 0)}, ys[3] = {0, 0, 0}, sy = 0.0, zy = 0.0;
+  check(wg_preview_one_iteration(default_context(), xs, ys, &sxzmp, &sy, w.data(), (int)window.size(), &zmpx2, &zy,
+                                 Simulation ? 1 : 0), "wg_preview_one_iteration");
+  for (int i = 0; i < 3; ++i) x(i, 0) = xs[i];
+  return 0;
+}
+int PreviewControl::OneIterationOfPreview1D(MAL_MATRIX(&x, double), double &sxzmp, std::deque<double> &ZMPPositions,
+                                            unsigned int lindex, double &zmpx2, bool Simulation)
+{
+  if (!m_Coherent) throw std::runtime_error("PreviewControl: weights not computed");
+  // the reference exit(0)s here (PreviewControl.cpp:394-399); an exception is the library-safe equivalent
+  if (ZMPPositions.size() < m_SizeOfPreviewWindow || ZMPPositions.size() - lindex < m_SizeOfPreviewWindow)
+    throw std::runtime_error("ZMPPositions.size()< m_SizeOfPreviewWindow");
+  std::vector<double> w(ZMPPositions.begin() + lindex, ZMPPositions.begin() + lindex + m_SizeOfPreviewWindow);
+  return run1d(x, sxzmp, w, zmpx2, Simulation);
+}
+int PreviewControl::OneIterationOfPreview1D(MAL_MATRIX(&x, double), double &sxzmp, std::vector<double> &Z,
+                                            unsigned int lindex, double &zmpx2, bool Simulation)
+{
+  if (!m_Coherent) throw std::runtime_error("PreviewControl: weights not computed");
+  if (Z.size() < m_SizeOfPreviewWindow) throw std::runtime_error("ZMPPositions.size()< m_SizeOfPreviewWindow");
+  const unsigned NL = m_SizeOfPreviewWindow;
+  const int TestSize = (int)Z.size() - (int)lindex - (int)NL;
+  std::vector<double> w(NL, 0.0);
+  if (TestSize >= 0) {
+    for (unsigned i = 0; i < NL; ++i) w[i] = Z[lindex + i];
+    return run1d(x, sxzmp, w, zmpx2, Simulation);
+  }
+  // wrap-around branch, PreviewControl.cpp:455-466: the reference indexes F with the ABSOLUTE buffer index
+  // (ux += F(i) Z[i] for i in [lindex, size) and again for i in [0, StillToRealized)); reproduced as written
+  for (unsigned i = lindex; i < Z.size() && i < NL; ++i) w[i] += Z[i];
+  const int Still = (int)NL - (int)Z.size() + (int)lindex;
+  for (int i = 0; i < Still && i < (int)NL; ++i) w[i] += Z[i];
+  int rc = run1d(x, sxzmp, w, zmpx2, false);
+  if (Simulation) sxzmp += (Z[lindex] - zmpx2);
+  return rc;
+}
+int PreviewControl::RunWholeTrajectory(const std::deque<ZMPPosition> &Z, MAL_MATRIX(&x, double), MAL_MATRIX(&y, double),
+                                       double &sxzmp, double &syzmp, std::vector<double> &com6, std::vector<double> &zmp2,
+                                       bool Simulation)
+{
+  if (!m_Coherent) throw std::runtime_error("PreviewControl: weights not computed");
+  load_gains(this, m_Gains);
+  wg_ctx *ctx = default_context();
+  const int64_t offs[2] = {0, (int64_t)Z.size()};
+  std::vector<double> w(2 * Z.size());
+  for (size_t i = 0; i < Z.size(); ++i) { w[2 * i] = Z[i].px; w[2 * i + 1] = Z[i].py; }
+  wg_preview_plan *plan = nullptr;
+  check(wg_preview_plan_create(ctx, 1, offs, &plan), "wg_preview_plan_create");
+  double st[8] = {x(0, 0), x(1, 0), x(2, 0), y(0, 0), y(1, 0), y(2, 0), sxzmp, syzmp};
+  com6.assign(6 * Z.size(), 0.0); zmp2.assign(2 * Z.size(), 0.0);
+  const int rc = wg_preview_run_batch(ctx, plan, WG_MEM_HOST, w.data(), st, com6.data(), zmp2.data(), Simulation ? 1 : 0);
+  const int64_t steps = wg_preview_plan_total_steps(plan);
+  wg_preview_plan_destroy(plan);
+  check(rc, "wg_preview_run_batch");
+  for (int i = 0; i < 3; ++i) { x(i, 0) = st[i]; y(i, 0) = st[3 + i]; }
+  sxzmp = st[6]; syzmp = st[7];
+  return (int)steps;
+}
+
+// ---------------------------------------------------------------------------------------------
+// OptCholesky
+// ---------------------------------------------------------------------------------------------
+OptCholesky::OptCholesky(unsigned int lNbMaxOfConstraints, unsigned int lCardU, unsigned int mode)
+    : m_NbMaxOfConstraints(lNbMaxOfConstraints), m_CardU(lCardU), m_A(0), m_L(0), m_iL(0), m_UpdateMode(mode),
+      m_NbOfConstraints(0) {}
+OptCholesky::~OptCholesky() {}
+void OptCholesky::SetToZero() { m_SetActiveConstraints.clear(); }
+void OptCholesky::SetA(double *aA, unsigned int n) { m_A = aA; m_NbOfConstraints = n; }
+void OptCholesky::SetL(double *aL) { m_L = aL; }
+void OptCholesky::SetiL(double *aiL) { m_iL = aiL; }
+int OptCholesky::CurrentNumberOfRows() { return (int)m_SetActiveConstraints.size(); }
+int OptCholesky::AddActiveConstraints(std::vector<unsigned int> &l)
+{
+  int r = 0;
+  for (unsigned li = 0; li < l.size(); ++li) {
+    r = AddActiveConstraint(l[li]);
+    if (r < 0) return -((int)li);
+  }
+  return r;
+}
+int OptCholesky::AddActiveConstraint(unsigned int aConstraint)
+{
+  m_SetActiveConstraints.push_back(aConstraint);
+  if (m_A == 0 || m_L == 0) return 0;   // UpdateCholeskyMatrix* returns -1 but AddActiveConstraint ignores it (:92-104)
+  const int k = (int)m_SetActiveConstraints.size();
+  std::vector<int32_t> rows(m_SetActiveConstraints.begin(), m_SetActiveConstraints.end());
+  const long long a_elems = (m_UpdateMode == MODE_FORTRAN) ? (long long)(m_NbOfConstraints + 1) * m_CardU
+                                                            : (long long)m_NbOfConstraints * m_CardU;
+  const int rc = wg_optcholesky_add_rows_batch(default_context(), WG_MEM_HOST, 1, (int)m_UpdateMode,
+                                               (int)m_NbMaxOfConstraints, (int)m_CardU, (int)m_NbOfConstraints, m_A,
+                                               a_elems, rows.data(), k, k - 1, k, m_L,
+                                               (long long)m_NbMaxOfConstraints * m_NbMaxOfConstraints);
+  check(rc, "wg_optcholesky_add_rows_batch");
+  return 0;
+}
+int OptCholesky::ComputeNormalCholeskyOnANormal()
+{
+  if (m_A == 0 || m_L == 0) return -1;
+  if (m_NbMaxOfConstraints != m_CardU) return -2;
+  check(wg_optcholesky_full_batch(default_context(), WG_MEM_HOST, 1, (int)m_NbMaxOfConstraints, m_A, m_L, nullptr, 0),
+        "wg_optcholesky_full_batch");
+  return 0;
+}
+int OptCholesky::ComputeInverseCholeskyNormal(int mode)
+{
+  if (m_iL == 0) return -1;
+  const int size = (mode == 0) ? (int)m_SetActiveConstraints.size() : (int)m_NbMaxOfConstraints;
+  check(wg_optcholesky_full_batch(default_context(), WG_MEM_HOST, 1, (int)m_NbMaxOfConstraints, nullptr, m_L, m_iL, size),
+        "wg_optcholesky_full_batch");
+  return 0;
+}
+
+}  // namespace PatternGeneratorJRL
+
+// ---------------------------------------------------------------------------------------------
+// PLDPSolver
+// ---------------------------------------------------------------------------------------------
+namespace Optimization {
+namespace Solver {
+
+PLDPSolver::PLDPSolver(unsigned int CardU, double *iPu, double *Px, double *Pu, double *)
+    : m_CardV(CardU)
+{
+  std::memset(&m_Hot, 0, sizeof m_Hot);
+  std::memset(&m_Info, 0, sizeof m_Info);
+  check(wg_pldp_set_constants(default_context(), (int)CardU, iPu, Px, Pu), "wg_pldp_set_constants");
+}
+PLDPSolver::~PLDPSolver() {}
+int PLDPSolver::SolveProblem(double *D, unsigned int NbOfConstraints, double *DPu, double *DPx, double *ZMPRef,
+                             double *XkYk, double *X, std::vector<int> &SimilarConstraint,
+                             unsigned int NumberOfRemovedConstraints, bool StartingSequence)
+{
+  wg_pldp_batch b;
+  std::memset(&b, 0, sizeof b);
+  int32_t m = (int32_t)NbOfConstraints, nrem = (int32_t)NumberOfRemovedConstraints, start = StartingSequence ? 1 : 0;
+  b.D = D; b.m = &m; b.DPu = DPu; b.dpu_stride = (long long)(NbOfConstraints + 1) * 2 * m_CardV;
+  b.DPx = DPx; b.dpx_stride = NbOfConstraints ? NbOfConstraints : 1;
+  b.ZMPRef = ZMPRef; b.XkYk = XkYk; b.X = X;
+  std::vector<int32_t> sim(SimilarConstraint.begin(), SimilarConstraint.end());
+  b.similar = sim.empty() ? nullptr : sim.data(); b.similar_stride = (long long)sim.size();
+  b.n_removed = &nrem; b.starting = &start;
+  b.hot = &m_Hot; b.hot_start = 1;   // m_HotStart = true, PLDPSolver.cpp:65
+  b.max_iterations = 0; b.info = &m_Info;
+  check(wg_pldp_solve_batch(default_context(), WG_MEM_HOST, 1, &b), "wg_pldp_solve_batch");
+  if (m_Info.status == 2) return -2;
+  return m_Info.rc;
+}
+
+}  // namespace Solver
+}  // namespace Optimization
+
+namespace PatternGeneratorJRL {
+
+// ---------------------------------------------------------------------------------------------
+// ZMPRefTrajectoryGeneration (plugin commands of ZMPRefTrajectoryGeneration.cpp:49-110)
+// ---------------------------------------------------------------------------------------------
+ZMPRefTrajectoryGeneration::ZMPRefTrajectoryGeneration(SimplePluginManager *lSPM)
+    : SimplePlugin(lSPM), m_Tsingle(0.), m_Tdble(0.), m_SamplingPeriod(0.005), m_Omega(0.), m_ComHeight(0.),
+      m_StepHeight(0.), m_OnLineMode(false)
+{
+  std::string names[6] = {":omega", ":stepheight", ":singlesupporttime", ":doublesupporttime", ":comheight", ":samplingperiod"};
+  for (auto &n : names) RegisterMethod(n);
+}
+void ZMPRefTrajectoryGeneration::CallMethod(std::string &Method, std::istringstream &strm)
+{
+  if (Method == ":omega") strm >> m_Omega;
+  else if (Method == ":stepheight") strm >> m_StepHeight;
+  else if (Method == ":singlesupporttime") strm >> m_Tsingle;
+  else if (Method == ":doublesupporttime") strm >> m_Tdble;
+  else if (Method == ":comheight") strm >> m_ComHeight;
+  else if (Method == ":samplingperiod") strm >> m_SamplingPeriod;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ZMPVelocityReferencedQP
+// ---------------------------------------------------------------------------------------------
+ZMPVelocityReferencedQP::ZMPVelocityReferencedQP(SimplePluginManager *lSPM, std::string, double sole_length,
+                                                 double sole_width)
+    : ZMPRefTrajectoryGeneration(lSPM), m_SoleLength(sole_length), m_SoleWidth(sole_width), m_ParamsDirty(true),
+      m_StepsBeforeStop(0)
+{
+  std::memset(&m_State, 0, sizeof m_State);
+  wg_herdt_mpc_default_params(&m_Params);
+  m_Tsingle = m_Params.t_single; m_Tdble = m_Params.t_double;
+  std::string names[3] = {":previewcontroltime", ":numberstepsbeforestop", ":stoppg"};
+  for (auto &n : names) RegisterMethod(n);
+}
+ZMPVelocityReferencedQP::~ZMPVelocityReferencedQP() {}
+void ZMPVelocityReferencedQP::CallMethod(std::string &Method, std::istringstream &strm)
+{
+  if (Method == ":numberstepsbeforestop") {
+    unsigned n = 0;
+    strm >> n;
+    m_StepsBeforeStop = n;
+    m_State.sup_steps_left = (int32_t)n;   // CurrentSupport.NbStepsLeft + SupportFSM::NbStepsSSDS (:197-202)
+    m_State.nb_steps_ssds = (int32_t)n;
+  }
+  if (Method == ":stoppg") m_State.ending_phase = 1;
+  ZMPRefTrajectoryGeneration::CallMethod(Method, strm);
+  if (Method == ":singlesupporttime" || Method == ":doublesupporttime") m_ParamsDirty = true;
+}
+int ZMPVelocityReferencedQP::InitOnLine(std::deque<ZMPPosition> &FinalZMPTraj_deq, std::deque<COMState> &FinalCoMPositions_deq,
+                                        std::deque<FootAbsolutePosition> &FinalLeftFootTraj_deq,
+                                        std::deque<FootAbsolutePosition> &FinalRightFootTraj_deq,
+                                        FootAbsolutePosition &InitLeft, FootAbsolutePosition &InitRight,
+                                        std::deque<double> &, COMState &lStartingCOMState, double lStartingZMPPosition[3])
+{
+  wg_ctx *ctx = default_context();
+  wg_herdt_params hp;
+  wg_herdt_default_params(m_SoleLength, m_SoleWidth, &hp);
+  check(wg_herdt_set_params(ctx, &hp), "wg_herdt_set_params");
+  if (m_Tsingle > 0.0) m_Params.t_single = m_Tsingle;
+  if (m_Tdble > 0.0) m_Params.t_double = m_Tdble;
+  check(wg_herdt_mpc_set_params(ctx, &m_Params), "wg_herdt_mpc_set_params");
+  m_ParamsDirty = false;
+  const double init9[9] = {lStartingCOMState.x[0], lStartingCOMState.y[0], lStartingCOMState.z[0],
+                           InitLeft.x, InitLeft.y, InitLeft.theta, InitRight.x, InitRight.y, InitRight.theta};
+  const double keep_ref[3] = {m_State.new_ref[0], m_State.new_ref[1], m_State.new_ref[2]};
+  const int32_t keep_stop = m_State.ending_phase;
+  check(wg_herdt_mpc_init(ctx, WG_MEM_HOST, 1, init9, 0, &m_State), "wg_herdt_mpc_init");
+  for (int i = 0; i < 3; ++i) m_State.new_ref[i] = keep_ref[i];
+  m_State.ending_phase = keep_stop;
+  if (m_StepsBeforeStop) { m_State.sup_steps_left = (int32_t)m_StepsBeforeStop; m_State.nb_steps_ssds = (int32_t)m_StepsBeforeStop; }
+  // the TimeBuffer_/m_SamplingPeriod buffered start samples (ZMPVelocityReferencedQP.cpp:243-271)
+  const int AddArraySize = (int)(m_Params.time_buffer / m_Params.Ts);
+  FinalZMPTraj_deq.assign(AddArraySize, ZMPPosition());
+  FinalCoMPositions_deq.assign(AddArraySize, COMState());
+  FinalLeftFootTraj_deq.assign(AddArraySize, InitLeft);
+  FinalRightFootTraj_deq.assign(AddArraySize, InitRight);
+  double t = 0.0;
+  for (int i = 0; i < AddArraySize; ++i) {
+    ZMPPosition &z = FinalZMPTraj_deq[i];
+    z.px = lStartingZMPPosition[0]; z.py = lStartingZMPPosition[1]; z.pz = lStartingZMPPosition[2];
+    z.theta = 0.0; z.time = t; z.stepType = 0;
+    FinalCoMPositions_deq[i] = lStartingCOMState;
+    FinalLeftFootTraj_deq[i].time = FinalRightFootTraj_deq[i].time = t;
+    FinalLeftFootTraj_deq[i].stepType = FinalRightFootTraj_deq[i].stepType = 10;
+    t += m_Params.Ts;
+  }
+  m_State.com_back[9] = lStartingZMPPosition[0];
+  m_State.com_back[10] = lStartingZMPPosition[1];
+  m_OnLineMode = true;
+  return 0;
+}
+
+static void tick_to_rows(const double *com11, const wg_herdt_foot_sample &L, const wg_herdt_foot_sample &R, double time,
+                         COMState &c, ZMPPosition &z, FootAbsolutePosition &lf, FootAbsolutePosition &rf)
+{
+  c.reset();
+  for (int i = 0; i < 3; ++i) { c.x[i] = com11[i]; c.y[i] = com11[3 + i]; }
+  c.z[0] = com11[6]; c.yaw[0] = com11[7]; c.yaw[1] = com11[8];
+  std::memset(&z, 0, sizeof z);
+  z.px = com11[9]; z.py = com11[10]; z.time = time;
+  const wg_herdt_foot_sample *src[2] = {&L, &R};
+  FootAbsolutePosition *dst[2] = {&lf, &rf};
+  for (int f = 0; f < 2; ++f) {
+    FootAbsolutePosition &o = *dst[f];
+    std::memset(&o, 0, sizeof o);
+    o.x = src[f]->x; o.y = src[f]->y; o.z = src[f]->z; o.theta = src[f]->theta;
+    o.dx = src[f]->dx; o.dy = src[f]->dy; o.dz = src[f]->dz; o.dtheta = src[f]->dtheta;
+    o.ddx = src[f]->ddx; o.ddy = src[f]->ddy;
+    o.time = time;
+  }
+}
+
+void ZMPVelocityReferencedQP::OnLine(double time, std::deque<ZMPPosition> &FinalZMPTraj_deq,
+                                     std::deque<COMState> &FinalCOMTraj_deq,
+                                     std::deque<FootAbsolutePosition> &FinalLeftFootTraj_deq,
+                                     std::deque<FootAbsolutePosition> &FinalRightFootTraj_deq)
+{
+  // ZMPVelocityReferencedQP.cpp:331-346.  On the ticks where no QP fires only the end-of-online-mode test runs (here);
+  // on a firing tick the device loop runs both tests itself with the same clock value.
+  if (!m_State.online_mode) { m_OnLineMode = false; return; }
+  if (!(time + 0.00001 > m_State.upper_time_limit)) {
+    if (m_State.ending_phase && time >= m_State.time_to_stop) m_State.online_mode = 0;
+    m_OnLineMode = m_State.online_mode != 0;
+    return;
+  }
+  wg_ctx *ctx = default_context();
+  if (m_ParamsDirty) {
+    if (m_Tsingle > 0.0) m_Params.t_single = m_Tsingle;
+    if (m_Tdble > 0.0) m_Params.t_double = m_Tdble;
+    check(wg_herdt_mpc_set_params(ctx, &m_Params), "wg_herdt_mpc_set_params");
+    m_ParamsDirty = false;
+  }
+  // the caller owns the clock: make the device loop's first tick land exactly on it (clock + Ts == time)
+  double c0 = time - m_Params.Ts;
+  for (int guard = 0; guard < 4 && c0 + m_Params.Ts != time; ++guard)
+    c0 = std::nextafter(c0, (c0 + m_Params.Ts < time) ? 1e300 : -1e300);
+  m_State.clock = c0;
+  wg_herdt_tick rows[WG_HERDT_TICKS_PER_STEP];
+  std::memset(rows, 0, sizeof rows);
+  check(wg_herdt_mpc_run_batch(ctx, WG_MEM_HOST, 1, 1, &m_State, nullptr, rows, nullptr, nullptr), "wg_herdt_mpc_run_batch");
+  m_OnLineMode = m_State.online_mode != 0;
+  // deques: the inherited last element is final now (the feet part may have been rewritten), then 19 new samples,
+  // then the 20th, which the state keeps as the not-yet-final element
+  COMState c; ZMPPosition z; FootAbsolutePosition lf, rf;
+  const int n = WG_HERDT_TICKS_PER_STEP;
+  tick_to_rows(reinterpret_cast<const double *>(&rows[0]), rows[0].left, rows[0].right, time, c, z, lf, rf);
+  if (!FinalLeftFootTraj_deq.empty()) { lf.time = FinalLeftFootTraj_deq.back().time; FinalLeftFootTraj_deq.back() = lf; }
+  if (!FinalRightFootTraj_deq.empty()) { rf.time = FinalRightFootTraj_deq.back().time; FinalRightFootTraj_deq.back() = rf; }
+  for (int k = 1; k <= n; ++k) {
+    if (k < n)
+      tick_to_rows(reinterpret_cast<const double *>(&rows[k]), rows[k].left, rows[k].right, time + k * m_Params.Ts, c, z, lf, rf);
+    else
+      tick_to_rows(m_State.com_back, m_State.foot[0][2], m_State.foot[1][2], time + k * m_Params.Ts, c, z, lf, rf);
+    FinalCOMTraj_deq.push_back(c);
+    FinalZMPTraj_deq.push_back(z);
+    FinalLeftFootTraj_deq.push_back(lf);
+    FinalRightFootTraj_deq.push_back(rf);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PatternGeneratorInterface (Herdt path)
+// ---------------------------------------------------------------------------------------------
+PatternGeneratorInterface::PatternGeneratorInterface(double sole_length, double sole_width)
+    : SimplePlugin(this), m_InternalClock(0.0), m_AlgorithmforZMPCOM(0), m_Running(false)
+{
+  m_PC = new PreviewControl(this, OptimalControllerSolver::MODE_WITHOUT_INITIALPOS, true);   // PGI.cpp:254
+  m_ZMPVRQP = new ZMPVelocityReferencedQP(this, "", sole_length, sole_width);                // PGI.cpp:247
+  // start configuration of the reference's sample robot in half-sitting (TestHerdt2010 datref, line 1)
+  m_StartCOM.x[0] = 0.0316055; m_StartCOM.y[0] = 0.0; m_StartCOM.z[0] = 0.7116911;
+  std::memset(&m_StartLF, 0, sizeof m_StartLF); std::memset(&m_StartRF, 0, sizeof m_StartRF);
+  m_StartLF.y = 0.09; m_StartRF.y = -0.09;
+  // PGI.cpp:186-201
+  std::string names[] = {":LimitsFeasibility", ":ZMPShiftParameters", ":TimeDistributionParameters", ":stepseq", ":finish",
+                         ":StartOnLineStepSequencing", ":StopOnLineStepSequencing", ":readfilefromkw",
+                         ":SetAlgoForZmpTrajectory", ":SetAutoFirstStep", ":ChangeNextStep", ":samplingperiod",
+                         ":HerdtOnline", ":setVelReference", ":setCoMPerturbationForce"};
+  for (auto &n : names) SimplePlugin::RegisterMethod(n);
+}
+PatternGeneratorInterface::~PatternGeneratorInterface()
+{
+  delete m_ZMPVRQP;
+  delete m_PC;
+  UnregisterPlugin(this);
+}
+void PatternGeneratorInterface::SetStartConfiguration(const COMState &com, const FootAbsolutePosition &lf,
+                                                      const FootAbsolutePosition &rf)
+{
+  m_StartCOM = com; m_StartLF = lf; m_StartRF = rf;
+}
+int PatternGeneratorInterface::ParseCmd(std::istringstream &strm)
+{
+  std::string aCmd;
+  strm >> aCmd;
+  SimplePluginManager::CallMethod(aCmd, strm);
+  return 0;
+}
+int PatternGeneratorInterface::initOnlineHerdt()
+{
+  // PGI.cpp:517-560 (the start configuration comes from SetStartConfiguration instead of the robot model)
+  std::deque<double> rel;
+  double zmp0[3] = {0.0, 0.0, 0.0};
+  m_ZMPVRQP->InitOnLine(m_ZMPPositions, m_COMBuffer, m_LeftFootPositions, m_RightFootPositions, m_StartLF, m_StartRF, rel,
+                        m_StartCOM, zmp0);
+  m_Running = true;
+  return 0;
+}
+void PatternGeneratorInterface::CallMethod(std::string &Method, std::istringstream &strm)
+{
+  if (Method == ":SetAlgoForZmpTrajectory") {
+    std::string algo;
+    strm >> algo;
+    m_AlgorithmforZMPCOM = (algo == "Herdt") ? 1 : 0;
+  } else if (Method == ":HerdtOnline") {
+    initOnlineHerdt();             // the handler takes no argument: the three numbers of the test are ignored (PGI.cpp:1103-1109)
+  } else if (Method == ":setVelReference") {
+    m_ZMPVRQP->Reference(strm);
+  } else if (Method == ":setCoMPerturbationForce") {
+    double x = 0, y = 0;
+    strm >> x >> y;
+    m_ZMPVRQP->setCoMPerturbationForce(x, y);
+  }
+  // the other PGI commands configure subsystems outside the accelerated path (step stack, Kajita strategy): accepted, no-op
+}
+bool PatternGeneratorInterface::RunOneStepOfTheControlLoop(COMState &COMStateOut, ZMPPosition &ZMPTarget,
+                                                           FootAbsolutePosition &LeftFootPosition,
+                                                           FootAbsolutePosition &RightFootPosition)
+{
+  m_InternalClock += 0.005;        // PGI.cpp:1256
+  if (!m_Running) return false;
+  if (m_AlgorithmforZMPCOM == 1)
+    m_ZMPVRQP->OnLine(m_InternalClock, m_ZMPPositions, m_COMBuffer, m_LeftFootPositions, m_RightFootPositions);
+  // CoMAndFootOnlyStrategy::OneGlobalStepOfControl, CoMAndFootOnlyStrategy.cpp:56-124
+  if (m_ZMPPositions.empty() || m_COMBuffer.empty() || m_LeftFootPositions.empty() || m_RightFootPositions.empty()) {
+    m_Running = false;
+    return false;
+  }
+  COMStateOut = m_COMBuffer.front(); ZMPTarget = m_ZMPPositions.front();
+  LeftFootPosition = m_LeftFootPositions.front(); RightFootPosition = m_RightFootPositions.front();
+  m_COMBuffer.pop_front(); m_ZMPPositions.pop_front(); m_LeftFootPositions.pop_front(); m_RightFootPositions.pop_front();
+  return true;
+}
+
+}  // namespace PatternGeneratorJRL

@@ -16,8 +16,6 @@
  * Parity unpinned by golden vectors: the reference ships no test or datref for PLDP.
  */
 #include <cmath>
-#include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -175,7 +173,6 @@ int oracle_pldp_solve(int N, const double *iPu, const double *Px, const double *
       }
     }
     double alpha = Alpha;
-    if (getenv("PLDP_DEBUG")) printf("ora it %d k %zu alpha %.17g cand %d\n", it, k, Alpha, toadd ? (int)which : -1);
     if (alpha >= 1.0) { alpha = 1.0; cont = false; }
     if (alpha < 0.0) { status = 2; cont = false; }
     if (status != 2) for (int i = 0; i < U; ++i) Vk[i] = Vk[i] + alpha * d[i];
@@ -201,6 +198,23 @@ int oracle_pldp_solve(int N, const double *iPu, const double *Px, const double *
   if (info) { info[0] = rc; info[1] = status; info[2] = it; info[3] = (int)act.size(); }
   if (active_out) for (int i = 0; i < 32; ++i) active_out[i] = i < (int)act.size() ? (int)act[i] : -1;
   return rc;
+}
+
+/* B cold-start problems back to back (CPU-baseline loop of bench.py: no Python in the timed region). */
+long oracle_pldp_solve_batch(int N, const double *iPu, const double *Px, const double *Pu, int B, const double *D,
+                             const int *m, const double *DPu, long dpu_stride, const double *DPx, long dpx_stride,
+                             const double *ZMPRef, const double *XkYk, double *X, int *iterations)
+{
+  long fails = 0;
+  int info[4];
+  for (int b = 0; b < B; ++b) {
+    oracle_pldp_solve(N, iPu, Px, Pu, D + (long)b * 2 * N, m[b], DPu + (long)b * dpu_stride, DPx + (long)b * dpx_stride,
+                      ZMPRef + (long)b * 2 * N, XkYk + (long)b * 6, X + (long)b * 2 * N, 0, 1, nullptr, 0, 128, info,
+                      nullptr);
+    if (iterations) iterations[b] = info[2];
+    fails += (info[0] != 0 || info[1] != 0);
+  }
+  return fails;
 }
 
 } /* extern "C" */

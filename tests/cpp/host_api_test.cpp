@@ -1,0 +1,220 @@
+// host_api_test.cpp - drives the host-side C++ class mirror (jrl_walkgen_b200/host) the way the reference's own tests
+// drive jrl-walkgen: tests/TestOptCholesky.cpp, tests/TestHerdt2010.cpp + tests/TestObject.cpp, tests/TestRiccatiEquation.cpp.
+// Run by tests/test_host_cpp_gpu.py on the GPU box; numerical comparison against the golden datref / the oracle is
+// done there on the files this program writes.
+//   host_api_test optcholesky
+//   host_api_test herdt2010 <out.dat> <nticks>
+//   host_api_test preview <out.bin>
+//   host_api_test pldp <in.bin> <out.bin>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include "../../jrl_walkgen_b200/host/PreviewControl.hh"
+#include "../../jrl_walkgen_b200/host/OptCholesky.hh"
+#include "../../jrl_walkgen_b200/host/PLDPSolver.hh"
+#include "../../jrl_walkgen_b200/host/patterngeneratorinterface.hh"
+
+using namespace PatternGeneratorJRL;
+
+// ---- tests/TestOptCholesky.cpp:86-180 ---------------------------------------------------------------------
+static int test_optcholesky()
+{
+  const unsigned NbOfConstraints = 12, CardU = 15;
+  srand(0);
+  std::vector<double> A(NbOfConstraints * CardU);
+  for (unsigned i = 0; i < NbOfConstraints * CardU; ++i) A[i] = (double)rand() / (double)RAND_MAX;
+  std::vector<double> L(NbOfConstraints * NbOfConstraints, 0.0), iL(NbOfConstraints * NbOfConstraints, 0.0);
+  OptCholesky anOCD(NbOfConstraints, CardU, OptCholesky::MODE_NORMAL);
+  anOCD.SetA(A.data(), NbOfConstraints);
+  anOCD.SetL(L.data());
+  anOCD.SetiL(iL.data());
+  for (unsigned i = 0; i < NbOfConstraints; ++i) anOCD.AddActiveConstraint(i);
+  if (anOCD.CurrentNumberOfRows() != (int)NbOfConstraints) return 1;
+  double dist = 0.0;
+  for (unsigned i = 0; i < NbOfConstraints; ++i)
+    for (unsigned j = 0; j < NbOfConstraints; ++j) {
+      double m = 0.0, l = 0.0;
+      for (unsigned k = 0; k < CardU; ++k) m += A[i * CardU + k] * A[j * CardU + k];
+      for (unsigned k = 0; k < NbOfConstraints; ++k) l += L[i * NbOfConstraints + k] * L[j * NbOfConstraints + k];
+      dist += (m - l) * (m - l);
+    }
+  dist = sqrt(dist);
+  std::cout << "distance A A^T - L L^T: " << dist << std::endl;
+  if (dist > 1e-6) return 2;                                       // TestOptCholesky.cpp:143-150
+  // full decomposition of M = A A^T and its inverse (:155-177)
+  const unsigned n = NbOfConstraints;
+  std::vector<double> M(n * n), L2(n * n, 0.0), iL2(n * n, 0.0);
+  for (unsigned i = 0; i < n; ++i)
+    for (unsigned j = 0; j < n; ++j) {
+      double m = 0.0;
+      for (unsigned k = 0; k < CardU; ++k) m += A[i * CardU + k] * A[j * CardU + k];
+      M[i * n + j] = m;
+    }
+  OptCholesky anOCD2(n, n, OptCholesky::MODE_NORMAL);
+  anOCD2.SetA(M.data(), n);
+  anOCD2.SetL(L2.data());
+  anOCD2.SetiL(iL2.data());
+  if (anOCD2.ComputeNormalCholeskyOnANormal() != 0) return 3;
+  if (anOCD2.ComputeInverseCholeskyNormal(1) != 0) return 4;
+  double worst = 0.0;
+  for (unsigned i = 0; i < n; ++i)
+    for (unsigned j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (unsigned k = 0; k < n; ++k) s += iL2[i * n + k] * L2[k * n + j];
+      worst = std::max(worst, fabs(s - (i == j ? 1.0 : 0.0)));
+    }
+  std::cout << "max |iL L - I|: " << worst << std::endl;
+  return worst < 1e-9 ? 0 : 5;
+}
+
+// ---- tests/TestHerdt2010.cpp (OnLine profile) through ParseCmd + the 5 ms tick ------------------------------
+static void cmd(PatternGeneratorInterface &pgi, const char *s)
+{
+  std::istringstream strm(s);
+  pgi.ParseCmd(strm);
+}
+static int test_herdt2010(const char *out, int nticks)
+{
+  PatternGeneratorInterface aPGI;
+  // tests/CommonTools.cpp:56-76 (the first 9 commands, as TestHerdt2010 sends them)
+  const char *common[] = {":comheight 0.8078", ":samplingperiod 0.005", ":previewcontroltime 1.6", ":omega 0.0",
+                          ":stepheight 0.07", ":singlesupporttime 0.78", ":doublesupporttime 0.02", ":armparameters 0.5",
+                          ":LimitsFeasibility 0.0"};
+  for (const char *c : common) cmd(aPGI, c);
+  // tests/TestHerdt2010.cpp:66-90
+  cmd(aPGI, ":SetAlgoForZmpTrajectory Herdt");
+  cmd(aPGI, ":singlesupporttime 0.7");
+  cmd(aPGI, ":doublesupporttime 0.1");
+  cmd(aPGI, ":HerdtOnline 0.2 0.0 0.0");
+  cmd(aPGI, ":numberstepsbeforestop 2");
+  aPGI.VRQP()->SetInitialSupportFrame(0.0, 0.1, 0.0);             // datref-era initial frame
+  std::ofstream aof(out);
+  aof.precision(8);
+  aof.setf(std::ios::scientific, std::ios::floatfield);
+  COMState com; ZMPPosition zmp; FootAbsolutePosition lf, rf;
+  int it = 0;
+  for (; it < nticks; ++it) {
+    if (!aPGI.RunOneStepOfTheControlLoop(com, zmp, lf, rf)) break;
+    // the 38 columns of tests/TestObject.cpp:333-389
+    aof << (it + 1) * 0.005 << " " << com.x[0] << " " << com.y[0] << " " << com.z[0] << " " << com.yaw[0] << " " << com.x[1]
+        << " " << com.y[1] << " " << com.z[1] << " " << zmp.px << " " << zmp.py << " ";
+    const FootAbsolutePosition *ff[2] = {&lf, &rf};
+    for (int f = 0; f < 2; ++f)
+      aof << ff[f]->x << " " << ff[f]->y << " " << ff[f]->z << " " << ff[f]->dx << " " << ff[f]->dy << " " << ff[f]->dz << " "
+          << ff[f]->ddx << " " << ff[f]->ddy << " " << ff[f]->ddz << " " << ff[f]->theta << " " << ff[f]->omega << " "
+          << ff[f]->omega2 << " ";
+    aof << zmp.px << " " << zmp.py << " 0 0" << std::endl;
+    // generateEvent(), tests/TestHerdt2010.cpp:232-244
+    if (it == 5 * 200) cmd(aPGI, ":setVelReference  0.2 0.0 0.0");
+    if (it == 10 * 200) cmd(aPGI, ":setVelReference  0.0 0.2 0.0");
+  }
+  std::cout << "ticks written: " << it << std::endl;
+  return it == nticks ? 0 : 1;
+}
+
+// ---- PreviewControl: tick-by-tick OneIterationOfPreview vs the batched whole-trajectory call -----------------
+static int test_preview(const char *out)
+{
+  SimplePluginManager spm;
+  PreviewControl aPC(&spm, OptimalControllerSolver::MODE_WITHOUT_INITIALPOS, true);
+  std::string m1(":samplingperiod"), m2(":previewcontroltime"), m3(":comheight");
+  { std::istringstream s("0.005"); spm.CallMethod(m1, s); }
+  { std::istringstream s("1.6"); spm.CallMethod(m2, s); }
+  { std::istringstream s("0.814"); spm.CallMethod(m3, s); }
+  if (!aPC.IsCoherent()) return 1;
+  std::cout << "Ks " << aPC.Gains().Ks << " Kx " << aPC.Gains().Kx[0] << " " << aPC.Gains().Kx[1] << " " << aPC.Gains().Kx[2]
+            << " F0 " << aPC.Gains().F[0] << std::endl;
+  const unsigned NL = 320, nsteps = 200;
+  std::deque<ZMPPosition> zmp(NL + nsteps);
+  for (unsigned i = 0; i < zmp.size(); ++i) {
+    zmp[i].px = 0.2 * (i / 160); zmp[i].py = ((i / 160) % 2 ? -0.095 : 0.095); zmp[i].pz = 0; zmp[i].theta = 0;
+    zmp[i].time = i * 0.005; zmp[i].stepType = 1;
+  }
+  MAL_MATRIX_DIM(x, double, 3, 1); MAL_MATRIX_DIM(y, double, 3, 1);
+  double sx = 0, sy = 0, zx = 0, zy = 0;
+  std::vector<double> serial;
+  for (unsigned k = 0; k < nsteps; ++k) {
+    aPC.OneIterationOfPreview(x, y, sx, sy, zmp, k, zx, zy, true);
+    for (int i = 0; i < 3; ++i) serial.push_back(x(i, 0));
+    for (int i = 0; i < 3; ++i) serial.push_back(y(i, 0));
+    serial.push_back(zx); serial.push_back(zy);
+  }
+  MAL_MATRIX_DIM(x2, double, 3, 1); MAL_MATRIX_DIM(y2, double, 3, 1);
+  double sx2 = 0, sy2 = 0;
+  std::vector<double> com6, zmp2;
+  std::deque<ZMPPosition> zcut(zmp.begin(), zmp.begin() + NL + nsteps - 1);
+  const int steps = aPC.RunWholeTrajectory(zcut, x2, y2, sx2, sy2, com6, zmp2, true);
+  if (steps != (int)nsteps) return 2;
+  double worst = 0.0;
+  for (unsigned k = 0; k < nsteps; ++k) {
+    for (int i = 0; i < 6; ++i) worst = std::max(worst, fabs(com6[6 * k + i] - serial[8 * k + i]));
+    worst = std::max(worst, fabs(zmp2[2 * k] - serial[8 * k + 6]));
+  }
+  std::cout << "max |batched - tick by tick|: " << worst << std::endl;
+  // window under-filled: the reference LTHROWs (PreviewControl.cpp:341-344)
+  bool thrown = false;
+  std::deque<ZMPPosition> shortq(zmp.begin(), zmp.begin() + NL - 1);
+  try { aPC.OneIterationOfPreview(x, y, sx, sy, shortq, 0, zx, zy, true); } catch (const std::exception &) { thrown = true; }
+  if (!thrown) return 3;
+  // 1-D variant on a deque<double>
+  std::deque<double> z1(NL + 5);
+  for (unsigned i = 0; i < z1.size(); ++i) z1[i] = zmp[i].px;
+  MAL_MATRIX_DIM(x1, double, 3, 1);
+  double s1 = 0, zz = 0;
+  aPC.OneIterationOfPreview1D(x1, s1, z1, 0, zz, true);
+  if (fabs(x1(0, 0) - serial[0]) > 1e-15) return 4;
+  std::ofstream f(out, std::ios::binary);
+  f.write(reinterpret_cast<const char *>(serial.data()), sizeof(double) * serial.size());
+  return worst < 1e-10 ? 0 : 5;
+}
+
+// ---- PLDPSolver: one problem from a file, through the reference's class interface ---------------------------
+static int test_pldp(const char *in, const char *out)
+{
+  std::ifstream f(in, std::ios::binary);
+  int32_t hdr[2];
+  f.read(reinterpret_cast<char *>(hdr), sizeof hdr);
+  const unsigned N = 16, nprob = (unsigned)hdr[1];
+  std::vector<double> iPu(N * N), Px(N * 3), Pu(N * N), iLQ(4 * N * N, 0.0);
+  f.read(reinterpret_cast<char *>(iPu.data()), 8 * iPu.size());
+  f.read(reinterpret_cast<char *>(Px.data()), 8 * Px.size());
+  f.read(reinterpret_cast<char *>(Pu.data()), 8 * Pu.size());
+  Optimization::Solver::PLDPSolver solver(N, iPu.data(), Px.data(), Pu.data(), iLQ.data());
+  std::ofstream o(out, std::ios::binary);
+  std::vector<int> similar(8 * N, 0);
+  for (unsigned p = 0; p < nprob; ++p) {
+    int32_t mm = 0, nrem = 0, start = 0, pad = 0;
+    f.read(reinterpret_cast<char *>(&mm), 4); f.read(reinterpret_cast<char *>(&nrem), 4);
+    f.read(reinterpret_cast<char *>(&start), 4); f.read(reinterpret_cast<char *>(&pad), 4);
+    const unsigned m = (unsigned)mm;
+    std::vector<double> D(2 * N), DPu((m + 1) * 2 * N), DPx(m), Z(2 * N), xk(6), X(2 * N);
+    f.read(reinterpret_cast<char *>(D.data()), 8 * D.size());
+    f.read(reinterpret_cast<char *>(DPu.data()), 8 * DPu.size());
+    f.read(reinterpret_cast<char *>(DPx.data()), 8 * DPx.size());
+    f.read(reinterpret_cast<char *>(Z.data()), 8 * Z.size());
+    f.read(reinterpret_cast<char *>(xk.data()), 8 * xk.size());
+    const int rc = solver.SolveProblem(D.data(), m, DPu.data(), DPx.data(), Z.data(), xk.data(), X.data(), similar,
+                                       (unsigned)nrem, start != 0);
+    if (rc != 0) return 10 + p;
+    o.write(reinterpret_cast<const char *>(X.data()), 8 * X.size());
+  }
+  return 0;
+}
+
+int main(int argc, char **argv)
+{
+  try {
+    std::string what = argc > 1 ? argv[1] : "";
+    if (what == "optcholesky") return test_optcholesky();
+    if (what == "herdt2010" && argc > 3) return test_herdt2010(argv[2], atoi(argv[3]));
+    if (what == "preview" && argc > 2) return test_preview(argv[2]);
+    if (what == "pldp" && argc > 3) return test_pldp(argv[2], argv[3]);
+    std::cerr << "usage: host_api_test optcholesky | herdt2010 out.dat nticks | preview out.bin | pldp in.bin out.bin" << std::endl;
+    return 64;
+  } catch (const std::exception &e) {
+    std::cerr << "exception: " << e.what() << std::endl;
+    return 65;
+  }
+}

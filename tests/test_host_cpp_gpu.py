@@ -1,0 +1,95 @@
+"""The host-side C++ class mirror (jrl_walkgen_b200/host: PatternGeneratorInterface::ParseCmd, ZMPVelocityReferencedQP,
+PreviewControl, OptCholesky, PLDPSolver - same names and signatures as the reference) driven by tests/cpp/host_api_test.cpp
+the way the reference's own tests drive jrl-walkgen; outputs compared here against the golden datref and the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import pldp_oracle as po
+from jrl_walkgen_b200 import workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "host_api_test")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    return EXE
+
+
+@pytest.mark.gpu
+def test_cpp_testoptcholesky(exe):
+    """tests/TestOptCholesky.cpp through the OptCholesky class: exit code 0 = its own 1e-6 criterion holds."""
+    r = subprocess.run([exe, "optcholesky"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_testherdt2010_online_prefix_matches_datref(exe, tmp_path):
+    """tests/TestHerdt2010.cpp (OnLine profile, t < 25 s) through ParseCmd strings and RunOneStepOfTheControlLoop:
+    the 38-column trace against the reference's datref with the reference's tolerance (TestObject.cpp:475-495)."""
+    out = tmp_path / "TestHerdt2010OnLineTestFGPI.dat"
+    r = subprocess.run([exe, "herdt2010", str(out), "5000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(out)
+    gold = np.load(os.path.join(GOLD, "herdt_online_prefix.npz"))["q"] / 1e7
+    assert rows.shape == (5000, 38)
+    err = np.abs(rows[:, :37] - gold[:, :37])
+    acc = np.zeros(37, bool); acc[[16, 17, 28, 29]] = True      # swing-foot accelerations: see test_herdt_mpc_gpu.py
+    assert err[:, ~acc].max() < 1e-6, (err[:, ~acc].max(), np.unravel_index(err.argmax(), err.shape))
+    assert err[:, acc].max() < 2e-5
+
+
+@pytest.mark.gpu
+def test_cpp_preview_control_matches_oracle(exe, tmp_path):
+    out = tmp_path / "preview.bin"
+    r = subprocess.run([exe, "preview", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(out).reshape(200, 8)
+    g = ol.OracleGains(0.005, 1.6, 0.814, 1)
+    z = np.zeros((520, 2))
+    i = np.arange(520)
+    z[:, 0] = 0.2 * (i // 160); z[:, 1] = np.where((i // 160) % 2 == 1, -0.095, 0.095)
+    st = np.zeros((1, 8))
+    com, zmp, steps = ol.oracle_preview_batch(g, np.array([0, 519]), z[:519], st)
+    assert steps == 200
+    assert np.abs(got[:, :6] - com[:200]).max() < 1e-9 and np.abs(got[:, 6:] - zmp[:200]).max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_cpp_pldpsolver_hot_sequence_matches_oracle(exe, tmp_path):
+    """A hot-started receding-horizon sequence through PLDPSolver::SolveProblem (one solver object, as
+    ZMPConstrainedQPFastFormulation uses it): X bitwise equal to the oracle port."""
+    K = W.DimitrovConstants()
+    rng = np.random.default_rng([9, 1])
+    polys = W._support_polygons(rng, K.N, K.T, count=K.N + 12)
+    xk = np.zeros(6); xk[0], xk[3] = polys[0][0]
+    hot = np.zeros(1, dtype=po.STATE)
+    n_removed = 0
+    blobs, expect = [], []
+    for t in range(12):
+        p = W.pldp_problem_from(K, polys[t:t + K.N], xk)
+        X, info, act = po.oracle_solve(K, W.pldp_pack(K, [p]), 0, hot=hot, starting=(t == 0), n_removed=n_removed)
+        if info[1] != 0:
+            break
+        blobs.append(struct.pack("4i", p["m"], n_removed, int(t == 0), 0) + p["D"].tobytes() + p["DPu"].tobytes()
+                     + p["DPx"].tobytes() + p["ZMPRef"].tobytes() + p["XkYk"].tobytes())
+        expect.append(X)
+        n_removed = p["n_first"]
+        xk = W.pldp_advance(K, xk, X)
+    assert len(expect) >= 6
+    fin = tmp_path / "pldp_in.bin"; fout = tmp_path / "pldp_out.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("2i", 0, len(expect)) + K.iPu.tobytes() + K.Px.tobytes() + K.Pu.tobytes())
+        for b in blobs:
+            f.write(b)
+    r = subprocess.run([exe, "pldp", str(fin), str(fout)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(fout).reshape(len(expect), 32)
+    assert np.array_equal(got, np.array(expect))
