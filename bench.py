@@ -88,6 +88,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def reduce_over_ranks(dist, times, units, device="cuda"):
+    """Multi-GPU reduction of the measurements (the data path itself has no collective): element-wise MAX of the times,
+    SUM of the unit counts.  dist = torch.distributed (nccl on the GPUs, gloo in the CPU tests) or None."""
+    if dist is None:
+        return list(times), list(units)
+    import torch
+    t = torch.tensor(list(times), dtype=torch.float64, device=device)
+    u = torch.tensor(list(units), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t], [float(v) for v in u]
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -478,15 +491,7 @@ def run_cuda(args):
     d2h = comp.nbytes + zmpp.nbytes + stp.nbytes
 
     # ---- max over ranks ----------------------------------------------------------------------
-    total_steps_all = steps_per_pass
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = float(t[0]), float(t[1])
-        s = torch.tensor([steps_per_pass], dtype=torch.float64, device="cuda")
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        total_steps_all = float(s[0])
+    (ms_total, e2e_s), (total_steps_all,) = reduce_over_ranks(dist, [ms_total, e2e_s], [float(steps_per_pass)])
     ms_per_step = ms_total / args.steps
     value = total_steps_all / (ms_per_step * 1e-3)
     e2e_value = total_steps_all * e2e_steps / e2e_s

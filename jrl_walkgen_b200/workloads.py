@@ -14,6 +14,13 @@ from __future__ import annotations
 
 import numpy as np
 
+def shard_instances(B, rank, world):
+    """Instances are independent: rank r of `world` owns the contiguous index range [lo, hi)."""
+    base, rem = divmod(int(B), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 NL = 320
 LEAD_IN = 2 * NL
 PER_STEP = 160
