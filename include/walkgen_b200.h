@@ -378,6 +378,89 @@ int wg_optcholesky_add_rows_batch(wg_ctx *ctx, int mem, int B, int mode, int nb_
  * ComputeInverseCholeskyNormal on the leading inv_size x inv_size block. */
 int wg_optcholesky_full_batch(wg_ctx *ctx, int mem, int B, int n, const double *A, double *L, double *iL, int inv_size);
 
+/* ------------------------------------------------------------------------------------------------
+ * Kajita2003 front end: footsteps -> 5 ms ZMP reference and feet trajectories, batched
+ *   replaces StepStackHandler::ReadStepSequenceAccordingToWalkMode / PrepareForSupportFoot /
+ *                CreateArcInStepStack / FinishOnTheLastCorrectSupportFoot
+ *                (src/StepStackHandler.cpp:128-175, :754-764, :299-457, :872-883)            [host]
+ *            ZMPDiscretization::GetZMPDiscretization = InitOnLine + OnLineAddFoot per step +
+ *                EndPhaseOfTheWalking + FilterOutValues + UpdateCurrentSupportFootPosition
+ *                (src/ZMPRefTrajectoryGeneration/ZMPDiscretization.cpp:145-175, :319-513, :573-1020,
+ *                 :1129-1300, :1046-1107, :515-561)                                          [device]
+ *            FootTrajectoryGenerationStandard::UpdateFootPosition (first overload) and the
+ *                Polynome3/4/5 boundary-value polynomials
+ *                (src/FootTrajectoryGeneration/FootTrajectoryGenerationStandard.cpp:409-563,
+ *                 src/Mathematics/PolynomeFoot.cpp:38-56, :103-126, :177-200)                 [device]
+ * The output ZMP reference has exactly the layout wg_preview_run_batch consumes, so footsteps -> CoM runs
+ * without leaving the GPU (wg_kajita_run_batch).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct wg_rel_step {      /* RelativeFootPosition (include/jrl/walkgen/pgtypes.hh)                  */
+  double sx, sy;                  /* next support foot in the frame of the current one (m)                   */
+  double theta;                   /* relative yaw in DEGREES, as in :stepseq                                 */
+  double ss_time, ds_time;        /* SStime / DStime; ds_time == 0 selects the generator's defaults          */
+  int32_t step_type;              /* 1 normal; 3/4/5 = step-over ZMP shifts (ZMPDiscretization.cpp:700-728)   */
+  int32_t reserved;
+} wg_rel_step;                    /* 48 bytes */
+
+typedef struct wg_zmpdisc_params {
+  double sampling_period;         /* :samplingperiod       0.005                                             */
+  double preview_time;            /* :previewcontroltime   1.6                                               */
+  double t_single, t_double;      /* :singlesupporttime / :doublesupporttime (0.78 / 0.02 in the tests)      */
+  double step_height;             /* :stepheight           0.07                                              */
+  double omega;                   /* :omega (degrees)      0.0                                               */
+  double modulation;              /* m_ModulationSupportCoefficient = 0.9 (ZMPDiscretization.cpp:99)         */
+  double zmp_neutral[2];          /* m_ZMPNeutralPosition (0, 0)                                             */
+  double zmp_shift[4];            /* :ZMPShiftParameters (only used by step types 3/4/5)                     */
+  double foot_b, foot_h, foot_f;  /* m_FootB/H/F: heel, ankle height, toe lengths for the omega correction   */
+  double filter_time;             /* 0.05: window of the sin^2 smoothing filter (ZMPDiscretization.cpp:237)  */
+} wg_zmpdisc_params;
+
+void wg_zmpdisc_default_params(wg_zmpdisc_params *p);   /* the values of tests/CommonTools.cpp:56-69 */
+
+typedef struct wg_foot_sample {   /* the fields of FootAbsolutePosition this path writes */
+  double x, y, z, theta, omega, omega2;    /* theta, omega in degrees */
+} wg_foot_sample;                 /* 48 bytes */
+
+/* StepStackHandler on the host (tiny, sequential, string/command driven in the reference).  Each appends to
+ * steps[*n] (capacity cap) and returns WG_OK or WG_ERR_INVALID when full.  keep_last is m_KeepLastCorrectSupportFoot. */
+int wg_steps_support_foot(wg_rel_step *steps, int cap, int *n, int support_foot, double ss, double ds);
+int wg_steps_arc(wg_rel_step *steps, int cap, int *n, double x, double y, double arc_deg, int support_foot,
+                 double ss, double ds, int *keep_last);
+int wg_steps_last_support(wg_rel_step *steps, int cap, int *n, int keep_last, double ss, double ds);
+
+/* Number of 5 ms samples GetZMPDiscretization emits for a step list (host arithmetic only):
+ * 2*NL lead-in + sum over steps 1.. of round((DS+SS)/T) + round(Tdble/(2T)) + 3*NL. */
+int64_t wg_zmpdisc_sample_count(const wg_zmpdisc_params *p, int n_steps, const wg_rel_step *steps);
+
+/* A Kajita plan = the step stacks of B walks (what StepStackHandler holds when :finish / :stepseq arrives), resident
+ * on the GPU.  Walk b owns steps [step_offsets[b], step_offsets[b+1]) (HOST arrays; uploaded once, a few KB per
+ * walk); init_feet[b] = {left x, y, theta, right x, y, theta} (InitLeft/RightFootAbsolutePosition, theta in degrees).
+ * The plan computes the sample offsets of the ragged batch (walk b owns samples [so[b], so[b+1])) and, when preview
+ * gains are set on the context, an internal wg_preview_plan over them. */
+typedef struct wg_kajita_plan wg_kajita_plan;
+int wg_kajita_plan_create(wg_ctx *ctx, const wg_zmpdisc_params *p, int B, const int64_t *step_offsets_host,
+                          const wg_rel_step *steps_host, const double *init_feet_host, wg_kajita_plan **out);
+int wg_kajita_plan_destroy(wg_kajita_plan *plan);
+const int64_t *wg_kajita_plan_sample_offsets(const wg_kajita_plan *plan);   /* host array of B+1 entries */
+int64_t wg_kajita_plan_total_samples(const wg_kajita_plan *plan);
+int64_t wg_kajita_plan_total_steps(const wg_kajita_plan *plan);             /* preview steps, sum of L_b-NL+1 */
+/* Replace the step values of every walk (same step counts and timings, hence the same sample offsets): the H2D copy
+ * a caller streaming new footstep plans pays per batch.  Asynchronous on the context stream. */
+int wg_kajita_plan_set_steps(wg_kajita_plan *plan, const wg_rel_step *steps_host, const double *init_feet_host);
+
+/* ZMPDiscretization::GetZMPDiscretization for every walk of the plan.  Outputs (any may be NULL), `mem` says where
+ * they live: zmpref_xy [total][2] (px, py) filtered = FinalZMPPositions; zmp_theta [total] (degrees);
+ * left/right [total] feet; step_type [total][3] = stepType of the ZMP, left-foot and right-foot samples. */
+int wg_zmpdisc_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *zmpref_xy, double *zmp_theta,
+                         wg_foot_sample *left, wg_foot_sample *right, int32_t *step_type);
+
+/* Footsteps -> CoM: GetZMPDiscretization followed by the preview loop of wg_preview_run_batch on the same device
+ * buffers; the ZMP reference only leaves the GPU if zmpref_xy != NULL.  state/com_out/zmp_out as in
+ * wg_preview_run_batch.  With WG_MEM_HOST the walks are processed in chunks and the D2H copy of a chunk's outputs
+ * overlaps the kernels of the next one. */
+int wg_kajita_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *state, double *com_out, double *zmp_out,
+                        double *zmpref_xy, wg_foot_sample *left, wg_foot_sample *right, int simulation);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,8 +19,9 @@ QP_INPUT_DTYPE, QP_OUTPUT_DTYPE = _capi.herdt_dtypes()
 FOOT_DTYPE, TICK_DTYPE, MPC_STATE_DTYPE, MPC_STEP_DTYPE = _capi.herdt_mpc_dtypes()
 TICKS_PER_STEP = _capi.HERDT_TICKS_PER_STEP
 PLDP_STATE_DTYPE, PLDP_INFO_DTYPE = _capi.pldp_dtypes()
+REL_STEP_DTYPE, KAJITA_FOOT_DTYPE = _capi.kajita_dtypes()
 
-__all__ = ["Context", "PreviewPlan", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
+__all__ = ["Context", "PreviewPlan", "KajitaPlan", "zmpdisc_default_params", "REL_STEP_DTYPE", "KAJITA_FOOT_DTYPE", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
            "PLDP_STATE_DTYPE", "PLDP_INFO_DTYPE", "FOOT_DTYPE", "TICK_DTYPE", "MPC_STATE_DTYPE", "MPC_STEP_DTYPE", "TICKS_PER_STEP", "QP_INPUT_DTYPE",
            "QP_OUTPUT_DTYPE", "WalkgenError", "device_count",
            "MODE_WITH_INITIALPOS", "MODE_WITHOUT_INITIALPOS", "WG_MEM_HOST", "WG_MEM_DEVICE"]
@@ -51,6 +52,13 @@ def herdt_mpc_default_params() -> HerdtMpcParams:
     """Constants of ZMPVelocityReferencedQP's ctor and the TestHerdt2010 script (step timing 0.7/0.1 s)."""
     p = HerdtMpcParams()
     _capi.load().wg_herdt_mpc_default_params(C.byref(p))
+    return p
+
+
+def zmpdisc_default_params() -> "_capi.ZmpDiscParams":
+    """The ZMPDiscretization / FootTrajectoryGenerationStandard parameters tests/CommonTools.cpp:56-69 sets."""
+    p = _capi.ZmpDiscParams()
+    _capi.load().wg_zmpdisc_default_params(C.byref(p))
     return p
 
 
@@ -175,6 +183,10 @@ class Context:
     def preview_plan(self, offsets) -> "PreviewPlan":
         return PreviewPlan(self, offsets)
 
+    def kajita_plan(self, step_offsets, steps, init_feet, params=None) -> "KajitaPlan":
+        """The step stacks of B walks, resident on the GPU (wg_kajita_plan_create)."""
+        return KajitaPlan(self, step_offsets, steps, init_feet, params)
+
     def preview_one_iteration(self, x, y, sx, sy, window_xy, simulation=True):
         """PreviewControl::OneIterationOfPreview for one instance (host buffers)."""
         x = np.array(x, dtype=np.float64)
@@ -297,6 +309,47 @@ class Context:
         self._check(self.lib.wg_optcholesky_full_batch(self.h, WG_MEM_HOST, B, n, A.ctypes.data, L.ctypes.data,
                                                        None if iL is None else iL.ctypes.data, n))
         return L, iL
+
+
+class KajitaPlan:
+    """Footsteps -> ZMP reference + feet (ZMPDiscretization) -> CoM (preview control) for a ragged batch of walks."""
+
+    def __init__(self, ctx: Context, step_offsets, steps, init_feet, params=None):
+        self.ctx = ctx
+        self.params = params if params is not None else zmpdisc_default_params()
+        self.step_offsets = np.ascontiguousarray(step_offsets, dtype=np.int64)
+        self.B = len(self.step_offsets) - 1
+        steps = np.ascontiguousarray(steps, dtype=REL_STEP_DTYPE)
+        feet = np.ascontiguousarray(init_feet, dtype=np.float64).reshape(self.B, 6)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.wg_kajita_plan_create(ctx.h, C.byref(self.params), self.B,
+                                                 self.step_offsets.ctypes.data_as(_capi.c_i64_p), steps.ctypes.data,
+                                                 feet.ctypes.data, C.byref(h)))
+        self.h = h
+        so = ctx.lib.wg_kajita_plan_sample_offsets(h)
+        self.sample_offsets = np.ctypeslib.as_array(so, shape=(self.B + 1,)).copy()
+        self.total_samples = int(ctx.lib.wg_kajita_plan_total_samples(h))
+        self.total_steps = int(ctx.lib.wg_kajita_plan_total_steps(h))
+
+    def set_steps(self, steps, init_feet=None):
+        self.ctx._check(self.ctx.lib.wg_kajita_plan_set_steps(self.h, _ptr(steps), _ptr(init_feet)))
+
+    def discretize(self, zmpref_xy=None, zmp_theta=None, left=None, right=None, step_type=None, mem=WG_MEM_HOST):
+        """ZMPDiscretization::GetZMPDiscretization for every walk."""
+        self.ctx._check(self.ctx.lib.wg_zmpdisc_run_batch(self.ctx.h, self.h, mem, _ptr(zmpref_xy), _ptr(zmp_theta),
+                                                          _ptr(left), _ptr(right), _ptr(step_type)))
+
+    def run(self, state, com_out=None, zmp_out=None, zmpref_xy=None, left=None, right=None, simulation=True,
+            mem=WG_MEM_HOST):
+        """Footsteps -> CoM on the GPU."""
+        self.ctx._check(self.ctx.lib.wg_kajita_run_batch(self.ctx.h, self.h, mem, _ptr(state), _ptr(com_out),
+                                                         _ptr(zmp_out), _ptr(zmpref_xy), _ptr(left), _ptr(right),
+                                                         int(simulation)))
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.wg_kajita_plan_destroy(self.h)
+            self.h = None
 
 
 class PreviewPlan:

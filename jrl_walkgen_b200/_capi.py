@@ -80,6 +80,24 @@ class PldpBatch(C.Structure):
                 ("max_iterations", C.c_int32), ("info", C.c_void_p)]
 
 
+class ZmpDiscParams(C.Structure):
+    """Mirror of wg_zmpdisc_params."""
+    _fields_ = [("sampling_period", C.c_double), ("preview_time", C.c_double), ("t_single", C.c_double),
+                ("t_double", C.c_double), ("step_height", C.c_double), ("omega", C.c_double),
+                ("modulation", C.c_double), ("zmp_neutral", C.c_double * 2), ("zmp_shift", C.c_double * 4),
+                ("foot_b", C.c_double), ("foot_h", C.c_double), ("foot_f", C.c_double), ("filter_time", C.c_double)]
+
+
+def kajita_dtypes():
+    """numpy mirrors of wg_rel_step (48 B) and wg_foot_sample (48 B)."""
+    np = _np()
+    step = np.dtype([("sx", "f8"), ("sy", "f8"), ("theta", "f8"), ("ss_time", "f8"), ("ds_time", "f8"),
+                     ("step_type", "i4"), ("reserved", "i4")])
+    foot = np.dtype([("x", "f8"), ("y", "f8"), ("z", "f8"), ("theta", "f8"), ("omega", "f8"), ("omega2", "f8")])
+    assert step.itemsize == 48 and foot.itemsize == 48
+    return step, foot
+
+
 def pldp_dtypes():
     """numpy mirrors of wg_pldp_state (392 B) and wg_pldp_info (144 B)."""
     np = _np()
@@ -186,6 +204,23 @@ SIGNATURES = {
                                                 C.c_void_p, C.c_longlong]),
     "wg_optcholesky_full_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int]),
+    "wg_zmpdisc_default_params": (None, [C.POINTER(ZmpDiscParams)]),
+    "wg_steps_support_foot": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, C.c_double, C.c_double]),
+    "wg_steps_arc": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
+                               C.c_double, c_int_p]),
+    "wg_steps_last_support": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, C.c_double, C.c_double]),
+    "wg_zmpdisc_sample_count": (C.c_int64, [C.POINTER(ZmpDiscParams), C.c_int, C.c_void_p]),
+    "wg_kajita_plan_create": (C.c_int, [C.c_void_p, C.POINTER(ZmpDiscParams), C.c_int, c_i64_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_void_p)]),
+    "wg_kajita_plan_destroy": (C.c_int, [C.c_void_p]),
+    "wg_kajita_plan_sample_offsets": (c_i64_p, [C.c_void_p]),
+    "wg_kajita_plan_total_samples": (C.c_int64, [C.c_void_p]),
+    "wg_kajita_plan_total_steps": (C.c_int64, [C.c_void_p]),
+    "wg_kajita_plan_set_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wg_zmpdisc_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "wg_kajita_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int]),
     "wg_herdt_mpc_default_params": (None, [C.POINTER(HerdtMpcParams)]),
     "wg_herdt_mpc_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtMpcParams)]),
     "wg_herdt_mpc_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

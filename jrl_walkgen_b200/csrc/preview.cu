@@ -561,10 +561,11 @@ int wg_preview_plan_destroy(wg_preview_plan *pl)
 int64_t wg_preview_plan_total_steps(const wg_preview_plan *pl) { return pl ? pl->total_steps : 0; }
 int64_t wg_preview_plan_total_samples(const wg_preview_plan *pl) { return pl ? pl->total_samples : 0; }
 
-static int preview_launch(wg_ctx *ctx, wg_preview_plan *pl, const double *d_zmp, double *d_state,
-                          double *d_com, double *d_zmpout, int simulation)
+// Launch over `count` trajectories listed in d_order (device array of trajectory indices of this plan).
+int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count, const double *d_zmp,
+                            double *d_state, double *d_com, double *d_zmpout, int simulation)
 {
-  if (pl->total_steps == 0) return WG_OK;
+  if (pl->total_steps == 0 || count <= 0) return WG_OK;
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
   const int span = FIR_TILE + NLpad;
   const size_t smem = sizeof(double2) * (size_t)(span + (span >> 3) + 2);
@@ -578,12 +579,18 @@ static int preview_launch(wg_ctx *ctx, wg_preview_plan *pl, const double *d_zmp,
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
   wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
   if (simulation)
-    preview_fused_kernel<true><<<pl->B, FIR_THREADS, smem, ctx->stream>>>(pl->d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
+    preview_fused_kernel<true><<<count, FIR_THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
   else
-    preview_fused_kernel<false><<<pl->B, FIR_THREADS, smem, ctx->stream>>>(pl->d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
+    preview_fused_kernel<false><<<count, FIR_THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;
+}
+
+static int preview_launch(wg_ctx *ctx, wg_preview_plan *pl, const double *d_zmp, double *d_state,
+                          double *d_com, double *d_zmpout, int simulation)
+{
+  return wgi_preview_launch_range(ctx, pl, pl->d_order, pl->B, d_zmp, d_state, d_com, d_zmpout, simulation);
 }
 
 int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *zmpref_xy, double *state,

@@ -14,7 +14,7 @@ struct wg_preview_consts;  // preview.cu
 // Kernel ids of the per-kernel CUDA-event profiler (wg_prof_*): bench.py reads the average launch
 // duration of each kernel over the timed region from these.
 enum { WG_K_PREVIEW_FIR = 0, WG_K_PREVIEW_RECUR = 1, WG_K_HERDT_QP = 2, WG_K_HERDT_MPC = 3, WG_K_PLDP = 4,
-       WG_K_OPTCHOL = 5, WG_K_PREVIEW_FUSED = 6, WG_K_COUNT = 8 };
+       WG_K_OPTCHOL = 5, WG_K_PREVIEW_FUSED = 6, WG_K_ZMPDISC = 7, WG_K_COUNT = 8 };
 
 struct wg_prof_state {
   bool on = false;
@@ -84,6 +84,12 @@ inline void wg_prof_stop(wg_ctx *ctx)
   cudaEventRecord(p.ev[2 * p.used + 1], ctx->stream);
   p.used++;
 }
+
+// preview.cu internals used by zmpdisc.cu (the footsteps -> CoM pipeline): launch the fused preview kernel over `count`
+// trajectories listed in the device array d_order.
+extern "C" int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count,
+                                        const double *d_zmp, double *d_state, double *d_com, double *d_zmpout,
+                                        int simulation);
 
 struct wg_device_guard {
   int prev = -1;

@@ -77,6 +77,45 @@ def preview_batch(B, seed=0):
     return offsets, np.ascontiguousarray(np.concatenate(walks, axis=0))
 
 
+def kajita_steps_batch(B, seed=0, ss=0.78, ds=0.02):
+    """Config 2 as FOOTSTEPS (the input of the on-GPU front end, wg_kajita_plan_create): walk b is, with equal odds,
+    a straight walk (:stepseq of 8-20 steps, sx in U[0.05, 0.25], sy = -/+ U[0.19, 0.21] alternating, theta = 0, closed by
+    a half step that brings the feet together) or an arc (:supportfoot 1, :arc 0 R a -1, :lastsupport with R in U[0.5, 2],
+    a in U[30, 180] degrees: StepStackHandler::CreateArcInStepStack through the product's host builder wg_steps_arc).
+    -> (step_offsets int64[B+1], steps REL_STEP_DTYPE[total], init_feet float64[B][6])."""
+    import ctypes as C
+    from . import _capi
+    from . import REL_STEP_DTYPE
+    lib = _capi.load()
+    walks = []
+    for b in range(B):
+        rng = np.random.default_rng([seed, 2, b])
+        if rng.random() < 0.5:
+            n = int(rng.integers(8, 21))
+            st = np.zeros(n + 2, dtype=REL_STEP_DTYPE)
+            side = -1.0
+            st[0]["sy"] = side * rng.uniform(0.095, 0.105)
+            for i in range(1, n + 1):
+                side = -side
+                st[i]["sx"] = rng.uniform(0.05, 0.25)
+                st[i]["sy"] = side * rng.uniform(0.19, 0.21)
+            st[n + 1]["sy"] = -side * rng.uniform(0.19, 0.21)
+            st["ss_time"], st["ds_time"], st["step_type"] = ss, ds, 1
+        else:
+            st = np.zeros(128, dtype=REL_STEP_DTYPE)
+            n = C.c_int(0); keep = C.c_int(0)
+            R = rng.uniform(0.5, 2.0); arc = rng.uniform(30.0, 180.0)
+            assert lib.wg_steps_support_foot(st.ctypes.data, 128, C.byref(n), 1, ss, ds) == 0
+            assert lib.wg_steps_arc(st.ctypes.data, 128, C.byref(n), 0.0, R, arc, -1, ss, ds, C.byref(keep)) == 0
+            assert lib.wg_steps_last_support(st.ctypes.data, 128, C.byref(n), keep.value, ss, ds) == 0
+            st = st[:n.value].copy()
+        walks.append(st)
+    lens = np.array([len(w) for w in walks], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    feet = np.tile(np.array([0.00949035, 0.095, 0.0, 0.00949035, -0.095, 0.0]), (B, 1))
+    return offsets, np.ascontiguousarray(np.concatenate(walks)), np.ascontiguousarray(feet)
+
+
 # ------------------------------------------------------------------------------------------------
 # Config 4 - "Dimitrov ZMPQPWithConstraint PLDPSolver/OptCholesky batched: 16,384 constrained CoP QPs"
 # ------------------------------------------------------------------------------------------------

@@ -6,6 +6,10 @@ Run in the build container (needs /root/reference); the GPU box only sees the co
                             not in the container), stored as int64 of value*1e7 (the datref is truncated
                             to 7 decimals by TestObject.cpp:48-56).
   herdt_emergency_prefix.npz : tests/TestHerdt2010EmergencyStopTestFGPI.datref.cmake rows 0..1027.
+  kajita_<profile>.npz    : tests/TestKajita2003<profile>TestFGPI.datref.cmake, every row, columns 11-13, 20-22
+                            (left foot x y z theta omega omega2), 23-25, 32-34 (right foot), 35-36 (world ZMP
+                            reference): the outputs of ZMPDiscretization + FootTrajectoryGenerationStandard, which do
+                            not depend on the proprietary HRP-2 model.  Also column 1 of the first row.
 """
 import os
 import sys
@@ -29,6 +33,12 @@ def main():
     b = np.loadtxt(os.path.join(REF, "tests", "TestHerdt2010EmergencyStopTestFGPI.datref.cmake"))
     np.savez_compressed(os.path.join(HERE, "herdt_emergency_prefix.npz"), q=quantised(b[:1028]),
                         source="tests/TestHerdt2010EmergencyStopTestFGPI.datref.cmake rows 0..1027", scale=1e7)
+    cols = [10, 11, 12, 19, 20, 21, 22, 23, 24, 31, 32, 33, 34, 35]
+    for prof in ("StraightWalking", "Circle", "PbFlorentSeq1", "PbFlorentSeq2"):
+        src = "tests/TestKajita2003%sTestFGPI.datref.cmake" % prof
+        k = np.loadtxt(os.path.join(REF, src))
+        np.savez_compressed(os.path.join(HERE, "kajita_%s.npz" % prof), q=quantised(k[:, cols]), cols=np.array(cols) + 1,
+                            t0=k[0, 0], source=src, scale=1e7)
     print("written", [f for f in os.listdir(HERE) if f.endswith(".npz")])
 
 

@@ -34,7 +34,7 @@ def test_header_is_plain_c_and_struct_layouts_match_the_python_mirrors(tmp_path)
     prog = tmp_path / "sizes.c"
     structs = ["wg_preview_gains_t", "wg_herdt_params", "wg_herdt_qp_input", "wg_herdt_qp_output", "wg_herdt_mpc_params",
                "wg_herdt_foot_sample", "wg_herdt_tick", "wg_herdt_mpc_state", "wg_herdt_mpc_step", "wg_pldp_state",
-               "wg_pldp_info", "wg_pldp_batch"]
+               "wg_pldp_info", "wg_pldp_batch", "wg_rel_step", "wg_foot_sample", "wg_zmpdisc_params"]
     body = "\n".join(f'  printf("{s} %zu\\n", sizeof({s}));' for s in structs)
     prog.write_text(f'#include <stdio.h>\n#include "{HEADER}"\nint main(void) {{\n{body}\n  return 0;\n}}\n')
     exe = tmp_path / "sizes"
@@ -53,6 +53,9 @@ def test_header_is_plain_c_and_struct_layouts_match_the_python_mirrors(tmp_path)
     assert sizes["wg_herdt_params"] == C.sizeof(_capi.HerdtParams)
     assert sizes["wg_herdt_mpc_params"] == C.sizeof(_capi.HerdtMpcParams)
     assert sizes["wg_pldp_batch"] == C.sizeof(_capi.PldpBatch)
+    assert sizes["wg_rel_step"] == wg.REL_STEP_DTYPE.itemsize == 48
+    assert sizes["wg_foot_sample"] == wg.KAJITA_FOOT_DTYPE.itemsize == 48
+    assert sizes["wg_zmpdisc_params"] == C.sizeof(_capi.ZmpDiscParams)
 
 
 def test_host_only_entry_points_work_without_a_gpu():
