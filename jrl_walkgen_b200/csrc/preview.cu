@@ -222,6 +222,9 @@ struct PreviewConsts {
   // P[sim][l] = M_sim^(FIR_R * 2^l), row-major 4x4; M_sim is the closed-loop one-tick matrix of the
   // 4-state (x, dx, ddx, s) with (sim = 1) or without (sim = 0) the integrated-error update.
   double P[2][SCAN_LEVELS][16];
+  // One tick is X' = M X + g f + h p (f = preview sum, p = ZMP reference of the tick).  State after the FIR_R ticks
+  // of a thread started from zero: sum_r G[sim][r] f_r + H[sim][r] p_r with G[r] = M^(FIR_R-1-r) g, same for H.
+  double G[2][FIR_R][4], H[2][FIR_R][4];
 };
 __constant__ PreviewConsts c_pc;
 __constant__ double c_F[WG_PREVIEW_MAX_NL + 8];
@@ -312,7 +315,10 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
     }
     // window invariant at tap j: w[(j+r) % 8] holds p[8t + r + j]
     const double2 *wp = sp + pad9(FIR_R * t + FIR_R);   // next sample to enter the window
-    for (int jj = 0; jj < NLpad; jj += FIR_R) {
+    // threads whose 8 ticks all lie past the trajectory's last step (ragged last tile) skip the FIR: their
+    // ax/ay stay 0 and nothing downstream of the scan reads them (the scan only propagates upwards)
+    const int ntaps = (start + FIR_R * t < nsteps) ? NLpad : 0;
+    for (int jj = 0; jj < ntaps; jj += FIR_R) {
 #pragma unroll
       for (int u = 0; u < FIR_R; ++u) {
         const double f = c_F[jj + u];
@@ -330,21 +336,35 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
     // re-read from the tile in both passes below rather than kept in registers across the scan
     const double2 *own = sp + pad9(FIR_R * t);
 
-    // ---- (2a) local pass from a zero state (thread 0: from the carried state)
-    Axis cx, cy;
-    if (t == 0) {
-      cx.x0 = s_carry[0]; cx.x1 = s_carry[1]; cx.x2 = s_carry[2]; cx.s = s_carry[6];
-      cy.x0 = s_carry[3]; cy.x1 = s_carry[4]; cy.x2 = s_carry[5]; cy.s = s_carry[7];
-    } else {
-      cx.x0 = cx.x1 = cx.x2 = cx.s = 0.0;
-      cy.x0 = cy.x1 = cy.x2 = cy.s = 0.0;
-    }
-    const Axis inx = cx, iny = cy;
+    // ---- (2a) local aggregate: state after this thread's 8 ticks started from zero, as the linear map of its
+    //      inputs (thread 0 adds M^8 x the carried state)
+    Axis cx, cy, inx, iny;
+    cx.x0 = cx.x1 = cx.x2 = cx.s = 0.0;
+    cy.x0 = cy.x1 = cy.x2 = cy.s = 0.0;
+    inx = cx; iny = cy;
+    {
+      const double(*Gm)[4] = c_pc.G[SIM ? 1 : 0];
+      const double(*Hm)[4] = c_pc.H[SIM ? 1 : 0];
 #pragma unroll
-    for (int r = 0; r < FIR_R; ++r) {
-      const double2 pk = own[r];
-      preview_tick<SIM>(cx, ax[r], pk.x);
-      preview_tick<SIM>(cy, ay[r], pk.y);
+      for (int r = 0; r < FIR_R; ++r) {
+        cx.x0 = fma(Gm[r][0], ax[r], cx.x0); cx.x1 = fma(Gm[r][1], ax[r], cx.x1);
+        cx.x2 = fma(Gm[r][2], ax[r], cx.x2); cx.s = fma(Gm[r][3], ax[r], cx.s);
+        cy.x0 = fma(Gm[r][0], ay[r], cy.x0); cy.x1 = fma(Gm[r][1], ay[r], cy.x1);
+        cy.x2 = fma(Gm[r][2], ay[r], cy.x2); cy.s = fma(Gm[r][3], ay[r], cy.s);
+        if (SIM) {
+          const double2 pk = own[r];
+          cx.x0 = fma(Hm[r][0], pk.x, cx.x0); cx.x1 = fma(Hm[r][1], pk.x, cx.x1);
+          cx.x2 = fma(Hm[r][2], pk.x, cx.x2); cx.s = fma(Hm[r][3], pk.x, cx.s);
+          cy.x0 = fma(Hm[r][0], pk.y, cy.x0); cy.x1 = fma(Hm[r][1], pk.y, cy.x1);
+          cy.x2 = fma(Hm[r][2], pk.y, cy.x2); cy.s = fma(Hm[r][3], pk.y, cy.s);
+        }
+      }
+      if (t == 0) {
+        inx.x0 = s_carry[0]; inx.x1 = s_carry[1]; inx.x2 = s_carry[2]; inx.s = s_carry[6];
+        iny.x0 = s_carry[3]; iny.x1 = s_carry[4]; iny.x2 = s_carry[5]; iny.s = s_carry[7];
+        scan_combine(cx, Pm[0], inx.x0, inx.x1, inx.x2, inx.s);
+        scan_combine(cy, Pm[0], iny.x0, iny.x1, iny.x2, iny.s);
+      }
     }
     // ---- (2b) Kogge-Stone scan over threads: c_t += M^(8d) c_{t-d}
 #pragma unroll
@@ -444,7 +464,7 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
 namespace {
 
 // Closed-loop one-tick matrix of the 4-state (x, dx, ddx, s) and its powers M^(8 2^l), in extended precision.
-void scan_matrices(const wg_preview_gains_t &g, bool sim, double (*P)[16])
+void scan_matrices(const wg_preview_gains_t &g, bool sim, double (*P)[16], double (*G)[4], double (*H)[4])
 {
   typedef long double LD;
   LD M[4][4];
@@ -469,6 +489,23 @@ void scan_matrices(const wg_preview_gains_t &g, bool sim, double (*P)[16])
       }
     std::memcpy(X, Y, sizeof Y);
   };
+  if (G && H) {
+    // g = column of f, h = column of p of one tick; G[r] = M^(FIR_R-1-r) g, H[r] = M^(FIR_R-1-r) h
+    LD g4[4], h4[4] = {0, 0, 0, 0};
+    LD zb = 0;
+    for (int i = 0; i < 3; ++i) { g4[i] = (LD)g.B[i]; zb += (LD)g.C[i] * (LD)g.B[i]; }
+    g4[3] = sim ? -zb : (LD)0;
+    h4[3] = sim ? (LD)1 : (LD)0;
+    for (int r = FIR_R - 1; r >= 0; --r) {
+      for (int i = 0; i < 4; ++i) { G[r][i] = (double)g4[i]; H[r][i] = (double)h4[i]; }
+      LD gn[4], hn[4];
+      for (int i = 0; i < 4; ++i) {
+        gn[i] = 0; hn[i] = 0;
+        for (int k = 0; k < 4; ++k) { gn[i] += M[i][k] * g4[k]; hn[i] += M[i][k] * h4[k]; }
+      }
+      std::memcpy(g4, gn, sizeof gn); std::memcpy(h4, hn, sizeof hn);
+    }
+  }
   for (int r = 1; r < FIR_R; r <<= 1) square(M);   // M^FIR_R (FIR_R is a power of two)
   for (int l = 0; l < SCAN_LEVELS; ++l) {
     for (int i = 0; i < 4; ++i)
@@ -494,8 +531,8 @@ int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *g)
   pc.Ks = g->Ks;
   pc.NL = g->NL;
   pc.NLpad = (g->NL + FIR_R - 1) / FIR_R * FIR_R;
-  scan_matrices(*g, false, pc.P[0]);
-  scan_matrices(*g, true, pc.P[1]);
+  scan_matrices(*g, false, pc.P[0], pc.G[0], pc.H[0]);
+  scan_matrices(*g, true, pc.P[1], pc.G[1], pc.H[1]);
   std::vector<double> F(WG_PREVIEW_MAX_NL + 8, 0.0);
   std::copy(g->F, g->F + g->NL, F.begin());
   WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
