@@ -8,7 +8,7 @@
 // B200-first restructuring.  The reference evaluates, per 5 ms tick and per axis,
 //     u = -Kx.x + Ks.s + sum_{i<NL} F[i] * p[k+i]          (640 MACs through a deque of 48-byte structs)
 // and then the 3-state update.  One kernel, preview_fused_kernel, does all of it; one CTA owns one
-// trajectory and walks it in tiles of 1024 ticks:
+// trajectory and walks it in tiles of 8 x (threads per CTA) ticks (512 by default):
 //   (1) FIR.  The preview sum does not depend on the state, so it is a FIR filter of the ZMP reference
 //       (>94% of the flops: 1280 of 1360 per step).  Each thread produces R=8 consecutive outputs for
 //       both axes from a register-resident sliding window: per tap it issues ONE 128-bit shared-memory
@@ -19,13 +19,17 @@
 //       4-state X = (x, dx, ddx, s) with a CONSTANT closed-loop matrix M (spectral radius 0.983), so the
 //       serial chain of the reference is replaced by: every thread runs its 8 ticks from a zero state
 //       (thread 0: from the carried state) in the reference's statement order; a Kogge-Stone scan over the
-//       128 threads combines them with the constant matrices M^(8 d), d = 1..32 (warp shuffles inside a warp,
+//       CTA's threads combines them with the constant matrices M^(8 d), d = 1..32 (warp shuffles inside a warp,
 //       one shared-memory exchange of the four warp totals across warps); every thread then re-runs its 8 ticks from its true start state and
 //       emits CoM and ZMP.  The last tick's state is carried to the next tile in shared memory.
+//   (3) Stores.  A lane owns 8 consecutive ticks (the sliding window wants that), which is the worst layout for
+//       stores (32 lines per instruction); CoM/ZMP rows are therefore staged two ticks at a time in the dead tile
+//       buffer and written with consecutive lanes on consecutive 16 bytes.
 // The FIR result never goes to HBM: traffic is the streaming minimum (16 B in per tick + the NL-sample
 // halo once per tile, 64 B out).
 //
 #include "wg_common.h"
+#include <cstdlib>
 #include <vector>
 #include <cmath>
 #include <algorithm>
@@ -212,8 +216,6 @@ extern "C" int wg_preview_gains(double T, double preview_time, double zc, int mo
 // Device side
 // ---------------------------------------------------------------------------------------------
 constexpr int FIR_R = 8;                      // ticks per thread
-constexpr int FIR_THREADS = 128;
-constexpr int FIR_TILE = FIR_R * FIR_THREADS; // ticks per tile
 constexpr int SCAN_LEVELS = 6;                // M^(8 d), d = 1, 2, 4, ..., 32 threads
 
 struct PreviewConsts {
@@ -274,14 +276,15 @@ __device__ __forceinline__ void scan_combine(Axis &c, const double *__restrict__
   c.s = fma(P[12], n0, fma(P[13], n1, fma(P[14], n2, fma(P[15], n3, c.s))));
 }
 
-template <bool SIM>
-__global__ void __launch_bounds__(FIR_THREADS, 5)
+template <bool SIM, int FIR_THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(FIR_THREADS, MIN_CTAS)
 preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ offsets,
                      const double2 *__restrict__ p, double *__restrict__ state, double *__restrict__ com,
                      double *__restrict__ zmp)
 {
+  constexpr int FIR_TILE = FIR_R * FIR_THREADS;   // ticks per tile
   extern __shared__ double2 sp[];             // padded tile of (px,py), then the scan exchange area
-  __shared__ double s_tot[FIR_THREADS / 32][8];   // warp totals of the scan (x axis 0..3, y axis 4..7)
+  __shared__ double s_tot[FIR_THREADS / 32 + 1][8];   // warp totals of the scan (x axis 0..3, y axis 4..7)
   __shared__ double s_carry[8];
   const int b = order[blockIdx.x];
   const int64_t o = offsets[b];
@@ -335,6 +338,9 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
     // the ZMP reference of the thread's own ticks (the `ZMPPositions[lindex]` of the error integrator) is
     // re-read from the tile in both passes below rather than kept in registers across the scan
     const double2 *own = sp + pad9(FIR_R * t);
+    double2 pk[FIR_R];                          // kept in registers: the tile buffer becomes the store staging area
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r) pk[r] = SIM ? own[r] : make_double2(0.0, 0.0);
 
     // ---- (2a) local aggregate: state after this thread's 8 ticks started from zero, as the linear map of its
     //      inputs (thread 0 adds M^8 x the carried state)
@@ -352,11 +358,10 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
         cy.x0 = fma(Gm[r][0], ay[r], cy.x0); cy.x1 = fma(Gm[r][1], ay[r], cy.x1);
         cy.x2 = fma(Gm[r][2], ay[r], cy.x2); cy.s = fma(Gm[r][3], ay[r], cy.s);
         if (SIM) {
-          const double2 pk = own[r];
-          cx.x0 = fma(Hm[r][0], pk.x, cx.x0); cx.x1 = fma(Hm[r][1], pk.x, cx.x1);
-          cx.x2 = fma(Hm[r][2], pk.x, cx.x2); cx.s = fma(Hm[r][3], pk.x, cx.s);
-          cy.x0 = fma(Hm[r][0], pk.y, cy.x0); cy.x1 = fma(Hm[r][1], pk.y, cy.x1);
-          cy.x2 = fma(Hm[r][2], pk.y, cy.x2); cy.s = fma(Hm[r][3], pk.y, cy.s);
+          cx.x0 = fma(Hm[r][0], pk[r].x, cx.x0); cx.x1 = fma(Hm[r][1], pk[r].x, cx.x1);
+          cx.x2 = fma(Hm[r][2], pk[r].x, cx.x2); cx.s = fma(Hm[r][3], pk[r].x, cx.s);
+          cy.x0 = fma(Hm[r][0], pk[r].y, cy.x0); cy.x1 = fma(Hm[r][1], pk[r].y, cy.x1);
+          cy.x2 = fma(Hm[r][2], pk[r].y, cy.x2); cy.s = fma(Hm[r][3], pk[r].y, cy.s);
         }
       }
       if (t == 0) {
@@ -429,24 +434,52 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
         else { sx = wx_in; sy = wy_in; }
       }
     }
-    // ---- (2d) final pass: emit CoM / ZMP of the valid ticks
+    // ---- (2d) final pass: emit CoM / ZMP of the valid ticks.  A lane owns 8 consecutive ticks, so direct stores would
+    //      put 32 different 128-byte lines behind every store instruction (measured: 0.34 ms of the 0.83 ms pass).  The
+    //      warp stages two ticks per lane in its slice of the (now dead) tile buffer - every FIR read of the tile
+    //      happened before the barrier above - and copies the slice out with consecutive lanes on consecutive 16 bytes.
     const int k0 = start + FIR_R * t;
     const int last = min(start + FIR_TILE, nsteps) - 1;   // last valid tick of this tile
-    double *pc = com ? com + 6 * (o + k0) : nullptr;
-    double *pz = zmp ? zmp + 2 * (o + k0) : nullptr;
+    {
+      constexpr int CHUNK_C = 7, CHUNK_Z = 3;     // double2 per lane and round: 6 (+1 pad) of CoM, 2 (+1 pad) of ZMP
+      double2 *stg_c = sp + (t >> 5) * (32 * (CHUNK_C + CHUNK_Z));
+      double2 *stg_z = stg_c + 32 * CHUNK_C;
+      const int kw = start + FIR_R * (t & ~31);   // first tick of this warp
+      double2 *gc = reinterpret_cast<double2 *>(com) + 3 * (o + kw);
+      double2 *gz = reinterpret_cast<double2 *>(zmp) + (o + kw);
 #pragma unroll
-    for (int r = 0; r < FIR_R; ++r) {
-      if (k0 + r <= last) {
-        const double2 pk = own[r];
-        const double zx = preview_tick<SIM>(sx, ax[r], pk.x);
-        const double zy = preview_tick<SIM>(sy, ay[r], pk.y);
-        if (pc) {
-          double2 *q = reinterpret_cast<double2 *>(pc + 6 * r);
-          q[0] = make_double2(sx.x0, sx.x1);
-          q[1] = make_double2(sx.x2, sy.x0);
-          q[2] = make_double2(sy.x1, sy.x2);
+      for (int j = 0; j < FIR_R / 2; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = 2 * j + h;
+          if (k0 + r <= last) {
+            const double zx = preview_tick<SIM>(sx, ax[r], pk[r].x);
+            const double zy = preview_tick<SIM>(sy, ay[r], pk[r].y);
+            double2 *q = stg_c + CHUNK_C * lane + 3 * h;
+            q[0] = make_double2(sx.x0, sx.x1);
+            q[1] = make_double2(sx.x2, sy.x0);
+            q[2] = make_double2(sy.x1, sy.x2);
+            stg_z[CHUNK_Z * lane + h] = make_double2(zx, zy);
+          }
         }
-        if (pz) *reinterpret_cast<double2 *>(pz + 2 * r) = make_double2(zx, zy);
+        __syncwarp();
+        if (com) {
+#pragma unroll
+          for (int it = 0; it < 6; ++it) {
+            const int idx = 32 * it + lane, c = idx / 6, part = idx - 6 * c;
+            const int row = kw + FIR_R * c + 2 * j;             // first of the two ticks of lane c in this round
+            if (row + (part >= 3) <= last) gc[3 * (FIR_R * c + 2 * j) + part] = stg_c[CHUNK_C * c + part];
+          }
+        }
+        if (zmp) {
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int idx = 32 * it + lane, c = idx >> 1, part = idx & 1;
+            const int row = kw + FIR_R * c + 2 * j + part;
+            if (row <= last) gz[FIR_R * c + 2 * j + part] = stg_z[CHUNK_Z * c + part];
+          }
+        }
+        __syncwarp();
       }
     }
     if (k0 <= last && last < k0 + FIR_R) {   // the thread that ran the tile's last valid tick carries the state
@@ -515,6 +548,34 @@ void scan_matrices(const wg_preview_gains_t &g, bool sim, double (*P)[16], doubl
 }
 
 }  // namespace
+
+// One CTA shape of the fused kernel: THREADS threads (tile = 8 x THREADS ticks), at least MIN_CTAS resident per SM.
+template <int THREADS, int MIN_CTAS>
+static int preview_launch_shape(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count, const double *d_zmp,
+                                double *d_state, double *d_com, double *d_zmpout, int simulation)
+{
+  const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
+  const int span = FIR_R * THREADS + NLpad;
+  const size_t smem = sizeof(double2) * (size_t)(span + (span >> 3) + 2);
+  if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the FIR tile");
+  static bool attr_set = false;
+  if (!attr_set) {
+    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fused_kernel<true, THREADS, MIN_CTAS>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fused_kernel<false, THREADS, MIN_CTAS>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
+  wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
+  if (simulation)
+    preview_fused_kernel<true, THREADS, MIN_CTAS><<<count, THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
+  else
+    preview_fused_kernel<false, THREADS, MIN_CTAS><<<count, THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
+  wg_prof_stop(ctx);
+  WG_LAUNCHED(ctx);
+  return WG_OK;
+}
 
 extern "C" {
 
@@ -603,25 +664,16 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
                             double *d_state, double *d_com, double *d_zmpout, int simulation)
 {
   if (pl->total_steps == 0 || count <= 0) return WG_OK;
-  const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
-  const int span = FIR_TILE + NLpad;
-  const size_t smem = sizeof(double2) * (size_t)(span + (span >> 3) + 2);
-  if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the FIR tile");
-  static bool attr_set = false;
-  if (!attr_set) {
-    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+  static int shape = -1;   // WG_PREVIEW_SHAPE: tuning knob for the CTA shape (default 64 threads x 8 CTAs/SM, 128 registers, no spills; measured 0.752 ms vs 0.778 (128 x 4) and 0.766 (32 x 16) on config 2)
+  if (shape < 0) {
+    const char *e = getenv("WG_PREVIEW_SHAPE");
+    shape = e ? atoi(e) : 0;
   }
-  const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
-  wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
-  if (simulation)
-    preview_fused_kernel<true><<<count, FIR_THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
-  else
-    preview_fused_kernel<false><<<count, FIR_THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
-  wg_prof_stop(ctx);
-  WG_LAUNCHED(ctx);
-  return WG_OK;
+  switch (shape) {
+  case 1: return preview_launch_shape<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation);
+  case 2: return preview_launch_shape<32, 16>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation);
+  default: return preview_launch_shape<64, 8>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation);
+  }
 }
 
 static int preview_launch(wg_ctx *ctx, wg_preview_plan *pl, const double *d_zmp, double *d_state,
