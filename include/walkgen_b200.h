@@ -230,7 +230,8 @@ typedef struct wg_herdt_mpc_params {
   double hip_acc_limit;     /* uaLimitHipYaw_ 0.1                (:71)                             */
   double feet_cross_limit;  /* uLimitFeet_ 5 deg                 (:73)                             */
   int32_t nb_steps_ssds;    /* SupportFSM NbStepsSSDS 2 (:80); :numberstepsbeforestop overrides    */
-  int32_t pad_;
+  int32_t return_to_centre; /* 1: end-of-walk jerk towards the feet centre (:410-421, since 3.1.8);
+                               0: always apply the QP jerk (the code the committed datrefs were made with) */
 } wg_herdt_mpc_params;
 
 void wg_herdt_mpc_default_params(wg_herdt_mpc_params *out);

@@ -68,7 +68,7 @@ class HerdtMpcParams(C.Structure):
                 ("ds_period", C.c_double), ("dsss_period", C.c_double), ("t_single", C.c_double),
                 ("t_double", C.c_double), ("step_height", C.c_double), ("hip_lower", C.c_double * 2),
                 ("hip_upper", C.c_double * 2), ("foot_vel_limit", C.c_double), ("hip_acc_limit", C.c_double),
-                ("feet_cross_limit", C.c_double), ("nb_steps_ssds", C.c_int32), ("pad_", C.c_int32)]
+                ("feet_cross_limit", C.c_double), ("nb_steps_ssds", C.c_int32), ("return_to_centre", C.c_int32)]
 
 
 class PldpBatch(C.Structure):

@@ -377,7 +377,7 @@ herdt_mpc_kernel(int B, int nsteps, const herdt::Consts *__restrict__ Cp, const 
       // ---- jerk to apply (ZMPVelocityReferencedQP.cpp:404-431)
       double jx = s.jr[0][0], jy = s.jr[1][0];
       int running = 1;
-      if (st.sup_steps_left == 0) {
+      if (M.return_to_centre && st.sup_steps_left == 0) {
         jx = (st.foot[0][0].x + st.foot[1][0].x) / 2 - st.com_front[0];
         jy = (st.foot[0][0].y + st.foot[1][0].y) / 2 - st.com_front[3];
         running = st.running;
@@ -594,6 +594,7 @@ void wg_herdt_mpc_default_params(wg_herdt_mpc_params *p)
   p->hip_acc_limit = 0.1;
   p->feet_cross_limit = 5.0 / 180.0 * PI;
   p->nb_steps_ssds = 2;
+  p->return_to_centre = 1;
 }
 
 int wg_herdt_mpc_set_params(wg_ctx *ctx, const wg_herdt_mpc_params *params)

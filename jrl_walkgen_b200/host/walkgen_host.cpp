@@ -371,6 +371,16 @@ void ZMPVelocityReferencedQP::CallMethod(std::string &Method, std::istringstream
   ZMPRefTrajectoryGeneration::CallMethod(Method, strm);
   if (Method == ":singlesupporttime" || Method == ":doublesupporttime") m_ParamsDirty = true;
 }
+void ZMPVelocityReferencedQP::SetHipYawJoints(double lLeft, double uLeft, double lRight, double uRight,
+                                              double upperVelocityBound)
+{
+  const double lo = -30.0 / 180.0 * M_PI, up = 45.0 / 180.0 * M_PI;   // OrientationsPreview.cpp:50-66
+  m_Params.hip_lower[0] = (lLeft == uLeft) ? lo : lLeft;   m_Params.hip_upper[0] = (lLeft == uLeft) ? up : uLeft;
+  m_Params.hip_lower[1] = (lRight == uRight) ? lo : lRight; m_Params.hip_upper[1] = (lRight == uRight) ? up : uRight;
+  m_Params.foot_vel_limit = fabs(upperVelocityBound);
+  m_ParamsDirty = true;
+}
+
 int ZMPVelocityReferencedQP::InitOnLine(std::deque<ZMPPosition> &FinalZMPTraj_deq, std::deque<COMState> &FinalCoMPositions_deq,
                                         std::deque<FootAbsolutePosition> &FinalLeftFootTraj_deq,
                                         std::deque<FootAbsolutePosition> &FinalRightFootTraj_deq,

@@ -238,6 +238,13 @@ class ZMPVelocityReferencedQP : public ZMPRefTrajectoryGeneration {
   void CallMethod(std::string &Method, std::istringstream &strm);
   /* datref-era initial support frame ("oracle pins") */
   void SetInitialSupportFrame(double x, double y, double yaw) { m_State.sup_x = x; m_State.sup_y = y; m_State.sup_yaw = yaw; }
+  /* what OrientationsPreview's ctor reads from the CjrlHumanoidDynamicRobot (OrientationsPreview.cpp:48-68): hip-yaw
+   * lower/upper bounds (equal bounds -> the reference's -30/+45 deg defaults) and |upperVelocityBound| */
+  void SetHipYawJoints(double lLeft, double uLeft, double lRight, double uRight, double upperVelocityBound);
+  /* end-of-walk jerk towards the feet centre (ZMPVelocityReferencedQP.cpp:410-421, since 3.1.8); default on */
+  void SetReturnToCentre(bool on) { m_Params.return_to_centre = on; m_ParamsDirty = true; }
+  /* the three settings under which the reference's committed TestHerdt2010 datrefs are reproduced */
+  void SetDatrefEra() { SetInitialSupportFrame(0.0, 0.1, 0.0); SetHipYawJoints(0, 0, 0, 0, 0.0); SetReturnToCentre(false); }
   const wg_herdt_mpc_state &State() const { return m_State; }
  private:
   wg_herdt_mpc_state m_State;

@@ -396,6 +396,9 @@ struct Sim {
   /* state */
   double clock = 0.0, UpperTimeLimitToUpdate = 0.0, TimeToStopOnLineMode = -1.0;
   bool OnLineMode = false, EndingPhase = false, Running = false;
+  /* the end-of-walk branch of OnLine (:410-421) was added in 3.1.8 ("Put the CoM at the center of the feet when
+   * stopping"); the committed datrefs predate it - tests switch it off to reproduce them */
+  bool returnToCentre = true;
   double NewRef[3] = {0, 0, 0}, Ref[3] = {0, 0, 0};
   Support Current;
   double comx[3], comy[3], ComHeight = 0.0;  /* LIPM state m_CoM + m_ComHeight */
@@ -812,7 +815,7 @@ struct Sim {
       unsigned currentIndex = comq.size();
       comq.resize((unsigned)(QP_T / Ts) + currentIndex);
       zmpq.resize((unsigned)(QP_T / Ts) + currentIndex);
-      if (States.size() && States[0].NbStepsLeft == 0) {
+      if (returnToCentre && States.size() && States[0].NbStepsLeft == 0) {
         double jx = (lfq[0].x + rfq[0].x) / 2 - comq[0].x[0];
         double jy = (lfq[0].y + rfq[0].y) / 2 - comq[0].y[0];
         if (fabs(jx) < 1e-3 && fabs(jy) < 1e-3) Running = false;
@@ -949,6 +952,7 @@ void oracle_herdt_sim_set_robot(void *h, double lHipL, double uHipL, double lHip
   Sim *s = static_cast<Sim *>(h);
   s->lHipL = lHipL; s->uHipL = uHipL; s->lHipR = lHipR; s->uHipR = uHipR; s->uvLimitFoot = uvLimitFoot;
 }
+void oracle_herdt_sim_set_return_to_centre(void *h, int on) { static_cast<Sim *>(h)->returnToCentre = on != 0; }
 /* Override the initial DS support position.  At the surveyed commit InitOnLine takes it from the left
  * foot (ZMPVelocityReferencedQP.cpp:277-279); the committed datref predates ChangeLog 3.1.8 "Fix PG
  * initialization" and was produced with the support frame at (0, 0.1, 0) - see tests/test_herdt_oracle.py. */

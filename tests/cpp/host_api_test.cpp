@@ -3,7 +3,7 @@
 // Run by tests/test_host_cpp_gpu.py on the GPU box; numerical comparison against the golden datref / the oracle is
 // done there on the files this program writes.
 //   host_api_test optcholesky
-//   host_api_test herdt2010 <out.dat> <nticks>
+//   host_api_test herdt2010 <out.dat> <nticks> [emergency]
 //   host_api_test preview <out.bin>
 //   host_api_test pldp <in.bin> <out.bin>
 #include <cmath>
@@ -75,7 +75,7 @@ static void cmd(PatternGeneratorInterface &pgi, const char *s)
   std::istringstream strm(s);
   pgi.ParseCmd(strm);
 }
-static int test_herdt2010(const char *out, int nticks)
+static int test_herdt2010(const char *out, int nticks, bool emergency)
 {
   PatternGeneratorInterface aPGI;
   // tests/CommonTools.cpp:56-76 (the first 9 commands, as TestHerdt2010 sends them)
@@ -87,9 +87,9 @@ static int test_herdt2010(const char *out, int nticks)
   cmd(aPGI, ":SetAlgoForZmpTrajectory Herdt");
   cmd(aPGI, ":singlesupporttime 0.7");
   cmd(aPGI, ":doublesupporttime 0.1");
-  cmd(aPGI, ":HerdtOnline 0.2 0.0 0.0");
+  cmd(aPGI, emergency ? ":HerdtOnline 0.2 0.0 0.2" : ":HerdtOnline 0.2 0.0 0.0");
   cmd(aPGI, ":numberstepsbeforestop 2");
-  aPGI.VRQP()->SetInitialSupportFrame(0.0, 0.1, 0.0);             // datref-era initial frame
+  aPGI.VRQP()->SetDatrefEra();                                    // the code/robot the datref was made with
   std::ofstream aof(out);
   aof.precision(8);
   aof.setf(std::ios::scientific, std::ios::floatfield);
@@ -107,8 +107,21 @@ static int test_herdt2010(const char *out, int nticks)
           << ff[f]->omega2 << " ";
     aof << zmp.px << " " << zmp.py << " 0 0" << std::endl;
     // generateEvent(), tests/TestHerdt2010.cpp:232-244
-    if (it == 5 * 200) cmd(aPGI, ":setVelReference  0.2 0.0 0.0");
+    if (emergency) {   // generateEventEmergencyStop(), :258-262
+      if (it == 5 * 200) cmd(aPGI, ":setVelReference  0.0 0.0 0.4");
+      if (it == 10 * 200) cmd(aPGI, ":setVelReference  0.2 0.0 -0.2");
+      if (it == 3040) cmd(aPGI, ":setVelReference 0.0 0.0 0.0");
+      if (it == 4160) { cmd(aPGI, ":setVelReference  0.0 0.0 0.0"); cmd(aPGI, ":stoppg"); }
+      continue;
+    }
+    if (it == 5 * 200 || it == 35 * 200 || it == 55 * 200 || it == 75 * 200) cmd(aPGI, ":setVelReference  0.2 0.0 0.0");
     if (it == 10 * 200) cmd(aPGI, ":setVelReference  0.0 0.2 0.0");
+    if (it == 25 * 200 || it == 65 * 200) cmd(aPGI, ":setVelReference  0.0 0.0 -10.");
+    if (it == 45 * 200) cmd(aPGI, ":setVelReference  0.0 0.0 10.0");
+    if (it == 85 * 200) cmd(aPGI, ":setVelReference  0.2 0.0 6.0832");
+    if (it == 95 * 200) cmd(aPGI, ":setVelReference  0.2 0.0 -6.0832");
+    if (it == 105 * 200) cmd(aPGI, ":setVelReference 0.0 0.0 0.0");
+    if (it == 110 * 200) { cmd(aPGI, ":setVelReference  0.0 0.0 0.0"); cmd(aPGI, ":stoppg"); }
   }
   std::cout << "ticks written: " << it << std::endl;
   return it == nticks ? 0 : 1;
@@ -208,7 +221,7 @@ int main(int argc, char **argv)
   try {
     std::string what = argc > 1 ? argv[1] : "";
     if (what == "optcholesky") return test_optcholesky();
-    if (what == "herdt2010" && argc > 3) return test_herdt2010(argv[2], atoi(argv[3]));
+    if (what == "herdt2010" && argc > 3) return test_herdt2010(argv[2], atoi(argv[3]), argc > 4 && std::string(argv[4]) == "emergency");
     if (what == "preview" && argc > 2) return test_preview(argv[2]);
     if (what == "pldp" && argc > 3) return test_pldp(argv[2], argv[3]);
     std::cerr << "usage: host_api_test optcholesky | herdt2010 out.dat nticks | preview out.bin | pldp in.bin out.bin" << std::endl;

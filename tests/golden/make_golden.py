@@ -1,11 +1,11 @@
 """Extract golden vectors from the reference's own test data into small committed fixtures.
 
 Run in the build container (needs /root/reference); the GPU box only sees the committed .npz files.
-  herdt_online_prefix.npz : tests/TestHerdt2010OnLineTestFGPI.datref.cmake rows 0..4999 (t < 25 s: the
-                            translation-only prefix; later rows involve robot-specific hip-yaw limits that are
-                            not in the container), stored as int64 of value*1e7 (the datref is truncated
-                            to 7 decimals by TestObject.cpp:48-56).
-  herdt_emergency_prefix.npz : tests/TestHerdt2010EmergencyStopTestFGPI.datref.cmake rows 0..1027.
+  herdt_online_full.npz   : tests/TestHerdt2010OnLineTestFGPI.datref.cmake, all 22 348 rows x 38 columns, stored as
+                            int64 of value*1e7 (the datref is truncated to 7 decimals by TestObject.cpp:48-56):
+                            first row `q0` + row-to-row differences `dq` (int32; compresses 10x better).
+                            Read back with tests/herdt_oracle.py:load_golden().
+  herdt_emergency_full.npz : tests/TestHerdt2010EmergencyStopTestFGPI.datref.cmake, all 4 508 rows, same coding.
   kajita_<profile>.npz    : tests/TestKajita2003<profile>TestFGPI.datref.cmake, every row, columns 11-13, 20-22
                             (left foot x y z theta omega omega2), 23-25, 32-34 (right foot), 35-36 (world ZMP
                             reference): the outputs of ZMPDiscretization + FootTrajectoryGenerationStandard, which do
@@ -27,12 +27,13 @@ def quantised(a):
 
 
 def main():
-    a = np.loadtxt(os.path.join(REF, "tests", "TestHerdt2010OnLineTestFGPI.datref.cmake"))
-    np.savez_compressed(os.path.join(HERE, "herdt_online_prefix.npz"), q=quantised(a[:5000]),
-                        source="tests/TestHerdt2010OnLineTestFGPI.datref.cmake rows 0..4999", scale=1e7)
-    b = np.loadtxt(os.path.join(REF, "tests", "TestHerdt2010EmergencyStopTestFGPI.datref.cmake"))
-    np.savez_compressed(os.path.join(HERE, "herdt_emergency_prefix.npz"), q=quantised(b[:1028]),
-                        source="tests/TestHerdt2010EmergencyStopTestFGPI.datref.cmake rows 0..1027", scale=1e7)
+    for name, out in (("TestHerdt2010OnLineTestFGPI", "herdt_online_full.npz"),
+                      ("TestHerdt2010EmergencyStopTestFGPI", "herdt_emergency_full.npz")):
+        src = "tests/%s.datref.cmake" % name
+        q = quantised(np.loadtxt(os.path.join(REF, src)))
+        dq = np.diff(q, axis=0)
+        assert np.abs(dq).max() < 2**31
+        np.savez_compressed(os.path.join(HERE, out), q0=q[0], dq=dq.astype(np.int32), source=src, scale=1e7)
     cols = [10, 11, 12, 19, 20, 21, 22, 23, 24, 31, 32, 33, 34, 35]
     for prof in ("StraightWalking", "Circle", "PbFlorentSeq1", "PbFlorentSeq2"):
         src = "tests/TestKajita2003%sTestFGPI.datref.cmake" % prof

@@ -35,6 +35,7 @@ def lib():
                                            C.c_int, C.c_int]
         L.oracle_herdt_sim_delete.argtypes = [C.c_void_p]
         L.oracle_herdt_sim_set_robot.argtypes = [C.c_void_p] + [C.c_double] * 5
+        L.oracle_herdt_sim_set_return_to_centre.argtypes = [C.c_void_p, C.c_int]
         L.oracle_herdt_sim_set_initial_support.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         L.oracle_herdt_sim_set_vel_ref.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         L.oracle_herdt_sim_steps_before_stop.argtypes = [C.c_void_p, C.c_uint]
@@ -59,6 +60,13 @@ def default_params(sole_length=0.25, sole_width=0.14):
     return p
 
 
+def load_golden(name):
+    """tests/golden/herdt_<name>_full.npz -> the reference datref as float rows [time, 37 columns] (see make_golden.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "herdt_%s_full.npz" % name))
+    q = np.concatenate([z["q0"][None, :].astype(np.int64), z["dq"].astype(np.int64)], axis=0).cumsum(axis=0)
+    return q / 1e7
+
+
 class Sim:
     """Closed-loop TestHerdt2010 harness around the oracle."""
 
@@ -71,6 +79,17 @@ class Sim:
 
     def initial_support(self, x, y, yaw):
         lib().oracle_herdt_sim_set_initial_support(self.h, x, y, yaw)
+
+    def datref_era(self):
+        """The three settings that make the surveyed code path reproduce the reference's committed datrefs, which are
+        older than the source (oracle pins): (1) initial double-support frame at (0, 0.1, 0) (pre-3.1.8
+        InitOnLine), (2) hip-yaw velocity bound 0 = what OrientationsPreview.cpp:67 reads from a robot file without
+        velocity limits (the test robot's; hip angle limits equal -> the -30/+45 deg defaults of :52-53), (3) no
+        return-to-centre jerk at the end of the walk (ZMPVelocityReferencedQP.cpp:410-421 was added in 3.1.8)."""
+        self.initial_support(0.0, 0.1, 0.0)
+        d = np.pi / 180.0
+        lib().oracle_herdt_sim_set_robot(self.h, -30 * d, 45 * d, -30 * d, 45 * d, 0.0)
+        lib().oracle_herdt_sim_set_return_to_centre(self.h, 0)
 
     def vel_ref(self, x, y, yaw):
         lib().oracle_herdt_sim_set_vel_ref(self.h, x, y, yaw)
@@ -98,11 +117,47 @@ class Sim:
             self.h = None
 
 
-def run_online_script(nticks, events, initial_support=None, **kw):
+# tests/TestHerdt2010.cpp:225-244 (generateEventOnLineWalking) and :258-262 (generateEventEmergencyStop):
+# (tick at which the ParseCmd is issued, :setVelReference arguments, followed by :stoppg?)
+ONLINE_SCRIPT = [(5 * 200, (0.2, 0.0, 0.0), False),           # walkForward
+                 (10 * 200, (0.0, 0.2, 0.0), False),          # walkSidewards
+                 (25 * 200, (0.0, 0.0, -10.0), False),        # startTurningRightOnSpot
+                 (35 * 200, (0.2, 0.0, 0.0), False),
+                 (45 * 200, (0.0, 0.0, 10.0), False),         # startTurningLeftOnSpot
+                 (55 * 200, (0.2, 0.0, 0.0), False),
+                 (65 * 200, (0.0, 0.0, -10.0), False),
+                 (75 * 200, (0.2, 0.0, 0.0), False),
+                 (85 * 200, (0.2, 0.0, 6.0832), False),       # startTurningLeft
+                 (95 * 200, (0.2, 0.0, -6.0832), False),      # startTurningRight
+                 (105 * 200, (0.0, 0.0, 0.0), False),         # stop
+                 (110 * 200, (0.0, 0.0, 0.0), True)]          # stopOnLineWalking (:setVelReference 0 0 0 + :stoppg)
+EMERGENCY_SCRIPT = [(5 * 200, (0.0, 0.0, 0.4), False),        # startTurningLeft2
+                    (10 * 200, (0.2, 0.0, -0.2), False),      # startTurningRight2
+                    (3040, (0.0, 0.0, 0.0), False),           # 15.2*200 stop
+                    (4160, (0.0, 0.0, 0.0), True)]            # 20.8*200 stopOnLineWalking
+
+
+def events_from(script):
+    def make(v, stop):
+        def ev(s):
+            s.vel_ref(*v)
+            if stop:
+                s.stoppg()
+        return ev
+    return {t: make(v, stop) for t, v, stop in script}
+
+
+ONLINE_EVENTS = events_from(ONLINE_SCRIPT)
+EMERGENCY_EVENTS = events_from(EMERGENCY_SCRIPT)
+
+
+def run_online_script(nticks, events, initial_support=None, datref_era=False, **kw):
     """TestHerdt2010 OnLine: tests/TestHerdt2010.cpp:66-90 (start) and :232-244 (events).  `events` maps the tick
     index (m_OneStep.NbOfIt at the time generateEvent() runs) to a callable(sim)."""
     sim = Sim(**kw)
     sim.steps_before_stop(2)
+    if datref_era:
+        sim.datref_era()
     if initial_support is not None:
         sim.initial_support(*initial_support)
     rows = np.zeros((nticks, 37))

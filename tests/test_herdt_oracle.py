@@ -1,13 +1,16 @@
 """Pins for the Herdt2010 oracle (oracle/oracle_herdt.cpp, oracle/oracle_qp.cpp) - all CPU.
 
-Golden vector: the reference's own tests/TestHerdt2010OnLineTestFGPI.datref.cmake (rows 0..4999, t < 25 s),
-committed as tests/golden/herdt_online_prefix.npz by tests/golden/make_golden.py.  The reference compares every
-column with |delta| < 1e-6 on 7-decimal-truncated values (tests/TestObject.cpp:475-495); so do we.
+Golden vectors: the reference's own tests/TestHerdt2010OnLineTestFGPI.datref.cmake (ALL 22 348 rows: translations,
+turns on the spot, curved walking, stop) and tests/TestHerdt2010EmergencyStopTestFGPI.datref.cmake (all 4 508 rows),
+committed as tests/golden/herdt_{online,emergency}_full.npz by tests/golden/make_golden.py.  The reference compares
+every column with |delta| < 1e-6 on 7-decimal-truncated values (tests/TestObject.cpp:475-495); so do we.
 
-Finding (documented in DESIGN.md): the committed datref was generated before ChangeLog 3.1.8 "Fix PG
-initialization": its first velocity event is only reproduced when the initial double-support frame is
-(0, 0.1, 0) instead of the left-foot position the surveyed InitOnLine uses
-(ZMPVelocityReferencedQP.cpp:277-279).  Everything else is the surveyed code path, restated.
+Finding (documented in DESIGN.md): the committed datrefs are older than the source (ChangeLog 3.1.8).  They are
+reproduced, every row and column, by the surveyed code path with three datref-era settings (herdt_oracle.Sim.datref_era):
+initial double-support frame (0, 0.1, 0) instead of the left-foot position (ZMPVelocityReferencedQP.cpp:277-279,
+"Fix PG initialization"); hip-yaw velocity bound 0 (what OrientationsPreview.cpp:67 reads from the test robot) with
+the default -30/+45 deg angle limits; and no return-to-centre jerk at the end of the walk (:410-421, "Put the CoM at
+the center of the feet when stopping").  Each of the three is shown to matter below.
 """
 import ctypes as C
 import os
@@ -17,9 +20,7 @@ import pytest
 
 import herdt_oracle as ho
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-EVENTS = {5 * 200: lambda s: s.vel_ref(0.2, 0.0, 0.0),      # walkForward      tests/TestHerdt2010.cpp:232
-          10 * 200: lambda s: s.vel_ref(0.0, 0.2, 0.0)}     # walkSidewards    tests/TestHerdt2010.cpp:233
+EVENTS = ho.ONLINE_EVENTS
 
 
 @pytest.fixture(scope="module")
@@ -35,10 +36,64 @@ def test_reference_qld_object_code_is_the_solver_here():
     assert ho.lib().oracle_herdt_have_ref_qld() == 1
 
 
+def _check_full(name, events):
+    gold = ho.load_golden(name)
+    sim, rows = ho.run_online_script(len(gold), events, datref_era=True)
+    sim.close()
+    assert np.allclose(gold[:, 0], 0.005 * np.arange(1, len(gold) + 1), atol=1e-9)
+    err = np.abs(rows[:, :36] - gold[:, 1:37])
+    assert err.max() < 1e-6, (err.max(), np.unravel_index(err.argmax(), err.shape))
+    return gold, rows, err
+
+
+def test_oracle_reproduces_whole_online_datref():
+    """All 22 348 rows x 36 columns of TestHerdt2010OnLine: 1117 QPs through the reference's own ql0001_."""
+    gold, rows, err = _check_full("online", ho.ONLINE_EVENTS)
+    assert gold.shape == (22348, 38)
+    assert err.max() < 3.5e-7                                  # 1e-7 truncation + QLD's 1e-8 tolerance through the loop
+    assert np.abs(gold[:, 4]).max() > 0.8 and np.abs(gold[:, 19]).max() > 40.0   # trunk yaw (rad), foot yaw (deg) exercised
+    assert np.abs(rows[-1, :2] - gold[-1, 1:3]).max() < 1e-6
+
+
+def test_oracle_reproduces_whole_emergency_stop_datref():
+    gold, rows, err = _check_full("emergency", ho.EMERGENCY_EVENTS)
+    assert gold.shape == (4508, 38)
+    assert err.max() < 5e-7
+
+
+def test_each_datref_era_setting_matters():
+    """Surveyed-HEAD behaviour differs from the committed datref exactly where the three settings act."""
+    gold = ho.load_golden("online")
+    d = np.pi / 180.0
+    # (2) a non-zero hip-yaw velocity bound (HRP-2's 3.54108 rad/s): first difference at the first QP after the
+    # first rotation command (tick 5000 -> row 5028)
+    sim = ho.Sim(); sim.steps_before_stop(2); sim.datref_era()
+    ho.lib().oracle_herdt_sim_set_robot(sim.h, -30 * d, 45 * d, -30 * d, 45 * d, 3.54108)
+    rows = np.zeros((5600, 37))
+    for it in range(5600):
+        rows[it] = sim.tick()[1]
+        if it in ho.ONLINE_EVENTS:
+            ho.ONLINE_EVENTS[it](sim)
+    sim.close()
+    bad = np.nonzero(np.abs(rows[:, :36] - gold[:5600, 1:37]).max(axis=1) > 1e-6)[0]
+    assert bad[0] == 5028
+    # (3) with the return-to-centre branch the emergency-stop trace leaves the datref only once the last step is taken
+    golde = ho.load_golden("emergency")
+    sim = ho.Sim(); sim.steps_before_stop(2); sim.datref_era()
+    ho.lib().oracle_herdt_sim_set_return_to_centre(sim.h, 1)
+    rows = np.zeros((len(golde), 37))
+    for it in range(len(golde)):
+        rows[it] = sim.tick()[1]
+        if it in ho.EMERGENCY_EVENTS:
+            ho.EMERGENCY_EVENTS[it](sim)
+    sim.close()
+    bad = np.nonzero(np.abs(rows[:, :36] - golde[:, 1:37]).max(axis=1) > 1e-6)[0]
+    assert bad[0] > 3040 + 600
+
+
 def test_oracle_reproduces_reference_datref_prefix(online_run):
     sim, rows = online_run
-    gold = np.load(os.path.join(GOLD, "herdt_online_prefix.npz"))["q"] / 1e7
-    assert gold.shape == (5000, 38)
+    gold = ho.load_golden("online")[:5000]
     assert np.allclose(gold[:, 0], 0.005 * np.arange(1, 5001), atol=1e-9)
     err = np.abs(rows[:, :36] - gold[:, 1:37])
     # datref is truncated to 7 decimals -> up to 1e-7 of quantisation; reference tolerance is 1e-6
@@ -51,7 +106,7 @@ def test_oracle_without_datref_era_override_differs_only_in_first_ds(online_run)
     """With the surveyed InitOnLine (support frame = left foot) only the QPs solved while the robot is still in
     its initial double support differ, and only laterally."""
     sim2, rows2 = ho.run_online_script(1300, EVENTS, logging=False)
-    gold = np.load(os.path.join(GOLD, "herdt_online_prefix.npz"))["q"] / 1e7
+    gold = ho.load_golden("online")
     err = np.abs(rows2[:, :36] - gold[:1300, 1:37])
     xcols = [0, 4, 7, 9, 21]  # CoM x, dx, ZMP x, LF x, RF x
     assert err[:, xcols].max() < 1e-6
@@ -61,7 +116,7 @@ def test_oracle_without_datref_era_override_differs_only_in_first_ds(online_run)
 
 
 def test_emergency_stop_rest_prefix():
-    gold = np.load(os.path.join(GOLD, "herdt_emergency_prefix.npz"))["q"] / 1e7
+    gold = ho.load_golden("emergency")[:1028]
     sim, rows = ho.run_online_script(1028, {}, initial_support=(0.0, 0.1, 0.0))
     assert np.abs(rows[:, :36] - gold[:, 1:37]).max() < 1e-6
     sim.close()
