@@ -314,6 +314,111 @@ def herdt_leg(ctx, wg, args, rank, fp64_peak, want_cpu):
 
 
 # ------------------------------------------------------------------------------------------------
+# Kajita front end + preview: footsteps -> 5 ms ZMP reference + feet -> CoM without leaving the GPU
+# ------------------------------------------------------------------------------------------------
+def kajita_leg(ctx, wg, args, rank, hbm_peak):
+    from jrl_walkgen_b200 import workloads
+    B = args.walks
+    off, steps, feet = workloads.kajita_steps_batch(B, seed=1000 * rank)
+    plan = ctx.kajita_plan(off, steps, feet)
+    n, nsteps = plan.total_samples, plan.total_steps
+    dst = ctx.to_device(np.zeros((B, 8)))
+    dcom = ctx.alloc(n * 48); dzmp = ctx.alloc(n * 16); dref = ctx.alloc(n * 16)
+    dl = ctx.alloc(n * 48); dr = ctx.alloc(n * 48)
+    for _ in range(3):
+        plan.run(dst, dcom, dzmp, dref, dl, dr, True, mem=wg.WG_MEM_DEVICE)
+    ctx.sync()
+    ctx.prof_begin(4 * args.steps + 8)
+    ctx.timer_start()
+    for _ in range(args.steps):
+        plan.set_steps(steps, feet)                       # a new batch of footstep plans: the H2D copy of a real caller
+        plan.run(dst, dcom, dzmp, dref, dl, dr, True, mem=wg.WG_MEM_DEVICE)
+    ms = ctx.timer_stop_ms() / args.steps
+    prof = ctx.prof_end()
+    zd_ms = prof[7][1] / prof[7][0] if 7 in prof else None
+    # end to end: host step lists in, host CoM/ZMP/ZMP-reference/feet out
+    com = ctx.pinned((n, 6)); zmp = ctx.pinned((n, 2)); ref = ctx.pinned((n, 2))
+    st = ctx.pinned((B, 8))
+    n_e2e = max(2, min(args.steps, 4))
+    st[:] = 0.0
+    plan.run(st, com, zmp, ref, None, None, True, mem=wg.WG_MEM_HOST)
+    te = time.perf_counter()
+    for _ in range(n_e2e):
+        st[:] = 0.0
+        plan.set_steps(steps, feet)
+        plan.run(st, com, zmp, ref, None, None, True, mem=wg.WG_MEM_HOST)
+    ctx.sync()
+    e2e_s = time.perf_counter() - te
+    res = {"workload": "kajita2003_footsteps_to_com_%d_walks" % B, "walks": B, "footsteps": int(len(steps)),
+           "samples": int(n), "preview_steps": int(nsteps), "ms_per_pass": ms,
+           "preview_steps_per_s": nsteps / (ms * 1e-3),
+           "zmpdisc_ms_per_launch": zd_ms,
+           # the front-end kernel is store bound: ZMP reference (16 B) + two feet (2 x 48 B) per 5 ms sample
+           "zmpdisc_roofline": None if zd_ms is None else {
+               "kernel": "zmpdisc_kernel", "bound": "hbm", "achieved": 112.0 * n / (zd_ms * 1e-3) / 1e9, "peak": hbm_peak,
+               "unit": "GB/s", "frac": 112.0 * n / (zd_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+               "algorithmic_bytes_per_sample": 112.0},
+           "e2e": {"value": nsteps * n_e2e / e2e_s, "unit": "preview steps/s", "h2d_bytes_per_step": int(steps.nbytes + feet.nbytes + st.nbytes),
+                   "d2h_bytes_per_step": int(com.nbytes + zmp.nbytes + ref.nbytes + st.nbytes),
+                   "api": "wg_kajita_plan_set_steps + wg_kajita_run_batch(WG_MEM_HOST): step lists in, CoM/ZMP/ZMP reference out"}}
+    for b in (dst, dcom, dzmp, dref, dl, dr):
+        b.free()
+    plan.destroy()
+    return res, ({"zmpdisc_kernel": {"launches": int(prof[7][0]), "avg_ms": zd_ms}} if zd_ms is not None else {})
+
+
+# ------------------------------------------------------------------------------------------------
+# Mixed sweep (BASELINE configs[4]): 10^6 Herdt2010 MPC instances x 100 control periods, instance i -> rank i mod G
+# ------------------------------------------------------------------------------------------------
+SWEEP_WORKLOAD = "herdt2010_mpc_sweep_1M_instances_x_100_periods"
+
+
+def sweep_leg(ctx, wg, args, rank, world, dist):
+    """Strong scaling: the 10^6 instances are dealt round-robin to the ranks; every rank advances its share
+    by 100 QP periods (10 s of walking: start from rest in double support, constant random velocity reference per
+    instance, seed = instance index order) without leaving the device.  No data-path collective; the times are reduced
+    with one MAX all-reduce."""
+    import ctypes as C
+    total, periods, chunk = args.sweep_instances, args.sweep_periods, 10
+    mine = np.arange(rank, total, world)
+    B = len(mine)
+    rng = np.random.default_rng(2010)
+    v_all = np.column_stack([rng.uniform(-0.2, 0.3, total), rng.uniform(-0.15, 0.15, total), rng.uniform(-0.2, 0.2, total)])
+    v = np.ascontiguousarray(v_all[mine])
+    ctx.herdt_set_params()
+    ctx.herdt_mpc_set_params()
+    d_st = ctx.herdt_mpc_init(B, device=True)
+    d_v = ctx.to_device(v)
+    lib, h = ctx.lib, ctx.h
+    # warm the kernel on a throw-away copy of a small slice
+    d_w = ctx.herdt_mpc_init(min(B, 4096), device=True)
+    ctx._check(lib.wg_herdt_mpc_run_batch(h, wg.WG_MEM_DEVICE, min(B, 4096), 2, C.c_void_p(d_w.ptr), C.c_void_p(d_v.ptr),
+                                          None, None, None))
+    ctx.sync(); d_w.free()
+    if dist is not None:
+        dist.barrier()
+    ctx.reset_launches()
+    ctx.timer_start()
+    done = 0
+    while done < periods:
+        n = min(chunk, periods - done)
+        ctx._check(lib.wg_herdt_mpc_run_batch(h, wg.WG_MEM_DEVICE, B, n, C.c_void_p(d_st.ptr),
+                                              C.c_void_p(d_v.ptr) if done == 0 else None, None, None, None))
+        done += n
+    ms = ctx.timer_stop_ms()
+    launches = ctx.launches
+    st = d_st.download(wg.MPC_STATE_DTYPE, (B,))
+    fails = int(st["fail_count"].sum()); solves = int(st["qp_count"].sum())
+    d_st.free(); d_v.free()
+    (ms_max,), (solves_all, fails_all) = reduce_over_ranks(dist, [ms], [float(solves), float(fails)])
+    return {"workload": SWEEP_WORKLOAD, "instances_total": total, "instances_per_rank": B, "periods": periods,
+            "n_gpus": world, "scaling": "strong", "sharding": "instance i -> rank i mod G, no collective on the data path",
+            "seconds": ms_max * 1e-3, "qp_solves": int(solves_all), "qp_solves_per_s": solves_all / (ms_max * 1e-3),
+            "failures": int(fails_all), "launches_per_rank": int(launches),
+            "state_bytes_per_rank": int(B * wg.MPC_STATE_DTYPE.itemsize)}
+
+
+# ------------------------------------------------------------------------------------------------
 # Dimitrov PLDP leg (BASELINE configs[3]: 16 384 constrained CoP QPs)
 # ------------------------------------------------------------------------------------------------
 PLDP_WORKLOAD = "dimitrov_pldp_16384_constrained_cop_qps_N16"
@@ -522,6 +627,22 @@ def run_cuda(args):
             pldp["pldp_solves_per_s"] = world / float(t[0])
             pldp["instances"] = pldp["instances"] * world
 
+    kajita = None
+    if not args.no_kajita:
+        try:
+            hbm_pk = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+        except OSError:
+            hbm_pk = 6650.0
+        kajita, kj_kern = kajita_leg(ctx, wg, args, rank, hbm_pk)
+        herdt_kern = dict(herdt_kern or {}, **kj_kern)
+        if dist is not None:
+            (t_k,), (s_k,) = reduce_over_ranks(dist, [kajita["ms_per_pass"]], [float(kajita["preview_steps"])])
+            kajita["preview_steps_per_s"] = s_k / (t_k * 1e-3)
+            kajita["walks"] = kajita["walks"] * world
+    sweep = None
+    if args.sweep:
+        sweep = sweep_leg(ctx, wg, args, rank, world, dist)
+
     if rank == 0:
         # roofline of the dominant kernel (largest share of the timed region)
         peaks = {}
@@ -563,7 +684,7 @@ def run_cuda(args):
                            "preview_steps_per_pass_per_gpu": steps_per_pass,
                            "l2": "inputs+outputs per pass (%.2f GB) exceed the 126 MB L2" % ((n * 80) / 1e9)},
                 "roofline": roof, "kernels": dict(kern, **(herdt_kern or {})), "fp64_peak_tflops_measured": fp64_peak,
-                "herdt": herdt, "pldp": pldp,
+                "herdt": herdt, "pldp": pldp, "kajita_front_end": kajita, "sweep": sweep,
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "passes": e2e_steps, "api": "wg_preview_run_batch(WG_MEM_HOST), pinned host buffers"},
@@ -588,6 +709,10 @@ def main():
     ap.add_argument("--no-herdt", action="store_true")
     ap.add_argument("--pldp-instances", type=int, default=16384)
     ap.add_argument("--no-pldp", action="store_true")
+    ap.add_argument("--no-kajita", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also run BASELINE configs[4]: 1M MPC instances x 100 periods")
+    ap.add_argument("--sweep-instances", type=int, default=1000000)
+    ap.add_argument("--sweep-periods", type=int, default=100)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
