@@ -462,6 +462,100 @@ int wg_zmpdisc_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *zmp
 int wg_kajita_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *state, double *com_out, double *zmp_out,
                         double *zmpref_xy, wg_foot_sample *left, wg_foot_sample *right, int simulation);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dimitrov2008 front to back: feet trajectories -> support polygons -> per-period constraint matrices ->
+ * PLDP solve -> LIPM, closed loop on the device (one warp owns one walk for its whole duration)
+ *   replaces ComputeConvexHull::DoComputeConvexHull                     (src/Mathematics/ConvexHull.cpp:87-203)
+ *            FootConstraintsAsLinearSystem::BuildLinearConstraintInequalities / ComputeLinearSystem /
+ *                FindSimilarConstraints          (src/Mathematics/FootConstraintsAsLinearSystem.cpp:258-539, :94-256, :53-92)
+ *            ZMPConstrainedQPFastFormulation::InitConstants = InitializeMatrixPbConstants +
+ *                BuildingConstantPartOfTheObjectiveFunction(+QLDANDLQ) + BuildingConstantPartOfConstraintMatrices
+ *                (src/ZMPRefTrajectoryGeneration/ZMPConstrainedQPFastFormulation.cpp:158-246, :390-614, :616-720)  [host]
+ *            ZMPConstrainedQPFastFormulation::BuildConstraintMatrices (:759-1022) and the PLDP branch of
+ *                BuildZMPTrajectoryFromFootTrajectory (:1095-1480), GetZMPDiscretization (:1483-1520)            [device]
+ *            LinearizedInvertedPendulum2D::Interpolation / OneIteration (src/PreviewControl/LinearizedInvertedPendulum2D.cpp:157-264)
+ * ---------------------------------------------------------------------------------------------- */
+#define WG_LCI_MAX_ROWS 8              /* "bounded to 8 constraints per support foot (double support case)", :775-777 */
+
+typedef struct wg_lci {               /* LinearConstraintInequality_t (include/jrl/walkgen/pgtypes.hh:168-177): A z + B >= 0 */
+  double A[WG_LCI_MAX_ROWS][2];
+  double B[WG_LCI_MAX_ROWS];
+  double center[2];
+  double t_start, t_end;              /* StartingTime, EndingTime (the accumulated 5 ms clock of the feet samples)       */
+  int32_t rows;
+  int32_t first_sample;               /* index of the 5 ms sample that opened the polygon                                */
+  int32_t state;                      /* 1 right foot is support (left flying), 2 left foot is support, 3 double support */
+  int32_t rc;                         /* 0, or -1 when ComputeLinearSystem reports "Linear system ill-computed" (:244-249) */
+  int32_t similar[WG_LCI_MAX_ROWS];   /* SimilarConstraints                                                              */
+} wg_lci;                             /* 272 bytes */
+
+typedef struct wg_dimitrov_params {
+  double T;                           /* m_QP_T 0.1                                                                      */
+  double sampling_period;             /* m_SamplingPeriod 0.005                                                          */
+  double com_height;                  /* m_ComHeight 0.80                                                                */
+  double alpha, beta;                 /* m_Alpha 200, m_Beta 1000                                                        */
+  double constraint_x, constraint_y;  /* :setdimitrovconstraint  0.04 0.04                                               */
+  double sole_length, sole_width;     /* CjrlFoot::getSoleSize of both feet (robot data; HRP-2 test robot: 0.25 x 0.14)  */
+  int32_t max_iterations;             /* PLDP iteration cap standing in for the 1.3 ms wall-clock cap; <= 0: 128         */
+  int32_t cold_restart;               /* what to do when a hot-started solve finds its start point infeasible by more
+                                         than m_tol ("PB ON constraint" then a negative step: the reference prints and
+                                         calls exit(0), PLDPSolver.cpp:611-616, :822-828).  0 (default, the reference's
+                                         observable behaviour short of killing the process): the walk stops there with
+                                         status 1.  1: the period is solved again from the cold start point
+                                         (StartingSequence semantics, no kept constraints) and flagged status 5.        */
+} wg_dimitrov_params;
+
+void wg_dimitrov_default_params(wg_dimitrov_params *p);
+
+/* The constants of InitConstants() for QP_N = 16 (host arithmetic, uploaded to the context; also installs them as the
+ * PLDP constants of wg_pldp_solve_batch).  Any out pointer may be NULL.  Row-major: iPu, Pu, iLQ, OptC [16][16] (one
+ * axis block); Px, OptB [16][3]. */
+int wg_dimitrov_set_params(wg_ctx *ctx, const wg_dimitrov_params *p, double *iPu, double *Px, double *Pu, double *iLQ,
+                           double *OptB, double *OptC);
+
+/* DoComputeConvexHull for B point sets of n points each (xy [B][n][2], n <= 8): hull_xy [B][8][2], counts [B]. */
+int wg_convex_hull_batch(wg_ctx *ctx, int mem, int B, int n, const double *xy, double *hull_xy, int32_t *counts);
+
+/* BuildLinearConstraintInequalities for a ragged batch of feet buffers: walk b owns samples
+ * [sample_offsets[b], sample_offsets[b+1]) of left/right/step_type (step_type [total][3] as written by
+ * wg_zmpdisc_run_batch: ZMP, left foot, right foot; only the left foot's is read) and writes at most
+ * lci_offsets[b+1]-lci_offsets[b] polygons at lci + lci_offsets[b]; n_lci[b] = number found (a walk that needs more
+ * fails with WG_ERR_INVALID in host mode and n_lci[b] = -needed in device mode).  sample_offsets / lci_offsets are
+ * HOST arrays; the others live in `mem`.  Sample i of a walk carries time = the 5 ms clock accumulated i times. */
+int wg_fcals_build_batch(wg_ctx *ctx, int mem, int B, const int64_t *sample_offsets, const wg_foot_sample *left,
+                         const wg_foot_sample *right, const int32_t *step_type, const int64_t *lci_offsets,
+                         wg_lci *lci, int32_t *n_lci);
+
+typedef struct wg_dimitrov_period {   /* one iteration of the loop of BuildZMPTrajectoryFromFootTrajectory */
+  double t_start;                     /* StartingTime                                                       */
+  double xk[6];                       /* LIPM state the QP was built for (x, dx, ddx, y, dy, ddy)            */
+  double jerk_x, jerk_y;              /* ptX[0], ptX[N]                                                      */
+  int32_t m;                          /* NbOfConstraints                                                     */
+  int32_t n_first;                    /* NextNumberOfRemovedConstraints                                      */
+  int32_t rc, status;                 /* as wg_pldp_info; status 5 = solved again from the cold start (cold_restart) */
+  int32_t iterations, n_active;
+  int32_t active[WG_PLDP_NVAR];
+} wg_dimitrov_period;                 /* 224 bytes */
+
+/* Number of QP periods the loop runs for a feet buffer of n samples (host arithmetic, the loop bound of :1190-1194). */
+int64_t wg_dimitrov_period_count(const wg_dimitrov_params *p, int64_t n_samples);
+
+/* GetZMPDiscretization of ZMPConstrainedQPFastFormulation for every walk of a Kajita plan: ZMPDiscretization, then
+ * FootConstraintsAsLinearSystem, then the receding-horizon PLDP loop.  Outputs (any may be NULL) live in `mem`:
+ *   com_out [total][6]   COMStates x[0..2], y[0..2]; rows the loop does not reach are zero
+ *   zmp_out [total][2]   ZMPRefPositions px, py after the loop (rows it does not reach keep the discretised reference)
+ *   left/right [total]   feet
+ *   periods              walk b's periods at periods + period_offsets[b] (period_offsets: HOST array of B+1 entries,
+ *                        period_offsets[b+1]-period_offsets[b] >= wg_dimitrov_period_count of the walk), or NULL
+ *   status [B]           0, 1 = a PLDP solve failed: NaN (the reference prints IFAIL and returns -1, :1373-1377) or
+ *                        an infeasible hot start (the reference calls exit(0)); the walk stops at that period,
+ *                        2 = no polygon covers a sample time ("HERE 3", :800-804), 3 = polygon capacity,
+ *                        4 = ZMPDiscretization refused the walk
+ *   periods_done [B]     periods attempted (the failing one included) */
+int wg_dimitrov_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *com_out, double *zmp_out,
+                          wg_foot_sample *left, wg_foot_sample *right, const int64_t *period_offsets,
+                          wg_dimitrov_period *periods, int32_t *status, int32_t *periods_done);
+
 #ifdef __cplusplus
 }
 #endif

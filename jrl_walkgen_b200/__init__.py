@@ -20,8 +20,10 @@ FOOT_DTYPE, TICK_DTYPE, MPC_STATE_DTYPE, MPC_STEP_DTYPE = _capi.herdt_mpc_dtypes
 TICKS_PER_STEP = _capi.HERDT_TICKS_PER_STEP
 PLDP_STATE_DTYPE, PLDP_INFO_DTYPE = _capi.pldp_dtypes()
 REL_STEP_DTYPE, KAJITA_FOOT_DTYPE = _capi.kajita_dtypes()
+LCI_DTYPE, DIMITROV_PERIOD_DTYPE = _capi.dimitrov_dtypes()
+DimitrovParams = _capi.DimitrovParams
 
-__all__ = ["Context", "PreviewPlan", "KajitaPlan", "zmpdisc_default_params", "REL_STEP_DTYPE", "KAJITA_FOOT_DTYPE", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
+__all__ = ["LCI_DTYPE", "DIMITROV_PERIOD_DTYPE", "DimitrovParams", "dimitrov_default_params", "Context", "PreviewPlan", "KajitaPlan", "zmpdisc_default_params", "REL_STEP_DTYPE", "KAJITA_FOOT_DTYPE", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
            "PLDP_STATE_DTYPE", "PLDP_INFO_DTYPE", "FOOT_DTYPE", "TICK_DTYPE", "MPC_STATE_DTYPE", "MPC_STEP_DTYPE", "TICKS_PER_STEP", "QP_INPUT_DTYPE",
            "QP_OUTPUT_DTYPE", "WalkgenError", "device_count",
            "MODE_WITH_INITIALPOS", "MODE_WITHOUT_INITIALPOS", "WG_MEM_HOST", "WG_MEM_DEVICE"]
@@ -52,6 +54,13 @@ def herdt_mpc_default_params() -> HerdtMpcParams:
     """Constants of ZMPVelocityReferencedQP's ctor and the TestHerdt2010 script (step timing 0.7/0.1 s)."""
     p = HerdtMpcParams()
     _capi.load().wg_herdt_mpc_default_params(C.byref(p))
+    return p
+
+
+def dimitrov_default_params() -> "_capi.DimitrovParams":
+    """The constants of ZMPConstrainedQPFastFormulation's ctor (ZMPConstrainedQPFastFormulation.cpp:79-96)."""
+    p = _capi.DimitrovParams()
+    _capi.load().wg_dimitrov_default_params(C.byref(p))
     return p
 
 
@@ -309,6 +318,75 @@ class Context:
         self._check(self.lib.wg_optcholesky_full_batch(self.h, WG_MEM_HOST, B, n, A.ctypes.data, L.ctypes.data,
                                                        None if iL is None else iL.ctypes.data, n))
         return L, iL
+
+
+    # ---- Dimitrov2008 front to back ------------------------------------------------------------------------------
+    def dimitrov_set_params(self, params=None):
+        """InitConstants(): -> dict of the constant matrices (one axis block, row-major)."""
+        self.dimitrov_params = params if params is not None else dimitrov_default_params()
+        out = {k: np.zeros(shape) for k, shape in (("iPu", (16, 16)), ("Px", (16, 3)), ("Pu", (16, 16)),
+                                                   ("iLQ", (16, 16)), ("OptB", (16, 3)), ("OptC", (16, 16)))}
+        self._check(self.lib.wg_dimitrov_set_params(self.h, C.byref(self.dimitrov_params),
+                                                    *[out[k].ctypes.data for k in ("iPu", "Px", "Pu", "iLQ", "OptB", "OptC")]))
+        return out
+
+    def convex_hull_batch(self, points):
+        """DoComputeConvexHull for [B][n][2] point sets -> (hull [B][8][2], counts [B])."""
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        B, n = pts.shape[0], pts.shape[1]
+        hull = np.zeros((B, 8, 2)); cnt = np.zeros(B, dtype=np.int32)
+        self._check(self.lib.wg_convex_hull_batch(self.h, WG_MEM_HOST, B, n, pts.ctypes.data, hull.ctypes.data, cnt.ctypes.data))
+        return hull, cnt
+
+    def fcals_build(self, left, right, types, cap=None):
+        """BuildLinearConstraintInequalities for ONE feet buffer (left/right: [n][6] floats or KAJITA_FOOT_DTYPE,
+        types [n][3]) -> LCI_DTYPE records."""
+        L = np.ascontiguousarray(left).view(np.float64).reshape(-1, 6)
+        R = np.ascontiguousarray(right).view(np.float64).reshape(-1, 6)
+        ty = np.ascontiguousarray(types, dtype=np.int32).reshape(-1, 3)
+        n = len(L)
+        cap = cap or 1024
+        so = np.array([0, n], dtype=np.int64); lo = np.array([0, cap], dtype=np.int64)
+        out = np.zeros(cap, dtype=LCI_DTYPE); cnt = np.zeros(1, dtype=np.int32)
+        if not hasattr(self, "dimitrov_params"):
+            self.dimitrov_set_params()
+        self._check(self.lib.wg_fcals_build_batch(self.h, WG_MEM_HOST, 1, so.ctypes.data_as(_capi.c_i64_p), L.ctypes.data,
+                                                  R.ctypes.data, ty.ctypes.data, lo.ctypes.data_as(_capi.c_i64_p),
+                                                  out.ctypes.data, cnt.ctypes.data))
+        return out[:cnt[0]]
+
+    def dimitrov_run(self, walks, init_feet, zmpdisc_params=None, want_feet=True):
+        """footsteps -> ZMPDiscretization -> support polygons -> PLDP receding-horizon loop -> CoM / ZMP at 5 ms for a
+        list of step arrays.  -> dict(com, zmp, left, right, types, periods (list per walk), status, periods_done,
+        sample_offsets)."""
+        if not hasattr(self, "dimitrov_params"):
+            self.dimitrov_set_params()
+        B = len(walks)
+        off = np.concatenate([[0], np.cumsum([len(w) for w in walks])]).astype(np.int64)
+        steps = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=REL_STEP_DTYPE) for w in walks]))
+        plan = KajitaPlan(self, off, steps, np.ascontiguousarray(init_feet, dtype=np.float64), zmpdisc_params)
+        try:
+            so = plan.sample_offsets
+            ns = int(so[-1])
+            pc = [int(self.lib.wg_dimitrov_period_count(C.byref(self.dimitrov_params), int(so[b + 1] - so[b]))) for b in range(B)]
+            po = np.concatenate([[0], np.cumsum(pc)]).astype(np.int64)
+            com = np.zeros((ns, 6)); zmp = np.zeros((ns, 2))
+            left = np.zeros(ns, dtype=KAJITA_FOOT_DTYPE) if want_feet else None
+            right = np.zeros(ns, dtype=KAJITA_FOOT_DTYPE) if want_feet else None
+            per = np.zeros(max(1, int(po[-1])), dtype=DIMITROV_PERIOD_DTYPE)
+            status = np.zeros(B, dtype=np.int32); done = np.zeros(B, dtype=np.int32)
+            self._check(self.lib.wg_dimitrov_run_batch(self.h, plan.h, WG_MEM_HOST, com.ctypes.data, zmp.ctypes.data,
+                                                       _ptr(left), _ptr(right), po.ctypes.data_as(_capi.c_i64_p),
+                                                       per.ctypes.data, status.ctypes.data, done.ctypes.data))
+            types = None
+            if want_feet:
+                types = np.zeros((ns, 3), dtype=np.int32)
+                plan.discretize(step_type=types)
+        finally:
+            plan.destroy()
+        return {"com": com, "zmp": zmp, "left": left, "right": right, "types": types, "status": status,
+                "periods_done": done, "periods": [per[po[b]:po[b] + done[b]] for b in range(B)],
+                "period_counts": np.array(pc), "sample_offsets": so}
 
 
 class KajitaPlan:

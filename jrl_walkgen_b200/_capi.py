@@ -88,6 +88,26 @@ class ZmpDiscParams(C.Structure):
                 ("foot_b", C.c_double), ("foot_h", C.c_double), ("foot_f", C.c_double), ("filter_time", C.c_double)]
 
 
+class DimitrovParams(C.Structure):
+    """Mirror of wg_dimitrov_params."""
+    _fields_ = [("T", C.c_double), ("sampling_period", C.c_double), ("com_height", C.c_double), ("alpha", C.c_double),
+                ("beta", C.c_double), ("constraint_x", C.c_double), ("constraint_y", C.c_double),
+                ("sole_length", C.c_double), ("sole_width", C.c_double), ("max_iterations", C.c_int32),
+                ("cold_restart", C.c_int32)]
+
+
+def dimitrov_dtypes():
+    """numpy mirrors of wg_lci (272 B) and wg_dimitrov_period (224 B)."""
+    np = _np()
+    lci = np.dtype([("A", "f8", (8, 2)), ("B", "f8", 8), ("center", "f8", 2), ("t_start", "f8"), ("t_end", "f8"),
+                    ("rows", "i4"), ("first_sample", "i4"), ("state", "i4"), ("rc", "i4"), ("similar", "i4", 8)])
+    period = np.dtype([("t_start", "f8"), ("xk", "f8", 6), ("jerk_x", "f8"), ("jerk_y", "f8"), ("m", "i4"),
+                       ("n_first", "i4"), ("rc", "i4"), ("status", "i4"), ("iterations", "i4"), ("n_active", "i4"),
+                       ("active", "i4", 32)])
+    assert lci.itemsize == 272 and period.itemsize == 224
+    return lci, period
+
+
 def kajita_dtypes():
     """numpy mirrors of wg_rel_step (48 B) and wg_foot_sample (48 B)."""
     np = _np()
@@ -221,6 +241,14 @@ SIGNATURES = {
                                        C.c_void_p]),
     "wg_kajita_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int]),
+    "wg_dimitrov_default_params": (None, [C.POINTER(DimitrovParams)]),
+    "wg_dimitrov_set_params": (C.c_int, [C.c_void_p, C.POINTER(DimitrovParams)] + [C.c_void_p] * 6),
+    "wg_dimitrov_period_count": (C.c_int64, [C.POINTER(DimitrovParams), C.c_int64]),
+    "wg_convex_hull_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wg_fcals_build_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i64_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       c_i64_p, C.c_void_p, C.c_void_p]),
+    "wg_dimitrov_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, c_i64_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wg_herdt_mpc_default_params": (None, [C.POINTER(HerdtMpcParams)]),
     "wg_herdt_mpc_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtMpcParams)]),
     "wg_herdt_mpc_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

@@ -14,7 +14,7 @@ struct wg_preview_consts;  // preview.cu
 // Kernel ids of the per-kernel CUDA-event profiler (wg_prof_*): bench.py reads the average launch
 // duration of each kernel over the timed region from these.
 enum { WG_K_PREVIEW_FIR = 0, WG_K_PREVIEW_RECUR = 1, WG_K_HERDT_QP = 2, WG_K_HERDT_MPC = 3, WG_K_PLDP = 4,
-       WG_K_OPTCHOL = 5, WG_K_PREVIEW_FUSED = 6, WG_K_ZMPDISC = 7, WG_K_COUNT = 8 };
+       WG_K_OPTCHOL = 5, WG_K_PREVIEW_FUSED = 6, WG_K_ZMPDISC = 7, WG_K_FCALS = 8, WG_K_DIMITROV = 9, WG_K_COUNT = 10 };
 
 struct wg_prof_state {
   bool on = false;
@@ -43,6 +43,8 @@ struct wg_ctx {
   void *herdt_mpc = nullptr;
   // PLDP constants (pldp.cu)
   void *pldp = nullptr;
+  // Dimitrov front-to-back pipeline (dimitrov.cu)
+  void *dimitrov = nullptr;
 };
 
 inline int wg_fail(wg_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
@@ -90,6 +92,18 @@ inline void wg_prof_stop(wg_ctx *ctx)
 extern "C" int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count,
                                         const double *d_zmp, double *d_state, double *d_com, double *d_zmpout,
                                         int simulation);
+
+// zmpdisc.cu / pldp.cu internals used by dimitrov.cu
+struct wgi_kajita_view {
+  int B;
+  const int64_t *samp_off, *step_off;   // host, B+1 entries
+  const int64_t *d_samp_off;            // device
+  const int *d_zd_status;               // device, per walk
+  double sampling_period;
+};
+extern "C" int wgi_kajita_discretize_device(wg_ctx *ctx, wg_kajita_plan *pl, double **zmpref, wg_foot_sample **left,
+                                            wg_foot_sample **right, int32_t **types, wgi_kajita_view *view);
+extern "C" const void *wgi_pldp_device_consts(wg_ctx *ctx);   // PldpConsts on the device, or nullptr
 
 struct wg_device_guard {
   int prev = -1;

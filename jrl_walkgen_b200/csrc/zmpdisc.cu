@@ -761,6 +761,31 @@ static int zd_check_status(wg_ctx *ctx, wg_kajita_plan *pl)
   return WG_OK;
 }
 
+// Internal (dimitrov.cu): run GetZMPDiscretization for every walk of the plan into device buffers.  A NULL *zmpref /
+// *left / *right is replaced by the plan's own staging buffer; the step types always go to the plan's buffer.
+extern "C" int wgi_kajita_discretize_device(wg_ctx *ctx, wg_kajita_plan *pl, double **zmpref, wg_foot_sample **left,
+                                            wg_foot_sample **right, int32_t **types, wgi_kajita_view *view)
+{
+  if (!ctx || !pl || pl->ctx != ctx) return WG_ERR_INVALID;
+  const size_t ns = (size_t)pl->samp_off[pl->B];
+  int rc;
+  if (!*zmpref) { if ((rc = zd_stage(ctx, &pl->d_zmpref, 2 * ns)) != WG_OK) return rc; *zmpref = pl->d_zmpref; }
+  if (!*left) { if ((rc = zd_stage(ctx, &pl->d_left, ns)) != WG_OK) return rc; *left = pl->d_left; }
+  if (!*right) { if ((rc = zd_stage(ctx, &pl->d_right, ns)) != WG_OK) return rc; *right = pl->d_right; }
+  if ((rc = zd_stage(ctx, &pl->d_types, 3 * ns)) != WG_OK) return rc;
+  *types = pl->d_types;
+  Out o;
+  o.zmpref = reinterpret_cast<double2 *>(*zmpref); o.ztheta = nullptr; o.left = *left; o.right = *right; o.types = *types;
+  if ((rc = zd_launch(ctx, pl, 0, pl->B, o)) != WG_OK) return rc;
+  view->B = pl->B;
+  view->samp_off = pl->samp_off.data();
+  view->step_off = pl->step_off.data();
+  view->d_samp_off = pl->d_samp_off;
+  view->d_zd_status = pl->d_status;
+  view->sampling_period = pl->P.sampling_period;
+  return WG_OK;
+}
+
 extern "C" {
 
 int wg_zmpdisc_run_batch(wg_ctx *ctx, wg_kajita_plan *pl, int mem, double *zmpref_xy, double *zmp_theta,

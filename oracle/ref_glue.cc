@@ -12,6 +12,9 @@ using std::string;
 #include <Mathematics/qld.hh>          /* ql0001_            (qld.hh:27-31)        */
 #include <Mathematics/OptCholesky.hh>  /* OptCholesky        (OptCholesky.hh:42-140) */
 #include <Mathematics/PLDPSolver.hh>   /* Optimization::Solver::PLDPSolver (PLDPSolver.hh:44-68)  */
+#include <Mathematics/ConvexHull.hh>   /* ComputeConvexHull::DoComputeConvexHull (ConvexHull.hh)   */
+#include <Mathematics/FootConstraintsAsLinearSystem.hh>  /* BuildLinearConstraintInequalities (:60-67) */
+#include <deque>
 
 using namespace PatternGeneratorJRL;
 
@@ -80,6 +83,57 @@ int ref_pldp_solve(void *h, double *D, unsigned m, double *DPu, double *DPx, dou
   std::vector<int> sim(similar, similar + n_similar);
   return static_cast<Optimization::Solver::PLDPSolver *>(h)->SolveProblem(D, m, DPu, DPx, ZMPRef, XkYk, X, sim,
                                                            n_removed, starting != 0);
+}
+
+/* ---- ComputeConvexHull::DoComputeConvexHull (ConvexHull.cpp:87-203): points as (col=x, row=y) pairs ---- */
+int ref_convex_hull(int n, const double *xy, double *hull_xy, int cap)
+{
+  std::vector<CH_Point> in(n), out;
+  for (int i = 0; i < n; ++i) { in[i].col = xy[2 * i]; in[i].row = xy[2 * i + 1]; }
+  ComputeConvexHull ch;
+  ch.DoComputeConvexHull(in, out);
+  for (int i = 0; i < (int)out.size() && i < cap; ++i) { hull_xy[2 * i] = out[i].col; hull_xy[2 * i + 1] = out[i].row; }
+  return (int)out.size();
+}
+
+/* ---- FootConstraintsAsLinearSystem::BuildLinearConstraintInequalities (FootConstraintsAsLinearSystem.cpp:258-539)
+ * feet: [n][4] = x, y, z, theta(deg); step_type/time: the left foot's, [n].  Output polygon p: rows[p], A[p][8][2],
+ * Bv[p][8], center[p][2], similar[p][8], t0t1[p][2].  Returns the number of polygons (or -1). */
+int ref_fcals_build(int n, const double *left, const double *right, const int *step_type, const double *time,
+                    double sole_length, double sole_width, double cx, double cy, int cap, int *rows, double *A,
+                    double *Bv, double *center, int *similar, double *t0t1)
+{
+  CjrlHumanoidDynamicRobot robot;
+  robot.left.sole_length = robot.right.sole_length = sole_length;
+  robot.left.sole_width = robot.right.sole_width = sole_width;
+  robot.left.ankle_z = robot.right.ankle_z = 0.105;
+  SimplePluginManager spm;
+  FootConstraintsAsLinearSystem fcals(&spm, &robot);
+  std::deque<FootAbsolutePosition> L(n), R(n);
+  for (int i = 0; i < n; ++i) {
+    std::memset(&L[i], 0, sizeof(FootAbsolutePosition)); std::memset(&R[i], 0, sizeof(FootAbsolutePosition));
+    L[i].x = left[4 * i]; L[i].y = left[4 * i + 1]; L[i].z = left[4 * i + 2]; L[i].theta = left[4 * i + 3];
+    R[i].x = right[4 * i]; R[i].y = right[4 * i + 1]; R[i].z = right[4 * i + 2]; R[i].theta = right[4 * i + 3];
+    L[i].stepType = step_type[i]; L[i].time = time[i]; R[i].time = time[i];
+  }
+  std::deque<LinearConstraintInequality_t *> q;
+  int rc = fcals.BuildLinearConstraintInequalities(L, R, q, cx, cy);
+  int np = (int)q.size();
+  for (int p = 0; p < np; ++p) {
+    if (p < cap) {
+      const int nr = (int)q[p]->A.size1();
+      rows[p] = nr;
+      for (int j = 0; j < nr && j < 8; ++j) {
+        A[(p * 8 + j) * 2] = q[p]->A(j, 0); A[(p * 8 + j) * 2 + 1] = q[p]->A(j, 1);
+        Bv[p * 8 + j] = q[p]->B(j, 0);
+        similar[p * 8 + j] = q[p]->SimilarConstraints[j];
+      }
+      center[2 * p] = q[p]->Center(0); center[2 * p + 1] = q[p]->Center(1);
+      t0t1[2 * p] = q[p]->StartingTime; t0t1[2 * p + 1] = q[p]->EndingTime;
+    }
+    delete q[p];
+  }
+  return rc < 0 ? rc : np;
 }
 
 } /* extern "C" */

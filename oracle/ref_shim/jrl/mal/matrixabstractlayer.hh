@@ -1,8 +1,75 @@
 /* Stand-in for jrl-mal's <jrl/mal/matrixabstractlayer.hh> (jrl-mal >= 1.9.0 is an
- * un-vendored dependency of the reference, CMakeLists.txt:45).  The reference math
- * sources compiled by oracle/Makefile (OptCholesky.cpp, PLDPSolver.cpp) include this
- * header but use none of its macros, so an empty header is sufficient.
+ * un-vendored dependency of the reference, CMakeLists.txt:45).  Written for this repository;
+ * it only provides the handful of MAL_* macros used by the reference sources that
+ * oracle/Makefile compiles where they lie (OptCholesky.cpp and PLDPSolver.cpp use none;
+ * FootConstraintsAsLinearSystem.cpp and pgtypes.hh use MAL_MATRIX / MAL_VECTOR, *_RESIZE,
+ * MAL_MATRIX_NB_ROWS, MAL_VECTOR_DIM and MAL_RET_A_by_B).  Semantics are those of the
+ * Boost uBLAS backend of jrl-mal: dense row-major double storage, resize keeps the old
+ * contents; NEW elements are zero here (uBLAS leaves them uninitialised).
  * TEST INFRASTRUCTURE ONLY - nothing under oracle/ is linked into the product. */
 #ifndef ORACLE_REF_SHIM_MAL_HH
 #define ORACLE_REF_SHIM_MAL_HH
+#include <vector>
+#include <cstddef>
+
+namespace oracle_mal {
+
+template <typename T> class vector {
+ public:
+  vector() {}
+  explicit vector(std::size_t n) : d_(n, T()) {}
+  void resize(std::size_t n) { d_.resize(n, T()); }
+  std::size_t size() const { return d_.size(); }
+  T &operator()(std::size_t i) { return d_[i]; }
+  const T &operator()(std::size_t i) const { return d_[i]; }
+  T &operator[](std::size_t i) { return d_[i]; }
+  const T &operator[](std::size_t i) const { return d_[i]; }
+ private:
+  std::vector<T> d_;
+};
+
+template <typename T> class matrix {
+ public:
+  matrix() : r_(0), c_(0) {}
+  matrix(std::size_t r, std::size_t c) : r_(r), c_(c), d_(r * c, T()) {}
+  void resize(std::size_t r, std::size_t c)
+  {
+    std::vector<T> n(r * c, T());
+    for (std::size_t i = 0; i < r && i < r_; ++i)
+      for (std::size_t j = 0; j < c && j < c_; ++j) n[i * c + j] = d_[i * c_ + j];
+    d_.swap(n); r_ = r; c_ = c;
+  }
+  std::size_t size1() const { return r_; }
+  std::size_t size2() const { return c_; }
+  T &operator()(std::size_t i, std::size_t j) { return d_[i * c_ + j]; }
+  const T &operator()(std::size_t i, std::size_t j) const { return d_[i * c_ + j]; }
+ private:
+  std::size_t r_, c_;
+  std::vector<T> d_;
+};
+
+/* prod(matrix, vector): plain row-by-row accumulation, as uBLAS' dense matrix-vector product */
+template <typename T> vector<T> prod(const matrix<T> &A, const vector<T> &x)
+{
+  vector<T> y(A.size1());
+  for (std::size_t i = 0; i < A.size1(); ++i) {
+    T t = T();
+    for (std::size_t j = 0; j < A.size2(); ++j) t += A(i, j) * x(j);
+    y(i) = t;
+  }
+  return y;
+}
+
+}  // namespace oracle_mal
+
+#define MAL_VECTOR(name, type) oracle_mal::vector<type> name
+#define MAL_VECTOR_DIM(name, type, n) oracle_mal::vector<type> name(n)
+#define MAL_VECTOR_RESIZE(name, n) name.resize(n)
+#define MAL_VECTOR_SIZE(name) name.size()
+#define MAL_MATRIX(name, type) oracle_mal::matrix<type> name
+#define MAL_MATRIX_DIM(name, type, r, c) oracle_mal::matrix<type> name(r, c)
+#define MAL_MATRIX_RESIZE(name, r, c) name.resize(r, c)
+#define MAL_MATRIX_NB_ROWS(name) name.size1()
+#define MAL_MATRIX_NB_COLS(name) name.size2()
+#define MAL_RET_A_by_B(A, B) oracle_mal::prod(A, B)
 #endif
