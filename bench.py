@@ -523,6 +523,119 @@ def pldp_leg(ctx, wg, args, rank, fp64_peak, want_cpu):
     return res, {"pldp_kernel": {"launches": args.steps, "avg_ms": ms}}
 
 
+# ------------------------------------------------------------------------------------------------
+# Dimitrov2008 front to back (SURVEY 8a rows a19-a21 in closed loop): footsteps -> feet -> support polygons ->
+# per-period constraint matrices -> PLDP -> LIPM, CoM/ZMP at 5 ms, without leaving the GPU
+# ------------------------------------------------------------------------------------------------
+def _cpu_dimitrov_worker(args):
+    import dimitrov_oracle as do
+    import zmpdisc_oracle as zo
+    walks, feet, seconds = args
+    par = do.default_params()
+    par.cold_restart = 1
+    zp = zo.default_params()
+    periods = 0; done_walks = 0
+    t0 = time.perf_counter()
+    while True:
+        for st, f in zip(walks, feet):
+            o = zo.run(zp, st.astype(zo.REL_STEP_DTYPE), f)
+            out = do.run(o["left"], o["right"], o["types"][:, 1].copy(), par)
+            periods += len(out["periods"]); done_walks += 1
+            if time.perf_counter() - t0 >= seconds:
+                return periods, done_walks, time.perf_counter() - t0
+        if not walks:
+            return 0, 0, 1.0
+
+
+def cpu_dimitrov_rate(off, steps, feet, seconds=5.0, procs=None):
+    """The oracle chain (ZMPDiscretization, FootConstraintsAsLinearSystem, BuildConstraintMatrices, PLDP, LIPM
+    restatements; hull/polygons/PLDP bitwise pinned to the reference's object code), one process per core."""
+    import multiprocessing as mp
+    procs = procs or host_cores()
+    B = len(off) - 1
+    jobs = []
+    for i in range(procs):
+        idx = [(i * 8 + k) % B for k in range(8)]
+        jobs.append(([steps[off[b]:off[b + 1]].copy() for b in idx], [feet[b].copy() for b in idx], seconds))
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_cpu_dimitrov_worker, jobs)
+    total = sum(r[0] for r in res); wall = max(r[2] for r in res)
+    return {"value": total / wall, "unit": "QP periods/s", "cores": procs, "kind": "port",
+            "sample": f"{procs} processes x up to 8 walks repeated for {seconds:.0f} s ({total} periods, "
+                      f"{sum(r[1] for r in res)} walks): oracle chain footsteps -> CoM, cold_restart = 1",
+            "us_per_period_per_core": 1e6 * wall * procs / max(1, total)}
+
+
+def dimitrov_leg(ctx, wg, args, rank, want_cpu):
+    import ctypes as C
+    from jrl_walkgen_b200 import workloads, _capi
+    B = args.dimitrov_walks
+    off, steps, feet = workloads.kajita_steps_batch(B, seed=2000 + 1000 * rank)
+    par = wg.dimitrov_default_params()
+    par.cold_restart = 1
+    ctx.dimitrov_set_params(par)
+    plan = ctx.kajita_plan(off, steps, feet)
+    n = plan.total_samples
+    so = plan.sample_offsets
+    pc = np.array([ctx.lib.wg_dimitrov_period_count(C.byref(par), int(so[b + 1] - so[b])) for b in range(B)], dtype=np.int64)
+    dcom = ctx.alloc(n * 48); dzmp = ctx.alloc(n * 16); dl = ctx.alloc(n * 48); dr = ctx.alloc(n * 48)
+    dstat = ctx.alloc(B * 4); ddone = ctx.alloc(B * 4)
+
+    def run_dev():
+        ctx._check(ctx.lib.wg_dimitrov_run_batch(ctx.h, plan.h, wg.WG_MEM_DEVICE, dcom.ptr, dzmp.ptr, dl.ptr, dr.ptr, None,
+                                                 None, dstat.ptr, ddone.ptr))
+    for _ in range(2):
+        run_dev()
+    ctx.sync()
+    reps = max(2, min(args.steps, 5))
+    ctx.prof_begin(4 * reps + 8)
+    ctx.timer_start()
+    for _ in range(reps):
+        plan.set_steps(steps, feet)
+        run_dev()
+    ms = ctx.timer_stop_ms() / reps
+    prof = ctx.prof_end()
+    status = dstat.download(np.int32, (B,)); done = ddone.download(np.int32, (B,))
+    periods = int(done.sum())
+    kern = {}
+    for kid, name in ((7, "zmpdisc_kernel"), (8, "fcals_kernel"), (9, "dimitrov_kernel")):
+        if kid in prof:
+            kern[name] = {"launches": int(prof[kid][0]), "avg_ms": prof[kid][1] / prof[kid][0]}
+    # end to end: host step lists in, host CoM / ZMP out
+    com = ctx.pinned((n, 6)); zmp = ctx.pinned((n, 2))
+    hstat = np.zeros(B, dtype=np.int32); hdone = np.zeros(B, dtype=np.int32)
+
+    def run_host():
+        plan.set_steps(steps, feet)
+        ctx._check(ctx.lib.wg_dimitrov_run_batch(ctx.h, plan.h, wg.WG_MEM_HOST, com.ctypes.data, zmp.ctypes.data, None, None,
+                                                 None, None, hstat.ctypes.data, hdone.ctypes.data))
+    run_host()
+    n_e2e = 2
+    te = time.perf_counter()
+    for _ in range(n_e2e):
+        run_host()
+    e2e_s = time.perf_counter() - te
+    assert (hdone == done).all()
+    res = {"workload": "dimitrov2008_footsteps_to_com_%d_walks_N16_pldp" % B, "walks": B, "samples": int(n),
+           "qp_periods": periods, "qp_periods_if_all_walks_completed": int(pc.sum()), "ms_per_pass": ms,
+           "qp_periods_per_s": periods / (ms * 1e-3), "walks_per_s": B / (ms * 1e-3),
+           "walks_completed": int((status == 0).sum()),
+           "walks_stopped_like_the_reference": int((status == 1).sum()),
+           "note": "cold_restart = 1 (a hot start the reference answers with exit(0) is solved again from the cold start "
+                   "point); walks whose closing double-support hull carries a duplicated half-plane stop with the "
+                   "reference's NaN / IFAIL exit and are counted as stopped, their periods up to the stop are counted",
+           "kernels": kern,
+           "e2e": {"value": periods * n_e2e / e2e_s, "unit": "QP periods/s", "h2d_bytes_per_step": int(steps.nbytes + feet.nbytes),
+                   "d2h_bytes_per_step": int(com.nbytes + zmp.nbytes + hstat.nbytes + hdone.nbytes),
+                   "api": "wg_kajita_plan_set_steps + wg_dimitrov_run_batch(WG_MEM_HOST): step lists in, CoM/ZMP at 5 ms out"}}
+    if want_cpu:
+        res["cpu_baseline"] = cpu_dimitrov_rate(off, steps, feet, seconds=max(2.0, args.cpu_seconds / 2))
+    for b in (dcom, dzmp, dl, dr, dstat, ddone):
+        b.free()
+    plan.destroy()
+    return res, kern
+
+
 def run_cuda(args):
     rank, local_rank, world = dist_env()
     import jrl_walkgen_b200 as wg
@@ -639,6 +752,15 @@ def run_cuda(args):
             (t_k,), (s_k,) = reduce_over_ranks(dist, [kajita["ms_per_pass"]], [float(kajita["preview_steps"])])
             kajita["preview_steps_per_s"] = s_k / (t_k * 1e-3)
             kajita["walks"] = kajita["walks"] * world
+    dimitrov = None
+    if not args.no_dimitrov:
+        dimitrov, dm_kern = dimitrov_leg(ctx, wg, args, rank, want_cpu=(rank == 0 and world == 1))
+        herdt_kern = dict(herdt_kern or {}, **dm_kern)
+        if dist is not None:
+            (t_d,), (p_d, w_d) = reduce_over_ranks(dist, [dimitrov["ms_per_pass"]], [float(dimitrov["qp_periods"]), float(dimitrov["walks"])])
+            dimitrov["qp_periods_per_s"] = p_d / (t_d * 1e-3)
+            dimitrov["walks_per_s"] = w_d / (t_d * 1e-3)
+            dimitrov["walks"] = int(w_d)
     sweep = None
     if args.sweep:
         sweep = sweep_leg(ctx, wg, args, rank, world, dist)
@@ -684,7 +806,7 @@ def run_cuda(args):
                            "preview_steps_per_pass_per_gpu": steps_per_pass,
                            "l2": "inputs+outputs per pass (%.2f GB) exceed the 126 MB L2" % ((n * 80) / 1e9)},
                 "roofline": roof, "kernels": dict(kern, **(herdt_kern or {})), "fp64_peak_tflops_measured": fp64_peak,
-                "herdt": herdt, "pldp": pldp, "kajita_front_end": kajita, "sweep": sweep,
+                "herdt": herdt, "pldp": pldp, "kajita_front_end": kajita, "dimitrov_front_to_back": dimitrov, "sweep": sweep,
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "passes": e2e_steps, "api": "wg_preview_run_batch(WG_MEM_HOST), pinned host buffers"},
@@ -710,6 +832,8 @@ def main():
     ap.add_argument("--pldp-instances", type=int, default=16384)
     ap.add_argument("--no-pldp", action="store_true")
     ap.add_argument("--no-kajita", action="store_true")
+    ap.add_argument("--dimitrov-walks", type=int, default=4096)
+    ap.add_argument("--no-dimitrov", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also run BASELINE configs[4]: 1M MPC instances x 100 periods")
     ap.add_argument("--sweep-instances", type=int, default=1000000)
     ap.add_argument("--sweep-periods", type=int, default=100)

@@ -65,7 +65,8 @@ void wg_launch_count_reset(wg_ctx *ctx);
 /* Per-kernel CUDA-event profiler on the context stream.  Between wg_prof_begin(capacity = max number of
  * kernel launches to record) and wg_prof_end every kernel this library launches is bracketed by an event
  * pair; wg_prof_get returns the launch count and the summed duration of one kernel id:
- *   2 Herdt QP solve, 3 Herdt closed-loop periods, 4 PLDP solve, 5 OptCholesky, 6 preview (fused FIR + scan). */
+ *   2 Herdt QP solve, 3 Herdt closed-loop periods, 4 PLDP solve, 5 OptCholesky, 6 preview (fused FIR + scan),
+ *   7 ZMPDiscretization, 8 support polygons (FCALS / convex hull), 9 Dimitrov receding-horizon loop. */
 int wg_prof_begin(wg_ctx *ctx, int capacity);
 int wg_prof_end(wg_ctx *ctx);                        /* synchronises the stream and accumulates      */
 int wg_prof_get(wg_ctx *ctx, int kernel_id, long long *launches, double *total_ms);
