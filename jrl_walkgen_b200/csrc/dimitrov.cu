@@ -31,10 +31,9 @@
 namespace {
 
 constexpr int DM_N = PLDP_N;          // 16
-constexpr int DM_WARPS = 1;           // loop kernel: one warp per CTA (32 KB of shared memory each, 7 CTAs per SM)
+constexpr int DM_WARPS = 4;           // loop kernel: 4 warps per CTA, ~9 KB of shared memory per warp
 constexpr int FC_WARPS = 4;           // polygon kernel
 constexpr int DM_MAXM = WG_LCI_MAX_ROWS * DM_N;   // 128
-constexpr int DM_ACAP = 81 * 32;      // doubles of shared memory per warp for DPu: m <= 80 (5 rows per sample on average)
 
 struct DimConsts {
   double Px[DM_N * 3];
@@ -299,18 +298,17 @@ struct DimWarp {
   int rowi[DM_MAXM];
 };
 
-__global__ void __launch_bounds__(DM_WARPS * 32)
+__global__ void __launch_bounds__(DM_WARPS * 32, 4)
 dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__restrict__ Cp,
                 const int64_t *__restrict__ samp_off, const double *__restrict__ clock,
                 const int64_t *__restrict__ lci_off, const wg_lci *__restrict__ lci, const int32_t *__restrict__ n_lci,
                 const int *__restrict__ zd_status, double *__restrict__ com, double *__restrict__ zmp,
                 const int64_t *__restrict__ per_off, wg_dimitrov_period *__restrict__ periods,
-                int32_t *__restrict__ status_out, int32_t *__restrict__ done_out, double *__restrict__ scratch,
-                int *__restrict__ next_walk)
+                int32_t *__restrict__ status_out, int32_t *__restrict__ done_out, int *__restrict__ next_walk,
+                const int *__restrict__ order)
 {
   __shared__ DimWarp ws[DM_WARPS];
   __shared__ double sPu[DM_N * DM_N];
-  extern __shared__ __align__(16) double sA[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DimConsts &K = *Kp;
   const PldpConsts &C = *Cp;
@@ -321,10 +319,11 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
   const double T = K.T, Ts = K.Ts;
   const double tol = 1e-8;   // m_tol, PLDPSolver.cpp:66
   const int ii = lane & (N - 1), ax = lane >> 4;
-  // walks differ in length by an order of magnitude: every warp fetches its next walk from a global counter
+  // walks differ in length by an order of magnitude: every warp fetches its next walk from a global counter, longest
+  // walks first (`order`)
   for (;;) {
     int b = 0;
-    if (lane == 0) b = atomicAdd(next_walk, 1);
+    if (lane == 0) { b = atomicAdd(next_walk, 1); if (b < B) b = order[b]; }
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= B) break;
     const int64_t s0 = samp_off[b];
@@ -350,6 +349,7 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
       int it = first, my_p = first;
       double te = P[it].t_end;
       bool past = false;
+#pragma unroll 1
       for (int i = 0; i < N; ++i) {
         const double ltime = ST + i * T;
         if (ltime > te) { ++it; if (it >= np) { past = true; break; } te = P[it].t_end; }
@@ -371,6 +371,7 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
         w.zref[lane + N] = q.center[1];
         const double zx = cx0 * K.Px[lane * 3 + 0] + cx1 * K.Px[lane * 3 + 1] + cx2 * K.Px[lane * 3 + 2];
         const double zy = cy0 * K.Px[lane * 3 + 0] + cy1 * K.Px[lane * 3 + 1] + cy2 * K.Px[lane * 3 + 2];
+#pragma unroll 1
         for (int j = 0; j < my_rows; ++j) {
           const double a0 = q.A[j][0], a1 = q.A[j][1];
           w.rowa[0][roff + j] = a0;
@@ -380,43 +381,31 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
         }
       }
       __syncwarp();
-      // DPu: element (r, k + N ax) = A_r[ax] * Pu[k N + i_r], column-major with leading dimension m + 1
-      double *A = (ld * PLDP_U <= DM_ACAP) ? sA + (size_t)warp * DM_ACAP
-                                          : scratch + ((size_t)blockIdx.x * DM_WARPS + warp) * ((DM_MAXM + 1) * PLDP_U);
-      for (int r = lane; r < ld; r += 32) {
-        if (r < m) {
-          const double a0 = w.rowa[0][r], a1 = w.rowa[1][r];
-          const int ir = w.rowi[r];
-#pragma unroll 4
-          for (int k = 0; k < N; ++k) {
-            const double pu = sPu[k * N + ir];
-            A[r + (size_t)k * ld] = a0 * pu;
-            A[r + (size_t)(k + N) * ld] = a1 * pu;
-          }
-        } else {
-          for (int c = 0; c < PLDP_U; ++c) A[r + (size_t)c * ld] = 0.0;
-        }
-      }
+      // DPu (:885-905) is never materialised: element (r, k + N ax) = A_r[ax] * Pu[k N + i_r] is formed where it is used
+      // (RankMat, pldp.cuh) by the same single IEEE multiplication the reference stores
+      const RankMat M{w.rowa[0], w.rowa[1], w.rowi, sPu};
       // D = OptB xk - OptC ZMPRef (:1268-1276), row `lane`
       double Dl;
       {
         double t1 = 0.0, t2 = 0.0;
+#pragma unroll 2
         for (int j = 0; j < N; ++j) t1 += K.OptC[ii * N + j] * w.zref[j + N * ax];
         for (int j = 0; j < 3; ++j) t2 += K.OptB[ii * 3 + j] * w.xk[3 * ax + j];
         Dl = t2 - t1;
       }
       __syncwarp();
-      // ---- PLDPSolver::SolveProblem, hot-started from the previous period
+      // ---- PLDPSolver::SolveProblem, hot-started from the previous period.  A second pass (cold_restart) solves the
+      // period again from the cold start point when the reference would print "PB ON constraint" and call exit(0).
       PldpRes r;
-      double Vk = pldp_solve_warp(C, w.pw, A, ld, m, w.bv, Dl, w.zref, w.xk, !starting, w.pw.prev_zmp, n_prev,
-                                  w.prev_active, removed, K.max_iter, tol, lane, r);
-      int pstatus = r.status;
-      if ((pstatus == 1 || pstatus == 2) && K.cold_restart) {
-        // the reference prints "PB ON constraint" and calls exit(0); solve the period again from the cold start point
+      double Vk = 0.0;
+      int pstatus = 0;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool cold = attempt == 1;
+        Vk = pldp_solve_warp(C, w.pw, M, m, w.bv, Dl, w.zref, w.xk, !starting && !cold, w.pw.prev_zmp, cold ? 0 : n_prev,
+                             w.prev_active, cold ? 0 : removed, K.max_iter, tol, lane, r);
+        pstatus = cold ? (r.status == 0 ? 5 : r.status) : r.status;
+        if (cold || !((pstatus == 1 || pstatus == 2) && K.cold_restart)) break;
         __syncwarp();
-        Vk = pldp_solve_warp(C, w.pw, A, ld, m, w.bv, Dl, w.zref, w.xk, false, w.pw.prev_zmp, 0, w.prev_active, 0,
-                             K.max_iter, tol, lane, r);
-        pstatus = r.status == 0 ? 5 : r.status;
       }
       starting = false;
       removed = n_first;
@@ -430,6 +419,7 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
         if (lane < r.kproj && r.v2 < 0.0) w.prev_active[__popc(keep & ((1u << lane) - 1u))] = w.pw.active[lane];
         n_prev = __popc(keep);
         double z = 0.0;
+#pragma unroll 2
         for (int j = 0; j < N; ++j) z = add(z, mul(C.Pu[j * N + ii], bcast(Vk, j + N * ax)));
 #pragma unroll
         for (int j = 0; j < 3; ++j) z = add(z, mul(C.Px[ii * 3 + j], w.xk[3 * ax + j]));
@@ -438,6 +428,7 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
       }
       // NewX = iLQ^T X: entries 0 and N (:1382-1400)
       double jx = 0.0, jy = 0.0;
+#pragma unroll 2
       for (int j = 0; j < N; ++j) {
         const double vx = bcast(Vk, j), vy = bcast(Vk, j + N);
         jx += K.iLQc0[j] * vx;
@@ -852,21 +843,25 @@ int wg_dimitrov_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *co
   // ---- FootConstraintsAsLinearSystem
   if ((rc = launch_fcals(ctx, H, B, V.d_samp_off, d_left, d_right, d_types, d_lo, d_lci, d_nlci)) != WG_OK) return rc;
   // ---- the loop
-  const size_t smem = sizeof(double) * (size_t)DM_ACAP * DM_WARPS;
-  static bool attr = false;
-  if (!attr) {
-    WG_CUDA(ctx, cudaFuncSetAttribute(dimitrov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  const int grid = std::max(1, std::min((B + DM_WARPS - 1) / DM_WARPS, ctx->sm_count * 7));
-  if ((rc = dm_ensure(ctx, H, 11, sizeof(double) * ((size_t)grid * DM_WARPS * (DM_MAXM + 1) * PLDP_U + 2))) != WG_OK) return rc;
-  double *d_scratch = static_cast<double *>(H->buf[11]);
-  int *d_next = reinterpret_cast<int *>(d_scratch + (size_t)grid * DM_WARPS * (DM_MAXM + 1) * PLDP_U);
+  const int grid = std::max(1, std::min((B + DM_WARPS - 1) / DM_WARPS, ctx->sm_count * 4));
+  if ((rc = dm_ensure(ctx, H, 11, 64)) != WG_OK) return rc;
+  int *d_next = static_cast<int *>(H->buf[11]);
   WG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(int), ctx->stream));
+  // longest-processing-time-first order (the sample count is a faithful proxy of the period count)
+  if ((rc = dm_ensure(ctx, H, 2, sizeof(int) * nb)) != WG_OK) return rc;
+  {
+    std::vector<int> order(B);
+    for (int b = 0; b < B; ++b) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return V.samp_off[a + 1] - V.samp_off[a] > V.samp_off[b + 1] - V.samp_off[b];
+    });
+    WG_CUDA(ctx, cudaMemcpyAsync(H->buf[2], order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `order` is a pageable temporary
+  }
   wg_prof_start(ctx, WG_K_DIMITROV);
-  dimitrov_kernel<<<grid, DM_WARPS * 32, smem, ctx->stream>>>(B, H->d, dC, V.d_samp_off, H->d_time, d_lo, d_lci, d_nlci,
+  dimitrov_kernel<<<grid, DM_WARPS * 32, 0, ctx->stream>>>(B, H->d, dC, V.d_samp_off, H->d_time, d_lo, d_lci, d_nlci,
                                                               V.d_zd_status, d_com, zmp_out ? d_zmp : nullptr, d_po, d_per,
-                                                              d_st, d_dn, d_scratch, d_next);
+                                                              d_st, d_dn, d_next, static_cast<const int *>(H->buf[2]));
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   if (host) {

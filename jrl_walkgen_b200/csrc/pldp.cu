@@ -74,7 +74,8 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
     const double *xk = XkYk + (size_t)b * 6;
     const bool hs = hot && hot_start;
     PldpRes r;
-    const double Vk = pldp_solve_warp(C, w, A, ld, m, bv, Dl, zr, xk, hs && !start, hs ? hot[b].prev_zmp : nullptr,
+    const DenseMat M{A, ld};
+    const double Vk = pldp_solve_warp(C, w, M, m, bv, Dl, zr, xk, hs && !start, hs ? hot[b].prev_zmp : nullptr,
                                       hs ? hot[b].n_prev : 0, hs ? hot[b].prev_active : nullptr,
                                       nremoved ? nremoved[b] : 0, max_iter, tol, lane, r);
     const int status = r.status, it = r.it, k = r.k, kproj = r.kproj;
@@ -91,6 +92,7 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
       if (lane < kproj && v2 < 0.0) hot[b].prev_active[__popc(keep & ((1u << lane) - 1u))] = w.active[lane];
       if (lane == 0) hot[b].n_prev = __popc(keep);
       double z = 0.0;
+#pragma unroll 2
       for (int j = 0; j < N; ++j) z = add(z, mul(C.Pu[j * N + ii], bcast(Vk, j + N * ax)));
 #pragma unroll
       for (int j = 0; j < 3; ++j) z = add(z, mul(C.Px[ii * 3 + j], xk[3 * ax + j]));

@@ -20,6 +20,7 @@ struct PldpConsts {
 struct PldpWarp {
   double L[PLDP_KMAX * (PLDP_KMAX + 1) / 2];   // packed lower triangle, row i at i(i+1)/2
   double prev_zmp[PLDP_U];
+  double vec[2][PLDP_U];                        // broadcast staging: c / d and Vk (one LDS instead of two SHFL per read)
   int active[PLDP_KMAX];
 };
 
@@ -28,18 +29,44 @@ __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, 
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// ---- the constraint matrix (m+1) x 32 as the solver sees it: M.row(r).at(c) ------------------------------------
+// DenseMat: column-major array with leading dimension ld, as the reference receives it (global or shared memory).
+struct DenseMat {
+  const double *A;
+  int ld;
+  struct Row {
+    const double *p; int ld;
+    __device__ __forceinline__ double at(int c) const { return p[(size_t)c * ld]; }
+  };
+  __device__ __forceinline__ Row row(int r) const { return Row{A + r, ld}; }
+};
+// RankMat: the matrix BuildConstraintMatrices writes (ZMPConstrainedQPFastFormulation.cpp:885-905), never materialised:
+// element (r, k + 16 ax) = a[ax][r] * Pu[k * 16 + i_r], the same single IEEE multiplication the reference stores.
+struct RankMat {
+  const double *a0, *a1;   // [m]   A_r(0), A_r(1)
+  const int *ri;           // [m]   previewed sample of row r
+  const double *Pu;        // [16][16] m_Pu
+  struct Row {
+    double a0, a1; const double *pu;
+    __device__ __forceinline__ double at(int c) const { return mul(c < PLDP_N ? a0 : a1, pu[(c & (PLDP_N - 1)) * PLDP_N]); }
+  };
+  __device__ __forceinline__ Row row(int r) const { return Row{a0[r], a1[r], Pu + ri[r]}; }
+};
+
 // OptCholesky::UpdateCholeskyMatrixFortran (OptCholesky.cpp:171-223): row `i` of L for the active rows act[0..i].
 // Lane j computes M(i,j) = A_act[i] . A_act[j] in the reference's order and then the forward recurrence
 // L(i,j) = (M(i,j) - sum_{k<j} L(i,k) L(j,k)) / L(j,j), with the L(i,k) broadcast as they become final.
-__device__ void chol_add_row(double *L, const int *act, int i, const double *A, int ld, int lane)
+template <class Mat>
+__device__ __noinline__ void chol_add_row(double *L, const int *act, int i, const Mat &M, int lane)
 {
   double r = 0.0;
-  if (lane <= i) {
-    const double *ri = A + act[i], *rj = A + act[lane];
+  {
+    const typename Mat::Row ri = M.row(act[i]), rj = M.row(act[lane <= i ? lane : i]);
 #pragma unroll 4
-    for (int k = 0; k < PLDP_U; ++k) r = add(r, mul(ri[(size_t)k * ld], rj[(size_t)k * ld]));
+    for (int k = 0; k < PLDP_U; ++k) r = add(r, mul(ri.at(k), rj.at(k)));
   }
   double lij = 0.0;
+#pragma unroll 1
   for (int j = 0; j <= i; ++j) {
     // lane j finalises L(i,j)
     if (lane == j) lij = (j != i) ? r / L[tri(j) + j] : sqrt(r);
@@ -51,19 +78,21 @@ __device__ void chol_add_row(double *L, const int *act, int i, const double *A, 
   __syncwarp();
 }
 
-// PLDPSolver::SolveProblem for the problem (A: (m+1) x 32 column-major with leading dimension ld, bv, Dl = D[lane], zr,
-// xk) by the calling warp.  use_prev: start from the shifted previous ZMP solution prev_zmp[32] (hot start, not the
-// first call); n_prev / prev_active / nr: constraints kept from the previous solve and NumberOfRemovedConstraints.
+// PLDPSolver::SolveProblem for the problem (M: m x 32 constraint matrix, bv, Dl = D[lane], zr, xk) by the calling warp.
+// use_prev: start from the shifted previous ZMP solution prev_zmp[32] (hot start, not the first call); n_prev /
+// prev_active / nr: constraints kept from the previous solve and NumberOfRemovedConstraints.
 // Returns Vk (lane = entry); r.v2 / r.kproj: multipliers of the last projection (lane i < kproj), w.active[0..r.k).
 struct PldpRes { int status, it, k, kproj; double v2; };
 
-__device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp &w, const double *A, int ld, int m,
+template <class Mat>
+__device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp &w, const Mat &M, int m,
                                                   const double *bv, double Dl, const double *zr, const double *xk,
                                                   bool use_prev, const double *prev_zmp, int n_prev,
                                                   const int *prev_active, int nr, int max_iter, double tol, int lane,
                                                   PldpRes &r)
 {
   constexpr int N = PLDP_N;
+  constexpr int SLABS = 4;                       // rows lane, lane+32, lane+64, lane+96: m <= 128
   int status = 0;
   // `similar` is accepted for interface parity only: the A_j = -A_i reuse (PLDPSolver.cpp:570-590) yields products
   // bit-identical to computing every row directly, which is what the lanes do
@@ -78,9 +107,11 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
 #pragma unroll
     for (int j = 0; j < 3; ++j) Vk = add(Vk, -mul(ipx[j], xk[3 * ax + j]));
     if (use_prev) {
+#pragma unroll 2
       for (int j = 0; j < N - 1; ++j) Vk = add(Vk, mul(C.iPu[j * N + ii], w.prev_zmp[j + 1 + N * ax]));
       Vk = add(Vk, mul(C.iPu[(N - 1) * N + ii], zr[N - 1 + N * ax]));
     } else {
+#pragma unroll 2
       for (int j = 0; j < N; ++j) Vk = add(Vk, mul(C.iPu[j * N + ii], zr[j + N * ax]));
     }
   }
@@ -88,20 +119,23 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
   int k = 0;
   if (n_prev > 0) {
     const int np = n_prev;
+#pragma unroll 1
     for (int i = 0; i < np && k < PLDP_KMAX; ++i) {
       const int idx = prev_active[i] - nr;
       if (idx >= 0 && idx < m) {
         if (lane == 0) w.active[k] = idx;
         __syncwarp();
-        chol_add_row(w.L, w.active, k, A, ld, lane);
+        chol_add_row(w.L, w.active, k, M, lane);
         ++k;
       }
     }
   }
   // activity flags of the rows this lane owns (rows lane, lane+32, lane+64, lane+96)
   unsigned mine = 0;
+#pragma unroll 1
   for (int i = 0; i < k; ++i) { const int r = w.active[i]; if ((r & 31) == lane) mine |= 1u << (r >> 5); }
   int kproj = 0;         // size of the active set at the last projection (v2 is defined for lanes < kproj)
+  const int ns = (m + 31) >> 5;   // slabs of 32 rows in use
 
   double v2 = 0.0;       // lane i < k holds v2[i] of the last projection
   int it = 0;
@@ -109,19 +143,21 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
   while (cont) {
     // ---- step 1: c = -D - Vk (PLDPSolver.cpp:805-807)
     const double c = add(-Dl, -Vk);
+    __syncwarp();
+    w.vec[0][lane] = c;
+    w.vec[1][lane] = Vk;
+    __syncwarp();
     // ---- step 2: ComputeProjectedDescentDirection (PLDPSolver.cpp:404-532)
     // v1 = E c : lane li owns active row li
     double v1 = 0.0;
-    {
-      const double *row = A + ((lane < k) ? w.active[lane] : 0);
+    if (k > 0) {
+      const typename Mat::Row row = M.row(w.active[lane < k ? lane : 0]);
 #pragma unroll 4
-      for (int j = 0; j < PLDP_U; ++j) {
-        const double cj = bcast(c, j);
-        if (lane < k) v1 = add(v1, mul(row[(size_t)j * ld], cj));
-      }
+      for (int j = 0; j < PLDP_U; ++j) v1 = add(v1, mul(row.at(j), w.vec[0][j]));
     }
     // forward substitution L y = v1 (:342-365): y[i] += -L(i,k) y[k] in k order, then / L(i,i) (skipped when 0)
     double y = v1;
+#pragma unroll 1
     for (int i = 0; i < k; ++i) {
       if (lane == i) { const double dg = w.L[tri(i) + i]; if (dg != 0.0) y = y / dg; }
       const double yi = bcast(y, i);
@@ -131,9 +167,11 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
     // sum taken in INCREASING k' as the reference does.  Lane k' forms its product in parallel; only the ordered
     // additions are serial (the products and the shuffles are off the dependency chain).
     v2 = y;
+#pragma unroll 1
     for (int i = k - 1; i >= 0; --i) {
       const double p = (lane > i && lane < k) ? mul(w.L[tri(lane) + i], v2) : 0.0;
       double acc = bcast(v2, i);
+#pragma unroll 2
       for (int kk = i + 1; kk < k; ++kk) acc = add(acc, -bcast(p, kk));
       acc = acc / w.L[tri(i) + i];
       if (lane == i) v2 = acc;
@@ -141,49 +179,71 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
     kproj = k;
     // d = c - E^T v2 (:509-518): lane li, sequential over the active rows
     double d = c;
+#pragma unroll 1
     for (int j = 0; j < k; ++j) {
       const double vj = bcast(v2, j);
-      d = add(d, -mul(A[w.active[j] + (size_t)lane * ld], vj));
+      d = add(d, -mul(M.row(w.active[j]).at(lane), vj));
     }
-    // ---- step 3: ComputeAlpha (:534-653): rows lane, lane+32, ... ; running minimum in row order
+    __syncwarp();
+    w.vec[0][lane] = d;
+    __syncwarp();
+    // ---- step 3: ComputeAlpha (:534-653): rows lane, lane+32, ... ; running minimum in row order.  The column index
+    // runs in the OUTER loop so that the (up to 4) rows of a lane advance as independent dependency chains; each row's
+    // own sum keeps the reference's order.
     double alpha = 10000000.0;
     int cand = -1;
     {
-      double best = 10000000.0; int besti = 0x7fffffff;
-      for (int s = 0; s * 32 < m; ++s) {
-        const int li = lane + 32 * s;
-        double t1 = 0.0, t2 = 0.0;
-        const bool mineok = (li < m) && !((mine >> s) & 1u);
-        const double *row = A + (li < m ? li : 0);
-#pragma unroll 4
-        for (int j = 0; j < PLDP_U; ++j) {
-          const double dj = bcast(d, j);
-          if (mineok) t1 = add(t1, mul(row[(size_t)j * ld], dj));
-        }
-        const unsigned neg = __ballot_sync(0xffffffffu, mineok && t1 < 0.0);
-        if (neg) {
-          t2 = mineok ? -bv[li < m ? li : 0] : 0.0;
-#pragma unroll 4
-          for (int j = 0; j < PLDP_U; ++j) {
-            const double vj = bcast(Vk, j);
-            if (mineok && t1 < 0.0) t2 = add(t2, -mul(row[(size_t)j * ld], vj));
-          }
-          if (mineok && t1 < 0.0) {
-            if (t2 > tol) status = 1;                // "PB ON constraint": the start point violates row li
-            else if (t2 > 0.0) t2 = -tol;
-            const double la = t2 / t1;
-            if (la < best) { best = la; besti = li; }
-          }
-        }
-      }
-      // the reference keeps the FIRST row (in index order) that attains the minimum
+      double t1[SLABS];
+      bool ok[SLABS];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+      for (int s = 0; s < SLABS; ++s) { const int li = lane + 32 * s; ok[s] = (li < m) && !((mine >> s) & 1u); t1[s] = 0.0; }
+      {
+        typename Mat::Row rows[SLABS];
+#pragma unroll
+        for (int s = 0; s < SLABS; ++s) rows[s] = M.row((lane + 32 * s) < m ? lane + 32 * s : 0);
+#pragma unroll 2
+        for (int j = 0; j < PLDP_U; ++j) {
+          const double dj = w.vec[0][j];
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s)
+            if (s < ns) t1[s] = add(t1[s], mul(rows[s].at(j), dj));
+        }
+        bool want[SLABS];
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < SLABS; ++s) { want[s] = ok[s] && t1[s] < 0.0; any = any || want[s]; }
+        double best = 10000000.0; int besti = 0x7fffffff;
+        if (__any_sync(0xffffffffu, any)) {
+          double t2[SLABS];
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) t2[s] = -bv[(lane + 32 * s) < m ? lane + 32 * s : 0];
+#pragma unroll 2
+          for (int j = 0; j < PLDP_U; ++j) {
+            const double vj = w.vec[1][j];
+#pragma unroll
+            for (int s = 0; s < SLABS; ++s)
+              if (s < ns) t2[s] = add(t2[s], -mul(rows[s].at(j), vj));
+          }
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) {
+            if (want[s]) {
+              double t = t2[s];
+              if (t > tol) status = 1;                // "PB ON constraint": the start point violates row li
+              else if (t > 0.0) t = -tol;
+              const double la = t / t1[s];
+              if (la < best) { best = la; besti = lane + 32 * s; }
+            }
+          }
+        }
+        // the reference keeps the FIRST row (in index order) that attains the minimum
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+          if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (best < alpha) { alpha = best; if (alpha < 1.0) cand = besti; }
       }
-      if (best < alpha) { alpha = best; if (alpha < 1.0) cand = besti; }
     }
     status = __reduce_max_sync(0xffffffffu, status);
     if (alpha >= 1.0) { alpha = 1.0; cont = false; }
@@ -196,7 +256,7 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
         if (lane == 0) w.active[k] = cand;
         if ((cand & 31) == lane) mine |= 1u << (cand >> 5);
         __syncwarp();
-        chol_add_row(w.L, w.active, k, A, ld, lane);
+        chol_add_row(w.L, w.active, k, M, lane);
         ++k;
       }
     }
