@@ -533,6 +533,7 @@ def _cpu_dimitrov_worker(args):
     walks, feet, seconds = args
     par = do.default_params()
     par.cold_restart = 1
+    par.merge_duplicate_rows = 1
     zp = zo.default_params()
     periods = 0; done_walks = 0
     t0 = time.perf_counter()
@@ -572,9 +573,15 @@ def dimitrov_leg(ctx, wg, args, rank, want_cpu):
     B = args.dimitrov_walks
     off, steps, feet = workloads.kajita_steps_batch(B, seed=2000 + 1000 * rank)
     par = wg.dimitrov_default_params()
-    par.cold_restart = 1
-    ctx.dimitrov_set_params(par)
     plan = ctx.kajita_plan(off, steps, feet)
+    # one untimed pass with the reference's exact semantics (defaults): how many walks the reference itself would finish
+    ctx.dimitrov_set_params(par)
+    f_stat = np.zeros(B, dtype=np.int32); f_done = np.zeros(B, dtype=np.int32)
+    ctx._check(ctx.lib.wg_dimitrov_run_batch(ctx.h, plan.h, wg.WG_MEM_HOST, None, None, None, None, None, None,
+                                             f_stat.ctypes.data, f_done.ctypes.data))
+    par.cold_restart = 1
+    par.merge_duplicate_rows = 1
+    ctx.dimitrov_set_params(par)
     n = plan.total_samples
     so = plan.sample_offsets
     pc = np.array([ctx.lib.wg_dimitrov_period_count(C.byref(par), int(so[b + 1] - so[b])) for b in range(B)], dtype=np.int64)
@@ -619,11 +626,14 @@ def dimitrov_leg(ctx, wg, args, rank, want_cpu):
     res = {"workload": "dimitrov2008_footsteps_to_com_%d_walks_N16_pldp" % B, "walks": B, "samples": int(n),
            "qp_periods": periods, "qp_periods_if_all_walks_completed": int(pc.sum()), "ms_per_pass": ms,
            "qp_periods_per_s": periods / (ms * 1e-3), "walks_per_s": B / (ms * 1e-3),
-           "walks_completed": int((status == 0).sum()),
-           "walks_stopped_like_the_reference": int((status == 1).sum()),
-           "note": "cold_restart = 1 (a hot start the reference answers with exit(0) is solved again from the cold start "
-                   "point); walks whose closing double-support hull carries a duplicated half-plane stop with the "
-                   "reference's NaN / IFAIL exit and are counted as stopped, their periods up to the stop are counted",
+           "walks_completed": int((status == 0).sum()), "walks_stopped": int((status != 0).sum()),
+           "reference_semantics": {"walks_completed": int((f_stat == 0).sum()), "walks_stopped": int((f_stat != 0).sum()),
+                                   "qp_periods_before_the_stops": int(f_done.sum()),
+                                   "note": "defaults = the reference bit for bit: a walk stops where the reference calls "
+                                           "exit(0) (m_tol drift of a hot start) or returns IFAIL (NaN on a duplicated half-plane)"},
+           "note": "timed with cold_restart = 1 and merge_duplicate_rows = 1 (both off by default, both outside the "
+                   "reference): infeasible hot starts are solved again from the cold start point, half-planes that repeat "
+                   "their predecessor are dropped",
            "kernels": kern,
            "e2e": {"value": periods * n_e2e / e2e_s, "unit": "QP periods/s", "h2d_bytes_per_step": int(steps.nbytes + feet.nbytes),
                    "d2h_bytes_per_step": int(com.nbytes + zmp.nbytes + hstat.nbytes + hdone.nbytes),

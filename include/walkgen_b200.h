@@ -504,6 +504,11 @@ typedef struct wg_dimitrov_params {
                                          observable behaviour short of killing the process): the walk stops there with
                                          status 1.  1: the period is solved again from the cold start point
                                          (StartingSequence semantics, no kept constraints) and flagged status 5.        */
+  int32_t merge_duplicate_rows;       /* 0 (default): the polygons of the reference, bit for bit.  1: a half-plane that
+                                         repeats its predecessor (all three coefficients within 1e-9: the reference's hull
+                                         keeps corners that are collinear only up to rounding) is dropped, which removes
+                                         the singular active sets behind the reference's NaN / IFAIL stops.               */
+  int32_t reserved;
 } wg_dimitrov_params;
 
 void wg_dimitrov_default_params(wg_dimitrov_params *p);

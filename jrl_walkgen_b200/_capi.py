@@ -93,7 +93,7 @@ class DimitrovParams(C.Structure):
     _fields_ = [("T", C.c_double), ("sampling_period", C.c_double), ("com_height", C.c_double), ("alpha", C.c_double),
                 ("beta", C.c_double), ("constraint_x", C.c_double), ("constraint_y", C.c_double),
                 ("sole_length", C.c_double), ("sole_width", C.c_double), ("max_iterations", C.c_int32),
-                ("cold_restart", C.c_int32)]
+                ("cold_restart", C.c_int32), ("merge_duplicate_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 def dimitrov_dtypes():

@@ -47,6 +47,7 @@ struct DimConsts {
   int interval;                       // (int)(T / Ts)
   int max_iter;
   int cold_restart;
+  int merge_rows;
 };
 
 struct DimHost {
@@ -160,7 +161,7 @@ __device__ __forceinline__ void dv_edge(const P2 &from, const P2 &to, const P2 &
 
 // ComputeLinearSystem + FindSimilarConstraints into the record at `o` (every field except t_end, which the lane of the
 // NEXT state change owns)
-__device__ void dv_write_polygon(wg_lci *o, const P2 *v, int n, double t_start, int first_sample, int state)
+__device__ void dv_write_polygon(wg_lci *o, const P2 *v, int n, double t_start, int first_sample, int state, int merge)
 {
   double A0[WG_LCI_MAX_ROWS], A1[WG_LCI_MAX_ROWS], Bv[WG_LCI_MAX_ROWS];
   double C0 = 0.0, C1 = 0.0;
@@ -171,6 +172,17 @@ __device__ void dv_write_polygon(wg_lci *o, const P2 *v, int n, double t_start, 
   C0 += v[n - 1].col; C1 += v[n - 1].row;
   C0 /= (double)n; C1 /= (double)n;
   dv_edge(v[n - 1], v[0], v[0], A0[n - 1], Bv[n - 1], A1[n - 1]);
+  if (merge) {
+    // NOT in the reference (wg_dimitrov_params.merge_duplicate_rows): drop a half-plane that repeats its predecessor
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+      if (k > 0 && fabs(A0[i] - A0[k - 1]) <= 1e-9 && fabs(A1[i] - A1[k - 1]) <= 1e-9 && fabs(Bv[i] - Bv[k - 1]) <= 1e-9) continue;
+      A0[k] = A0[i]; A1[k] = A1[i]; Bv[k] = Bv[i];
+      ++k;
+    }
+    if (k > 1 && fabs(A0[k - 1] - A0[0]) <= 1e-9 && fabs(A1[k - 1] - A1[0]) <= 1e-9 && fabs(Bv[k - 1] - Bv[0]) <= 1e-9) --k;
+    n = k;
+  }
   const double W0 = (A0[0] * C0 + A1[0] * C1) + Bv[0], W1 = (A0[1] * C0 + A1[1] * C1) + Bv[1];
   for (int i = 0; i < WG_LCI_MAX_ROWS; ++i) {
     o->A[i][0] = i < n ? A0[i] : 0.0; o->A[i][1] = i < n ? A1[i] : 0.0; o->B[i] = i < n ? Bv[i] : 0.0;
@@ -271,7 +283,7 @@ fcals_kernel(int B, const DimConsts *__restrict__ Kp, const int64_t *__restrict_
             if (L.z < R.z) dv_foot_corners(L, hw, hh, hull);
             else dv_foot_corners(R, hw, hh, hull);
           }
-          dv_write_polygon(out + idx, hull, nh, t, i, res);
+          dv_write_polygon(out + idx, hull, nh, t, i, res, Kp->merge_rows);
         }
       }
       count += __popc(bm);
@@ -588,6 +600,7 @@ int make_constants(const wg_dimitrov_params &p, DimHost *H)
   H->h.interval = (int)(T / p.sampling_period);
   H->h.max_iter = p.max_iterations > 0 ? p.max_iterations : 4 * PLDP_KMAX;
   H->h.cold_restart = p.cold_restart;
+  H->h.merge_rows = p.merge_duplicate_rows;
   if (H->h.interval < 1 || H->h.interval > 31) return WG_ERR_INVALID;   // interval + 1 samples = one per lane
   return WG_OK;
 }

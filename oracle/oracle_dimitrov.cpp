@@ -107,7 +107,7 @@ void edge(const Pt &from, const Pt &to, const Pt &icpt, double &a, double &b, do
   }
 }
 
-int linear_system(const std::vector<Pt> &v, wg_lci &o)
+int linear_system(const std::vector<Pt> &v, wg_lci &o, int merge)
 {
   const unsigned n = (unsigned)v.size();
   double C0 = 0.0, C1 = 0.0;
@@ -124,6 +124,21 @@ int linear_system(const std::vector<Pt> &v, wg_lci &o)
   o.A[n - 1][0] = a; o.A[n - 1][1] = c; o.B[n - 1] = b;
   o.center[0] = C0; o.center[1] = C1;
   o.rows = (int)n;
+  if (merge) {
+    /* NOT in the reference (wg_dimitrov_params.merge_duplicate_rows): drop a half-plane that repeats its predecessor */
+    auto near = [&](int i, int j) {
+      return fabs(o.A[i][0] - o.A[j][0]) <= 1e-9 && fabs(o.A[i][1] - o.A[j][1]) <= 1e-9 && fabs(o.B[i] - o.B[j]) <= 1e-9;
+    };
+    int k = 0;
+    for (int i = 0; i < (int)n; ++i) {
+      if (k > 0 && near(i, k - 1)) continue;
+      o.A[k][0] = o.A[i][0]; o.A[k][1] = o.A[i][1]; o.B[k] = o.B[i];
+      ++k;
+    }
+    if (k > 1 && near(k - 1, 0)) --k;
+    for (int i = k; i < (int)n; ++i) { o.A[i][0] = 0.0; o.A[i][1] = 0.0; o.B[i] = 0.0; }
+    o.rows = k;
+  }
   /* W = A C (rows 0 and 1 only are tested, :244-249) */
   const double W0 = (o.A[0][0] * C0 + o.A[0][1] * C1) + o.B[0], W1 = (o.A[1][0] * C0 + o.A[1][1] * C1) + o.B[1];
   return (W0 < 0 || W1 < 0) ? -1 : 0;
@@ -258,7 +273,7 @@ int oracle_convex_hull(int n, const double *xy, double *hull_xy, int cap)
 /* BuildLinearConstraintInequalities.  feet [n][4] = x, y, z, theta(deg); step_type / time: the left foot's.
  * Returns the number of polygons found (the first `cap` are stored). */
 int oracle_fcals_build(int n, const double *left, const double *right, const int *step_type, const double *time,
-                       double sole_length, double sole_width, double cx, double cy, int cap, wg_lci *out)
+                       double sole_length, double sole_width, double cx, double cy, int cap, wg_lci *out, int merge)
 {
   double lhw = sole_length, lhh = sole_width, rhw = sole_length, rhh = sole_width;
   rhw *= 0.5; rhh *= 0.5; lhw *= 0.5; lhh *= 0.5;
@@ -293,7 +308,7 @@ int oracle_fcals_build(int n, const double *left, const double *right, const int
       wg_lci o;
       std::memset(&o, 0, sizeof o);
       if ((int)hull.size() > WG_LCI_MAX_ROWS) return -2;
-      o.rc = linear_system(hull, o);
+      o.rc = linear_system(hull, o, merge);
       find_similar(o);
       o.t_start = time[i];
       o.first_sample = i;
@@ -400,7 +415,7 @@ long oracle_dimitrov_run(const wg_dimitrov_params *par, long n, const double *le
   { double t = 0.0; for (long i = 0; i < n; ++i) { time[i] = t; t += par->sampling_period; } }
   std::vector<wg_lci> lci(4096);
   const int np = oracle_fcals_build((int)n, left, right, step_type, time.data(), par->sole_length, par->sole_width,
-                                    par->constraint_x, par->constraint_y, (int)lci.size(), lci.data());
+                                    par->constraint_x, par->constraint_y, (int)lci.size(), lci.data(), par->merge_duplicate_rows);
   if (np < 0 || np > (int)lci.size()) return -4;
   const double T = par->T, Ts = par->sampling_period;
   const int interval = (int)(T / Ts);

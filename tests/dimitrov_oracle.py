@@ -18,12 +18,12 @@ class Params(C.Structure):
     _fields_ = [("T", C.c_double), ("sampling_period", C.c_double), ("com_height", C.c_double), ("alpha", C.c_double),
                 ("beta", C.c_double), ("constraint_x", C.c_double), ("constraint_y", C.c_double),
                 ("sole_length", C.c_double), ("sole_width", C.c_double), ("max_iterations", C.c_int32),
-                ("cold_restart", C.c_int32)]
+                ("cold_restart", C.c_int32), ("merge_duplicate_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 def default_params():
     """ZMPConstrainedQPFastFormulation.cpp:79-96 + the sole of the HRP-2 test robot (0.25 x 0.14)."""
-    return Params(0.1, 0.005, 0.80, 200.0, 1000.0, 0.04, 0.04, 0.25, 0.14, 0, 0)
+    return Params(0.1, 0.005, 0.80, 200.0, 1000.0, 0.04, 0.04, 0.25, 0.14, 0, 0, 0, 0)
 
 
 def clock(n, Ts=0.005):
@@ -60,7 +60,7 @@ def fcals(left, right, left_type, par=None, cap=512):
                                        C.c_void_p(st.ctypes.data), C.c_void_p(t.ctypes.data),
                                        C.c_double(par.sole_length), C.c_double(par.sole_width),
                                        C.c_double(par.constraint_x), C.c_double(par.constraint_y), cap,
-                                       C.c_void_p(out.ctypes.data))
+                                       C.c_void_p(out.ctypes.data), int(par.merge_duplicate_rows))
     assert 0 <= n <= cap, n
     return out[:n]
 

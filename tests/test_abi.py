@@ -34,7 +34,8 @@ def test_header_is_plain_c_and_struct_layouts_match_the_python_mirrors(tmp_path)
     prog = tmp_path / "sizes.c"
     structs = ["wg_preview_gains_t", "wg_herdt_params", "wg_herdt_qp_input", "wg_herdt_qp_output", "wg_herdt_mpc_params",
                "wg_herdt_foot_sample", "wg_herdt_tick", "wg_herdt_mpc_state", "wg_herdt_mpc_step", "wg_pldp_state",
-               "wg_pldp_info", "wg_pldp_batch", "wg_rel_step", "wg_foot_sample", "wg_zmpdisc_params"]
+               "wg_pldp_info", "wg_pldp_batch", "wg_rel_step", "wg_foot_sample", "wg_zmpdisc_params", "wg_lci",
+               "wg_dimitrov_params", "wg_dimitrov_period"]
     body = "\n".join(f'  printf("{s} %zu\\n", sizeof({s}));' for s in structs)
     prog.write_text(f'#include <stdio.h>\n#include "{HEADER}"\nint main(void) {{\n{body}\n  return 0;\n}}\n')
     exe = tmp_path / "sizes"
@@ -56,6 +57,11 @@ def test_header_is_plain_c_and_struct_layouts_match_the_python_mirrors(tmp_path)
     assert sizes["wg_rel_step"] == wg.REL_STEP_DTYPE.itemsize == 48
     assert sizes["wg_foot_sample"] == wg.KAJITA_FOOT_DTYPE.itemsize == 48
     assert sizes["wg_zmpdisc_params"] == C.sizeof(_capi.ZmpDiscParams)
+    assert sizes["wg_lci"] == wg.LCI_DTYPE.itemsize == 272
+    assert sizes["wg_dimitrov_period"] == wg.DIMITROV_PERIOD_DTYPE.itemsize == 224
+    assert sizes["wg_dimitrov_params"] == C.sizeof(_capi.DimitrovParams)
+    import dimitrov_oracle as do
+    assert C.sizeof(do.Params) == sizes["wg_dimitrov_params"] and do.LCI.itemsize == 272 and do.PERIOD.itemsize == 224
 
 
 def test_host_only_entry_points_work_without_a_gpu():

@@ -162,6 +162,24 @@ def test_oracle_loop_stops_like_the_reference_on_duplicated_hull_rows():
     assert np.isnan(out["periods"]["jerk_x"][-1])
 
 
+def test_oracle_robust_mode_completes_every_profile():
+    """cold_restart + merge_duplicate_rows (both NOT in the reference, both off by default): every TestKajita2003 profile
+    runs to its last period; the polygons only lose rows that repeat their predecessor."""
+    par = do.default_params()
+    par.cold_restart = 1
+    par.merge_duplicate_rows = 1
+    for name in PROFILES:
+        left, right, lt, _ = feet_of(name)
+        out = do.run(left, right, lt, par)
+        assert out["failed_at"] is None and len(out["periods"]) == do.period_count(len(left), par), name
+        assert set(out["periods"]["status"]) <= {0, 5}
+        P0, P1 = do.fcals(left, right, lt), do.fcals(left, right, lt, par)
+        assert len(P0) == len(P1) and (P1["rows"] <= P0["rows"]).all() and (P1["rows"] >= 4).all()
+        assert (P1["rows"][P0["state"] != 3] == 4).all()
+    left, right, lt, _ = feet_of("Circle")
+    assert do.fcals(left, right, lt)[-1]["rows"] == 6 and do.fcals(left, right, lt, par)[-1]["rows"] == 4
+
+
 @pytest.mark.parametrize("name", PROFILES)
 def test_oracle_loop_properties(name):
     """Size-independent properties of the generated walk (cold_restart = 1 so that the walk continues where the
@@ -299,6 +317,46 @@ def test_gpu_dimitrov_closed_loop_matches_oracle(ctx, name, cold):
     assert np.abs(out["com"][nw:]).max() == 0.0
     # rows the loop does not reach keep the discretised ZMP reference
     np.testing.assert_array_equal(out["zmp"][nw:], o["zmp"][nw:, :2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", PROFILES)
+def test_gpu_dimitrov_robust_mode_matches_oracle(ctx, name):
+    """cold_restart + merge_duplicate_rows: every profile completes on the device as in the oracle."""
+    import jrl_walkgen_b200 as wg
+    steps = zo.profile_steps(name)
+    o = zo.run(zo.default_params(), steps)
+    par = do.default_params()
+    par.cold_restart = 1; par.merge_duplicate_rows = 1
+    ref = do.run(o["left"], o["right"], o["types"][:, 1].copy(), par)
+    gp = wg.dimitrov_default_params()
+    gp.cold_restart = 1; gp.merge_duplicate_rows = 1
+    ctx.dimitrov_set_params(gp)
+    out = ctx.dimitrov_run([steps], [zo.INIT_FEET])
+    per, rper = out["periods"][0], ref["periods"]
+    assert out["status"][0] == 0 and ref["failed_at"] is None and len(per) == len(rper) == out["period_counts"][0]
+    assert (per["m"] == rper["m"]).all() and set(per["status"]) <= {0, 5}
+    # The cold-restart decision is the reference's `violation > m_tol` test on a violation that the solver's own
+    # tolerance handling parks AT m_tol (1.0000000x e-8): with rotated feet (device sin/cos differ from glibc's in the
+    # last bit) the two sides can decide differently, and since PLDP never drops a constraint inside a solve the
+    # restarted period ends on a different vertex.  Parity is therefore asserted up to the first differing decision
+    # (456 of 497 periods on PbFlorentSeq2, all periods on the other profiles); the rest is checked by property.
+    differ = np.nonzero(per["status"] != rper["status"])[0]
+    good = len(per) if len(differ) == 0 else int(differ[0])
+    assert good >= 0.9 * len(per), (good, len(per))
+    if name != "PbFlorentSeq2":
+        assert good == len(per)
+    n = 20 * good
+    np.testing.assert_allclose(out["com"][:n, [0, 3]], ref["com"][:n, [0, 3]], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out["zmp"][:n], ref["zmp"][:n], rtol=0, atol=1e-6)
+    P = ctx.fcals_build(o["left"], o["right"], o["types"])
+    Pr = do.fcals(o["left"], o["right"], o["types"][:, 1].copy(), par)
+    assert (P["rows"] == Pr["rows"]).all()
+    for k in range(len(per)):         # every period, including those after a differing decision: CoP inside its polygon
+        pk = P[np.searchsorted(P["t_end"], per["t_start"][k], side="left")]
+        r = pk["rows"]
+        assert (pk["A"][:r] @ out["zmp"][20 * k + 19] + pk["B"][:r] > -1e-6).all(), k
+    ctx.dimitrov_set_params()
 
 
 @pytest.mark.gpu
