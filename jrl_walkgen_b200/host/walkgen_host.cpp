@@ -23,6 +23,11 @@ wg_ctx *default_context()
   return ctx;
 }
 
+void walkgen_b200_check(int rc, const char *what)
+{
+  if (rc != WG_OK) throw std::runtime_error(std::string("walkgen_b200: ") + what + ": " + wg_last_error(walkgen_b200::default_context()));
+}
+
 static void check(int rc, const char *what)
 {
   if (rc != WG_OK) throw std::runtime_error(std::string("walkgen_b200: ") + what + ": " + wg_last_error(default_context()));
@@ -574,6 +579,151 @@ bool PatternGeneratorInterface::RunOneStepOfTheControlLoop(COMState &COMStateOut
   LeftFootPosition = m_LeftFootPositions.front(); RightFootPosition = m_RightFootPositions.front();
   m_COMBuffer.pop_front(); m_ZMPPositions.pop_front(); m_LeftFootPositions.pop_front(); m_RightFootPositions.pop_front();
   return true;
+}
+
+}  // namespace PatternGeneratorJRL
+
+// ---- Dimitrov2008 path -------------------------------------------------------------------------------------------
+namespace PatternGeneratorJRL {
+
+using walkgen_b200::walkgen_b200_check;
+
+void ComputeConvexHull::DoComputeConvexHull(std::vector<CH_Point> aVecOfPoints, std::vector<CH_Point> &TheConvexHull)
+{
+  if (aVecOfPoints.empty()) return;
+  if (aVecOfPoints.size() > 8) throw std::runtime_error("walkgen_b200: DoComputeConvexHull is built for at most 8 points (two feet)");
+  wg_ctx *ctx = walkgen_b200::default_context();
+  double xy[16], hull[16];
+  int32_t n = 0;
+  for (size_t i = 0; i < aVecOfPoints.size(); ++i) { xy[2 * i] = aVecOfPoints[i].col; xy[2 * i + 1] = aVecOfPoints[i].row; }
+  walkgen_b200_check(wg_convex_hull_batch(ctx, WG_MEM_HOST, 1, (int)aVecOfPoints.size(), xy, hull, &n), "wg_convex_hull_batch");
+  for (int i = 0; i < n; ++i) { CH_Point p; p.col = hull[2 * i]; p.row = hull[2 * i + 1]; TheConvexHull.push_back(p); }
+}
+
+FootConstraintsAsLinearSystem::FootConstraintsAsLinearSystem(SimplePluginManager *aSPM, double sole_length, double sole_width)
+    : SimplePlugin(aSPM), m_SoleLength(sole_length), m_SoleWidth(sole_width) {}
+
+int FootConstraintsAsLinearSystem::BuildLinearConstraintInequalities(
+    std::deque<FootAbsolutePosition> &Left, std::deque<FootAbsolutePosition> &Right,
+    std::deque<LinearConstraintInequality_t *> &Queue, double ConstraintOnX, double ConstraintOnY)
+{
+  if (Left.size() != Right.size()) return -1;
+  const size_t n = Left.size();
+  if (n == 0) return 0;
+  wg_ctx *ctx = walkgen_b200::default_context();
+  wg_dimitrov_params p;
+  wg_dimitrov_default_params(&p);
+  p.constraint_x = ConstraintOnX; p.constraint_y = ConstraintOnY;
+  p.sole_length = m_SoleLength; p.sole_width = m_SoleWidth;
+  walkgen_b200_check(wg_dimitrov_set_params(ctx, &p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr), "wg_dimitrov_set_params");
+  std::vector<wg_foot_sample> l(n), r(n);
+  std::vector<int32_t> ty(3 * n, 0);
+  for (size_t i = 0; i < n; ++i) {
+    l[i].x = Left[i].x; l[i].y = Left[i].y; l[i].z = Left[i].z; l[i].theta = Left[i].theta; l[i].omega = l[i].omega2 = 0;
+    r[i].x = Right[i].x; r[i].y = Right[i].y; r[i].z = Right[i].z; r[i].theta = Right[i].theta; r[i].omega = r[i].omega2 = 0;
+    ty[3 * i + 1] = Left[i].stepType; ty[3 * i + 2] = Right[i].stepType;
+  }
+  // a state change needs at least one sample: n polygons is the hard bound, a walk has a few per step
+  const int64_t cap = (int64_t)std::min<size_t>(n, 4096);
+  const int64_t so[2] = {0, (int64_t)n}, lo[2] = {0, cap};
+  std::vector<wg_lci> out((size_t)cap);
+  int32_t cnt = 0;
+  walkgen_b200_check(wg_fcals_build_batch(ctx, WG_MEM_HOST, 1, so, l.data(), r.data(), ty.data(), lo, out.data(), &cnt),
+                     "wg_fcals_build_batch");
+  for (int k = 0; k < cnt; ++k) {
+    LinearConstraintInequality_t *q = new LinearConstraintInequality_t;
+    const int nr = out[k].rows;
+    q->A.resize(nr, 2); q->B.resize(nr, 1);
+    q->Center.assign(out[k].center, out[k].center + 2);
+    q->SimilarConstraints.assign(out[k].similar, out[k].similar + nr);
+    for (int j = 0; j < nr; ++j) { q->A(j, 0) = out[k].A[j][0]; q->A(j, 1) = out[k].A[j][1]; q->B(j, 0) = out[k].B[j]; }
+    // the clock of the feet samples as the caller set it (the device uses the accumulated 5 ms clock, which is what
+    // ZMPDiscretization writes into .time)
+    q->StartingTime = Left[out[k].first_sample].time;
+    q->EndingTime = (k + 1 < cnt) ? Left[out[k + 1].first_sample].time : Left[n - 1].time;
+    Queue.push_back(q);
+  }
+  return 0;
+}
+
+ZMPConstrainedQPFastFormulation::ZMPConstrainedQPFastFormulation(SimplePluginManager *lSPM, std::string, double sole_length,
+                                                                 double sole_width)
+    : ZMPRefTrajectoryGeneration(lSPM), m_Dirty(true), m_Status(0), m_Done(0)
+{
+  wg_dimitrov_default_params(&m_Par);
+  m_Par.sole_length = sole_length; m_Par.sole_width = sole_width;
+  wg_zmpdisc_default_params(&m_Zd);
+  std::string name = ":setdimitrovconstraint";
+  RegisterMethod(name);
+}
+
+int ZMPConstrainedQPFastFormulation::InitConstants()
+{
+  wg_ctx *ctx = walkgen_b200::default_context();
+  const int rc = wg_dimitrov_set_params(ctx, &m_Par, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc == WG_OK) m_Dirty = false;
+  return rc == WG_OK ? 0 : -1;
+}
+
+void ZMPConstrainedQPFastFormulation::CallMethod(std::string &Method, std::istringstream &strm)
+{
+  if (Method == ":setdimitrovconstraint") {       /* ZMPConstrainedQPFastFormulation.cpp:1586-1596 */
+    strm >> m_Par.constraint_x >> m_Par.constraint_y;
+    m_Dirty = true;
+    return;
+  }
+  ZMPRefTrajectoryGeneration::CallMethod(Method, strm);
+}
+
+void ZMPConstrainedQPFastFormulation::GetZMPDiscretization(
+    std::deque<ZMPPosition> &ZMPPositions, std::deque<COMState> &COMStates, std::deque<RelativeFootPosition> &Rel,
+    std::deque<FootAbsolutePosition> &Left, std::deque<FootAbsolutePosition> &Right, double, COMState &, double[3],
+    FootAbsolutePosition &InitLeft, FootAbsolutePosition &InitRight)
+{
+  if (Rel.empty()) return;
+  wg_ctx *ctx = walkgen_b200::default_context();
+  m_Zd.sampling_period = m_SamplingPeriod; m_Zd.t_single = m_Tsingle; m_Zd.t_double = m_Tdble;
+  m_Zd.step_height = m_StepHeight; m_Zd.omega = m_Omega;
+  m_Par.sampling_period = m_SamplingPeriod;
+  // the context's constants are shared by every generator object: (re)install this object's before each plan
+  if (InitConstants() != 0) throw std::runtime_error(std::string("walkgen_b200: ") + wg_last_error(ctx));
+  std::vector<wg_rel_step> steps(Rel.size());
+  for (size_t i = 0; i < Rel.size(); ++i) {
+    std::memset(&steps[i], 0, sizeof(wg_rel_step));
+    steps[i].sx = Rel[i].sx; steps[i].sy = Rel[i].sy; steps[i].theta = Rel[i].theta;
+    steps[i].ss_time = Rel[i].SStime; steps[i].ds_time = Rel[i].DStime; steps[i].step_type = Rel[i].stepType;
+  }
+  const int64_t off[2] = {0, (int64_t)steps.size()};
+  const double feet[6] = {InitLeft.x, InitLeft.y, InitLeft.theta, InitRight.x, InitRight.y, InitRight.theta};
+  wg_kajita_plan *plan = nullptr;
+  walkgen_b200_check(wg_kajita_plan_create(ctx, &m_Zd, 1, off, steps.data(), feet, &plan), "wg_kajita_plan_create");
+  const int64_t n = wg_kajita_plan_total_samples(plan);
+  std::vector<double> com(6 * (size_t)n), zmp(2 * (size_t)n);
+  std::vector<wg_foot_sample> l((size_t)n), r((size_t)n);
+  int32_t status = 0, done = 0;
+  const int rc = wg_dimitrov_run_batch(ctx, plan, WG_MEM_HOST, com.data(), zmp.data(), l.data(), r.data(), nullptr, nullptr,
+                                       &status, &done);
+  wg_kajita_plan_destroy(plan);
+  walkgen_b200_check(rc, "wg_dimitrov_run_batch");
+  m_Status = status; m_Done = done;
+  ZMPPositions.resize((size_t)n); COMStates.resize((size_t)n); Left.resize((size_t)n); Right.resize((size_t)n);
+  double t = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    ZMPPosition &z = ZMPPositions[(size_t)i];
+    z.px = zmp[2 * i]; z.py = zmp[2 * i + 1]; z.pz = 0.0; z.theta = 0.0; z.time = t; z.stepType = 0;
+    COMState &c = COMStates[(size_t)i];
+    c.reset();
+    for (int k = 0; k < 3; ++k) { c.x[k] = com[6 * i + k]; c.y[k] = com[6 * i + 3 + k]; }
+    c.z[0] = m_Par.com_height;
+    FootAbsolutePosition *fp[2] = {&Left[(size_t)i], &Right[(size_t)i]};
+    const wg_foot_sample *fs[2] = {&l[(size_t)i], &r[(size_t)i]};
+    for (int f = 0; f < 2; ++f) {
+      std::memset(fp[f], 0, sizeof(FootAbsolutePosition));
+      fp[f]->x = fs[f]->x; fp[f]->y = fs[f]->y; fp[f]->z = fs[f]->z; fp[f]->theta = fs[f]->theta;
+      fp[f]->omega = fs[f]->omega; fp[f]->omega2 = fs[f]->omega2; fp[f]->time = t;
+    }
+    t += m_SamplingPeriod;
+  }
 }
 
 }  // namespace PatternGeneratorJRL

@@ -254,6 +254,79 @@ class ZMPVelocityReferencedQP : public ZMPRefTrajectoryGeneration {
   unsigned m_StepsBeforeStop;
 };
 
+/* ---- Dimitrov2008 path: the classes around PLDPSolver (names and signatures of the reference) ------------------------ */
+struct RelativeFootPosition {            /* include/jrl/walkgen/pgtypes.hh:100-109 */
+  double sx, sy, theta;
+  double SStime, DStime;
+  int stepType;
+  double DeviationHipHeight;
+};
+typedef struct { double col, row; } CH_Point;                       /* src/Mathematics/ConvexHull.hh:39-42 */
+struct LinearConstraintInequality_t {    /* include/jrl/walkgen/pgtypes.hh:168-177; A z + B >= 0 */
+  MAL_MATRIX(A, double);
+  MAL_MATRIX(B, double);
+  std::vector<double> Center;
+  std::vector<int> SimilarConstraints;
+  double StartingTime, EndingTime;
+};
+
+class ComputeConvexHull {                /* src/Mathematics/ConvexHull.hh:47-60 */
+ public:
+  void DoComputeConvexHull(std::vector<CH_Point> aVecOfPoints, std::vector<CH_Point> &TheConvexHull);
+};
+
+class FootConstraintsAsLinearSystem : public SimplePlugin {   /* src/Mathematics/FootConstraintsAsLinearSystem.hh:54-120 */
+ public:
+  /* the robot is only asked for the sole size of its feet (FootConstraintsAsLinearSystem.cpp:269-281): pass it directly */
+  FootConstraintsAsLinearSystem(SimplePluginManager *aSPM, double sole_length = 0.25, double sole_width = 0.14);
+  int BuildLinearConstraintInequalities(std::deque<FootAbsolutePosition> &LeftFootAbsolutePositions,
+                                        std::deque<FootAbsolutePosition> &RightFootAbsolutePositions,
+                                        std::deque<LinearConstraintInequality_t *> &QueueOfLConstraintInequalities,
+                                        double ConstraintOnX, double ConstraintOnY);
+  void CallMethod(std::string &, std::istringstream &) {}
+ private:
+  double m_SoleLength, m_SoleWidth;
+};
+
+class ZMPConstrainedQPFastFormulation : public ZMPRefTrajectoryGeneration {   /* ...ZMPConstrainedQPFastFormulation.hh */
+ public:
+  static const unsigned int PLDP = 2;
+  ZMPConstrainedQPFastFormulation(SimplePluginManager *lSPM, std::string DataFile, double sole_length = 0.25,
+                                  double sole_width = 0.14);
+  /* the whole walk, off line, as in the reference: ZMPDiscretization + BuildZMPTrajectoryFromFootTrajectory (PLDP).
+   * Returns through the deques; LastStatus() = 0, or 1 where the reference prints IFAIL / calls exit(0). */
+  void GetZMPDiscretization(std::deque<ZMPPosition> &ZMPPositions, std::deque<COMState> &COMStates,
+                            std::deque<RelativeFootPosition> &RelativeFootPositions,
+                            std::deque<FootAbsolutePosition> &LeftFootAbsolutePositions,
+                            std::deque<FootAbsolutePosition> &RightFootAbsolutePositions, double Xmax,
+                            COMState &lStartingCOMState, double lStartingZMPPosition[3],
+                            FootAbsolutePosition &InitLeftFootAbsolutePosition,
+                            FootAbsolutePosition &InitRightFootAbsolutePosition);
+  int InitConstants();
+  void SetAlpha(const double &a) { m_Par.alpha = a; m_Dirty = true; }
+  const double &GetAlpha() const { return m_Par.alpha; }
+  void SetBeta(const double &b) { m_Par.beta = b; m_Dirty = true; }
+  const double &GetBeta() const { return m_Par.beta; }
+  /* :setdimitrovconstraint X Y; the ZMPRefTrajectoryGeneration commands reach the embedded ZMPDiscretization */
+  void CallMethod(std::string &Method, std::istringstream &strm);
+  /* not in the reference (both off by default): wg_dimitrov_params.cold_restart / merge_duplicate_rows */
+  void SetRobustMode(bool cold_restart, bool merge_duplicate_rows)
+  { m_Par.cold_restart = cold_restart; m_Par.merge_duplicate_rows = merge_duplicate_rows; m_Dirty = true; }
+  int LastStatus() const { return m_Status; }
+  int PeriodsDone() const { return m_Done; }
+  /* InitOnLine / OnLine are not provided by the reference for this generator either (they return 0 / do nothing) */
+  int InitOnLine(std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
+                 std::deque<FootAbsolutePosition> &, FootAbsolutePosition &, FootAbsolutePosition &, std::deque<double> &,
+                 COMState &, double[3]) { return 0; }
+  void OnLine(double, std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
+              std::deque<FootAbsolutePosition> &) {}
+ private:
+  wg_dimitrov_params m_Par;
+  wg_zmpdisc_params m_Zd;
+  bool m_Dirty;
+  int m_Status, m_Done;
+};
+
 /* The PGI facade for the Herdt path: command bus + the 5 ms tick. */
 class PatternGeneratorInterface : public SimplePluginManager, public SimplePlugin {
  public:

@@ -216,6 +216,54 @@ static int test_pldp(const char *in, const char *out)
   return 0;
 }
 
+
+// ZMPConstrainedQPFastFormulation::GetZMPDiscretization on TestKajita2003's straight walk (tests/TestKajita2003.cpp:104-119)
+// + FootConstraintsAsLinearSystem on the feet it returns.  out: int64 n, int32 status, done, npoly, pad; com[n][6];
+// rows[npoly] (int32)
+static int test_dimitrov(const char *out, bool robust)
+{
+  SimplePluginManager spm;
+  ZMPConstrainedQPFastFormulation gen(&spm, "");
+  const char *cmds[] = {":samplingperiod 0.005", ":singlesupporttime 0.78", ":doublesupporttime 0.02", ":stepheight 0.07",
+                        ":setdimitrovconstraint 0.04 0.04"};
+  for (const char *c : cmds) {
+    std::istringstream is(c);
+    std::string m; is >> m;
+    spm.CallMethod(m, is);
+  }
+  gen.SetRobustMode(robust, robust);
+  std::deque<RelativeFootPosition> rel;
+  const double seq[][3] = {{0.0, -0.105, 0.0}, {0.2, 0.21, 0.0}, {0.2, -0.21, 0.0}, {0.2, 0.21, 0.0}, {0.2, -0.21, 0.0},
+                           {0.2, 0.21, 0.0}, {0.2, -0.21, 0.0}, {0.2, 0.21, 0.0}, {0.2, -0.21, 0.0}, {0.2, 0.21, 0.0},
+                           {0.2, -0.21, 0.0}, {0.2, 0.21, 0.0}, {0.2, -0.21, 0.0}, {0.2, 0.21, 0.0}, {0.2, -0.21, 0.0},
+                           {0.0, 0.21, 0.0}};
+  for (const auto &t : seq) { RelativeFootPosition r = {t[0], t[1], t[2], 0.78, 0.02, 1, 0.0}; rel.push_back(r); }
+  std::deque<ZMPPosition> zmp; std::deque<COMState> com; std::deque<FootAbsolutePosition> left, right;
+  COMState start; double zstart[3] = {0, 0, 0};
+  FootAbsolutePosition il, ir;
+  std::memset(&il, 0, sizeof il); std::memset(&ir, 0, sizeof ir);
+  il.x = 0.00949035; il.y = 0.095; ir.x = 0.00949035; ir.y = -0.095;
+  gen.GetZMPDiscretization(zmp, com, rel, left, right, 0.0, start, zstart, il, ir);
+  FootConstraintsAsLinearSystem fcals(&spm);
+  std::deque<LinearConstraintInequality_t *> q;
+  // the step type of the samples is what ZMPDiscretization writes; GetZMPDiscretization does not return it, the polygon
+  // scan only needs ">= 10 means double support": mark the samples where both feet are on the ground
+  for (size_t i = 0; i < left.size(); ++i) left[i].stepType = (left[i].z == 0.0 && right[i].z == 0.0) ? 10 : 1;
+  if (fcals.BuildLinearConstraintInequalities(left, right, q, 0.04, 0.04) != 0) return 3;
+  FILE *f = fopen(out, "wb");
+  if (!f) return 4;
+  const int64_t n = (int64_t)com.size();
+  const int32_t hdr[4] = {gen.LastStatus(), gen.PeriodsDone(), (int32_t)q.size(), 0};
+  fwrite(&n, 8, 1, f); fwrite(hdr, 4, 4, f);
+  for (int64_t i = 0; i < n; ++i) { fwrite(com[i].x, 8, 3, f); fwrite(com[i].y, 8, 3, f); }
+  for (size_t k = 0; k < q.size(); ++k) { const int32_t r = (int32_t)q[k]->A.size1(); fwrite(&r, 4, 1, f); delete q[k]; }
+  fclose(f);
+  std::vector<CH_Point> pts = {{0.1, 0.0}, {0.0, 0.1}, {-0.1, 0.0}, {0.0, -0.1}, {0.0, 0.0}}, hull;
+  ComputeConvexHull ch;
+  ch.DoComputeConvexHull(pts, hull);
+  return hull.size() == 4 ? 0 : 5;
+}
+
 int main(int argc, char **argv)
 {
   try {
@@ -224,6 +272,7 @@ int main(int argc, char **argv)
     if (what == "herdt2010" && argc > 3) return test_herdt2010(argv[2], atoi(argv[3]), argc > 4 && std::string(argv[4]) == "emergency");
     if (what == "preview" && argc > 2) return test_preview(argv[2]);
     if (what == "pldp" && argc > 3) return test_pldp(argv[2], argv[3]);
+    if (what == "dimitrov" && argc > 2) return test_dimitrov(argv[2], argc > 3 && std::string(argv[3]) == "robust");
     std::cerr << "usage: host_api_test optcholesky | herdt2010 out.dat nticks | preview out.bin | pldp in.bin out.bin" << std::endl;
     return 64;
   } catch (const std::exception &e) {

@@ -101,3 +101,33 @@ def test_cpp_pldpsolver_hot_sequence_matches_oracle(exe, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     got = np.fromfile(fout).reshape(len(expect), 32)
     assert np.array_equal(got, np.array(expect))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robust", (False, True))
+def test_cpp_dimitrov_generator_matches_oracle(exe, tmp_path, robust):
+    """ZMPConstrainedQPFastFormulation::GetZMPDiscretization (command strings + RelativeFootPosition deque in, CoM deque
+    out) and FootConstraintsAsLinearSystem::BuildLinearConstraintInequalities through the class mirror, on the straight
+    walk of TestKajita2003: bitwise the oracle chain, in the reference-faithful mode (stops at period 17, where the
+    reference calls exit(0)) and in the robust mode (all 185 periods)."""
+    import dimitrov_oracle as do
+    import zmpdisc_oracle as zo
+    out = tmp_path / "dim.bin"
+    r = subprocess.run([exe, "dimitrov", str(out)] + (["robust"] if robust else []), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = out.read_bytes()
+    n = struct.unpack_from("<q", raw, 0)[0]
+    status, done, npoly, _ = struct.unpack_from("<4i", raw, 8)
+    com = np.frombuffer(raw, dtype=np.float64, count=6 * n, offset=24).reshape(n, 6)
+    rows = np.frombuffer(raw, dtype=np.int32, count=npoly, offset=24 + 48 * n)
+    o = zo.run(zo.default_params(), zo.profile_steps("StraightWalking"))
+    par = do.default_params()
+    par.cold_restart = par.merge_duplicate_rows = int(robust)
+    ref = do.run(o["left"], o["right"], o["types"][:, 1].copy(), par)
+    assert n == len(o["left"])
+    assert done == len(ref["periods"]) and status == (0 if ref["failed_at"] is None else 1)
+    assert (done, status) == ((185, 0) if robust else (18, 1))
+    good = done - status
+    assert com[:20 * good].tobytes() == ref["com"][:20 * good].tobytes()
+    P = do.fcals(o["left"], o["right"], o["types"][:, 1].copy())
+    assert npoly == len(P) and (rows == P["rows"]).all()
