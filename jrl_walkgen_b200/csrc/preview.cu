@@ -231,6 +231,8 @@ struct PreviewConsts {
 __constant__ PreviewConsts c_pc;
 __constant__ double c_F[WG_PREVIEW_MAX_NL + 8];
 
+constexpr int PV_MAX_CHUNKS = 16;
+
 struct wg_preview_plan {
   wg_ctx *ctx;
   int B;
@@ -240,6 +242,14 @@ struct wg_preview_plan {
   int *d_order;        // trajectories sorted by decreasing length (longest CTAs are scheduled first)
   // staging buffers for WG_MEM_HOST calls
   double *d_zmp, *d_state, *d_com, *d_zmpout;
+  // WG_MEM_HOST pipeline: chunk c = trajectories [chunk_first[c], chunk_first[c+1]) (contiguous sample ranges); its
+  // upload, kernel and downloads run on three streams so that H2D, compute and D2H of different chunks overlap
+  int n_chunks;
+  int chunk_first[PV_MAX_CHUNKS + 1];
+  int64_t chunk_samp[PV_MAX_CHUNKS + 1];   // offsets[chunk_first[c]]
+  int *d_order_chunked;                    // trajectories sorted by decreasing length inside each chunk
+  cudaStream_t up_stream, down_stream;
+  cudaEvent_t ev_up[PV_MAX_CHUNKS], ev_k[PV_MAX_CHUNKS], ev_done;
 };
 
 __device__ __forceinline__ int pad9(int e) { return e + (e >> 3); }
@@ -629,8 +639,38 @@ int wg_preview_plan_create(wg_ctx *ctx, int B, const int64_t *offsets, wg_previe
   pl->ctx = ctx; pl->B = B; pl->NL = NL;
   pl->total_samples = B > 0 ? offsets[B] : 0;
   pl->total_steps = total_steps;
+  // chunks of about equal sample counts, at least 8 trajectories each
+  pl->n_chunks = std::max(1, std::min(PV_MAX_CHUNKS, B / 8));
+  {
+    const int64_t total = B > 0 ? offsets[B] : 0;
+    int b = 0;
+    pl->chunk_first[0] = 0;
+    for (int c = 1; c < pl->n_chunks; ++c) {
+      const int64_t target = total * c / pl->n_chunks;
+      while (b < B && offsets[b] < target) ++b;
+      pl->chunk_first[c] = std::max(b, pl->chunk_first[c - 1]);
+    }
+    pl->chunk_first[pl->n_chunks] = B;
+    for (int c = 0; c <= pl->n_chunks; ++c) pl->chunk_samp[c] = B > 0 ? offsets[pl->chunk_first[c]] : 0;
+  }
+  std::vector<int> order_chunked(B);
+  for (int b = 0; b < B; ++b) order_chunked[b] = b;
+  for (int c = 0; c < pl->n_chunks; ++c)
+    std::stable_sort(order_chunked.begin() + pl->chunk_first[c], order_chunked.begin() + pl->chunk_first[c + 1], [&](int a, int b) {
+      return offsets[a + 1] - offsets[a] > offsets[b + 1] - offsets[b];
+    });
   cudaError_t e = cudaMalloc(&pl->d_offsets, sizeof(int64_t) * (B + 1));
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_order, sizeof(int) * std::max(1, B));
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_order_chunked, sizeof(int) * std::max(1, B));
+  if (e == cudaSuccess && B > 0)
+    e = cudaMemcpyAsync(pl->d_order_chunked, order_chunked.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->up_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->down_stream, cudaStreamNonBlocking);
+  for (int c = 0; c < PV_MAX_CHUNKS && e == cudaSuccess; ++c) {
+    e = cudaEventCreateWithFlags(&pl->ev_up[c], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_k[c], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_done, cudaEventDisableTiming);
   if (e == cudaSuccess && B > 0)
     e = cudaMemcpyAsync(pl->d_offsets, offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess && B > 0)
@@ -650,7 +690,11 @@ int wg_preview_plan_destroy(wg_preview_plan *pl)
   if (!pl) return WG_OK;
   wg_device_guard guard(pl->ctx->device);
   cudaStreamSynchronize(pl->ctx->stream);
-  cudaFree(pl->d_offsets); cudaFree(pl->d_order);
+  if (pl->up_stream) { cudaStreamSynchronize(pl->up_stream); cudaStreamDestroy(pl->up_stream); }
+  if (pl->down_stream) { cudaStreamSynchronize(pl->down_stream); cudaStreamDestroy(pl->down_stream); }
+  for (int c = 0; c < PV_MAX_CHUNKS; ++c) { if (pl->ev_up[c]) cudaEventDestroy(pl->ev_up[c]); if (pl->ev_k[c]) cudaEventDestroy(pl->ev_k[c]); }
+  if (pl->ev_done) cudaEventDestroy(pl->ev_done);
+  cudaFree(pl->d_offsets); cudaFree(pl->d_order); cudaFree(pl->d_order_chunked);
   cudaFree(pl->d_zmp); cudaFree(pl->d_state); cudaFree(pl->d_com); cudaFree(pl->d_zmpout);
   delete pl;
   return WG_OK;
@@ -704,17 +748,30 @@ int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double
     WG_CUDA(ctx, cudaMalloc(&pl->d_zmpout, sizeof(double) * 2 * std::max<size_t>(1, ns)));
     WG_CUDA(ctx, cudaMemsetAsync(pl->d_zmpout, 0, sizeof(double) * 2 * std::max<size_t>(1, ns), ctx->stream));
   }
-  WG_CUDA(ctx, cudaMemcpyAsync(pl->d_zmp, zmpref_xy, sizeof(double) * 2 * ns, cudaMemcpyHostToDevice, ctx->stream));
+  // ---- pipelined over chunks: upload (up_stream) -> kernel (ctx->stream) -> downloads (down_stream)
   WG_CUDA(ctx, cudaMemcpyAsync(pl->d_state, state, sizeof(double) * 8 * pl->B, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = preview_launch(ctx, pl, pl->d_zmp, pl->d_state, com_out ? pl->d_com : nullptr,
-                          zmp_out ? pl->d_zmpout : nullptr, simulation);
-  if (rc != WG_OK) return rc;
+  WG_CUDA(ctx, cudaEventRecord(pl->ev_done, ctx->stream));          // allocations / memsets / previous call are done
+  WG_CUDA(ctx, cudaStreamWaitEvent(pl->up_stream, pl->ev_done, 0));
+  for (int c = 0; c < pl->n_chunks; ++c) {
+    const int b0 = pl->chunk_first[c], b1 = pl->chunk_first[c + 1];
+    const size_t s0 = (size_t)pl->chunk_samp[c], cnt = (size_t)(pl->chunk_samp[c + 1] - pl->chunk_samp[c]);
+    if (b1 <= b0) continue;
+    if (cnt) WG_CUDA(ctx, cudaMemcpyAsync(pl->d_zmp + 2 * s0, zmpref_xy + 2 * s0, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, pl->up_stream));
+    WG_CUDA(ctx, cudaEventRecord(pl->ev_up[c], pl->up_stream));
+    WG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl->ev_up[c], 0));
+    int rc = wgi_preview_launch_range(ctx, pl, pl->d_order_chunked + b0, b1 - b0, pl->d_zmp, pl->d_state,
+                                      com_out ? pl->d_com : nullptr, zmp_out ? pl->d_zmpout : nullptr, simulation);
+    if (rc != WG_OK) return rc;
+    WG_CUDA(ctx, cudaEventRecord(pl->ev_k[c], ctx->stream));
+    WG_CUDA(ctx, cudaStreamWaitEvent(pl->down_stream, pl->ev_k[c], 0));
+    if (com_out && cnt)
+      WG_CUDA(ctx, cudaMemcpyAsync(com_out + 6 * s0, pl->d_com + 6 * s0, sizeof(double) * 6 * cnt, cudaMemcpyDeviceToHost, pl->down_stream));
+    if (zmp_out && cnt)
+      WG_CUDA(ctx, cudaMemcpyAsync(zmp_out + 2 * s0, pl->d_zmpout + 2 * s0, sizeof(double) * 2 * cnt, cudaMemcpyDeviceToHost, pl->down_stream));
+  }
   WG_CUDA(ctx, cudaMemcpyAsync(state, pl->d_state, sizeof(double) * 8 * pl->B, cudaMemcpyDeviceToHost, ctx->stream));
-  if (com_out)
-    WG_CUDA(ctx, cudaMemcpyAsync(com_out, pl->d_com, sizeof(double) * 6 * ns, cudaMemcpyDeviceToHost, ctx->stream));
-  if (zmp_out)
-    WG_CUDA(ctx, cudaMemcpyAsync(zmp_out, pl->d_zmpout, sizeof(double) * 2 * ns, cudaMemcpyDeviceToHost, ctx->stream));
   WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  WG_CUDA(ctx, cudaStreamSynchronize(pl->down_stream));
   return WG_OK;
 }
 
