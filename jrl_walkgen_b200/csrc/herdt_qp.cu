@@ -1,6 +1,7 @@
 // herdt_qp.cu - batched Herdt2010 velocity-referenced QP for sm_100a: host constants, kernels, C ABI.
 // Device algorithm: herdt_qp.cuh.
 #include "herdt_qp.cuh"
+#include <algorithm>
 #include <vector>
 #include <cmath>
 
@@ -17,6 +18,9 @@ struct HerdtState {
   wg_herdt_qp_input *d_in = nullptr;
   wg_herdt_qp_output *d_out = nullptr;
   int cap = 0;
+  // WG_MEM_HOST pipeline: upload / download streams and per-chunk events
+  cudaStream_t up = nullptr, down = nullptr;
+  cudaEvent_t ev_up[8] = {nullptr}, ev_k[8] = {nullptr}, ev0 = nullptr;
 };
 
 HerdtState *state_of(wg_ctx *ctx)
@@ -162,6 +166,10 @@ void wg_herdt_release(wg_ctx *ctx)
   if (!ctx->herdt) return;
   HerdtState *st = static_cast<HerdtState *>(ctx->herdt);
   cudaFree(st->d_consts); cudaFree(st->d_in); cudaFree(st->d_out);
+  if (st->up) cudaStreamDestroy(st->up);
+  if (st->down) cudaStreamDestroy(st->down);
+  for (int c = 0; c < 8; ++c) { if (st->ev_up[c]) cudaEventDestroy(st->ev_up[c]); if (st->ev_k[c]) cudaEventDestroy(st->ev_k[c]); }
+  if (st->ev0) cudaEventDestroy(st->ev0);
   delete st;
   ctx->herdt = nullptr;
 }
@@ -248,11 +256,34 @@ int wg_herdt_qp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_herdt_qp_input
     WG_CUDA(ctx, cudaMalloc(&st->d_out, sizeof(wg_herdt_qp_output) * (size_t)B));
     st->cap = B;
   }
-  WG_CUDA(ctx, cudaMemcpyAsync(st->d_in, in, sizeof(wg_herdt_qp_input) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = herdt_launch(ctx, st, B, st->d_in, st->d_out);
-  if (rc != WG_OK) return rc;
-  WG_CUDA(ctx, cudaMemcpyAsync(out, st->d_out, sizeof(wg_herdt_qp_output) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+  // two or three large chunks (small launches waste the tail of the persistent grid: 8 chunks of 2048 measured 18 % SLOWER than
+  // the unpipelined call): the upload of chunk c+1 and the download of chunk c-1 overlap the kernel of chunk c
+  if (!st->up) {
+    WG_CUDA(ctx, cudaStreamCreateWithFlags(&st->up, cudaStreamNonBlocking));
+    WG_CUDA(ctx, cudaStreamCreateWithFlags(&st->down, cudaStreamNonBlocking));
+    for (int c = 0; c < 8; ++c) {
+      WG_CUDA(ctx, cudaEventCreateWithFlags(&st->ev_up[c], cudaEventDisableTiming));
+      WG_CUDA(ctx, cudaEventCreateWithFlags(&st->ev_k[c], cudaEventDisableTiming));
+    }
+    WG_CUDA(ctx, cudaEventCreateWithFlags(&st->ev0, cudaEventDisableTiming));
+  }
+  static const int want = getenv("WG_HERDT_CHUNKS") ? atoi(getenv("WG_HERDT_CHUNKS")) : 2;
+  const int nch = std::max(1, std::min(std::min(8, want), B / 4096));
+  WG_CUDA(ctx, cudaEventRecord(st->ev0, ctx->stream));
+  WG_CUDA(ctx, cudaStreamWaitEvent(st->up, st->ev0, 0));
+  for (int c = 0; c < nch; ++c) {
+    const size_t b0 = (size_t)B * c / nch, b1 = (size_t)B * (c + 1) / nch;
+    WG_CUDA(ctx, cudaMemcpyAsync(st->d_in + b0, in + b0, sizeof(wg_herdt_qp_input) * (b1 - b0), cudaMemcpyHostToDevice, st->up));
+    WG_CUDA(ctx, cudaEventRecord(st->ev_up[c], st->up));
+    WG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->ev_up[c], 0));
+    int rc = herdt_launch(ctx, st, (int)(b1 - b0), st->d_in + b0, st->d_out + b0);
+    if (rc != WG_OK) return rc;
+    WG_CUDA(ctx, cudaEventRecord(st->ev_k[c], ctx->stream));
+    WG_CUDA(ctx, cudaStreamWaitEvent(st->down, st->ev_k[c], 0));
+    WG_CUDA(ctx, cudaMemcpyAsync(out + b0, st->d_out + b0, sizeof(wg_herdt_qp_output) * (b1 - b0), cudaMemcpyDeviceToHost, st->down));
+  }
   WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  WG_CUDA(ctx, cudaStreamSynchronize(st->down));
   return WG_OK;
 }
 
