@@ -307,9 +307,11 @@ struct DimWarp {
   double zref[PLDP_U];
   double xk[6];
   int prev_active[PLDP_U];
-  int rowi[DM_MAXM];
+  unsigned char rowi[DM_MAXM];
 };
 
+// 4 CTAs/SM (128 registers): at 6 CTAs/SM (80 registers, spills) 4096 walks ran 52 % SLOWER - a walk is a serial chain of
+// some hundred periods, a batch of a few thousand walks is bound by its longest walks, not by the number of resident warps
 __global__ void __launch_bounds__(DM_WARPS * 32, 4)
 dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__restrict__ Cp,
                 const int64_t *__restrict__ samp_off, const double *__restrict__ clock,

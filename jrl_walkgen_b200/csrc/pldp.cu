@@ -33,7 +33,7 @@ struct PldpHost {
 };
 
 // One instance per warp.
-__global__ void __launch_bounds__(PLDP_WARPS * 32)
+__global__ void __launch_bounds__(PLDP_WARPS * 32, 8)
 pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__ D, const int *__restrict__ mvec,
             const double *__restrict__ DPu, long long dpu_stride, const double *__restrict__ DPx, long long dpx_stride,
             const double *__restrict__ ZMPRef, const double *__restrict__ XkYk, double *__restrict__ X,
@@ -298,6 +298,12 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
   int a_cap = (int)((pb->dpu_stride + 1) & ~1LL);
   size_t smem = sizeof(double) * (size_t)a_cap * PLDP_WARPS;
   if (smem > 200 * 1024) { a_cap = 0; smem = 0; }
+  // Measured (16 384 cold-started problems, m ~ 68): constraint matrix staged in shared memory, 8 warps/SM: 4.57 ms; read
+  // from L2 (the batch's matrices, 290 MB, stream through once per iteration of their own warp), 32 warps/SM at 64
+  // registers: 3.53 ms.  The solver is a chain of dependent FP64 operations: resident warps hide more than shared memory
+  // saves.  WG_PLDP_STAGE=1 restores the staged variant.
+  static const int stage = getenv("WG_PLDP_STAGE") ? atoi(getenv("WG_PLDP_STAGE")) : 0;
+  if (!stage) { a_cap = 0; smem = 0; }
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     WG_CUDA(ctx, cudaFuncSetAttribute(pldp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

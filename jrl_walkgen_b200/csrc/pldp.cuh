@@ -32,23 +32,30 @@ __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(
 // ---- the constraint matrix (m+1) x 32 as the solver sees it: M.row(r).at(c) ------------------------------------
 // DenseMat: column-major array with leading dimension ld, as the reference receives it (global or shared memory).
 struct DenseMat {
+  static constexpr int kHalfUnroll = 2;   // the two axis halves are one flat column loop
   const double *A;
   int ld;
   struct Row {
     const double *p; int ld;
     __device__ __forceinline__ double at(int c) const { return p[(size_t)c * ld]; }
+    // the same element addressed as (axis half h, column kk of the half); cf = coef(h)
+    __device__ __forceinline__ double coef(int) const { return 0.0; }
+    __device__ __forceinline__ double at_h(double, int h, int kk) const { return p[(size_t)(h * PLDP_N + kk) * ld]; }
   };
   __device__ __forceinline__ Row row(int r) const { return Row{A + r, ld}; }
 };
 // RankMat: the matrix BuildConstraintMatrices writes (ZMPConstrainedQPFastFormulation.cpp:885-905), never materialised:
 // element (r, k + 16 ax) = a[ax][r] * Pu[k * 16 + i_r], the same single IEEE multiplication the reference stores.
 struct RankMat {
+  static constexpr int kHalfUnroll = 1;   // keep the loop over the axis halves rolled (code size)
   const double *a0, *a1;   // [m]   A_r(0), A_r(1)
-  const int *ri;           // [m]   previewed sample of row r
+  const unsigned char *ri; // [m]   previewed sample of row r
   const double *Pu;        // [16][16] m_Pu
   struct Row {
     double a0, a1; const double *pu;
     __device__ __forceinline__ double at(int c) const { return mul(c < PLDP_N ? a0 : a1, pu[(c & (PLDP_N - 1)) * PLDP_N]); }
+    __device__ __forceinline__ double coef(int h) const { return h ? a1 : a0; }
+    __device__ __forceinline__ double at_h(double cf, int, int kk) const { return mul(cf, pu[kk * PLDP_N]); }
   };
   __device__ __forceinline__ Row row(int r) const { return Row{a0[r], a1[r], Pu + ri[r]}; }
 };
@@ -62,8 +69,12 @@ __device__ __noinline__ void chol_add_row(double *L, const int *act, int i, cons
   double r = 0.0;
   {
     const typename Mat::Row ri = M.row(act[i]), rj = M.row(act[lane <= i ? lane : i]);
+#pragma unroll(Mat::kHalfUnroll)
+    for (int h = 0; h < 2; ++h) {
+      const double ci = ri.coef(h), cj = rj.coef(h);
 #pragma unroll 4
-    for (int k = 0; k < PLDP_U; ++k) r = add(r, mul(ri.at(k), rj.at(k)));
+      for (int kk = 0; kk < PLDP_N; ++kk) r = add(r, mul(ri.at_h(ci, h, kk), rj.at_h(cj, h, kk)));
+    }
   }
   double lij = 0.0;
 #pragma unroll 1
@@ -152,8 +163,12 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
     double v1 = 0.0;
     if (k > 0) {
       const typename Mat::Row row = M.row(w.active[lane < k ? lane : 0]);
+#pragma unroll(Mat::kHalfUnroll)
+      for (int h = 0; h < 2; ++h) {
+        const double cf = row.coef(h);
 #pragma unroll 4
-      for (int j = 0; j < PLDP_U; ++j) v1 = add(v1, mul(row.at(j), w.vec[0][j]));
+        for (int kk = 0; kk < PLDP_N; ++kk) v1 = add(v1, mul(row.at_h(cf, h, kk), w.vec[0][h * PLDP_N + kk]));
+      }
     }
     // forward substitution L y = v1 (:342-365): y[i] += -L(i,k) y[k] in k order, then / L(i,i) (skipped when 0)
     double y = v1;
@@ -201,12 +216,18 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
         typename Mat::Row rows[SLABS];
 #pragma unroll
         for (int s = 0; s < SLABS; ++s) rows[s] = M.row((lane + 32 * s) < m ? lane + 32 * s : 0);
-#pragma unroll 2
-        for (int j = 0; j < PLDP_U; ++j) {
-          const double dj = w.vec[0][j];
+#pragma unroll(Mat::kHalfUnroll)
+        for (int h = 0; h < 2; ++h) {
+          double cf[SLABS];
 #pragma unroll
-          for (int s = 0; s < SLABS; ++s)
-            if (s < ns) t1[s] = add(t1[s], mul(rows[s].at(j), dj));
+          for (int s = 0; s < SLABS; ++s) cf[s] = rows[s].coef(h);
+#pragma unroll 2
+          for (int kk = 0; kk < PLDP_N; ++kk) {
+            const double dj = w.vec[0][h * PLDP_N + kk];
+#pragma unroll
+            for (int s = 0; s < SLABS; ++s)
+              if (s < ns) t1[s] = add(t1[s], mul(rows[s].at_h(cf[s], h, kk), dj));
+          }
         }
         bool want[SLABS];
         bool any = false;
@@ -217,12 +238,18 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
           double t2[SLABS];
 #pragma unroll
           for (int s = 0; s < SLABS; ++s) t2[s] = -bv[(lane + 32 * s) < m ? lane + 32 * s : 0];
-#pragma unroll 2
-          for (int j = 0; j < PLDP_U; ++j) {
-            const double vj = w.vec[1][j];
+#pragma unroll(Mat::kHalfUnroll)
+          for (int h = 0; h < 2; ++h) {
+            double cf[SLABS];
 #pragma unroll
-            for (int s = 0; s < SLABS; ++s)
-              if (s < ns) t2[s] = add(t2[s], -mul(rows[s].at(j), vj));
+            for (int s = 0; s < SLABS; ++s) cf[s] = rows[s].coef(h);
+#pragma unroll 2
+            for (int kk = 0; kk < PLDP_N; ++kk) {
+              const double vj = w.vec[1][h * PLDP_N + kk];
+#pragma unroll
+              for (int s = 0; s < SLABS; ++s)
+                if (s < ns) t2[s] = add(t2[s], -mul(rows[s].at_h(cf[s], h, kk), vj));
+            }
           }
 #pragma unroll
           for (int s = 0; s < SLABS; ++s) {
