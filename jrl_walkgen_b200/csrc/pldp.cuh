@@ -89,6 +89,38 @@ __device__ __noinline__ void chol_add_row(double *L, const int *act, int i, cons
   __syncwarp();
 }
 
+// Rows 0..k-1 of L at once (the hot start re-activates the kept constraints before the first iteration: the reference
+// calls AddActiveConstraint k times, PLDPSolver.cpp:763-778).  Lane i owns row i; column by column, every entry is the same
+// expression in the same order as in chol_add_row - L(i,j) = (M(i,j) - sum_{t<j} L(i,t) L(j,t)) / L(j,j) with t ascending -
+// so the factor is bit-identical, but the k(k+1)/2 serial divisions become k steps of one parallel division.
+template <class Mat>
+__device__ __noinline__ void chol_build(double *L, const int *act, int k, const Mat &M, int lane)
+{
+  const bool own = lane < k;
+  const typename Mat::Row ri = M.row(act[own ? lane : 0]);
+#pragma unroll 1
+  for (int j = 0; j < k; ++j) {
+    const typename Mat::Row rj = M.row(act[j]);
+    double r = 0.0;
+#pragma unroll(Mat::kHalfUnroll)
+    for (int h = 0; h < 2; ++h) {
+      const double ci = ri.coef(h), cj = rj.coef(h);
+#pragma unroll 4
+      for (int kk = 0; kk < PLDP_N; ++kk) r = add(r, mul(ri.at_h(ci, h, kk), rj.at_h(cj, h, kk)));
+    }
+    if (own && lane >= j) {
+      const double *Li = L + tri(lane), *Lj = L + tri(j);
+#pragma unroll 2
+      for (int t = 0; t < j; ++t) r = add(r, -mul(Li[t], Lj[t]));
+    }
+    double d = 0.0;
+    if (lane == j) { d = sqrt(r); L[tri(j) + j] = d; }
+    d = bcast(d, j);
+    if (own && lane > j) L[tri(lane) + j] = r / d;
+    __syncwarp();
+  }
+}
+
 // PLDPSolver::SolveProblem for the problem (M: m x 32 constraint matrix, bv, Dl = D[lane], zr, xk) by the calling warp.
 // use_prev: start from the shifted previous ZMP solution prev_zmp[32] (hot start, not the first call); n_prev /
 // prev_active / nr: constraints kept from the previous solve and NumberOfRemovedConstraints.
@@ -135,11 +167,11 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
       const int idx = prev_active[i] - nr;
       if (idx >= 0 && idx < m) {
         if (lane == 0) w.active[k] = idx;
-        __syncwarp();
-        chol_add_row(w.L, w.active, k, M, lane);
         ++k;
       }
     }
+    __syncwarp();
+    if (k > 0) chol_build(w.L, w.active, k, M, lane);
   }
   // activity flags of the rows this lane owns (rows lane, lane+32, lane+64, lane+96)
   unsigned mine = 0;
