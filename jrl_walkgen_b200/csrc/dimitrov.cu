@@ -59,8 +59,10 @@ struct DimHost {
   // clock table and scratch (grow-only)
   double *d_time = nullptr; size_t time_cap = 0;
   std::vector<double> time_h;
-  void *buf[12] = {nullptr};
-  size_t cap[12] = {0};
+  void *buf[14] = {nullptr};
+  size_t cap[14] = {0};
+  // the longest-first walk order of the last plan, kept on the device (slot 12)
+  const void *order_plan = nullptr; int order_B = 0; int64_t order_total = -1;
   std::map<int64_t, int64_t> period_cache;
 };
 
@@ -76,6 +78,7 @@ int dm_ensure(wg_ctx *ctx, DimHost *p, int slot, size_t bytes)
   WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   cudaFree(p->buf[slot]);
   p->buf[slot] = nullptr; p->cap[slot] = 0;
+  if (slot == 12) p->order_plan = nullptr;
   WG_CUDA(ctx, cudaMalloc(&p->buf[slot], bytes ? bytes : 8));
   p->cap[slot] = bytes;
   return WG_OK;
@@ -862,21 +865,22 @@ int wg_dimitrov_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *co
   if ((rc = dm_ensure(ctx, H, 11, 64)) != WG_OK) return rc;
   int *d_next = static_cast<int *>(H->buf[11]);
   WG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(int), ctx->stream));
-  // longest-processing-time-first order (the sample count is a faithful proxy of the period count)
-  if ((rc = dm_ensure(ctx, H, 2, sizeof(int) * nb)) != WG_OK) return rc;
-  {
+  // longest-processing-time-first order (the sample count is a faithful proxy of the period count); uploaded once per plan
+  if ((rc = dm_ensure(ctx, H, 12, sizeof(int) * nb)) != WG_OK) return rc;
+  if (H->order_plan != plan || H->order_B != B || H->order_total != (int64_t)ns) {
     std::vector<int> order(B);
     for (int b = 0; b < B; ++b) order[b] = b;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
       return V.samp_off[a + 1] - V.samp_off[a] > V.samp_off[b + 1] - V.samp_off[b];
     });
-    WG_CUDA(ctx, cudaMemcpyAsync(H->buf[2], order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    WG_CUDA(ctx, cudaMemcpyAsync(H->buf[12], order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
     WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `order` is a pageable temporary
+    H->order_plan = plan; H->order_B = B; H->order_total = (int64_t)ns;
   }
   wg_prof_start(ctx, WG_K_DIMITROV);
   dimitrov_kernel<<<grid, DM_WARPS * 32, 0, ctx->stream>>>(B, H->d, dC, V.d_samp_off, H->d_time, d_lo, d_lci, d_nlci,
                                                               V.d_zd_status, d_com, zmp_out ? d_zmp : nullptr, d_po, d_per,
-                                                              d_st, d_dn, d_next, static_cast<const int *>(H->buf[2]));
+                                                              d_st, d_dn, d_next, static_cast<const int *>(H->buf[12]));
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   if (host) {

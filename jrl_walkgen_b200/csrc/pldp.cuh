@@ -37,10 +37,10 @@ struct DenseMat {
   int ld;
   struct Row {
     const double *p; int ld;
-    __device__ __forceinline__ double at(int c) const { return p[(size_t)c * ld]; }
+    __device__ __forceinline__ double at(int c) const { return p[c * ld]; }   // 32-bit index: (m+1) * 32 < 2^31
     // the same element addressed as (axis half h, column kk of the half); cf = coef(h)
     __device__ __forceinline__ double coef(int) const { return 0.0; }
-    __device__ __forceinline__ double at_h(double, int h, int kk) const { return p[(size_t)(h * PLDP_N + kk) * ld]; }
+    __device__ __forceinline__ double at_h(double, int h, int kk) const { return p[(h * PLDP_N + kk) * ld]; }
   };
   __device__ __forceinline__ Row row(int r) const { return Row{A + r, ld}; }
 };
