@@ -126,8 +126,8 @@ struct Out {
 __device__ __forceinline__ void put_foot(wg_foot_sample *dst, int64_t g, const Foot &f)
 {
   if (!dst) return;
-  double *q = reinterpret_cast<double *>(dst + g);
-  q[0] = f.x; q[1] = f.y; q[2] = f.z; q[3] = f.theta; q[4] = f.omega; q[5] = f.omega2;
+  double2 *q = reinterpret_cast<double2 *>(dst + g);      // 48-byte records, 16-byte aligned: three 128-bit stores
+  q[0] = make_double2(f.x, f.y); q[1] = make_double2(f.z, f.theta); q[2] = make_double2(f.omega, f.omega2);
 }
 
 // Filter the head of a segment (samples 0 .. min(len, ZD_HEAD) - 1) serially: they read filtered history.
@@ -174,12 +174,14 @@ __device__ __forceinline__ double2 filter_body(const ZdConsts &K, const double2 
   return make_double2(a0, a1);
 }
 
-__global__ void __launch_bounds__(ZD_THREADS)
+__global__ void __launch_bounds__(ZD_THREADS, 4)
 zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ step_off,
                const wg_rel_step *__restrict__ steps, const double *__restrict__ init_feet,
-               const int64_t *__restrict__ samp_off, Out out, int *__restrict__ status)
+               const int64_t *__restrict__ samp_off, Out out, int *__restrict__ status,
+               const int *__restrict__ order, int *__restrict__ next_walk)
 {
   extern __shared__ double2 zd_smem[];
+  __shared__ Poly s_poly[ZD_WARPS][7];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double2 *u = zd_smem + (size_t)warp * (K.cap + 2 * ZD_HIST + ZD_HEAD);
   double2 *histA = u + K.cap, *histB = histA + ZD_HIST, *head = histB + ZD_HIST;
@@ -187,7 +189,12 @@ zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ ste
   const double T = P.sampling_period;
   const unsigned FULL = 0xffffffffu;
 
-  for (int b = b0 + blockIdx.x * ZD_WARPS + warp; b < b1; b += gridDim.x * ZD_WARPS) {
+  // walks differ in length (8-20 steps, arcs): every warp fetches its next walk from a counter, longest walks first
+  for (;;) {
+    int b = 0;
+    if (lane == 0) { b = atomicAdd(next_walk, 1); b = (b0 + b < b1) ? order[b0 + b] : -1; }
+    b = __shfl_sync(FULL, b, 0);
+    if (b < 0) break;
     const int64_t s0 = step_off[b];
     const int ns = (int)(step_off[b + 1] - s0);
     const int64_t o = samp_off[b];
@@ -313,9 +320,17 @@ zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ ste
       const double vrel0 = vd0 + vpre0, vrel1 = vd1 + vpre1;
       const double mod = lTsingle * P.modulation;
       const double end_lift_param = (lTsingle - mod) * 0.5;
-      const Poly PX = poly5(mod, vrel0), PY = poly5(mod, vrel1), PZ = poly4(P.t_single, P.step_height);
-      const Poly PT = poly3(mod, rel_theta), PO = poly3(end_lift_param, P.omega), PO2 = poly3(mod, 2 * P.omega);
-      const Poly PZT = poly3(lTsingle, rel_zmp_theta);
+      // the seven boundary-value polynomials of the step live in shared memory (every lane evaluates them at its own
+      // time: broadcast reads) instead of 42 registers per lane
+      Poly *pp = s_poly[warp];
+      __syncwarp();
+      if (lane == 0) {
+        pp[0] = poly5(mod, vrel0); pp[1] = poly5(mod, vrel1); pp[2] = poly4(P.t_single, P.step_height);
+        pp[3] = poly3(mod, rel_theta); pp[4] = poly3(end_lift_param, P.omega); pp[5] = poly3(mod, 2 * P.omega);
+        pp[6] = poly3(lTsingle, rel_zmp_theta);
+      }
+      __syncwarp();
+      const Poly &PX = pp[0], &PY = pp[1], &PZ = pp[2], &PT = pp[3], &PO = pp[4], &PO2 = pp[5], &PZT = pp[6];
       const double end_lift = (P.t_single - mod) * 0.5, start_land = end_lift + mod;
       Foot dsL = L, dsR = R;        // feet during double support: last sample with z = 0
       dsL.z = 0.0;
@@ -472,6 +487,8 @@ struct wg_kajita_plan {
   // chunks of consecutive walks for the pipelined host path
   std::vector<int> chunk_first;    // chunk c = walks [chunk_first[c], chunk_first[c+1])
   int *d_order;                    // walks sorted by decreasing length inside each chunk
+  int *d_order_all;                // walks sorted by decreasing length over the whole batch (single-launch path)
+  int *d_next;                     // work counter of the front-end kernel
   // device staging for WG_MEM_HOST calls and scratch for the ZMP reference
   double *d_zmpref, *d_state, *d_com, *d_zmpout, *d_ztheta;
   wg_foot_sample *d_left, *d_right;
@@ -621,7 +638,7 @@ int wg_kajita_plan_destroy(wg_kajita_plan *pl)
   if (pl->copy_stream) cudaStreamSynchronize(pl->copy_stream);
   if (pl->pv) wg_preview_plan_destroy(pl->pv);
   cudaFree(pl->d_step_off); cudaFree(pl->d_samp_off); cudaFree(pl->d_steps); cudaFree(pl->d_init_feet);
-  cudaFree(pl->d_status); cudaFree(pl->d_order);
+  cudaFree(pl->d_status); cudaFree(pl->d_order); cudaFree(pl->d_order_all); cudaFree(pl->d_next);
   cudaFree(pl->d_zmpref); cudaFree(pl->d_state); cudaFree(pl->d_com); cudaFree(pl->d_zmpout); cudaFree(pl->d_ztheta);
   cudaFree(pl->d_left); cudaFree(pl->d_right); cudaFree(pl->d_types);
   for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
@@ -676,7 +693,15 @@ int wg_kajita_plan_create(wg_ctx *ctx, const wg_zmpdisc_params *p, int B, const 
     std::stable_sort(order.begin() + pl->chunk_first[c], order.begin() + pl->chunk_first[c + 1], [&](int a, int b) {
       return pl->samp_off[a + 1] - pl->samp_off[a] > pl->samp_off[b + 1] - pl->samp_off[b];
     });
+  std::vector<int> order_all(B);
+  for (int b = 0; b < B; ++b) order_all[b] = b;
+  std::stable_sort(order_all.begin(), order_all.end(), [&](int a, int b) {
+    return pl->samp_off[a + 1] - pl->samp_off[a] > pl->samp_off[b + 1] - pl->samp_off[b];
+  });
   cudaError_t e = cudaMalloc(&pl->d_step_off, sizeof(int64_t) * (B + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_order_all, sizeof(int) * B);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_next, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_order_all, order_all.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_samp_off, sizeof(int64_t) * (B + 1));
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_steps, sizeof(wg_rel_step) * pl->total_steps_in);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_init_feet, sizeof(double) * 6 * B);
@@ -736,10 +761,14 @@ static int zd_launch(wg_ctx *ctx, wg_kajita_plan *pl, int b0, int b1, const Out 
     attr = smem;
   }
   const int walks = b1 - b0;
-  const int grid = std::max(1, std::min((walks + ZD_WARPS - 1) / ZD_WARPS, ctx->sm_count * 16));
+  const int grid = std::max(1, std::min((walks + ZD_WARPS - 1) / ZD_WARPS, ctx->sm_count * 4));
+  // the whole batch uses the global longest-first order, a chunk [b0, b1) the per-chunk one (both are permutations of
+  // their range stored at positions b0 .. b1-1)
+  const int *order = (b0 == 0 && b1 == pl->B) ? pl->d_order_all : pl->d_order;
+  WG_CUDA(ctx, cudaMemsetAsync(pl->d_next, 0, sizeof(int), ctx->stream));
   wg_prof_start(ctx, WG_K_ZMPDISC);
   zmpdisc_kernel<<<grid, ZD_THREADS, smem, ctx->stream>>>(pl->K, b0, b1, pl->d_step_off, pl->d_steps, pl->d_init_feet,
-                                                         pl->d_samp_off, o, pl->d_status);
+                                                         pl->d_samp_off, o, pl->d_status, order, pl->d_next);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;
