@@ -296,11 +296,11 @@ __device__ inline void write_tick(wg_herdt_tick *row, const double *com11, const
   row->right = R;
 }
 
-__global__ void __launch_bounds__(MPC_WARPS * 32)
+__global__ void __launch_bounds__(MPC_WARPS * 32, 3)
 herdt_mpc_kernel(int B, int nsteps, const herdt::Consts *__restrict__ Cp, const wg_herdt_mpc_params *__restrict__ Mp,
                  wg_herdt_mpc_state *__restrict__ states, const double *__restrict__ vel_ref,
                  wg_herdt_tick *__restrict__ ticks, wg_herdt_mpc_step *__restrict__ steps,
-                 wg_herdt_qp_input *__restrict__ qp_in)
+                 wg_herdt_qp_input *__restrict__ qp_in, int *__restrict__ next_instance)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   herdt::Work *works = reinterpret_cast<herdt::Work *>(smem_raw);
@@ -314,7 +314,12 @@ herdt_mpc_kernel(int B, int nsteps, const herdt::Consts *__restrict__ Cp, const 
   const double T = C.P.T;
   constexpr int STW = (int)(sizeof(wg_herdt_mpc_state) / 8);
 
-  for (int b = blockIdx.x * MPC_WARPS + warp; b < B; b += gridDim.x * MPC_WARPS) {
+  // every warp takes its next instance from a work counter (the QP of an instance costs 10-42 active-set iterations)
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(next_instance, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= B) break;
     {
       const double *src = reinterpret_cast<const double *>(states + b);
       double *dst = reinterpret_cast<double *>(&st);
@@ -543,6 +548,7 @@ struct MpcState {
   // staging for WG_MEM_HOST calls
   void *d_states = nullptr, *d_ref = nullptr, *d_ticks = nullptr, *d_steps = nullptr, *d_qpin = nullptr;
   size_t cap_states = 0, cap_ref = 0, cap_ticks = 0, cap_steps = 0, cap_qpin = 0;
+  int *d_next = nullptr;   // work counter of herdt_mpc_kernel
 };
 
 int ensure(wg_ctx *ctx, void **p, size_t *cap, size_t bytes)
@@ -566,7 +572,7 @@ void wg_herdt_mpc_release(wg_ctx *ctx)
   if (!ctx->herdt_mpc) return;
   MpcState *m = static_cast<MpcState *>(ctx->herdt_mpc);
   cudaFree(m->d_params); cudaFree(m->d_states); cudaFree(m->d_ref); cudaFree(m->d_ticks); cudaFree(m->d_steps);
-  cudaFree(m->d_qpin);
+  cudaFree(m->d_qpin); cudaFree(m->d_next);
   delete m;
   ctx->herdt_mpc = nullptr;
 }
@@ -663,9 +669,11 @@ static int mpc_launch(wg_ctx *ctx, MpcState *m, int B, int nsteps, wg_herdt_mpc_
   int blocks = (B + MPC_WARPS - 1) / MPC_WARPS;
   const int cap = ctx->sm_count * per_sm;
   if (blocks > cap) blocks = cap;
+  if (!m->d_next) WG_CUDA(ctx, cudaMalloc(&m->d_next, sizeof(int)));
+  WG_CUDA(ctx, cudaMemsetAsync(m->d_next, 0, sizeof(int), ctx->stream));
   wg_prof_start(ctx, WG_K_HERDT_MPC);
   herdt_mpc_kernel<<<blocks, MPC_WARPS * 32, smem, ctx->stream>>>(B, nsteps, wg_herdt_device_consts(ctx), m->d_params,
-                                                                  states, vel_ref, ticks, steps, qp_in);
+                                                                  states, vel_ref, ticks, steps, qp_in, m->d_next);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;

@@ -18,6 +18,7 @@ struct HerdtState {
   wg_herdt_qp_input *d_in = nullptr;
   wg_herdt_qp_output *d_out = nullptr;
   int cap = 0;
+  int *d_next = nullptr;          // work counter of herdt_qp_kernel
   // WG_MEM_HOST pipeline: upload / download streams and per-chunk events
   cudaStream_t up = nullptr, down = nullptr;
   cudaEvent_t ev_up[8] = {nullptr}, ev_k[8] = {nullptr}, ev0 = nullptr;
@@ -110,16 +111,21 @@ void compute_consts(const wg_herdt_params &P, Consts &C)
 
 constexpr int QP_WARPS = 4;  // warps (instances) per block
 
-__global__ void __launch_bounds__(QP_WARPS * 32)
+__global__ void __launch_bounds__(QP_WARPS * 32, 3)
 herdt_qp_kernel(int B, const Consts *__restrict__ Cp, const wg_herdt_qp_input *__restrict__ in,
-                wg_herdt_qp_output *__restrict__ out)
+                wg_herdt_qp_output *__restrict__ out, int *__restrict__ next_instance)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   herdt::Work *works = reinterpret_cast<herdt::Work *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Consts &C = *Cp;
   herdt::Work &s = works[warp];
-  for (int b = blockIdx.x * QP_WARPS + warp; b < B; b += gridDim.x * QP_WARPS) {
+  // solve times differ (10-42 active-set iterations): every warp takes its next instance from a work counter
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(next_instance, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= B) break;
     // stage the 784-byte input record
     {
       const double *src = reinterpret_cast<const double *>(in + b);
@@ -165,7 +171,7 @@ void wg_herdt_release(wg_ctx *ctx)
 {
   if (!ctx->herdt) return;
   HerdtState *st = static_cast<HerdtState *>(ctx->herdt);
-  cudaFree(st->d_consts); cudaFree(st->d_in); cudaFree(st->d_out);
+  cudaFree(st->d_consts); cudaFree(st->d_in); cudaFree(st->d_out); cudaFree(st->d_next);
   if (st->up) cudaStreamDestroy(st->up);
   if (st->down) cudaStreamDestroy(st->down);
   for (int c = 0; c < 8; ++c) { if (st->ev_up[c]) cudaEventDestroy(st->ev_up[c]); if (st->ev_k[c]) cudaEventDestroy(st->ev_k[c]); }
@@ -232,8 +238,10 @@ static int herdt_launch(wg_ctx *ctx, HerdtState *st, int B, const wg_herdt_qp_in
   int blocks = (B + QP_WARPS - 1) / QP_WARPS;
   const int cap = ctx->sm_count * per_sm;
   if (blocks > cap) blocks = cap;   // persistent: a multiple of the SM count, grid-stride over instances
+  if (!st->d_next) WG_CUDA(ctx, cudaMalloc(&st->d_next, sizeof(int)));
+  WG_CUDA(ctx, cudaMemsetAsync(st->d_next, 0, sizeof(int), ctx->stream));
   wg_prof_start(ctx, WG_K_HERDT_QP);
-  herdt_qp_kernel<<<blocks, QP_WARPS * 32, smem, ctx->stream>>>(B, st->d_consts, d_in, d_out);
+  herdt_qp_kernel<<<blocks, QP_WARPS * 32, smem, ctx->stream>>>(B, st->d_consts, d_in, d_out, st->d_next);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;
