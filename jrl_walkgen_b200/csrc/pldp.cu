@@ -30,6 +30,7 @@ struct PldpHost {
   // staging for WG_MEM_HOST calls
   void *buf[10] = {nullptr};
   size_t cap[10] = {0};
+  int *d_next = nullptr;   // work counter of pldp_kernel
 };
 
 // One instance per warp.
@@ -39,7 +40,7 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
             const double *__restrict__ ZMPRef, const double *__restrict__ XkYk, double *__restrict__ X,
             const int *__restrict__ similar, long long similar_stride, const int *__restrict__ nremoved,
             const int *__restrict__ starting, wg_pldp_state *__restrict__ hot, int hot_start, int max_iter,
-            double tol, wg_pldp_info *__restrict__ info, int a_cap)
+            double tol, wg_pldp_info *__restrict__ info, int a_cap, int *__restrict__ next_problem)
 {
   __shared__ PldpWarp ws[PLDP_WARPS];
   extern __shared__ __align__(16) double sA[];   // a_cap doubles per warp: the instance's constraint matrix (0: read it from L2)
@@ -47,7 +48,12 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
   const PldpConsts &C = *Cp;
   PldpWarp &w = ws[warp];
   constexpr int N = PLDP_N;
-  for (int b = blockIdx.x * PLDP_WARPS + warp; b < B; b += gridDim.x * PLDP_WARPS) {
+  // iteration counts differ (5-33 on the bench workload): every warp takes its next problem from a work counter
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(next_problem, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= B) break;
     const int m = mvec[b];
     const int ld = m + 1;
     const double *A = DPu + (size_t)b * dpu_stride;
@@ -215,7 +221,7 @@ void wg_pldp_release(wg_ctx *ctx)
 {
   if (!ctx->pldp) return;
   PldpHost *p = static_cast<PldpHost *>(ctx->pldp);
-  cudaFree(p->d);
+  cudaFree(p->d); cudaFree(p->d_next);
   for (void *b : p->buf) cudaFree(b);
   delete p;
   ctx->pldp = nullptr;
@@ -312,10 +318,12 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
   int grid = (B + PLDP_WARPS - 1) / PLDP_WARPS;
   const int per_sm = smem ? (int)((227 * 1024) / (smem + sizeof(PldpWarp) * PLDP_WARPS + 1024)) : 8;
   if (grid > ctx->sm_count * (per_sm > 0 ? per_sm : 1)) grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+  if (!p->d_next) WG_CUDA(ctx, cudaMalloc(&p->d_next, sizeof(int)));
+  WG_CUDA(ctx, cudaMemsetAsync(p->d_next, 0, sizeof(int), ctx->stream));
   wg_prof_start(ctx, WG_K_PLDP);
   pldp_kernel<<<grid, PLDP_WARPS * 32, smem, ctx->stream>>>(
       B, p->d, d.D, d.m, d.DPu, d.dpu_stride, d.DPx, d.dpx_stride, d.ZMPRef, d.XkYk, d.X, d.similar, d.similar_stride,
-      d.n_removed, d.starting, d.hot, pb->hot_start, max_iter, tol, d.info, a_cap);
+      d.n_removed, d.starting, d.hot, pb->hot_start, max_iter, tol, d.info, a_cap, p->d_next);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   if (mem == WG_MEM_HOST) {
