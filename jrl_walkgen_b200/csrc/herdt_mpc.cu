@@ -309,6 +309,9 @@ herdt_mpc_kernel(int B, int nsteps, const herdt::Consts *__restrict__ Cp, const 
   const herdt::Consts &C = *Cp;
   const wg_herdt_mpc_params &M = *Mp;
   herdt::Work &s = works[warp];
+  // this kernel is register-bound at 3 CTAs/SM: the solver's T factor stays in shared memory here (the open-loop kernel keeps
+  // it in global memory to reach 16 warps/SM)
+  double *Tw = reinterpret_cast<double *>(smem_raw + (sizeof(herdt::Work) + sizeof(MpcWarp)) * MPC_WARPS) + (size_t)warp * herdt::TRI;
   MpcWarp &w = mws[warp];
   wg_herdt_mpc_state &st = w.st;
   const double T = C.P.T;
@@ -376,7 +379,7 @@ herdt_mpc_kernel(int B, int nsteps, const herdt::Consts *__restrict__ Cp, const 
         for (int e = lane; e < (int)(sizeof(wg_herdt_qp_input) / 8); e += 32) dst[e] = src[e];
       }
       int q = 0;
-      const herdt::Result r = herdt::solve_warp(s, C, lane, q);
+      const herdt::Result r = herdt::solve_warp(s, C, lane, q, Tw);
       const int ns = (r.n_vars - 2 * N) / 2;
 
       // ---- jerk to apply (ZMPVelocityReferencedQP.cpp:404-431)
@@ -658,7 +661,7 @@ int wg_herdt_mpc_init(wg_ctx *ctx, int mem, int B, const double *init9, int init
 static int mpc_launch(wg_ctx *ctx, MpcState *m, int B, int nsteps, wg_herdt_mpc_state *states, const double *vel_ref,
                       wg_herdt_tick *ticks, wg_herdt_mpc_step *steps, wg_herdt_qp_input *qp_in)
 {
-  const size_t smem = (sizeof(herdt::Work) + sizeof(MpcWarp)) * MPC_WARPS;
+  const size_t smem = (sizeof(herdt::Work) + sizeof(MpcWarp) + sizeof(double) * herdt::TRI) * MPC_WARPS;
   static bool attr = false;
   if (!attr) {
     WG_CUDA(ctx, cudaFuncSetAttribute(herdt_mpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -19,6 +19,7 @@ struct HerdtState {
   wg_herdt_qp_output *d_out = nullptr;
   int cap = 0;
   int *d_next = nullptr;          // work counter of herdt_qp_kernel
+  double *d_T = nullptr; size_t cap_T = 0;   // per-warp T slices
   // WG_MEM_HOST pipeline: upload / download streams and per-chunk events
   cudaStream_t up = nullptr, down = nullptr;
   cudaEvent_t ev_up[8] = {nullptr}, ev_k[8] = {nullptr}, ev0 = nullptr;
@@ -111,15 +112,16 @@ void compute_consts(const wg_herdt_params &P, Consts &C)
 
 constexpr int QP_WARPS = 4;  // warps (instances) per block
 
-__global__ void __launch_bounds__(QP_WARPS * 32, 3)
+__global__ void __launch_bounds__(QP_WARPS * 32, 4)
 herdt_qp_kernel(int B, const Consts *__restrict__ Cp, const wg_herdt_qp_input *__restrict__ in,
-                wg_herdt_qp_output *__restrict__ out, int *__restrict__ next_instance)
+                wg_herdt_qp_output *__restrict__ out, int *__restrict__ next_instance, double *__restrict__ scratchT)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   herdt::Work *works = reinterpret_cast<herdt::Work *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Consts &C = *Cp;
   herdt::Work &s = works[warp];
+  double *Tw = scratchT + ((size_t)blockIdx.x * QP_WARPS + warp) * herdt::TRI;
   // solve times differ (10-42 active-set iterations): every warp takes its next instance from a work counter
   for (;;) {
     int b = 0;
@@ -134,7 +136,7 @@ herdt_qp_kernel(int B, const Consts *__restrict__ Cp, const wg_herdt_qp_input *_
     }
     __syncwarp();
     int q = 0;
-    const herdt::Result r = herdt::solve_warp(s, C, lane, q);
+    const herdt::Result r = herdt::solve_warp(s, C, lane, q, Tw);
     // ---- write wg_herdt_qp_output (960 B)
     wg_herdt_qp_output &o = out[b];
     const int ns = (r.n_vars - 2 * N) / 2;
@@ -171,7 +173,7 @@ void wg_herdt_release(wg_ctx *ctx)
 {
   if (!ctx->herdt) return;
   HerdtState *st = static_cast<HerdtState *>(ctx->herdt);
-  cudaFree(st->d_consts); cudaFree(st->d_in); cudaFree(st->d_out); cudaFree(st->d_next);
+  cudaFree(st->d_consts); cudaFree(st->d_in); cudaFree(st->d_out); cudaFree(st->d_next); cudaFree(st->d_T);
   if (st->up) cudaStreamDestroy(st->up);
   if (st->down) cudaStreamDestroy(st->down);
   for (int c = 0; c < 8; ++c) { if (st->ev_up[c]) cudaEventDestroy(st->ev_up[c]); if (st->ev_k[c]) cudaEventDestroy(st->ev_k[c]); }
@@ -239,9 +241,16 @@ static int herdt_launch(wg_ctx *ctx, HerdtState *st, int B, const wg_herdt_qp_in
   const int cap = ctx->sm_count * per_sm;
   if (blocks > cap) blocks = cap;   // persistent: a multiple of the SM count, grid-stride over instances
   if (!st->d_next) WG_CUDA(ctx, cudaMalloc(&st->d_next, sizeof(int)));
+  const size_t needT = (size_t)blocks * QP_WARPS * herdt::TRI;
+  if (st->cap_T < needT) {
+    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(st->d_T); st->d_T = nullptr; st->cap_T = 0;
+    WG_CUDA(ctx, cudaMalloc(&st->d_T, sizeof(double) * needT));
+    st->cap_T = needT;
+  }
   WG_CUDA(ctx, cudaMemsetAsync(st->d_next, 0, sizeof(int), ctx->stream));
   wg_prof_start(ctx, WG_K_HERDT_QP);
-  herdt_qp_kernel<<<blocks, QP_WARPS * 32, smem, ctx->stream>>>(B, st->d_consts, d_in, d_out, st->d_next);
+  herdt_qp_kernel<<<blocks, QP_WARPS * 32, smem, ctx->stream>>>(B, st->d_consts, d_in, d_out, st->d_next, st->d_T);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;

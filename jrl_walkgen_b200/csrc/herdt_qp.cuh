@@ -51,7 +51,6 @@ struct Work {
   double PX[NPTS + 2], PY[NPTS + 2];
   double Gam[NPTS][NPTS];
   double a[MAXM + 2], b[MAXM + 2], d[MAXM + 2], inrm[MAXM + 2];
-  double T[TRI];
   double u[QMAX], gv[QMAX], w[QMAX], r[QMAX], ca[QMAX + 1], cb[QMAX + 1];
   double theta[NPTS][2], sigma[NPTS][2];
   double g[2][N], j0[2][N], Z[2][N], jr[2][N];
@@ -157,7 +156,9 @@ struct Result {
 
 // Build and solve the QP of the instance in s.in.  On return s.jr / s.ff hold the solution, s.u / s.W / q the
 // multipliers of the active rows.  All 32 lanes of the warp must call.
-__device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_out)
+// T: [TRI] doubles of scratch for the inverse Cholesky factor of the active Gram matrix, private to the warp (shared or
+// global memory: the open-loop kernel keeps it in global memory to fit 16 warps/SM).
+__device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_out, double *__restrict__ T)
 {
   const wg_herdt_params &P = C.P;
   const int axis = lane >> 4, i = lane & 15;
@@ -355,7 +356,7 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         __syncwarp();
 #pragma unroll 1
         for (int j = lane; j < q; j += 32) {
-          const double *Tr = s.T + tri(j);
+          const double *Tr = T + tri(j);
           double wv_ = 0.0;
 #pragma unroll 4
           for (int e = 0; e <= j; ++e) wv_ = fma(Tr[e], s.gv[e], wv_);
@@ -366,7 +367,7 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         for (int j = lane; j < q; j += 32) {
           double rj = 0.0;
 #pragma unroll 4
-          for (int r = j; r < q; ++r) rj = fma(s.T[tri(r) + j], s.w[r], rj);
+          for (int r = j; r < q; ++r) rj = fma(T[tri(r) + j], s.w[r], rj);
           s.u[j] -= rj;
         }
         __syncwarp();
@@ -406,7 +407,7 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
       double wsq = 0.0;
 #pragma unroll 1
       for (int j = lane; j < q; j += 32) {
-        const double *Tr = s.T + tri(j);
+        const double *Tr = T + tri(j);
         double w0 = 0.0, w1 = 0.0;
         int e = 0;
 #pragma unroll 2
@@ -423,8 +424,8 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         double r0 = 0.0, r1 = 0.0;
         int r = j;
 #pragma unroll 2
-        for (; r + 1 < q; r += 2) { r0 = fma(s.T[tri(r) + j], s.w[r], r0); r1 = fma(s.T[tri(r + 1) + j], s.w[r + 1], r1); }
-        if (r < q) r0 = fma(s.T[tri(r) + j], s.w[r], r0);
+        for (; r + 1 < q; r += 2) { r0 = fma(T[tri(r) + j], s.w[r], r0); r1 = fma(T[tri(r + 1) + j], s.w[r + 1], r1); }
+        if (r < q) r0 = fma(T[tri(r) + j], s.w[r], r0);
         const double rj = r0 + r1;
         s.r[j] = rj;
         if (rj > 0.0) {
@@ -464,8 +465,8 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         // full step: row p becomes active; append a row to T (inverse Cholesky factor of the active Gram matrix)
         const double idd = rsqrt(delta);
 #pragma unroll 1
-        for (int j = lane; j < q; j += 32) s.T[tri(q) + j] = -s.r[j] * idd;
-        if (lane == 0) { s.T[tri(q) + q] = idd; s.W[q] = p; s.u[q] = up; }
+        for (int j = lane; j < q; j += 32) T[tri(q) + j] = -s.r[j] * idd;
+        if (lane == 0) { T[tri(q) + q] = idd; s.W[q] = p; s.u[q] = up; }
         if ((p & 31) == lane) actbits |= 1u << (p >> 5);
         ++q;
         __syncwarp();
@@ -477,16 +478,16 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         const int kl = s.W[l];
         if ((kl & 31) == lane) actbits &= ~(1u << (kl >> 5));
 #pragma unroll 1
-        for (int j = lane; j < q; j += 32) s.w[j] = (j <= l) ? s.T[tri(l) + j] : 0.0;
+        for (int j = lane; j < q; j += 32) s.w[j] = (j <= l) ? T[tri(l) + j] : 0.0;
         __syncwarp();
 #pragma unroll 1
         for (int r = l + 1; r < q; ++r) {
-          const double *Tr = s.T + tri(r);
+          const double *Tr = T + tri(r);
           const double p1 = s.w[l], p2 = Tr[l];
           const double ih = rsqrt(p1 * p1 + p2 * p2);
           const double c_ = p1 * ih, s_ = p2 * ih;
           __syncwarp();
-          double *Tn = s.T + tri(r - 1);
+          double *Tn = T + tri(r - 1);
 #pragma unroll 1
           for (int j = lane; j <= r; j += 32) {
             const double x1 = s.w[j], x2 = Tr[j];
