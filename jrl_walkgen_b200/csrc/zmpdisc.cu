@@ -92,6 +92,30 @@ struct Foot {
   double x, y, z, theta, omega, omega2;
 };
 
+// Toe / heel rotation of the swing foot for omega != 0 (FootTrajectoryGenerationStandard.cpp:520-563).  Out of line: the
+// six sin/cos expansions would otherwise sit in the middle of the sample loop of every step.
+__device__ __noinline__ void omega_correction(double lo, double lth, double Bf, double H, double Ff, Foot &f)
+{
+  double dX, dFZ;
+  if (lo < 0) {
+    const double X1 = Bf * cos(-lo), X2 = H * sin(-lo), Z1 = H * cos(-lo), Z2 = Bf * sin(-lo);
+    dX = -(Bf - X1 + X2);
+    dFZ = Z1 + Z2 - H;
+  } else {
+    const double X1 = Ff * cos(lo), X2 = H * sin(lo), Z1 = H * cos(lo), Z2 = Ff * sin(lo);
+    dX = (Ff - X1 + X2);
+    dFZ = Z1 + Z2 - H;
+  }
+  if (dX != 0.0) {
+    f.x += cos(lth) * dX;
+    f.y += sin(lth) * dX;
+  } else {
+    f.x += 0.0;
+    f.y += 0.0;
+  }
+  f.z += dFZ;
+}
+
 struct Frame {   // m_CurrentSupportFootPosition: rotation (row-major 2x2) + translation
   double r00, r01, r10, r11, tx, ty;
 };
@@ -138,9 +162,11 @@ __device__ void filter_head(const ZdConsts &K, const double2 *u, int len, int ul
                             double2 final0, double2 *head)
 {
   const int nh = min(len, ZD_HEAD);
+#pragma unroll 1
   for (int i = 0; i < nh; ++i) {
     double a0 = 0, a1 = 0;
     const int64_t o = F0 + i - 1 - 2;
+#pragma unroll 1
     for (int j = 0; j < K.nw; ++j) {
       int r = i - j + 2;
       double2 v;
@@ -217,8 +243,10 @@ zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ ste
       const int n = K.n_lead;
       const double2 u2 = make_double2(0.0 + (P.zmp_neutral[0] - 0.0) * (2.0 / (double)n),
                                       0.0 + (P.zmp_neutral[1] - 0.0) * (2.0 / (double)n));
+#pragma unroll 1
       for (int i = lane; i < n; i += 32) {
         double a0 = 0, a1 = 0;
+#pragma unroll 1
         for (int j = 0; j < K.nw; ++j) {
           int r = i - j + 2;
           double2 v;
@@ -358,28 +386,15 @@ zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ ste
         else
           f.omega = peval(PO, 4, lt - start_land) - P.omega;
         const double lo = f.omega * M_PI / 180.0, lth = f.theta * M_PI / 180.0;
-        double dX, dFZ;
         const double Bf = P.foot_b, H = P.foot_h, Ff = P.foot_f;
-        if (lo < 0) {
-          const double X1 = Bf * cos(-lo), X2 = H * sin(-lo), Z1 = H * cos(-lo), Z2 = Bf * sin(-lo);
-          dX = -(Bf - X1 + X2);
-          dFZ = Z1 + Z2 - H;
-        } else if (lo == 0.0) {     // cos(0) = 1, sin(0) = 0 exactly: the correction vanishes without the trig calls
-          dX = (Ff - Ff + 0.0);
-          dFZ = H + 0.0 - H;
+        if (lo == 0.0) {            // cos(0) = 1, sin(0) = 0 exactly: the correction vanishes without the trig calls
+          const double dX = (Ff - Ff + 0.0), dFZ = H + 0.0 - H;
+          f.x += dX;               // x + c*0 = x for finite c
+          f.y += dX;
+          f.z += dFZ;
         } else {
-          const double X1 = Ff * cos(lo), X2 = H * sin(lo), Z1 = H * cos(lo), Z2 = Ff * sin(lo);
-          dX = (Ff - X1 + X2);
-          dFZ = Z1 + Z2 - H;
+          omega_correction(lo, lth, Bf, H, Ff, f);   // rarely taken (omega = 0 in every reference profile): out of line
         }
-        if (dX != 0.0) {
-          f.x += cos(lth) * dX;
-          f.y += sin(lth) * dX;
-        } else {                   // x + c*0 = x for finite c
-          f.x += 0.0;
-          f.y += 0.0;
-        }
-        f.z += dFZ;
         return f;
       };
       // emit the segment
