@@ -403,3 +403,47 @@ def test_gpu_dimitrov_batch_properties(ctx):
             z = out["zmp"][s0 + 20 * k + 19]
             r = p["rows"]
             assert (p["A"][:r] @ z + p["B"][:r] > -1e-6).all(), (b, k)
+
+
+@pytest.mark.gpu
+def test_gpu_dimitrov_edge_cases(ctx):
+    """Error conventions and degenerate inputs of the Dimitrov entry points: too few period records and too small a
+    polygon capacity are refused (WG_ERR_INVALID), a context without constants answers WG_ERR_NOT_READY, a walk that is
+    a single (initial) step - double support from the first to the last sample - runs and matches the oracle."""
+    import jrl_walkgen_b200 as wg
+    from jrl_walkgen_b200 import _capi
+    steps = zo.profile_steps("StraightWalking")
+    # (1) not ready: a fresh context has no Dimitrov constants
+    c2 = wg.Context(0)
+    try:
+        plan = wg.KajitaPlan(c2, np.array([0, len(steps)], dtype=np.int64), steps, zo.INIT_FEET)
+        rc = c2.lib.wg_dimitrov_run_batch(c2.h, plan.h, wg.WG_MEM_HOST, None, None, None, None, None, None, None, None)
+        assert rc == _capi.WG_ERR_NOT_READY
+        plan.destroy()
+    finally:
+        c2.close()
+    # (2) period records: one fewer than the loop needs
+    ctx.dimitrov_set_params()
+    plan = wg.KajitaPlan(ctx, np.array([0, len(steps)], dtype=np.int64), steps, zo.INIT_FEET)
+    need = int(ctx.lib.wg_dimitrov_period_count(C.byref(ctx.dimitrov_params), int(plan.total_samples)))
+    assert need == 185
+    per = np.zeros(need, dtype=wg.DIMITROV_PERIOD_DTYPE)
+    po = np.array([0, need - 1], dtype=np.int64)
+    rc = ctx.lib.wg_dimitrov_run_batch(ctx.h, plan.h, wg.WG_MEM_HOST, None, None, None, None,
+                                       po.ctypes.data_as(_capi.c_i64_p), per.ctypes.data, None, None)
+    assert rc == _capi.WG_ERR_INVALID
+    plan.destroy()
+    # (3) polygon capacity
+    o = zo.run(zo.default_params(), steps)
+    with pytest.raises(wg.WalkgenError):
+        ctx.fcals_build(o["left"], o["right"], o["types"], cap=5)
+    # (4) a walk of one step: the whole buffer is one double-support polygon
+    one = steps[:1].copy()
+    o1 = zo.run(zo.default_params(), one)
+    ref = do.run(o1["left"], o1["right"], o1["types"][:, 1].copy())
+    out = ctx.dimitrov_run([one], [zo.INIT_FEET])
+    P = ctx.fcals_build(o1["left"], o1["right"], o1["types"])
+    assert len(P) == 1 and P["state"][0] == 3 and P["rows"][0] == 4
+    assert out["status"][0] == (0 if ref["failed_at"] is None else 1) and out["periods_done"][0] == len(ref["periods"])
+    good = len(ref["periods"]) - (0 if ref["failed_at"] is None else 1)
+    assert out["com"][:20 * good].tobytes() == ref["com"][:20 * good].tobytes()
