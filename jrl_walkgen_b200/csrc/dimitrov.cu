@@ -57,7 +57,7 @@ struct DimHost {
   bool ready = false;
   double iPu[DM_N * DM_N], iLQ[DM_N * DM_N];
   // clock table and scratch (grow-only)
-  double *d_time = nullptr; size_t time_cap = 0;
+  double *d_time = nullptr;
   std::vector<double> time_h;
   void *buf[14] = {nullptr};
   size_t cap[14] = {0};
@@ -380,7 +380,6 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
       const int m = __shfl_sync(0xffffffffu, incl, N - 1);
       const int roff = incl - my_rows;
       const int n_first = __shfl_sync(0xffffffffu, my_rows, 0);
-      const int ld = m + 1;
       if (lane < 6) w.xk[lane] = lane == 0 ? cx0 : lane == 1 ? cx1 : lane == 2 ? cx2 : lane == 3 ? cy0 : lane == 4 ? cy1 : cy2;
       if (lane < N) {
         const wg_lci &q = P[my_p];
