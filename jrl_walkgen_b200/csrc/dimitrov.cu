@@ -313,8 +313,9 @@ struct DimWarp {
   unsigned char rowi[DM_MAXM];
 };
 
-// 4 CTAs/SM (128 registers): at 6 CTAs/SM (80 registers, spills) 4096 walks ran 52 % SLOWER - a walk is a serial chain of
-// some hundred periods, a batch of a few thousand walks is bound by its longest walks, not by the number of resident warps
+// 4 CTAs/SM (128 registers) measured best at both batch sizes tried: 4096 walks 36.1 ms (3 CTAs/SM at 161 registers: 38 ms, 5
+// CTAs/SM at 96 registers: 47.8 ms, 6 at 80 registers with spills: 58 ms); 16 384 walks 111 ms (3: 122 ms, 5: 121 ms).  A walk is
+// a serial chain of some hundred periods: per-warp speed (registers, few warps per scheduler) counts as much as residency.
 __global__ void __launch_bounds__(DM_WARPS * 32, 4)
 dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__restrict__ Cp,
                 const int64_t *__restrict__ samp_off, const double *__restrict__ clock,
