@@ -16,6 +16,7 @@
 // :890-900) becomes an iteration cap, and the paths on which the reference calls exit(0) (:822-828) or prints
 // return a status instead.
 #include "wg_common.h"
+#include <algorithm>
 #include <vector>
 #include <cmath>
 
@@ -31,6 +32,9 @@ struct PldpHost {
   void *buf[10] = {nullptr};
   size_t cap[10] = {0};
   int *d_next = nullptr;   // work counter of pldp_kernel
+  // WG_MEM_HOST pipeline
+  cudaStream_t up = nullptr, down = nullptr;
+  cudaEvent_t ev_up[4] = {nullptr}, ev_k[4] = {nullptr}, ev0 = nullptr;
 };
 
 // One instance per warp.
@@ -222,6 +226,10 @@ void wg_pldp_release(wg_ctx *ctx)
   if (!ctx->pldp) return;
   PldpHost *p = static_cast<PldpHost *>(ctx->pldp);
   cudaFree(p->d); cudaFree(p->d_next);
+  if (p->up) cudaStreamDestroy(p->up);
+  if (p->down) cudaStreamDestroy(p->down);
+  for (int c = 0; c < 4; ++c) { if (p->ev_up[c]) cudaEventDestroy(p->ev_up[c]); if (p->ev_k[c]) cudaEventDestroy(p->ev_k[c]); }
+  if (p->ev0) cudaEventDestroy(p->ev0);
   for (void *b : p->buf) cudaFree(b);
   delete p;
   ctx->pldp = nullptr;
@@ -267,72 +275,97 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
   const int max_iter = pb->max_iterations > 0 ? pb->max_iterations : 4 * PLDP_KMAX;
   const double tol = 1e-8;   // m_tol, PLDPSolver.cpp:66
   wg_pldp_batch d = *pb;
-  if (mem == WG_MEM_HOST) {
-    const size_t nb = (size_t)B;
-    struct Item { int slot; const void *src; size_t bytes; const void **dst; };
-    const Item in[] = {
-        {0, pb->D, sizeof(double) * PLDP_U * nb, (const void **)&d.D},
-        {1, pb->m, sizeof(int) * nb, (const void **)&d.m},
-        {2, pb->DPu, sizeof(double) * (size_t)pb->dpu_stride * nb, (const void **)&d.DPu},
-        {3, pb->DPx, sizeof(double) * (size_t)pb->dpx_stride * nb, (const void **)&d.DPx},
-        {4, pb->ZMPRef, sizeof(double) * PLDP_U * nb, (const void **)&d.ZMPRef},
-        {5, pb->XkYk, sizeof(double) * 6 * nb, (const void **)&d.XkYk},
-        {6, pb->similar, pb->similar ? sizeof(int) * (size_t)pb->similar_stride * nb : 0, (const void **)&d.similar},
-        {7, pb->n_removed, pb->n_removed ? sizeof(int) * nb : 0, (const void **)&d.n_removed},
-        {8, pb->starting, pb->starting ? sizeof(int) * nb : 0, (const void **)&d.starting}};
-    for (const Item &it : in) {
-      if (!it.src) continue;
-      int rc = ensure(ctx, p, it.slot, it.bytes);
-      if (rc != WG_OK) return rc;
-      WG_CUDA(ctx, cudaMemcpyAsync(p->buf[it.slot], it.src, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
-      *it.dst = p->buf[it.slot];
+  // launch over instances [b0, b0 + n) of the device-side batch `d`
+  auto launch = [&](int b0, int n) -> int {
+    int grid = (n + PLDP_WARPS - 1) / PLDP_WARPS;
+    // Measured (16 384 cold-started problems, m ~ 68): constraint matrix staged in shared memory, 8 warps/SM: 4.57 ms; read
+    // from L2 (the batch's matrices, 290 MB, stream through once per iteration of their own warp), 32 warps/SM at 64
+    // registers: 3.53 ms, 2.85 ms with the work counter.  The solver is a chain of dependent FP64 operations: resident warps
+    // hide more than shared memory saves.  WG_PLDP_STAGE=1 restores the staged variant.
+    static const int stage = getenv("WG_PLDP_STAGE") ? atoi(getenv("WG_PLDP_STAGE")) : 0;
+    int a_cap = stage ? (int)((pb->dpu_stride + 1) & ~1LL) : 0;
+    size_t smem = sizeof(double) * (size_t)a_cap * PLDP_WARPS;
+    if (smem > 200 * 1024) { a_cap = 0; smem = 0; }
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      WG_CUDA(ctx, cudaFuncSetAttribute(pldp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
     }
-    // outputs + hot-start state share one allocation: X | info | hot
-    const size_t ox = 0, oi = ox + sizeof(double) * PLDP_U * nb, oh = oi + sizeof(wg_pldp_info) * nb;
-    const size_t total = oh + sizeof(wg_pldp_state) * nb;
-    int rc = ensure(ctx, p, 9, total);
+    const int per_sm = smem ? (int)((227 * 1024) / (smem + sizeof(PldpWarp) * PLDP_WARPS + 1024)) : 8;
+    if (grid > ctx->sm_count * (per_sm > 0 ? per_sm : 1)) grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+    if (!p->d_next) WG_CUDA(ctx, cudaMalloc(&p->d_next, sizeof(int)));
+    WG_CUDA(ctx, cudaMemsetAsync(p->d_next, 0, sizeof(int), ctx->stream));
+    const size_t o = (size_t)b0;
+    wg_prof_start(ctx, WG_K_PLDP);
+    pldp_kernel<<<grid, PLDP_WARPS * 32, smem, ctx->stream>>>(
+        n, p->d, d.D + o * PLDP_U, d.m + o, d.DPu + o * d.dpu_stride, d.dpu_stride, d.DPx + o * d.dpx_stride, d.dpx_stride,
+        d.ZMPRef + o * PLDP_U, d.XkYk + o * 6, d.X + o * PLDP_U, d.similar ? d.similar + o * d.similar_stride : nullptr,
+        d.similar_stride, d.n_removed ? d.n_removed + o : nullptr, d.starting ? d.starting + o : nullptr,
+        d.hot ? d.hot + o : nullptr, pb->hot_start, max_iter, tol, d.info ? d.info + o : nullptr, a_cap, p->d_next);
+    wg_prof_stop(ctx);
+    WG_LAUNCHED(ctx);
+    return WG_OK;
+  };
+  if (mem == WG_MEM_DEVICE) return launch(0, B);
+  if (mem != WG_MEM_HOST) return WG_ERR_INVALID;
+  // ---- host buffers: stage, then up to 4 chunks pipelined over upload / kernel / download streams (the upload of the
+  // constraint matrices, 17 KB per problem, is twice the kernel time)
+  const size_t nb = (size_t)B;
+  struct Item { int slot; const void *src; size_t per; const void **dst; };
+  const Item in[] = {
+      {0, pb->D, sizeof(double) * PLDP_U, (const void **)&d.D},
+      {1, pb->m, sizeof(int), (const void **)&d.m},
+      {2, pb->DPu, sizeof(double) * (size_t)pb->dpu_stride, (const void **)&d.DPu},
+      {3, pb->DPx, sizeof(double) * (size_t)pb->dpx_stride, (const void **)&d.DPx},
+      {4, pb->ZMPRef, sizeof(double) * PLDP_U, (const void **)&d.ZMPRef},
+      {5, pb->XkYk, sizeof(double) * 6, (const void **)&d.XkYk},
+      {6, pb->similar, pb->similar ? sizeof(int) * (size_t)pb->similar_stride : 0, (const void **)&d.similar},
+      {7, pb->n_removed, pb->n_removed ? sizeof(int) : 0, (const void **)&d.n_removed},
+      {8, pb->starting, pb->starting ? sizeof(int) : 0, (const void **)&d.starting}};
+  for (const Item &it : in) {
+    if (!it.src) continue;
+    int rc = ensure(ctx, p, it.slot, it.per * nb);
     if (rc != WG_OK) return rc;
-    char *base = static_cast<char *>(p->buf[9]);
-    d.X = reinterpret_cast<double *>(base + ox);
-    d.info = pb->info ? reinterpret_cast<wg_pldp_info *>(base + oi) : nullptr;
-    d.hot = pb->hot ? reinterpret_cast<wg_pldp_state *>(base + oh) : nullptr;
-    if (pb->hot) WG_CUDA(ctx, cudaMemcpyAsync(d.hot, pb->hot, sizeof(wg_pldp_state) * nb, cudaMemcpyHostToDevice, ctx->stream));
-  } else if (mem != WG_MEM_DEVICE) {
-    return WG_ERR_INVALID;
+    *it.dst = p->buf[it.slot];
   }
-  // shared-memory copy of each instance's constraint matrix when it fits (dpu_stride bounds (m+1)*32)
-  int a_cap = (int)((pb->dpu_stride + 1) & ~1LL);
-  size_t smem = sizeof(double) * (size_t)a_cap * PLDP_WARPS;
-  if (smem > 200 * 1024) { a_cap = 0; smem = 0; }
-  // Measured (16 384 cold-started problems, m ~ 68): constraint matrix staged in shared memory, 8 warps/SM: 4.57 ms; read
-  // from L2 (the batch's matrices, 290 MB, stream through once per iteration of their own warp), 32 warps/SM at 64
-  // registers: 3.53 ms.  The solver is a chain of dependent FP64 operations: resident warps hide more than shared memory
-  // saves.  WG_PLDP_STAGE=1 restores the staged variant.
-  static const int stage = getenv("WG_PLDP_STAGE") ? atoi(getenv("WG_PLDP_STAGE")) : 0;
-  if (!stage) { a_cap = 0; smem = 0; }
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    WG_CUDA(ctx, cudaFuncSetAttribute(pldp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  // outputs + hot-start state share one allocation: X | info | hot
+  const size_t ox = 0, oi = ox + sizeof(double) * PLDP_U * nb, oh = oi + sizeof(wg_pldp_info) * nb;
+  int rc = ensure(ctx, p, 9, oh + sizeof(wg_pldp_state) * nb);
+  if (rc != WG_OK) return rc;
+  char *base = static_cast<char *>(p->buf[9]);
+  d.X = reinterpret_cast<double *>(base + ox);
+  d.info = pb->info ? reinterpret_cast<wg_pldp_info *>(base + oi) : nullptr;
+  d.hot = pb->hot ? reinterpret_cast<wg_pldp_state *>(base + oh) : nullptr;
+  if (!p->up) {
+    WG_CUDA(ctx, cudaStreamCreateWithFlags(&p->up, cudaStreamNonBlocking));
+    WG_CUDA(ctx, cudaStreamCreateWithFlags(&p->down, cudaStreamNonBlocking));
+    for (int c = 0; c < 4; ++c) {
+      WG_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_up[c], cudaEventDisableTiming));
+      WG_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_k[c], cudaEventDisableTiming));
+    }
+    WG_CUDA(ctx, cudaEventCreateWithFlags(&p->ev0, cudaEventDisableTiming));
   }
-  int grid = (B + PLDP_WARPS - 1) / PLDP_WARPS;
-  const int per_sm = smem ? (int)((227 * 1024) / (smem + sizeof(PldpWarp) * PLDP_WARPS + 1024)) : 8;
-  if (grid > ctx->sm_count * (per_sm > 0 ? per_sm : 1)) grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);
-  if (!p->d_next) WG_CUDA(ctx, cudaMalloc(&p->d_next, sizeof(int)));
-  WG_CUDA(ctx, cudaMemsetAsync(p->d_next, 0, sizeof(int), ctx->stream));
-  wg_prof_start(ctx, WG_K_PLDP);
-  pldp_kernel<<<grid, PLDP_WARPS * 32, smem, ctx->stream>>>(
-      B, p->d, d.D, d.m, d.DPu, d.dpu_stride, d.DPx, d.dpx_stride, d.ZMPRef, d.XkYk, d.X, d.similar, d.similar_stride,
-      d.n_removed, d.starting, d.hot, pb->hot_start, max_iter, tol, d.info, a_cap, p->d_next);
-  wg_prof_stop(ctx);
-  WG_LAUNCHED(ctx);
-  if (mem == WG_MEM_HOST) {
-    const size_t nb = (size_t)B;
-    WG_CUDA(ctx, cudaMemcpyAsync(pb->X, d.X, sizeof(double) * PLDP_U * nb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (pb->info) WG_CUDA(ctx, cudaMemcpyAsync(pb->info, d.info, sizeof(wg_pldp_info) * nb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (pb->hot) WG_CUDA(ctx, cudaMemcpyAsync(pb->hot, d.hot, sizeof(wg_pldp_state) * nb, cudaMemcpyDeviceToHost, ctx->stream));
-    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int nch = std::max(1, std::min(4, B / 2048));
+  WG_CUDA(ctx, cudaEventRecord(p->ev0, ctx->stream));
+  WG_CUDA(ctx, cudaStreamWaitEvent(p->up, p->ev0, 0));
+  for (int c = 0; c < nch; ++c) {
+    const size_t b0 = nb * c / nch, b1 = nb * (c + 1) / nch, n = b1 - b0;
+    for (const Item &it : in)
+      if (it.src)
+        WG_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(p->buf[it.slot]) + b0 * it.per, static_cast<const char *>(it.src) + b0 * it.per,
+                                     it.per * n, cudaMemcpyHostToDevice, p->up));
+    if (pb->hot) WG_CUDA(ctx, cudaMemcpyAsync(d.hot + b0, pb->hot + b0, sizeof(wg_pldp_state) * n, cudaMemcpyHostToDevice, p->up));
+    WG_CUDA(ctx, cudaEventRecord(p->ev_up[c], p->up));
+    WG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->ev_up[c], 0));
+    if ((rc = launch((int)b0, (int)n)) != WG_OK) return rc;
+    WG_CUDA(ctx, cudaEventRecord(p->ev_k[c], ctx->stream));
+    WG_CUDA(ctx, cudaStreamWaitEvent(p->down, p->ev_k[c], 0));
+    WG_CUDA(ctx, cudaMemcpyAsync(pb->X + b0 * PLDP_U, d.X + b0 * PLDP_U, sizeof(double) * PLDP_U * n, cudaMemcpyDeviceToHost, p->down));
+    if (pb->info) WG_CUDA(ctx, cudaMemcpyAsync(pb->info + b0, d.info + b0, sizeof(wg_pldp_info) * n, cudaMemcpyDeviceToHost, p->down));
+    if (pb->hot) WG_CUDA(ctx, cudaMemcpyAsync(pb->hot + b0, d.hot + b0, sizeof(wg_pldp_state) * n, cudaMemcpyDeviceToHost, p->down));
   }
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  WG_CUDA(ctx, cudaStreamSynchronize(p->down));
   return WG_OK;
 }
 
