@@ -307,7 +307,9 @@ int wg_herdt_mpc_init(wg_ctx *ctx, int mem, int B, const double *init9, int init
  *             period inherits at the back of the deques, final only now, then its first 19 new samples)
  *   steps   : [B][nsteps] or NULL     per-period summaries
  *   qp_in   : [B] or NULL             the QP input of each instance's LAST period (workload capture)
- * Instances whose on-line mode ended (:stoppg + preview horizon elapsed) are left untouched. */
+ * Instances whose on-line mode ended (:stoppg + preview horizon elapsed) are left untouched.
+ * A period is three kernel launches (FSM + QP record, the solver of wg_herdt_qp_solve_batch, interpolation + state update);
+ * the environment variable WG_HERDT_MPC_SPLIT=0 selects the single fused kernel instead (same results, slower on large batches). */
 int wg_herdt_mpc_run_batch(wg_ctx *ctx, int mem, int B, int nsteps, wg_herdt_mpc_state *states,
                            const double *vel_ref, wg_herdt_tick *ticks, wg_herdt_mpc_step *steps,
                            wg_herdt_qp_input *qp_in);
