@@ -814,6 +814,13 @@ def run_cuda(args):
                                    "MEASURED_PEAKS.json has no FP64 entry",
                     "algorithmic_flop_per_step": fl}
         roof["hbm_frac_streaming_minimum"] = BYTES_PER_STEP * steps_per_pass / (ms_per_step * 1e-3) / 1e9 / hbm_peak
+        if dom_name == "preview_fused_kernel" and args.walks == 4096:
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this (seeded, deterministic) workload from the
+            # committed `ncu --set full` capture (profiles/r1_v8_ncu_summary.md: 282.5 MB + 884.3 MB); algorithmic bytes of
+            # the same launch: 80 B x 14.5 M steps = 1163 MB, i.e. no wasted re-reads
+            roof["traffic"] = 1166.8e6
+            roof["traffic_unit"] = "bytes per launch"
+            roof["traffic_source"] = "profiles/r1_v8_ncu_summary.md (ncu --set full, same command)"
         cpu = None
         if world == 1:
             subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
