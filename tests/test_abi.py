@@ -77,6 +77,17 @@ def test_host_only_entry_points_work_without_a_gpu():
     assert g.NL == 320 and abs(g.Ks - 618.7) / 618.7 < 2e-4     # src/data/PreviewControlParameters.ini
     from jrl_walkgen_b200 import _capi
     assert _capi.load().wg_version() > 0
+    # Dimitrov: defaults of ZMPConstrainedQPFastFormulation's ctor (:79-96) and the loop bound of :1190-1194 on the accumulated
+    # 5 ms clock, against the oracle's restatement (host arithmetic only)
+    import dimitrov_oracle as do
+    d = wg.dimitrov_default_params()
+    assert (d.T, d.sampling_period, d.com_height, d.alpha, d.beta, d.constraint_x, d.constraint_y) == (0.1, 0.005, 0.80, 200.0, 1000.0, 0.04, 0.04)
+    assert (d.cold_restart, d.merge_duplicate_rows) == (0, 0)
+    for n in (1, 2, 321, 322, 1602, 4002, 4003, 9999, 20001):
+        assert _capi.load().wg_dimitrov_period_count(C.byref(d), n) == do.period_count(n), n
+    z = wg.zmpdisc_default_params()
+    steps = np.zeros(3, dtype=wg.REL_STEP_DTYPE); steps["ss_time"], steps["ds_time"] = 0.78, 0.02
+    assert _capi.load().wg_zmpdisc_sample_count(C.byref(z), 3, steps.ctypes.data) == 640 + 2 * 160 + 2 + 960
 
 
 def test_no_cpu_fallback():
