@@ -280,7 +280,7 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
     int grid = (n + PLDP_WARPS - 1) / PLDP_WARPS;
     // Measured (16 384 cold-started problems, m ~ 68): constraint matrix staged in shared memory, 8 warps/SM: 4.57 ms; read
     // from L2 (the batch's matrices, 290 MB, stream through once per iteration of their own warp), 32 warps/SM at 64
-    // registers: 3.53 ms, 2.85 ms with the work counter.  The solver is a chain of dependent FP64 operations: resident warps
+    // registers: 3.53 ms, 2.85 ms with the work counter (24 warps/SM at 80 registers: 3.10 ms).  The solver is a chain of dependent FP64 operations: resident warps
     // hide more than shared memory saves.  WG_PLDP_STAGE=1 restores the staged variant.
     static const int stage = getenv("WG_PLDP_STAGE") ? atoi(getenv("WG_PLDP_STAGE")) : 0;
     int a_cap = stage ? (int)((pb->dpu_stride + 1) & ~1LL) : 0;
