@@ -1,11 +1,17 @@
 /* Stand-in for jrl-mal's <jrl/mal/matrixabstractlayer.hh> (jrl-mal >= 1.9.0 is an
  * un-vendored dependency of the reference, CMakeLists.txt:45).  Written for this repository;
- * it only provides the handful of MAL_* macros used by the reference sources that
- * oracle/Makefile compiles where they lie (OptCholesky.cpp and PLDPSolver.cpp use none;
+ * it only provides the MAL_* macros used by the reference sources that oracle/Makefile
+ * compiles where they lie (OptCholesky.cpp and PLDPSolver.cpp use none;
  * FootConstraintsAsLinearSystem.cpp and pgtypes.hh use MAL_MATRIX / MAL_VECTOR, *_RESIZE,
- * MAL_MATRIX_NB_ROWS, MAL_VECTOR_DIM and MAL_RET_A_by_B).  Semantics are those of the
- * Boost uBLAS backend of jrl-mal: dense row-major double storage, resize keeps the old
- * contents; NEW elements are zero here (uBLAS leaves them uninitialised).
+ * MAL_MATRIX_NB_ROWS, MAL_VECTOR_DIM and MAL_RET_A_by_B; PreviewControl.cpp and
+ * OptimalControllerSolver.cpp add matrix products, sums, scalar scaling, transposes, FILL /
+ * SET_IDENTITY, the raw data block handed to LAPACK and MAL_INVERSE).  Semantics are those of
+ * the Boost uBLAS backend of jrl-mal: dense row-major double storage, resize keeps the old
+ * contents; NEW elements are zero here (uBLAS leaves them uninitialised); a product element is
+ * t = 0; t += a(i,k)*b(k,j) for k ascending (uBLAS matrix_matrix_prod / matrix_vector_prod1),
+ * and `prod(A,x) + s*B` is evaluated element by element as (sum) + (s*B(i,j)), which is what
+ * the uBLAS expression templates do.  MAL_INVERSE is LAPACK dgetrf_ + dgetri_ as in jrl-mal's
+ * boost backend (the LAPACK symbols are resolved by oracle/ref_glue.cc at run time).
  * TEST INFRASTRUCTURE ONLY - nothing under oracle/ is linked into the product. */
 #ifndef ORACLE_REF_SHIM_MAL_HH
 #define ORACLE_REF_SHIM_MAL_HH
@@ -24,6 +30,8 @@ template <typename T> class vector {
   const T &operator()(std::size_t i) const { return d_[i]; }
   T &operator[](std::size_t i) { return d_[i]; }
   const T &operator[](std::size_t i) const { return d_[i]; }
+  T *data() { return d_.empty() ? 0 : &d_[0]; }
+  void fill(T v) { for (std::size_t i = 0; i < d_.size(); ++i) d_[i] = v; }
  private:
   std::vector<T> d_;
 };
@@ -43,10 +51,85 @@ template <typename T> class matrix {
   std::size_t size2() const { return c_; }
   T &operator()(std::size_t i, std::size_t j) { return d_[i * c_ + j]; }
   const T &operator()(std::size_t i, std::size_t j) const { return d_[i * c_ + j]; }
+  T *data() { return d_.empty() ? 0 : &d_[0]; }
+  void fill(T v) { for (std::size_t i = 0; i < d_.size(); ++i) d_[i] = v; }
+  void set_identity()
+  {
+    for (std::size_t i = 0; i < r_; ++i)
+      for (std::size_t j = 0; j < c_; ++j) (*this)(i, j) = (i == j) ? T(1) : T(0);
+  }
  private:
   std::size_t r_, c_;
   std::vector<T> d_;
 };
+
+/* prod(matrix, matrix): element (i,j) = 0 + sum_k a(i,k)*b(k,j), k ascending */
+template <typename T> matrix<T> prod(const matrix<T> &A, const matrix<T> &B)
+{
+  matrix<T> Cm(A.size1(), B.size2());
+  for (std::size_t i = 0; i < A.size1(); ++i)
+    for (std::size_t j = 0; j < B.size2(); ++j) {
+      T t = T();
+      for (std::size_t k = 0; k < A.size2(); ++k) t += A(i, k) * B(k, j);
+      Cm(i, j) = t;
+    }
+  return Cm;
+}
+template <typename T> matrix<T> trans(const matrix<T> &A)
+{
+  matrix<T> R(A.size2(), A.size1());
+  for (std::size_t i = 0; i < A.size1(); ++i)
+    for (std::size_t j = 0; j < A.size2(); ++j) R(j, i) = A(i, j);
+  return R;
+}
+template <typename T> matrix<T> operator+(const matrix<T> &A, const matrix<T> &B)
+{
+  matrix<T> R(A.size1(), A.size2());
+  for (std::size_t i = 0; i < A.size1(); ++i)
+    for (std::size_t j = 0; j < A.size2(); ++j) R(i, j) = A(i, j) + B(i, j);
+  return R;
+}
+template <typename T> matrix<T> operator-(const matrix<T> &A, const matrix<T> &B)
+{
+  matrix<T> R(A.size1(), A.size2());
+  for (std::size_t i = 0; i < A.size1(); ++i)
+    for (std::size_t j = 0; j < A.size2(); ++j) R(i, j) = A(i, j) - B(i, j);
+  return R;
+}
+template <typename T> matrix<T> operator-(const matrix<T> &A)
+{
+  matrix<T> R(A.size1(), A.size2());
+  for (std::size_t i = 0; i < A.size1(); ++i)
+    for (std::size_t j = 0; j < A.size2(); ++j) R(i, j) = -A(i, j);
+  return R;
+}
+template <typename T> matrix<T> operator*(const matrix<T> &A, T s)
+{
+  matrix<T> R(A.size1(), A.size2());
+  for (std::size_t i = 0; i < A.size1(); ++i)
+    for (std::size_t j = 0; j < A.size2(); ++j) R(i, j) = A(i, j) * s;
+  return R;
+}
+template <typename T> matrix<T> operator*(T s, const matrix<T> &A)
+{
+  matrix<T> R(A.size1(), A.size2());
+  for (std::size_t i = 0; i < A.size1(); ++i)
+    for (std::size_t j = 0; j < A.size2(); ++j) R(i, j) = s * A(i, j);
+  return R;
+}
+template <typename S, typename T> S &operator<<(S &os, const matrix<T> &A)
+{
+  os << "[" << A.size1() << "," << A.size2() << "](";
+  for (std::size_t i = 0; i < A.size1(); ++i) {
+    os << (i ? ",(" : "(");
+    for (std::size_t j = 0; j < A.size2(); ++j) os << (j ? "," : "") << A(i, j);
+    os << ")";
+  }
+  os << ")";
+  return os;
+}
+/* inverse of a square matrix by LU (dgetrf_ / dgetri_); defined in oracle/ref_glue.cc */
+void lapack_inverse(const matrix<double> &A, matrix<double> &invA);
 
 /* prod(matrix, vector): plain row-by-row accumulation, as uBLAS' dense matrix-vector product */
 template <typename T> vector<T> prod(const matrix<T> &A, const vector<T> &x)
@@ -72,4 +155,12 @@ template <typename T> vector<T> prod(const matrix<T> &A, const vector<T> &x)
 #define MAL_MATRIX_NB_ROWS(name) name.size1()
 #define MAL_MATRIX_NB_COLS(name) name.size2()
 #define MAL_RET_A_by_B(A, B) oracle_mal::prod(A, B)
+#define MAL_MATRIX_TYPE(type) oracle_mal::matrix<type>
+#define MAL_MATRIX_FILL(name, v) name.fill(v)
+#define MAL_VECTOR_FILL(name, v) name.fill(v)
+#define MAL_MATRIX_SET_IDENTITY(name) name.set_identity()
+#define MAL_RET_TRANSPOSE(name) oracle_mal::trans(name)
+#define MAL_RET_MATRIX_DATABLOCK(name) name.data()
+#define MAL_RET_VECTOR_DATABLOCK(name) name.data()
+#define MAL_INVERSE(name, inv, type) oracle_mal::lapack_inverse(name, inv)
 #endif
