@@ -230,11 +230,7 @@ int wg_herdt_set_params(wg_ctx *ctx, const wg_herdt_params *params)
 static int herdt_launch(wg_ctx *ctx, HerdtState *st, int B, const wg_herdt_qp_input *d_in, wg_herdt_qp_output *d_out)
 {
   const size_t smem = sizeof(herdt::Work) * QP_WARPS;
-  static bool attr = false;
-  if (!attr) {
-    WG_CUDA(ctx, cudaFuncSetAttribute(herdt_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  WG_SMEM_ATTR(ctx, WG_ATTR_HERDT_QP, herdt_qp_kernel, smem);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   int blocks = (B + QP_WARPS - 1) / QP_WARPS;

@@ -286,11 +286,7 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
     int a_cap = stage ? (int)((pb->dpu_stride + 1) & ~1LL) : 0;
     size_t smem = sizeof(double) * (size_t)a_cap * PLDP_WARPS;
     if (smem > 200 * 1024) { a_cap = 0; smem = 0; }
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      WG_CUDA(ctx, cudaFuncSetAttribute(pldp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem = smem;
-    }
+    WG_SMEM_ATTR(ctx, WG_ATTR_PLDP, pldp_kernel, smem);
     const int per_sm = smem ? (int)((227 * 1024) / (smem + sizeof(PldpWarp) * PLDP_WARPS + 1024)) : 8;
     if (grid > ctx->sm_count * (per_sm > 0 ? per_sm : 1)) grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);
     if (!p->d_next) WG_CUDA(ctx, cudaMalloc(&p->d_next, sizeof(int)));

@@ -29,6 +29,8 @@
 // halo once per tile, 64 B out).
 //
 #include "wg_common.h"
+#include <atomic>
+#include <mutex>
 #include <cstdlib>
 #include <vector>
 #include <cmath>
@@ -230,6 +232,33 @@ struct PreviewConsts {
 };
 __constant__ PreviewConsts c_pc;
 __constant__ double c_F[WG_PREVIEW_MAX_NL + 8];
+
+// The FIR taps are DFMA operands straight from the constant bank (no load instruction in the inner loop), so the gains
+// live in ONE __constant__ block per device, while gains belong to a context.  Every context keeps a host image of the
+// block; preview_bind() (called under g_pv_mutex right before each launch) re-uploads it when the block currently holds
+// another context's gains (or older gains of this one), after draining the device so that no running kernel sees the
+// switch.  Two contexts on one GPU with different gains therefore stay correct; they just do not overlap.
+namespace {
+struct PreviewImage {
+  PreviewConsts pc;
+  double F[WG_PREVIEW_MAX_NL + 8];
+};
+std::mutex g_pv_mutex;
+std::atomic<unsigned long long> g_pv_gen_counter{0};
+unsigned long long g_pv_bound[64];   // generation of the gains held by each device's __constant__ block (0 = none)
+
+int preview_bind(wg_ctx *ctx)
+{
+  if (ctx->device < 0 || ctx->device >= 64) return WG_ERR_INVALID;
+  if (g_pv_bound[ctx->device] == ctx->preview_gen) return WG_OK;
+  const PreviewImage *im = reinterpret_cast<const PreviewImage *>(ctx->preview_image.data());
+  WG_CUDA(ctx, cudaDeviceSynchronize());
+  WG_CUDA(ctx, cudaMemcpyToSymbol(c_pc, &im->pc, sizeof im->pc));
+  WG_CUDA(ctx, cudaMemcpyToSymbol(c_F, im->F, sizeof im->F));
+  g_pv_bound[ctx->device] = ctx->preview_gen;
+  return WG_OK;
+}
+}  // namespace
 
 constexpr int PV_MAX_CHUNKS = 16;
 
@@ -568,15 +597,12 @@ static int preview_launch_shape(wg_ctx *ctx, wg_preview_plan *pl, const int *d_o
   const int span = FIR_R * THREADS + NLpad;
   const size_t smem = sizeof(double2) * (size_t)(span + (span >> 3) + 2);
   if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the FIR tile");
-  static bool attr_set = false;
-  if (!attr_set) {
-    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fused_kernel<true, THREADS, MIN_CTAS>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    WG_CUDA(ctx, cudaFuncSetAttribute(preview_fused_kernel<false, THREADS, MIN_CTAS>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
+  constexpr int slot = WG_ATTR_PREVIEW_0 + (THREADS == 128 ? 0 : THREADS == 32 ? 2 : 4);
+  if (simulation) WG_SMEM_ATTR(ctx, slot, (preview_fused_kernel<true, THREADS, MIN_CTAS>), smem);
+  else WG_SMEM_ATTR(ctx, slot + 1, (preview_fused_kernel<false, THREADS, MIN_CTAS>), smem);
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
+  std::lock_guard<std::mutex> lock(g_pv_mutex);
+  { const int rc = preview_bind(ctx); if (rc != WG_OK) return rc; }
   wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
   if (simulation)
     preview_fused_kernel<true, THREADS, MIN_CTAS><<<count, THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
@@ -594,7 +620,9 @@ int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *g)
   if (!ctx || !g || g->NL <= 0 || g->NL > WG_PREVIEW_MAX_NL) return WG_ERR_INVALID;
   wg_device_guard guard(ctx->device);
   static_assert((FIR_R & (FIR_R - 1)) == 0, "FIR_R must be a power of two");
-  PreviewConsts pc;
+  ctx->preview_image.assign(sizeof(PreviewImage), 0);
+  PreviewImage *im = reinterpret_cast<PreviewImage *>(ctx->preview_image.data());
+  PreviewConsts &pc = im->pc;
   std::memcpy(pc.A, g->A, sizeof pc.A);
   std::memcpy(pc.B, g->B, sizeof pc.B);
   std::memcpy(pc.C, g->C, sizeof pc.C);
@@ -604,12 +632,9 @@ int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *g)
   pc.NLpad = (g->NL + FIR_R - 1) / FIR_R * FIR_R;
   scan_matrices(*g, false, pc.P[0], pc.G[0], pc.H[0]);
   scan_matrices(*g, true, pc.P[1], pc.G[1], pc.H[1]);
-  std::vector<double> F(WG_PREVIEW_MAX_NL + 8, 0.0);
-  std::copy(g->F, g->F + g->NL, F.begin());
-  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  WG_CUDA(ctx, cudaMemcpyToSymbol(c_pc, &pc, sizeof pc));
-  WG_CUDA(ctx, cudaMemcpyToSymbol(c_F, F.data(), sizeof(double) * F.size()));
+  std::copy(g->F, g->F + g->NL, im->F);          // the rest of F stays zero: the FIR runs over NLpad taps
   ctx->preview_gains = *g;
+  ctx->preview_gen = ++g_pv_gen_counter;           // the device block is refreshed lazily by preview_bind()
   ctx->preview_ready = true;
   return WG_OK;
 }
@@ -775,6 +800,64 @@ int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double
   return WG_OK;
 }
 
+}  // extern "C"
+
+// ---- single tick for the class wrappers (PreviewControl::OneIterationOfPreview called once per 5 ms tick) ----
+// One CTA: the 2 x NL window products are reduced over 128 threads, thread 0 then runs the tick in the reference's
+// statement order.  Window, state and results live in ONE mapped pinned host buffer owned by the context (zero copy:
+// the kernel reads 16 NL bytes over PCIe and writes 10 doubles back), so a tick is one launch + one stream
+// synchronisation: no allocation, no plan, no memcpy calls.
+struct PreviewTickBuf {
+  double *h = nullptr;      // pinned, mapped: [2 NLmax window | 8 state | 2 zmp]
+  double *d = nullptr;      // device alias of h
+  int cap_nl = 0;
+};
+
+template <bool SIM>
+__global__ void __launch_bounds__(128)
+preview_tick_kernel(const double2 *__restrict__ win, double *__restrict__ io)
+{
+  __shared__ double2 part[4];
+  const int NL = c_pc.NL, t = threadIdx.x;
+  double fx = 0.0, fy = 0.0;
+  for (int i = t; i < NL; i += 128) {
+    const double2 v = win[i];
+    fx = fma(c_F[i], v.x, fx);
+    fy = fma(c_F[i], v.y, fy);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    fx += __shfl_down_sync(0xffffffffu, fx, d);
+    fy += __shfl_down_sync(0xffffffffu, fy, d);
+  }
+  if ((t & 31) == 0) part[t >> 5] = make_double2(fx, fy);
+  __syncthreads();
+  if (t == 0) {
+    fx = (part[0].x + part[1].x) + (part[2].x + part[3].x);
+    fy = (part[0].y + part[1].y) + (part[2].y + part[3].y);
+    Axis ax, ay;
+    ax.x0 = io[0]; ax.x1 = io[1]; ax.x2 = io[2]; ax.s = io[6];
+    ay.x0 = io[3]; ay.x1 = io[4]; ay.x2 = io[5]; ay.s = io[7];
+    const double2 p0 = win[0];
+    const double zx = preview_tick<SIM>(ax, fx, p0.x);
+    const double zy = preview_tick<SIM>(ay, fy, p0.y);
+    io[0] = ax.x0; io[1] = ax.x1; io[2] = ax.x2; io[6] = ax.s;
+    io[3] = ay.x0; io[4] = ay.x1; io[5] = ay.x2; io[7] = ay.s;
+    io[8] = zx; io[9] = zy;
+  }
+}
+
+extern "C" {
+
+void wg_preview_release(wg_ctx *ctx)
+{
+  PreviewTickBuf *tb = static_cast<PreviewTickBuf *>(ctx->preview_tick);
+  if (!tb) return;
+  if (tb->h) cudaFreeHost(tb->h);
+  delete tb;
+  ctx->preview_tick = nullptr;
+}
+
 int wg_preview_one_iteration(wg_ctx *ctx, double *x, double *y, double *sxzmp, double *syzmp,
                              const double *window_xy, int n_available, double *zmpx2, double *zmpy2,
                              int simulation)
@@ -783,18 +866,33 @@ int wg_preview_one_iteration(wg_ctx *ctx, double *x, double *y, double *sxzmp, d
   if (!ctx->preview_ready) return wg_fail(ctx, WG_ERR_NOT_READY, "wg_preview_set_gains not called");
   const int NL = ctx->preview_gains.NL;
   if (n_available < NL) return wg_fail(ctx, WG_ERR_WINDOW, "ZMPPositions.size()<m_SizeOfPreviewWindow");
-  int64_t offs[2] = {0, NL};
-  wg_preview_plan *pl = nullptr;
-  int rc = wg_preview_plan_create(ctx, 1, offs, &pl);
-  if (rc != WG_OK) return rc;
-  double st[8] = {x[0], x[1], x[2], y[0], y[1], y[2], *sxzmp, *syzmp};
-  std::vector<double> zo(2 * NL);
-  rc = wg_preview_run_batch(ctx, pl, WG_MEM_HOST, window_xy, st, nullptr, zo.data(), simulation);
-  wg_preview_plan_destroy(pl);
-  if (rc != WG_OK) return rc;
-  for (int i = 0; i < 3; ++i) { x[i] = st[i]; y[i] = st[3 + i]; }
-  *sxzmp = st[6]; *syzmp = st[7];
-  *zmpx2 = zo[0]; *zmpy2 = zo[1];
+  wg_device_guard guard(ctx->device);
+  PreviewTickBuf *tb = static_cast<PreviewTickBuf *>(ctx->preview_tick);
+  if (!tb) { tb = new (std::nothrow) PreviewTickBuf(); if (!tb) return WG_ERR_ALLOC; ctx->preview_tick = tb; }
+  if (tb->cap_nl < NL) {
+    if (tb->h) { cudaFreeHost(tb->h); tb->h = nullptr; tb->cap_nl = 0; }
+    WG_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&tb->h), sizeof(double) * (2 * (size_t)NL + 10), cudaHostAllocMapped));
+    WG_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void **>(&tb->d), tb->h, 0));
+    tb->cap_nl = NL;
+  }
+  std::memcpy(tb->h, window_xy, sizeof(double) * 2 * (size_t)NL);
+  double *io = tb->h + 2 * (size_t)tb->cap_nl;
+  for (int i = 0; i < 3; ++i) { io[i] = x[i]; io[3 + i] = y[i]; }
+  io[6] = *sxzmp; io[7] = *syzmp;
+  {
+    std::lock_guard<std::mutex> lock(g_pv_mutex);
+    const int rc = preview_bind(ctx);
+    if (rc != WG_OK) return rc;
+    const double2 *dw = reinterpret_cast<const double2 *>(tb->d);
+    double *dio = tb->d + 2 * (size_t)tb->cap_nl;
+    if (simulation) preview_tick_kernel<true><<<1, 128, 0, ctx->stream>>>(dw, dio);
+    else preview_tick_kernel<false><<<1, 128, 0, ctx->stream>>>(dw, dio);
+    WG_LAUNCHED(ctx);
+  }
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 3; ++i) { x[i] = io[i]; y[i] = io[3 + i]; }
+  *sxzmp = io[6]; *syzmp = io[7];
+  *zmpx2 = io[8]; *zmpy2 = io[9];
   return WG_OK;
 }
 

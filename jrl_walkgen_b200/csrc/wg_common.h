@@ -37,6 +37,9 @@ struct wg_ctx {
   bool preview_ready = false;
   wg_preview_gains_t preview_gains;
   double *d_previewF = nullptr;  // device copy of F padded with zeros
+  std::vector<unsigned char> preview_image;   // host image of the kernels' __constant__ block (PreviewConsts + taps)
+  unsigned long long preview_gen = 0;         // bumped by wg_preview_set_gains
+  void *preview_tick = nullptr;               // buffers of wg_preview_one_iteration (preview.cu)
   // Herdt constants (herdt_qp.cu)
   void *herdt = nullptr;
   // Herdt closed loop (herdt_mpc.cu)
@@ -86,6 +89,19 @@ inline void wg_prof_stop(wg_ctx *ctx)
   cudaEventRecord(p.ev[2 * p.used + 1], ctx->stream);
   p.used++;
 }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE, per-function attribute: keep the largest value set so far
+// per (device, slot) instead of in function-local statics (a second context on another GPU must set it again, a second
+// context on the same GPU must not lower it).  Slots: one per kernel instantiation that needs more than 48 KB.
+enum { WG_ATTR_PREVIEW_0 = 0, /* .. 5: {sim, nosim} x 3 CTA shapes */ WG_ATTR_HERDT_QP = 6, WG_ATTR_HERDT_MPC = 7,
+       WG_ATTR_PLDP = 8, WG_ATTR_PLDP_RANKED = 9, WG_ATTR_ZMPDISC = 10, WG_ATTR_DIMITROV = 11, WG_ATTR_DENSEQP = 12,
+       WG_ATTR_SLOTS = 16 };
+extern "C" int wgi_smem_attr(wg_ctx *ctx, int slot, const void *func, size_t bytes);
+#define WG_SMEM_ATTR(ctx, slot, func, bytes)                                              \
+  do {                                                                                    \
+    int rc__ = wgi_smem_attr((ctx), (slot), reinterpret_cast<const void *>(func), (bytes)); \
+    if (rc__ != WG_OK) return rc__;                                                       \
+  } while (0)
 
 // preview.cu internals used by zmpdisc.cu (the footsteps -> CoM pipeline): launch the fused preview kernel over `count`
 // trajectories listed in the device array d_order.

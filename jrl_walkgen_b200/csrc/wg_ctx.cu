@@ -1,10 +1,30 @@
 // wg_ctx.cu - context, memory and timing entry points of the C ABI (include/walkgen_b200.h).
 #include "wg_common.h"
 
+extern "C" void wg_preview_release(wg_ctx *ctx);
 extern void wg_herdt_release(wg_ctx *ctx);
 extern void wg_herdt_mpc_release(wg_ctx *ctx);
 extern void wg_pldp_release(wg_ctx *ctx);
 extern void wg_dimitrov_release(wg_ctx *ctx);
+
+#include <mutex>
+
+namespace {
+std::mutex g_attr_mutex;
+size_t g_attr_smem[64][WG_ATTR_SLOTS];   // zero-initialised: largest dynamic shared memory size set per (device, slot)
+}
+
+extern "C" int wgi_smem_attr(wg_ctx *ctx, int slot, const void *func, size_t bytes)
+{
+  if (bytes <= 48 * 1024) return WG_OK;   // the default limit needs no opt-in
+  if (ctx->device < 0 || ctx->device >= 64 || slot < 0 || slot >= WG_ATTR_SLOTS) return WG_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  if (bytes > g_attr_smem[ctx->device][slot]) {
+    WG_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    g_attr_smem[ctx->device][slot] = bytes;
+  }
+  return WG_OK;
+}
 
 extern "C" {
 
@@ -41,6 +61,7 @@ int wg_ctx_destroy(wg_ctx *ctx)
   if (!ctx) return WG_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  wg_preview_release(ctx);
   wg_herdt_mpc_release(ctx);
   wg_herdt_release(ctx);
   wg_dimitrov_release(ctx);

@@ -1,6 +1,8 @@
 // walkgen_host.cpp - implementation of the host-side class mirror (walkgen_host.hh) over the C ABI.
 // No algorithm lives here: every numerical result comes from libwalkgen_b200's CUDA kernels.
 #include "walkgen_host.hh"
+#include <fstream>
+#include <iostream>
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
@@ -124,6 +126,38 @@ void PreviewControl::ComputeOptimalWeights(unsigned int mode)
   if (!(m_SamplingPeriod > 0.0) || !(m_PreviewControlTime > 0.0) || !(m_Zc > 0.0)) return;
   if (wg_preview_gains(m_SamplingPeriod, m_PreviewControlTime, m_Zc, (int)mode, &m_Gains) != WG_OK) return;
   m_SizeOfPreviewWindow = (unsigned)m_Gains.NL;
+  m_Coherent = true;
+  if (g_gains_owner == this) g_gains_owner = nullptr;   // force a reload
+}
+void PreviewControl::ReadPrecomputedFile(std::string aFileName)
+{
+  std::ifstream aif(aFileName.c_str(), std::ifstream::in);
+  if (!aif.is_open()) {
+    std::cerr << "PreviewControl - Unable to open " << aFileName << std::endl;
+    return;
+  }
+  wg_preview_gains_t g;
+  std::memset(&g, 0, sizeof g);
+  aif >> g.zc >> g.T >> g.preview_time;
+  float r;                                    // the reference parses the gains into a float (:157)
+  for (int i = 0; i < 3; ++i) { aif >> r; g.Kx[i] = r; }
+  aif >> r; g.Ks = r;
+  const unsigned NL = (unsigned)(g.preview_time / g.T);
+  if (NL == 0 || NL > WG_PREVIEW_MAX_NL) {
+    std::cerr << "PreviewControl - window of " << NL << " samples not supported" << std::endl;
+    return;
+  }
+  for (unsigned i = 0; i < NL; ++i) { aif >> r; g.F[i] = r; }
+  const double T = g.T;
+  const double A[9] = {1.0, T, T * T / 2.0, 0.0, 1.0, T, 0.0, 0.0, 1.0};
+  std::memcpy(g.A, A, sizeof A);
+  g.B[0] = T * T * T / 6.0; g.B[1] = T * T / 2.0; g.B[2] = T;
+  g.C[0] = 1.0; g.C[1] = 0.0; g.C[2] = -g.zc / 9.81;
+  g.NL = (int)NL;
+  g.mode = (int)m_DefaultWeightComputationMode;
+  m_Gains = g;
+  m_Zc = g.zc; m_SamplingPeriod = g.T; m_PreviewControlTime = g.preview_time;
+  m_SizeOfPreviewWindow = NL;
   m_Coherent = true;
   if (g_gains_owner == this) g_gains_owner = nullptr;   // force a reload
 }

@@ -108,6 +108,9 @@ class PreviewControl : public SimplePlugin {
   PreviewControl(SimplePluginManager *lSPM, unsigned int defaultMode = OptimalControllerSolver::MODE_WITH_INITIALPOS,
                  bool computeWeightsAutomatically = false);
   ~PreviewControl();
+  /* Reads zc, T, preview time, Kx[3], Ks and the NL window weights; like the reference (PreviewControl.cpp:142-196)
+   * every gain goes through a `float`, and an unreadable file only prints to cerr. */
+  void ReadPrecomputedFile(std::string aFileName);
   /* x, y: 3 x 1 CoM state per axis (in/out).  Returns 0; throws std::runtime_error when fewer than the preview window
    * of ZMP positions is available from lindex on (the reference LTHROWs, PreviewControl.cpp:341-344). */
   int OneIterationOfPreview(MAL_MATRIX(&x, double), MAL_MATRIX(&y, double), double &sxzmp, double &syzmp,

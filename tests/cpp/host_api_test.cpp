@@ -6,6 +6,8 @@
 //   host_api_test herdt2010 <out.dat> <nticks> [emergency]
 //   host_api_test preview <out.bin>
 //   host_api_test pldp <in.bin> <out.bin>
+//   host_api_test preview1d <gains.ini> <in.bin> <out.bin>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -183,6 +185,61 @@ static int test_preview(const char *out)
   return worst < 1e-10 ? 0 : 5;
 }
 
+// ---- PreviewControl: ReadPrecomputedFile + both OneIterationOfPreview1D overloads on inputs from a file --------------
+// in.bin : int32 L, ncases; double z[L] (deque overload, run with lindex = k over the whole buffer from a zero state);
+//          then per case int32 Lc, lindex, sim, pad; double x0[3], s0, buf[Lc] (vector overload, one call).
+// out.bin: per deque step x[3], zmp (4 doubles); per case x[3], s, zmp (5 doubles); then one double: mean wall-clock
+//          microseconds of a OneIterationOfPreview call (2-D, per-tick path of the class mirror).
+static int test_preview1d(const char *ini, const char *in, const char *out)
+{
+  SimplePluginManager spm;
+  PreviewControl aPC(&spm, OptimalControllerSolver::MODE_WITHOUT_INITIALPOS, false);
+  aPC.ReadPrecomputedFile(ini);
+  if (!aPC.IsCoherent()) return 1;
+  const unsigned NL = (unsigned)aPC.Gains().NL;
+  std::ifstream f(in, std::ios::binary);
+  int32_t hdr[2];
+  f.read(reinterpret_cast<char *>(hdr), sizeof hdr);
+  std::vector<double> z(hdr[0]);
+  f.read(reinterpret_cast<char *>(z.data()), 8 * z.size());
+  std::ofstream o(out, std::ios::binary);
+  std::deque<double> zq(z.begin(), z.end());
+  MAL_MATRIX_DIM(x, double, 3, 1);
+  double s = 0.0, zz = 0.0;
+  for (unsigned k = 0; k + NL <= zq.size(); ++k) {
+    aPC.OneIterationOfPreview1D(x, s, zq, k, zz, true);
+    const double row[4] = {x(0, 0), x(1, 0), x(2, 0), zz};
+    o.write(reinterpret_cast<const char *>(row), sizeof row);
+  }
+  for (int c = 0; c < hdr[1]; ++c) {
+    int32_t h4[4];
+    f.read(reinterpret_cast<char *>(h4), sizeof h4);
+    double x0s[4];
+    f.read(reinterpret_cast<char *>(x0s), sizeof x0s);
+    std::vector<double> buf(h4[0]);
+    f.read(reinterpret_cast<char *>(buf.data()), 8 * buf.size());
+    MAL_MATRIX_DIM(xc, double, 3, 1);
+    for (int i = 0; i < 3; ++i) xc(i, 0) = x0s[i];
+    double sc = x0s[3], zc = 0.0;
+    aPC.OneIterationOfPreview1D(xc, sc, buf, (unsigned)h4[1], zc, h4[2] != 0);
+    const double row[5] = {xc(0, 0), xc(1, 0), xc(2, 0), sc, zc};
+    o.write(reinterpret_cast<const char *>(row), sizeof row);
+  }
+  // latency of the per-tick path (what a PGI calling the class mirror every 5 ms pays)
+  std::deque<ZMPPosition> zmp(NL + 8);
+  for (unsigned i = 0; i < zmp.size(); ++i) { zmp[i].px = 0.01 * i; zmp[i].py = 0.1; zmp[i].pz = 0; zmp[i].theta = 0; zmp[i].time = 0; zmp[i].stepType = 1; }
+  MAL_MATRIX_DIM(x2, double, 3, 1); MAL_MATRIX_DIM(y2, double, 3, 1);
+  double sx = 0, sy = 0, zx = 0, zy = 0;
+  for (int k = 0; k < 50; ++k) aPC.OneIterationOfPreview(x2, y2, sx, sy, zmp, 0, zx, zy, true);
+  const int reps = 2000;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int k = 0; k < reps; ++k) aPC.OneIterationOfPreview(x2, y2, sx, sy, zmp, k & 7, zx, zy, true);
+  const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+  o.write(reinterpret_cast<const char *>(&us), sizeof us);
+  std::cout << "OneIterationOfPreview per tick: " << us << " us" << std::endl;
+  return 0;
+}
+
 // ---- PLDPSolver: one problem from a file, through the reference's class interface ---------------------------
 static int test_pldp(const char *in, const char *out)
 {
@@ -271,6 +328,7 @@ int main(int argc, char **argv)
     if (what == "optcholesky") return test_optcholesky();
     if (what == "herdt2010" && argc > 3) return test_herdt2010(argv[2], atoi(argv[3]), argc > 4 && std::string(argv[4]) == "emergency");
     if (what == "preview" && argc > 2) return test_preview(argv[2]);
+    if (what == "preview1d" && argc > 4) return test_preview1d(argv[2], argv[3], argv[4]);
     if (what == "pldp" && argc > 3) return test_pldp(argv[2], argv[3]);
     if (what == "dimitrov" && argc > 2) return test_dimitrov(argv[2], argc > 3 && std::string(argv[3]) == "robust");
     std::cerr << "usage: host_api_test optcholesky | herdt2010 out.dat nticks | preview out.bin | pldp in.bin out.bin" << std::endl;

@@ -228,3 +228,48 @@ def test_gpu_one_iteration_vs_reference_object(ctx):
         assert np.abs(x - com_r[k, :3]).max() < 1e-9 and np.abs(y - com_r[k, 3:]).max() < 1e-9
         assert abs(zx - zmp_r[k, 0]) < 1e-9 and abs(zy - zmp_r[k, 1]) < 1e-9
     rp.close()
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_1d_variants_and_precomputed_file_vs_reference_object(tmp_path):
+    """The host class mirror (PreviewControl::ReadPrecomputedFile, OneIterationOfPreview1D deque and vector overloads
+    including the wrap-around branch of PreviewControl.cpp:448-466) driven by tests/cpp/host_api_test.cpp, against the
+    reference object that read the SAME gains file (both parse the gains through `float`)."""
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "tests", "cpp")], check=True)
+    exe = os.path.join(root, "tests", "cpp", "host_api_test")
+    o = ol.OracleGains(0.005, 1.6, 0.814, 1)
+    ini = os.path.join(tmp_path, "gains.ini")
+    pr.write_precomputed_file(ini, 0.814, 0.005, 1.6, o.Kx, o.Ks, o.F)
+    rp = pr.RefPreview(1, False)
+    rp.read_file(ini)
+    rng = np.random.default_rng(31)
+    z = synth_walk(rng, 1200)[:, 0].copy()
+    cases = []
+    for (L, lindex) in ((1500, 0), (1500, 700), (1500, 1180), (320, 0), (320, 1), (320, 137), (320, 319)):
+        for sim in (1, 0):
+            cases.append((L, lindex, sim, rng.normal(scale=0.01, size=3), float(rng.normal(scale=0.01)),
+                          synth_walk(rng, L)[:, 1].copy()))
+    fin = os.path.join(tmp_path, "in.bin"); fout = os.path.join(tmp_path, "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("2i", len(z), len(cases)) + z.tobytes())
+        for (L, lindex, sim, x0, s0, buf) in cases:
+            f.write(struct.pack("4i", L, lindex, sim, 0) + x0.tobytes() + struct.pack("d", s0) + buf.tobytes())
+    r = subprocess.run([exe, "preview1d", ini, fin, fout], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(fout)
+    steps = len(z) - 320 + 1
+    traj = got[:4 * steps].reshape(steps, 4)
+    st4 = np.zeros(4)
+    com_r, zmp_r, steps_r = rp.run_1d_deque(z, st4)
+    assert steps_r == steps
+    assert np.abs(traj[:, :3] - com_r[:steps]).max() < 1e-9 and np.abs(traj[:, 3] - zmp_r[:steps]).max() < 1e-9
+    rows = got[4 * steps:4 * steps + 5 * len(cases)].reshape(len(cases), 5)
+    for row, (L, lindex, sim, x0, s0, buf) in zip(rows, cases):
+        rc, x, s, zz = rp.step_1d_vector(buf, lindex, x0, s0, bool(sim))
+        assert rc == 0
+        assert np.abs(row[:3] - x).max() < 1e-9 and abs(row[3] - s) < 1e-9 and abs(row[4] - zz) < 1e-9, (L, lindex, sim)
+    rp.close()
+    print("class-mirror OneIterationOfPreview latency per tick: %.1f us" % got[-1])
