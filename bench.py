@@ -101,6 +101,17 @@ def reduce_over_ranks(dist, times, units, device="cuda"):
     return [float(v) for v in t], [float(v) for v in u]
 
 
+def ncu_traffic(kernel, walks):
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t[kernel]
+        if int(e.get("walks", walks)) != int(walks):
+            return {"traffic": None}
+        return {"traffic": float(e["dram_bytes_per_launch"]), "traffic_unit": "bytes per launch", "traffic_source": e["source"]}
+    except (OSError, KeyError, ValueError):
+        return {"traffic": None}
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -112,33 +123,118 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_preview_rate(offsets, z, seconds=10.0, threads=None):
-    """Reference CPU path (oracle port in the reference's deque/AoS layout), one walk per thread."""
-    import oracle_lib as ol
-    threads = threads or host_cores()
-    g = ol.OracleGains(0.005, 1.6, 0.814, 1)
+def cpu_preview_rate(offsets, z, seconds=10.0):
+    """cpu_baseline of the main line: the reference arm (below) timed on a bounded sample - whole passes over the first
+    walks of the batch, grown until one pass takes a few seconds."""
     B = len(offsets) - 1
-    # bounded sample: first `nb` walks, grown until the call takes a few seconds
-    nb = min(B, max(threads * 2, 32))
-    n = int(offsets[-1])
-    com = np.zeros((n, 6)); zmp = np.zeros((n, 2))
-    best = None
-    t_used = 0.0
+    cores = host_cores()
+    nb = min(B, max(cores * 4, 64))
     while True:
-        off = offsets[:nb + 1]
-        st = np.zeros((nb, 8))
-        t = time.perf_counter()
-        _, _, steps = ol.oracle_preview_batch(g, off, z, st, threads=threads, out=(com, zmp))
-        dt = time.perf_counter() - t
-        t_used += dt
-        rate = steps / dt
-        best = (rate, steps, nb, dt)
-        if dt >= seconds / 3 or nb >= B or t_used > seconds:
+        arm = ReferencePreviewArm(offsets[:nb + 1], z[:int(offsets[nb])])
+        arm.one_pass()                                     # warm-up: workers start, pin, build their PreviewControl
+        steps, dt = arm.one_pass()
+        arm.close()
+        if dt >= seconds / 3 or nb >= B:
             break
-        nb = min(B, int(nb * max(2.0, (seconds / 3) / max(dt, 1e-3))))
-    return {"value": best[0], "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {best[2]} of {B} walks ({best[1]} preview steps, {best[3]:.2f} s), one walk per thread, "
-                      "oracle port of PreviewControl::OneIterationOfPreview over std::deque<ZMPPosition>"}
+        nb = min(B, int(nb * max(2.0, (seconds / 2) / max(dt, 1e-3))))
+    return {"value": steps / dt, "unit": UNIT, "cores": arm.procs, "kind": arm.kind,
+            "sample": f"first {nb} of {B} walks ({steps} preview steps in {dt:.2f} s); " + arm.describe(nb, steps)}
+
+
+# ---- reference arm: the reference's OWN PreviewControl object code, one process per core ----------------
+_REF_JOB = {}
+
+
+def _ref_worker(i):
+    """Worker i of P (forked: offsets / z are inherited copy-on-write): pins itself to one core on first use, builds its
+    own PreviewControl object of the reference (oracle/_ref) and runs OneIterationOfPreview over walks i, i+P, ...
+    exactly as the reference's caller does (one call at lindex 0 per tick, then pop_front)."""
+    import preview_ref as pr
+    J = _REF_JOB
+    if "rp" not in J:
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            os.sched_setaffinity(0, {cpus[i % len(cpus)]})
+        except (AttributeError, OSError):
+            pass
+        rp = pr.RefPreview(1, False)
+        if J["own_gains"] and pr.lapack_available():
+            rp.compute_weights(0.005, 1.6, 0.814, 1)          # the reference's own dgges_ Riccati solve
+        else:
+            g = J["gains"]
+            rp.set_gains(0.005, 1.6, 0.814, g.Kx, g.Ks, g.F)
+        J["rp"] = rp
+        n = int(J["offsets"][-1])
+        J["com"] = np.zeros((n, 6)); J["zmp"] = np.zeros((n, 2))   # only this worker's rows are ever touched
+    B = len(J["offsets"]) - 1
+    st = np.zeros((B, 8))
+    t = time.perf_counter()
+    steps = J["rp"].run_batch(J["offsets"], J["z"], st, J["com"], J["zmp"], b0=i, b1=B, stride=J["P"])
+    return int(steps), time.perf_counter() - t
+
+
+class ReferencePreviewArm:
+    """bench.py --impl reference and the cpu_baseline leg: PreviewControl::OneIterationOfPreview of the reference
+    (its own source compiled into oracle/_ref; falls back to the oracle port when that library is absent), one walking
+    problem per call chain, one PROCESS per host core (one instance per core)."""
+
+    def __init__(self, offsets, z, procs=None):
+        import multiprocessing as mp
+        import oracle_lib as ol
+        import preview_ref as pr
+        self.procs = procs or host_cores()
+        self.kind = "reference" if pr.lib() is not None else "port"
+        self.offsets, self.z = offsets, z
+        self.gains = ol.OracleGains(0.005, 1.6, 0.814, 1)
+        self.own_gains = False
+        if self.kind == "reference":
+            self.own_gains = pr.lapack_available()
+            _REF_JOB.clear()
+            _REF_JOB.update(offsets=offsets, z=z, P=self.procs, gains=self.gains, own_gains=self.own_gains)
+            self.pool = mp.get_context("fork").Pool(self.procs)
+        else:
+            self.pool = None
+
+    def one_pass(self):
+        """-> (preview steps, wall seconds) of one pass over every walk."""
+        t = time.perf_counter()
+        if self.pool is not None:
+            res = self.pool.map(_ref_worker, range(self.procs), chunksize=1)
+            steps = sum(r[0] for r in res)
+        else:
+            import oracle_lib as ol
+            st = np.zeros((len(self.offsets) - 1, 8))
+            _, _, steps = ol.oracle_preview_batch(self.gains, self.offsets, self.z, st, threads=self.procs, want_out=False)
+        return steps, time.perf_counter() - t
+
+    def describe(self, walks, steps):
+        what = ("the reference's own PreviewControl.cpp object code (oracle/_ref), std::deque<ZMPPosition> popped per tick"
+                if self.kind == "reference" else "oracle port of PreviewControl::OneIterationOfPreview over std::deque<ZMPPosition>")
+        gains = "gains from the reference's own dgges_ Riccati solve" if self.own_gains else "gains from the oracle's Riccati fixed point"
+        return f"each step = all {walks} walks ({steps} preview steps), one process per core pinned with sched_setaffinity; {what}; {gains}"
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.terminate()
+            self.pool.join()
+
+
+def herdt_cpu_inputs(n_sims=48, periods=30, seed=7):
+    """Closed-loop QP inputs for the CPU Herdt leg of the reference arm, generated on the CPU by the oracle's
+    TestHerdt2010 harness (no GPU on this path): n_sims walks under random velocity references (the distribution of
+    BASELINE configs[2]), `periods` QP periods each."""
+    import herdt_oracle as ho
+    rng = np.random.default_rng(seed)
+    ins = []
+    for k in range(n_sims):
+        sim = ho.Sim(textbook=True, logging=True)
+        sim.steps_before_stop(2)
+        sim.vel_ref(float(rng.uniform(-0.2, 0.3)), float(rng.uniform(-0.15, 0.15)), float(rng.uniform(-0.2, 0.2)))
+        for _ in range(20 * periods):
+            sim.tick()
+        ins.append(sim.log()[0].copy())
+        sim.close()
+    return np.concatenate(ins)
 
 
 def run_reference(args):
@@ -148,29 +244,29 @@ def run_reference(args):
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
     from jrl_walkgen_b200 import workloads
     offsets, z = workloads.preview_batch(args.walks, seed=0)
-    cores = host_cores()
-    rates, ms = [], []
-    import oracle_lib as ol
-    g = ol.OracleGains(0.005, 1.6, 0.814, 1)
-    nb = min(args.walks, max(cores * 4, 64))
-    n = int(offsets[nb])
-    com = np.zeros((n, 6)); zmp = np.zeros((n, 2))
-    steps = 0
+    arm = ReferencePreviewArm(offsets, z)
+    ms, steps = [], 0
     for it in range(args.warmup + args.steps):
-        st = np.zeros((nb, 8))
-        t = time.perf_counter()
-        _, _, steps = ol.oracle_preview_batch(g, offsets[:nb + 1], z, st, threads=cores, out=(com, zmp))
-        dt = time.perf_counter() - t
+        steps, dt = arm.one_pass()
         if it >= args.warmup:
-            rates.append(steps / dt); ms.append(dt * 1e3)
+            ms.append(dt * 1e3)
+    arm.close()
     value = float(steps * len(ms) / (sum(ms) * 1e-3))
-    sample = f"each step = first {nb} of {args.walks} walks ({steps} preview steps), one walk per thread"
+    sample = arm.describe(args.walks, steps)
+    herdt = None
+    if not args.no_herdt:
+        qin = herdt_cpu_inputs()
+        herdt = cpu_herdt_rate(qin, seconds=max(2.0, args.cpu_seconds / 2))
+        herdt["workload"] = HERDT_WORKLOAD
+        herdt["inputs"] = f"{len(qin)} closed-loop QPs of 48 oracle walks under random velocity references (CPU-generated)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "walks": args.walks, "NL": 320, "T": 0.005},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "walks_per_gpu": args.walks, "NL": 320, "T": 0.005,
+                       "preview_steps_per_pass_per_gpu": int(steps)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs, "kind": arm.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "herdt": herdt, "herdt_qp_solves_per_s": None if herdt is None else herdt["value"],
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -586,8 +682,13 @@ def dimitrov_leg(ctx, wg, args, rank, want_cpu):
     # one untimed pass with the reference's exact semantics (defaults): how many walks the reference itself would finish
     ctx.dimitrov_set_params(par)
     f_stat = np.zeros(B, dtype=np.int32); f_done = np.zeros(B, dtype=np.int32)
-    ctx._check(ctx.lib.wg_dimitrov_run_batch(ctx.h, plan.h, wg.WG_MEM_HOST, None, None, None, None, None, None,
-                                             f_stat.ctypes.data, f_done.ctypes.data))
+    t_ref_sem = None
+    for rep in range(3):                                  # the last two repetitions are timed (wall clock, sync inside the call)
+        if rep == 1:
+            t_ref_sem = time.perf_counter()
+        ctx._check(ctx.lib.wg_dimitrov_run_batch(ctx.h, plan.h, wg.WG_MEM_HOST, None, None, None, None, None, None,
+                                                 f_stat.ctypes.data, f_done.ctypes.data))
+    t_ref_sem = (time.perf_counter() - t_ref_sem) / 2
     par.cold_restart = 1
     par.merge_duplicate_rows = 1
     ctx.dimitrov_set_params(par)
@@ -638,6 +739,7 @@ def dimitrov_leg(ctx, wg, args, rank, want_cpu):
            "walks_completed": int((status == 0).sum()), "walks_stopped": int((status != 0).sum()),
            "reference_semantics": {"walks_completed": int((f_stat == 0).sum()), "walks_stopped": int((f_stat != 0).sum()),
                                    "qp_periods_before_the_stops": int(f_done.sum()),
+                                   "qp_periods_per_s": float(f_done.sum()) / t_ref_sem, "ms_per_pass": t_ref_sem * 1e3,
                                    "note": "defaults = the reference bit for bit: a walk stops where the reference calls "
                                            "exit(0) (m_tol drift of a hot start) or returns IFAIL (NaN on a duplicated half-plane)"},
            "note": "timed with cold_restart = 1 and merge_duplicate_rows = 1 (both off by default, both outside the "
@@ -689,18 +791,23 @@ def run_cuda(args):
         ctx._check(ctx.lib.wg_memcpy_h2d(ctx.h, ds.ptr, st0.ctypes.data, st0.nbytes))  # reset 256 KB of states
         plan.run(dz, ds, dcom, dzmp, True, mem=wg.WG_MEM_DEVICE)
 
+    # A bench "step" is `passes` passes over the 4096-walk batch (default 72: K = 20 steps time ~1.1 s of kernels, so that
+    # clocks and throttle reasons are sampled under sustained load; one pass alone is 0.77 ms).  Every pass re-reads the
+    # 254 MB input and rewrites the 1.0 GB output, far above the 126 MB L2: nothing is served from cache between passes.
+    passes = max(1, args.passes_per_step)
     for _ in range(max(args.warmup, 3)):
-        one_pass()
+        for _ in range(passes):
+            one_pass()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
     ctx.reset_launches()
-    ctx.prof_begin(4 * args.steps + 8)
+    ctx.prof_begin(passes * args.steps + 8)
     barrier()
     t0 = time.time()
     ctx.timer_start()
-    for _ in range(args.steps):
+    for _ in range(args.steps * passes):
         one_pass()
     ms_total = ctx.timer_stop_ms()
     t1 = time.time()
@@ -712,7 +819,7 @@ def run_cuda(args):
     zp = ctx.pinned(z.shape); zp[:] = z
     stp = ctx.pinned((B, 8))
     comp = ctx.pinned((n, 6)); zmpp = ctx.pinned((n, 2))
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(args.steps, args.e2e_passes)          # ~21 ms per pass: 48 passes time ~1 s
     for _ in range(2):
         stp[:] = 0.0
         plan.run(zp, stp, comp, zmpp, True, mem=wg.WG_MEM_HOST)
@@ -727,10 +834,32 @@ def run_cuda(args):
     h2d = z.nbytes + stp.nbytes
     d2h = comp.nbytes + zmpp.nbytes + stp.nbytes
 
+    # ---- host link probe: what the e2e leg is bounded by.  Every rank copies 256 MB pinned <-> device at the same time
+    # (after a barrier); the per-rank rates are summed over the ranks.  On one GPU this is the PCIe link; at N > 1 the sum
+    # shows whether the box's host side (root complex / host DRAM / virtualised IOMMU path) scales with the GPU count.
+    link = {}
+    nb_probe = 256 << 20
+    dprobe = ctx.alloc(nb_probe)
+    hprobe = ctx.pinned((nb_probe // 8,))
+    hprobe[:] = 1.0
+    for name, fn in (("h2d", lambda: ctx._check(ctx.lib.wg_memcpy_h2d(ctx.h, dprobe.ptr, hprobe.ctypes.data, nb_probe))),
+                     ("d2h", lambda: ctx._check(ctx.lib.wg_memcpy_d2h(ctx.h, hprobe.ctypes.data, dprobe.ptr, nb_probe)))):
+        fn(); ctx.sync()
+        barrier()
+        tp = time.perf_counter()
+        for _ in range(4):
+            fn()
+        ctx.sync()
+        link[name] = 4 * nb_probe / (time.perf_counter() - tp) / 1e9
+    dprobe.free()
+    (_, _), (h2d_sum, d2h_sum) = reduce_over_ranks(dist, [0.0, 0.0], [link["h2d"], link["d2h"]])
+    link = {"h2d_gbs_sum_over_ranks": h2d_sum, "d2h_gbs_sum_over_ranks": d2h_sum, "ranks": world,
+            "how": "4 x 256 MB pinned copies per direction per rank, all ranks at once"}
+
     # ---- max over ranks ----------------------------------------------------------------------
     (ms_total, e2e_s), (total_steps_all,) = reduce_over_ranks(dist, [ms_total, e2e_s], [float(steps_per_pass)])
     ms_per_step = ms_total / args.steps
-    value = total_steps_all / (ms_per_step * 1e-3)
+    value = total_steps_all * passes / (ms_per_step * 1e-3)
     e2e_value = total_steps_all * e2e_steps / e2e_s
     for b_ in (dz, ds, dcom, dzmp):
         b_.free()
@@ -781,7 +910,7 @@ def run_cuda(args):
             dimitrov["walks_per_s"] = w_d / (t_d * 1e-3)
             dimitrov["walks"] = int(w_d)
     sweep = None
-    if args.sweep:
+    if not args.no_sweep:
         sweep = sweep_leg(ctx, wg, args, rank, world, dist)
 
     if rank == 0:
@@ -813,14 +942,13 @@ def run_cuda(args):
                     "peak_source": "measured live: register-resident DFMA chains on all SMs (wg_measure_fp64_peak); "
                                    "MEASURED_PEAKS.json has no FP64 entry",
                     "algorithmic_flop_per_step": fl}
-        roof["hbm_frac_streaming_minimum"] = BYTES_PER_STEP * steps_per_pass / (ms_per_step * 1e-3) / 1e9 / hbm_peak
-        if dom_name == "preview_fused_kernel" and args.walks == 4096:
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this (seeded, deterministic) workload from the
-            # committed `ncu --set full` capture (profiles/r1_v8_ncu_summary.md: 282.5 MB + 884.3 MB); algorithmic bytes of
-            # the same launch: 80 B x 14.5 M steps = 1163 MB, i.e. no wasted re-reads
-            roof["traffic"] = 1166.8e6
-            roof["traffic_unit"] = "bytes per launch"
-            roof["traffic_source"] = "profiles/r1_v8_ncu_summary.md (ncu --set full, same command)"
+        roof["hbm_frac_streaming_minimum"] = BYTES_PER_STEP * steps_per_pass * passes / (ms_per_step * 1e-3) / 1e9 / hbm_peak
+        roof["algorithmic_bytes_per_launch"] = BYTES_PER_STEP * steps_per_pass
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this (seeded, deterministic) workload: not
+        # measurable from inside the process, so it is read from the committed summary of the round's `ncu --set full`
+        # capture of this same command (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); null when
+        # that file has no entry for this kernel and batch size.
+        roof.update(ncu_traffic(dom_name, args.walks))
         cpu = None
         if world == 1:
             subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
@@ -829,13 +957,18 @@ def run_cuda(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "walks_per_gpu": B, "NL": 320, "T": 0.005,
-                           "preview_steps_per_pass_per_gpu": steps_per_pass,
+                           "preview_steps_per_pass_per_gpu": steps_per_pass, "passes_per_step": passes,
                            "l2": "inputs+outputs per pass (%.2f GB) exceed the 126 MB L2" % ((n * 80) / 1e9)},
                 "roofline": roof, "kernels": dict(kern, **(herdt_kern or {})), "fp64_peak_tflops_measured": fp64_peak,
                 "herdt": herdt, "pldp": pldp, "kajita_front_end": kajita, "dimitrov_front_to_back": dimitrov, "sweep": sweep,
+                "herdt_qp_solves_per_s": None if herdt is None else herdt["qp_solves_per_s"],
+                "herdt_qp_solves_per_s_e2e": None if herdt is None else herdt["e2e"]["value"],
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "passes": e2e_steps, "api": "wg_preview_run_batch(WG_MEM_HOST), pinned host buffers"},
+                        "passes": e2e_steps, "api": "wg_preview_run_batch(WG_MEM_HOST), pinned host buffers",
+                        "host_link": link,
+                        "bound": "host link: %.0f B per preview step cross PCIe (16 in, 64 out); at the probed D2H rate the "
+                                 "64 B/step alone cap the leg at %.2f G steps/s" % (BYTES_PER_STEP, d2h_sum / 64.0)},
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     plan.destroy()
@@ -860,7 +993,11 @@ def main():
     ap.add_argument("--no-kajita", action="store_true")
     ap.add_argument("--dimitrov-walks", type=int, default=4096)
     ap.add_argument("--no-dimitrov", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also run BASELINE configs[4]: 1M MPC instances x 100 periods")
+    ap.add_argument("--sweep", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip BASELINE configs[4]: 1M MPC instances x 100 periods")
+    ap.add_argument("--passes-per-step", type=int, default=72,
+                    help="passes over the batch per bench step (timed region = steps x passes x 0.77 ms)")
+    ap.add_argument("--e2e-passes", type=int, default=48)
     ap.add_argument("--sweep-instances", type=int, default=1000000)
     ap.add_argument("--sweep-periods", type=int, default=100)
     args = ap.parse_args()

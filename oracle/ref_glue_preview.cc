@@ -220,6 +220,26 @@ long ref_preview_run(void *h, const double *zmpref_xy, long L, double *state8, d
   return steps;
 }
 
+/* The same over walks [b0, b1) of a ragged batch (bench.py --impl reference: the reference's own per-tick call in
+ * its own data layout, one walk after the other): offsets [B+1], zmpref_xy [offsets[B]][2], state [B][8],
+ * com_out [offsets[B]][6] / zmp_out [offsets[B]][2] (row offsets[b]+k = step k of walk b) or NULL.
+ * Walks b0, b0+stride, ... are processed.  Returns the number of preview steps, or -1. */
+long ref_preview_run_batch(void *h, int b0, int b1, int stride, const long long *offsets, const double *zmpref_xy,
+                           double *state, double *com_out, double *zmp_out, int simulation)
+{
+  long total = 0;
+  for (int b = b0; b < b1; b += stride) {
+    const long long o = offsets[b];
+    const long L = (long)(offsets[b + 1] - o);
+    if (L < (long)static_cast<RefPreview *>(h)->pc->m_SizeOfPreviewWindow) continue;
+    const long n = ref_preview_run(h, zmpref_xy + 2 * o, L, state + 8 * (long)b, com_out ? com_out + 6 * o : 0,
+                                   zmp_out ? zmp_out + 2 * o : 0, simulation, 0);
+    if (n < 0) return -1;
+    total += n;
+  }
+  return total;
+}
+
 /* OneIterationOfPreview1D, deque<double> overload (:376-421), iterated with lindex = k. */
 long ref_preview_run_1d_deque(void *h, const double *zmpref, long L, double *state4, double *com_out, double *zmp_out,
                               int simulation)

@@ -37,30 +37,58 @@ template <typename T> class vector {
 };
 
 template <typename T> class matrix {
+  /* up to 16 elements live inside the object: the 3x3 / 3x1 / 1x1 temporaries of the preview recursion then cost no
+   * heap allocation (uBLAS' unbounded_array would new[] each of them; the stand-in must not make the reference's
+   * per-tick call slower than it is) */
+  enum { INLINE = 16 };
  public:
-  matrix() : r_(0), c_(0) {}
-  matrix(std::size_t r, std::size_t c) : r_(r), c_(c), d_(r * c, T()) {}
+  matrix() : r_(0), c_(0), p_(in_) {}
+  matrix(std::size_t r, std::size_t c) : r_(0), c_(0), p_(in_) { alloc(r, c); }
+  matrix(const matrix &o) : r_(0), c_(0), p_(in_) { *this = o; }
+  matrix &operator=(const matrix &o)
+  {
+    if (this != &o) {
+      if (o.r_ * o.c_ != r_ * c_) alloc_raw(o.r_, o.c_);
+      r_ = o.r_; c_ = o.c_;
+      for (std::size_t i = 0; i < r_ * c_; ++i) p_[i] = o.p_[i];
+    }
+    return *this;
+  }
   void resize(std::size_t r, std::size_t c)
   {
-    std::vector<T> n(r * c, T());
+    if (r == r_ && c == c_) return;
+    matrix n(r, c);
     for (std::size_t i = 0; i < r && i < r_; ++i)
-      for (std::size_t j = 0; j < c && j < c_; ++j) n[i * c + j] = d_[i * c_ + j];
-    d_.swap(n); r_ = r; c_ = c;
+      for (std::size_t j = 0; j < c && j < c_; ++j) n(i, j) = (*this)(i, j);
+    *this = n;
   }
   std::size_t size1() const { return r_; }
   std::size_t size2() const { return c_; }
-  T &operator()(std::size_t i, std::size_t j) { return d_[i * c_ + j]; }
-  const T &operator()(std::size_t i, std::size_t j) const { return d_[i * c_ + j]; }
-  T *data() { return d_.empty() ? 0 : &d_[0]; }
-  void fill(T v) { for (std::size_t i = 0; i < d_.size(); ++i) d_[i] = v; }
+  T &operator()(std::size_t i, std::size_t j) { return p_[i * c_ + j]; }
+  const T &operator()(std::size_t i, std::size_t j) const { return p_[i * c_ + j]; }
+  T *data() { return r_ * c_ ? p_ : 0; }
+  void fill(T v) { for (std::size_t i = 0; i < r_ * c_; ++i) p_[i] = v; }
   void set_identity()
   {
     for (std::size_t i = 0; i < r_; ++i)
       for (std::size_t j = 0; j < c_; ++j) (*this)(i, j) = (i == j) ? T(1) : T(0);
   }
  private:
+  void alloc_raw(std::size_t r, std::size_t c)
+  {
+    if (r * c <= INLINE) { heap_.clear(); p_ = in_; }
+    else { heap_.assign(r * c, T()); p_ = &heap_[0]; }
+  }
+  void alloc(std::size_t r, std::size_t c)
+  {
+    alloc_raw(r, c);
+    r_ = r; c_ = c;
+    for (std::size_t i = 0; i < r * c; ++i) p_[i] = T();
+  }
   std::size_t r_, c_;
-  std::vector<T> d_;
+  T in_[INLINE];
+  std::vector<T> heap_;
+  T *p_;
 };
 
 /* prod(matrix, matrix): element (i,j) = 0 + sum_k a(i,k)*b(k,j), k ascending */

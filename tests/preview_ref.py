@@ -32,6 +32,8 @@ def lib():
         r.ref_preview_set_gains.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, D, C.c_double, D, C.c_int]
         r.ref_preview_run.restype = C.c_long
         r.ref_preview_run.argtypes = [C.c_void_p, D, C.c_long, D, D, D, C.c_int, C.c_int]
+        r.ref_preview_run_batch.restype = C.c_long
+        r.ref_preview_run_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, ol.I64, D, D, D, D, C.c_int]
         r.ref_preview_run_1d_deque.restype = C.c_long
         r.ref_preview_run_1d_deque.argtypes = [C.c_void_p, D, C.c_long, D, D, D, C.c_int]
         r.ref_preview_step_1d_vector.restype = C.c_int
@@ -102,6 +104,12 @@ class RefPreview:
         steps = self.r.ref_preview_run(self.h, ol.dptr(z), L, ol.dptr(state8), ol.dptr(com), ol.dptr(zmp), int(simulation),
                                        int(use_lindex))
         return com, zmp, steps
+
+    def run_batch(self, offsets, zmpref_xy, state, com, zmp, b0=0, b1=None, stride=1, simulation=True):
+        """Walks b0, b0+stride, ... < b1 of a ragged batch; outputs in place.  Returns the number of preview steps."""
+        b1 = len(offsets) - 1 if b1 is None else b1
+        return self.r.ref_preview_run_batch(self.h, b0, b1, stride, offsets.ctypes.data_as(ol.I64), ol.dptr(zmpref_xy),
+                                            ol.dptr(state), ol.dptr(com), ol.dptr(zmp), int(simulation))
 
     def run_1d_deque(self, zmpref, state4, simulation=True):
         z = np.ascontiguousarray(zmpref, dtype=np.float64)
