@@ -189,6 +189,7 @@ def pldp_problem_from(K: DimitrovConstants, polys, xk):
     zref = np.zeros(2 * N)
     DPu = np.zeros((2 * N, m + 1))              # column-major storage: DPu[c, r] is element (r, c)
     DPx = np.zeros(m)
+    a01 = np.zeros((m, 2)); ri = np.zeros(m, dtype=np.uint8); sim = np.zeros(m, dtype=np.int32)
     r = 0
     for i, (cen, rows) in enumerate(polys):
         zref[i], zref[i + N] = cen
@@ -198,10 +199,14 @@ def pldp_problem_from(K: DimitrovConstants, polys, xk):
             DPx[r] = zx * a0 + zy * a1 + b
             DPu[:N, r] = a0 * K.Pu[:, i]
             DPu[N:, r] = a1 * K.Pu[:, i]
+            a01[r] = (a0, a1); ri[r] = i
+            # rows come in exactly negated pairs (n, -n): the odd row of a pair is flagged, SimilarConstraints-style
+            if r > 0 and ri[r - 1] == i and a01[r - 1, 0] == -a0 and a01[r - 1, 1] == -a1 and sim[r - 1] == 0:
+                sim[r] = -1
             r += 1
     D = np.concatenate([K.OptB @ xk[:3] - K.OptC @ zref[:N], K.OptB @ xk[3:] - K.OptC @ zref[N:]])
     return {"D": D, "m": m, "DPu": DPu.ravel(), "DPx": DPx, "ZMPRef": zref, "XkYk": np.array(xk, dtype=np.float64),
-            "n_first": len(polys[0][1])}
+            "n_first": len(polys[0][1]), "a01": a01, "ri": ri, "similar": sim}
 
 
 def pldp_problem(K: DimitrovConstants, rng):
@@ -232,10 +237,15 @@ def pldp_pack(K, probs):
     out = {"D": np.stack([p["D"] for p in probs]), "m": np.array([p["m"] for p in probs], dtype=np.int32),
            "DPu": np.zeros((B, dpu_stride)), "DPx": np.zeros((B, mmax)),
            "ZMPRef": np.stack([p["ZMPRef"] for p in probs]), "XkYk": np.stack([p["XkYk"] for p in probs]),
-           "dpu_stride": dpu_stride, "dpx_stride": mmax}
+           "dpu_stride": dpu_stride, "dpx_stride": mmax,
+           # the same matrices in rank-structured form (wg_pldp_solve_batch_ranked): row r = (A_r(0), A_r(1), sample i_r),
+           # element (r, k + 16 ax) = A_r(ax) * Pu[k][i_r]; and SimilarConstraints-style flags
+           "a01": np.zeros((B, 128, 2)), "ri": np.zeros((B, 128), dtype=np.uint8),
+           "similar": np.zeros((B, 128), dtype=np.int32)}
     for b, p in enumerate(probs):
         out["DPu"][b, :len(p["DPu"])] = p["DPu"]
         out["DPx"][b, :p["m"]] = p["DPx"]
+        out["a01"][b, :p["m"]] = p["a01"]; out["ri"][b, :p["m"]] = p["ri"]; out["similar"][b, :p["m"]] = p["similar"]
     return out
 
 

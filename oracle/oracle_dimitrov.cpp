@@ -27,6 +27,10 @@
 
 #include "../include/walkgen_b200.h"
 
+extern "C" int oracle_pldp_solve_sim(int N, const double *iPu, const double *Px, const double *Pu, const double *D, int m,
+                                     const double *A, const double *b, const double *ZMPRef, const double *XkYk, double *X,
+                                     int n_removed, int starting, void *hot, int hot_start, int max_iter, int *info,
+                                     int *active_out, const int *similar);
 extern "C" int oracle_pldp_solve(int N, const double *iPu, const double *Px, const double *Pu, const double *D, int m,
                                  const double *DPu, const double *DPx, const double *ZMPRef, const double *XkYk,
                                  double *X, int n_removed, int starting, void *hot, int hot_start, int max_iter,
@@ -388,6 +392,26 @@ int oracle_dimitrov_build_constraints(int N, double T, double StartingTime, int 
   return (int)m;
 }
 
+/* m_SimilarConstraints as BuildConstraintMatrices fills it (:889): the SimilarConstraints of the polygon of each previewed
+ * sample, row by row, for the same polygon walk as oracle_dimitrov_build_constraints.  Returns m. */
+int oracle_dimitrov_similar(int N, double T, double StartingTime, int np, const wg_lci *lci, int *similar)
+{
+  int it = 0;
+  while (it < np) {
+    if (StartingTime >= lci[it].t_start && StartingTime <= lci[it].t_end) break;
+    ++it;
+  }
+  if (it == np) return -1;
+  int r = 0;
+  for (int i = 0; i < N; ++i) {
+    const double ltime = StartingTime + i * T;
+    if (ltime > lci[it].t_end) ++it;
+    if (it == np) return -3;
+    for (int j = 0; j < lci[it].rows; ++j) similar[r++] = lci[it].similar[j];
+  }
+  return r;
+}
+
 /* number of periods of the loop `for (StartingTime = 0; StartingTime < EndingTime - N*T; StartingTime += T)` for a
  * feet buffer of n samples whose clock is the sampling period accumulated sample by sample */
 long oracle_dimitrov_period_count(int N, double T, double Ts, long n)
@@ -434,15 +458,19 @@ long oracle_dimitrov_run(const wg_dimitrov_params *par, long n, const double *le
                                                     K.OptC.data(), xk, DPu.data(), DPx.data(), ZMPRef.data(), D.data(), first);
     if (m < 0) return -2;
     int info[4], act[32];
-    int rc = oracle_pldp_solve(N, K.iPu.data(), K.Px.data(), K.Pu.data(), D.data(), m, DPu.data(), DPx.data(),
-                               ZMPRef.data(), xk, X.data(), (int)removed, starting ? 1 : 0, &hot, use_hot_start,
-                               max_iter, info, act);
+    /* m_SimilarConstraints is handed to the solver as the reference does (:1336); the reuse it enables is bit-neutral
+     * for these flags (the flagged row is the exact negation of the row it points to) */
+    int similar[8 * 16];
+    oracle_dimitrov_similar(N, T, ST, np, lci.data(), similar);
+    int rc = oracle_pldp_solve_sim(N, K.iPu.data(), K.Px.data(), K.Pu.data(), D.data(), m, DPu.data(), DPx.data(),
+                                   ZMPRef.data(), xk, X.data(), (int)removed, starting ? 1 : 0, &hot, use_hot_start,
+                                   max_iter, info, act, similar);
     if ((info[1] == 1 || info[1] == 2) && par->cold_restart) {
       /* the reference prints "PB ON constraint" and calls exit(0) here; cold_restart solves the period again from the
        * cold start point (StartingSequence = true, no kept constraints) */
       hot.n_prev = 0;
-      rc = oracle_pldp_solve(N, K.iPu.data(), K.Px.data(), K.Pu.data(), D.data(), m, DPu.data(), DPx.data(),
-                             ZMPRef.data(), xk, X.data(), 0, 1, &hot, use_hot_start, max_iter, info, act);
+      rc = oracle_pldp_solve_sim(N, K.iPu.data(), K.Px.data(), K.Pu.data(), D.data(), m, DPu.data(), DPx.data(),
+                                 ZMPRef.data(), xk, X.data(), 0, 1, &hot, use_hot_start, max_iter, info, act, similar);
       if (info[1] == 0) info[1] = 5;
     }
     starting = false;

@@ -89,11 +89,17 @@ struct OraclePldpState {
   int pad_;
 };
 
-/* One SolveProblem.  info[0..3] = rc, status, iterations, n_active; active[32]. */
-int oracle_pldp_solve(int N, const double *iPu, const double *Px, const double *Pu, const double *D, int m,
-                      const double *A, const double *b, const double *ZMPRef, const double *XkYk, double *X,
-                      int n_removed, int starting, OraclePldpState *hot, int hot_start, int max_iter, int *info,
-                      int *active_out)
+/* One SolveProblem.  info[0..3] = rc, status, iterations, n_active; active[32].
+ * similar: SimilarConstraints [m] or NULL.  ComputeAlpha's reuse (PLDPSolver.cpp:570-590) is restated as written:
+ * m_ConstraintsValueComputed[li] is reset when row li is visited and set once its product is formed, so a flag that
+ * points BACKWARD (li + similar[li] < li: the only kind FindSimilarConstraints produces, -2 / -3) reuses -tmp1 of that row
+ * iff the row is not active; the second reuse (:600-610) tests m_ConstraintsValueComputed[lindex + m], which nothing ever
+ * sets, and is dead code.  A flag pointing forward would read the flag array as the PREVIOUS ComputeAlpha call left it
+ * (uninitialised memory on the first one): status 6 here. */
+int oracle_pldp_solve_sim(int N, const double *iPu, const double *Px, const double *Pu, const double *D, int m,
+                          const double *A, const double *b, const double *ZMPRef, const double *XkYk, double *X,
+                          int n_removed, int starting, OraclePldpState *hot, int hot_start, int max_iter, int *info,
+                          int *active_out, const int *similar)
 {
   const int U = 2 * N, ld = m + 1;
   const double tol = 1e-8;
@@ -132,6 +138,7 @@ int oracle_pldp_solve(int N, const double *iPu, const double *Px, const double *
   int it = 0;
   bool cont = true;
   size_t kproj = 0;
+  std::vector<char> computed(2 * (size_t)m + 2, 0);
   while (cont) {
     for (int i = 0; i < U; ++i) c[i] = -D[i] - Vk[i];
     const size_t k = act.size();
@@ -159,19 +166,35 @@ int oracle_pldp_solve(int N, const double *iPu, const double *Px, const double *
     unsigned which = 0;
     for (int li = 0; li < m; ++li) {
       bool found = false;
+      computed[li] = 0; computed[li + m] = 0;
       for (size_t q = 0; q < k; ++q) if ((int)act[q] == li) { found = true; break; }
       if (found) continue;
       tmp1[li] = 0.0;
-      for (int lj = 0; lj < U; ++lj) tmp1[li] += A[li + (long)lj * ld] * d[lj];
+      bool tbc = true;
+      if (similar && similar[li] != 0) {
+        const int lindex = li + similar[li];
+        if (lindex < 0 || lindex >= li) { status = 6; cont = false; break; }
+        if (computed[lindex]) { tmp1[li] = -tmp1[lindex]; tbc = false; }
+      }
+      if (tbc)
+        for (int lj = 0; lj < U; ++lj) tmp1[li] += A[li + (long)lj * ld] * d[lj];
+      computed[li] = 1;
       if (tmp1[li] < 0.0) {
         tmp2[li] = -b[li];
-        for (int lj = 0; lj < U; ++lj) tmp2[li] -= A[li + (long)lj * ld] * Vk[lj];
+        tbc = true;
+        if (similar && similar[li] != 0 && computed[li + similar[li] + m]) {   /* never true, :600-610 */
+          tmp2[li] += -tmp2[li + similar[li]] - b[li + similar[li]];
+          tbc = false;
+        }
+        if (tbc)
+          for (int lj = 0; lj < U; ++lj) tmp2[li] -= A[li + (long)lj * ld] * Vk[lj];
         if (tmp2[li] > tol) status = status > 1 ? status : 1;
         else if (tmp2[li] > 0.0) tmp2[li] = -tol;
         double la = tmp2[li] / tmp1[li];
         if (Alpha > la) { Alpha = la; if (Alpha < 1) { toadd = true; which = li; } }
       }
     }
+    if (status == 6) break;
     double alpha = Alpha;
     if (alpha >= 1.0) { alpha = 1.0; cont = false; }
     if (alpha < 0.0) { status = 2; cont = false; }
@@ -198,6 +221,15 @@ int oracle_pldp_solve(int N, const double *iPu, const double *Px, const double *
   if (info) { info[0] = rc; info[1] = status; info[2] = it; info[3] = (int)act.size(); }
   if (active_out) for (int i = 0; i < 32; ++i) active_out[i] = i < (int)act.size() ? (int)act[i] : -1;
   return rc;
+}
+
+int oracle_pldp_solve(int N, const double *iPu, const double *Px, const double *Pu, const double *D, int m,
+                      const double *A, const double *b, const double *ZMPRef, const double *XkYk, double *X,
+                      int n_removed, int starting, OraclePldpState *hot, int hot_start, int max_iter, int *info,
+                      int *active_out)
+{
+  return oracle_pldp_solve_sim(N, iPu, Px, Pu, D, m, A, b, ZMPRef, XkYk, X, n_removed, starting, hot, hot_start, max_iter,
+                               info, active_out, nullptr);
 }
 
 /* B cold-start problems back to back (CPU-baseline loop of bench.py: no Python in the timed region). */

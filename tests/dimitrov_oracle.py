@@ -115,6 +115,17 @@ def build_constraints(K, lci, t_start, xk):
             "n_first": int(first[1]), "first": int(first[0])}
 
 
+def similar_flags(K, lci, t_start):
+    """m_SimilarConstraints for the period starting at t_start (ZMPConstrainedQPFastFormulation.cpp:889)."""
+    sim = np.zeros(8 * K.N, dtype=np.int32)
+    lci = np.ascontiguousarray(lci)
+    m = ol.oracle().oracle_dimitrov_similar(K.N, C.c_double(K.T), C.c_double(t_start), len(lci), C.c_void_p(lci.ctypes.data),
+                                            C.c_void_p(sim.ctypes.data))
+    if m < 0:
+        raise RuntimeError(f"similar_flags: {m}")
+    return sim, m
+
+
 def period_count(n, par=None):
     par = par or default_params()
     f = ol.oracle().oracle_dimitrov_period_count

@@ -18,6 +18,8 @@ def lib():
         L.oracle_pldp_solve.restype = C.c_int
         L.oracle_pldp_solve.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int,
                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_pldp_solve_sim.restype = C.c_int
+        L.oracle_pldp_solve_sim.argtypes = L.oracle_pldp_solve.argtypes + [C.c_void_p]
         L.oracle_optcholesky_add_rows.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_optcholesky_full.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_optcholesky_inverse.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -25,15 +27,17 @@ def lib():
     return L
 
 
-def oracle_solve(K, pb, b, hot=None, hot_start=True, starting=True, n_removed=0, max_iter=128):
+def oracle_solve(K, pb, b, hot=None, hot_start=True, starting=True, n_removed=0, max_iter=128, similar=None):
     """One SolveProblem by the oracle port.  -> (X[32], info[4], active[32])."""
+    sim = None if similar is None else np.ascontiguousarray(similar, dtype=np.int32)
     X = np.zeros(32); info = np.zeros(4, dtype=np.int32); act = np.zeros(32, dtype=np.int32)
     m = int(pb["m"][b])
     A = np.ascontiguousarray(pb["DPu"][b]); bb = np.ascontiguousarray(pb["DPx"][b])
-    lib().oracle_pldp_solve(16, K.iPu.ctypes.data, K.Px.ctypes.data, K.Pu.ctypes.data, pb["D"][b].ctypes.data, m,
-                            A.ctypes.data, bb.ctypes.data, pb["ZMPRef"][b].ctypes.data, pb["XkYk"][b].ctypes.data,
-                            X.ctypes.data, int(n_removed), int(starting), None if hot is None else hot.ctypes.data,
-                            int(hot_start), max_iter, info.ctypes.data, act.ctypes.data)
+    lib().oracle_pldp_solve_sim(16, K.iPu.ctypes.data, K.Px.ctypes.data, K.Pu.ctypes.data, pb["D"][b].ctypes.data, m,
+                                A.ctypes.data, bb.ctypes.data, pb["ZMPRef"][b].ctypes.data, pb["XkYk"][b].ctypes.data,
+                                X.ctypes.data, int(n_removed), int(starting), None if hot is None else hot.ctypes.data,
+                                int(hot_start), max_iter, info.ctypes.data, act.ctypes.data,
+                                None if sim is None else sim.ctypes.data)
     return X, info, act
 
 

@@ -145,6 +145,30 @@ def test_oracle_loop_equals_the_loop_driven_through_the_reference_pldp_object():
     ref.close()
 
 
+@needs_ref
+@pytest.mark.parametrize("name", PROFILES)
+def test_oracle_loop_equals_reference_pldp_object_with_real_similar_flags_whole_walks(name):
+    """Every period of all four TestKajita2003 profiles (843 periods) through the reference's PLDPSolver object fed with
+    the REAL m_SimilarConstraints of the reference's FootConstraintsAsLinearSystem object code, cold_restart on both
+    sides (a fresh solver object where the oracle re-solves from the cold start point): jerks bitwise equal, and where
+    the oracle stops on NaN (duplicated half-plane) the reference's SolveProblem returns -1 as well.  Runs in a
+    subprocess: a reference exit(0) must not end pytest."""
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "dimitrov_ref_loop.py"), name], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["done"] and res["flagged_rows"] > 1000
+    expect = {"StraightWalking": (185, None), "Circle": (55, 55), "PbFlorentSeq1": (147, 147), "PbFlorentSeq2": (456, 456)}[name]
+    assert (res["compared"], res["failed_at"]) == expect
+    assert res["restarts"] >= 2
+    if res["failed_at"] is not None:
+        assert res["ref_rc_at_stop"] == -1
+
+
 def test_oracle_loop_stops_like_the_reference_on_duplicated_hull_rows():
     """FINDING: for rotated parallel feet the reference's hull keeps collinear corners (the cross product is not exactly
     0), the final double-support polygon then carries the same half-plane twice, and as soon as both copies are active

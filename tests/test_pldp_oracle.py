@@ -105,6 +105,42 @@ def test_oracle_pldp_equals_reference_object_code_cold_and_hot():
     assert kept > 0                                                 # the hot start did carry constraints over
 
 
+def test_oracle_pldp_similar_constraints_semantics_equal_reference_object_code():
+    """ComputeAlpha's `A_j = -A_i` reuse (PLDPSolver.cpp:570-590) driven by SimilarConstraints.
+    (a) flags consistent with the matrix (row li is the exact negation of row li + similar[li], as FindSimilarConstraints
+        guarantees): reference object == oracle with the flags == oracle without them, bitwise - the reuse is bit-neutral;
+    (b) backward flags that do NOT match the matrix: the reference reuses -tmp1 of the other row anyway; the oracle
+        restates that exactly (bitwise equal X and activation order), and the result differs from the flag-less solve."""
+    if ol.ref() is None:
+        pytest.skip("oracle/_ref not built on this machine")
+    K, pb = W.pldp_batch(24, seed=11)
+    differ = 0
+    for b in range(24):
+        m = int(pb["m"][b])
+        sim_ok = np.ascontiguousarray(pb["similar"][b])
+        assert (sim_ok[:m] != 0).sum() == m // 2
+        X0, i0, a0 = po.oracle_solve(K, pb, b, starting=True)
+        X1, i1, a1 = po.oracle_solve(K, pb, b, starting=True, similar=sim_ok)
+        ref = po.RefPLDP(K); rc, Xr = ref.solve(pb, b, starting=True, similar=sim_ok); ref.close()
+        assert rc == 0 and np.array_equal(X1, Xr) and np.array_equal(X0, X1) and np.array_equal(a0, a1)
+        rng = np.random.default_rng([11, b])
+        sim_bad = np.zeros(128, dtype=np.int32)
+        for li in range(1, m):
+            if rng.random() < 0.3:
+                sim_bad[li] = -int(rng.integers(1, min(li, 5) + 1))
+        X2, i2, a2 = po.oracle_solve(K, pb, b, starting=True, similar=sim_bad)
+        if i2[1] != 0:
+            continue          # a wrong reuse can drive the step length negative: the reference would exit(0) - and take
+                              # the test process with it - so it is only called where the oracle predicts a clean solve
+        ref = po.RefPLDP(K); rc, Xr2 = ref.solve(pb, b, starting=True, similar=sim_bad); ref.close()
+        assert np.array_equal(X2, Xr2, equal_nan=True) and rc == i2[0], (b, np.abs(X2 - Xr2).max())
+        differ += int(not np.array_equal(X2, X0))
+    assert differ >= 2
+    # forward / out-of-range flags: the reference reads stale or uninitialised memory; the oracle refuses (status 6)
+    sim_fwd = np.zeros(128, dtype=np.int32); sim_fwd[0] = 2
+    assert po.oracle_solve(K, pb, 0, starting=True, similar=sim_fwd)[1][1] == 6
+
+
 def test_oracle_pldp_solution_is_the_constrained_optimum():
     """Property: X minimises 1/2 |v|^2 + D.v over {A v + b >= 0}: feasibility and KKT with multipliers -v2 >= 0."""
     K, pb = W.pldp_batch(30, seed=5)
