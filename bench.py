@@ -570,62 +570,78 @@ def cpu_pldp_rate(pb, seconds=5.0, procs=None):
 
 
 def pldp_leg(ctx, wg, args, rank, fp64_peak, want_cpu):
+    """configs[3]: 16 384 DISTINCT cold-started constrained CoP QPs, through both entry points: wg_pldp_solve_batch (the
+    dense (m+1) x 32 matrix the reference hands to SolveProblem) and wg_pldp_solve_batch_ranked (rows as (A_r(0), A_r(1),
+    i_r): the structure every reference call has); results are bitwise equal (tests/test_pldp_gpu.py)."""
     from jrl_walkgen_b200 import workloads
     B = args.pldp_instances
-    distinct = min(B, 2048)
-    K, small = workloads.pldp_batch(distinct, seed=100 + rank)
-    reps = -(-B // distinct)
-    pb = {k: (np.tile(v, (reps,) + (1,) * (v.ndim - 1))[:B] if isinstance(v, np.ndarray) else v) for k, v in small.items()}
+    K, pb = workloads.pldp_batch(B, seed=100 + rank)
+    small = {k: (v[:2048] if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
     ctx.pldp_set_constants(K.iPu, K.Px, K.Pu)
     dev = {k: (ctx.to_device(v) if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
     dX = ctx.alloc(B * 32 * 8); dinfo = ctx.alloc(B * wg.PLDP_INFO_DTYPE.itemsize)
-    for _ in range(3):
-        ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=B, X=dX, info=dinfo)
-    ctx.sync()
-    ctx.prof_begin(args.steps + 4)
-    for _ in range(args.steps):
-        ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=B, X=dX, info=dinfo)
-    prof = ctx.prof_end()
-    ms = prof[4][1] / prof[4][0]
+    d_flush = ctx.alloc(256 << 20)
+    ms = {}
+    for ranked in (False, True):
+        for _ in range(3):
+            ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=B, X=dX, info=dinfo, ranked=ranked)
+        ctx.sync()
+        ctx.prof_begin(args.steps + 4)
+        for _ in range(args.steps):
+            ctx._check(ctx.lib.wg_memset_device(ctx.h, d_flush.ptr, 0, 256 << 20))      # L2 flush between launches
+            ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=B, X=dX, info=dinfo, ranked=ranked)
+        prof = ctx.prof_end()
+        ms[ranked] = prof[4][1] / prof[4][0]
     info = dinfo.download(wg.PLDP_INFO_DTYPE, (B,))
     it = info["iterations"].astype(np.float64); k = info["n_active"].astype(np.float64); m = pb["m"].astype(np.float64)
     u = 32.0
     # SURVEY 8d: F = 2u^2 (v0) + I (2 k u 2 + 2 k^2 + 2 m u) + sum_k (2 k u + k^2); k averaged as k_final / 2 over the run
     flops = float(np.sum(2 * u * u + it * (4 * (k / 2) * u + 2 * (k / 2) ** 2 + 2 * m * u) + k * (k * u + k * k / 3)))
-    ach = flops / (ms * 1e-3) / 1e12
-    # end to end with host buffers
-    n_e2e = max(2, min(args.steps, 5))
+    # end to end with pinned host buffers, both entries
+    n_e2e = max(3, min(args.steps, 8))
     pin = {}
-    for k_, v_ in pb.items():          # pinned host copies, as every other e2e leg
+    for k_, v_ in pb.items():
         if isinstance(v_, np.ndarray):
             pin[k_] = ctx.pinned(v_.shape, v_.dtype); pin[k_][...] = v_
         else:
             pin[k_] = v_
     pX = ctx.pinned((B, 32)); pinfo = ctx.pinned((B,), wg.PLDP_INFO_DTYPE)
-    ctx.pldp_solve(pin, X=pX, info=pinfo)
-    te = time.perf_counter()
-    for _ in range(n_e2e):
-        ctx.pldp_solve(pin, X=pX, info=pinfo)
-    e2e_s = time.perf_counter() - te
-    assert int(((pinfo["rc"] != 0) | (pinfo["status"] != 0)).sum()) == 0
-    h2d = sum(v.nbytes for v in pb.values() if isinstance(v, np.ndarray))
-    res = {"workload": PLDP_WORKLOAD, "instances": B, "distinct_problems": distinct,
-           "pldp_solves_per_s": B / (ms * 1e-3), "ms_per_launch": ms,
+    e2e = {}
+    for ranked in (False, True):
+        ctx.pldp_solve(pin, X=pX, info=pinfo, ranked=ranked)
+        te = time.perf_counter()
+        for _ in range(n_e2e):
+            ctx.pldp_solve(pin, X=pX, info=pinfo, ranked=ranked)
+        e2e[ranked] = B * n_e2e / (time.perf_counter() - te)
+        assert int(((pinfo["rc"] != 0) | (pinfo["status"] != 0)).sum()) == 0
+    common = sum(pb[k_].nbytes for k_ in ("D", "m", "DPx", "ZMPRef", "XkYk"))
+    h2d = {False: common + pb["DPu"].nbytes, True: common + pb["a0"].nbytes + pb["a1"].nbytes + pb["ri"].nbytes}
+    d2h = int(B * (256 + wg.PLDP_INFO_DTYPE.itemsize))
+
+    def roof(t_ms, note):
+        ach = flops / (t_ms * 1e-3) / 1e12
+        return {"kernel": "pldp_kernel", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ach / fp64_peak, "traffic": None, "algorithmic_flop_per_solve_mean": flops / B, "note": note}
+    res = {"workload": PLDP_WORKLOAD, "instances": B, "distinct_problems": B,
+           "pldp_solves_per_s": B / (ms[True] * 1e-3), "ms_per_launch": ms[True], "entry": "wg_pldp_solve_batch_ranked",
            "iterations_mean": float(it.mean()), "iterations_max": int(it.max()), "active_mean": float(k.mean()),
            "constraints_mean": float(m.mean()), "failures": int(((info["rc"] != 0) | (info["status"] != 0)).sum()),
-           "roofline": {"kernel": "pldp_kernel", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                        "frac": ach / fp64_peak, "traffic": None, "algorithmic_flop_per_solve_mean": flops / B,
-                        "note": "non-fused FP64 in the reference's serial summation order (bitwise parity): latency "
-                                "bound by design; constraint matrix re-read from L2 every iteration"},
-           "e2e": {"value": B * n_e2e / e2e_s, "unit": "PLDP solves/s", "h2d_bytes_per_step": int(h2d),
-                   "d2h_bytes_per_step": int(B * (256 + wg.PLDP_INFO_DTYPE.itemsize)),
-                   "api": "wg_pldp_solve_batch(WG_MEM_HOST), pinned host buffers, 4 pipelined chunks"}}
+           "roofline": roof(ms[True], "non-fused FP64 in the reference's serial summation order (bitwise parity): latency bound by "
+                                      "design; rank-structured rows, no constraint matrix in memory"),
+           "e2e": {"value": e2e[True], "unit": "PLDP solves/s", "h2d_bytes_per_step": int(h2d[True]), "d2h_bytes_per_step": d2h,
+                   "api": "wg_pldp_solve_batch_ranked(WG_MEM_HOST), pinned host buffers, 4 pipelined chunks"},
+           "dense_entry": {"entry": "wg_pldp_solve_batch", "pldp_solves_per_s": B / (ms[False] * 1e-3), "ms_per_launch": ms[False],
+                           "roofline": roof(ms[False], "dense (m+1) x 32 matrix re-read from L2 every iteration"),
+                           "e2e": {"value": e2e[False], "unit": "PLDP solves/s", "h2d_bytes_per_step": int(h2d[False]),
+                                   "d2h_bytes_per_step": d2h,
+                                   "api": "wg_pldp_solve_batch(WG_MEM_HOST), pinned host buffers, 4 pipelined chunks"}}}
     if want_cpu:
         res["cpu_baseline"] = cpu_pldp_rate(small, seconds=max(2.0, args.cpu_seconds / 2))
-    for v in list(dev.values()) + [dX, dinfo]:
+    for v in list(dev.values()) + [dX, dinfo, d_flush]:
         if hasattr(v, "free"):
             v.free()
-    return res, {"pldp_kernel": {"launches": args.steps, "avg_ms": ms}}
+    return res, {"pldp_kernel<ranked>": {"launches": args.steps, "avg_ms": ms[True]},
+                 "pldp_kernel<dense>": {"launches": args.steps, "avg_ms": ms[False]}}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -323,6 +323,8 @@ int wg_herdt_mpc_run_batch(wg_ctx *ctx, int mem, int B, int nsteps, wg_herdt_mpc
  * ---------------------------------------------------------------------------------------------- */
 #define WG_PLDP_CARDU 16                 /* m_CardV = QP_N                                          */
 #define WG_PLDP_NVAR (2 * WG_PLDP_CARDU)  /* 32                                                      */
+#define WG_PLDP_MAX_ROWS 128             /* NbOfConstraints <= 8 rows x QP_N samples ("bounded to 8 constraints per support
+                                            foot", ZMPConstrainedQPFastFormulation.cpp:775-777); larger m is refused  */
 
 /* Constants the PLDPSolver ctor borrows (PLDPSolver.hh:48-52): iPu, Px, Pu are CardU x CardU, CardU x 3, CardU x CardU
  * row-major host arrays.  (iLQ is only read by the reference's debug dumps and is not needed.) */
@@ -340,7 +342,9 @@ typedef struct wg_pldp_info {
   int32_t rc;          /* return value of SolveProblem: 0, or -1 when X[0] / X[CardU] is NaN or Inf (PLDPSolver.cpp:955-964) */
   int32_t status;      /* 0 ok; 1 start point violated a constraint by more than m_tol ("PB ON constraint", :611-616);
                           2 negative step length (the reference calls exit(0), :822-828); 3 active-set capacity;
-                          4 iteration cap reached (stands in for the 1.3 ms wall-clock cap, :890-900)                 */
+                          4 iteration cap reached (stands in for the 1.3 ms wall-clock cap, :890-900);
+                          6 a SimilarConstraints entry points forward or outside the problem (device-side batches; host-side
+                            ones are refused with WG_ERR_INVALID); 7 m outside [0, WG_PLDP_MAX_ROWS] (X = NaN, rc = -1)   */
   int32_t iterations;  /* m_ItNb                                                                                       */
   int32_t n_active;
   int32_t active[WG_PLDP_NVAR];   /* m_ActivatedConstraints in activation order, -1 padded                             */
@@ -359,7 +363,11 @@ typedef struct wg_pldp_batch {
   const double *ZMPRef;   /* [B][32]                                                                              */
   const double *XkYk;     /* [B][6]   (x, dx, ddx, y, dy, ddy)                                                    */
   double *X;              /* [B][32]  out                                                                         */
-  const int32_t *similar; /* [B][similar_stride] SimilarConstraints, or NULL (the reuse is bit-neutral)           */
+  const int32_t *similar; /* [B][similar_stride] SimilarConstraints, or NULL.  similar[li] = s != 0 makes ComputeAlpha take
+                             the product of row li as minus that of row li + s when that row is not active
+                             (PLDPSolver.cpp:570-590), exactly as the reference does; s must be <= 0 with li + s >= 0 (the
+                             reference only ever builds -2 / -3, FootConstraintsAsLinearSystem.cpp:53-92).  For flags that
+                             match the matrix the reuse is bit-neutral, so NULL gives the same result                    */
   long long similar_stride;
   const int32_t *n_removed; /* [B] NumberOfRemovedConstraints, or NULL (0)                                        */
   const int32_t *starting;  /* [B] StartingSequence, or NULL (true)                                               */
@@ -370,6 +378,17 @@ typedef struct wg_pldp_batch {
 } wg_pldp_batch;
 
 int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *batch);
+
+/* The same solve with the constraint matrix in the rank-structured form every call of the reference has: row r of the
+ * matrix BuildConstraintMatrices writes (ZMPConstrainedQPFastFormulation.cpp:885-905) is
+ *     element (r, k + 16 ax) = A_r(ax) * Pu[k][i_r]
+ * with A_r = the half-plane normal of the row, i_r = the previewed sample it belongs to and Pu the matrix given to
+ * wg_pldp_set_constants.  The caller passes A0 = A_r(0), A1 = A_r(1) and sample = i_r ([B][row_stride] each, row_stride >=
+ * max m) instead of batch->DPu (ignored, may be NULL): 17 bytes per row instead of 256 cross PCIe / HBM, the products are
+ * formed where they are used by the same single IEEE multiplication the reference stores, and X / the activation sequence
+ * are bitwise those of wg_pldp_solve_batch on the materialised matrix. */
+int wg_pldp_solve_batch_ranked(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *batch, const double *A0, const double *A1,
+                               const uint8_t *sample, long long row_stride);
 
 /* OptCholesky, B instances: compute rows k0..k1-1 of L for the active rows rows[b][0..k1) of A_b (rows 0..k0-1 of L
  * must already be there: this is AddActiveConstraint called k1-k0 times).  mode 1 = MODE_FORTRAN (A column-major,

@@ -277,27 +277,37 @@ class Context:
                                                    Pu.ctypes.data_as(D)))
 
     def pldp_solve(self, pb, hot=None, hot_start=True, starting=None, n_removed=None, similar=None, max_iterations=0,
-                   mem=WG_MEM_HOST, B=None, X=None, info=None):
+                   mem=WG_MEM_HOST, B=None, X=None, info=None, ranked=False, similar_stride=None):
         """wg_pldp_solve_batch.  pb: dict with D [B][32], m [B] int32, DPu [B][dpu_stride], DPx [B][dpx_stride],
         ZMPRef [B][32], XkYk [B][6], dpu_stride, dpx_stride (numpy arrays, or DeviceBuffers with mem=WG_MEM_DEVICE).
-        Returns (X, info)."""
+        ranked=True: wg_pldp_solve_batch_ranked on pb["a0"], pb["a1"] [B][row_stride] float64 and pb["ri"] [B][row_stride]
+        uint8 (pb["row_stride"]) instead of DPu.  Returns (X, info)."""
         if mem == WG_MEM_HOST:
             B = len(pb["m"])
             X = np.zeros((B, 32)) if X is None else X
             info = np.zeros(B, dtype=PLDP_INFO_DTYPE) if info is None else info
-        keep = [np.ascontiguousarray(pb[k]) if mem == WG_MEM_HOST else pb[k] for k in ("D", "m", "DPu", "DPx", "ZMPRef", "XkYk")]
+        names = ("D", "m", "DPu", "DPx", "ZMPRef", "XkYk")
+        keep = [None if (ranked and k == "DPu") else (np.ascontiguousarray(pb[k]) if mem == WG_MEM_HOST else pb[k]) for k in names]
+        rk = None
+        if ranked:
+            rk = [np.ascontiguousarray(pb[k]) if mem == WG_MEM_HOST else pb[k] for k in ("a0", "a1", "ri")]
         opt = [None if a is None else (np.ascontiguousarray(a, dtype=np.int32) if mem == WG_MEM_HOST else a)
                for a in (similar, n_removed, starting)]
         def vp(a):
             p = _ptr(a)
             return None if p is None else p.value
-        b = _capi.PldpBatch(D=vp(keep[0]), m=vp(keep[1]), DPu=vp(keep[2]), dpu_stride=int(pb["dpu_stride"]),
+        if similar_stride is None:
+            similar_stride = 0 if opt[0] is None or mem != WG_MEM_HOST else opt[0].shape[1]
+        b = _capi.PldpBatch(D=vp(keep[0]), m=vp(keep[1]), DPu=vp(keep[2]), dpu_stride=int(pb.get("dpu_stride", 0)),
                             DPx=vp(keep[3]), dpx_stride=int(pb["dpx_stride"]), ZMPRef=vp(keep[4]), XkYk=vp(keep[5]),
-                            X=vp(X), similar=vp(opt[0]),
-                            similar_stride=0 if opt[0] is None or mem != WG_MEM_HOST else opt[0].shape[1],
+                            X=vp(X), similar=vp(opt[0]), similar_stride=int(similar_stride),
                             n_removed=vp(opt[1]), starting=vp(opt[2]), hot=vp(hot), hot_start=int(bool(hot_start)),
                             max_iterations=int(max_iterations), info=vp(info))
-        self._check(self.lib.wg_pldp_solve_batch(self.h, mem, int(B), C.byref(b)))
+        if ranked:
+            self._check(self.lib.wg_pldp_solve_batch_ranked(self.h, mem, int(B), C.byref(b), vp(rk[0]), vp(rk[1]), vp(rk[2]),
+                                                            int(pb["row_stride"])))
+        else:
+            self._check(self.lib.wg_pldp_solve_batch(self.h, mem, int(B), C.byref(b)))
         return X, info
 
     def optcholesky_add_rows(self, A, rows, L, mode, nb_max, card_u, nb_constraints, k0, k1):

@@ -326,13 +326,13 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
                 const int *__restrict__ order)
 {
   __shared__ DimWarp ws[DM_WARPS];
-  __shared__ double sPu[DM_N * DM_N];
+  __shared__ double sPu[DM_N * DM_N], sPuT[DM_N * DM_N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DimConsts &K = *Kp;
   const PldpConsts &C = *Cp;
   DimWarp &w = ws[warp];
   constexpr int N = DM_N;
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) sPu[e] = K.Pu[e];
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) { sPu[e] = K.Pu[e]; sPuT[(e % N) * N + e / N] = K.Pu[e]; }
   __syncthreads();
   const double T = K.T, Ts = K.Ts;
   const double tol = 1e-8;   // m_tol, PLDPSolver.cpp:66
@@ -400,7 +400,7 @@ dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__res
       __syncwarp();
       // DPu (:885-905) is never materialised: element (r, k + N ax) = A_r[ax] * Pu[k N + i_r] is formed where it is used
       // (RankMat, pldp.cuh) by the same single IEEE multiplication the reference stores
-      const RankMat M{w.rowa[0], w.rowa[1], w.rowi, sPu};
+      const RankMat M{w.rowa[0], w.rowa[1], w.rowi, sPu, sPuT};
       // D = OptB xk - OptC ZMPRef (:1268-1276), row `lane`
       double Dl;
       {

@@ -29,29 +29,48 @@ struct PldpHost {
   PldpConsts *d = nullptr;
   bool ready = false;
   // staging for WG_MEM_HOST calls
-  void *buf[10] = {nullptr};
-  size_t cap[10] = {0};
+  void *buf[13] = {nullptr};
+  size_t cap[13] = {0};
   int *d_next = nullptr;   // work counter of pldp_kernel
   // WG_MEM_HOST pipeline
   cudaStream_t up = nullptr, down = nullptr;
   cudaEvent_t ev_up[4] = {nullptr}, ev_k[4] = {nullptr}, ev0 = nullptr;
 };
 
-// One instance per warp.
-__global__ void __launch_bounds__(PLDP_WARPS * 32, 8)
+// The rank-structured form of the constraint matrix (wg_pldp_solve_batch_ranked): per instance three arrays of m entries.
+struct PldpRanked {
+  const double *a0, *a1;      // [B][row_stride]
+  const unsigned char *ri;    // [B][row_stride]
+  long long row_stride;
+};
+
+// One instance per warp.  RANKED = false: the dense (m+1) x 32 column-major matrix the reference hands to SolveProblem, read
+// from L2 (8 CTAs/SM at 64 registers).  RANKED = true: the matrix is formed on the fly from (A_r(0), A_r(1), i_r) and the
+// context's Pu (RankMat): 17 bytes per row instead of 256, nothing re-read from L2 (4 CTAs/SM at 128 registers).
+template <bool RANKED>
+__global__ void __launch_bounds__(PLDP_WARPS * 32, RANKED ? 4 : 8)
 pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__ D, const int *__restrict__ mvec,
             const double *__restrict__ DPu, long long dpu_stride, const double *__restrict__ DPx, long long dpx_stride,
             const double *__restrict__ ZMPRef, const double *__restrict__ XkYk, double *__restrict__ X,
             const int *__restrict__ similar, long long similar_stride, const int *__restrict__ nremoved,
             const int *__restrict__ starting, wg_pldp_state *__restrict__ hot, int hot_start, int max_iter,
-            double tol, wg_pldp_info *__restrict__ info, int a_cap, int *__restrict__ next_problem)
+            double tol, wg_pldp_info *__restrict__ info, int a_cap, int *__restrict__ next_problem, PldpRanked rk)
 {
   __shared__ PldpWarp ws[PLDP_WARPS];
+  __shared__ double s_t1[PLDP_WARPS][WG_PLDP_MAX_ROWS];     // SimilarConstraints scratch (see pldp_solve_warp)
+  __shared__ unsigned s_amask[PLDP_WARPS][4];
+  __shared__ double sPu[RANKED ? 2 * PLDP_N * PLDP_N : 1];   // Pu and its transpose
+  __shared__ double s_rowa[RANKED ? PLDP_WARPS : 1][2][RANKED ? WG_PLDP_MAX_ROWS : 1];   // the instance's (A_r(0), A_r(1)) ...
+  __shared__ unsigned char s_rowi[RANKED ? PLDP_WARPS : 1][RANKED ? WG_PLDP_MAX_ROWS : 4];   // ... and i_r, staged once
   extern __shared__ __align__(16) double sA[];   // a_cap doubles per warp: the instance's constraint matrix (0: read it from L2)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const PldpConsts &C = *Cp;
   PldpWarp &w = ws[warp];
   constexpr int N = PLDP_N;
+  if (RANKED) {
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) { sPu[e] = C.Pu[e]; sPu[N * N + e] = C.PuT[e]; }
+    __syncthreads();
+  }
   // iteration counts differ (5-33 on the bench workload): every warp takes its next problem from a work counter
   for (;;) {
     int b = 0;
@@ -59,9 +78,18 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= B) break;
     const int m = mvec[b];
+    if (m < 0 || m > WG_PLDP_MAX_ROWS) {
+      // device-side batches are not validated on the host: refuse the instance instead of ignoring rows past 128
+      X[(size_t)b * PLDP_U + lane] = nan("");
+      if (info) {
+        if (lane == 0) { info[b].rc = -1; info[b].status = 7; info[b].iterations = 0; info[b].n_active = 0; }
+        info[b].active[lane] = -1;
+      }
+      continue;
+    }
     const int ld = m + 1;
-    const double *A = DPu + (size_t)b * dpu_stride;
-    if (a_cap > 0 && ld * PLDP_U <= a_cap) {
+    const double *A = RANKED ? nullptr : DPu + (size_t)b * dpu_stride;
+    if (!RANKED && a_cap > 0 && ld * PLDP_U <= a_cap) {
       // stage the (m+1) x 32 column-major matrix once: every iteration re-reads all of it
       double *dst = sA + (size_t)warp * a_cap;
       const int n = ld * PLDP_U;
@@ -84,10 +112,29 @@ pldp_kernel(int B, const PldpConsts *__restrict__ Cp, const double *__restrict__
     const double *xk = XkYk + (size_t)b * 6;
     const bool hs = hot && hot_start;
     PldpRes r;
-    const DenseMat M{A, ld};
-    const double Vk = pldp_solve_warp(C, w, M, m, bv, Dl, zr, xk, hs && !start, hs ? hot[b].prev_zmp : nullptr,
-                                      hs ? hot[b].n_prev : 0, hs ? hot[b].prev_active : nullptr,
-                                      nremoved ? nremoved[b] : 0, max_iter, tol, lane, r);
+    const PldpSim simv{similar ? similar + (size_t)b * similar_stride : nullptr, s_t1[warp], s_amask[warp]};
+    const PldpSim *simp = similar ? &simv : nullptr;
+    double Vk;
+    if (RANKED) {
+      const size_t ro = (size_t)b * rk.row_stride;
+      __syncwarp();
+      for (int e = lane; e < m; e += 32) {
+        s_rowa[warp][0][e] = rk.a0[ro + e];
+        s_rowa[warp][1][e] = rk.a1[ro + e];
+        const unsigned char i_r = rk.ri[ro + e];
+        s_rowi[warp][e] = i_r < N ? i_r : 0;      // host-side batches are validated; a bad device-side index must not read outside Pu
+      }
+      __syncwarp();
+      const RankMat M{s_rowa[warp][0], s_rowa[warp][1], s_rowi[warp], sPu, sPu + N * N};
+      Vk = pldp_solve_warp(C, w, M, m, bv, Dl, zr, xk, hs && !start, hs ? hot[b].prev_zmp : nullptr,
+                           hs ? hot[b].n_prev : 0, hs ? hot[b].prev_active : nullptr,
+                           nremoved ? nremoved[b] : 0, max_iter, tol, lane, r, simp);
+    } else {
+      const DenseMat M{A, ld};
+      Vk = pldp_solve_warp(C, w, M, m, bv, Dl, zr, xk, hs && !start, hs ? hot[b].prev_zmp : nullptr,
+                           hs ? hot[b].n_prev : 0, hs ? hot[b].prev_active : nullptr,
+                           nremoved ? nremoved[b] : 0, max_iter, tol, lane, r, simp);
+    }
     const int status = r.status, it = r.it, k = r.k, kproj = r.kproj;
     const double v2 = r.v2;
     const int ii = lane & (N - 1), ax = lane >> 4;
@@ -247,6 +294,8 @@ int wg_pldp_set_constants(wg_ctx *ctx, int card_u, const double *iPu, const doub
   std::memcpy(p->h.iPu, iPu, sizeof p->h.iPu);
   std::memcpy(p->h.Px, Px, sizeof p->h.Px);
   std::memcpy(p->h.Pu, Pu, sizeof p->h.Pu);
+  for (int k = 0; k < PLDP_N; ++k)
+    for (int i = 0; i < PLDP_N; ++i) p->h.PuT[i * PLDP_N + k] = Pu[k * PLDP_N + i];
   // PLDPSolver::PrecomputeiPuPx, PLDPSolver.cpp:264-285 (same summation order)
   std::memset(p->h.iPuPx, 0, sizeof p->h.iPuPx);
   for (int i = 0; i < N; ++i)
@@ -263,18 +312,47 @@ int wg_pldp_set_constants(wg_ctx *ctx, int card_u, const double *iPu, const doub
   return WG_OK;
 }
 
-int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
+}  // extern "C"
+
+// Common body of wg_pldp_solve_batch (ranked == nullptr) and wg_pldp_solve_batch_ranked.
+static int pldp_solve_impl(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb, const PldpRanked *ranked)
 {
   if (!ctx || !pb || B < 0) return WG_ERR_INVALID;
   PldpHost *p = pldp_of(ctx);
   if (!p->ready) return wg_fail(ctx, WG_ERR_NOT_READY, "wg_pldp_set_constants not called");
   if (B == 0) return WG_OK;
-  if (!pb->D || !pb->m || !pb->DPu || !pb->DPx || !pb->ZMPRef || !pb->XkYk || !pb->X) return WG_ERR_INVALID;
-  if (pb->dpu_stride <= 0 || pb->dpx_stride <= 0) return WG_ERR_INVALID;
+  if (!pb->D || !pb->m || !pb->DPx || !pb->ZMPRef || !pb->XkYk || !pb->X) return WG_ERR_INVALID;
+  if (!ranked && (!pb->DPu || pb->dpu_stride <= 0)) return WG_ERR_INVALID;
+  if (ranked && (!ranked->a0 || !ranked->a1 || !ranked->ri || ranked->row_stride <= 0)) return WG_ERR_INVALID;
+  if (pb->dpx_stride <= 0) return WG_ERR_INVALID;
+  if (pb->similar && pb->similar_stride <= 0) return WG_ERR_INVALID;
+  if (mem == WG_MEM_HOST) {
+    // host-side batches are validated here (device-side ones by the kernel: status 7 / 6)
+    for (int b = 0; b < B; ++b) {
+      const long long m = pb->m[b];
+      if (m < 0 || m > WG_PLDP_MAX_ROWS) return wg_fail(ctx, WG_ERR_INVALID, "m[b] outside [0, WG_PLDP_MAX_ROWS]");
+      if (!ranked && pb->dpu_stride < (m + 1) * PLDP_U) return wg_fail(ctx, WG_ERR_INVALID, "dpu_stride < (m[b]+1)*32");
+      if (ranked && ranked->row_stride < m) return wg_fail(ctx, WG_ERR_INVALID, "row_stride < m[b]");
+      if (pb->dpx_stride < m) return wg_fail(ctx, WG_ERR_INVALID, "dpx_stride < m[b]");
+      if (pb->similar) {
+        if (pb->similar_stride < m) return wg_fail(ctx, WG_ERR_INVALID, "similar_stride < m[b]");
+        const int32_t *sm = pb->similar + (size_t)b * pb->similar_stride;
+        for (long long r = 0; r < m; ++r)
+          if (sm[r] > 0 || r + sm[r] < 0)
+            return wg_fail(ctx, WG_ERR_INVALID, "SimilarConstraints must be 0 or point backward inside the problem");
+      }
+      if (ranked) {
+        const unsigned char *ri = ranked->ri + (size_t)b * ranked->row_stride;
+        for (long long r = 0; r < m; ++r)
+          if (ri[r] >= PLDP_N) return wg_fail(ctx, WG_ERR_INVALID, "previewed sample index of a row >= 16");
+      }
+    }
+  }
   wg_device_guard guard(ctx->device);
   const int max_iter = pb->max_iterations > 0 ? pb->max_iterations : 4 * PLDP_KMAX;
   const double tol = 1e-8;   // m_tol, PLDPSolver.cpp:66
   wg_pldp_batch d = *pb;
+  PldpRanked dr = ranked ? *ranked : PldpRanked{nullptr, nullptr, nullptr, 0};
   // launch over instances [b0, b0 + n) of the device-side batch `d`
   auto launch = [&](int b0, int n) -> int {
     int grid = (n + PLDP_WARPS - 1) / PLDP_WARPS;
@@ -283,21 +361,31 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
     // registers: 3.53 ms, 2.85 ms with the work counter (24 warps/SM at 80 registers: 3.10 ms).  The solver is a chain of dependent FP64 operations: resident warps
     // hide more than shared memory saves.  WG_PLDP_STAGE=1 restores the staged variant.
     static const int stage = getenv("WG_PLDP_STAGE") ? atoi(getenv("WG_PLDP_STAGE")) : 0;
-    int a_cap = stage ? (int)((pb->dpu_stride + 1) & ~1LL) : 0;
+    int a_cap = (stage && !ranked) ? (int)((pb->dpu_stride + 1) & ~1LL) : 0;
     size_t smem = sizeof(double) * (size_t)a_cap * PLDP_WARPS;
-    if (smem > 200 * 1024) { a_cap = 0; smem = 0; }
-    WG_SMEM_ATTR(ctx, WG_ATTR_PLDP, pldp_kernel, smem);
-    const int per_sm = smem ? (int)((227 * 1024) / (smem + sizeof(PldpWarp) * PLDP_WARPS + 1024)) : 8;
+    if (smem > 190 * 1024) { a_cap = 0; smem = 0; }
+    WG_SMEM_ATTR(ctx, WG_ATTR_PLDP, pldp_kernel<false>, smem);
+    const int per_sm = smem ? (int)((227 * 1024) / (smem + (sizeof(PldpWarp) + 1100) * PLDP_WARPS + 1024)) : (ranked ? 4 : 8);
     if (grid > ctx->sm_count * (per_sm > 0 ? per_sm : 1)) grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);
     if (!p->d_next) WG_CUDA(ctx, cudaMalloc(&p->d_next, sizeof(int)));
     WG_CUDA(ctx, cudaMemsetAsync(p->d_next, 0, sizeof(int), ctx->stream));
     const size_t o = (size_t)b0;
     wg_prof_start(ctx, WG_K_PLDP);
-    pldp_kernel<<<grid, PLDP_WARPS * 32, smem, ctx->stream>>>(
-        n, p->d, d.D + o * PLDP_U, d.m + o, d.DPu + o * d.dpu_stride, d.dpu_stride, d.DPx + o * d.dpx_stride, d.dpx_stride,
-        d.ZMPRef + o * PLDP_U, d.XkYk + o * 6, d.X + o * PLDP_U, d.similar ? d.similar + o * d.similar_stride : nullptr,
-        d.similar_stride, d.n_removed ? d.n_removed + o : nullptr, d.starting ? d.starting + o : nullptr,
-        d.hot ? d.hot + o : nullptr, pb->hot_start, max_iter, tol, d.info ? d.info + o : nullptr, a_cap, p->d_next);
+    if (ranked) {
+      const PldpRanked rk{dr.a0 + o * dr.row_stride, dr.a1 + o * dr.row_stride, dr.ri + o * dr.row_stride, dr.row_stride};
+      pldp_kernel<true><<<grid, PLDP_WARPS * 32, 0, ctx->stream>>>(
+          n, p->d, d.D + o * PLDP_U, d.m + o, nullptr, 0, d.DPx + o * d.dpx_stride, d.dpx_stride,
+          d.ZMPRef + o * PLDP_U, d.XkYk + o * 6, d.X + o * PLDP_U, d.similar ? d.similar + o * d.similar_stride : nullptr,
+          d.similar_stride, d.n_removed ? d.n_removed + o : nullptr, d.starting ? d.starting + o : nullptr,
+          d.hot ? d.hot + o : nullptr, pb->hot_start, max_iter, tol, d.info ? d.info + o : nullptr, 0, p->d_next, rk);
+    } else {
+      pldp_kernel<false><<<grid, PLDP_WARPS * 32, smem, ctx->stream>>>(
+          n, p->d, d.D + o * PLDP_U, d.m + o, d.DPu + o * d.dpu_stride, d.dpu_stride, d.DPx + o * d.dpx_stride, d.dpx_stride,
+          d.ZMPRef + o * PLDP_U, d.XkYk + o * 6, d.X + o * PLDP_U, d.similar ? d.similar + o * d.similar_stride : nullptr,
+          d.similar_stride, d.n_removed ? d.n_removed + o : nullptr, d.starting ? d.starting + o : nullptr,
+          d.hot ? d.hot + o : nullptr, pb->hot_start, max_iter, tol, d.info ? d.info + o : nullptr, a_cap, p->d_next,
+          PldpRanked{nullptr, nullptr, nullptr, 0});
+    }
     wg_prof_stop(ctx);
     WG_LAUNCHED(ctx);
     return WG_OK;
@@ -311,7 +399,10 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
   const Item in[] = {
       {0, pb->D, sizeof(double) * PLDP_U, (const void **)&d.D},
       {1, pb->m, sizeof(int), (const void **)&d.m},
-      {2, pb->DPu, sizeof(double) * (size_t)pb->dpu_stride, (const void **)&d.DPu},
+      {2, ranked ? nullptr : pb->DPu, ranked ? 0 : sizeof(double) * (size_t)pb->dpu_stride, (const void **)&d.DPu},
+      {10, ranked ? ranked->a0 : nullptr, ranked ? sizeof(double) * (size_t)ranked->row_stride : 0, (const void **)&dr.a0},
+      {11, ranked ? ranked->a1 : nullptr, ranked ? sizeof(double) * (size_t)ranked->row_stride : 0, (const void **)&dr.a1},
+      {12, ranked ? ranked->ri : nullptr, ranked ? sizeof(unsigned char) * (size_t)ranked->row_stride : 0, (const void **)&dr.ri},
       {3, pb->DPx, sizeof(double) * (size_t)pb->dpx_stride, (const void **)&d.DPx},
       {4, pb->ZMPRef, sizeof(double) * PLDP_U, (const void **)&d.ZMPRef},
       {5, pb->XkYk, sizeof(double) * 6, (const void **)&d.XkYk},
@@ -363,6 +454,20 @@ int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
   WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   WG_CUDA(ctx, cudaStreamSynchronize(p->down));
   return WG_OK;
+}
+
+extern "C" {
+
+int wg_pldp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb)
+{
+  return pldp_solve_impl(ctx, mem, B, pb, nullptr);
+}
+
+int wg_pldp_solve_batch_ranked(wg_ctx *ctx, int mem, int B, const wg_pldp_batch *pb, const double *A0, const double *A1,
+                               const uint8_t *sample, long long row_stride)
+{
+  const PldpRanked rk{A0, A1, sample, row_stride};
+  return pldp_solve_impl(ctx, mem, B, pb, &rk);
 }
 
 int wg_optcholesky_add_rows_batch(wg_ctx *ctx, int mem, int B, int mode, int nb_max, int card_u, int nb_constraints,

@@ -15,6 +15,14 @@ struct PldpConsts {
   double Px[PLDP_N * 3];
   double Pu[PLDP_N * PLDP_N];
   double iPuPx[PLDP_U * 6];           // PLDPSolver::PrecomputeiPuPx (PLDPSolver.cpp:264-285)
+  double PuT[PLDP_N * PLDP_N];        // Pu transposed: PuT[i][k] = Pu[k][i] (lane-contiguous reads of one sample's column)
+};
+
+// SimilarConstraints of one problem + the scratch ComputeAlpha needs to honour them (see pldp_solve_warp); null = none
+struct PldpSim {
+  const int *similar;     // [m]
+  double *t1;             // [128] per warp
+  unsigned *amask;        // [4]   per warp: activity bit of every row
 };
 
 struct PldpWarp {
@@ -53,13 +61,17 @@ struct RankMat {
   const double *a0, *a1;   // [m]   A_r(0), A_r(1)
   const unsigned char *ri; // [m]   previewed sample of row r
   const double *Pu;        // [16][16] m_Pu
+  const double *PuT;       // [16][16] its transpose
   struct Row {
-    double a0, a1; const double *pu;
-    __device__ __forceinline__ double at(int c) const { return mul(c < PLDP_N ? a0 : a1, pu[(c & (PLDP_N - 1)) * PLDP_N]); }
+    double a0, a1; const double *pu; const double *put;
+    // one row read ACROSS lanes (lane = column c): the 16 entries of sample i_r are contiguous in PuT (reading them from
+    // Pu[k][i_r] puts the 16 lanes of a half-warp on one shared-memory bank pair: a 16-way conflict per load)
+    __device__ __forceinline__ double at(int c) const { return mul(c < PLDP_N ? a0 : a1, put[c & (PLDP_N - 1)]); }
     __device__ __forceinline__ double coef(int h) const { return h ? a1 : a0; }
+    // a lane walking down ITS row (kk serial): lanes hold different samples i_r, contiguous in Pu[kk][.]
     __device__ __forceinline__ double at_h(double cf, int, int kk) const { return mul(cf, pu[kk * PLDP_N]); }
   };
-  __device__ __forceinline__ Row row(int r) const { return Row{a0[r], a1[r], Pu + ri[r]}; }
+  __device__ __forceinline__ Row row(int r) const { const int i = ri[r]; return Row{a0[r], a1[r], Pu + i, PuT + i * PLDP_N}; }
 };
 
 // OptCholesky::UpdateCholeskyMatrixFortran (OptCholesky.cpp:171-223): row `i` of L for the active rows act[0..i].
@@ -134,13 +146,17 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
                                                   const double *bv, double Dl, const double *zr, const double *xk,
                                                   bool use_prev, const double *prev_zmp, int n_prev,
                                                   const int *prev_active, int nr, int max_iter, double tol, int lane,
-                                                  PldpRes &r)
+                                                  PldpRes &r, const PldpSim *sim = nullptr)
 {
   constexpr int N = PLDP_N;
   constexpr int SLABS = 4;                       // rows lane, lane+32, lane+64, lane+96: m <= 128
   int status = 0;
-  // `similar` is accepted for interface parity only: the A_j = -A_i reuse (PLDPSolver.cpp:570-590) yields products
-  // bit-identical to computing every row directly, which is what the lanes do
+  // SimilarConstraints (sim): ComputeAlpha's `A_j = -A_i` reuse (PLDPSolver.cpp:570-590) takes tmp1[li] = -tmp1[li + s]
+  // when s = similar[li] != 0 and row li + s was visited and is not active.  For flags that match the matrix (the only
+  // kind the reference builds: the flagged row is the exact negation of the other) this is bit-identical to the direct
+  // product, which is why the Dimitrov loop passes no flags; the stand-alone solver honours caller-supplied flags exactly
+  // (chains included), and refuses flags that point forward or out of range (status 6: the reference would read its flag
+  // array as an earlier call left it).  The second reuse (:600-610) can never fire and is not restated.
 
   // ---- ComputeInitialSolution (PLDPSolver.cpp:287-340): lane = i (x part) or i + N (y part)
   const int ii = lane & (N - 1), ax = lane >> 4;
@@ -263,6 +279,33 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
               if (s < ns) t1[s] = add(t1[s], mul(rows[s].at_h(cf[s], h, kk), dj));
           }
         }
+        if (sim) {
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) {
+            if (lane + 32 * s < m) sim->t1[lane + 32 * s] = t1[s];
+            const unsigned bits = __ballot_sync(0xffffffffu, (mine >> s) & 1u);
+            if (lane == 0) sim->amask[s] = bits;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) {
+            if (!ok[s]) continue;
+            const int li = lane + 32 * s;
+            int rr = li;
+            bool neg = false;
+#pragma unroll 1
+            for (;;) {
+              const int sm = sim->similar[rr];
+              if (sm == 0) break;
+              const int t = rr + sm;
+              if (t < 0 || t >= rr) { status = 6; break; }
+              if ((sim->amask[t >> 5] >> (t & 31)) & 1u) break;      // active rows are skipped before their product
+              rr = t; neg = !neg;
+            }
+            if (rr != li) t1[s] = neg ? -sim->t1[rr] : sim->t1[rr];
+          }
+        }
         bool want[SLABS];
         bool any = false;
 #pragma unroll
@@ -270,6 +313,10 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
         double best = 10000000.0; int besti = 0x7fffffff;
         if (__any_sync(0xffffffffu, any)) {
           double t2[SLABS];
+          // slabs in which no row moves towards its bound (t1 < 0) need no second product: skip them as a whole
+          bool wslab[SLABS];
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) wslab[s] = __any_sync(0xffffffffu, want[s]);
 #pragma unroll
           for (int s = 0; s < SLABS; ++s) t2[s] = -bv[(lane + 32 * s) < m ? lane + 32 * s : 0];
 #pragma unroll(Mat::kHalfUnroll)
@@ -282,7 +329,7 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
               const double vj = w.vec[1][h * PLDP_N + kk];
 #pragma unroll
               for (int s = 0; s < SLABS; ++s)
-                if (s < ns) t2[s] = add(t2[s], -mul(rows[s].at_h(cf[s], h, kk), vj));
+                if (wslab[s]) t2[s] = add(t2[s], -mul(rows[s].at_h(cf[s], h, kk), vj));
             }
           }
 #pragma unroll
@@ -307,6 +354,7 @@ __device__ __forceinline__ double pldp_solve_warp(const PldpConsts &C, PldpWarp 
       }
     }
     status = __reduce_max_sync(0xffffffffu, status);
+    if (status == 6) break;
     if (alpha >= 1.0) { alpha = 1.0; cont = false; }
     if (alpha < 0.0) { status = 2; cont = false; }     // the reference calls exit(0) here (:822-828)
     // ---- new solution (:830-834)

@@ -240,12 +240,13 @@ def pldp_pack(K, probs):
            "dpu_stride": dpu_stride, "dpx_stride": mmax,
            # the same matrices in rank-structured form (wg_pldp_solve_batch_ranked): row r = (A_r(0), A_r(1), sample i_r),
            # element (r, k + 16 ax) = A_r(ax) * Pu[k][i_r]; and SimilarConstraints-style flags
-           "a01": np.zeros((B, 128, 2)), "ri": np.zeros((B, 128), dtype=np.uint8),
+           "a0": np.zeros((B, 128)), "a1": np.zeros((B, 128)), "ri": np.zeros((B, 128), dtype=np.uint8), "row_stride": 128,
            "similar": np.zeros((B, 128), dtype=np.int32)}
     for b, p in enumerate(probs):
         out["DPu"][b, :len(p["DPu"])] = p["DPu"]
         out["DPx"][b, :p["m"]] = p["DPx"]
-        out["a01"][b, :p["m"]] = p["a01"]; out["ri"][b, :p["m"]] = p["ri"]; out["similar"][b, :p["m"]] = p["similar"]
+        out["a0"][b, :p["m"]] = p["a01"][:, 0]; out["a1"][b, :p["m"]] = p["a01"][:, 1]
+        out["ri"][b, :p["m"]] = p["ri"]; out["similar"][b, :p["m"]] = p["similar"]
     return out
 
 

@@ -159,3 +159,123 @@ def test_gpu_pldp_full_size_properties_and_device_mode(pctx):
     empty = {k: (v[:0] if isinstance(v, np.ndarray) else v) for k, v in small.items()}
     Xe, ie = ctx.pldp_solve(empty)
     assert len(Xe) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_pldp_ranked_entry_is_bitwise_the_dense_entry(pctx):
+    """wg_pldp_solve_batch_ranked (rows as (A_r(0), A_r(1), i_r), products formed on the fly) against wg_pldp_solve_batch
+    on the materialised matrix: X, activation order, iteration counts and hot-start memory bit for bit - cold batch,
+    device-resident call and a hot-started receding-horizon sequence."""
+    import jrl_walkgen_b200 as wg
+    ctx, K = pctx
+    _, pb = W.pldp_batch(2048, seed=41, K=K)
+    Xd, infod = ctx.pldp_solve(pb)
+    Xr, infor = ctx.pldp_solve(pb, ranked=True)
+    assert (infod["status"] == 0).all()
+    assert np.array_equal(Xd, Xr) and infod.tobytes() == infor.tobytes()
+    # device-resident ranked call
+    B = 2048
+    dev = {k: (ctx.to_device(v) if isinstance(v, np.ndarray) else v) for k, v in pb.items() if k != "DPu"}
+    dX = ctx.alloc(B * 32 * 8); dinfo = ctx.alloc(B * wg.PLDP_INFO_DTYPE.itemsize)
+    ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=B, X=dX, info=dinfo, ranked=True)
+    ctx.sync()
+    assert np.array_equal(dX.download(np.float64, (B, 32)), Xd)
+    for v in list(dev.values()) + [dX, dinfo]:
+        if hasattr(v, "free"):
+            v.free()
+    # hot-started sequence, both entries side by side
+    Bh, T = 32, 12
+    polys = [W._support_polygons(np.random.default_rng([43, b]), K.N, K.T, count=K.N + T) for b in range(Bh)]
+    xk = np.zeros((Bh, 6))
+    for b in range(Bh):
+        xk[b, 0], xk[b, 3] = polys[b][0][0]
+    hot_d = np.zeros(Bh, dtype=wg.PLDP_STATE_DTYPE); hot_r = hot_d.copy()
+    n_removed = np.zeros(Bh, dtype=np.int32)
+    for t in range(T):
+        probs = [W.pldp_problem_from(K, polys[b][t:t + K.N], xk[b]) for b in range(Bh)]
+        p2 = W.pldp_pack(K, probs)
+        st = np.full(Bh, int(t == 0), dtype=np.int32)
+        X1, i1 = ctx.pldp_solve(p2, hot=hot_d, starting=st, n_removed=n_removed)
+        X2, i2 = ctx.pldp_solve(p2, hot=hot_r, starting=st, n_removed=n_removed, ranked=True)
+        assert np.array_equal(X1, X2, equal_nan=True) and i1.tobytes() == i2.tobytes() and hot_d.tobytes() == hot_r.tobytes()
+        for b in range(Bh):
+            if i1["status"][b] == 0:
+                xk[b] = W.pldp_advance(K, xk[b], X1[b])
+        n_removed = np.array([p["n_first"] for p in probs], dtype=np.int32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranked", [False, True])
+def test_gpu_pldp_similar_constraints_semantics(pctx, ranked):
+    """SimilarConstraints through the C ABI: flags that match the matrix are bit-neutral; backward flags that do NOT match
+    it reproduce the reference's reuse of -tmp1 exactly (against the oracle port, itself bitwise the reference object on
+    such flags, tests/test_pldp_oracle.py); forward / out-of-range flags are refused."""
+    import jrl_walkgen_b200 as wg
+    ctx, K = pctx
+    _, pb = W.pldp_batch(96, seed=11, K=K)
+    X0, i0 = ctx.pldp_solve(pb, ranked=ranked)
+    X1, i1 = ctx.pldp_solve(pb, similar=pb["similar"], ranked=ranked)
+    assert np.array_equal(X0, X1) and i0.tobytes() == i1.tobytes()
+    rng = np.random.default_rng(5)
+    bad = np.zeros((96, 128), dtype=np.int32)
+    for b in range(96):
+        for li in range(1, int(pb["m"][b])):
+            if rng.random() < 0.3:
+                bad[b, li] = -int(rng.integers(1, min(li, 5) + 1))
+    X2, i2 = ctx.pldp_solve(pb, similar=bad, ranked=ranked)
+    differ = 0
+    for b in range(96):
+        Xo, io, act = po.oracle_solve(K, pb, b, starting=True, similar=bad[b])
+        assert i2["status"][b] == io[1] and i2["iterations"][b] == io[2], b
+        assert np.array_equal(X2[b], Xo, equal_nan=True) and np.array_equal(i2["active"][b], act), b
+        differ += int(not np.array_equal(X2[b], X0[b], equal_nan=True))
+    assert differ >= 10
+    fwd = np.zeros((96, 128), dtype=np.int32); fwd[7, 0] = 2
+    with pytest.raises(wg.WalkgenError) as ei:
+        ctx.pldp_solve(pb, similar=fwd, ranked=ranked)
+    assert ei.value.code == -3
+    # device-side batches are not validated on the host: the kernel reports status 6 for that instance only
+    keys = [k for k in pb if not (ranked and k == "DPu")]
+    dev = {k: (ctx.to_device(pb[k]) if isinstance(pb[k], np.ndarray) else pb[k]) for k in keys}
+    dfwd = ctx.to_device(fwd)
+    dX = ctx.alloc(96 * 32 * 8); dinfo = ctx.alloc(96 * wg.PLDP_INFO_DTYPE.itemsize)
+    ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=96, X=dX, info=dinfo, similar=dfwd, similar_stride=128, ranked=ranked)
+    ctx.sync()
+    info = dinfo.download(wg.PLDP_INFO_DTYPE, (96,))
+    assert info["status"][7] == 6 and (np.delete(info["status"], 7) == 0).all()
+    for v in list(dev.values()) + [dX, dinfo, dfwd]:
+        if hasattr(v, "free"):
+            v.free()
+
+
+@pytest.mark.gpu
+def test_gpu_pldp_refuses_out_of_range_problem_sizes(pctx):
+    """m > WG_PLDP_MAX_ROWS (= 128 = 8 rows x 16 samples), m < 0 and strides shorter than the problem: WG_ERR_INVALID for
+    host batches; for device batches the kernel writes status 7 / NaN for the offending instance and solves the others."""
+    import jrl_walkgen_b200 as wg
+    ctx, K = pctx
+    _, pb = W.pldp_batch(8, seed=3, K=K)
+    for bad_m in (129, -1):
+        p2 = dict(pb); p2["m"] = pb["m"].copy(); p2["m"][3] = bad_m
+        with pytest.raises(wg.WalkgenError) as ei:
+            ctx.pldp_solve(p2)
+        assert ei.value.code == -3
+    p3 = dict(pb); p3["dpu_stride"] = 32 * int(pb["m"].max())        # one row short of (m+1)*32
+    with pytest.raises(wg.WalkgenError):
+        ctx.pldp_solve(p3)
+    p4 = dict(pb); p4["dpx_stride"] = int(pb["m"].max()) - 1
+    with pytest.raises(wg.WalkgenError):
+        ctx.pldp_solve(p4)
+    X0, i0 = ctx.pldp_solve(pb)
+    m_bad = pb["m"].copy(); m_bad[3] = 200
+    dev = {k: (ctx.to_device(m_bad if k == "m" else v) if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    dX = ctx.alloc(8 * 32 * 8); dinfo = ctx.alloc(8 * wg.PLDP_INFO_DTYPE.itemsize)
+    ctx.pldp_solve(dev, mem=wg.WG_MEM_DEVICE, B=8, X=dX, info=dinfo)
+    ctx.sync()
+    X = dX.download(np.float64, (8, 32)); info = dinfo.download(wg.PLDP_INFO_DTYPE, (8,))
+    assert info["status"][3] == 7 and info["rc"][3] == -1 and np.isnan(X[3]).all()
+    keep = np.arange(8) != 3
+    assert np.array_equal(X[keep], X0[keep]) and (info["status"][keep] == 0).all()
+    for v in list(dev.values()) + [dX, dinfo]:
+        if hasattr(v, "free"):
+            v.free()

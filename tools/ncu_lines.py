@@ -18,7 +18,12 @@ def main():
     hi = next(i for i, r in enumerate(rows) if "Address" in r and "Source" in r)
     h = rows[hi]
     ia, isrc, iinst, ismp = h.index("Address"), h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
-    sass = [(int(r[ia], 16), r[isrc].strip(), int(r[iinst] or 0), int(r[ismp] or 0)) for r in rows[hi + 1:] if len(r) > ismp]
+    body = []
+    for r in rows[hi + 1:]:          # a capture with several launches holds one table per launch: use the first
+        if "Address" in r and "Source" in r:
+            break
+        body.append(r)
+    sass = [(int(r[ia], 16), r[isrc].strip(), int(r[iinst] or 0), int(r[ismp] or 0)) for r in body if len(r) > ismp]
     base = sass[0][0]
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=td, capture_output=True)
