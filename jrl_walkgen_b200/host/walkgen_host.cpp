@@ -367,7 +367,7 @@ namespace PatternGeneratorJRL {
 // ---------------------------------------------------------------------------------------------
 ZMPRefTrajectoryGeneration::ZMPRefTrajectoryGeneration(SimplePluginManager *lSPM)
     : SimplePlugin(lSPM), m_Tsingle(0.), m_Tdble(0.), m_SamplingPeriod(0.005), m_Omega(0.), m_ComHeight(0.),
-      m_StepHeight(0.), m_OnLineMode(false)
+      m_StepHeight(0.), m_CurrentTime(0.), m_OnLineMode(false)
 {
   std::string names[6] = {":omega", ":stepheight", ":singlesupporttime", ":doublesupporttime", ":comheight", ":samplingperiod"};
   for (auto &n : names) RegisterMethod(n);
@@ -388,13 +388,37 @@ void ZMPRefTrajectoryGeneration::CallMethod(std::string &Method, std::istringstr
 ZMPVelocityReferencedQP::ZMPVelocityReferencedQP(SimplePluginManager *lSPM, std::string, double sole_length,
                                                  double sole_width)
     : ZMPRefTrajectoryGeneration(lSPM), m_SoleLength(sole_length), m_SoleWidth(sole_width), m_ParamsDirty(true),
-      m_StepsBeforeStop(0)
+      m_StepsBeforeStop(0), m_HaveLastQP(false)
 {
   std::memset(&m_State, 0, sizeof m_State);
+  std::memset(&m_LastQP, 0, sizeof m_LastQP);
   wg_herdt_mpc_default_params(&m_Params);
   m_Tsingle = m_Params.t_single; m_Tdble = m_Params.t_double;
   std::string names[3] = {":previewcontroltime", ":numberstepsbeforestop", ":stoppg"};
   for (auto &n : names) RegisterMethod(n);
+}
+ZMPVelocityReferencedQP::ZMPVelocityReferencedQP(SimplePluginManager *lSPM, std::string, CjrlHumanoidDynamicRobot *aHS)
+    : ZMPRefTrajectoryGeneration(lSPM), m_SoleLength(0.25), m_SoleWidth(0.14), m_ParamsDirty(true), m_StepsBeforeStop(0),
+      m_HaveLastQP(false)
+{
+  std::memset(&m_State, 0, sizeof m_State);
+  std::memset(&m_LastQP, 0, sizeof m_LastQP);
+  wg_herdt_mpc_default_params(&m_Params);
+  m_Tsingle = m_Params.t_single; m_Tdble = m_Params.t_double;
+  std::string names[3] = {":previewcontroltime", ":numberstepsbeforestop", ":stoppg"};
+  for (auto &n : names) RegisterMethod(n);
+  if (aHS) {
+    // RelativeFeetInequalities::set_feet_dimensions (relative-feet-inequalities.cpp:153-182): the LEFT foot's sole wins
+    double l = 0.0, w = 0.0;
+    if (aHS->rightFoot()) aHS->rightFoot()->getSoleSize(l, w);
+    if (aHS->leftFoot()) aHS->leftFoot()->getSoleSize(l, w);
+    if (l > 0.0 && w > 0.0) { m_SoleLength = l; m_SoleWidth = w; }
+    // OrientationsPreview::OrientationsPreview (OrientationsPreview.cpp:42-68)
+    CjrlJoint *waist = aHS->waist();
+    CjrlJoint *lh = aHS->jointsBetween(*waist, *aHS->leftFoot()->associatedAnkle())[1];
+    CjrlJoint *rh = aHS->jointsBetween(*waist, *aHS->rightFoot()->associatedAnkle())[1];
+    SetHipYawJoints(lh->lowerBound(0), lh->upperBound(0), rh->lowerBound(0), rh->upperBound(0), lh->upperVelocityBound(0));
+  }
 }
 ZMPVelocityReferencedQP::~ZMPVelocityReferencedQP() {}
 void ZMPVelocityReferencedQP::CallMethod(std::string &Method, std::istringstream &strm)
@@ -424,7 +448,8 @@ int ZMPVelocityReferencedQP::InitOnLine(std::deque<ZMPPosition> &FinalZMPTraj_de
                                         std::deque<FootAbsolutePosition> &FinalLeftFootTraj_deq,
                                         std::deque<FootAbsolutePosition> &FinalRightFootTraj_deq,
                                         FootAbsolutePosition &InitLeft, FootAbsolutePosition &InitRight,
-                                        std::deque<double> &, COMState &lStartingCOMState, double lStartingZMPPosition[3])
+                                        std::deque<RelativeFootPosition> &, COMState &lStartingCOMState,
+                                        MAL_S3_VECTOR_TYPE(double) &lStartingZMPPosition)
 {
   wg_ctx *ctx = default_context();
   wg_herdt_params hp;
@@ -442,6 +467,16 @@ int ZMPVelocityReferencedQP::InitOnLine(std::deque<ZMPPosition> &FinalZMPTraj_de
   for (int i = 0; i < 3; ++i) m_State.new_ref[i] = keep_ref[i];
   m_State.ending_phase = keep_stop;
   if (m_StepsBeforeStop) { m_State.sup_steps_left = (int32_t)m_StepsBeforeStop; m_State.nb_steps_ssds = (int32_t)m_StepsBeforeStop; }
+  // CoM_ takes the whole starting state and OrientPrw_->CurrentTrunkState its yaw (ZMPVelocityReferencedQP.cpp:283-301):
+  // wg_herdt_mpc_init only knows the position, the derivatives are written into the (host-editable) state record here
+  for (int i = 1; i < 3; ++i) {
+    m_State.com_x[i] = lStartingCOMState.x[i]; m_State.com_y[i] = lStartingCOMState.y[i];
+    m_State.com_front[i] = lStartingCOMState.x[i]; m_State.com_front[3 + i] = lStartingCOMState.y[i];
+    m_State.com_back[i] = lStartingCOMState.x[i]; m_State.com_back[3 + i] = lStartingCOMState.y[i];
+  }
+  for (int i = 0; i < 3; ++i) m_State.trunk_yaw[i] = lStartingCOMState.yaw[i];
+  m_State.com_back[7] = lStartingCOMState.yaw[0]; m_State.com_back[8] = lStartingCOMState.yaw[1];
+  m_HaveLastQP = false;
   // the TimeBuffer_/m_SamplingPeriod buffered start samples (ZMPVelocityReferencedQP.cpp:243-271)
   const int AddArraySize = (int)(m_Params.time_buffer / m_Params.Ts);
   FinalZMPTraj_deq.assign(AddArraySize, ZMPPosition());
@@ -462,6 +497,29 @@ int ZMPVelocityReferencedQP::InitOnLine(std::deque<ZMPPosition> &FinalZMPTraj_de
   m_State.com_back[10] = lStartingZMPPosition[1];
   m_OnLineMode = true;
   return 0;
+}
+
+solution_t &ZMPVelocityReferencedQP::Solution()
+{
+  if (!m_HaveLastQP) return m_Solution;
+  wg_herdt_qp_output out;
+  check(wg_herdt_qp_solve_batch(default_context(), WG_MEM_HOST, 1, &m_LastQP, &out), "wg_herdt_qp_solve_batch");
+  solution_t &S = m_Solution;
+  S.NbVariables = (unsigned)out.n_vars; S.NbConstraints = (unsigned)out.n_rows; S.Fail = out.fail;
+  S.Solution_vec.assign(out.x, out.x + out.n_vars);
+  S.ConstrLagr_vec.assign(out.lagr, out.lagr + out.n_rows);
+  S.LBoundsLagr_vec.assign(out.n_vars, 0.0); S.UBoundsLagr_vec.assign(out.n_vars, 0.0);   // the +-1e8 box never binds
+  S.SupportStates_deq.clear(); S.SupportOrientations_deq.clear(); S.TrunkOrientations_deq.clear();
+  for (int i = 0; i <= WG_HERDT_N; ++i) {
+    support_state_t st;
+    st.Phase = m_LastQP.sup_phase[i]; st.Foot = m_LastQP.sup_foot[i]; st.StepNumber = (unsigned)m_LastQP.sup_step[i];
+    st.StateChanged = m_LastQP.sup_changed[i] != 0;
+    st.X = m_LastQP.sup_x[i]; st.Y = m_LastQP.sup_y[i]; st.Yaw = m_LastQP.sup_yaw[i];
+    S.SupportStates_deq.push_back(st);
+    if (i > 0 && st.StateChanged && st.StepNumber > 0) S.SupportOrientations_deq.push_back(st.Yaw);
+  }
+  m_HaveLastQP = false;
+  return S;
 }
 
 static void tick_to_rows(const double *com11, const wg_herdt_foot_sample &L, const wg_herdt_foot_sample &R, double time,
@@ -511,7 +569,8 @@ void ZMPVelocityReferencedQP::OnLine(double time, std::deque<ZMPPosition> &Final
   m_State.clock = c0;
   wg_herdt_tick rows[WG_HERDT_TICKS_PER_STEP];
   std::memset(rows, 0, sizeof rows);
-  check(wg_herdt_mpc_run_batch(ctx, WG_MEM_HOST, 1, 1, &m_State, nullptr, rows, nullptr, nullptr), "wg_herdt_mpc_run_batch");
+  check(wg_herdt_mpc_run_batch(ctx, WG_MEM_HOST, 1, 1, &m_State, nullptr, rows, nullptr, &m_LastQP), "wg_herdt_mpc_run_batch");
+  m_HaveLastQP = true;
   m_OnLineMode = m_State.online_mode != 0;
   // deques: the inherited last element is final now (the feet part may have been rewritten), then 19 new samples,
   // then the 20th, which the state keeps as the not-yet-final element
@@ -535,85 +594,7 @@ void ZMPVelocityReferencedQP::OnLine(double time, std::deque<ZMPPosition> &Final
 // ---------------------------------------------------------------------------------------------
 // PatternGeneratorInterface (Herdt path)
 // ---------------------------------------------------------------------------------------------
-PatternGeneratorInterface::PatternGeneratorInterface(double sole_length, double sole_width)
-    : SimplePlugin(this), m_InternalClock(0.0), m_AlgorithmforZMPCOM(0), m_Running(false)
-{
-  m_PC = new PreviewControl(this, OptimalControllerSolver::MODE_WITHOUT_INITIALPOS, true);   // PGI.cpp:254
-  m_ZMPVRQP = new ZMPVelocityReferencedQP(this, "", sole_length, sole_width);                // PGI.cpp:247
-  // start configuration of the reference's sample robot in half-sitting (TestHerdt2010 datref, line 1)
-  m_StartCOM.x[0] = 0.0316055; m_StartCOM.y[0] = 0.0; m_StartCOM.z[0] = 0.7116911;
-  std::memset(&m_StartLF, 0, sizeof m_StartLF); std::memset(&m_StartRF, 0, sizeof m_StartRF);
-  m_StartLF.y = 0.09; m_StartRF.y = -0.09;
-  // PGI.cpp:186-201
-  std::string names[] = {":LimitsFeasibility", ":ZMPShiftParameters", ":TimeDistributionParameters", ":stepseq", ":finish",
-                         ":StartOnLineStepSequencing", ":StopOnLineStepSequencing", ":readfilefromkw",
-                         ":SetAlgoForZmpTrajectory", ":SetAutoFirstStep", ":ChangeNextStep", ":samplingperiod",
-                         ":HerdtOnline", ":setVelReference", ":setCoMPerturbationForce"};
-  for (auto &n : names) SimplePlugin::RegisterMethod(n);
-}
-PatternGeneratorInterface::~PatternGeneratorInterface()
-{
-  delete m_ZMPVRQP;
-  delete m_PC;
-  UnregisterPlugin(this);
-}
-void PatternGeneratorInterface::SetStartConfiguration(const COMState &com, const FootAbsolutePosition &lf,
-                                                      const FootAbsolutePosition &rf)
-{
-  m_StartCOM = com; m_StartLF = lf; m_StartRF = rf;
-}
-int PatternGeneratorInterface::ParseCmd(std::istringstream &strm)
-{
-  std::string aCmd;
-  strm >> aCmd;
-  SimplePluginManager::CallMethod(aCmd, strm);
-  return 0;
-}
-int PatternGeneratorInterface::initOnlineHerdt()
-{
-  // PGI.cpp:517-560 (the start configuration comes from SetStartConfiguration instead of the robot model)
-  std::deque<double> rel;
-  double zmp0[3] = {0.0, 0.0, 0.0};
-  m_ZMPVRQP->InitOnLine(m_ZMPPositions, m_COMBuffer, m_LeftFootPositions, m_RightFootPositions, m_StartLF, m_StartRF, rel,
-                        m_StartCOM, zmp0);
-  m_Running = true;
-  return 0;
-}
-void PatternGeneratorInterface::CallMethod(std::string &Method, std::istringstream &strm)
-{
-  if (Method == ":SetAlgoForZmpTrajectory") {
-    std::string algo;
-    strm >> algo;
-    m_AlgorithmforZMPCOM = (algo == "Herdt") ? 1 : 0;
-  } else if (Method == ":HerdtOnline") {
-    initOnlineHerdt();             // the handler takes no argument: the three numbers of the test are ignored (PGI.cpp:1103-1109)
-  } else if (Method == ":setVelReference") {
-    m_ZMPVRQP->Reference(strm);
-  } else if (Method == ":setCoMPerturbationForce") {
-    double x = 0, y = 0;
-    strm >> x >> y;
-    m_ZMPVRQP->setCoMPerturbationForce(x, y);
-  }
-  // the other PGI commands configure subsystems outside the accelerated path (step stack, Kajita strategy): accepted, no-op
-}
-bool PatternGeneratorInterface::RunOneStepOfTheControlLoop(COMState &COMStateOut, ZMPPosition &ZMPTarget,
-                                                           FootAbsolutePosition &LeftFootPosition,
-                                                           FootAbsolutePosition &RightFootPosition)
-{
-  m_InternalClock += 0.005;        // PGI.cpp:1256
-  if (!m_Running) return false;
-  if (m_AlgorithmforZMPCOM == 1)
-    m_ZMPVRQP->OnLine(m_InternalClock, m_ZMPPositions, m_COMBuffer, m_LeftFootPositions, m_RightFootPositions);
-  // CoMAndFootOnlyStrategy::OneGlobalStepOfControl, CoMAndFootOnlyStrategy.cpp:56-124
-  if (m_ZMPPositions.empty() || m_COMBuffer.empty() || m_LeftFootPositions.empty() || m_RightFootPositions.empty()) {
-    m_Running = false;
-    return false;
-  }
-  COMStateOut = m_COMBuffer.front(); ZMPTarget = m_ZMPPositions.front();
-  LeftFootPosition = m_LeftFootPositions.front(); RightFootPosition = m_RightFootPositions.front();
-  m_COMBuffer.pop_front(); m_ZMPPositions.pop_front(); m_LeftFootPositions.pop_front(); m_RightFootPositions.pop_front();
-  return true;
-}
+// (PatternGeneratorInterface: see walkgen_host_pgi.cpp)
 
 }  // namespace PatternGeneratorJRL
 
@@ -711,8 +692,8 @@ void ZMPConstrainedQPFastFormulation::CallMethod(std::string &Method, std::istri
 
 void ZMPConstrainedQPFastFormulation::GetZMPDiscretization(
     std::deque<ZMPPosition> &ZMPPositions, std::deque<COMState> &COMStates, std::deque<RelativeFootPosition> &Rel,
-    std::deque<FootAbsolutePosition> &Left, std::deque<FootAbsolutePosition> &Right, double, COMState &, double[3],
-    FootAbsolutePosition &InitLeft, FootAbsolutePosition &InitRight)
+    std::deque<FootAbsolutePosition> &Left, std::deque<FootAbsolutePosition> &Right, double, COMState &,
+    MAL_S3_VECTOR_TYPE(double) &, FootAbsolutePosition &InitLeft, FootAbsolutePosition &InitRight)
 {
   if (Rel.empty()) return;
   wg_ctx *ctx = walkgen_b200::default_context();

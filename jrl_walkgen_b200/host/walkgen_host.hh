@@ -46,7 +46,64 @@ class Matrix {
 
 }  // namespace walkgen_b200
 
+/* ---- stand-ins for the abstract-robot-dynamics interfaces the hot path reads ------------------------------------------
+ * The reference asks its CjrlHumanoidDynamicRobot for exactly this on the accelerated path: the sole size and ankle
+ * position of the feet (relative-feet-inequalities.cpp:153-182, FootConstraintsAsLinearSystem.cpp:269-281) and the bounds
+ * of the hip-yaw joints, found as jointsBetween(waist, ankle)[1] (OrientationsPreview.cpp:42-68).  A build that has the real
+ * abstract-robot-dynamics headers defines WALKGEN_B200_HAVE_ABSTRACT_ROBOT_DYNAMICS and passes its own robot. */
+#ifndef WALKGEN_B200_HAVE_ABSTRACT_ROBOT_DYNAMICS
+struct vector3d {
+  double v[3];
+  double &operator[](int i) { return v[i]; }
+  const double &operator[](int i) const { return v[i]; }
+};
+class CjrlJoint {
+ public:
+  CjrlJoint(double lower = 0.0, double upper = 0.0, double upperVelocity = 0.0) : m_Lo(lower), m_Up(upper), m_Vel(upperVelocity) {}
+  double lowerBound(unsigned int) const { return m_Lo; }
+  double upperBound(unsigned int) const { return m_Up; }
+  double upperVelocityBound(unsigned int) const { return m_Vel; }
+ private:
+  double m_Lo, m_Up, m_Vel;
+};
+class CjrlFoot {
+ public:
+  CjrlFoot(double soleLength = 0.25, double soleWidth = 0.14, double ankleHeight = 0.105)
+      : m_Length(soleLength), m_Width(soleWidth) { m_Ankle[0] = 0.0; m_Ankle[1] = 0.0; m_Ankle[2] = ankleHeight; }
+  void getSoleSize(double &outLength, double &outWidth) const { outLength = m_Length; outWidth = m_Width; }
+  void getAnklePositionInLocalFrame(vector3d &out) const { for (int i = 0; i < 3; ++i) out[i] = m_Ankle[i]; }
+  CjrlJoint *associatedAnkle() { return &m_AnkleJoint; }
+ private:
+  double m_Length, m_Width, m_Ankle[3];
+  CjrlJoint m_AnkleJoint;
+};
+/* Defaults: the sole of the reference's test robot (0.25 x 0.14 m) and hip-yaw joints without limits (equal
+ * bounds make OrientationsPreview fall back to -30 / +45 degrees; a zero velocity bound is what the datref-era robot file
+ * gave). */
+class CjrlHumanoidDynamicRobot {
+ public:
+  CjrlHumanoidDynamicRobot(double soleLength = 0.25, double soleWidth = 0.14, double ankleHeight = 0.105)
+      : m_Left(soleLength, soleWidth, ankleHeight), m_Right(soleLength, soleWidth, ankleHeight) {}
+  CjrlFoot *leftFoot() { return &m_Left; }
+  CjrlFoot *rightFoot() { return &m_Right; }
+  CjrlJoint *waist() { return &m_Waist; }
+  /* waist -> hip yaw -> ankle: element [1] is the hip-yaw joint of that leg, as the reference indexes it */
+  std::vector<CjrlJoint *> jointsBetween(const CjrlJoint &, const CjrlJoint &inEndJoint)
+  {
+    const bool left = (&inEndJoint == m_Left.associatedAnkle());
+    std::vector<CjrlJoint *> r;
+    r.push_back(&m_Waist); r.push_back(left ? &m_LeftHipYaw : &m_RightHipYaw); r.push_back(left ? m_Left.associatedAnkle() : m_Right.associatedAnkle());
+    return r;
+  }
+  void setHipYawJoints(const CjrlJoint &left, const CjrlJoint &right) { m_LeftHipYaw = left; m_RightHipYaw = right; }
+ private:
+  CjrlFoot m_Left, m_Right;
+  CjrlJoint m_Waist, m_LeftHipYaw, m_RightHipYaw;
+};
+#endif
+
 #define MAL_MATRIX(name, type) walkgen_b200::Matrix name
+#define MAL_VECTOR_TYPE(type) std::vector<type>
 #define MAL_MATRIX_DIM(name, type, r, c) walkgen_b200::Matrix name(r, c)
 #define MAL_MATRIX_RESIZE(name, r, c) (name).resize(r, c)
 #define MAL_MATRIX_NB_ROWS(name) (name).size1()
@@ -72,6 +129,14 @@ struct FootAbsolutePosition {
   double ddx, ddy, ddz, ddtheta, ddomega, ddomega2;
   double time;
   int stepType;
+};
+
+typedef COMState COMPosition;            /* include/jrl/walkgen/pgtypes.hh:88 (deprecated alias kept by the reference) */
+struct RelativeFootPosition {            /* include/jrl/walkgen/pgtypes.hh:100-109 */
+  double sx, sy, theta;
+  double SStime, DStime;
+  int stepType;
+  double DeviationHipHeight;
 };
 
 class SimplePluginManager;
@@ -194,20 +259,60 @@ class PLDPSolver {
 
 namespace PatternGeneratorJRL {
 
+class StepStackHandler;
+
+/* MAL_S3_VECTOR_TYPE(double) of the reference signatures: a 3-vector with (i) / [i] access */
+struct S3Vector {
+  double v[3];
+  S3Vector() { v[0] = v[1] = v[2] = 0.0; }
+  double &operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+  double &operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+};
+#define MAL_S3_VECTOR_TYPE(type) PatternGeneratorJRL::S3Vector
+
+/* The virtual interface of src/ZMPRefTrajectoryGeneration/ZMPRefTrajectoryGeneration.hh:208-328, signature for signature. */
 class ZMPRefTrajectoryGeneration : public SimplePlugin {
  public:
   explicit ZMPRefTrajectoryGeneration(SimplePluginManager *lSPM);
   virtual ~ZMPRefTrajectoryGeneration() {}
+  virtual void GetZMPDiscretization(std::deque<ZMPPosition> &ZMPPositions, std::deque<COMState> &COMStates,
+                                    std::deque<RelativeFootPosition> &RelativeFootPositions,
+                                    std::deque<FootAbsolutePosition> &LeftFootAbsolutePositions,
+                                    std::deque<FootAbsolutePosition> &RightFootAbsolutePositions, double Xmax,
+                                    COMState &lStartingCOMState, MAL_S3_VECTOR_TYPE(double) &lStartingZMPPosition,
+                                    FootAbsolutePosition &InitLeftFootAbsolutePosition,
+                                    FootAbsolutePosition &InitRightFootAbsolutePosition) = 0;
   virtual int InitOnLine(std::deque<ZMPPosition> &FinalZMPPositions, std::deque<COMState> &CoMStates,
                          std::deque<FootAbsolutePosition> &FinalLeftFootTraj_deq,
                          std::deque<FootAbsolutePosition> &FinalRightFootTraj_deq,
                          FootAbsolutePosition &InitLeftFootAbsolutePosition,
-                         FootAbsolutePosition &InitRightFootAbsolutePosition, std::deque<double> &RelativeFootPositions,
-                         COMState &lStartingCOMState, double lStartingZMPPosition[3]) = 0;
+                         FootAbsolutePosition &InitRightFootAbsolutePosition,
+                         std::deque<RelativeFootPosition> &RelativeFootPositions, COMState &lStartingCOMState,
+                         MAL_S3_VECTOR_TYPE(double) &lStartingZMPPosition) = 0;
+  virtual void OnLineAddFoot(RelativeFootPosition &NewRelativeFootPosition, std::deque<ZMPPosition> &FinalZMPPositions,
+                             std::deque<COMState> &COMStates, std::deque<FootAbsolutePosition> &FinalLeftFootAbsolutePositions,
+                             std::deque<FootAbsolutePosition> &FinalRightFootAbsolutePositions, bool EndSequence) = 0;
   virtual void OnLine(double time, std::deque<ZMPPosition> &FinalZMPPositions, std::deque<COMState> &CoMStates,
                       std::deque<FootAbsolutePosition> &FinalLeftFootTraj_deq,
                       std::deque<FootAbsolutePosition> &FinalRightFootTraj_deq) = 0;
+  virtual void EndPhaseOfTheWalking(std::deque<ZMPPosition> &ZMPPositions, std::deque<COMState> &FinalCOMStates,
+                                    std::deque<FootAbsolutePosition> &LeftFootAbsolutePositions,
+                                    std::deque<FootAbsolutePosition> &RightFootAbsolutePositions) = 0;
+  virtual int OnLineFootChange(double time, FootAbsolutePosition &aFootAbsolutePosition,
+                               std::deque<ZMPPosition> &FinalZMPPositions, std::deque<COMState> &COMStates,
+                               std::deque<FootAbsolutePosition> &FinalLeftFootAbsolutePositions,
+                               std::deque<FootAbsolutePosition> &FinalRightFootAbsolutePositions,
+                               StepStackHandler *aStepStackHandler) = 0;
+  virtual int ReturnOptimalTimeToRegenerateAStep() = 0;
   virtual void CallMethod(std::string &Method, std::istringstream &strm);
+  void SetTSingleSupport(double v) { m_Tsingle = v; }
+  void SetTDoubleSupport(double v) { m_Tdble = v; }
+  void SetSamplingPeriod(double v) { m_SamplingPeriod = v; }
+  void SetComHeight(double v) { m_ComHeight = v; }
+  double GetCurrentTime() const { return m_CurrentTime; }
+  void SetCurrentTime(double t) { m_CurrentTime = t; }
   double GetTSingleSupport() const { return m_Tsingle; }
   double GetTDoubleSupport() const { return m_Tdble; }
   double GetSamplingPeriod() const { return m_SamplingPeriod; }
@@ -215,7 +320,26 @@ class ZMPRefTrajectoryGeneration : public SimplePlugin {
   bool GetOnLineMode() const { return m_OnLineMode; }
  protected:
   double m_Tsingle, m_Tdble, m_SamplingPeriod, m_Omega, m_ComHeight, m_StepHeight;
+  double m_CurrentTime;
   bool m_OnLineMode;
+};
+
+/* Herdt's solution_t (src/privatepgtypes.hh:340-404): the fields a caller of ZMPVelocityReferencedQP::Solution() reads. */
+struct support_state_t {                 /* src/privatepgtypes.hh:291-320 */
+  int Phase, Foot;                       /* WG_SS / WG_DS, WG_LEFT / WG_RIGHT */
+  unsigned int StepNumber;
+  bool StateChanged;
+  double X, Y, Yaw;
+};
+struct solution_t {
+  unsigned int NbVariables, NbConstraints;
+  int Fail, Print;
+  bool useWarmStart;
+  std::vector<double> Solution_vec, initialSolution;
+  std::deque<double> SupportOrientations_deq, TrunkOrientations_deq;
+  std::deque<support_state_t> SupportStates_deq;
+  std::vector<double> ConstrLagr_vec, LBoundsLagr_vec, UBoundsLagr_vec;
+  solution_t() : NbVariables(0), NbConstraints(0), Fail(0), Print(0), useWarmStart(false) {}
 };
 
 class ZMPVelocityReferencedQP : public ZMPRefTrajectoryGeneration {
@@ -223,12 +347,30 @@ class ZMPVelocityReferencedQP : public ZMPRefTrajectoryGeneration {
   /* the robot is only asked for its sole size in the reference (RelativeFeetInequalities): pass it directly */
   ZMPVelocityReferencedQP(SimplePluginManager *lSPM, std::string DataFile, double sole_length = 0.25,
                           double sole_width = 0.14);
+  /* the reference's constructor (ZMPVelocityReferencedQP.hh:59-60): sole size and hip-yaw joint bounds are read from the
+   * robot as RelativeFeetInequalities / OrientationsPreview do */
+  ZMPVelocityReferencedQP(SimplePluginManager *lSPM, std::string DataFile, CjrlHumanoidDynamicRobot *aHS);
   ~ZMPVelocityReferencedQP();
   int InitOnLine(std::deque<ZMPPosition> &FinalZMPPositions, std::deque<COMState> &CoMStates,
                  std::deque<FootAbsolutePosition> &FinalLeftFootTraj_deq,
                  std::deque<FootAbsolutePosition> &FinalRightFootTraj_deq,
                  FootAbsolutePosition &InitLeftFootAbsolutePosition, FootAbsolutePosition &InitRightFootAbsolutePosition,
-                 std::deque<double> &RelativeFootPositions, COMState &lStartingCOMState, double lStartingZMPPosition[3]);
+                 std::deque<RelativeFootPosition> &RelativeFootPositions, COMState &lStartingCOMState,
+                 MAL_S3_VECTOR_TYPE(double) &lStartingZMPPosition);
+  /* the off-line / foot-by-foot entry points are empty in the reference too (ZMPVelocityReferencedQP.cpp:462-521) */
+  void GetZMPDiscretization(std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<RelativeFootPosition> &,
+                            std::deque<FootAbsolutePosition> &, std::deque<FootAbsolutePosition> &, double, COMState &,
+                            MAL_S3_VECTOR_TYPE(double) &, FootAbsolutePosition &, FootAbsolutePosition &) {}
+  void OnLineAddFoot(RelativeFootPosition &, std::deque<ZMPPosition> &, std::deque<COMState> &,
+                     std::deque<FootAbsolutePosition> &, std::deque<FootAbsolutePosition> &, bool) {}
+  void EndPhaseOfTheWalking(std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
+                            std::deque<FootAbsolutePosition> &) {}
+  int OnLineFootChange(double, FootAbsolutePosition &, std::deque<ZMPPosition> &, std::deque<COMState> &,
+                       std::deque<FootAbsolutePosition> &, std::deque<FootAbsolutePosition> &, StepStackHandler *) { return -1; }
+  int ReturnOptimalTimeToRegenerateAStep() { return 2 * (int)(1.6 / m_SamplingPeriod); }
+  /* Solution_ of the last QP (ZMPVelocityReferencedQP.hh:126): Solution_vec, multipliers and the previewed support states,
+   * obtained by solving the recorded QP of the last period once more through wg_herdt_qp_solve_batch */
+  solution_t &Solution();
   void OnLine(double time, std::deque<ZMPPosition> &FinalZMPPositions, std::deque<COMState> &CoMStates,
               std::deque<FootAbsolutePosition> &FinalLeftFootTraj_deq,
               std::deque<FootAbsolutePosition> &FinalRightFootTraj_deq);
@@ -237,6 +379,7 @@ class ZMPVelocityReferencedQP : public ZMPRefTrajectoryGeneration {
   bool Running() const { return m_State.running != 0; }
   void EndingPhase(bool EndingPhase) { m_State.ending_phase = EndingPhase; }
   void setCoMPerturbationForce(double, double) {}   /* parsed but never consumed by the reference either */
+  void setCoMPerturbationForce(std::istringstream &strm) { double x, y; strm >> x >> y; }
   unsigned QP_N() const { return WG_HERDT_N; }
   void CallMethod(std::string &Method, std::istringstream &strm);
   /* datref-era initial support frame ("oracle pins") */
@@ -255,15 +398,97 @@ class ZMPVelocityReferencedQP : public ZMPRefTrajectoryGeneration {
   double m_SoleLength, m_SoleWidth;
   bool m_ParamsDirty;
   unsigned m_StepsBeforeStop;
+  wg_herdt_qp_input m_LastQP;
+  bool m_HaveLastQP;
+  solution_t m_Solution;
+};
+
+/* ---- Kajita2003 front end: the step stack and the ZMP / feet discretisation -------------------------------------- */
+class StepStackHandler : public SimplePlugin {   /* src/StepStackHandler.hh */
+ public:
+  explicit StepStackHandler(SimplePluginManager *lSPM);
+  void ReadStepSequenceAccordingToWalkMode(std::istringstream &strm);   /* walk modes 0, 4, 5 (1 / 3 read and drop the hip height) */
+  void CreateArcInStepStack(double x, double y, double R, double arc_deg, int SupportFoot);
+  void CreateArcCenteredInStepStack(double R, double arc_deg, int SupportFoot);   /* not provided: throws */
+  void PrepareForSupportFoot(int SupportFoot);
+  void FinishOnTheLastCorrectSupportFoot();
+  void AddStepInTheStack(double sx, double sy, double theta, double sstime, double dstime);
+  void AddStandardOnLineStep(bool NewStep, double NewStepX, double NewStepY, double NewTheta);
+  void PushFrontAStepInTheStack(RelativeFootPosition &aRFP) { m_RelativeFootPositions.push_front(aRFP); }
+  bool RemoveFirstStepInTheStack();
+  void CopyRelativeFootPosition(std::deque<RelativeFootPosition> &lRelativeFootPositions, bool PerformClean);
+  RelativeFootPosition ReturnBackFootPosition() { return m_RelativeFootPositions.back(); }
+  bool ReturnFrontFootPosition(RelativeFootPosition &aRFP);
+  int ReturnStackSize() { return (int)m_RelativeFootPositions.size(); }
+  void ClearStack() { m_RelativeFootPositions.clear(); }
+  void SetWalkMode(int lWalkMode) { m_WalkMode = lWalkMode; }
+  int GetWalkMode() { return m_WalkMode; }
+  void SetSingleTimeSupport(double v) { m_SingleSupportTime = v; }
+  double GetSingleTimeSupport() { return m_SingleSupportTime; }
+  void SetDoubleTimeSupport(double v) { m_DoubleSupportTime = v; }
+  double GetDoubleTimeSupport() { return m_DoubleSupportTime; }
+  void StartOnLineStep() { m_OnLineSteps = true; }
+  void StopOnLineStep();
+  bool IsOnLineSteppingOn() { return m_OnLineSteps; }
+  void m_PartialStepSequence(std::istringstream &strm);
+  void CallMethod(std::string &Method, std::istringstream &strm);
+ private:
+  std::deque<RelativeFootPosition> m_RelativeFootPositions;
+  double m_SingleSupportTime, m_DoubleSupportTime;
+  int m_WalkMode, m_KeepLastCorrectSupportFoot;
+  bool m_OnLineSteps, m_TransitionFinishOnLine;
+};
+
+/* ZMPDiscretization (src/ZMPRefTrajectoryGeneration/ZMPDiscretization.hh): footsteps -> 5 ms ZMP reference + both feet.
+ * Every sample comes from zmpdisc_kernel (wg_zmpdisc_run_batch, batch of one walk).  The on-line entry points rest on
+ * the prefix property of the generator (a walk is a chain of segments - lead-in, one per step, end phase - each of which
+ * only depends on the state the previous one left): the walk given so far is discretised again and the samples not yet
+ * handed out are appended to the caller's queues. */
+class ZMPDiscretization : public ZMPRefTrajectoryGeneration {
+ public:
+  ZMPDiscretization(SimplePluginManager *lSPM, std::string DataFile = "", CjrlHumanoidDynamicRobot *aHS = 0);
+  ~ZMPDiscretization();
+  void GetZMPDiscretization(std::deque<ZMPPosition> &ZMPPositions, std::deque<COMState> &COMStates,
+                            std::deque<RelativeFootPosition> &RelativeFootPositions,
+                            std::deque<FootAbsolutePosition> &LeftFootAbsolutePositions,
+                            std::deque<FootAbsolutePosition> &RightFootAbsolutePositions, double Xmax,
+                            COMState &lStartingCOMState, MAL_S3_VECTOR_TYPE(double) &lStartingZMPPosition,
+                            FootAbsolutePosition &InitLeftFootAbsolutePosition,
+                            FootAbsolutePosition &InitRightFootAbsolutePosition);
+  int InitOnLine(std::deque<ZMPPosition> &FinalZMPPositions, std::deque<COMState> &CoMStates,
+                 std::deque<FootAbsolutePosition> &FinalLeftFootAbsolutePositions,
+                 std::deque<FootAbsolutePosition> &FinalRightFootAbsolutePositions,
+                 FootAbsolutePosition &InitLeftFootAbsolutePosition, FootAbsolutePosition &InitRightFootAbsolutePosition,
+                 std::deque<RelativeFootPosition> &RelativeFootPositions, COMState &lStartingCOMState,
+                 MAL_S3_VECTOR_TYPE(double) &lStartingZMPPosition);
+  void OnLineAddFoot(RelativeFootPosition &NewRelativeFootPosition, std::deque<ZMPPosition> &FinalZMPPositions,
+                     std::deque<COMState> &COMStates, std::deque<FootAbsolutePosition> &FinalLeftFootAbsolutePositions,
+                     std::deque<FootAbsolutePosition> &FinalRightFootAbsolutePositions, bool EndSequence);
+  /* the Kajita generator has no per-tick work: its queues are filled foot by foot (ZMPDiscretization.cpp:562-571) */
+  void OnLine(double, std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
+              std::deque<FootAbsolutePosition> &) {}
+  void EndPhaseOfTheWalking(std::deque<ZMPPosition> &ZMPPositions, std::deque<COMState> &FinalCOMStates,
+                            std::deque<FootAbsolutePosition> &LeftFootAbsolutePositions,
+                            std::deque<FootAbsolutePosition> &RightFootAbsolutePositions);
+  /* returns -1 in the reference as well (ZMPDiscretization.cpp:1111-1120) */
+  int OnLineFootChange(double, FootAbsolutePosition &, std::deque<ZMPPosition> &, std::deque<COMState> &,
+                       std::deque<FootAbsolutePosition> &, std::deque<FootAbsolutePosition> &, StepStackHandler *) { return -1; }
+  int ReturnOptimalTimeToRegenerateAStep();
+  void SetZMPShift(std::vector<double> &ZMPShift);
+  void SetPreviewControlTime(double v) { m_PreviewControlTime = v; }
+  void CallMethod(std::string &Method, std::istringstream &strm);
+ private:
+  /* discretise m_Steps (+ end phase) and append samples [m_Emitted, upto) to the queues */
+  void emit(std::deque<ZMPPosition> &Z, std::deque<COMState> &C, std::deque<FootAbsolutePosition> &L,
+            std::deque<FootAbsolutePosition> &R, bool with_end_phase);
+  wg_zmpdisc_params m_Zd;
+  double m_PreviewControlTime;
+  std::vector<wg_rel_step> m_Steps;
+  double m_InitFeet[6];
+  int64_t m_Emitted;
 };
 
 /* ---- Dimitrov2008 path: the classes around PLDPSolver (names and signatures of the reference) ------------------------ */
-struct RelativeFootPosition {            /* include/jrl/walkgen/pgtypes.hh:100-109 */
-  double sx, sy, theta;
-  double SStime, DStime;
-  int stepType;
-  double DeviationHipHeight;
-};
 typedef struct { double col, row; } CH_Point;                       /* src/Mathematics/ConvexHull.hh:39-42 */
 struct LinearConstraintInequality_t {    /* include/jrl/walkgen/pgtypes.hh:168-177; A z + B >= 0 */
   MAL_MATRIX(A, double);
@@ -302,7 +527,7 @@ class ZMPConstrainedQPFastFormulation : public ZMPRefTrajectoryGeneration {   /*
                             std::deque<RelativeFootPosition> &RelativeFootPositions,
                             std::deque<FootAbsolutePosition> &LeftFootAbsolutePositions,
                             std::deque<FootAbsolutePosition> &RightFootAbsolutePositions, double Xmax,
-                            COMState &lStartingCOMState, double lStartingZMPPosition[3],
+                            COMState &lStartingCOMState, MAL_S3_VECTOR_TYPE(double) &lStartingZMPPosition,
                             FootAbsolutePosition &InitLeftFootAbsolutePosition,
                             FootAbsolutePosition &InitRightFootAbsolutePosition);
   int InitConstants();
@@ -319,10 +544,17 @@ class ZMPConstrainedQPFastFormulation : public ZMPRefTrajectoryGeneration {   /*
   int PeriodsDone() const { return m_Done; }
   /* InitOnLine / OnLine are not provided by the reference for this generator either (they return 0 / do nothing) */
   int InitOnLine(std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
-                 std::deque<FootAbsolutePosition> &, FootAbsolutePosition &, FootAbsolutePosition &, std::deque<double> &,
-                 COMState &, double[3]) { return 0; }
+                 std::deque<FootAbsolutePosition> &, FootAbsolutePosition &, FootAbsolutePosition &,
+                 std::deque<RelativeFootPosition> &, COMState &, MAL_S3_VECTOR_TYPE(double) &) { return 0; }
+  void OnLineAddFoot(RelativeFootPosition &, std::deque<ZMPPosition> &, std::deque<COMState> &,
+                     std::deque<FootAbsolutePosition> &, std::deque<FootAbsolutePosition> &, bool) {}
   void OnLine(double, std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
               std::deque<FootAbsolutePosition> &) {}
+  void EndPhaseOfTheWalking(std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
+                            std::deque<FootAbsolutePosition> &) {}
+  int OnLineFootChange(double, FootAbsolutePosition &, std::deque<ZMPPosition> &, std::deque<COMState> &,
+                       std::deque<FootAbsolutePosition> &, std::deque<FootAbsolutePosition> &, StepStackHandler *) { return -1; }
+  int ReturnOptimalTimeToRegenerateAStep() { return 0; }
  private:
   wg_dimitrov_params m_Par;
   wg_zmpdisc_params m_Zd;
@@ -330,10 +562,14 @@ class ZMPConstrainedQPFastFormulation : public ZMPRefTrajectoryGeneration {   /*
   int m_Status, m_Done;
 };
 
-/* The PGI facade for the Herdt path: command bus + the 5 ms tick. */
+/* The PGI facade (include/jrl/walkgen/patterngeneratorinterface.hh:55-306) for the accelerated paths: command bus + the
+ * 5 ms tick, for the Herdt on-line generator and for the Kajita off-line / on-line step sequences.  Whole-body inverse
+ * kinematics and the multibody second preview stage are outside the accelerated path: as with the
+ * reference's CoMAndFootOnlyStrategy the configuration / velocity / acceleration vectors are left as the caller passed them. */
 class PatternGeneratorInterface : public SimplePluginManager, public SimplePlugin {
  public:
   PatternGeneratorInterface(double sole_length = 0.25, double sole_width = 0.14);
+  explicit PatternGeneratorInterface(CjrlHumanoidDynamicRobot *aHDR);
   ~PatternGeneratorInterface();
   /* Reads the first token and broadcasts the rest (PatternGeneratorInterfacePrivate.cpp:1030-1041). */
   int ParseCmd(std::istringstream &strm);
@@ -342,14 +578,45 @@ class PatternGeneratorInterface : public SimplePluginManager, public SimplePlugi
    * Returns false when the deques ran empty (end of the motion). */
   bool RunOneStepOfTheControlLoop(COMState &COMStateOut, ZMPPosition &ZMPTarget, FootAbsolutePosition &LeftFootPosition,
                                   FootAbsolutePosition &RightFootPosition);
+  /* the four overloads of patterngeneratorinterface.hh:115-176 */
+  bool RunOneStepOfTheControlLoop(MAL_VECTOR_TYPE(double) &CurrentConfiguration, MAL_VECTOR_TYPE(double) &CurrentVelocity,
+                                  MAL_VECTOR_TYPE(double) &CurrentAcceleration, MAL_VECTOR_TYPE(double) &ZMPTarget);
+  bool RunOneStepOfTheControlLoop(MAL_VECTOR_TYPE(double) &CurrentConfiguration, MAL_VECTOR_TYPE(double) &CurrentVelocity,
+                                  MAL_VECTOR_TYPE(double) &CurrentAcceleration, MAL_VECTOR_TYPE(double) &ZMPTarget,
+                                  COMState &COMState, FootAbsolutePosition &LeftFootPosition,
+                                  FootAbsolutePosition &RightFootPosition);
+  bool RunOneStepOfTheControlLoop(FootAbsolutePosition &LeftFootPosition, FootAbsolutePosition &RightFootPosition,
+                                  ZMPPosition &ZMPRefPos, COMPosition &COMRefPos);
+  /* (the COMPosition flavour of the 7-argument overload is the same function: COMPosition is a typedef of COMState) */
+  void ReadSequenceOfSteps(std::istringstream &strm);
+  void FinishAndRealizeStepSequence();
+  void StartOnLineStepSequencing();
+  void StopOnLineStepSequencing();
+  void AddOnLineStep(double X, double Y, double Theta);
+  void AddStepInStack(double dx, double dy, double theta);
+  int GetWalkMode() const { return m_StepStackHandler->GetWalkMode(); }
   void setVelocityReference(double x, double y, double yaw) { m_ZMPVRQP->Reference(x, y, yaw); }
+  StepStackHandler *SSH() { return m_StepStackHandler; }
+  ZMPDiscretization *ZMPD() { return m_ZMPD; }
+  /* CoM of the first preview stage for the tick last returned (the Kajita path; the reference's second stage needs the
+   * multibody robot model) */
+  const std::deque<COMState> &COMBuffer() const { return m_COMBuffer; }
   void SetStartConfiguration(const COMState &com, const FootAbsolutePosition &lf, const FootAbsolutePosition &rf);
   ZMPVelocityReferencedQP *VRQP() { return m_ZMPVRQP; }
   PreviewControl *PC() { return m_PC; }
  private:
   int initOnlineHerdt();
+  void construct(double sole_length, double sole_width, CjrlHumanoidDynamicRobot *aHDR);
+  void kajitaPreviewOverQueues();
   ZMPVelocityReferencedQP *m_ZMPVRQP;
   PreviewControl *m_PC;
+  StepStackHandler *m_StepStackHandler;
+  ZMPDiscretization *m_ZMPD;
+  CjrlHumanoidDynamicRobot *m_OwnRobot;
+  std::vector<double> m_ZMPShift;
+  bool m_AutoFirstStep, m_KajitaOnLine;
+  double m_PreviewState[8];             /* x[3], y[3], sxzmp, syzmp of the first preview stage */
+  size_t m_PreviewedUpTo;               /* samples of the queues whose CoM has been computed */
   std::deque<ZMPPosition> m_ZMPPositions;
   std::deque<COMState> m_COMBuffer;
   std::deque<FootAbsolutePosition> m_LeftFootPositions, m_RightFootPositions;
@@ -359,6 +626,9 @@ class PatternGeneratorInterface : public SimplePluginManager, public SimplePlugi
   int m_AlgorithmforZMPCOM;   /* 0 Kajita (default), 1 Herdt */
   bool m_Running;
 };
+
+/* patterngeneratorinterface.hh:306 */
+PatternGeneratorInterface *patternGeneratorInterfaceFactory(CjrlHumanoidDynamicRobot *aHDR);
 
 }  // namespace PatternGeneratorJRL
 

@@ -7,6 +7,7 @@
 //   host_api_test preview <out.bin>
 //   host_api_test pldp <in.bin> <out.bin>
 //   host_api_test preview1d <gains.ini> <in.bin> <out.bin>
+//   host_api_test kajita2003 <profile> <out.dat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -185,6 +186,64 @@ static int test_preview(const char *out)
   return worst < 1e-10 ? 0 : 5;
 }
 
+// ---- tests/TestKajita2003.cpp through ParseCmd + the 5 ms tick ------------------------------------------------------
+// profile: StraightWalking (:stepseq, tests/TestKajita2003.cpp:104-119), Circle (:supportfoot / :arc / :lastsupport /
+// :finish, :68-92), OnLine (:StartOnLineStepSequencing + :StopOnLineStepSequencing after 5 s).  Writes one row per tick:
+// time, CoM x y z yaw dx dy (7), ZMP ref px py (2), left foot x y z theta omega omega2 (6), right foot (6) = 22 columns.
+static int test_kajita2003(const char *profile, const char *out)
+{
+  CjrlHumanoidDynamicRobot robot;                                  // sole 0.25 x 0.14, ankle height 0.105
+  PatternGeneratorInterface *aPGI = patternGeneratorInterfaceFactory(&robot);
+  // tests/CommonTools.cpp:56-76
+  const char *common[] = {":comheight 0.8078", ":samplingperiod 0.005", ":previewcontroltime 1.6", ":omega 0.0",
+                          ":stepheight 0.07", ":singlesupporttime 0.78", ":doublesupporttime 0.02", ":armparameters 0.5",
+                          ":LimitsFeasibility 0.0", ":ZMPShiftParameters 0.015 0.015 0.015 0.015",
+                          ":TimeDistributionParameters 2.0 3.7 1.7 3.0", ":UpperBodyMotionParameters -0.1 -1.0 0.0"};
+  for (const char *c : common) cmd(*aPGI, c);
+  // start configuration of the HRP-2 half-sitting pose as the reference evaluates it (first row of the Kajita datrefs)
+  COMState com0; FootAbsolutePosition lf0, rf0;
+  std::memset(&lf0, 0, sizeof lf0); std::memset(&rf0, 0, sizeof rf0);
+  com0.z[0] = 0.8078; lf0.x = rf0.x = 0.00949035; lf0.y = 0.095; rf0.y = -0.095;
+  aPGI->SetStartConfiguration(com0, lf0, rf0);
+  const std::string prof(profile);
+  cmd(*aPGI, ":SetAlgoForZmpTrajectory Kajita");
+  if (prof == "StraightWalking") {
+    cmd(*aPGI, ":stepseq 0.0 -0.105 0.0 0.2 0.21 0.0 0.2 -0.21 0.0 0.2 0.21 0.0 0.2 -0.21 0.0 0.2 0.21 0.0 0.2 -0.21 0.0 "
+               "0.2 0.21 0.0 0.2 -0.21 0.0 0.2 0.21 0.0 0.2 -0.21 0.0 0.2 0.21 0.0 0.2 -0.21 0.0 0.2 0.21 0.0 0.2 -0.21 0.0 0.0 0.21 0.0");
+  } else if (prof == "Circle") {
+    cmd(*aPGI, ":supportfoot 1");
+    cmd(*aPGI, ":arc 0.0 0.75 30.0 -1");
+    cmd(*aPGI, ":lastsupport");
+    cmd(*aPGI, ":finish");
+  } else if (prof == "OnLine") {
+    cmd(*aPGI, ":StartOnLineStepSequencing 0.0 -0.105 0.0 0.2 0.21 0.0 0.2 -0.21 0.0 0.2 0.21 0.0");
+  } else {
+    return 2;
+  }
+  std::ofstream aof(out);
+  aof.precision(10);
+  aof.setf(std::ios::scientific, std::ios::floatfield);
+  // the vector overload of patterngeneratorinterface.hh:152-158, as TestObject.cpp:280-300 calls it
+  std::vector<double> conf(36, 0.0), vel(36, 0.0), acc(36, 0.0), zmptarget(3, 0.0);
+  COMState com; FootAbsolutePosition lf, rf;
+  int it = 0;
+  for (; it < 40000; ++it) {
+    if (prof == "OnLine" && it == 1000) cmd(*aPGI, ":StopOnLineStepSequencing");
+    if (!aPGI->RunOneStepOfTheControlLoop(conf, vel, acc, zmptarget, com, lf, rf)) break;
+    aof << (it + 1) * 0.005 << " " << com.x[0] << " " << com.y[0] << " " << com.z[0] << " " << com.yaw[0] << " " << com.x[1]
+        << " " << com.y[1] << " " << zmptarget[0] << " " << zmptarget[1];
+    const FootAbsolutePosition *ff[2] = {&lf, &rf};
+    for (int f = 0; f < 2; ++f)
+      aof << " " << ff[f]->x << " " << ff[f]->y << " " << ff[f]->z << " " << ff[f]->theta << " " << ff[f]->omega << " "
+          << ff[f]->omega2;
+    aof << std::endl;
+  }
+  for (double v : conf) if (v != 0.0) return 3;                   // joint space is left untouched on this path
+  std::cout << "ticks written: " << it << std::endl;
+  delete aPGI;
+  return it > 0 ? 0 : 1;
+}
+
 // ---- PreviewControl: ReadPrecomputedFile + both OneIterationOfPreview1D overloads on inputs from a file --------------
 // in.bin : int32 L, ncases; double z[L] (deque overload, run with lindex = k over the whole buffer from a zero state);
 //          then per case int32 Lc, lindex, sim, pad; double x0[3], s0, buf[Lc] (vector overload, one call).
@@ -296,7 +355,7 @@ static int test_dimitrov(const char *out, bool robust)
                            {0.0, 0.21, 0.0}};
   for (const auto &t : seq) { RelativeFootPosition r = {t[0], t[1], t[2], 0.78, 0.02, 1, 0.0}; rel.push_back(r); }
   std::deque<ZMPPosition> zmp; std::deque<COMState> com; std::deque<FootAbsolutePosition> left, right;
-  COMState start; double zstart[3] = {0, 0, 0};
+  COMState start; S3Vector zstart;
   FootAbsolutePosition il, ir;
   std::memset(&il, 0, sizeof il); std::memset(&ir, 0, sizeof ir);
   il.x = 0.00949035; il.y = 0.095; ir.x = 0.00949035; ir.y = -0.095;
@@ -328,6 +387,7 @@ int main(int argc, char **argv)
     if (what == "optcholesky") return test_optcholesky();
     if (what == "herdt2010" && argc > 3) return test_herdt2010(argv[2], atoi(argv[3]), argc > 4 && std::string(argv[4]) == "emergency");
     if (what == "preview" && argc > 2) return test_preview(argv[2]);
+    if (what == "kajita2003" && argc > 3) return test_kajita2003(argv[2], argv[3]);
     if (what == "preview1d" && argc > 4) return test_preview1d(argv[2], argv[3], argv[4]);
     if (what == "pldp" && argc > 3) return test_pldp(argv[2], argv[3]);
     if (what == "dimitrov" && argc > 2) return test_dimitrov(argv[2], argc > 3 && std::string(argv[3]) == "robust");

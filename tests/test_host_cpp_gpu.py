@@ -131,3 +131,51 @@ def test_cpp_dimitrov_generator_matches_oracle(exe, tmp_path, robust):
     assert com[:20 * good].tobytes() == ref["com"][:20 * good].tobytes()
     P = do.fcals(o["left"], o["right"], o["types"][:, 1].copy())
     assert npoly == len(P) and (rows == P["rows"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("profile", ["StraightWalking", "Circle"])
+def test_cpp_testkajita2003_through_parsecmd(exe, tmp_path, profile):
+    """tests/TestKajita2003.cpp (StraightWalking: `:stepseq`; Circle: `:supportfoot`, `:arc`, `:lastsupport`, `:finish`)
+    through the PGI mirror built by patternGeneratorInterfaceFactory over the stand-in robot, ticked with the 7-argument
+    RunOneStepOfTheControlLoop overload: feet and ZMP reference (datref columns 11-36) at the datref's 1e-7 truncation on
+    every row, the number of ticks of the reference (3362 for the straight walk), and the CoM of the first preview stage
+    against the oracle's OneIterationOfPreview on the same ZMP reference (the datref CoM holds the multibody second stage
+    of the proprietary HRP-2 model)."""
+    import zmpdisc_oracle as zo
+    out = tmp_path / "kajita.dat"
+    r = subprocess.run([exe, "kajita2003", profile, str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(out)
+    gold = zo.golden(profile)                       # columns 11-13, 20-22 (left), 23-25, 32-34 (right), 35-36 (ZMP ref)
+    assert rows.shape[0] == gold.shape[0]
+    got = np.column_stack([rows[:, 9:15], rows[:, 15:21], rows[:, 7:9]])
+    assert np.abs(got - gold).max() < 1.2e-7
+    o = zo.run(zo.default_params(), zo.profile_steps(profile))
+    z = np.ascontiguousarray(o["zmp"][:, :2])
+    g = ol.OracleGains(0.005, 1.6, 0.8078, 1)
+    st = np.zeros((1, 8))
+    com, _, steps = ol.oracle_preview_batch(g, np.array([0, len(z)]), z, st)
+    n = rows.shape[0]
+    assert steps >= n
+    assert np.abs(rows[:, 1] - com[:n, 0]).max() < 1e-9 and np.abs(rows[:, 2] - com[:n, 3]).max() < 1e-9
+    assert np.abs(rows[:, 5] - com[:n, 1]).max() < 1e-8 and np.abs(rows[:, 6] - com[:n, 4]).max() < 1e-8
+    assert np.abs(rows[:, 3] - 0.8078).max() == 0.0
+
+
+@pytest.mark.gpu
+def test_cpp_kajita_online_step_sequencing(exe, tmp_path):
+    """`:StartOnLineStepSequencing` with three steps, default steps taken from the stack handler while the queues run low,
+    `:StopOnLineStepSequencing` after 5 s: the walk goes on past the given steps, ends with the feet side by side, and the
+    ZMP reference stays inside the box spanned by the feet (margin of half a sole)."""
+    out = tmp_path / "online.dat"
+    r = subprocess.run([exe, "kajita2003", "OnLine", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(out)
+    assert rows.shape[0] > 1500
+    lf, rf, z = rows[:, 9:12], rows[:, 15:18], rows[:, 7:9]
+    assert lf[:, 2].min() >= 0.0 and rf[:, 2].min() >= 0.0 and max(lf[:, 2].max(), rf[:, 2].max()) > 0.06
+    assert lf[-1, 0] > 0.5 and abs(lf[-1, 0] - rf[-1, 0]) < 1e-9 and abs(lf[-1, 1] - rf[-1, 1] - 0.19) < 1e-9
+    lo = np.minimum(lf[:, :2], rf[:, :2]) - 0.13; hi = np.maximum(lf[:, :2], rf[:, :2]) + 0.13
+    assert ((z >= lo) & (z <= hi)).all()
+    assert np.abs(rows[-1, 1:3] - z[-1]).max() < 5e-3          # the CoM has converged onto the final ZMP reference
