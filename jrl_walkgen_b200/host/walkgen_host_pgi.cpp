@@ -448,11 +448,10 @@ void PatternGeneratorInterface::StartOnLineStepSequencing()
 }
 void PatternGeneratorInterface::StopOnLineStepSequencing()
 {
+  // PGI.cpp:875-878: the stack is emptied and the transition flagged; the tick then takes one more default step (which
+  // brings the feet side by side) and closes the walk with EndPhaseOfTheWalking (PGI.cpp:1283-1314)
   if (!m_KajitaOnLine) return;
   m_StepStackHandler->StopOnLineStep();
-  m_ZMPD->EndPhaseOfTheWalking(m_ZMPPositions, m_COMBuffer, m_LeftFootPositions, m_RightFootPositions);
-  kajitaPreviewOverQueues();
-  m_KajitaOnLine = false;
 }
 void PatternGeneratorInterface::AddOnLineStep(double X, double Y, double Theta)
 {
@@ -524,8 +523,9 @@ bool PatternGeneratorInterface::RunOneStepOfTheControlLoop(COMState &COMStateOut
       RelativeFootPosition f;
       if (m_StepStackHandler->ReturnStackSize() == 0) m_StepStackHandler->AddStandardOnLineStep(false, 0.0, 0.0, 0.0);
       if (m_StepStackHandler->ReturnFrontFootPosition(f)) {
-        m_StepStackHandler->RemoveFirstStepInTheStack();
-        m_ZMPD->OnLineAddFoot(f, m_ZMPPositions, m_COMBuffer, m_LeftFootPositions, m_RightFootPositions, false);
+        const bool last = m_StepStackHandler->RemoveFirstStepInTheStack();   // true: stack empty after :StopOnLineStepSequencing
+        m_ZMPD->OnLineAddFoot(f, m_ZMPPositions, m_COMBuffer, m_LeftFootPositions, m_RightFootPositions, last);
+        if (last) m_KajitaOnLine = false;
         kajitaPreviewOverQueues();
       }
     }
