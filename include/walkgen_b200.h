@@ -197,11 +197,29 @@ typedef struct wg_herdt_qp_output {
   int32_t iterations;               /* active-set changes (adds + drops)                                  */
 } wg_herdt_qp_output;
 
+/* Optimal active set of one solve, as a warm start for the next solve of the same instance: the 0-based rows (without the
+ * dummy row: CoP row 4 i + e of previewed sample i, foot row 4N + 5 s + e of previewed step s) in activation order, and where
+ * the previewed steps start, so that a later solve can shift the rows by the samples that left the horizon. */
+typedef struct wg_herdt_active_set {
+  int8_t rows[40];                  /* -1 padded                                                            */
+  int8_t n;                         /* 0: no guess (cold start)                                             */
+  int8_t step_pi[2];                /* previewed sample (1..N) at which previewed step 1 / 2 starts, 0 = none */
+  int8_t pad_[5];
+} wg_herdt_active_set;              /* 48 bytes */
+
 int wg_herdt_set_params(wg_ctx *ctx, const wg_herdt_params *params);
 
 /* Build and solve B independent QPs.  in/out are arrays of B structs (host or device per `mem`). */
 int wg_herdt_qp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_herdt_qp_input *in,
                             wg_herdt_qp_output *out);
+
+/* The same solve, warm started.  guess[b] (or NULL) is the active set a solve of the same instance `age` QP periods earlier
+ * ended on (age 0: the same QP): its rows are shifted by the samples / steps that left the horizon, taken as equalities all
+ * at once, guesses whose multiplier comes out negative are dropped, and the dual active-set iteration continues from that
+ * pair.  The QP is strictly convex, so the optimum - x, multipliers, active set - is the one of the cold start; only the
+ * path (and `iterations`) changes.  active_out[b] (or NULL; may alias guess) receives the optimal active set. */
+int wg_herdt_qp_solve_batch_warm(wg_ctx *ctx, int mem, int B, const wg_herdt_qp_input *in, wg_herdt_qp_output *out,
+                                 const wg_herdt_active_set *guess, int age, wg_herdt_active_set *active_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Herdt2010 closed loop: the whole ZMPVelocityReferencedQP::OnLine cycle on the device, batched
@@ -233,6 +251,10 @@ typedef struct wg_herdt_mpc_params {
   int32_t nb_steps_ssds;    /* SupportFSM NbStepsSSDS 2 (:80); :numberstepsbeforestop overrides    */
   int32_t return_to_centre; /* 1: end-of-walk jerk towards the feet centre (:410-421, since 3.1.8);
                                0: always apply the QP jerk (the code the committed datrefs were made with) */
+  int32_t warm_start;       /* 1: every QP starts from the previous period's optimal active set, shifted by one sample
+                               (same optimum, another path: +8 % closed-loop rate measured); 0 (default): cold start as
+                               QLD does                                                                               */
+  int32_t reserved;
 } wg_herdt_mpc_params;
 
 void wg_herdt_mpc_default_params(wg_herdt_mpc_params *out);
@@ -279,6 +301,8 @@ typedef struct wg_herdt_mpc_state {
   int32_t online_mode, ending_phase, running, nb_steps_ssds;
   int32_t qp_count, fail_count, last_fail;
   int64_t iterations_total;            /* active-set changes summed over all QPs of this instance     */
+  wg_herdt_active_set warm;            /* optimal active set of the last QP (warm start of the next one, see
+                                          wg_herdt_mpc_params::warm_start); n = 0 after InitOnLine        */
 } wg_herdt_mpc_state;
 
 /* Summary of one QP period (optional output). */

@@ -18,6 +18,7 @@ from ._capi import (MODE_WITH_INITIALPOS, MODE_WITHOUT_INITIALPOS, WG_MEM_DEVICE
 QP_INPUT_DTYPE, QP_OUTPUT_DTYPE = _capi.herdt_dtypes()
 FOOT_DTYPE, TICK_DTYPE, MPC_STATE_DTYPE, MPC_STEP_DTYPE = _capi.herdt_mpc_dtypes()
 TICKS_PER_STEP = _capi.HERDT_TICKS_PER_STEP
+ACTIVE_SET_DTYPE = _capi.herdt_active_set_dtype()
 PLDP_STATE_DTYPE, PLDP_INFO_DTYPE = _capi.pldp_dtypes()
 REL_STEP_DTYPE, KAJITA_FOOT_DTYPE = _capi.kajita_dtypes()
 LCI_DTYPE, DIMITROV_PERIOD_DTYPE = _capi.dimitrov_dtypes()
@@ -25,7 +26,7 @@ DimitrovParams = _capi.DimitrovParams
 
 __all__ = ["LCI_DTYPE", "DIMITROV_PERIOD_DTYPE", "DimitrovParams", "dimitrov_default_params", "Context", "PreviewPlan", "KajitaPlan", "zmpdisc_default_params", "REL_STEP_DTYPE", "KAJITA_FOOT_DTYPE", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
            "PLDP_STATE_DTYPE", "PLDP_INFO_DTYPE", "FOOT_DTYPE", "TICK_DTYPE", "MPC_STATE_DTYPE", "MPC_STEP_DTYPE", "TICKS_PER_STEP", "QP_INPUT_DTYPE",
-           "QP_OUTPUT_DTYPE", "WalkgenError", "device_count",
+           "QP_OUTPUT_DTYPE", "ACTIVE_SET_DTYPE", "WalkgenError", "device_count",
            "MODE_WITH_INITIALPOS", "MODE_WITHOUT_INITIALPOS", "WG_MEM_HOST", "WG_MEM_DEVICE"]
 
 
@@ -226,6 +227,22 @@ class Context:
             return outputs
         self._check(self.lib.wg_herdt_qp_solve_batch(self.h, mem, int(count), _ptr(inputs), _ptr(outputs)))
         return outputs
+
+    def herdt_qp_solve_warm(self, inputs, guess=None, age=1, outputs=None, active=None):
+        """wg_herdt_qp_solve_batch_warm on host arrays -> (outputs, optimal active sets)."""
+        inputs = np.ascontiguousarray(inputs, dtype=QP_INPUT_DTYPE)
+        B = len(inputs)
+        if outputs is None:
+            outputs = np.zeros(B, dtype=QP_OUTPUT_DTYPE)
+        if active is None:
+            active = np.zeros(B, dtype=ACTIVE_SET_DTYPE)
+        if guess is not None:
+            guess = np.ascontiguousarray(guess, dtype=ACTIVE_SET_DTYPE)
+            assert len(guess) == B
+        self._check(self.lib.wg_herdt_qp_solve_batch_warm(self.h, WG_MEM_HOST, B, inputs.ctypes.data, outputs.ctypes.data,
+                                                          guess.ctypes.data if guess is not None else None, int(age),
+                                                          active.ctypes.data))
+        return outputs, active
 
 
     # ---- Herdt2010 closed loop -----------------------------------------------------------------

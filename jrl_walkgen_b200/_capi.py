@@ -68,7 +68,8 @@ class HerdtMpcParams(C.Structure):
                 ("ds_period", C.c_double), ("dsss_period", C.c_double), ("t_single", C.c_double),
                 ("t_double", C.c_double), ("step_height", C.c_double), ("hip_lower", C.c_double * 2),
                 ("hip_upper", C.c_double * 2), ("foot_vel_limit", C.c_double), ("hip_acc_limit", C.c_double),
-                ("feet_cross_limit", C.c_double), ("nb_steps_ssds", C.c_int32), ("return_to_centre", C.c_int32)]
+                ("feet_cross_limit", C.c_double), ("nb_steps_ssds", C.c_int32), ("return_to_centre", C.c_int32),
+                ("warm_start", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PldpBatch(C.Structure):
@@ -154,6 +155,14 @@ def herdt_dtypes():
     return qin, qout
 
 
+def herdt_active_set_dtype():
+    """numpy mirror of wg_herdt_active_set (48 B)."""
+    np = _np()
+    d = np.dtype([("rows", "i1", 40), ("n", "i1"), ("step_pi", "i1", 2), ("pad_", "i1", 5)])
+    assert d.itemsize == 48
+    return d
+
+
 def herdt_mpc_dtypes():
     """numpy mirrors of wg_herdt_foot_sample, wg_herdt_tick (256 B), wg_herdt_mpc_state, wg_herdt_mpc_step (144 B)."""
     np = _np()
@@ -171,12 +180,13 @@ def herdt_mpc_dtypes():
         ("sup_nb_instants", "i4"), ("sup_changed", "i4"), ("in_translation", "i4"), ("in_rotation", "i4"),
         ("post_rotation", "i4"), ("steps_after_rotation", "i4"), ("fsm_support_foot", "i4"),
         ("online_mode", "i4"), ("ending_phase", "i4"), ("running", "i4"), ("nb_steps_ssds", "i4"),
-        ("qp_count", "i4"), ("fail_count", "i4"), ("last_fail", "i4"), ("iterations_total", "i8")])
+        ("qp_count", "i4"), ("fail_count", "i4"), ("last_fail", "i4"), ("iterations_total", "i8"),
+        ("warm", herdt_active_set_dtype())])
     step = np.dtype([("time", "f8"), ("com_x", "f8", 3), ("com_y", "f8", 3), ("jerk_x", "f8"), ("jerk_y", "f8"),
                      ("next_foot_x", "f8"), ("next_foot_y", "f8"), ("sup_x", "f8"), ("sup_y", "f8"),
                      ("sup_yaw", "f8"), ("sup_foot", "i4"), ("sup_phase", "i4"), ("n_prw_steps", "i4"),
                      ("fail", "i4"), ("iterations", "i4"), ("n_active", "i4"), ("pad_", "i4", 2)])
-    assert foot.itemsize == 80 and tick.itemsize == 256 and step.itemsize == 144 and state.itemsize == 952
+    assert foot.itemsize == 80 and tick.itemsize == 256 and step.itemsize == 144 and state.itemsize == 1000
     return foot, tick, state, step
 
 
@@ -217,6 +227,8 @@ SIGNATURES = {
     "wg_herdt_default_params": (None, [C.c_double, C.c_double, C.POINTER(HerdtParams)]),
     "wg_herdt_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtParams)]),
     "wg_herdt_qp_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wg_herdt_qp_solve_batch_warm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_void_p]),
     "wg_pldp_set_constants": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "wg_pldp_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(PldpBatch)]),
     "wg_pldp_solve_batch_ranked": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(PldpBatch), C.c_void_p, C.c_void_p,

@@ -380,8 +380,18 @@ herdt_mpc_kernel(int B, int nsteps, const herdt::Consts *__restrict__ Cp, const 
         for (int e = lane; e < (int)(sizeof(wg_herdt_qp_input) / 8); e += 32) dst[e] = src[e];
       }
       int q = 0;
-      const herdt::Result r = herdt::solve_warp(s, C, lane, q, Tw);
+      const herdt::Result r = herdt::solve_warp(s, C, lane, q, Tw, M.warm_start ? &st.warm : nullptr, 1);
       const int ns = (r.n_vars - 2 * N) / 2;
+      {   // optimal active set -> warm start of the next period
+        const int nq = r.fail ? 0 : q;
+        for (int e = lane; e < (int)sizeof(st.warm.rows); e += 32) st.warm.rows[e] = (e < nq) ? (int8_t)s.W[e] : (int8_t)-1;
+        if (lane == 0) {
+          int p1 = 0, p2 = 0;
+          for (int k = N; k >= 1; --k) { const int sn = s.in.sup_step[k]; if (sn == 1) p1 = k; else if (sn == 2) p2 = k; }
+          st.warm.n = (int8_t)nq; st.warm.step_pi[0] = (int8_t)p1; st.warm.step_pi[1] = (int8_t)p2;
+        }
+        __syncwarp();
+      }
 
       // ---- jerk to apply (ZMPVelocityReferencedQP.cpp:404-431)
       double jx = s.jr[0][0], jy = s.jr[1][0];
@@ -863,6 +873,8 @@ mpc_post_kernel(int B, int step, int nsteps, const herdt::Consts *__restrict__ C
 
 const herdt::Consts *wg_herdt_device_consts(wg_ctx *ctx);
 const herdt::Consts *wg_herdt_host_consts(wg_ctx *ctx);
+int wg_herdt_qp_solve_device(wg_ctx *ctx, int B, const wg_herdt_qp_input *in, wg_herdt_qp_output *out,
+                             const herdt::LaunchOpts &opt);
 
 void wg_herdt_mpc_release(wg_ctx *ctx)
 {
@@ -898,6 +910,8 @@ void wg_herdt_mpc_default_params(wg_herdt_mpc_params *p)
   p->feet_cross_limit = 5.0 / 180.0 * PI;
   p->nb_steps_ssds = 2;
   p->return_to_centre = 1;
+  p->warm_start = 0;   // measured on B200: 24.8 -> 23.5 active-set changes per QP, +8 % closed-loop rate (the guess is taken row by
+                       // row, each row costs the two triangular products of a regular iteration); cold start stays the default
 }
 
 int wg_herdt_mpc_set_params(wg_ctx *ctx, const wg_herdt_mpc_params *params)
@@ -974,7 +988,15 @@ static int mpc_launch_split(wg_ctx *ctx, MpcState *m, int B, int nsteps, wg_herd
                                                                       vel_ref, rec, scr);
     wg_prof_stop(ctx);
     WG_LAUNCHED(ctx);
-    if ((rc = wg_herdt_qp_solve_batch(ctx, WG_MEM_DEVICE, B, rec, out)) != WG_OK) return rc;
+    {
+      herdt::LaunchOpts opt;
+      opt.fire = reinterpret_cast<const unsigned char *>(&scr->fire); opt.fire_stride = sizeof(MpcScratch);
+      unsigned char *warm = reinterpret_cast<unsigned char *>(&states->warm);
+      if (m->h_params.warm_start) { opt.guess = warm; opt.guess_stride = sizeof(wg_herdt_mpc_state); }
+      opt.active_out = warm; opt.active_stride = sizeof(wg_herdt_mpc_state);
+      opt.age = 1;
+      if ((rc = wg_herdt_qp_solve_device(ctx, B, rec, out, opt)) != WG_OK) return rc;
+    }
     wg_prof_start(ctx, WG_K_HERDT_MPC);
     mpc_post_kernel<<<blocks, MPC_WARPS * 32, smem_post, ctx->stream>>>(B, step, nsteps, wg_herdt_device_consts(ctx), m->d_params,
                                                                         states, out, scr, ticks, steps);

@@ -20,6 +20,7 @@ struct HerdtState {
   int cap = 0;
   int *d_next = nullptr;          // work counter of herdt_qp_kernel
   double *d_T = nullptr; size_t cap_T = 0;   // per-warp T slices
+  wg_herdt_active_set *d_act = nullptr; int cap_act = 0;   // staging of the warm-start sets (WG_MEM_HOST)
   // WG_MEM_HOST pipeline: upload / download streams and per-chunk events
   cudaStream_t up = nullptr, down = nullptr;
   cudaEvent_t ev_up[8] = {nullptr}, ev_k[8] = {nullptr}, ev0 = nullptr;
@@ -114,7 +115,8 @@ constexpr int QP_WARPS = 4;  // warps (instances) per block
 
 __global__ void __launch_bounds__(QP_WARPS * 32, 4)
 herdt_qp_kernel(int B, const Consts *__restrict__ Cp, const wg_herdt_qp_input *__restrict__ in,
-                wg_herdt_qp_output *__restrict__ out, int *__restrict__ next_instance, double *__restrict__ scratchT)
+                wg_herdt_qp_output *__restrict__ out, int *__restrict__ next_instance, double *__restrict__ scratchT,
+                herdt::LaunchOpts opt)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   herdt::Work *works = reinterpret_cast<herdt::Work *>(smem_raw);
@@ -128,6 +130,7 @@ herdt_qp_kernel(int B, const Consts *__restrict__ Cp, const wg_herdt_qp_input *_
     if (lane == 0) b = atomicAdd(next_instance, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= B) break;
+    if (opt.fire && !*reinterpret_cast<const int *>(opt.fire + (size_t)b * opt.fire_stride)) continue;   // closed loop: no QP this period
     // stage the 784-byte input record
     {
       const double *src = reinterpret_cast<const double *>(in + b);
@@ -136,7 +139,20 @@ herdt_qp_kernel(int B, const Consts *__restrict__ Cp, const wg_herdt_qp_input *_
     }
     __syncwarp();
     int q = 0;
-    const herdt::Result r = herdt::solve_warp(s, C, lane, q, Tw);
+    const wg_herdt_active_set *guess =
+        opt.guess ? reinterpret_cast<const wg_herdt_active_set *>(opt.guess + (size_t)b * opt.guess_stride) : nullptr;
+    const herdt::Result r = herdt::solve_warp(s, C, lane, q, Tw, guess, opt.age);
+    if (opt.active_out) {   // may alias the guess: the solve is done with it
+      wg_herdt_active_set *ao = reinterpret_cast<wg_herdt_active_set *>(opt.active_out + (size_t)b * opt.active_stride);
+      const int nq = r.fail ? 0 : q;
+      for (int e = lane; e < (int)sizeof(ao->rows); e += 32) ao->rows[e] = (e < nq) ? (int8_t)s.W[e] : (int8_t)-1;
+      if (lane == 0) {
+        int p1 = 0, p2 = 0;
+        for (int k = N; k >= 1; --k) { const int sn = s.in.sup_step[k]; if (sn == 1) p1 = k; else if (sn == 2) p2 = k; }
+        ao->n = (int8_t)nq; ao->step_pi[0] = (int8_t)p1; ao->step_pi[1] = (int8_t)p2;
+        for (int e = 0; e < 5; ++e) ao->pad_[e] = 0;
+      }
+    }
     // ---- write wg_herdt_qp_output (960 B)
     wg_herdt_qp_output &o = out[b];
     const int ns = (r.n_vars - 2 * N) / 2;
@@ -173,7 +189,7 @@ void wg_herdt_release(wg_ctx *ctx)
 {
   if (!ctx->herdt) return;
   HerdtState *st = static_cast<HerdtState *>(ctx->herdt);
-  cudaFree(st->d_consts); cudaFree(st->d_in); cudaFree(st->d_out); cudaFree(st->d_next); cudaFree(st->d_T);
+  cudaFree(st->d_consts); cudaFree(st->d_in); cudaFree(st->d_out); cudaFree(st->d_next); cudaFree(st->d_T); cudaFree(st->d_act);
   if (st->up) cudaStreamDestroy(st->up);
   if (st->down) cudaStreamDestroy(st->down);
   for (int c = 0; c < 8; ++c) { if (st->ev_up[c]) cudaEventDestroy(st->ev_up[c]); if (st->ev_k[c]) cudaEventDestroy(st->ev_k[c]); }
@@ -227,7 +243,8 @@ int wg_herdt_set_params(wg_ctx *ctx, const wg_herdt_params *params)
   return WG_OK;
 }
 
-static int herdt_launch(wg_ctx *ctx, HerdtState *st, int B, const wg_herdt_qp_input *d_in, wg_herdt_qp_output *d_out)
+static int herdt_launch(wg_ctx *ctx, HerdtState *st, int B, const wg_herdt_qp_input *d_in, wg_herdt_qp_output *d_out,
+                        const herdt::LaunchOpts &opt = herdt::LaunchOpts())
 {
   const size_t smem = sizeof(herdt::Work) * QP_WARPS;
   WG_SMEM_ATTR(ctx, WG_ATTR_HERDT_QP, herdt_qp_kernel, smem);
@@ -246,7 +263,7 @@ static int herdt_launch(wg_ctx *ctx, HerdtState *st, int B, const wg_herdt_qp_in
   }
   WG_CUDA(ctx, cudaMemsetAsync(st->d_next, 0, sizeof(int), ctx->stream));
   wg_prof_start(ctx, WG_K_HERDT_QP);
-  herdt_qp_kernel<<<blocks, QP_WARPS * 32, smem, ctx->stream>>>(B, st->d_consts, d_in, d_out, st->d_next, st->d_T);
+  herdt_qp_kernel<<<blocks, QP_WARPS * 32, smem, ctx->stream>>>(B, st->d_consts, d_in, d_out, st->d_next, st->d_T, opt);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;
@@ -300,4 +317,60 @@ int wg_herdt_qp_solve_batch(wg_ctx *ctx, int mem, int B, const wg_herdt_qp_input
   return WG_OK;
 }
 
+int wg_herdt_qp_solve_batch_warm(wg_ctx *ctx, int mem, int B, const wg_herdt_qp_input *in, wg_herdt_qp_output *out,
+                                 const wg_herdt_active_set *guess, int age, wg_herdt_active_set *active_out)
+{
+  if (!ctx || B < 0 || age < 0 || (B > 0 && (!in || !out))) return WG_ERR_INVALID;
+  HerdtState *st = state_of(ctx);
+  if (!st->ready) return wg_fail(ctx, WG_ERR_NOT_READY, "wg_herdt_set_params not called");
+  if (B == 0) return WG_OK;
+  wg_device_guard guard(ctx->device);
+  herdt::LaunchOpts opt;
+  opt.age = age;
+  opt.guess_stride = opt.active_stride = sizeof(wg_herdt_active_set);
+  if (mem == WG_MEM_DEVICE) {
+    opt.guess = reinterpret_cast<const unsigned char *>(guess);
+    opt.active_out = reinterpret_cast<unsigned char *>(active_out);
+    return herdt_launch(ctx, st, B, in, out, opt);
+  }
+  if (mem != WG_MEM_HOST) return WG_ERR_INVALID;
+  if (st->cap < B) {
+    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(st->d_in); cudaFree(st->d_out);
+    st->d_in = nullptr; st->d_out = nullptr; st->cap = 0;
+    WG_CUDA(ctx, cudaMalloc(&st->d_in, sizeof(wg_herdt_qp_input) * (size_t)B));
+    WG_CUDA(ctx, cudaMalloc(&st->d_out, sizeof(wg_herdt_qp_output) * (size_t)B));
+    st->cap = B;
+  }
+  if (st->cap_act < B) {
+    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(st->d_act); st->d_act = nullptr; st->cap_act = 0;
+    WG_CUDA(ctx, cudaMalloc(&st->d_act, sizeof(wg_herdt_active_set) * (size_t)B));
+    st->cap_act = B;
+  }
+  WG_CUDA(ctx, cudaMemcpyAsync(st->d_in, in, sizeof(wg_herdt_qp_input) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+  if (guess) {
+    WG_CUDA(ctx, cudaMemcpyAsync(st->d_act, guess, sizeof(wg_herdt_active_set) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+    opt.guess = reinterpret_cast<const unsigned char *>(st->d_act);
+  }
+  opt.active_out = reinterpret_cast<unsigned char *>(st->d_act);
+  int rc = herdt_launch(ctx, st, B, st->d_in, st->d_out, opt);
+  if (rc != WG_OK) return rc;
+  WG_CUDA(ctx, cudaMemcpyAsync(out, st->d_out, sizeof(wg_herdt_qp_output) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (active_out)
+    WG_CUDA(ctx, cudaMemcpyAsync(active_out, st->d_act, sizeof(wg_herdt_active_set) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return WG_OK;
+}
+
 }  // extern "C"
+
+// used by herdt_mpc.cu: the solve of one closed-loop period on device-resident records, skipping the instances that do not
+// fire, warm started from / writing back the active set kept in each instance's state
+int wg_herdt_qp_solve_device(wg_ctx *ctx, int B, const wg_herdt_qp_input *in, wg_herdt_qp_output *out,
+                             const herdt::LaunchOpts &opt)
+{
+  HerdtState *st = state_of(ctx);
+  if (!st->ready) return wg_fail(ctx, WG_ERR_NOT_READY, "wg_herdt_set_params not called");
+  return herdt_launch(ctx, st, B, in, out, opt);
+}

@@ -154,11 +154,198 @@ struct Result {
   int n_vars, n_rows, fail, iterations;
 };
 
+// Optional per-instance side inputs / outputs of herdt_qp_kernel, addressed as base + b * stride bytes so that they can live
+// inside larger records (the closed loop keeps the warm-start set inside wg_herdt_mpc_state).
+struct LaunchOpts {
+  const unsigned char *fire = nullptr;   size_t fire_stride = 0;     // int: 0 = skip instance b
+  const unsigned char *guess = nullptr;  size_t guess_stride = 0;    // wg_herdt_active_set of an earlier solve
+  unsigned char *active_out = nullptr;   size_t active_stride = 0;   // optimal active set (may alias guess)
+  int age = 1;
+};
+
+// Drop active row l: rotate rows (l, r), r > l, of the inverse Cholesky factor T so that column l vanishes below row l, then
+// delete row and column l (s.w holds the rotating copy of row l); W / cpt / u close the gap.  q is NOT decremented here.
+static __device__ __noinline__ void drop_row(Work &s, double *__restrict__ T, int q, int l, int lane, unsigned &actbits)
+{
+  const int kl = s.W[l];
+  if ((kl & 31) == lane) actbits &= ~(1u << (kl >> 5));
+#pragma unroll 1
+  for (int j = lane; j < q; j += 32) s.w[j] = (j <= l) ? T[tri(l) + j] : 0.0;
+  __syncwarp();
+#pragma unroll 1
+  for (int r = l + 1; r < q; ++r) {
+    const double *Tr = T + tri(r);
+    const double p1 = s.w[l], p2 = Tr[l];
+    const double ih = rsqrt(p1 * p1 + p2 * p2);
+    const double c_ = p1 * ih, s_ = p2 * ih;
+    __syncwarp();
+    double *Tn = T + tri(r - 1);
+#pragma unroll 1
+    for (int j = lane; j <= r; j += 32) {
+      const double x1 = s.w[j], x2 = Tr[j];
+      s.w[j] = c_ * x1 + s_ * x2;
+      const double nr = c_ * x2 - s_ * x1;
+      if (j < l) Tn[j] = nr;
+      else if (j > l) Tn[j - 1] = nr;
+    }
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (int base = 0; base < q; base += 32) {
+    const int j = base + lane;
+    const bool mv = (j > l && j < q);
+    const int Wn = mv ? s.W[j] : 0, cn = mv ? s.cpt[j] : 0;
+    const double un = mv ? s.u[j] : 0.0;
+    __syncwarp();
+    if (mv) { s.W[j - 1] = Wn; s.cpt[j - 1] = cn; s.u[j - 1] = un; }
+    __syncwarp();
+  }
+}
+
+// w = T gv and r = T' w for the current active set (gv in s.gv); returns this lane's share of |w|^2.
+static __device__ __noinline__ double tri_products(Work &s, const double *__restrict__ T, int q, int lane)
+{
+  double wsq = 0.0;
+#pragma unroll 1
+  for (int j = lane; j < q; j += 32) {
+    const double *Tr = T + tri(j);
+    double w0 = 0.0, w1 = 0.0;
+    int e = 0;
+#pragma unroll 2
+    for (; e + 1 <= j; e += 2) { w0 = fma(Tr[e], s.gv[e], w0); w1 = fma(Tr[e + 1], s.gv[e + 1], w1); }
+    if (e <= j) w0 = fma(Tr[e], s.gv[e], w0);
+    const double wv_ = w0 + w1;
+    s.w[j] = wv_;
+    wsq = fma(wv_, wv_, wsq);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int j = lane; j < q; j += 32) {
+    double r0 = 0.0, r1 = 0.0;
+    int r = j;
+#pragma unroll 2
+    for (; r + 1 < q; r += 2) { r0 = fma(T[tri(r) + j], s.w[r], r0); r1 = fma(T[tri(r + 1) + j], s.w[r + 1], r1); }
+    if (r < q) r0 = fma(T[tri(r) + j], s.w[r], r0);
+    s.r[j] = r0 + r1;
+  }
+  __syncwarp();
+  return wsq;
+}
+
+// Warm start of the dual active-set method from a guessed active set (the optimal set of the previous MPC period, shifted
+// by the samples / steps that left the horizon).  A Goldfarb-Idnani iterate is any "S-pair": the minimiser on the active
+// rows taken as equalities, with non-negative multipliers.  The guessed rows are taken all at once - T grows by one row per
+// independent guess, no violation scan, no step, no ratio test -, the multipliers of the equality-constrained optimum are
+// u = -(N' H^-1 N)^-1 s_W(P0) = -T'T s_W(P0), and guesses whose multiplier comes out negative are dropped one at a time
+// (most negative first) until the pair is dual feasible.  The main loop then continues from that pair; it reaches the same
+// unique optimum as the cold start (strictly convex QP), in a few iterations instead of ~25 when most of the guess is right.
+static __device__ __noinline__ void warm_start(Work &s, double *__restrict__ T, int m, int npts, int lane,
+                                               const wg_herdt_active_set *__restrict__ hint, int age, int &q,
+                                               unsigned &actbits, int &iterations)
+{
+  const int nh = hint->n;
+  if (nh <= 0 || nh > (int)sizeof(hint->rows) || age < 0) return;
+  // where the previewed steps of this QP start, to map the foot rows of the guess (a step that starts at previewed sample pi
+  // starts at pi - age one QP later; at pi = 1 the foot is down and no longer a variable, generator-vel-ref.cpp:106-128)
+  int pi_new[2] = {0, 0};
+  for (int k = N; k >= 1; --k) {
+    const int sn = s.in.sup_step[k];
+    if (sn == 1) pi_new[0] = k; else if (sn == 2) pi_new[1] = k;
+  }
+  int step_map[2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int pio = hint->step_pi[o] - age;
+    step_map[o] = (hint->step_pi[o] > 0 && pio > 0) ? (pio == pi_new[0] ? 0 : (pio == pi_new[1] ? 1 : -1)) : -1;
+  }
+#pragma unroll 1
+  for (int t = 0; t < nh && q < QMAX - 4; ++t) {
+    int p = hint->rows[t];
+    if (p < 0) continue;
+    if (p < 4 * N) { p -= 4 * age; if (p < 0) continue; }
+    else {
+      const int so = (p - 4 * N) / 5, e = (p - 4 * N) - 5 * so;
+      if (so > 1 || step_map[so] < 0) continue;
+      p = 4 * N + 5 * step_map[so] + e;
+    }
+    if (p >= m) continue;
+    const unsigned ab = __shfl_sync(0xffffffffu, actbits, p & 31);
+    if ((ab >> (p >> 5)) & 1u) continue;
+    if (!(s.inrm[p] > 0.0)) continue;                        // unused (all-zero) row
+    const int pp = row_point(p);
+    const double ap = s.a[p], bp = s.b[p];
+    const double Mpp = (ap * ap + bp * bp) * s.Gam[pp][pp];
+#pragma unroll 1
+    for (int j = lane; j < q; j += 32) {
+      const int k = s.W[j];
+      s.gv[j] = (s.a[k] * ap + s.b[k] * bp) * s.Gam[s.cpt[j]][pp];
+    }
+    __syncwarp();
+    const double delta = Mpp - warp_sum(tri_products(s, T, q, lane));
+    if (!(delta > 1e-9 * Mpp)) continue;                     // (nearly) dependent on the rows already taken
+    const double idd = rsqrt(delta);
+#pragma unroll 1
+    for (int j = lane; j < q; j += 32) T[tri(q) + j] = -s.r[j] * idd;
+    if (lane == 0) { T[tri(q) + q] = idd; s.W[q] = p; s.cpt[q] = pp; s.u[q] = 0.0; }
+    if ((p & 31) == lane) actbits |= 1u << (p >> 5);
+    ++q; ++iterations;
+    __syncwarp();
+  }
+#pragma unroll 1
+  while (q > 0) {
+#pragma unroll 1
+    for (int j = lane; j < q; j += 32) {
+      const int k = s.W[j], kp = s.cpt[j];
+      s.gv[j] = s.a[k] * s.PX[kp] + s.b[k] * s.PY[kp] + s.d[k];
+    }
+    __syncwarp();
+    tri_products(s, T, q, lane);
+    double umin = 0.0, umax = 0.0; int l = 0x7fffffff;
+#pragma unroll 1
+    for (int j = lane; j < q; j += 32) {
+      const double uj = -s.r[j];
+      s.u[j] = uj;
+      umax = fmax(umax, uj);
+      if (uj < umin) { umin = uj; l = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+    warp_argmin(umin, l);
+    __syncwarp();
+    if (!(umin < -1e-12 * umax) || l == 0x7fffffff) break;
+    drop_row(s, T, q, l, lane, actbits);
+    --q; ++iterations;
+  }
+  if (q == 0) return;
+  // move the point onto the S-pair: P = P0 + sum_j Gamma(:, kappa_j) (a_j, b_j) u_j
+#pragma unroll 1
+  for (int j = lane; j < q; j += 32) {
+    const int k = s.W[j];
+    const double uj = fmax(s.u[j], 0.0);
+    s.u[j] = uj;
+    s.ca[j] = uj * s.a[k]; s.cb[j] = uj * s.b[k];
+  }
+  __syncwarp();
+  if (lane < npts) {
+    double dx = 0.0, dy = 0.0;
+#pragma unroll 2
+    for (int j = 0; j < q; ++j) {
+      const double gm = s.Gam[lane][s.cpt[j]];
+      dx = fma(gm, s.ca[j], dx); dy = fma(gm, s.cb[j], dy);
+    }
+    s.PX[lane] += dx;
+    s.PY[lane] += dy;
+  }
+  __syncwarp();
+}
+
+
 // Build and solve the QP of the instance in s.in.  On return s.jr / s.ff hold the solution, s.u / s.W / q the
 // multipliers of the active rows.  All 32 lanes of the warp must call.
 // T: [TRI] doubles of scratch for the inverse Cholesky factor of the active Gram matrix, private to the warp (shared or
 // global memory: the open-loop kernel keeps it in global memory to fit 16 warps/SM).
-__device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_out, double *__restrict__ T)
+__device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_out, double *__restrict__ T,
+                                    const wg_herdt_active_set *__restrict__ hint = nullptr, int hint_age = 1)
 {
   const wg_herdt_params &P = C.P;
   const int axis = lane >> 4, i = lane & 15;
@@ -294,6 +481,7 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
   int refinements = 0;
   const int maxit = 40 * (m + 2 * N + 4);
   bool done = false;
+  if (hint) warm_start(s, T, m, npts, lane, hint, hint_age, q, actbits, res.iterations);
   while (!done) {
     // most violated row, normalised by its Euclidean norm (the pivoting rule of qld.cpp:1255-1331)
     double best = INF;
@@ -472,42 +660,9 @@ __device__ inline Result solve_warp(Work &s, const Consts &C, int lane, int &q_o
         __syncwarp();
         break;
       }
-      // partial step: multiplier l reached zero -> drop row l.  Rotate rows (l, r), r > l, so that column l
-      // vanishes below row l, then delete row and column l.  s.w holds the rotating copy of row l.
+      // partial step: multiplier l reached zero -> drop row l
       {
-        const int kl = s.W[l];
-        if ((kl & 31) == lane) actbits &= ~(1u << (kl >> 5));
-#pragma unroll 1
-        for (int j = lane; j < q; j += 32) s.w[j] = (j <= l) ? T[tri(l) + j] : 0.0;
-        __syncwarp();
-#pragma unroll 1
-        for (int r = l + 1; r < q; ++r) {
-          const double *Tr = T + tri(r);
-          const double p1 = s.w[l], p2 = Tr[l];
-          const double ih = rsqrt(p1 * p1 + p2 * p2);
-          const double c_ = p1 * ih, s_ = p2 * ih;
-          __syncwarp();
-          double *Tn = T + tri(r - 1);
-#pragma unroll 1
-          for (int j = lane; j <= r; j += 32) {
-            const double x1 = s.w[j], x2 = Tr[j];
-            s.w[j] = c_ * x1 + s_ * x2;
-            const double nr = c_ * x2 - s_ * x1;
-            if (j < l) Tn[j] = nr;
-            else if (j > l) Tn[j - 1] = nr;
-          }
-          __syncwarp();
-        }
-#pragma unroll 1
-        for (int base = 0; base < q; base += 32) {
-          const int j = base + lane;
-          const bool mv = (j > l && j < q);
-          const int Wn = mv ? s.W[j] : 0, cn = mv ? s.cpt[j] : 0;
-          const double un = mv ? s.u[j] : 0.0;
-          __syncwarp();
-          if (mv) { s.W[j - 1] = Wn; s.cpt[j - 1] = cn; s.u[j - 1] = un; }
-          __syncwarp();
-        }
+        drop_row(s, T, q, l, lane, actbits);
         --q;
       }
     }

@@ -158,3 +158,50 @@ def test_gpu_qp_full_size_idempotence(hctx):
         seg = out[r * len(ins):(r + 1) * len(ins)]
         assert np.array_equal(seg["x"], base["x"][:len(seg)])
         assert np.array_equal(seg["lagr"], base["lagr"][:len(seg)])
+
+
+@pytest.mark.gpu
+def test_gpu_qp_warm_start_reaches_the_cold_optimum(hctx):
+    """wg_herdt_qp_solve_batch_warm: the optimum does not depend on the guess.  (i) the QP's own optimal set as the guess
+    (age 0) is accepted in about one change per active row; (ii) consecutive closed-loop QPs, each warm started from its
+    predecessor's optimal set shifted by one sample (age 1: the closed loop's use), take far fewer iterations than cold;
+    (iii) a garbage guess (all rows of a random subset) still ends on the same optimum.  Reference optimum: the textbook
+    solver; x within 1e-8, identical active sets, KKT 1e-9 (check_against)."""
+    import jrl_walkgen_b200 as wg
+    ev = {200: lambda s: s.vel_ref(0.2, 0.05, 0.1), 1400: lambda s: s.vel_ref(-0.1, 0.1, -0.15),
+          2600: lambda s: s.vel_ref(0.0, 0.0, 0.0)}
+    ins, X, U, meta = logged_qps(3600, ev)
+    tb = oracle_solve(ins, 1)
+    ok = tb["fail"] == 0
+    assert ok.all()
+    cold, act = hctx.herdt_qp_solve_warm(ins)                      # no guess: cold start, returns the active sets
+    check_against(ins, cold, tb, xtol=1e-8)
+    plain = hctx.herdt_qp_solve(ins)
+    assert np.array_equal(plain["x"], cold["x"]) and np.array_equal(plain["iterations"], cold["iterations"])
+    for k in range(len(ins)):
+        m = int(tb["n_rows"][k])
+        rows = set(int(r) for r in act["rows"][k, :act["n"][k]])
+        assert set(np.nonzero(tb["lagr"][k, 1:m] > 1e-7 * max(tb["lagr"][k].max(), 1e-12))[0]) <= rows, k
+    # (i) own optimal set
+    own, act2 = hctx.herdt_qp_solve_warm(ins, guess=act, age=0)
+    check_against(ins, own, tb, xtol=1e-8)
+    assert (own["iterations"] <= act["n"] + 4).all()
+    # (ii) predecessor's set, one period older
+    guess = np.zeros(len(ins), dtype=wg.ACTIVE_SET_DTYPE)
+    guess[1:] = act[:-1]
+    warm, _ = hctx.herdt_qp_solve_warm(ins, guess=guess, age=1)
+    check_against(ins, warm, tb, xtol=1e-8)
+    # (iii) garbage
+    rng = np.random.default_rng(3)
+    bad = np.zeros(len(ins), dtype=wg.ACTIVE_SET_DTYPE)
+    bad["rows"][:] = -1
+    for k in range(len(ins)):
+        n = int(rng.integers(1, 30))
+        bad["rows"][k, :n] = rng.choice(74, size=n, replace=False)
+        bad["n"][k] = n
+        bad["step_pi"][k] = rng.integers(0, 17, size=2)
+    junk, _ = hctx.herdt_qp_solve_warm(ins, guess=bad, age=int(rng.integers(0, 3)))
+    check_against(ins, junk, tb, xtol=1e-8)
+    print(f"warm start: iterations cold {cold['iterations'].mean():.1f}, own set {own['iterations'].mean():.1f}, "
+          f"previous period {warm['iterations'].mean():.1f}, garbage {junk['iterations'].mean():.1f}")
+    assert warm["iterations"].mean() < cold["iterations"].mean()
