@@ -128,6 +128,26 @@ int64_t wg_preview_plan_total_samples(const wg_preview_plan *plan); /* offsets[B
 int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *plan, int mem, const double *zmpref_xy,
                          double *state, double *com_out, double *zmp_out, int simulation);
 
+/* Second stage of the two-stage scheme (ZMPPreviewControlWithMultiBodyZMP::EvaluateMultiBodyZMP / SecondStageOfControl,
+ * src/PreviewControl/ZMPPreviewControlWithMultiBodyZMP.cpp:447-479, :317-376), for callers that own the multibody model:
+ *   1. wg_preview_run_batch(simulation = 1) is the first stage: com_out row k = m_PC1x / m_PC1y after tick k;
+ *   2. the caller evaluates its robot's multibody ZMP for every first-stage tick (zmp_multibody_xy, same row indexing);
+ *   3. wg_preview_delta_zmp forms the stream the reference pushes into m_FIFODeltaZMPPositions:
+ *        delta[k] = zmpref[k + 1] - zmp_multibody[k]   (m_FIFOZMPRefPositions[0] AFTER the first stage popped it; the last
+ *        sample of a trajectory, which has no successor, gets 0);
+ *   4. wg_preview_stage2_run_batch runs the same preview controller on the delta stream (Simulation = true, state2 =
+ *      {m_Deltax, m_Deltay, m_sxDeltazmp, m_syDeltazmp}, zero after SetupFirstPhase) and writes
+ *        com_final_out row n = com_stage1 row n + (m_Deltax, m_Deltay) after step n   (all three derivatives, :352-356),
+ *      the CoM the reference hands back NL ticks after the first stage computed it (step n consumes delta[n, n + NL)).
+ *      dzmp_out (or NULL) receives Deltazmpx2 / Deltazmpy2.  Rows n > L - 2 NL + 1 of a trajectory of L samples are computed
+ *      from delta rows the first stage never produces (the caller's padding) and have no counterpart in the reference.
+ * The reference's own FIFO bookkeeping (Setup skips ZMPRefPositions[NL], :660) lives in the class mirror
+ * (jrl_walkgen_b200/host), which feeds these entry points the stream the FIFOs actually hold. */
+int wg_preview_delta_zmp(wg_ctx *ctx, wg_preview_plan *plan, int mem, const double *zmpref_xy,
+                         const double *zmp_multibody_xy, double *delta_out);
+int wg_preview_stage2_run_batch(wg_ctx *ctx, wg_preview_plan *plan, int mem, const double *delta_zmp_xy,
+                                const double *com_stage1, double *state2, double *com_final_out, double *dzmp_out);
+
 /* Single-call form of OneIterationOfPreview for the class wrappers (batch of one, one step):
  * host pointers; x[3], y[3], sxzmp, syzmp in/out; window = NL pairs starting at ZMPPositions[lindex]. */
 int wg_preview_one_iteration(wg_ctx *ctx, double *x, double *y, double *sxzmp, double *syzmp,

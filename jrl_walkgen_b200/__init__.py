@@ -473,6 +473,16 @@ class PreviewPlan:
         self.ctx._check(self.ctx.lib.wg_preview_run_batch(self.ctx.h, self.h, mem, _ptr(zmpref_xy), _ptr(state),
                                                           _ptr(com_out), _ptr(zmp_out), int(simulation)))
 
+    def delta_zmp(self, zmpref_xy, zmp_multibody_xy, delta_out, mem=WG_MEM_HOST):
+        """wg_preview_delta_zmp: delta[k] = zmpref[k + 1] - zmp_multibody[k] (EvaluateMultiBodyZMP)."""
+        self.ctx._check(self.ctx.lib.wg_preview_delta_zmp(self.ctx.h, self.h, mem, _ptr(zmpref_xy), _ptr(zmp_multibody_xy),
+                                                          _ptr(delta_out)))
+
+    def run_stage2(self, delta_zmp_xy, com_stage1, state2, com_final_out, dzmp_out=None, mem=WG_MEM_HOST):
+        """wg_preview_stage2_run_batch: SecondStageOfControl over the whole delta-ZMP stream."""
+        self.ctx._check(self.ctx.lib.wg_preview_stage2_run_batch(self.ctx.h, self.h, mem, _ptr(delta_zmp_xy), _ptr(com_stage1),
+                                                                 _ptr(state2), _ptr(com_final_out), _ptr(dzmp_out)))
+
     def destroy(self):
         if self.h:
             self.ctx.lib.wg_preview_plan_destroy(self.h)

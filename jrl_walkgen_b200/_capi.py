@@ -222,6 +222,9 @@ SIGNATURES = {
     "wg_preview_plan_total_samples": (C.c_int64, [C.c_void_p]),
     "wg_preview_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int]),
+    "wg_preview_delta_zmp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wg_preview_stage2_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
     "wg_preview_one_iteration": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                            c_double_p, C.c_int, c_double_p, c_double_p, C.c_int]),
     "wg_herdt_default_params": (None, [C.c_double, C.c_double, C.POINTER(HerdtParams)]),

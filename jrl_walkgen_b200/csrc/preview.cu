@@ -270,7 +270,7 @@ struct wg_preview_plan {
   int64_t *d_offsets;
   int *d_order;        // trajectories sorted by decreasing length (longest CTAs are scheduled first)
   // staging buffers for WG_MEM_HOST calls
-  double *d_zmp, *d_state, *d_com, *d_zmpout;
+  double *d_zmp, *d_state, *d_com, *d_zmpout, *d_add;
   // WG_MEM_HOST pipeline: chunk c = trajectories [chunk_first[c], chunk_first[c+1]) (contiguous sample ranges); its
   // upload, kernel and downloads run on three streams so that H2D, compute and D2H of different chunks overlap
   int n_chunks;
@@ -315,11 +315,13 @@ __device__ __forceinline__ void scan_combine(Axis &c, const double *__restrict__
   c.s = fma(P[12], n0, fma(P[13], n1, fma(P[14], n2, fma(P[15], n3, c.s))));
 }
 
-template <bool SIM, int FIR_THREADS, int MIN_CTAS>
+// ADD: second stage of ZMPPreviewControlWithMultiBodyZMP (SecondStageOfControl, ZMPPreviewControlWithMultiBodyZMP.cpp:317-376):
+// the stream is the delta ZMP, and the CoM rows written are com_add (the first stage's CoM of the same tick) + the state.
+template <bool SIM, int FIR_THREADS, int MIN_CTAS, bool ADD = false>
 __global__ void __launch_bounds__(FIR_THREADS, MIN_CTAS)
 preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ offsets,
                      const double2 *__restrict__ p, double *__restrict__ state, double *__restrict__ com,
-                     double *__restrict__ zmp)
+                     double *__restrict__ zmp, const double *__restrict__ com_add = nullptr)
 {
   constexpr int FIR_TILE = FIR_R * FIR_THREADS;   // ticks per tile
   extern __shared__ double2 sp[];             // padded tile of (px,py), then the scan exchange area
@@ -507,7 +509,14 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
           for (int it = 0; it < 6; ++it) {
             const int idx = 32 * it + lane, c = idx / 6, part = idx - 6 * c;
             const int row = kw + FIR_R * c + 2 * j;             // first of the two ticks of lane c in this round
-            if (row + (part >= 3) <= last) gc[3 * (FIR_R * c + 2 * j) + part] = stg_c[CHUNK_C * c + part];
+            if (row + (part >= 3) <= last) {
+              double2 v = stg_c[CHUNK_C * c + part];
+              if (ADD) {
+                const double2 a = __ldg(reinterpret_cast<const double2 *>(com_add) + 3 * (o + kw) + 3 * (FIR_R * c + 2 * j) + part);
+                v.x += a.x; v.y += a.y;
+              }
+              gc[3 * (FIR_R * c + 2 * j) + part] = v;
+            }
           }
         }
         if (zmp) {
@@ -591,7 +600,8 @@ void scan_matrices(const wg_preview_gains_t &g, bool sim, double (*P)[16], doubl
 // One CTA shape of the fused kernel: THREADS threads (tile = 8 x THREADS ticks), at least MIN_CTAS resident per SM.
 template <int THREADS, int MIN_CTAS>
 static int preview_launch_shape(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count, const double *d_zmp,
-                                double *d_state, double *d_com, double *d_zmpout, int simulation)
+                                double *d_state, double *d_com, double *d_zmpout, int simulation,
+                                const double *d_com_add = nullptr)
 {
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
   const int span = FIR_R * THREADS + NLpad;
@@ -603,6 +613,14 @@ static int preview_launch_shape(wg_ctx *ctx, wg_preview_plan *pl, const int *d_o
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
   std::lock_guard<std::mutex> lock(g_pv_mutex);
   { const int rc = preview_bind(ctx); if (rc != WG_OK) return rc; }
+  if (d_com_add && d_com) {   // second stage: always with the integrated error (Simulation = true, :343-347)
+    WG_SMEM_ATTR(ctx, WG_ATTR_PREVIEW_ADD_0 + (THREADS == 128 ? 0 : THREADS == 32 ? 1 : 2), (preview_fused_kernel<true, THREADS, MIN_CTAS, true>), smem);
+    wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
+    preview_fused_kernel<true, THREADS, MIN_CTAS, true><<<count, THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout, d_com_add);
+    wg_prof_stop(ctx);
+    WG_LAUNCHED(ctx);
+    return WG_OK;
+  }
   wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
   if (simulation)
     preview_fused_kernel<true, THREADS, MIN_CTAS><<<count, THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, d_com, d_zmpout);
@@ -720,7 +738,7 @@ int wg_preview_plan_destroy(wg_preview_plan *pl)
   for (int c = 0; c < PV_MAX_CHUNKS; ++c) { if (pl->ev_up[c]) cudaEventDestroy(pl->ev_up[c]); if (pl->ev_k[c]) cudaEventDestroy(pl->ev_k[c]); }
   if (pl->ev_done) cudaEventDestroy(pl->ev_done);
   cudaFree(pl->d_offsets); cudaFree(pl->d_order); cudaFree(pl->d_order_chunked);
-  cudaFree(pl->d_zmp); cudaFree(pl->d_state); cudaFree(pl->d_com); cudaFree(pl->d_zmpout);
+  cudaFree(pl->d_zmp); cudaFree(pl->d_state); cudaFree(pl->d_com); cudaFree(pl->d_zmpout); cudaFree(pl->d_add);
   delete pl;
   return WG_OK;
 }
@@ -730,7 +748,7 @@ int64_t wg_preview_plan_total_samples(const wg_preview_plan *pl) { return pl ? p
 
 // Launch over `count` trajectories listed in d_order (device array of trajectory indices of this plan).
 int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count, const double *d_zmp,
-                            double *d_state, double *d_com, double *d_zmpout, int simulation)
+                            double *d_state, double *d_com, double *d_zmpout, int simulation, const double *d_com_add)
 {
   if (pl->total_steps == 0 || count <= 0) return WG_OK;
   static int shape = -1;   // WG_PREVIEW_SHAPE: tuning knob for the CTA shape (default 64 threads x 8 CTAs/SM, 128 registers, no spills; measured 0.752 ms vs 0.778 (128 x 4) and 0.766 (32 x 16) on config 2)
@@ -739,20 +757,14 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
     shape = e ? atoi(e) : 0;
   }
   switch (shape) {
-  case 1: return preview_launch_shape<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation);
-  case 2: return preview_launch_shape<32, 16>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation);
-  default: return preview_launch_shape<64, 8>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation);
+  case 1: return preview_launch_shape<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add);
+  case 2: return preview_launch_shape<32, 16>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add);
+  default: return preview_launch_shape<64, 8>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add);
   }
 }
 
-static int preview_launch(wg_ctx *ctx, wg_preview_plan *pl, const double *d_zmp, double *d_state,
-                          double *d_com, double *d_zmpout, int simulation)
-{
-  return wgi_preview_launch_range(ctx, pl, pl->d_order, pl->B, d_zmp, d_state, d_com, d_zmpout, simulation);
-}
-
-int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *zmpref_xy, double *state,
-                         double *com_out, double *zmp_out, int simulation)
+static int preview_run(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *zmpref_xy, double *state,
+                       double *com_out, double *zmp_out, int simulation, const double *com_add)
 {
   if (!ctx || !pl || pl->ctx != ctx || !state || (!zmpref_xy && pl->total_samples > 0)) return WG_ERR_INVALID;
   if (!ctx->preview_ready || ctx->preview_gains.NL != pl->NL)
@@ -760,9 +772,10 @@ int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double
   wg_device_guard guard(ctx->device);
   if (pl->B == 0) return WG_OK;
   if (mem == WG_MEM_DEVICE)
-    return preview_launch(ctx, pl, zmpref_xy, state, com_out, zmp_out, simulation);
+    return wgi_preview_launch_range(ctx, pl, pl->d_order, pl->B, zmpref_xy, state, com_out, zmp_out, simulation, com_add);
   if (mem != WG_MEM_HOST) return WG_ERR_INVALID;
   const size_t ns = (size_t)pl->total_samples;
+  if (com_add && !pl->d_add) WG_CUDA(ctx, cudaMalloc(&pl->d_add, sizeof(double) * 6 * std::max<size_t>(1, ns)));
   if (!pl->d_zmp) WG_CUDA(ctx, cudaMalloc(&pl->d_zmp, sizeof(double) * 2 * std::max<size_t>(1, ns)));
   if (!pl->d_state) WG_CUDA(ctx, cudaMalloc(&pl->d_state, sizeof(double) * 8 * pl->B));
   if (com_out && !pl->d_com) {  // zero once: rows past a trajectory's last step read back as 0 in host mode
@@ -782,10 +795,13 @@ int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double
     const size_t s0 = (size_t)pl->chunk_samp[c], cnt = (size_t)(pl->chunk_samp[c + 1] - pl->chunk_samp[c]);
     if (b1 <= b0) continue;
     if (cnt) WG_CUDA(ctx, cudaMemcpyAsync(pl->d_zmp + 2 * s0, zmpref_xy + 2 * s0, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, pl->up_stream));
+    if (cnt && com_add)
+      WG_CUDA(ctx, cudaMemcpyAsync(pl->d_add + 6 * s0, com_add + 6 * s0, sizeof(double) * 6 * cnt, cudaMemcpyHostToDevice, pl->up_stream));
     WG_CUDA(ctx, cudaEventRecord(pl->ev_up[c], pl->up_stream));
     WG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl->ev_up[c], 0));
     int rc = wgi_preview_launch_range(ctx, pl, pl->d_order_chunked + b0, b1 - b0, pl->d_zmp, pl->d_state,
-                                      com_out ? pl->d_com : nullptr, zmp_out ? pl->d_zmpout : nullptr, simulation);
+                                      com_out ? pl->d_com : nullptr, zmp_out ? pl->d_zmpout : nullptr, simulation,
+                                      com_add ? pl->d_add : nullptr);
     if (rc != WG_OK) return rc;
     WG_CUDA(ctx, cudaEventRecord(pl->ev_k[c], ctx->stream));
     WG_CUDA(ctx, cudaStreamWaitEvent(pl->down_stream, pl->ev_k[c], 0));
@@ -800,7 +816,64 @@ int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double
   return WG_OK;
 }
 
+int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *zmpref_xy, double *state,
+                         double *com_out, double *zmp_out, int simulation)
+{
+  return preview_run(ctx, pl, mem, zmpref_xy, state, com_out, zmp_out, simulation, nullptr);
+}
+
+int wg_preview_stage2_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *delta_zmp_xy,
+                                const double *com_stage1, double *state2, double *com_final_out, double *dzmp_out)
+{
+  if (!com_stage1 || !com_final_out) return WG_ERR_INVALID;
+  return preview_run(ctx, pl, mem, delta_zmp_xy, state2, com_final_out, dzmp_out, 1, com_stage1);
+}
+
 }  // extern "C"
+
+// EvaluateMultiBodyZMP (ZMPPreviewControlWithMultiBodyZMP.cpp:464-469): after the first stage popped its FIFO,
+// delta[k] = ZMPRef[k + 1] - ZMPmultibody[k].
+__global__ void __launch_bounds__(256)
+delta_zmp_kernel(int B, const int64_t *__restrict__ offsets, const double2 *__restrict__ ref, const double2 *__restrict__ mb,
+                 double2 *__restrict__ delta)
+{
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const int64_t o = offsets[b], L = offsets[b + 1] - o;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < L; k += (int64_t)gridDim.x * blockDim.x) {
+      double2 d = make_double2(0.0, 0.0);
+      if (k + 1 < L) { const double2 r = ref[o + k + 1], m = mb[o + k]; d = make_double2(r.x - m.x, r.y - m.y); }
+      delta[o + k] = d;
+    }
+  }
+}
+
+extern "C" int wg_preview_delta_zmp(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *zmpref_xy,
+                                    const double *zmp_multibody_xy, double *delta_out)
+{
+  if (!ctx || !pl || pl->ctx != ctx || !zmpref_xy || !zmp_multibody_xy || !delta_out) return WG_ERR_INVALID;
+  wg_device_guard guard(ctx->device);
+  if (pl->B == 0 || pl->total_samples == 0) return WG_OK;
+  const size_t ns = (size_t)pl->total_samples;
+  const double *d_ref = zmpref_xy, *d_mb = zmp_multibody_xy;
+  double *d_out = delta_out;
+  if (mem == WG_MEM_HOST) {
+    if (!pl->d_zmp) WG_CUDA(ctx, cudaMalloc(&pl->d_zmp, sizeof(double) * 2 * ns));
+    if (!pl->d_add) WG_CUDA(ctx, cudaMalloc(&pl->d_add, sizeof(double) * 6 * ns));   // scratch here; d_zmpout must stay zero past the last step
+    WG_CUDA(ctx, cudaMemcpyAsync(pl->d_zmp, zmpref_xy, sizeof(double) * 2 * ns, cudaMemcpyHostToDevice, ctx->stream));
+    WG_CUDA(ctx, cudaMemcpyAsync(pl->d_add, zmp_multibody_xy, sizeof(double) * 2 * ns, cudaMemcpyHostToDevice, ctx->stream));
+    d_ref = pl->d_zmp; d_mb = pl->d_add; d_out = pl->d_add;   // in place: element k only reads mb[k]
+  } else if (mem != WG_MEM_DEVICE) return WG_ERR_INVALID;
+  const int64_t avg = (pl->total_samples + pl->B - 1) / pl->B;
+  dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (avg + 255) / 256)), (unsigned)std::min(pl->B, 65535));
+  delta_zmp_kernel<<<grid, 256, 0, ctx->stream>>>(pl->B, pl->d_offsets, reinterpret_cast<const double2 *>(d_ref),
+                                                 reinterpret_cast<const double2 *>(d_mb), reinterpret_cast<double2 *>(d_out));
+  WG_LAUNCHED(ctx);
+  if (mem == WG_MEM_HOST) {
+    WG_CUDA(ctx, cudaMemcpyAsync(delta_out, d_out, sizeof(double) * 2 * ns, cudaMemcpyDeviceToHost, ctx->stream));
+    WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return WG_OK;
+}
 
 // ---- single tick for the class wrappers (PreviewControl::OneIterationOfPreview called once per 5 ms tick) ----
 // One CTA: the 2 x NL window products are reduced over 128 threads, thread 0 then runs the tick in the reference's

@@ -245,6 +245,11 @@ int PreviewControl::OneIterationOfPreview1D(MAL_MATRIX(&x, double), double &sxzm
   if (Simulation) sxzmp += (Z[lindex] - zmpx2);
   return rc;
 }
+void PreviewControl::BindGains() const
+{
+  if (!m_Coherent) throw std::runtime_error("PreviewControl: weights not computed");
+  load_gains(this, m_Gains);
+}
 int PreviewControl::RunWholeTrajectory(const std::deque<ZMPPosition> &Z, MAL_MATRIX(&x, double), MAL_MATRIX(&y, double),
                                        double &sxzmp, double &syzmp, std::vector<double> &com6, std::vector<double> &zmp2,
                                        bool Simulation)

@@ -96,9 +96,24 @@ class CjrlHumanoidDynamicRobot {
     return r;
   }
   void setHipYawJoints(const CjrlJoint &left, const CjrlJoint &right) { m_LeftHipYaw = left; m_RightHipYaw = right; }
+  /* What ZMPPreviewControlWithMultiBodyZMP asks of the model (ZMPPreviewControlWithMultiBodyZMP.cpp:163-198, :447-479).  The
+   * stand-in holds no multibody model: a caller with one overrides zeroMomentumPoint() (and positionCenterOfMass()). */
+  virtual ~CjrlHumanoidDynamicRobot() {}
+  const std::vector<double> &currentConfiguration() const { return m_Q; }
+  const std::vector<double> &currentVelocity() const { return m_dQ; }
+  const std::vector<double> &currentAcceleration() const { return m_ddQ; }
+  bool currentConfiguration(const std::vector<double> &v) { m_Q = v; return true; }
+  bool currentVelocity(const std::vector<double> &v) { m_dQ = v; return true; }
+  bool currentAcceleration(const std::vector<double> &v) { m_ddQ = v; return true; }
+  virtual bool setProperty(std::string &, const std::string &) { return true; }
+  virtual bool getProperty(const std::string &, std::string &) { return true; }
+  virtual bool computeForwardKinematics() { return true; }
+  virtual vector3d zeroMomentumPoint() const { vector3d z; z[0] = z[1] = z[2] = 0.0; return z; }
+  virtual vector3d positionCenterOfMass() const { vector3d z; z[0] = z[1] = z[2] = 0.0; return z; }
  private:
   CjrlFoot m_Left, m_Right;
   CjrlJoint m_Waist, m_LeftHipYaw, m_RightHipYaw;
+  std::vector<double> m_Q, m_dQ, m_ddQ;
 };
 #endif
 
@@ -200,6 +215,9 @@ class PreviewControl : public SimplePlugin {
   void ComputeOptimalWeights(unsigned int mode);
   void CallMethod(std::string &Method, std::istringstream &astrm);
   const wg_preview_gains_t &Gains() const { return m_Gains; }
+  /* makes this object's gains the ones loaded in the process-wide context (done by every call above; public for the
+   * classes that drive the batched C ABI with this controller's gains) */
+  void BindGains() const;
  private:
   int run1d(walkgen_b200::Matrix &x, double &sxzmp, const std::vector<double> &window, double &zmpx2, bool Simulation);
   double m_SamplingPeriod, m_PreviewControlTime, m_Zc;
@@ -625,6 +643,111 @@ class PatternGeneratorInterface : public SimplePluginManager, public SimplePlugi
   double m_InternalClock;
   int m_AlgorithmforZMPCOM;   /* 0 Kajita (default), 1 Herdt */
   bool m_Running;
+};
+
+/* The interface of src/MotionGeneration/ComAndFootRealization.hh:55-219 that the two-stage scheme calls: whole-body
+ * realisation of a CoM + feet posture (IK in the reference; out of this library's scope - the caller supplies it). */
+class ComAndFootRealization {
+ public:
+  ComAndFootRealization() : m_HumanoidDynamicRobot(0) {}
+  virtual ~ComAndFootRealization() {}
+  virtual bool ComputePostureForGivenCoMAndFeetPosture(MAL_VECTOR_TYPE(double) &CoMPosition, MAL_VECTOR_TYPE(double) &CoMSpeed,
+                                                       MAL_VECTOR_TYPE(double) &CoMAcc, MAL_VECTOR_TYPE(double) &LeftFoot,
+                                                       MAL_VECTOR_TYPE(double) &RightFoot,
+                                                       MAL_VECTOR_TYPE(double) &CurrentConfiguration,
+                                                       MAL_VECTOR_TYPE(double) &CurrentVelocity,
+                                                       MAL_VECTOR_TYPE(double) &CurrentAcceleration, int IterationNumber,
+                                                       int Stage) = 0;
+  virtual bool InitializationCoM(MAL_VECTOR_TYPE(double) &BodyAnglesIni, MAL_S3_VECTOR_TYPE(double) &lStartingCOMPosition,
+                                 MAL_VECTOR_TYPE(double) &lStartingWaistPose, FootAbsolutePosition &InitLeftFootAbsPos,
+                                 FootAbsolutePosition &InitRightFootAbsPos) = 0;
+  virtual MAL_S3_VECTOR_TYPE(double) GetCOGInitialAnkles() { return MAL_S3_VECTOR_TYPE(double)(); }
+  virtual bool setHumanoidDynamicRobot(CjrlHumanoidDynamicRobot *aHumanoidDynamicRobot)
+  { m_HumanoidDynamicRobot = aHumanoidDynamicRobot; return true; }
+  CjrlHumanoidDynamicRobot *getHumanoidDynamicRobot() const { return m_HumanoidDynamicRobot; }
+ private:
+  CjrlHumanoidDynamicRobot *m_HumanoidDynamicRobot;
+};
+
+/* src/PreviewControl/ZMPPreviewControlWithMultiBodyZMP.hh: Kajita's two-stage scheme.  The FIFO bookkeeping is the
+ * reference's, statement for statement (Setup skipping ZMPRefPositions[NL] included); each stage's
+ * OneIterationOfPreview goes to the GPU through the PreviewControl mirror.  The multibody ZMP comes from the robot
+ * (zeroMomentumPoint(), as in the reference), the posture from the ComAndFootRealization: both are the caller's. */
+class ZMPPreviewControlWithMultiBodyZMP : public SimplePlugin {
+ public:
+  static const int ZMPCOM_TRAJECTORY_FULL = 1;
+  static const int ZMPCOM_TRAJECTORY_SECOND_STAGE_ONLY = 2;
+  static const int ZMPCOM_TRAJECTORY_FIRST_STAGE_ONLY = 3;
+  explicit ZMPPreviewControlWithMultiBodyZMP(SimplePluginManager *lSPM);
+  ~ZMPPreviewControlWithMultiBodyZMP();
+  void SetPreviewControl(PreviewControl *aPC);
+  void SetStrategyForStageActivation(int aZMPComTraj);
+  int GetStrategyForStageActivation() { return m_StageStrategy; }
+  void SetStrategyForPCStages(int Strategy) { m_StageStrategy = Strategy; }
+  int GetStrategyForPCStages() { return m_StageStrategy; }
+  bool setComAndFootRealization(ComAndFootRealization *aCFR) { m_ComAndFootRealization = aCFR; return true; }
+  ComAndFootRealization *getComAndFootRealization() { return m_ComAndFootRealization; }
+  bool setHumanoidDynamicRobot(CjrlHumanoidDynamicRobot *aHumanoidDynamicRobot)
+  { m_HumanoidDynamicRobot = aHumanoidDynamicRobot; return true; }
+  CjrlHumanoidDynamicRobot *getHumanoidDynamicRobot() const { return m_HumanoidDynamicRobot; }
+  int OneGlobalStepOfControl(FootAbsolutePosition &LeftFootPosition, FootAbsolutePosition &RightFootPosition,
+                             ZMPPosition &NewZMPRefPos, COMState &refandfinalCOMState,
+                             MAL_VECTOR_TYPE(double) &CurrentConfiguration, MAL_VECTOR_TYPE(double) &CurrentVelocity,
+                             MAL_VECTOR_TYPE(double) &CurrentAcceleration);
+  int FirstStageOfControl(FootAbsolutePosition &LeftFootPosition, FootAbsolutePosition &RightFootPosition,
+                          COMState &afCOMState);
+  int EvaluateMultiBodyZMP(int StartingIteration);
+  int SecondStageOfControl(COMState &refandfinalCOMState);
+  COMState GetLastCOMFromFirstStage() { return m_FIFOCOMStates.back(); }
+  int Setup(std::deque<ZMPPosition> &ZMPRefPositions, std::deque<COMState> &COMStates,
+            std::deque<FootAbsolutePosition> &LeftFootPositions, std::deque<FootAbsolutePosition> &RightFootPositions);
+  int SetupFirstPhase(std::deque<ZMPPosition> &ZMPRefPositions, std::deque<COMState> &COMStates,
+                      std::deque<FootAbsolutePosition> &LeftFootPositions,
+                      std::deque<FootAbsolutePosition> &RightFootPositions);
+  int SetupIterativePhase(std::deque<ZMPPosition> &ZMPRefPositions, std::deque<COMState> &COMStates,
+                          std::deque<FootAbsolutePosition> &LeftFootPositions,
+                          std::deque<FootAbsolutePosition> &RightFootPositions,
+                          MAL_VECTOR_TYPE(double) &CurrentConfiguration, MAL_VECTOR_TYPE(double) &CurrentVelocity,
+                          MAL_VECTOR_TYPE(double) &CurrentAcceleration, int localindex);
+  void CreateExtraCOMBuffer(std::deque<COMState> &ExtraCOMBuffer, std::deque<ZMPPosition> &ExtraZMPBuffer,
+                            std::deque<ZMPPosition> &ExtraZMPRefBuffer);
+  int EvaluateStartingCoM(MAL_VECTOR_TYPE(double) &BodyAnglesInit, MAL_S3_VECTOR_TYPE(double) &aStartingCOMState,
+                          MAL_VECTOR_TYPE(double) &aStartingWaistPosition, FootAbsolutePosition &InitLeftFootPosition,
+                          FootAbsolutePosition &InitRightFootPosition);
+  int EvaluateStartingState(MAL_VECTOR_TYPE(double) &BodyAnglesInit, MAL_S3_VECTOR_TYPE(double) &aStartingCOMState,
+                            MAL_S3_VECTOR_TYPE(double) &aStartingZMPPosition, MAL_VECTOR_TYPE(double) &aStartingWaistPosition,
+                            FootAbsolutePosition &InitLeftFootPosition, FootAbsolutePosition &InitRightFootPosition);
+  void UpdateTheZMPRefQueue(ZMPPosition NewZMPRefPos) { m_FIFOZMPRefPositions.push_back(NewZMPRefPos); }
+  void SetSamplingPeriod(double v) { m_SamplingPeriod = v; }
+  double SamplingPeriod() const { return m_SamplingPeriod; }
+  void SetPreviewControlTime(double v) { m_PreviewControlTime = v; }
+  double PreviewControlTime() const { return m_PreviewControlTime; }
+  void CallMethod(std::string &Method, std::istringstream &astrm);
+  /* Batched form (new): the whole scheme over a complete ZMP reference with the multibody ZMP of every first-stage tick
+   * supplied by `multibody_zmp(tick, CoM of that tick, out xy)`: one GPU pass per stage instead of two launches per tick.
+   * Same FIFO semantics as Setup + OneGlobalStepOfControl to the end of the stream; FinalCOMStates gets one state per
+   * global step (x, y filled). */
+  int RunWholeTrajectory(std::deque<ZMPPosition> &ZMPRefPositions, const COMState &StartingCOM,
+                         void (*multibody_zmp)(void *user, long tick, const double *com6, double *zmp_xy), void *user,
+                         std::deque<COMState> &FinalCOMStates);
+ private:
+  void CallToComAndFootRealization(COMState &acomp, FootAbsolutePosition &aLeftFAP, FootAbsolutePosition &aRightFAP,
+                                   MAL_VECTOR_TYPE(double) &CurrentConfiguration, MAL_VECTOR_TYPE(double) &CurrentVelocity,
+                                   MAL_VECTOR_TYPE(double) &CurrentAcceleration, int IterationNumber, int StageOfTheAlgorithm);
+  PreviewControl *m_PC;
+  bool m_OwnPC;
+  CjrlHumanoidDynamicRobot *m_HumanoidDynamicRobot;
+  ComAndFootRealization *m_ComAndFootRealization;
+  walkgen_b200::Matrix m_PC1x, m_PC1y, m_Deltax, m_Deltay;
+  double m_sxzmp, m_syzmp, m_sxDeltazmp, m_syDeltazmp;
+  double m_SamplingPeriod, m_PreviewControlTime;
+  unsigned int m_NL;
+  int m_StageStrategy, m_NumberOfIterations;
+  bool m_StartingNewSequence;
+  MAL_S3_VECTOR_TYPE(double) m_StartingCOMState;
+  std::deque<ZMPPosition> m_FIFOZMPRefPositions, m_FIFODeltaZMPPositions;
+  std::deque<COMState> m_FIFOCOMStates;
+  std::deque<FootAbsolutePosition> m_FIFOLeftFootPosition, m_FIFORightFootPosition;
 };
 
 /* patterngeneratorinterface.hh:306 */

@@ -19,6 +19,7 @@
  */
 #include <cmath>
 #include <cstring>
+#include <array>
 #include <deque>
 #include <thread>
 #include <vector>
@@ -354,6 +355,73 @@ long oracle_preview_run_batch_mt(const double *A, const double *B, const double 
   long total = 0;
   for (int b = 0; b < nb; ++b) { long long L = offsets[b + 1] - offsets[b]; if (L >= NL) total += (long)(L - NL + 1); }
   return total;
+}
+
+/* ZMPPreviewControlWithMultiBodyZMP, the two-stage scheme with a caller-supplied multibody ZMP, restated with the
+ * reference's FIFOs (src/PreviewControl/ZMPPreviewControlWithMultiBodyZMP.cpp):
+ *   SetupFirstPhase (:530-600): FIFO = ZMPRefPositions[0 .. NL), PC1 = (start CoM, 0, 0), Delta = 0, all sums 0;
+ *   SetupIterativePhase(i), i < NL (:602-664): FirstStageOfControl (preview at lindex 0 with Simulation = true,
+ *       push the CoM, pop the FIFO front, :378-446), EvaluateMultiBodyZMP (delta = FIFO[0] - ZMPmultibody, :447-479),
+ *       then push ZMPRefPositions[i + 1 + NL] - so ZMPRefPositions[NL] never enters the FIFO (:660);
+ *   OneGlobalStepOfControl (:194-266): FirstStageOfControl, EvaluateMultiBodyZMP, SecondStageOfControl (preview on the
+ *       delta FIFO at lindex 0, final CoM = FIFOCOM[0] + Delta on all three derivatives, pop both, :317-376); the caller
+ *       then feeds the next reference sample (UpdateTheZMPRefQueue, :753).
+ * zmb [n_zmb][2] is the multibody ZMP of first-stage tick k (the reference computes it from the posture realised for
+ * that tick's CoM).  Outputs: stage1 [ticks][6], delta [ticks][2] (ticks = first-stage ticks run), final_com [steps][6];
+ * returns steps = the number of OneGlobalStepOfControl calls the stream allows, or -1. */
+long oracle_two_stage_run(const double *A, const double *B, const double *C, const double *Kx, double Ks,
+                          const double *F, int NL, const double *zmpref_xy, long L, const double *zmb, long n_zmb,
+                          const double *com_start_xy, double *stage1, double *delta, double *final_com, long *ticks_out)
+{
+  if (L < 2 * (long)NL + 1) return -1;
+  std::deque<std::array<double, 2>> fifo_ref, fifo_delta;
+  std::deque<std::array<double, 6>> fifo_com;
+  for (int i = 0; i < NL; ++i) fifo_ref.push_back({zmpref_xy[2 * i], zmpref_xy[2 * i + 1]});
+  double pc1x[3] = {com_start_xy[0], 0, 0}, pc1y[3] = {com_start_xy[1], 0, 0}, sx = 0, sy = 0;
+  double dx[3] = {0, 0, 0}, dy[3] = {0, 0, 0}, sdx = 0, sdy = 0;
+  std::vector<double> win(2 * (size_t)NL);
+  long tick = 0;
+  auto first_stage = [&]() {
+    for (int i = 0; i < NL; ++i) { win[2 * i] = fifo_ref[i][0]; win[2 * i + 1] = fifo_ref[i][1]; }
+    double zx, zy;
+    oracle_preview_step(A, B, C, Kx, Ks, F, NL, pc1x, pc1y, &sx, &sy, win.data(), (int)fifo_ref.size(), &zx, &zy, 1);
+    fifo_com.push_back({pc1x[0], pc1x[1], pc1x[2], pc1y[0], pc1y[1], pc1y[2]});
+    if (stage1) for (int c = 0; c < 6; ++c) stage1[6 * tick + c] = fifo_com.back()[c];
+    fifo_ref.pop_front();
+  };
+  auto evaluate_multibody = [&]() {
+    std::array<double, 2> d = {fifo_ref[0][0] - zmb[2 * tick], fifo_ref[0][1] - zmb[2 * tick + 1]};
+    fifo_delta.push_back(d);
+    if (delta) { delta[2 * tick] = d[0]; delta[2 * tick + 1] = d[1]; }
+  };
+  for (int i = 0; i < NL; ++i) {               /* Setup */
+    if (tick >= n_zmb) return -1;
+    first_stage();
+    evaluate_multibody();
+    fifo_ref.push_back({zmpref_xy[2 * (size_t)(i + 1 + NL)], zmpref_xy[2 * (size_t)(i + 1 + NL) + 1]});
+    ++tick;
+  }
+  long next_ref = 2 * (long)NL + 1, steps = 0;
+  while ((long)fifo_ref.size() >= NL && tick < n_zmb) {   /* OneGlobalStepOfControl */
+    first_stage();
+    if (fifo_ref.empty()) break;
+    evaluate_multibody();
+    for (int i = 0; i < NL; ++i) { win[2 * i] = fifo_delta[i][0]; win[2 * i + 1] = fifo_delta[i][1]; }
+    double zx, zy;
+    oracle_preview_step(A, B, C, Kx, Ks, F, NL, dx, dy, &sdx, &sdy, win.data(), (int)fifo_delta.size(), &zx, &zy, 1);
+    const std::array<double, 6> &c0 = fifo_com[0];
+    if (final_com) {
+      double *o = final_com + 6 * steps;
+      o[0] = c0[0] + dx[0]; o[1] = c0[1] + dx[1]; o[2] = c0[2] + dx[2];
+      o[3] = c0[3] + dy[0]; o[4] = c0[4] + dy[1]; o[5] = c0[5] + dy[2];
+    }
+    fifo_delta.pop_front();
+    fifo_com.pop_front();
+    ++steps; ++tick;
+    if (next_ref < L) { fifo_ref.push_back({zmpref_xy[2 * next_ref], zmpref_xy[2 * next_ref + 1]}); ++next_ref; }
+  }
+  if (ticks_out) *ticks_out = tick;
+  return steps;
 }
 
 } /* extern "C" */

@@ -171,8 +171,31 @@ template <typename T> vector<T> prod(const matrix<T> &A, const vector<T> &x)
   return y;
 }
 
+/* jrl-mal's "small" fixed-size types (matrixabstractlayersmall*.hh): a 3-vector and a 4x4 matrix, only element access
+ * and assignment are used by the sources compiled here (ZMPPreviewControlWithMultiBodyZMP.cpp) */
+template <typename T> struct vec3 {
+  T v[3];
+  vec3() { v[0] = v[1] = v[2] = T(); }
+  T &operator()(std::size_t i) { return v[i]; }
+  const T &operator()(std::size_t i) const { return v[i]; }
+  T &operator[](std::size_t i) { return v[i]; }
+  const T &operator[](std::size_t i) const { return v[i]; }
+};
+template <typename T> struct mat4 {
+  T m[16];
+  mat4() { for (int i = 0; i < 16; ++i) m[i] = T(); }
+  T &operator()(std::size_t i, std::size_t j) { return m[4 * i + j]; }
+  const T &operator()(std::size_t i, std::size_t j) const { return m[4 * i + j]; }
+};
+
 }  // namespace oracle_mal
 
+#define MAL_VECTOR_TYPE(type) oracle_mal::vector<type>
+#define MAL_S3_VECTOR(name, type) oracle_mal::vec3<type> name
+#define MAL_S3_VECTOR_TYPE(type) oracle_mal::vec3<type>
+#define MAL_S4x4_MATRIX_TYPE(type) oracle_mal::mat4<type>
+#define MAL_S4x4_MATRIX(name, type) oracle_mal::mat4<type> name
+#define MAL_S4x4_MATRIX_ACCESS_I_J(name, i, j) name(i, j)
 #define MAL_VECTOR(name, type) oracle_mal::vector<type> name
 #define MAL_VECTOR_DIM(name, type, n) oracle_mal::vector<type> name(n)
 #define MAL_VECTOR_RESIZE(name, n) name.resize(n)

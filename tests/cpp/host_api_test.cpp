@@ -380,6 +380,114 @@ static int test_dimitrov(const char *out, bool robust)
   return hull.size() == 4 ? 0 : 5;
 }
 
+// ---- ZMPPreviewControlWithMultiBodyZMP: Setup + OneGlobalStepOfControl tick by tick, as the reference's callers drive it
+// (PatternGeneratorInterfacePrivate.cpp, DoubleStagePreviewControlStrategy), with test doubles for the model: the
+// realisation records the first-stage CoM it is asked to realise, the robot answers zeroMomentumPoint() with the
+// cart-table ZMP of that CoM at 0.9 zc plus a slow disturbance (tests/test_two_stage.py: synthetic_multibody_zmp).
+// Input: [L][2] doubles (ZMP reference); output: steps x 6 final CoM, then the batched RunWholeTrajectory result.
+namespace {
+struct ModelRobot : public CjrlHumanoidDynamicRobot {
+  double com6[6]; long tick; double zc;
+  ModelRobot() : tick(0), zc(0.807709) { for (int i = 0; i < 6; ++i) com6[i] = 0; }
+  static void model(long k, const double *c, double zc, double *out)
+  {
+    const double h = 0.9 * zc / 9.81;
+    out[0] = c[0] - h * c[2] + 0.003 * sin(0.02 * k);
+    out[1] = c[3] - h * c[5] + 0.002 * cos(0.015 * k);
+  }
+  vector3d zeroMomentumPoint() const { vector3d z; double o[2]; model(tick, com6, zc, o); z[0] = o[0]; z[1] = o[1]; z[2] = 0; return z; }
+};
+struct RecordingRealization : public ComAndFootRealization {
+  ModelRobot *robot; double start[3];
+  bool ComputePostureForGivenCoMAndFeetPosture(std::vector<double> &p, std::vector<double> &v, std::vector<double> &a,
+                                               std::vector<double> &, std::vector<double> &, std::vector<double> &,
+                                               std::vector<double> &, std::vector<double> &, int it, int stage)
+  {
+    if (stage == 0) {
+      robot->tick = it;
+      robot->com6[0] = p[0]; robot->com6[1] = v[0]; robot->com6[2] = a[0];
+      robot->com6[3] = p[1]; robot->com6[4] = v[1]; robot->com6[5] = a[1];
+    }
+    return true;
+  }
+  bool InitializationCoM(std::vector<double> &, S3Vector &c, std::vector<double> &, FootAbsolutePosition &, FootAbsolutePosition &)
+  { c[0] = start[0]; c[1] = start[1]; c[2] = start[2]; return true; }
+};
+void model_cb(void *user, long k, const double *c, double *out) { ModelRobot::model(k, c, *static_cast<double *>(user), out); }
+}  // namespace
+
+static int test_twostage(const char *in, const char *out, int max_ticks)
+{
+  std::ifstream fi(in, std::ios::binary);
+  std::vector<double> zin((std::istreambuf_iterator<char>(fi)), std::istreambuf_iterator<char>());
+  fi.clear(); fi.seekg(0, std::ios::end);
+  const size_t bytes = (size_t)fi.tellg();
+  fi.seekg(0);
+  zin.assign(bytes / sizeof(double), 0.0);
+  fi.read(reinterpret_cast<char *>(zin.data()), bytes);
+  const size_t L = zin.size() / 2;
+  SimplePluginManager spm;
+  ZMPPreviewControlWithMultiBodyZMP zpc(&spm);
+  PreviewControl pc(&spm, OptimalControllerSolver::MODE_WITHOUT_INITIALPOS, true);
+  pc.SetSamplingPeriod(0.005); pc.SetPreviewControlTime(1.6); pc.SetHeightOfCoM(0.807709);
+  zpc.SetPreviewControl(&pc);
+  ModelRobot robot;
+  RecordingRealization cfr; cfr.robot = &robot;
+  cfr.start[0] = zin[0] + 0.001; cfr.start[1] = zin[1] - 0.002; cfr.start[2] = 0.807709;
+  cfr.setHumanoidDynamicRobot(&robot);
+  zpc.setComAndFootRealization(&cfr);
+  zpc.setHumanoidDynamicRobot(&robot);
+  const unsigned NL = 320;
+  std::deque<ZMPPosition> ref(L);
+  std::deque<COMState> coms(L);
+  std::deque<FootAbsolutePosition> lf(L), rf(L);
+  for (size_t i = 0; i < L; ++i) {
+    std::memset(&ref[i], 0, sizeof(ZMPPosition)); std::memset(&lf[i], 0, sizeof(FootAbsolutePosition));
+    std::memset(&rf[i], 0, sizeof(FootAbsolutePosition));
+    ref[i].px = zin[2 * i]; ref[i].py = zin[2 * i + 1]; ref[i].time = 0.005 * i;
+  }
+  std::vector<double> body(36), waist(6);
+  S3Vector sc;
+  zpc.EvaluateStartingCoM(body, sc, waist, lf[0], rf[0]);
+  zpc.Setup(ref, coms, lf, rf);
+  std::vector<double> q, dq, ddq, serial;
+  size_t next_ref = 2 * NL + 1;
+  int steps = 0;
+  while (steps < max_ticks && next_ref <= L) {
+    COMState fin; ZMPPosition zp; std::memset(&zp, 0, sizeof zp);
+    zpc.OneGlobalStepOfControl(lf[0], rf[0], zp, fin, q, dq, ddq);
+    for (int j = 0; j < 3; ++j) serial.push_back(fin.x[j]);
+    for (int j = 0; j < 3; ++j) serial.push_back(fin.y[j]);
+    ++steps;
+    if (next_ref < L) zpc.UpdateTheZMPRefQueue(ref[next_ref]);
+    ++next_ref;
+  }
+  // batched form over the whole stream
+  ZMPPreviewControlWithMultiBodyZMP zb(&spm);
+  zb.SetPreviewControl(&pc);
+  COMState start; start.x[0] = cfr.start[0]; start.y[0] = cfr.start[1]; start.z[0] = cfr.start[2];
+  std::deque<COMState> fin_b;
+  double zc = 0.807709;
+  const int nb = zb.RunWholeTrajectory(ref, start, model_cb, &zc, fin_b);
+  if (nb != (int)(L - 2 * NL)) { std::cerr << "batched steps " << nb << std::endl; return 2; }
+  double worst = 0.0;
+  for (int n = 0; n < steps; ++n)
+    for (int j = 0; j < 3; ++j) {
+      worst = std::max(worst, fabs(fin_b[n].x[j] - serial[6 * n + j]));
+      worst = std::max(worst, fabs(fin_b[n].y[j] - serial[6 * n + 3 + j]));
+    }
+  std::cout << "two-stage: " << steps << " ticks, max |batched - tick by tick| = " << worst << std::endl;
+  std::ofstream f(out, std::ios::binary);
+  const double hdr[2] = {(double)steps, (double)nb};
+  f.write(reinterpret_cast<const char *>(hdr), sizeof hdr);
+  f.write(reinterpret_cast<const char *>(serial.data()), sizeof(double) * serial.size());
+  for (int n = 0; n < nb; ++n) {
+    double r[6] = {fin_b[n].x[0], fin_b[n].x[1], fin_b[n].x[2], fin_b[n].y[0], fin_b[n].y[1], fin_b[n].y[2]};
+    f.write(reinterpret_cast<const char *>(r), sizeof r);
+  }
+  return worst < 1e-9 ? 0 : 5;
+}
+
 int main(int argc, char **argv)
 {
   try {
@@ -389,6 +497,7 @@ int main(int argc, char **argv)
     if (what == "preview" && argc > 2) return test_preview(argv[2]);
     if (what == "kajita2003" && argc > 3) return test_kajita2003(argv[2], argv[3]);
     if (what == "preview1d" && argc > 4) return test_preview1d(argv[2], argv[3], argv[4]);
+    if (what == "twostage" && argc > 4) return test_twostage(argv[2], argv[3], atoi(argv[4]));
     if (what == "pldp" && argc > 3) return test_pldp(argv[2], argv[3]);
     if (what == "dimitrov" && argc > 2) return test_dimitrov(argv[2], argc > 3 && std::string(argv[3]) == "robust");
     std::cerr << "usage: host_api_test optcholesky | herdt2010 out.dat nticks | preview out.bin | pldp in.bin out.bin" << std::endl;
