@@ -102,6 +102,18 @@ typedef struct wg_preview_gains_t {
  * obtained with the structure-preserving doubling algorithm. */
 int wg_preview_gains(double T, double preview_time, double zc, int mode, wg_preview_gains_t *out);
 
+/* The same solve for B parameter sets at once on the device (one thread per set; the reference has a single-instance
+ * OptimalControllerSolver only): params [B][3] = (T, preview_time, zc); heads [B]; F [B][f_stride] with f_stride >= the
+ * largest NL (entries past NL are left untouched in device memory, zero in host memory).  A set the solve refuses
+ * (T <= 0, NL > f_stride, singular pencil) gets NL = 0 and Ks = NaN. */
+typedef struct wg_preview_gains_head {
+  double A[9], B[3], C[3], Kx[3], Ks;
+  double T, preview_time, zc;
+  int32_t mode, NL;
+} wg_preview_gains_head;              /* 184 bytes */
+int wg_preview_gains_batch(wg_ctx *ctx, int mem, int B, const double *params, int mode, wg_preview_gains_head *heads,
+                           double *F, long long f_stride);
+
 /* Upload gains to the context (constant memory image used by the kernels). */
 int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *gains);
 

@@ -228,6 +228,18 @@ class Context:
         self._check(self.lib.wg_herdt_qp_solve_batch(self.h, mem, int(count), _ptr(inputs), _ptr(outputs)))
         return outputs
 
+    def preview_gains_batch(self, params, mode=MODE_WITHOUT_INITIALPOS, f_stride=None):
+        """wg_preview_gains_batch on host arrays: params [B][3] = (T, preview_time, zc) -> (heads, F [B][f_stride])."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        B = len(params)
+        if f_stride is None:
+            f_stride = int(np.max(np.floor(params[:, 1] / params[:, 0]))) + 1 if B else 1
+        heads = np.zeros(B, dtype=_capi.preview_gains_head_dtype())
+        F = np.zeros((B, f_stride))
+        self._check(self.lib.wg_preview_gains_batch(self.h, WG_MEM_HOST, B, params.ctypes.data, int(mode), heads.ctypes.data,
+                                                    F.ctypes.data, int(f_stride)))
+        return heads, F
+
     def herdt_qp_solve_warm(self, inputs, guess=None, age=1, outputs=None, active=None):
         """wg_herdt_qp_solve_batch_warm on host arrays -> (outputs, optimal active sets)."""
         inputs = np.ascontiguousarray(inputs, dtype=QP_INPUT_DTYPE)

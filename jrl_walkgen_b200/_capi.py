@@ -155,6 +155,15 @@ def herdt_dtypes():
     return qin, qout
 
 
+def preview_gains_head_dtype():
+    """numpy mirror of wg_preview_gains_head (184 B)."""
+    np = _np()
+    d = np.dtype([("A", "f8", 9), ("B", "f8", 3), ("C", "f8", 3), ("Kx", "f8", 3), ("Ks", "f8"), ("T", "f8"),
+                  ("preview_time", "f8"), ("zc", "f8"), ("mode", "i4"), ("NL", "i4")])
+    assert d.itemsize == 184
+    return d
+
+
 def herdt_active_set_dtype():
     """numpy mirror of wg_herdt_active_set (48 B)."""
     np = _np()
@@ -215,6 +224,8 @@ SIGNATURES = {
     "wg_prof_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), c_double_p]),
     "wg_measure_fp64_peak": (C.c_int, [C.c_void_p, c_double_p]),
     "wg_preview_gains": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(PreviewGains)]),
+    "wg_preview_gains_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_longlong]),
     "wg_preview_set_gains": (C.c_int, [C.c_void_p, C.POINTER(PreviewGains)]),
     "wg_preview_plan_create": (C.c_int, [C.c_void_p, C.c_int, c_i64_p, C.POINTER(C.c_void_p)]),
     "wg_preview_plan_destroy": (C.c_int, [C.c_void_p]),

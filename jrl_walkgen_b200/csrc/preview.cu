@@ -40,18 +40,27 @@
 // Host: gains by structure-preserving doubling (SDA) for the DARE
 //     P = A'PA - A'Pb (R + b'Pb)^-1 b'PA + c'Qc
 // ---------------------------------------------------------------------------------------------
+#define WG_HD __host__ __device__
+
 namespace {
 
 struct Mat {  // tiny dense n x n (n <= 4), row-major
   int n;
   double a[16];
-  double &operator()(int i, int j) { return a[i * n + j]; }
-  double operator()(int i, int j) const { return a[i * n + j]; }
+  WG_HD double &operator()(int i, int j) { return a[i * n + j]; }
+  WG_HD double operator()(int i, int j) const { return a[i * n + j]; }
 };
 
-Mat mm(const Mat &A, const Mat &B)
+WG_HD Mat mat_zero(int n)
 {
-  Mat C{A.n, {0}};
+  Mat C;
+  C.n = n;
+  for (int i = 0; i < 16; ++i) C.a[i] = 0.0;
+  return C;
+}
+WG_HD Mat mm(const Mat &A, const Mat &B)
+{
+  Mat C = mat_zero(A.n);
   for (int i = 0; i < A.n; ++i)
     for (int j = 0; j < A.n; ++j) {
       double s = 0;
@@ -60,30 +69,33 @@ Mat mm(const Mat &A, const Mat &B)
     }
   return C;
 }
-Mat tr(const Mat &A)
+WG_HD Mat tr(const Mat &A)
 {
-  Mat C{A.n, {0}};
+  Mat C = mat_zero(A.n);
   for (int i = 0; i < A.n; ++i)
     for (int j = 0; j < A.n; ++j) C(i, j) = A(j, i);
   return C;
 }
-Mat add(const Mat &A, const Mat &B)
+WG_HD Mat add(const Mat &A, const Mat &B)
 {
-  Mat C{A.n, {0}};
+  Mat C = mat_zero(A.n);
   for (int i = 0; i < A.n * A.n; ++i) C.a[i] = A.a[i] + B.a[i];
   return C;
 }
 // X = W^-1 B by Gaussian elimination with partial pivoting.
-bool solve(Mat W, Mat B, Mat &X)
+WG_HD bool solve(Mat W, Mat B, Mat &X)
 {
   int n = W.n;
   for (int c = 0; c < n; ++c) {
     int piv = c;
     for (int r = c + 1; r < n; ++r)
-      if (std::fabs(W(r, c)) > std::fabs(W(piv, c))) piv = r;
+      if (fabs(W(r, c)) > fabs(W(piv, c))) piv = r;
     if (W(piv, c) == 0.0) return false;
     if (piv != c)
-      for (int j = 0; j < n; ++j) { std::swap(W(piv, j), W(c, j)); std::swap(B(piv, j), B(c, j)); }
+      for (int j = 0; j < n; ++j) {
+        double t = W(piv, j); W(piv, j) = W(c, j); W(c, j) = t;
+        t = B(piv, j); B(piv, j) = B(c, j); B(c, j) = t;
+      }
     for (int r = c + 1; r < n; ++r) {
       double f = W(r, c) / W(c, c);
       for (int j = c; j < n; ++j) W(r, j) -= f * W(c, j);
@@ -100,10 +112,10 @@ bool solve(Mat W, Mat B, Mat &X)
   return true;
 }
 
-bool dare_sda(const Mat &A0, const double *b, const double *c, double Q, double R, Mat &P)
+WG_HD bool dare_sda(const Mat &A0, const double *b, const double *c, double Q, double R, Mat &P)
 {
   int n = A0.n;
-  Mat A = A0, G{n, {0}}, H{n, {0}}, I{n, {0}};
+  Mat A = A0, G = mat_zero(n), H = mat_zero(n), I = mat_zero(n);
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) {
       G(i, j) = b[i] * b[j] / R;
@@ -112,7 +124,7 @@ bool dare_sda(const Mat &A0, const double *b, const double *c, double Q, double 
     }
   for (int it = 0; it < 200; ++it) {
     Mat W = add(I, mm(G, H));
-    Mat WiA, WiG;
+    Mat WiA = mat_zero(n), WiG = mat_zero(n);
     if (!solve(W, A, WiA)) return false;   // W^-1 A
     if (!solve(W, G, WiG)) return false;   // W^-1 G
     Mat At = tr(A);
@@ -121,8 +133,8 @@ bool dare_sda(const Mat &A0, const double *b, const double *c, double Q, double 
     Mat H1 = add(H, mm(mm(At, H), WiA));
     double diff = 0, norm = 0;
     for (int i = 0; i < n * n; ++i) {
-      diff = std::fmax(diff, std::fabs(H1.a[i] - H.a[i]));
-      norm = std::fmax(norm, std::fabs(H1.a[i]));
+      diff = fmax(diff, fabs(H1.a[i] - H.a[i]));
+      norm = fmax(norm, fabs(H1.a[i]));
     }
     A = A1; G = G1; H = H1;
     if (diff <= 1e-16 * norm) break;
@@ -133,24 +145,24 @@ bool dare_sda(const Mat &A0, const double *b, const double *c, double Q, double 
   return true;
 }
 
-}  // namespace
-
-extern "C" int wg_preview_gains(double T, double preview_time, double zc, int mode, wg_preview_gains_t *out)
+// PreviewControl::ComputeOptimalWeights + OptimalControllerSolver::ComputeWeights for one (T, preview time, zc, mode):
+// the head (A, B, C, Kx, Ks) and the NL window weights.  Host (wg_preview_gains) and device (preview_gains_kernel, one
+// thread per parameter set) run this same code.
+WG_HD int gains_core(double T, double preview_time, double zc, int mode, wg_preview_gains_head *out, double *F, int f_cap)
 {
-  if (!out || T <= 0.0 || preview_time <= 0.0) return WG_ERR_INVALID;
-  int NL = (int)(preview_time / T);
-  if (NL <= 0 || NL > WG_PREVIEW_MAX_NL) return WG_ERR_INVALID;
-  std::memset(out, 0, sizeof *out);
+  if (!(T > 0.0) || !(preview_time > 0.0)) return WG_ERR_INVALID;
+  const int NL = (int)(preview_time / T);
+  if (NL <= 0 || NL > WG_PREVIEW_MAX_NL || NL > f_cap) return WG_ERR_INVALID;
   out->T = T; out->preview_time = preview_time; out->zc = zc; out->mode = mode; out->NL = NL;
   const double A[9] = {1.0, T, T * T / 2.0, 0.0, 1.0, T, 0.0, 0.0, 1.0};
   const double B[3] = {T * T * T / 6.0, T * T / 2.0, T};
   const double C[3] = {1.0, 0.0, -zc / 9.81};
-  std::memcpy(out->A, A, sizeof A);
-  std::memcpy(out->B, B, sizeof B);
-  std::memcpy(out->C, C, sizeof C);
+  for (int i = 0; i < 9; ++i) out->A[i] = A[i];
+  for (int i = 0; i < 3; ++i) { out->B[i] = B[i]; out->C[i] = C[i]; out->Kx[i] = 0.0; }
+  out->Ks = 0.0;
 
-  Mat Ax{0, {0}};
-  double bx[4] = {0}, cx[4] = {0}, Q = 1.0, R;
+  Mat Ax = mat_zero(0);
+  double bx[4] = {0, 0, 0, 0}, cx[4] = {0, 0, 0, 0}, Q = 1.0, R;
   if (mode == WG_PREVIEW_MODE_WITHOUT_INITIALPOS) {
     // augmented (integrated error, state increment) system, PreviewControl.cpp:237-262
     R = 1e-6;
@@ -173,44 +185,110 @@ extern "C" int wg_preview_gains(double T, double preview_time, double zc, int mo
     return WG_ERR_INVALID;
   }
   int n = Ax.n;
-  Mat P{n, {0}};
+  Mat P = mat_zero(n);
   if (!dare_sda(Ax, bx, cx, Q, R, P)) return WG_ERR_INVALID;
 
-  double Pb[4] = {0}, bPb = 0;
+  double Pb[4] = {0, 0, 0, 0}, bPb = 0;
   for (int i = 0; i < n; ++i) {
     for (int j = 0; j < n; ++j) Pb[i] += P(i, j) * bx[j];
   }
   for (int i = 0; i < n; ++i) bPb += bx[i] * Pb[i];
   const double la = 1.0 / (R + bPb);
   Mat PA = mm(P, Ax);
-  double K[4] = {0};
+  double K[4] = {0, 0, 0, 0};
   for (int j = 0; j < n; ++j) {
     double s = 0;
     for (int l = 0; l < n; ++l) s += bx[l] * PA(l, j);
     K[j] = s * la;
   }
   // F[k] = la b' ((A - bK)')^k (P c'Q | c'Q)
-  double rec[4], nxt[4];
+  double rec[4] = {0, 0, 0, 0}, nxt[4];
   for (int i = 0; i < n; ++i) rec[i] = cx[i] * Q;
   if (mode == WG_PREVIEW_MODE_WITHOUT_INITIALPOS) {
     for (int i = 0; i < n; ++i) { nxt[i] = 0; for (int j = 0; j < n; ++j) nxt[i] += P(i, j) * rec[j]; }
-    std::memcpy(rec, nxt, sizeof rec);
+    for (int i = 0; i < n; ++i) rec[i] = nxt[i];
   }
   for (int k = 0; k < NL; ++k) {
     double s = 0;
     for (int l = 0; l < n; ++l) s += la * bx[l] * rec[l];
-    out->F[k] = s;
+    F[k] = s;
     for (int i = 0; i < n; ++i) {
       nxt[i] = 0;
       for (int j = 0; j < n; ++j) nxt[i] += (Ax(j, i) - bx[j] * K[i]) * rec[j];
     }
-    std::memcpy(rec, nxt, sizeof rec);
+    for (int i = 0; i < n; ++i) rec[i] = nxt[i];
   }
   out->Ks = K[0];
   if (mode == WG_PREVIEW_MODE_WITHOUT_INITIALPOS)
     for (int i = 0; i < 3; ++i) out->Kx[i] = K[i + 1];
   else
     for (int i = 0; i < 3; ++i) out->Kx[i] = K[i];
+  return WG_OK;
+}
+
+}  // namespace
+
+extern "C" int wg_preview_gains(double T, double preview_time, double zc, int mode, wg_preview_gains_t *out)
+{
+  if (!out) return WG_ERR_INVALID;
+  std::memset(out, 0, sizeof *out);
+  wg_preview_gains_head h;
+  const int rc = gains_core(T, preview_time, zc, mode, &h, out->F, WG_PREVIEW_MAX_NL);
+  if (rc != WG_OK) return rc;
+  std::memcpy(out->A, h.A, sizeof h.A); std::memcpy(out->B, h.B, sizeof h.B); std::memcpy(out->C, h.C, sizeof h.C);
+  std::memcpy(out->Kx, h.Kx, sizeof h.Kx);
+  out->Ks = h.Ks; out->T = T; out->preview_time = preview_time; out->zc = zc; out->mode = mode; out->NL = h.NL;
+  return WG_OK;
+}
+
+// Batched gains: one thread per (T, preview time, zc).  ~20 doubling steps on 4 x 4 matrices and an
+// NL-step 4-vector recursion per instance: a few 10^4 flops, register / local-memory resident.
+__global__ void __launch_bounds__(64)
+preview_gains_kernel(int B, const double *__restrict__ params, int mode, wg_preview_gains_head *__restrict__ heads,
+                     double *__restrict__ F, long long f_stride)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  wg_preview_gains_head h;
+  const int rc = gains_core(params[3 * (size_t)b], params[3 * (size_t)b + 1], params[3 * (size_t)b + 2], mode, &h,
+                            F + (size_t)b * f_stride, (int)(f_stride > WG_PREVIEW_MAX_NL ? WG_PREVIEW_MAX_NL : f_stride));
+  if (rc != WG_OK) {
+    h.NL = 0; h.mode = mode; h.Ks = 0.0 / 0.0;
+    h.T = params[3 * (size_t)b]; h.preview_time = params[3 * (size_t)b + 1]; h.zc = params[3 * (size_t)b + 2];
+  }
+  heads[b] = h;
+}
+
+extern "C" int wg_preview_gains_batch(wg_ctx *ctx, int mem, int B, const double *params, int mode,
+                                      wg_preview_gains_head *heads, double *F, long long f_stride)
+{
+  if (!ctx || B < 0 || f_stride <= 0 || (B > 0 && (!params || !heads || !F))) return WG_ERR_INVALID;
+  if (mode != WG_PREVIEW_MODE_WITHOUT_INITIALPOS && mode != WG_PREVIEW_MODE_WITH_INITIALPOS) return WG_ERR_INVALID;
+  if (B == 0) return WG_OK;
+  wg_device_guard guard(ctx->device);
+  const double *d_par = params; wg_preview_gains_head *d_heads = heads; double *d_F = F;
+  void *tmp = nullptr;
+  const size_t nb = (size_t)B, bytes_par = sizeof(double) * 3 * nb, bytes_h = sizeof(wg_preview_gains_head) * nb,
+               bytes_F = sizeof(double) * nb * (size_t)f_stride;
+  if (mem == WG_MEM_HOST) {
+    WG_CUDA(ctx, cudaMalloc(&tmp, bytes_par + bytes_h + bytes_F));
+    d_par = static_cast<double *>(tmp);
+    d_heads = reinterpret_cast<wg_preview_gains_head *>(static_cast<char *>(tmp) + bytes_par);
+    d_F = reinterpret_cast<double *>(static_cast<char *>(tmp) + bytes_par + bytes_h);
+    cudaError_t e = cudaMemcpyAsync(tmp, params, bytes_par, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_F, 0, bytes_F, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(tmp); return wg_fail(ctx, WG_ERR_CUDA, "wg_preview_gains_batch", e); }
+  } else if (mem != WG_MEM_DEVICE) return WG_ERR_INVALID;
+  preview_gains_kernel<<<(B + 63) / 64, 64, 0, ctx->stream>>>(B, d_par, mode, d_heads, d_F, f_stride);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && mem == WG_MEM_HOST) {
+    e = cudaMemcpyAsync(heads, d_heads, bytes_h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(F, d_F, bytes_F, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (tmp) cudaFree(tmp);
+  if (e != cudaSuccess) return wg_fail(ctx, WG_ERR_CUDA, "wg_preview_gains_batch", e);
   return WG_OK;
 }
 

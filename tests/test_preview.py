@@ -240,3 +240,39 @@ def test_gpu_preview_linearity_full_size(ctx):
     rows = _valid_rows(offsets, 320)[::97]
     assert np.abs(ca[rows] + cb[rows] - cs[rows])[:, [0, 3]].max() < 1e-9
     assert np.abs(fa + fb - fs)[:, :6].max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_gpu_batched_gains_match_host_solve_and_oracle(ctx):
+    """wg_preview_gains_batch (SURVEY 8f rank 4: OptimalControllerSolver::ComputeWeights for per-instance (T, preview time, zc),
+    one thread per parameter set) against the host solve of wg_preview_gains on every set, and against the oracle's Riccati
+    fixed point (an independent algorithm) on a sample: Ks, Kx and all NL window weights at 1e-9 relative.  Both modes;
+    a refused set (T <= 0) reports NL = 0 / NaN without disturbing its neighbours."""
+    import jrl_walkgen_b200 as wg
+    rng = np.random.default_rng(17)
+    B = 513
+    par = np.column_stack([rng.choice([0.005, 0.01, 0.002], B), rng.uniform(0.8, 2.0, B), rng.uniform(0.6, 1.0, B)])
+    par[0] = (0.005, 1.6, 0.814)
+    for mode in (wg.MODE_WITHOUT_INITIALPOS, wg.MODE_WITH_INITIALPOS):
+        p = par.copy()
+        p[7, 0] = -1.0
+        heads, F = ctx.preview_gains_batch(p, mode)
+        assert heads["NL"][7] == 0 and np.isnan(heads["Ks"][7])
+        worst = 0.0
+        for b in range(B):
+            if b == 7:
+                continue
+            g = wg.preview_gains(p[b, 0], p[b, 1], p[b, 2], mode)
+            assert heads["NL"][b] == g.NL
+            Fh = np.array(g.F[:g.NL])
+            e = max(abs(heads["Ks"][b] - g.Ks) / abs(g.Ks), np.abs(heads["Kx"][b] - np.array(g.Kx[:])).max() / np.abs(g.Kx[:]).max(),
+                    np.abs(F[b, :g.NL] - Fh).max() / np.abs(Fh).max())
+            worst = max(worst, e)
+            assert np.array_equal(heads["A"][b], np.array(g.A[:])) and np.array_equal(heads["C"][b], np.array(g.C[:]))
+            assert (F[b, g.NL:] == 0).all()
+        assert worst < 1e-9, worst
+        for b in (0, 1, 2, 100):
+            og = ol.OracleGains(p[b, 0], p[b, 1], p[b, 2], mode)
+            assert abs(heads["Ks"][b] - og.Ks) < 1e-8 * abs(og.Ks)
+            assert np.abs(F[b, :og.NL] - og.F).max() < 1e-8 * np.abs(og.F).max()
+        print(f"batched gains mode {mode}: max rel deviation from the host solve {worst:.2e}")
