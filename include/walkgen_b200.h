@@ -66,7 +66,8 @@ void wg_launch_count_reset(wg_ctx *ctx);
  * kernel launches to record) and wg_prof_end every kernel this library launches is bracketed by an event
  * pair; wg_prof_get returns the launch count and the summed duration of one kernel id:
  *   2 Herdt QP solve, 3 Herdt closed-loop periods, 4 PLDP solve, 5 OptCholesky, 6 preview (fused FIR + scan),
- *   7 ZMPDiscretization, 8 support polygons (FCALS / convex hull), 9 Dimitrov receding-horizon loop. */
+ *   7 ZMPDiscretization, 8 support polygons (FCALS / convex hull), 9 Dimitrov receding-horizon loop, 10 dense QP (qld),
+ *   11 Wieber2006 generator (assembly + interpolation kernels). */
 int wg_prof_begin(wg_ctx *ctx, int capacity);
 int wg_prof_end(wg_ctx *ctx);                        /* synchronises the stream and accumulates      */
 int wg_prof_get(wg_ctx *ctx, int kernel_id, long long *launches, double *total_ms);
@@ -456,6 +457,47 @@ int wg_optcholesky_add_rows_batch(wg_ctx *ctx, int mem, int B, int mode, int nb_
 /* ComputeNormalCholeskyOnANormal (A: [B][n][n] row-major, may be NULL to keep L) and, when iL != NULL,
  * ComputeInverseCholeskyNormal on the leading inv_size x inv_size block. */
 int wg_optcholesky_full_batch(wg_ctx *ctx, int mem, int B, int n, const double *A, double *L, double *iL, int inv_size);
+
+/* ------------------------------------------------------------------------------------------------
+ * General dense strictly convex QP, batched, in the ql0001_ calling convention
+ *   replaces ql0001_ / ql0002_ (src/Mathematics/qld.hh:27-31, qld.cpp:378-2090) for callers that hand it a dense problem:
+ *            ZMPQPWithConstraint (Wieber2006, n = 150, m <= 600: ZMPQPWithConstraint.cpp:1040-1046) and the QLD / QLDANDLQ
+ *            branches of ZMPConstrainedQPFastFormulation (:1297-1320)
+ *     min 1/2 x'Cx + d'x   s.t.  a_j'x + b_j = 0 (j < me),  a_j'x + b_j >= 0 (me <= j < m),  xl <= x <= xu
+ * Arrays are laid out as ql0001_ wants them: C column-major with leading dimension nmax, A column-major with leading
+ * dimension mmax (row j of QP k at A + k a_stride + j, its element i at + i mmax), multipliers u = m rows, then n lower
+ * bounds, then n upper bounds (qld.cpp:520-536).  One CTA per QP; dual active-set method in range-space form (qld.cu).
+ * ifail: 0 ok; 1 iteration limit 40 (m + n) (QLD :459); 2 C not positive definite (QLD would boost the diagonal, :809-854:
+ * this solver refuses); 3 more than n active rows; 5 bad dimensions; 10 + j: constraint j (1-based) cannot be satisfied
+ * together with the active ones (QLD's ifail > 10).  On failure x is the unconstrained minimiser.
+ * ---------------------------------------------------------------------------------------------- */
+#define WG_QLD_MAX_N 160
+#define WG_QLD_MAX_M 1024
+
+typedef struct wg_qld_batch {
+  int32_t n, nmax;            /* variables; leading dimension of C (>= n)                                        */
+  int32_t mmax;               /* leading dimension of A = rows allocated per QP (>= every m; the reference passes m + 1) */
+  int32_t shared_hessian;     /* 1: every QP has the Hessian given to wg_qld_set_shared_hessian (C ignored)      */
+  const int32_t *m;           /* [B] constraints of each QP                                                      */
+  const int32_t *me;          /* [B] equalities among them (the first me rows), or NULL (0)                      */
+  const double *C;            /* [B][nmax * n]                                                                   */
+  const double *d;            /* [B][n]                                                                          */
+  const double *A;            /* QP k at A + k * a_stride                                                        */
+  long long a_stride;         /* >= mmax * n                                                                     */
+  const double *b;            /* QP k at b + k * b_stride: [m]                                                   */
+  long long b_stride;
+  const double *xl, *xu;      /* [B][n] each, or both NULL (no bounds; the reference passes -1e8 / +1e8)          */
+  double *x;                  /* [B][n]        out                                                               */
+  double *u;                  /* [B][u_stride] out, or NULL                                                      */
+  long long u_stride;         /* >= mmax (+ 2 n when bounds are given)                                           */
+  int32_t *ifail;             /* [B]           out                                                               */
+  int32_t *iterations;        /* [B]           out (active-set changes), or NULL                                 */
+} wg_qld_batch;
+
+/* The Hessian shared by every QP of later wg_qld_solve_batch(shared_hessian = 1) calls (both reference generators have a
+ * constant C): its inverse is formed once, on the host in extended precision.  C: column-major, leading dimension nmax. */
+int wg_qld_set_shared_hessian(wg_ctx *ctx, int n, int nmax, const double *C);
+int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *batch);
 
 /* ------------------------------------------------------------------------------------------------
  * Kajita2003 front end: footsteps -> 5 ms ZMP reference and feet trajectories, batched

@@ -240,6 +240,47 @@ class Context:
                                                     F.ctypes.data, int(f_stride)))
         return heads, F
 
+    # ---- general dense QP (ql0001_ convention) ---------------------------------------------------
+    def qld_set_shared_hessian(self, Cmat):
+        Cmat = np.asfortranarray(Cmat, dtype=np.float64)
+        n = Cmat.shape[0]
+        self._check(self.lib.wg_qld_set_shared_hessian(self.h, n, n, Cmat.ctypes.data))
+
+    def qld_solve(self, d, A, b, m, C_=None, me=None, xl=None, xu=None, want_u=True):
+        """wg_qld_solve_batch on host arrays.  d [B][n]; A [B][mmax][n] (row r of QP k = A[k, r]; converted here to the
+        column-major layout of ql0001_); b [B][mmax]; m [B]; C_ [B][n][n] symmetric, or None for the shared Hessian.
+        Returns x [B][n], u [B][mmax (+ 2n)], ifail [B], iterations [B]."""
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        B, n = d.shape
+        A = np.asarray(A, dtype=np.float64)
+        mmax = A.shape[1]
+        Acm = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))          # [B][n][mmax]: element (r, i) at r + i * mmax
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        m = np.ascontiguousarray(m, dtype=np.int32)
+        q = _capi.QldBatch()
+        q.n = n; q.nmax = n; q.mmax = mmax
+        q.shared_hessian = 1 if C_ is None else 0
+        keep = [d, Acm, b, m]
+        q.m = m.ctypes.data; q.d = d.ctypes.data; q.A = Acm.ctypes.data; q.a_stride = mmax * n
+        q.b = b.ctypes.data; q.b_stride = mmax
+        if C_ is not None:
+            C_ = np.ascontiguousarray(C_, dtype=np.float64); keep.append(C_)
+            q.C = C_.ctypes.data
+        if me is not None:
+            me = np.ascontiguousarray(me, dtype=np.int32); keep.append(me)
+            q.me = me.ctypes.data
+        nb = 0
+        if xl is not None:
+            xl = np.ascontiguousarray(xl, dtype=np.float64); xu = np.ascontiguousarray(xu, dtype=np.float64)
+            keep += [xl, xu]
+            q.xl = xl.ctypes.data; q.xu = xu.ctypes.data
+            nb = 2 * n
+        x = np.zeros((B, n)); u = np.zeros((B, mmax + nb)); ifail = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
+        q.x = x.ctypes.data; q.u = u.ctypes.data if want_u else None; q.u_stride = mmax + nb
+        q.ifail = ifail.ctypes.data; q.iterations = it.ctypes.data
+        self._check(self.lib.wg_qld_solve_batch(self.h, WG_MEM_HOST, B, C.byref(q)))
+        return x, u, ifail, it
+
     def herdt_qp_solve_warm(self, inputs, guess=None, age=1, outputs=None, active=None):
         """wg_herdt_qp_solve_batch_warm on host arrays -> (outputs, optimal active sets)."""
         inputs = np.ascontiguousarray(inputs, dtype=QP_INPUT_DTYPE)

@@ -81,6 +81,15 @@ class PldpBatch(C.Structure):
                 ("max_iterations", C.c_int32), ("info", C.c_void_p)]
 
 
+class QldBatch(C.Structure):
+    """Mirror of wg_qld_batch."""
+    _fields_ = [("n", C.c_int32), ("nmax", C.c_int32), ("mmax", C.c_int32), ("shared_hessian", C.c_int32),
+                ("m", C.c_void_p), ("me", C.c_void_p), ("C", C.c_void_p), ("d", C.c_void_p), ("A", C.c_void_p),
+                ("a_stride", C.c_longlong), ("b", C.c_void_p), ("b_stride", C.c_longlong), ("xl", C.c_void_p),
+                ("xu", C.c_void_p), ("x", C.c_void_p), ("u", C.c_void_p), ("u_stride", C.c_longlong),
+                ("ifail", C.c_void_p), ("iterations", C.c_void_p)]
+
+
 class ZmpDiscParams(C.Structure):
     """Mirror of wg_zmpdisc_params."""
     _fields_ = [("sampling_period", C.c_double), ("preview_time", C.c_double), ("t_single", C.c_double),
@@ -252,6 +261,8 @@ SIGNATURES = {
                                                 C.c_void_p, C.c_longlong]),
     "wg_optcholesky_full_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int]),
+    "wg_qld_set_shared_hessian": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "wg_qld_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(QldBatch)]),
     "wg_zmpdisc_default_params": (None, [C.POINTER(ZmpDiscParams)]),
     "wg_steps_support_foot": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, C.c_double, C.c_double]),
     "wg_steps_arc": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,

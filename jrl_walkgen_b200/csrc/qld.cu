@@ -1,0 +1,655 @@
+// qld.cu - batched dense strictly convex QP in the ql0001_ calling convention, for sm_100a.
+//
+// Replaces ql0001_ / ql0002_ (src/Mathematics/qld.cpp:378-2090; Powell's ZQPCVX dual method) for the callers that hand it a
+// general dense problem: ZMPQPWithConstraint (Wieber2006: n = 150, m <= 600, ZMPQPWithConstraint.cpp:1040-1046) and the QLD
+// branches of ZMPConstrainedQPFastFormulation (:1297-1320):
+//      min 1/2 x'Cx + d'x   s.t.  a_j'x + b_j  = 0 (j < me),  a_j'x + b_j >= 0 (me <= j < m),  xl <= x <= xu.
+//
+// B200-first formulation.  One CTA owns one QP (QPs are taken from a work counter).  The method is the dual active-set method
+// of Goldfarb and Idnani in its RANGE-SPACE form, the same iteration herdt_qp.cuh runs in point space: with H^-1 at hand, the
+// only factorisation is the inverse Cholesky factor T of the active Gram matrix N'H^-1 N (grown by a row per added constraint,
+// shrunk by Givens rotations per dropped one), next to the columns Z = H^-1 N of the active normals.  A null-space /
+// orthogonal-factor implementation (QLD, QuadProg) rotates an n x n matrix on every active-set change - a chain of n - q
+// dependent Givens rotations; the range-space form replaces it by one n x n product with H^-1 (coalesced, n independent dot
+// products) and O(q^2) work on T, which is what a CTA does well, and it is cheap exactly where the reference's problems live:
+// few active rows (q << n).  H^-1 is formed once per Hessian (qld_hinv_kernel; once per BATCH when the Hessian is shared, as
+// in both reference generators, whose C is constant) and lives in L2; per-iteration HBM traffic is the m x n constraint matrix.
+// Pivoting follows QLD: the row with the largest violation normalised by its Euclidean norm (qld.cpp:1255-1331).
+#include "wg_common.h"
+#include <algorithm>
+#include <vector>
+#include <cmath>
+
+namespace {
+
+constexpr int QT = 256;              // threads per CTA
+constexpr int QW = QT / 32;
+
+struct QldState {
+  double *d_hinv_shared = nullptr;   // [n*n] inverse of the shared Hessian
+  double *d_c_shared = nullptr;      // [n*n] the shared Hessian itself (refinement step), symmetric dense
+  int shared_n = 0;
+  // per-call scratch
+  double *d_hinv = nullptr; size_t cap_hinv = 0;     // [B][n*n] per-QP inverses
+  double *d_work = nullptr; size_t cap_work = 0;     // per-CTA Z (n x qcap) and T (packed)
+  int *d_next = nullptr;
+  int *d_fail = nullptr; size_t cap_fail = 0;
+  // staging for WG_MEM_HOST
+  void *d_stage = nullptr; size_t cap_stage = 0;
+};
+
+QldState *state_of(wg_ctx *ctx)
+{
+  if (!ctx->qld) ctx->qld = new QldState();
+  return static_cast<QldState *>(ctx->qld);
+}
+
+int ensure(wg_ctx *ctx, void **p, size_t *cap, size_t bytes)
+{
+  if (*cap >= bytes) return WG_OK;
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  WG_CUDA(ctx, cudaMalloc(p, bytes));
+  *cap = bytes;
+  return WG_OK;
+}
+
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum / argmin through a small shared scratch area (QW doubles + QW ints); every thread gets the result
+__device__ double block_sum(double v, double *red)
+{
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < QW; ++w) t += red[w];
+  return t;
+}
+__device__ void block_argmin(double &v, int &idx, double *red, int *redi)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = v; redi[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  v = red[0]; idx = redi[0];
+#pragma unroll
+  for (int w = 1; w < QW; ++w)
+    if (red[w] < v || (red[w] == v && redi[w] < idx)) { v = red[w]; idx = redi[w]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// H^-1 of `count` symmetric positive definite matrices, one CTA each, in place in the n x n output block:
+// Cholesky C = L L' in the lower triangle, L^-1 (transposed) into the strict upper triangle, H^-1 = L^-T L^-1.
+// fail[b] = 1 when a pivot is not positive (QLD boosts the diagonal there, qld.cpp:809-854; this solver refuses).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(QT)
+qld_hinv_kernel(int count, int n, int nmax, const double *__restrict__ C, long long c_stride, double *__restrict__ Hinv,
+                int *__restrict__ fail)
+{
+  extern __shared__ double sm[];
+  double *dinv = sm, *hdiag = sm + n;
+  __shared__ int bad;
+  const int t = threadIdx.x;
+  for (int b = blockIdx.x; b < count; b += gridDim.x) {
+    const double *Cb = C + (size_t)b * c_stride;
+    double *W = Hinv + (size_t)b * n * n;
+    if (t == 0) bad = 0;
+    for (int e = t; e < n * n; e += QT) {
+      const int i = e / n, j = e - i * n;
+      W[e] = (j <= i) ? Cb[(size_t)j * nmax + i] : 0.0;      // lower triangle of the column-major C
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+      if (t == 0) {
+        const double p = W[j * n + j];
+        if (!(p > 0.0)) { bad = 1; W[j * n + j] = 1.0; dinv[j] = 1.0; }
+        else { const double l = sqrt(p); W[j * n + j] = l; dinv[j] = 1.0 / l; }
+      }
+      __syncthreads();
+      const double il = dinv[j];
+      for (int i = j + 1 + t; i < n; i += QT) W[i * n + j] *= il;
+      __syncthreads();
+      // trailing update of the lower triangle: W[i][k] -= W[i][j] W[k][j], j < k <= i
+      const int r = n - 1 - j;
+      for (int e = t; e < r * r; e += QT) {
+        const int ii = e / r, kk = e - ii * r;
+        if (kk <= ii) {
+          const int i = j + 1 + ii, k = j + 1 + kk;
+          W[i * n + k] -= W[i * n + j] * W[k * n + j];
+        }
+      }
+      __syncthreads();
+    }
+    // X = L^-1, column c by forward substitution, stored transposed: X[i][c] at W[c][i] (i > c), diagonal in dinv
+    for (int c = t; c < n; c += QT) {
+      for (int i = c + 1; i < n; ++i) {
+        double s = W[i * n + c] * dinv[c];
+        for (int k = c + 1; k < i; ++k) s = fma(W[i * n + k], W[c * n + k], s);
+        W[c * n + i] = -s * dinv[i];
+      }
+    }
+    __syncthreads();
+    // H^-1[a][b] = sum_{k >= a} X[k][a] X[k][b], b <= a; strict lower part over L (dead), diagonal via shared memory
+    for (int a = 0; a < n; ++a) {
+      for (int bb = t; bb <= a; bb += QT) {
+        double s = dinv[a] * ((bb == a) ? dinv[a] : W[bb * n + a]);
+        for (int k = a + 1; k < n; ++k) s = fma(W[a * n + k], W[bb * n + k], s);
+        if (bb == a) hdiag[a] = s; else W[a * n + bb] = s;
+      }
+    }
+    __syncthreads();
+    for (int e = t; e < n * n; e += QT) {
+      const int i = e / n, j = e - i * n;
+      if (j > i) W[e] = W[j * n + i]; else if (j == i) W[e] = hdiag[i];
+    }
+    if (t == 0 && fail) fail[b] = bad;
+    __syncthreads();
+  }
+}
+
+struct QldArgs {
+  int B, n, nmax, mmax, qcap;
+  const int *m, *me;
+  const double *C; long long c_stride;      // per-QP Hessians (refinement), or the shared one with stride 0
+  const double *Hinv; long long h_stride;   // 0: shared
+  const int *hfail;                         // per Hessian (index b, or 0 when shared), may be null
+  const double *d;
+  const double *A; long long a_stride;
+  const double *b; long long b_stride;
+  const double *xl, *xu;
+  double *x;
+  double *u; long long u_stride;
+  int *ifail, *iterations;
+  double *work; long long work_stride;      // per CTA
+  int *next;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// The solver.  Shared memory: x, x0, ap, zp, zd [n each]; inrm [m + 2n]; u, g, w, r [qcap each]; W, slot [qcap ints];
+// active flags [m + 2n bytes]; free-slot stack [qcap ints].
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(QT, 2)
+qld_kernel(QldArgs P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[QW];
+  __shared__ int redi[QW];
+  __shared__ int s_b;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n = P.n, qcap = P.qcap, mmax = P.mmax;
+  const bool bounds = (P.xl != nullptr) && (P.xu != nullptr);
+  const int mtot_max = mmax + (bounds ? 2 * n : 0);
+  double *x = reinterpret_cast<double *>(smem_raw);
+  double *x0 = x + n, *ap = x0 + n, *zp = ap + n, *zd = zp + n;
+  double *inrm = zd + n;
+  double *u = inrm + mtot_max, *g = u + qcap, *w = g + qcap, *r = w + qcap;
+  int *Wc = reinterpret_cast<int *>(r + qcap);
+  int *slot = Wc + qcap, *freeslot = slot + qcap;
+  signed char *sgn = reinterpret_cast<signed char *>(freeslot + qcap);   // sign of an active (equality) row
+  unsigned char *act = reinterpret_cast<unsigned char *>(sgn + qcap);
+  double *Z = P.work + (size_t)blockIdx.x * P.work_stride;                // n x qcap, column `slot` at Z + slot * n
+  double *T = Z + (size_t)n * qcap;                                       // packed lower triangle, row j at T + tri(j)
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+  for (;;) {
+    if (t == 0) s_b = atomicAdd(P.next, 1);
+    __syncthreads();
+    const int b = s_b;
+    __syncthreads();
+    if (b >= P.B) break;
+    const int m = P.m[b], me = P.me ? P.me[b] : 0;
+    const double *A = P.A + (size_t)b * P.a_stride, *bv = P.b + (size_t)b * P.b_stride;
+    const double *dv = P.d + (size_t)b * n;
+    const double *Hi = P.Hinv + (size_t)b * P.h_stride;
+    const double *Cm = P.C ? P.C + (size_t)b * P.c_stride : nullptr;
+    const double *xl = bounds ? P.xl + (size_t)b * n : nullptr, *xu = bounds ? P.xu + (size_t)b * n : nullptr;
+    int fail = 0, iters = 0, q = 0, neq = 0;
+    if (m < 0 || m > mmax || me < 0 || me > m) fail = 5;                  // QLD ifail 5: wrong dimensions
+    if (!fail && P.hfail && P.hfail[P.h_stride ? b : 0]) fail = 2;
+    const int mtot = fail ? 0 : m + (bounds ? 2 * n : 0);
+
+    // ---- unconstrained optimum x0 = -H^-1 d, row norms, flags
+    for (int i = t; i < n; i += QT) {
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s = fma(Hi[(size_t)j * n + i], dv[j], s);
+      x0[i] = -s; x[i] = -s;
+    }
+    for (int rr = t; rr < mtot; rr += QT) {
+      double s = 1.0;
+      if (rr < m) {
+        s = 0.0;
+        for (int j = 0; j < n; ++j) { const double a = A[rr + (size_t)j * mmax]; s = fma(a, a, s); }
+      }
+      inrm[rr] = s > 0.0 ? rsqrt(s) : 0.0;
+      act[rr] = 0;
+    }
+    for (int k = t; k < qcap; k += QT) freeslot[k] = qcap - 1 - k;
+    __syncthreads();
+    int nfree = qcap;
+    const int maxit = 40 * (mtot + n);
+    bool done = fail != 0;
+
+    while (!done) {
+      // ---- the row to add: equalities first, in order; then the most violated inequality (normalised)
+      int p; double sp; int sign = 1;
+      double xn2 = 0.0;
+      for (int i = t; i < n; i += QT) xn2 = fma(x[i], x[i], xn2);
+      const double xnorm = sqrt(block_sum(xn2, red));
+      if (neq < me) {
+        p = neq;
+        double s = 0.0;
+        for (int j = t; j < n; j += QT) s = fma(A[p + (size_t)j * mmax], x[j], s);
+        sp = block_sum(s, red) + bv[p];
+        if (sp > 0.0) { sign = -1; sp = -sp; }
+      } else {
+        double best = INF; int bi = 0x7fffffff;
+        for (int rr = t; rr < mtot; rr += QT) {
+          if (act[rr] || rr < me) continue;          // equalities are all taken above
+          double s, scale;
+          if (rr < m) {
+            s = 0.0;
+            for (int j = 0; j < n; ++j) s = fma(A[rr + (size_t)j * mmax], x[j], s);
+            const double bb = bv[rr];
+            s += bb;
+            scale = fabs(bb) * inrm[rr] + xnorm;
+          } else if (rr < m + n) {
+            const int i = rr - m;
+            s = x[i] - xl[i]; scale = fabs(xl[i]) + xnorm;
+          } else {
+            const int i = rr - m - n;
+            s = xu[i] - x[i]; scale = fabs(xu[i]) + xnorm;
+          }
+          const double sv = s * inrm[rr];
+          // converged rows: violation below 1e-11 of the row's own scale (distance units)
+          if (sv < -1e-11 * (scale + 1e-300) && sv < best) { best = sv; bi = rr; }
+        }
+        block_argmin(best, bi, red, redi);
+        if (bi == 0x7fffffff) break;             // no violated row left: optimal
+        p = bi;
+        sp = best / inrm[p];
+      }
+      // a_p into shared memory (bounds: +- unit vector)
+      for (int j = t; j < n; j += QT) {
+        double a;
+        if (p < m) a = sign * A[p + (size_t)j * mmax];
+        else if (p < m + n) a = (j == p - m) ? 1.0 : 0.0;
+        else a = (j == p - m - n) ? -1.0 : 0.0;
+        ap[j] = a;
+      }
+      __syncthreads();
+      // z_p = H^-1 a_p
+      double mpp = 0.0;
+      for (int i = t; i < n; i += QT) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = fma(Hi[(size_t)j * n + i], ap[j], s);
+        zp[i] = s;
+        mpp = fma(s, ap[i], mpp);
+      }
+      const double Mpp = block_sum(mpp, red);
+      double up = 0.0;
+      bool added = false;
+      while (!added && !done) {
+        if (++iters > maxit) { fail = 1; done = true; break; }
+        // g_k = z_k' a_p (warp per active row)
+        for (int k = warp; k < q; k += QW) {
+          const double *zk = Z + (size_t)slot[k] * n;
+          double s = 0.0;
+          for (int j = lane; j < n; j += 32) s = fma(zk[j], ap[j], s);
+          s = warp_sum(s);
+          if (lane == 0) g[k] = s;
+        }
+        __syncthreads();
+        double wsq = 0.0;
+        for (int j = t; j < q; j += QT) {
+          const double *Tr = T + tri(j);
+          double s = 0.0;
+          for (int e = 0; e <= j; ++e) s = fma(Tr[e], g[e], s);
+          w[j] = s;
+          wsq = fma(s, s, wsq);
+        }
+        const double delta = Mpp - block_sum(wsq, red);    // (block_sum synchronises: w is visible)
+        double t1 = INF; int l = 0x7fffffff;
+        for (int j = t; j < q; j += QT) {
+          double s = 0.0;
+          for (int rr = j; rr < q; ++rr) s = fma(T[tri(rr) + j], w[rr], s);
+          r[j] = s;
+          if (s > 0.0 && j >= neq) {                        // equality rows are never dropped
+            const double tj = u[j] / s;
+            if (tj < t1) { t1 = tj; l = j; }
+          }
+        }
+        block_argmin(t1, l, red, redi);
+        const bool dependent = !(delta > 1e-12 * Mpp);
+        const double t2 = dependent ? INF : -sp / delta;
+        const double tt = fmin(t1, t2);
+        if (!(tt < INF)) {
+          // the row is a combination of the active rows and cannot be satisfied
+          if (neq < me && fabs(sp) * inrm[p] <= 1e-9 * (fabs(bv[p]) * inrm[p] + xnorm + 1e-300)) { act[p] = 0; ++neq; added = true; break; }   // redundant equality
+          fail = 10 + p + 1; done = true; break;            // QLD: ifail > 10, constraint ifail - 10 inconsistent
+        }
+        if (!dependent || tt == t2) {
+          // primal direction z_p - Z r, step
+          for (int i = t; i < n; i += QT) {
+            double s = zp[i];
+            for (int k = 0; k < q; ++k) s = fma(-r[k], Z[(size_t)slot[k] * n + i], s);
+            x[i] = fma(tt, s, x[i]);
+          }
+          sp += tt * delta;
+        }
+        for (int j = t; j < q; j += QT) u[j] = fma(-tt, r[j], u[j]);
+        up += tt;
+        __syncthreads();
+        if (t2 <= t1) {
+          // full step: row p becomes active
+          if (q >= qcap || nfree <= 0) { fail = 3; done = true; break; }
+          const double idd = rsqrt(delta);
+          for (int j = t; j < q; j += QT) T[tri(q) + j] = -r[j] * idd;
+          const int sl = freeslot[nfree - 1];
+          for (int i = t; i < n; i += QT) Z[(size_t)sl * n + i] = zp[i];
+          if (t == 0) { T[tri(q) + q] = idd; Wc[q] = p; slot[q] = sl; u[q] = up; sgn[q] = (signed char)sign; act[p] = 1; }
+          --nfree; ++q;
+          if (neq < me) ++neq;
+          added = true;
+          __syncthreads();
+          break;
+        }
+        // partial step: multiplier l reached zero -> drop row l (warp 0 rotates T; see herdt_qp.cuh drop_row)
+        if (warp == 0) {
+          for (int j = lane; j < q; j += 32) w[j] = (j <= l) ? T[tri(l) + j] : 0.0;
+          __syncwarp();
+          for (int rr = l + 1; rr < q; ++rr) {
+            const double *Tr = T + tri(rr);
+            const double p1 = w[l], p2 = Tr[l];
+            const double ih = rsqrt(p1 * p1 + p2 * p2);
+            const double c_ = p1 * ih, s_ = p2 * ih;
+            __syncwarp();
+            double *Tn = T + tri(rr - 1);
+            for (int j = lane; j <= rr; j += 32) {
+              const double x1 = w[j], x2 = Tr[j];
+              w[j] = c_ * x1 + s_ * x2;
+              const double nr = c_ * x2 - s_ * x1;
+              if (j < l) Tn[j] = nr;
+              else if (j > l) Tn[j - 1] = nr;
+            }
+            __syncwarp();
+          }
+          if (lane == 0) { act[Wc[l]] = 0; freeslot[nfree] = slot[l]; }
+          __syncwarp();
+          for (int base = l; base < q - 1; base += 32) {
+            const int j = base + lane;
+            const bool mv = j < q - 1;
+            const int Wn = mv ? Wc[j + 1] : 0, sn = mv ? slot[j + 1] : 0;
+            const double un = mv ? u[j + 1] : 0.0;
+            const signed char gn = mv ? sgn[j + 1] : (signed char)1;
+            __syncwarp();
+            if (mv) { Wc[j] = Wn; slot[j] = sn; u[j] = un; sgn[j] = gn; }
+            __syncwarp();
+          }
+        }
+        ++nfree; --q;
+        __syncthreads();
+        if (dependent) continue;   // sp unchanged by a pure dual step
+        // recompute the violation of p on the moved point
+        double s = 0.0;
+        for (int j = t; j < n; j += QT) s = fma(ap[j], x[j], s);
+        s = block_sum(s, red);
+        if (p < m) sp = s + sign * bv[p];
+        else if (p < m + n) sp = s - xl[p - m];
+        else sp = s + xu[p - m - n];
+      }
+    }
+
+    // ---- x from the multipliers (x = x0 + sum_k u_k z_k), then one refinement step on the stationarity residual
+    if (!fail) {
+      for (int i = t; i < n; i += QT) {
+        double s = x0[i];
+        for (int k = 0; k < q; ++k) s = fma(u[k], Z[(size_t)slot[k] * n + i], s);
+        x[i] = s;
+      }
+      __syncthreads();
+      if (Cm) {
+        // res = C x + d - sum_k u_k a_k ; x -= H^-1 res
+        for (int i = t; i < n; i += QT) {
+          double s = dv[i];
+          for (int j = 0; j < n; ++j) s = fma(Cm[(size_t)j * P.nmax + i], x[j], s);
+          for (int k = 0; k < q; ++k) {
+            const int pk = Wc[k];
+            double a;
+            if (pk < m) a = sgn[k] * A[pk + (size_t)i * mmax];
+            else if (pk < m + n) a = (i == pk - m) ? 1.0 : 0.0;
+            else a = (i == pk - m - n) ? -1.0 : 0.0;
+            s = fma(-u[k], a, s);
+          }
+          zd[i] = s;
+        }
+        __syncthreads();
+        for (int i = t; i < n; i += QT) {
+          double s = 0.0;
+          for (int j = 0; j < n; ++j) s = fma(Hi[(size_t)j * n + i], zd[j], s);
+          x[i] -= s;
+        }
+        __syncthreads();
+      }
+    }
+    // ---- results: x, multipliers in QLD's layout (m rows, n lower bounds, n upper bounds; qld.cpp:520-536)
+    for (int i = t; i < n; i += QT) P.x[(size_t)b * n + i] = fail ? x0[i] : x[i];
+    if (P.u) {
+      double *uo = P.u + (size_t)b * P.u_stride;
+      const int mu = max(m, 0) + 2 * n;
+      for (int k = t; k < mu && k < P.u_stride; k += QT) uo[k] = 0.0;
+      __syncthreads();
+      if (!fail)
+        for (int k = t; k < q; k += QT) {
+          const int pk = Wc[k];
+          const int dst = pk < m ? pk : (bounds ? pk : -1);
+          if (dst >= 0 && dst < P.u_stride) uo[dst] = sgn[k] * u[k];
+        }
+    }
+    if (t == 0) {
+      P.ifail[b] = fail;
+      if (P.iterations) P.iterations[b] = iters;
+    }
+    __syncthreads();
+  }
+}
+
+size_t qld_smem_bytes(int n, int mmax, int qcap, bool bounds)
+{
+  const size_t mtot = (size_t)mmax + (bounds ? 2 * (size_t)n : 0);
+  size_t s = sizeof(double) * (5 * (size_t)n + mtot + 4 * (size_t)qcap) + sizeof(int) * 3 * (size_t)qcap + qcap + mtot;
+  return (s + 15) & ~(size_t)15;
+}
+
+int hinv_launch(wg_ctx *ctx, int count, int n, int nmax, const double *d_C, long long c_stride, double *d_hinv, int *d_fail)
+{
+  const int blocks = std::max(1, std::min(count, ctx->sm_count * 2));
+  qld_hinv_kernel<<<blocks, QT, sizeof(double) * 2 * n, ctx->stream>>>(count, n, nmax, d_C, c_stride, d_hinv, d_fail);
+  WG_LAUNCHED(ctx);
+  return WG_OK;
+}
+
+}  // namespace
+
+void wg_qld_release(wg_ctx *ctx)
+{
+  if (!ctx->qld) return;
+  QldState *st = static_cast<QldState *>(ctx->qld);
+  cudaFree(st->d_hinv_shared); cudaFree(st->d_c_shared); cudaFree(st->d_hinv); cudaFree(st->d_work); cudaFree(st->d_next);
+  cudaFree(st->d_fail); cudaFree(st->d_stage);
+  delete st;
+  ctx->qld = nullptr;
+}
+
+extern "C" {
+
+int wg_qld_set_shared_hessian(wg_ctx *ctx, int n, int nmax, const double *C)
+{
+  if (!ctx || n <= 0 || n > WG_QLD_MAX_N || nmax < n || !C) return WG_ERR_INVALID;
+  wg_device_guard guard(ctx->device);
+  QldState *st = state_of(ctx);
+  // the inverse in extended precision on the host: once per Hessian, and the generators' Hessians (sums of products of
+  // integrator matrices over 75 samples) are badly conditioned
+  typedef long double LD;
+  std::vector<LD> L((size_t)n * n, 0), X((size_t)n * n, 0);
+  for (int j = 0; j < n; ++j) {
+    LD p = C[(size_t)j * nmax + j];
+    for (int k = 0; k < j; ++k) p -= L[(size_t)j * n + k] * L[(size_t)j * n + k];
+    if (!(p > 0)) return wg_fail(ctx, WG_ERR_INVALID, "wg_qld_set_shared_hessian: C is not positive definite");
+    const LD l = sqrtl(p);
+    L[(size_t)j * n + j] = l;
+    for (int i = j + 1; i < n; ++i) {
+      LD v = C[(size_t)j * nmax + i];
+      for (int k = 0; k < j; ++k) v -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
+      L[(size_t)i * n + j] = v / l;
+    }
+  }
+  for (int c = 0; c < n; ++c) {          // X = L^-1
+    X[(size_t)c * n + c] = 1 / L[(size_t)c * n + c];
+    for (int i = c + 1; i < n; ++i) {
+      LD s = 0;
+      for (int k = c; k < i; ++k) s += L[(size_t)i * n + k] * X[(size_t)k * n + c];
+      X[(size_t)i * n + c] = -s / L[(size_t)i * n + i];
+    }
+  }
+  std::vector<double> H((size_t)n * n), Cs((size_t)n * n);
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b <= a; ++b) {
+      LD s = 0;
+      for (int k = a; k < n; ++k) s += X[(size_t)k * n + a] * X[(size_t)k * n + b];
+      H[(size_t)a * n + b] = H[(size_t)b * n + a] = (double)s;
+      Cs[(size_t)a * n + b] = Cs[(size_t)b * n + a] = C[(size_t)b * nmax + a];
+    }
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (st->shared_n != n) {
+    cudaFree(st->d_hinv_shared); cudaFree(st->d_c_shared);
+    st->d_hinv_shared = st->d_c_shared = nullptr; st->shared_n = 0;
+    WG_CUDA(ctx, cudaMalloc(&st->d_hinv_shared, sizeof(double) * n * n));
+    WG_CUDA(ctx, cudaMalloc(&st->d_c_shared, sizeof(double) * n * n));
+    st->shared_n = n;
+  }
+  WG_CUDA(ctx, cudaMemcpy(st->d_hinv_shared, H.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+  WG_CUDA(ctx, cudaMemcpy(st->d_c_shared, Cs.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+  return WG_OK;
+}
+
+int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q)
+{
+  if (!ctx || !q || B < 0) return WG_ERR_INVALID;
+  if (B == 0) return WG_OK;
+  const int n = q->n, nmax = q->nmax, mmax = q->mmax;
+  if (n <= 0 || n > WG_QLD_MAX_N || mmax < 0 || mmax > WG_QLD_MAX_M || !q->m || !q->d || !q->x || !q->ifail ||
+      (mmax > 0 && (!q->A || !q->b)) || (!q->shared_hessian && (!q->C || nmax < n)) || ((q->xl == nullptr) != (q->xu == nullptr)))
+    return WG_ERR_INVALID;
+  if (q->a_stride < (long long)mmax * n || q->b_stride < mmax || (q->u && q->u_stride < mmax)) return WG_ERR_INVALID;
+  wg_device_guard guard(ctx->device);
+  QldState *st = state_of(ctx);
+  if (q->shared_hessian && (st->shared_n != n || !st->d_hinv_shared))
+    return wg_fail(ctx, WG_ERR_NOT_READY, "wg_qld_set_shared_hessian not called for this n");
+  const bool bounds = q->xl != nullptr;
+  const size_t nb = (size_t)B;
+  int rc;
+  wg_qld_batch d = *q;       // device view of the batch
+  std::vector<std::pair<void *, std::pair<const void *, size_t>>> downloads;
+  if (mem == WG_MEM_HOST) {
+    // one staging block: every array of the batch, uploaded; results downloaded after the launch
+    const size_t szC = q->shared_hessian ? 0 : sizeof(double) * nb * nmax * n;
+    const size_t sz_m = sizeof(int) * nb, sz_d = sizeof(double) * nb * n, szA = sizeof(double) * nb * q->a_stride,
+                 szb = sizeof(double) * nb * q->b_stride, szu = q->u ? sizeof(double) * nb * q->u_stride : 0;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    const size_t o_m = off; off += al(sz_m);
+    const size_t o_me = off; off += q->me ? al(sz_m) : 0;
+    const size_t o_C = off; off += al(szC);
+    const size_t o_d = off; off += al(sz_d);
+    const size_t o_A = off; off += al(szA);
+    const size_t o_b = off; off += al(szb);
+    const size_t o_xl = off; off += bounds ? al(sz_d) : 0;
+    const size_t o_xu = off; off += bounds ? al(sz_d) : 0;
+    const size_t o_x = off; off += al(sz_d);
+    const size_t o_u = off; off += al(szu);
+    const size_t o_f = off; off += al(sz_m);
+    const size_t o_it = off; off += al(sz_m);
+    if ((rc = ensure(ctx, &st->d_stage, &st->cap_stage, off)) != WG_OK) return rc;
+    char *base = static_cast<char *>(st->d_stage);
+    auto up = [&](size_t o, const void *src, size_t bytes) -> cudaError_t {
+      return bytes ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+    };
+    WG_CUDA(ctx, up(o_m, q->m, sz_m));
+    if (q->me) WG_CUDA(ctx, up(o_me, q->me, sz_m));
+    WG_CUDA(ctx, up(o_C, q->C, szC));
+    WG_CUDA(ctx, up(o_d, q->d, sz_d));
+    WG_CUDA(ctx, up(o_A, q->A, szA));
+    WG_CUDA(ctx, up(o_b, q->b, szb));
+    if (bounds) { WG_CUDA(ctx, up(o_xl, q->xl, sz_d)); WG_CUDA(ctx, up(o_xu, q->xu, sz_d)); }
+    d.m = reinterpret_cast<const int *>(base + o_m);
+    d.me = q->me ? reinterpret_cast<const int *>(base + o_me) : nullptr;
+    d.C = szC ? reinterpret_cast<const double *>(base + o_C) : nullptr;
+    d.d = reinterpret_cast<const double *>(base + o_d);
+    d.A = reinterpret_cast<const double *>(base + o_A);
+    d.b = reinterpret_cast<const double *>(base + o_b);
+    d.xl = bounds ? reinterpret_cast<const double *>(base + o_xl) : nullptr;
+    d.xu = bounds ? reinterpret_cast<const double *>(base + o_xu) : nullptr;
+    d.x = reinterpret_cast<double *>(base + o_x);
+    d.u = q->u ? reinterpret_cast<double *>(base + o_u) : nullptr;
+    d.ifail = reinterpret_cast<int *>(base + o_f);
+    d.iterations = q->iterations ? reinterpret_cast<int *>(base + o_it) : nullptr;
+    downloads.push_back({q->x, {d.x, sz_d}});
+    if (q->u) downloads.push_back({q->u, {d.u, szu}});
+    downloads.push_back({q->ifail, {d.ifail, sz_m}});
+    if (q->iterations) downloads.push_back({q->iterations, {d.iterations, sz_m}});
+  } else if (mem != WG_MEM_DEVICE) return WG_ERR_INVALID;
+
+  QldArgs a;
+  a.B = B; a.n = n; a.nmax = q->shared_hessian ? n : nmax; a.mmax = mmax;
+  a.qcap = std::min(n + (bounds ? 0 : 0), WG_QLD_MAX_N);
+  a.m = d.m; a.me = d.me;
+  a.d = d.d; a.A = d.A; a.a_stride = q->a_stride; a.b = d.b; a.b_stride = q->b_stride;
+  a.xl = d.xl; a.xu = d.xu; a.x = d.x; a.u = d.u; a.u_stride = q->u_stride; a.ifail = d.ifail; a.iterations = d.iterations;
+  if (q->shared_hessian) {
+    a.Hinv = st->d_hinv_shared; a.h_stride = 0; a.hfail = nullptr;
+    a.C = st->d_c_shared; a.c_stride = 0;
+  } else {
+    if ((rc = ensure(ctx, reinterpret_cast<void **>(&st->d_hinv), &st->cap_hinv, sizeof(double) * nb * n * n)) != WG_OK) return rc;
+    if ((rc = ensure(ctx, reinterpret_cast<void **>(&st->d_fail), &st->cap_fail, sizeof(int) * nb)) != WG_OK) return rc;
+    if ((rc = hinv_launch(ctx, B, n, nmax, d.C, (long long)nmax * n, st->d_hinv, st->d_fail)) != WG_OK) return rc;
+    a.Hinv = st->d_hinv; a.h_stride = (long long)n * n; a.hfail = st->d_fail;
+    a.C = d.C; a.c_stride = (long long)nmax * n;
+  }
+  const size_t smem = qld_smem_bytes(n, mmax, a.qcap, bounds);
+  if (smem > 200 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "wg_qld_solve_batch: problem too large for shared memory");
+  WG_SMEM_ATTR(ctx, WG_ATTR_DENSEQP, qld_kernel, smem);
+  int per_sm = (int)std::min<size_t>(2, (220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  const int blocks = std::max(1, std::min(B, ctx->sm_count * per_sm));
+  a.work_stride = (long long)n * a.qcap + (long long)a.qcap * (a.qcap + 1) / 2;
+  if ((rc = ensure(ctx, reinterpret_cast<void **>(&st->d_work), &st->cap_work, sizeof(double) * (size_t)blocks * a.work_stride)) != WG_OK) return rc;
+  a.work = st->d_work;
+  if (!st->d_next) WG_CUDA(ctx, cudaMalloc(&st->d_next, sizeof(int)));
+  a.next = st->d_next;
+  WG_CUDA(ctx, cudaMemsetAsync(st->d_next, 0, sizeof(int), ctx->stream));
+  wg_prof_start(ctx, WG_K_QLD);
+  qld_kernel<<<blocks, QT, smem, ctx->stream>>>(a);
+  wg_prof_stop(ctx);
+  WG_LAUNCHED(ctx);
+  for (auto &dl : downloads)
+    WG_CUDA(ctx, cudaMemcpyAsync(dl.first, dl.second.first, dl.second.second, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mem == WG_MEM_HOST) WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return WG_OK;
+}
+
+}  // extern "C"

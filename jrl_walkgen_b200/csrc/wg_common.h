@@ -14,7 +14,8 @@ struct wg_preview_consts;  // preview.cu
 // Kernel ids of the per-kernel CUDA-event profiler (wg_prof_*): bench.py reads the average launch
 // duration of each kernel over the timed region from these.
 enum { WG_K_PREVIEW_FIR = 0, WG_K_PREVIEW_RECUR = 1, WG_K_HERDT_QP = 2, WG_K_HERDT_MPC = 3, WG_K_PLDP = 4,
-       WG_K_OPTCHOL = 5, WG_K_PREVIEW_FUSED = 6, WG_K_ZMPDISC = 7, WG_K_FCALS = 8, WG_K_DIMITROV = 9, WG_K_COUNT = 10 };
+       WG_K_OPTCHOL = 5, WG_K_PREVIEW_FUSED = 6, WG_K_ZMPDISC = 7, WG_K_FCALS = 8, WG_K_DIMITROV = 9, WG_K_QLD = 10, WG_K_WIEBER = 11,
+       WG_K_COUNT = 12 };
 
 struct wg_prof_state {
   bool on = false;
@@ -48,6 +49,9 @@ struct wg_ctx {
   void *pldp = nullptr;
   // Dimitrov front-to-back pipeline (dimitrov.cu)
   void *dimitrov = nullptr;
+  // dense QP solver (qld.cu) and the Wieber2006 generator on top of it (wieber.cu)
+  void *qld = nullptr;
+  void *wieber = nullptr;
 };
 
 inline int wg_fail(wg_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)

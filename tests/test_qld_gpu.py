@@ -1,0 +1,190 @@
+"""General dense QP (wg_qld_solve_batch, the ql0001_ calling convention) against the reference's OWN ql0001_ object code
+(oracle/_ref: src/Mathematics/qld.cpp compiled where it lies) on identical inputs.
+
+Criteria (north_star): identical optimal active sets, solution within 1e-6 (relative to its scale), KKT residuals <= 1e-9.
+Problem families: random strictly convex QPs of the sizes the reference's callers use (Herdt n = 36 / m = 75, Wieber
+n = 150 / m = 300 ... 450), with equalities, with finite bounds, per-QP and shared Hessians, infeasible rows, ragged m."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+D = ol.D
+IP = C.POINTER(C.c_int)
+
+
+def ref_qld(Cm, d, A, b, me=0, xl=None, xu=None):
+    """One call of the reference's ql0001_ (dummy row / mmax = m + 1 as QPProblem::solve and ZMPQPWithConstraint pass it)."""
+    r = ol.ref()
+    n = len(d); m = len(b)
+    mmax = m + 1
+    a = np.zeros((n, mmax)); a[:, :m] = A.T                      # column-major, leading dimension mmax
+    bb = np.zeros(mmax); bb[:m] = b
+    c = np.asfortranarray(Cm).copy(order="F")
+    xl = np.full(n, -1e8) if xl is None else np.array(xl, dtype=np.float64)
+    xu = np.full(n, 1e8) if xu is None else np.array(xu, dtype=np.float64)
+    mnn = m + 2 * n
+    x = np.zeros(n); u = np.zeros(mnn)
+    lwar = 3 * n * n // 2 + 10 * n + 2 * mmax + 20000
+    war = np.zeros(lwar); iwar = np.zeros(n + 10, dtype=np.int32); iwar[0] = 1
+    ci = lambda v: C.byref(C.c_int(v))
+    ifail = C.c_int(0)
+    eps = C.c_double(1e-8)
+    dd = np.array(d, dtype=np.float64)
+    r.ref_ql0001(ci(m), ci(me), ci(mmax), ci(n), ci(n), ci(mnn), ol.dptr(c), ol.dptr(dd), ol.dptr(a), ol.dptr(bb), ol.dptr(xl),
+                 ol.dptr(xu), ol.dptr(x), ol.dptr(u), ci(0), C.byref(ifail), ci(0), ol.dptr(war), ci(lwar),
+                 iwar.ctypes.data_as(IP), ci(len(iwar)), C.byref(eps))
+    return x, u, ifail.value
+
+
+def random_qp(rng, n, m, cond=1e3, active_frac=0.3):
+    """Strictly convex QP with a known interior-ish structure: rows are random half-spaces, a fraction of them cutting off
+    the unconstrained minimiser."""
+    Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    ev = np.exp(rng.uniform(0, np.log(cond), n))
+    Cm = (Q * ev) @ Q.T
+    Cm = 0.5 * (Cm + Cm.T)
+    d = rng.normal(size=n) * np.sqrt(ev.mean())
+    x0 = -np.linalg.solve(Cm, d)
+    A = rng.normal(size=(m, n))
+    # A x + b >= 0 feasible at the point xf, violated at x0 for some rows
+    xf = x0 + rng.normal(size=n) * 0.5
+    slack = rng.uniform(0.05, 1.0, m)
+    b = -A @ xf + slack
+    cut = rng.random(m) < active_frac
+    b[cut] = -A[cut] @ (0.5 * (x0 + xf)) - 0 * slack[cut] + (A[cut] @ (xf - x0)).clip(min=0) * 0.0
+    # make sure xf stays feasible for the cutting rows
+    viol = A @ xf + b
+    b[viol < 0.01] += (0.01 - viol[viol < 0.01])
+    return Cm, d, A, b
+
+
+def kkt(Cm, d, A, b, x, u_rows, xl=None, xu=None, u_lo=None, u_up=None, me=0):
+    grad = Cm @ x + d - A.T @ u_rows
+    if u_lo is not None:
+        grad = grad - u_lo + u_up
+    s = A @ x + b
+    scale = max(1.0, np.abs(d).max())
+    stat = np.abs(grad).max() / scale
+    rown = np.maximum(np.linalg.norm(A, axis=1), 1e-30)
+    feas = min((s[me:] / rown[me:]).min() if len(s) > me else 0.0, 0.0)
+    if xl is not None:
+        feas = min(feas, (x - xl).min(), (xu - x).min())
+        comp_b = max(np.abs(u_lo * (x - xl)).max(), np.abs(u_up * (xu - x)).max()) / scale
+    else:
+        comp_b = 0.0
+    eq = np.abs(s[:me] / rown[:me]).max() if me else 0.0
+    comp = max(np.abs(u_rows[me:] * s[me:]).max() / scale if len(s) > me else 0.0, comp_b)
+    return stat, feas, eq, comp
+
+
+def compare(ctx_out, k, Cm, d, A, b, me=0, xl=None, xu=None, xtol=1e-6):
+    x, u, ifail, it = ctx_out
+    m, n = A.shape
+    xr, ur, fr = ref_qld(Cm, d, A, b, me, xl, xu)
+    assert fr == 0 and ifail[k] == 0, (k, fr, ifail[k])
+    sc = max(1.0, np.abs(xr).max())
+    ex = np.abs(x[k] - xr).max() / sc
+    assert ex < xtol, (k, ex)
+    big = max(np.abs(ur[:m]).max(initial=0.0), 1e-12)
+    act_g = set(np.nonzero(np.abs(u[k, :m]) > 1e-7 * big)[0]); act_r = set(np.nonzero(np.abs(ur[:m]) > 1e-7 * big)[0])
+    assert act_g == act_r, (k, sorted(act_g ^ act_r))
+    assert (u[k, me:m] >= -1e-12 * big).all()
+    has_b = xl is not None
+    stat, feas, eq, comp = kkt(Cm, d, A, b, x[k], u[k, :m], xl, xu, u[k, m:m + n] if has_b else None,
+                               u[k, m + n:m + 2 * n] if has_b else None, me)
+    assert stat < 1e-9 and feas > -1e-9 and eq < 1e-9 and comp < 1e-9, (k, stat, feas, eq, comp)
+    return ex, max(stat, -feas, eq, comp)
+
+
+pytestmark = pytest.mark.skipif(ol.ref() is None, reason="oracle/_ref/libwalkgen_ref.so (reference ql0001_) not built")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,count", [(36, 75, 24), (150, 300, 6), (150, 450, 4), (8, 5, 16), (64, 0, 3)])
+def test_gpu_dense_qp_matches_reference_ql0001(ctx, n, m, count):
+    rng = np.random.default_rng(100 + n + m)
+    probs = [random_qp(rng, n, m) for _ in range(count)] if m else \
+        [(lambda Cm, d, A, b: (Cm, d, np.zeros((0, n)), np.zeros(0)))(*random_qp(rng, n, 3)) for _ in range(count)]
+    mmax = m + 1
+    Cs = np.stack([p[0] for p in probs]); ds = np.stack([p[1] for p in probs])
+    As = np.zeros((count, mmax, n)); bs = np.zeros((count, mmax))
+    for k, p in enumerate(probs):
+        As[k, :m] = p[2]; bs[k, :m] = p[3]
+    out = ctx.qld_solve(ds, As, bs, np.full(count, m), C_=Cs)
+    worst = (0.0, 0.0)
+    for k, p in enumerate(probs):
+        e = compare(out, k, *p)
+        worst = (max(worst[0], e[0]), max(worst[1], e[1]))
+    print(f"n={n} m={m}: max rel |x - x_ql0001| {worst[0]:.2e}, KKT {worst[1]:.2e}, iterations mean {out[3].mean():.1f} max {out[3].max()}")
+
+
+@pytest.mark.gpu
+def test_gpu_dense_qp_equalities_bounds_shared_hessian_and_ragged_m(ctx):
+    rng = np.random.default_rng(7)
+    n, mmax = 40, 61
+    Cm, _, _, _ = random_qp(rng, n, 4)
+    ctx.qld_set_shared_hessian(Cm)
+    probs = []
+    for k in range(20):
+        m = int(rng.integers(10, 61))
+        me = int(rng.integers(0, 4))
+        _, d, A, b = random_qp(rng, n, m)
+        x0 = -np.linalg.solve(Cm, d)
+        xf = x0 + rng.normal(size=n) * 0.3
+        b = -A @ xf + rng.uniform(0.05, 0.5, m)
+        b[:me] = -A[:me] @ xf                                       # equalities hold at xf
+        tight = rng.random(m) < 0.3
+        tight[:me] = False
+        b[tight] = -A[tight] @ (0.6 * xf + 0.4 * x0) + np.maximum(A[tight] @ (0.6 * xf + 0.4 * x0) - A[tight] @ xf, 0) * 0 
+        viol = A[me:] @ xf + b[me:]
+        b[me:][viol < 0.01] += 0.01 - viol[viol < 0.01]
+        xl = xf - rng.uniform(0.2, 2.0, n); xu = xf + rng.uniform(0.2, 2.0, n)
+        probs.append((d, A, b, me, xl, xu))
+    B = len(probs)
+    ds = np.stack([p[0] for p in probs])
+    As = np.zeros((B, mmax, n)); bs = np.zeros((B, mmax))
+    for k, p in enumerate(probs):
+        As[k, :len(p[2])] = p[1]; bs[k, :len(p[2])] = p[2]
+    ms = np.array([len(p[2]) for p in probs]); mes = np.array([p[3] for p in probs])
+    xl = np.stack([p[4] for p in probs]); xu = np.stack([p[5] for p in probs])
+    out = ctx.qld_solve(ds, As, bs, ms, me=mes, xl=xl, xu=xu)
+    x, u, ifail, it = out
+    worst = 0.0
+    nb_active = 0
+    for k, (d, A, b, me, l, h) in enumerate(probs):
+        m = len(b)
+        xr, ur, fr = ref_qld(Cm, d, A, b, me, l, h)
+        assert fr == 0 and ifail[k] == 0, (k, fr, ifail[k])
+        assert np.abs(x[k] - xr).max() < 1e-6 * max(1.0, np.abs(xr).max()), k
+        worst = max(worst, np.abs(x[k] - xr).max())
+        big = max(np.abs(ur).max(), 1e-12)
+        # rows, lower bounds, upper bounds: same active sets; QLD's layout u = [m rows | n lower | n upper]
+        ug = u[k, :m + 2 * n]
+        assert set(np.nonzero(np.abs(ug) > 1e-7 * big)[0]) == set(np.nonzero(np.abs(ur) > 1e-7 * big)[0]), k
+        nb_active += int((np.abs(u[k, m:m + 2 * n]) > 1e-7 * big).sum())
+        stat, feas, eq, comp = kkt(Cm, d, A, b, x[k], u[k, :m], l, h, u[k, m:m + n], u[k, m + n:m + 2 * n], me)
+        assert stat < 1e-9 and feas > -1e-9 and eq < 1e-9 and comp < 1e-9, (k, stat, feas, eq, comp)
+        assert (x[k] >= l - 1e-9).all() and (x[k] <= h + 1e-9).all()
+    assert nb_active > 0                                              # bounds were exercised
+    print(f"equalities + bounds + shared Hessian: max |x - x_ql0001| {worst:.2e}, active bounds {nb_active}")
+
+
+@pytest.mark.gpu
+def test_gpu_dense_qp_failure_codes(ctx):
+    """Inconsistent constraints report ifail > 10 like QLD; an indefinite Hessian is refused with 2; a bad m with 5."""
+    rng = np.random.default_rng(3)
+    n = 6
+    Cm = np.eye(n)
+    A = np.zeros((3, 4, n)); b = np.zeros((3, 4))
+    A[:, 0, 0] = 1.0; b[:, 0] = -1.0          # x0 >= 1
+    A[:, 1, 0] = -1.0; b[:, 1] = -1.0         # x0 <= -1: inconsistent with row 0
+    d = rng.normal(size=(3, n))
+    Cs = np.stack([Cm, Cm, Cm])
+    Cs[1, 2, 2] = -1.0
+    x, u, ifail, it = ctx.qld_solve(d, A, b, np.array([2, 2, 9]), C_=Cs)
+    assert ifail[0] > 10 and ifail[1] == 2 and ifail[2] == 5
+    xr, ur, fr = ref_qld(Cm, d[0], A[0, :2], b[0, :2])
+    assert fr > 10
