@@ -495,8 +495,16 @@ typedef struct wg_qld_batch {
 } wg_qld_batch;
 
 /* The Hessian shared by every QP of later wg_qld_solve_batch(shared_hessian = 1) calls (both reference generators have a
- * constant C): its inverse is formed once, on the host in extended precision.  C: column-major, leading dimension nmax. */
-int wg_qld_set_shared_hessian(wg_ctx *ctx, int n, int nmax, const double *C);
+ * constant C): its Cholesky factor is inverted once, on the host in extended precision.  C: column-major, leading dimension
+ * nmax.  eps > 0 applies QLD's own treatment of the Hessian first (ql0002_, qld.cpp:809-918): QLD factorises C + diag I, diag
+ * found by its 2 x 2 minor test and by doubling steps until every Cholesky pivot exceeds vsmall = eps (the accuracy argument
+ * of ql0001_, 1e-8 in every call of the reference).  For a well conditioned C diag is 0; for the reference's generators
+ * (eigenvalues down to 2e-9) it is not, and ql0001_'s results are those of the regularised problem - pass the reference's eps
+ * to reproduce them, 0 to solve the problem as stated.  wg_qld_shared_boost returns the diag that was added. */
+int wg_qld_set_shared_hessian(wg_ctx *ctx, int n, int nmax, const double *C, double eps);
+double wg_qld_shared_boost(wg_ctx *ctx);
+/* The rule alone (host arithmetic, no device): the multiple of I that ql0001_(eps) adds to C before factorising it. */
+double wg_qld_diagonal_boost(int n, int nmax, const double *C, double eps);
 int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *batch);
 
 /* ------------------------------------------------------------------------------------------------
@@ -680,6 +688,47 @@ int64_t wg_dimitrov_period_count(const wg_dimitrov_params *p, int64_t n_samples)
 int wg_dimitrov_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *com_out, double *zmp_out,
                           wg_foot_sample *left, wg_foot_sample *right, const int64_t *period_offsets,
                           wg_dimitrov_period *periods, int32_t *status, int32_t *periods_done);
+
+/* ------------------------------------------------------------------------------------------------
+ * Wieber2006 front to back: feet trajectories -> support polygons -> per-period dense QP (n = 2N = 150 jerks, m <= 8N CoP
+ * rows) -> LIPM, batched over walks
+ *   replaces ZMPQPWithConstraint::BuildLinearConstraintInequalities / ComputeLinearSystem
+ *                (src/ZMPRefTrajectoryGeneration/ZMPQPWithConstraint.cpp:229-502, :94-228)
+ *            ZMPQPWithConstraint::BuildMatricesPxPu (:504-663) and BuildZMPTrajectoryFromFootTrajectory (:665-1338: constant
+ *                matrices, the receding-horizon loop, ql0001_, the feasibility check of the solution, the 5 ms interpolation)
+ *            ZMPQPWithConstraint::GetZMPDiscretization (:1340-1387)
+ * ---------------------------------------------------------------------------------------------- */
+#define WG_WIEBER_MAX_N 80
+
+typedef struct wg_wieber_params {
+  double T;                           /* m_QP_T 0.02            (:71)                                                   */
+  double sampling_period;             /* m_SamplingPeriod 0.005 (:78)                                                   */
+  double com_height;                  /* ComHeight 0.80         (:674)                                                  */
+  double alpha, beta;                 /* 200, 1000              (:691)                                                  */
+  double constraint_x, constraint_y;  /* :setpbwconstraint XY, 0.04 0.04 (:68-69)                                        */
+  double sole_length, sole_width;     /* CjrlFoot::getSoleSize (robot data)                                             */
+  double qld_eps;                     /* Eps handed to ql0001_, 1e-8 (:734): QLD regularises the Hessian with it (see
+                                         wg_qld_set_shared_hessian); 0 solves the QP as stated                          */
+  int32_t N;                          /* m_QP_N 75              (:72); 2N <= WG_QLD_MAX_N                               */
+  int32_t reserved;
+} wg_wieber_params;
+
+void wg_wieber_default_params(wg_wieber_params *p);
+/* Constant matrices (host, the reference's summation order) and the Hessian of the dense solver (wg_qld_set_shared_hessian). */
+int wg_wieber_set_params(wg_ctx *ctx, const wg_wieber_params *p);
+/* Number of QP periods the loop runs for a feet buffer of n samples (the loop bound of :993-995). */
+int64_t wg_wieber_period_count(const wg_wieber_params *p, int64_t n_samples);
+/* GetZMPDiscretization of ZMPQPWithConstraint for every walk of a Kajita plan.  Outputs (any may be NULL) live in `mem`:
+ *   com_out [total][6]   COMStates x[0..2], y[0..2]; rows the loop does not reach are zero
+ *   zmp_out [total][2]   ZMPRefPositions px, py after the loop (rows it does not reach keep the discretised reference)
+ *   left / right [total] feet
+ *   status [B]           0; 1 = the QP failed or its solution violates a row by more than 1e-8 (the reference prints and
+ *                        returns -1, :1048-1052, :1085-1104); 2 = no polygon covers a sample time ("HERE 3", :545-549);
+ *                        3 = polygon capacity; 4 = ZMPDiscretization refused the walk.  A failed walk stops at that period
+ *   periods_done [B]     QP periods attempted
+ *   qp_iterations [B]    active-set changes summed over the walk's QPs */
+int wg_wieber_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *com_out, double *zmp_out, wg_foot_sample *left,
+                        wg_foot_sample *right, int32_t *status, int32_t *periods_done, long long *qp_iterations);
 
 #ifdef __cplusplus
 }

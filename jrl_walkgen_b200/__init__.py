@@ -241,10 +241,12 @@ class Context:
         return heads, F
 
     # ---- general dense QP (ql0001_ convention) ---------------------------------------------------
-    def qld_set_shared_hessian(self, Cmat):
+    def qld_set_shared_hessian(self, Cmat, eps=0.0):
+        """eps > 0: QLD's diagonal boost rule with vsmall = eps first (returns the multiple of I that was added)."""
         Cmat = np.asfortranarray(Cmat, dtype=np.float64)
         n = Cmat.shape[0]
-        self._check(self.lib.wg_qld_set_shared_hessian(self.h, n, n, Cmat.ctypes.data))
+        self._check(self.lib.wg_qld_set_shared_hessian(self.h, n, n, Cmat.ctypes.data, float(eps)))
+        return self.lib.wg_qld_shared_boost(self.h)
 
     def qld_solve(self, d, A, b, m, C_=None, me=None, xl=None, xu=None, want_u=True):
         """wg_qld_solve_batch on host arrays.  d [B][n]; A [B][mmax][n] (row r of QP k = A[k, r]; converted here to the
@@ -467,6 +469,38 @@ class Context:
         return {"com": com, "zmp": zmp, "left": left, "right": right, "types": types, "status": status,
                 "periods_done": done, "periods": [per[po[b]:po[b] + done[b]] for b in range(B)],
                 "period_counts": np.array(pc), "sample_offsets": so}
+
+    # ---- Wieber2006 generator ------------------------------------------------------------------
+    def wieber_set_params(self, params=None):
+        if params is None:
+            params = _capi.WieberParams()
+            self.lib.wg_wieber_default_params(C.byref(params))
+        self.wieber_params = params
+        self._check(self.lib.wg_wieber_set_params(self.h, C.byref(params)))
+
+    def wieber_run(self, walks, init_feet, zmpdisc_params=None, want_feet=False):
+        """footsteps -> ZMPDiscretization -> support polygons -> per-period dense QP -> CoM / ZMP at 5 ms for a list of step
+        arrays.  -> dict(com, zmp, left, right, status, periods_done, period_counts, qp_iterations, sample_offsets)."""
+        if not hasattr(self, "wieber_params"):
+            self.wieber_set_params()
+        B = len(walks)
+        off = np.concatenate([[0], np.cumsum([len(w) for w in walks])]).astype(np.int64)
+        steps = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=REL_STEP_DTYPE) for w in walks]))
+        plan = KajitaPlan(self, off, steps, np.ascontiguousarray(init_feet, dtype=np.float64), zmpdisc_params)
+        try:
+            so = plan.sample_offsets
+            ns = int(so[-1])
+            pc = [int(self.lib.wg_wieber_period_count(C.byref(self.wieber_params), int(so[b + 1] - so[b]))) for b in range(B)]
+            com = np.zeros((ns, 6)); zmp = np.zeros((ns, 2))
+            left = np.zeros(ns, dtype=KAJITA_FOOT_DTYPE) if want_feet else None
+            right = np.zeros(ns, dtype=KAJITA_FOOT_DTYPE) if want_feet else None
+            status = np.zeros(B, dtype=np.int32); done = np.zeros(B, dtype=np.int32); its = np.zeros(B, dtype=np.int64)
+            self._check(self.lib.wg_wieber_run_batch(self.h, plan.h, WG_MEM_HOST, com.ctypes.data, zmp.ctypes.data, _ptr(left),
+                                                     _ptr(right), status.ctypes.data, done.ctypes.data, its.ctypes.data))
+        finally:
+            plan.destroy()
+        return {"com": com, "zmp": zmp, "left": left, "right": right, "status": status, "periods_done": done,
+                "period_counts": np.array(pc), "qp_iterations": its, "sample_offsets": so}
 
 
 class KajitaPlan:

@@ -90,6 +90,14 @@ class QldBatch(C.Structure):
                 ("ifail", C.c_void_p), ("iterations", C.c_void_p)]
 
 
+class WieberParams(C.Structure):
+    """Mirror of wg_wieber_params."""
+    _fields_ = [("T", C.c_double), ("sampling_period", C.c_double), ("com_height", C.c_double), ("alpha", C.c_double),
+                ("beta", C.c_double), ("constraint_x", C.c_double), ("constraint_y", C.c_double),
+                ("sole_length", C.c_double), ("sole_width", C.c_double), ("qld_eps", C.c_double), ("N", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class ZmpDiscParams(C.Structure):
     """Mirror of wg_zmpdisc_params."""
     _fields_ = [("sampling_period", C.c_double), ("preview_time", C.c_double), ("t_single", C.c_double),
@@ -261,8 +269,15 @@ SIGNATURES = {
                                                 C.c_void_p, C.c_longlong]),
     "wg_optcholesky_full_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int]),
-    "wg_qld_set_shared_hessian": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "wg_qld_set_shared_hessian": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double]),
+    "wg_qld_shared_boost": (C.c_double, [C.c_void_p]),
+    "wg_qld_diagonal_boost": (C.c_double, [C.c_int, C.c_int, C.c_void_p, C.c_double]),
     "wg_qld_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(QldBatch)]),
+    "wg_wieber_default_params": (None, [C.POINTER(WieberParams)]),
+    "wg_wieber_set_params": (C.c_int, [C.c_void_p, C.POINTER(WieberParams)]),
+    "wg_wieber_period_count": (C.c_int64, [C.POINTER(WieberParams), C.c_int64]),
+    "wg_wieber_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "wg_zmpdisc_default_params": (None, [C.POINTER(ZmpDiscParams)]),
     "wg_steps_support_foot": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, C.c_double, C.c_double]),
     "wg_steps_arc": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,

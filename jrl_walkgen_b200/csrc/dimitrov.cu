@@ -662,6 +662,36 @@ void wg_dimitrov_release(wg_ctx *ctx)
   ctx->dimitrov = nullptr;
 }
 
+// Used by wieber.cu: BuildLinearConstraintInequalities of ZMPQPWithConstraint (ZMPQPWithConstraint.cpp:229-502) is the same
+// scan with the same half-plane arithmetic as FootConstraintsAsLinearSystem's, with its own sole size and security margins.
+// d_clock_out: the accumulated 5 ms clock table on the device (>= max_n entries).
+extern "C" int wgi_fcals_launch(wg_ctx *ctx, int B, const int64_t *d_samp_off, const wg_foot_sample *left,
+                                const wg_foot_sample *right, const int32_t *types, const int64_t *d_lci_off, wg_lci *lci,
+                                int32_t *n_lci, double hw, double hh, double sampling_period, size_t max_n,
+                                const double **d_clock_out)
+{
+  DimHost *H = dim_of(ctx);
+  if (H->ready && std::fabs(H->par.sampling_period - sampling_period) > 1e-15)
+    return wg_fail(ctx, WG_ERR_INVALID, "sampling period differs from the one given to wg_dimitrov_set_params");
+  if (!H->ready) H->par.sampling_period = sampling_period;     // clock table only
+  int rc = ensure_clock(ctx, H, max_n);
+  if (rc != WG_OK) return rc;
+  if ((rc = dm_ensure(ctx, H, 13, sizeof(DimConsts))) != WG_OK) return rc;
+  DimConsts alt;
+  std::memset(&alt, 0, sizeof alt);
+  alt.hw = hw; alt.hh = hh; alt.merge_rows = 0;
+  WG_CUDA(ctx, cudaMemcpyAsync(H->buf[13], &alt, sizeof alt, cudaMemcpyHostToDevice, ctx->stream));
+  WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));            // `alt` is a stack temporary
+  const int grid = std::max(1, std::min((B + FC_WARPS - 1) / FC_WARPS, ctx->sm_count * 8));
+  wg_prof_start(ctx, WG_K_FCALS);
+  fcals_kernel<<<grid, FC_WARPS * 32, 0, ctx->stream>>>(B, static_cast<const DimConsts *>(H->buf[13]), d_samp_off, left, right,
+                                                           types, H->d_time, d_lci_off, lci, n_lci);
+  wg_prof_stop(ctx);
+  WG_LAUNCHED(ctx);
+  if (d_clock_out) *d_clock_out = H->d_time;
+  return WG_OK;
+}
+
 extern "C" {
 
 void wg_dimitrov_default_params(wg_dimitrov_params *p)

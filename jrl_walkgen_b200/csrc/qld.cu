@@ -6,14 +6,19 @@
 //      min 1/2 x'Cx + d'x   s.t.  a_j'x + b_j  = 0 (j < me),  a_j'x + b_j >= 0 (me <= j < m),  xl <= x <= xu.
 //
 // B200-first formulation.  One CTA owns one QP (QPs are taken from a work counter).  The method is the dual active-set method
-// of Goldfarb and Idnani in its RANGE-SPACE form, the same iteration herdt_qp.cuh runs in point space: with H^-1 at hand, the
-// only factorisation is the inverse Cholesky factor T of the active Gram matrix N'H^-1 N (grown by a row per added constraint,
-// shrunk by Givens rotations per dropped one), next to the columns Z = H^-1 N of the active normals.  A null-space /
-// orthogonal-factor implementation (QLD, QuadProg) rotates an n x n matrix on every active-set change - a chain of n - q
-// dependent Givens rotations; the range-space form replaces it by one n x n product with H^-1 (coalesced, n independent dot
-// products) and O(q^2) work on T, which is what a CTA does well, and it is cheap exactly where the reference's problems live:
-// few active rows (q << n).  H^-1 is formed once per Hessian (qld_hinv_kernel; once per BATCH when the Hessian is shared, as
-// in both reference generators, whose C is constant) and lives in L2; per-iteration HBM traffic is the m x n constraint matrix.
+// of Goldfarb and Idnani in its RANGE-SPACE form, the same iteration herdt_qp.cuh runs in point space, written in the
+// variables v = L'x of the Cholesky factor C = L L' (Hessian = identity there): with X = L^-1 at hand, a row a_p becomes
+// y_p = X a_p, the Gram matrix of the active rows is Y'Y, and the only factorisation that changes during the solve is the
+// inverse Cholesky factor T of Y'Y (grown by a row per added constraint, shrunk by Givens rotations per dropped one), next
+// to the columns Y of the active rows.  A null-space / orthogonal-factor implementation (QLD, QuadProg) rotates an n x n
+// matrix on every active-set change - a chain of n - q dependent Givens rotations; here an active-set change costs two
+// triangular n x n products with X (coalesced, n independent dot products each) and O(q^2 + q n) work on T and Y, which is
+// what a CTA does well, and it is cheapest exactly where the reference's problems live: few active rows (q << n).
+// Working through the FACTOR matters: the Hessians of the reference's generators have condition numbers around 5e11
+// (ZMPQPWithConstraint), and products with an explicit H^-1 lose cond(H) eps = 5e-5 of relative accuracy - measured: jerks off
+// by 40 % on Wieber's QPs -, products with X lose sqrt(cond) eps = 7e-11.  X is formed once per Hessian (qld_factor_kernel;
+// once per BATCH, in extended precision on the host, when the Hessian is shared, as in both reference generators whose C is
+// constant) and lives in L2; per-iteration HBM traffic is the m x n constraint matrix.
 // Pivoting follows QLD: the row with the largest violation normalised by its Euclidean norm (qld.cpp:1255-1331).
 #include "wg_common.h"
 #include <algorithm>
@@ -29,6 +34,7 @@ struct QldState {
   double *d_hinv_shared = nullptr;   // [n*n] inverse of the shared Hessian
   double *d_c_shared = nullptr;      // [n*n] the shared Hessian itself (refinement step), symmetric dense
   int shared_n = 0;
+  double shared_boost = 0.0;         // the multiple of I QLD's rule added to the shared Hessian
   // per-call scratch
   double *d_hinv = nullptr; size_t cap_hinv = 0;     // [B][n*n] per-QP inverses
   double *d_work = nullptr; size_t cap_work = 0;     // per-CTA Z (n x qcap) and T (packed)
@@ -93,21 +99,22 @@ __device__ void block_argmin(double &v, int &idx, double *red, int *redi)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// H^-1 of `count` symmetric positive definite matrices, one CTA each, in place in the n x n output block:
-// Cholesky C = L L' in the lower triangle, L^-1 (transposed) into the strict upper triangle, H^-1 = L^-T L^-1.
+// X = L^-1 (C = L L') of `count` symmetric positive definite matrices, one CTA each, in place in the n x n output block,
+// stored SYMMETRICALLY: S[a][b] = X[max(a,b)][min(a,b)], so that both products the solver needs read it coalesced:
+//   y = X a   : y_i = sum_{j <= i} S[j n + i] a_j          z = X'v : z_j = sum_{i >= j} S[i n + j] v_i.
 // fail[b] = 1 when a pivot is not positive (QLD boosts the diagonal there, qld.cpp:809-854; this solver refuses).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QT)
-qld_hinv_kernel(int count, int n, int nmax, const double *__restrict__ C, long long c_stride, double *__restrict__ Hinv,
-                int *__restrict__ fail)
+qld_factor_kernel(int count, int n, int nmax, const double *__restrict__ C, long long c_stride, double *__restrict__ Sout,
+                  int *__restrict__ fail)
 {
   extern __shared__ double sm[];
-  double *dinv = sm, *hdiag = sm + n;
+  double *dinv = sm;
   __shared__ int bad;
   const int t = threadIdx.x;
   for (int b = blockIdx.x; b < count; b += gridDim.x) {
     const double *Cb = C + (size_t)b * c_stride;
-    double *W = Hinv + (size_t)b * n * n;
+    double *W = Sout + (size_t)b * n * n;
     if (t == 0) bad = 0;
     for (int e = t; e < n * n; e += QT) {
       const int i = e / n, j = e - i * n;
@@ -135,7 +142,7 @@ qld_hinv_kernel(int count, int n, int nmax, const double *__restrict__ C, long l
       }
       __syncthreads();
     }
-    // X = L^-1, column c by forward substitution, stored transposed: X[i][c] at W[c][i] (i > c), diagonal in dinv
+    // X = L^-1, column c by forward substitution, written transposed into the strict upper triangle: X[i][c] at W[c][i]
     for (int c = t; c < n; c += QT) {
       for (int i = c + 1; i < n; ++i) {
         double s = W[i * n + c] * dinv[c];
@@ -144,18 +151,9 @@ qld_hinv_kernel(int count, int n, int nmax, const double *__restrict__ C, long l
       }
     }
     __syncthreads();
-    // H^-1[a][b] = sum_{k >= a} X[k][a] X[k][b], b <= a; strict lower part over L (dead), diagonal via shared memory
-    for (int a = 0; a < n; ++a) {
-      for (int bb = t; bb <= a; bb += QT) {
-        double s = dinv[a] * ((bb == a) ? dinv[a] : W[bb * n + a]);
-        for (int k = a + 1; k < n; ++k) s = fma(W[a * n + k], W[bb * n + k], s);
-        if (bb == a) hdiag[a] = s; else W[a * n + bb] = s;
-      }
-    }
-    __syncthreads();
     for (int e = t; e < n * n; e += QT) {
       const int i = e / n, j = e - i * n;
-      if (j > i) W[e] = W[j * n + i]; else if (j == i) W[e] = hdiag[i];
+      if (j < i) W[e] = W[j * n + i]; else if (j == i) W[e] = dinv[i];
     }
     if (t == 0 && fail) fail[b] = bad;
     __syncthreads();
@@ -166,7 +164,7 @@ struct QldArgs {
   int B, n, nmax, mmax, qcap;
   const int *m, *me;
   const double *C; long long c_stride;      // per-QP Hessians (refinement), or the shared one with stride 0
-  const double *Hinv; long long h_stride;   // 0: shared
+  const double *S; long long h_stride;      // X = L^-1 in symmetric storage; stride 0: shared
   const int *hfail;                         // per Hessian (index b, or 0 when shared), may be null
   const double *d;
   const double *A; long long a_stride;
@@ -180,8 +178,8 @@ struct QldArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// The solver.  Shared memory: x, x0, ap, zp, zd [n each]; inrm [m + 2n]; u, g, w, r [qcap each]; W, slot [qcap ints];
-// active flags [m + 2n bytes]; free-slot stack [qcap ints].
+// The solver.  Shared memory: x, v, v0, ap, yp, yd [n each]; inrm [m + 2n]; u, g, w, r [qcap each]; W, slot [qcap ints];
+// active flags [m + 2n bytes]; free-slot stack [qcap ints].  v = L'x is the iterate, x = X'v is refreshed after every step.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QT, 2)
 qld_kernel(QldArgs P)
@@ -195,15 +193,15 @@ qld_kernel(QldArgs P)
   const bool bounds = (P.xl != nullptr) && (P.xu != nullptr);
   const int mtot_max = mmax + (bounds ? 2 * n : 0);
   double *x = reinterpret_cast<double *>(smem_raw);
-  double *x0 = x + n, *ap = x0 + n, *zp = ap + n, *zd = zp + n;
-  double *inrm = zd + n;
+  double *v = x + n, *v0 = v + n, *ap = v0 + n, *yp = ap + n, *yd = yp + n;
+  double *inrm = yd + n;
   double *u = inrm + mtot_max, *g = u + qcap, *w = g + qcap, *r = w + qcap;
   int *Wc = reinterpret_cast<int *>(r + qcap);
   int *slot = Wc + qcap, *freeslot = slot + qcap;
   signed char *sgn = reinterpret_cast<signed char *>(freeslot + qcap);   // sign of an active (equality) row
   unsigned char *act = reinterpret_cast<unsigned char *>(sgn + qcap);
-  double *Z = P.work + (size_t)blockIdx.x * P.work_stride;                // n x qcap, column `slot` at Z + slot * n
-  double *T = Z + (size_t)n * qcap;                                       // packed lower triangle, row j at T + tri(j)
+  double *Y = P.work + (size_t)blockIdx.x * P.work_stride;                // n x qcap, column `slot` at Y + slot * n
+  double *T = Y + (size_t)n * qcap;                                       // packed lower triangle, row j at T + tri(j)
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
   for (;;) {
@@ -215,7 +213,7 @@ qld_kernel(QldArgs P)
     const int m = P.m[b], me = P.me ? P.me[b] : 0;
     const double *A = P.A + (size_t)b * P.a_stride, *bv = P.b + (size_t)b * P.b_stride;
     const double *dv = P.d + (size_t)b * n;
-    const double *Hi = P.Hinv + (size_t)b * P.h_stride;
+    const double *S = P.S + (size_t)b * P.h_stride;
     const double *Cm = P.C ? P.C + (size_t)b * P.c_stride : nullptr;
     const double *xl = bounds ? P.xl + (size_t)b * n : nullptr, *xu = bounds ? P.xu + (size_t)b * n : nullptr;
     int fail = 0, iters = 0, q = 0, neq = 0;
@@ -223,11 +221,17 @@ qld_kernel(QldArgs P)
     if (!fail && P.hfail && P.hfail[P.h_stride ? b : 0]) fail = 2;
     const int mtot = fail ? 0 : m + (bounds ? 2 * n : 0);
 
-    // ---- unconstrained optimum x0 = -H^-1 d, row norms, flags
+    // ---- unconstrained optimum v0 = -X d, x = X'v0; row norms, flags
     for (int i = t; i < n; i += QT) {
       double s = 0.0;
-      for (int j = 0; j < n; ++j) s = fma(Hi[(size_t)j * n + i], dv[j], s);
-      x0[i] = -s; x[i] = -s;
+      for (int j = 0; j <= i; ++j) s = fma(S[(size_t)j * n + i], dv[j], s);
+      v0[i] = -s; v[i] = -s;
+    }
+    __syncthreads();
+    for (int j = t; j < n; j += QT) {
+      double s = 0.0;
+      for (int i = j; i < n; ++i) s = fma(S[(size_t)i * n + j], v[i], s);
+      x[j] = s;
     }
     for (int rr = t; rr < mtot; rr += QT) {
       double s = 1.0;
@@ -292,37 +296,54 @@ qld_kernel(QldArgs P)
         ap[j] = a;
       }
       __syncthreads();
-      // z_p = H^-1 a_p
+      // y_p = X a_p, M_pp = |y_p|^2
       double mpp = 0.0;
       for (int i = t; i < n; i += QT) {
         double s = 0.0;
-        for (int j = 0; j < n; ++j) s = fma(Hi[(size_t)j * n + i], ap[j], s);
-        zp[i] = s;
-        mpp = fma(s, ap[i], mpp);
+        for (int j = 0; j <= i; ++j) s = fma(S[(size_t)j * n + i], ap[j], s);
+        yp[i] = s;
+        mpp = fma(s, s, mpp);
       }
       const double Mpp = block_sum(mpp, red);
       double up = 0.0;
       bool added = false;
       while (!added && !done) {
         if (++iters > maxit) { fail = 1; done = true; break; }
-        // g_k = z_k' a_p (warp per active row)
+        // w = Q'y_p (warp per active row): the coordinates of y_p in the orthonormal basis Q of the active rows (Y = Q R)
         for (int k = warp; k < q; k += QW) {
-          const double *zk = Z + (size_t)slot[k] * n;
+          const double *qk = Y + (size_t)slot[k] * n;
           double s = 0.0;
-          for (int j = lane; j < n; j += 32) s = fma(zk[j], ap[j], s);
+          for (int j = lane; j < n; j += 32) s = fma(qk[j], yp[j], s);
+          s = warp_sum(s);
+          if (lane == 0) w[k] = s;
+        }
+        __syncthreads();
+        // yd = y_p - Q w: the part of y_p orthogonal to the active rows, with one re-orthogonalisation pass (Gram-Schmidt
+        // twice: |yd| stays accurate when y_p lies almost inside the span, which is the rule for adjacent CoP rows)
+        for (int i = t; i < n; i += QT) {
+          double s = yp[i];
+          for (int k = 0; k < q; ++k) s = fma(-w[k], Y[(size_t)slot[k] * n + i], s);
+          yd[i] = s;
+        }
+        __syncthreads();
+        for (int k = warp; k < q; k += QW) {
+          const double *qk = Y + (size_t)slot[k] * n;
+          double s = 0.0;
+          for (int j = lane; j < n; j += 32) s = fma(qk[j], yd[j], s);
           s = warp_sum(s);
           if (lane == 0) g[k] = s;
         }
         __syncthreads();
-        double wsq = 0.0;
-        for (int j = t; j < q; j += QT) {
-          const double *Tr = T + tri(j);
-          double s = 0.0;
-          for (int e = 0; e <= j; ++e) s = fma(Tr[e], g[e], s);
-          w[j] = s;
-          wsq = fma(s, s, wsq);
+        double dsq = 0.0;
+        for (int i = t; i < n; i += QT) {
+          double s = yd[i];
+          for (int k = 0; k < q; ++k) s = fma(-g[k], Y[(size_t)slot[k] * n + i], s);
+          yd[i] = s;
+          dsq = fma(s, s, dsq);
         }
-        const double delta = Mpp - block_sum(wsq, red);    // (block_sum synchronises: w is visible)
+        for (int k = t; k < q; k += QT) w[k] += g[k];
+        const double delta = block_sum(dsq, red);             // = a_p' (H^-1 - H^-1 N (N'H^-1 N)^-1 N'H^-1) a_p
+        // r = R^-1 w = T'w: the dual step direction
         double t1 = INF; int l = 0x7fffffff;
         for (int j = t; j < q; j += QT) {
           double s = 0.0;
@@ -334,7 +355,7 @@ qld_kernel(QldArgs P)
           }
         }
         block_argmin(t1, l, red, redi);
-        const bool dependent = !(delta > 1e-12 * Mpp);
+        const bool dependent = !(delta > 1e-22 * Mpp);
         const double t2 = dependent ? INF : -sp / delta;
         const double tt = fmin(t1, t2);
         if (!(tt < INF)) {
@@ -342,12 +363,14 @@ qld_kernel(QldArgs P)
           if (neq < me && fabs(sp) * inrm[p] <= 1e-9 * (fabs(bv[p]) * inrm[p] + xnorm + 1e-300)) { act[p] = 0; ++neq; added = true; break; }   // redundant equality
           fail = 10 + p + 1; done = true; break;            // QLD: ifail > 10, constraint ifail - 10 inconsistent
         }
-        if (!dependent || tt == t2) {
-          // primal direction z_p - Z r, step
-          for (int i = t; i < n; i += QT) {
-            double s = zp[i];
-            for (int k = 0; k < q; ++k) s = fma(-r[k], Z[(size_t)slot[k] * n + i], s);
-            x[i] = fma(tt, s, x[i]);
+        if (!dependent) {
+          // step along yd in the factor's variables, x = X'v
+          for (int i = t; i < n; i += QT) v[i] = fma(tt, yd[i], v[i]);
+          __syncthreads();
+          for (int j = t; j < n; j += QT) {
+            double s = 0.0;
+            for (int i = j; i < n; ++i) s = fma(S[(size_t)i * n + j], v[i], s);
+            x[j] = s;
           }
           sp += tt * delta;
         }
@@ -355,12 +378,12 @@ qld_kernel(QldArgs P)
         up += tt;
         __syncthreads();
         if (t2 <= t1) {
-          // full step: row p becomes active
+          // full step: row p becomes active; new basis vector yd / |yd|, new row of T = R^-T
           if (q >= qcap || nfree <= 0) { fail = 3; done = true; break; }
           const double idd = rsqrt(delta);
           for (int j = t; j < q; j += QT) T[tri(q) + j] = -r[j] * idd;
           const int sl = freeslot[nfree - 1];
-          for (int i = t; i < n; i += QT) Z[(size_t)sl * n + i] = zp[i];
+          for (int i = t; i < n; i += QT) Y[(size_t)sl * n + i] = yd[i] * idd;
           if (t == 0) { T[tri(q) + q] = idd; Wc[q] = p; slot[q] = sl; u[q] = up; sgn[q] = (signed char)sign; act[p] = 1; }
           --nfree; ++q;
           if (neq < me) ++neq;
@@ -368,26 +391,45 @@ qld_kernel(QldArgs P)
           __syncthreads();
           break;
         }
-        // partial step: multiplier l reached zero -> drop row l (warp 0 rotates T; see herdt_qp.cuh drop_row)
+        // partial step: multiplier l reached zero -> drop row l.  Warp 0 rotates rows (l, rr), rr > l, of T so that column l
+        // vanishes below row l and deletes row / column l (herdt_qp.cuh drop_row); the same rotations, kept in g (cosines)
+        // and w (sines), are then applied to the basis vectors Q_l, Q_rr by all threads (Q -> Q G').
         if (warp == 0) {
-          for (int j = lane; j < q; j += 32) w[j] = (j <= l) ? T[tri(l) + j] : 0.0;
+          for (int j = lane; j < q; j += 32) yd[j] = (j <= l) ? T[tri(l) + j] : 0.0;     // yd: rotating copy of row l (q <= n)
           __syncwarp();
           for (int rr = l + 1; rr < q; ++rr) {
             const double *Tr = T + tri(rr);
-            const double p1 = w[l], p2 = Tr[l];
+            const double p1 = yd[l], p2 = Tr[l];
             const double ih = rsqrt(p1 * p1 + p2 * p2);
             const double c_ = p1 * ih, s_ = p2 * ih;
             __syncwarp();
             double *Tn = T + tri(rr - 1);
             for (int j = lane; j <= rr; j += 32) {
-              const double x1 = w[j], x2 = Tr[j];
-              w[j] = c_ * x1 + s_ * x2;
+              const double x1 = yd[j], x2 = Tr[j];
+              yd[j] = c_ * x1 + s_ * x2;
               const double nr = c_ * x2 - s_ * x1;
               if (j < l) Tn[j] = nr;
               else if (j > l) Tn[j - 1] = nr;
             }
+            if (lane == 0) { g[rr] = c_; w[rr] = s_; }
             __syncwarp();
           }
+        }
+        __syncthreads();
+        {
+          const int sl_l = slot[l];
+          for (int i = t; i < n; i += QT) {
+            double ql = Y[(size_t)sl_l * n + i];
+            for (int rr = l + 1; rr < q; ++rr) {
+              double *qr = Y + (size_t)slot[rr] * n + i;
+              const double c_ = g[rr], s_ = w[rr], b2 = *qr;
+              *qr = c_ * b2 - s_ * ql;
+              ql = c_ * ql + s_ * b2;
+            }
+          }
+        }
+        __syncthreads();
+        if (warp == 0) {
           if (lane == 0) { act[Wc[l]] = 0; freeslot[nfree] = slot[l]; }
           __syncwarp();
           for (int base = l; base < q - 1; base += 32) {
@@ -414,40 +456,19 @@ qld_kernel(QldArgs P)
       }
     }
 
-    // ---- x from the multipliers (x = x0 + sum_k u_k z_k), then one refinement step on the stationarity residual
-    if (!fail) {
-      for (int i = t; i < n; i += QT) {
-        double s = x0[i];
-        for (int k = 0; k < q; ++k) s = fma(u[k], Z[(size_t)slot[k] * n + i], s);
-        x[i] = s;
-      }
+    // (No Newton step on the stationarity residual here: H^-1 res leaves the active rows, and with cond(H) = 5e11 its rounding
+    // noise moved vertex solutions of Wieber's QPs 2e-7 outside their active rows - measured.  v is kept by projected steps,
+    // each orthogonal to every active row, so the active rows hold to rounding and x = X'v needs no repair.)
+    // ---- results: x, multipliers in QLD's layout (m rows, n lower bounds, n upper bounds; qld.cpp:520-536)
+    if (fail) {
       __syncthreads();
-      if (Cm) {
-        // res = C x + d - sum_k u_k a_k ; x -= H^-1 res
-        for (int i = t; i < n; i += QT) {
-          double s = dv[i];
-          for (int j = 0; j < n; ++j) s = fma(Cm[(size_t)j * P.nmax + i], x[j], s);
-          for (int k = 0; k < q; ++k) {
-            const int pk = Wc[k];
-            double a;
-            if (pk < m) a = sgn[k] * A[pk + (size_t)i * mmax];
-            else if (pk < m + n) a = (i == pk - m) ? 1.0 : 0.0;
-            else a = (i == pk - m - n) ? -1.0 : 0.0;
-            s = fma(-u[k], a, s);
-          }
-          zd[i] = s;
-        }
-        __syncthreads();
-        for (int i = t; i < n; i += QT) {
-          double s = 0.0;
-          for (int j = 0; j < n; ++j) s = fma(Hi[(size_t)j * n + i], zd[j], s);
-          x[i] -= s;
-        }
-        __syncthreads();
+      for (int j = t; j < n; j += QT) {
+        double s = 0.0;
+        for (int i = j; i < n; ++i) s = fma(S[(size_t)i * n + j], v0[i], s);
+        x[j] = s;
       }
     }
-    // ---- results: x, multipliers in QLD's layout (m rows, n lower bounds, n upper bounds; qld.cpp:520-536)
-    for (int i = t; i < n; i += QT) P.x[(size_t)b * n + i] = fail ? x0[i] : x[i];
+    for (int i = t; i < n; i += QT) P.x[(size_t)b * n + i] = x[i];
     if (P.u) {
       double *uo = P.u + (size_t)b * P.u_stride;
       const int mu = max(m, 0) + 2 * n;
@@ -471,14 +492,14 @@ qld_kernel(QldArgs P)
 size_t qld_smem_bytes(int n, int mmax, int qcap, bool bounds)
 {
   const size_t mtot = (size_t)mmax + (bounds ? 2 * (size_t)n : 0);
-  size_t s = sizeof(double) * (5 * (size_t)n + mtot + 4 * (size_t)qcap) + sizeof(int) * 3 * (size_t)qcap + qcap + mtot;
+  size_t s = sizeof(double) * (6 * (size_t)n + mtot + 4 * (size_t)qcap) + sizeof(int) * 3 * (size_t)qcap + qcap + mtot;
   return (s + 15) & ~(size_t)15;
 }
 
 int hinv_launch(wg_ctx *ctx, int count, int n, int nmax, const double *d_C, long long c_stride, double *d_hinv, int *d_fail)
 {
   const int blocks = std::max(1, std::min(count, ctx->sm_count * 2));
-  qld_hinv_kernel<<<blocks, QT, sizeof(double) * 2 * n, ctx->stream>>>(count, n, nmax, d_C, c_stride, d_hinv, d_fail);
+  qld_factor_kernel<<<blocks, QT, sizeof(double) * n, ctx->stream>>>(count, n, nmax, d_C, c_stride, d_hinv, d_fail);
   WG_LAUNCHED(ctx);
   return WG_OK;
 }
@@ -495,13 +516,74 @@ void wg_qld_release(wg_ctx *ctx)
   ctx->qld = nullptr;
 }
 
+// QLD does not factorise the Hessian it is given but G + diag I (ql0002_, qld.cpp:809-918, lql = true): diag starts as
+// twice the largest of (vsmall - g_ii) and of the 2 x 2 minor bounds -min(g_ii, g_jj) + g_ij^2 / (|g_ii - g_jj| + |g_ij|);
+// whenever a Cholesky pivot then falls below vsmall, diag grows by vsmall - pivot / |w|^2 (w: the direction of smallest
+// curvature found so far), is DOUBLED, and the factorisation restarts.  vsmall is the `eps` the caller hands to ql0001_
+// (1e-8 in every call of the reference).  For the reference's generators this matters: their Hessians have eigenvalues down
+// to 2e-9, QLD regularises them, and its solutions differ from the exact minimiser by 40 % in the flat directions.  This
+// function restates that rule in QLD's operation order and returns the multiple of I that QLD adds (0: none).
+static double qld_diagonal_boost(int n, int nmax, const double *C, double vsmall)
+{
+  if (!(vsmall > 0.0)) return 0.0;
+  auto g = [&](int i, int j) { return C[(size_t)j * nmax + i]; };   // symmetric
+  std::vector<double> gd(n);
+  double diag = 0.0;
+  for (int i = 0; i < n; ++i) {
+    gd[i] = g(i, i);
+    diag = std::max(diag, vsmall - gd[i]);
+    for (int j = i + 1; j < n; ++j) {
+      double ga = -std::min(gd[i], g(j, j));
+      const double gb = std::fabs(gd[i] - g(j, j)) + std::fabs(g(i, j));
+      if (gb > 0.0) ga += g(i, j) * g(i, j) / gb;
+      diag = std::max(diag, ga);
+    }
+  }
+  if (!(diag > 0.0)) diag = 0.0;
+  std::vector<double> R((size_t)n * n, 0.0), w(n);     // R upper triangular, R(i, j) at i * n + j
+  bool boosted = diag > 0.0;
+  for (int pass = 0; pass < 200; ++pass) {
+    if (boosted) diag = 2.0 * diag;                    // L70: diag = diagr * diag
+    boosted = false;
+    int jfail = -1; double temp = 0.0;
+    for (int j = 0; j < n && jfail < 0; ++j) {
+      for (int i = 0; i <= j; ++i) {
+        temp = (i == j) ? gd[i] + diag : g(i, j);
+        for (int k = 0; k < i; ++k) temp -= R[(size_t)k * n + i] * R[(size_t)k * n + j];
+        if (i < j) R[(size_t)i * n + j] = temp / R[(size_t)i * n + i];
+      }
+      if (temp < vsmall) { jfail = j; break; }
+      R[(size_t)j * n + j] = std::sqrt(temp);
+    }
+    if (jfail < 0) return diag;
+    // L140-L160: w solves R(0..j-1, 0..j-1) w = -R(0..j-1, j), w_j = 1
+    const int j = jfail;
+    w[j] = 1.0;
+    double sumx = 1.0;
+    for (int k = j - 1; k >= 0; --k) {
+      double sum = 0.0;
+      for (int i = k + 1; i <= j; ++i) sum -= R[(size_t)k * n + i] * w[i];
+      w[k] = sum / R[(size_t)k * n + k];
+      sumx += w[k] * w[k];
+    }
+    diag = diag + vsmall - temp / sumx;
+    boosted = true;
+  }
+  return diag;
+}
+
 extern "C" {
 
-int wg_qld_set_shared_hessian(wg_ctx *ctx, int n, int nmax, const double *C)
+int wg_qld_set_shared_hessian(wg_ctx *ctx, int n, int nmax, const double *C_in, double eps)
 {
-  if (!ctx || n <= 0 || n > WG_QLD_MAX_N || nmax < n || !C) return WG_ERR_INVALID;
+  if (!ctx || n <= 0 || n > WG_QLD_MAX_N || nmax < n || !C_in) return WG_ERR_INVALID;
   wg_device_guard guard(ctx->device);
   QldState *st = state_of(ctx);
+  const double boost = qld_diagonal_boost(n, nmax, C_in, eps);
+  std::vector<double> Cb(C_in, C_in + (size_t)nmax * n);
+  for (int i = 0; i < n; ++i) Cb[(size_t)i * nmax + i] += boost;
+  const double *C = Cb.data();
+  st->shared_boost = boost;
   // the inverse in extended precision on the host: once per Hessian, and the generators' Hessians (sums of products of
   // integrator matrices over 75 samples) are badly conditioned
   typedef long double LD;
@@ -526,12 +608,10 @@ int wg_qld_set_shared_hessian(wg_ctx *ctx, int n, int nmax, const double *C)
       X[(size_t)i * n + c] = -s / L[(size_t)i * n + i];
     }
   }
-  std::vector<double> H((size_t)n * n), Cs((size_t)n * n);
+  std::vector<double> H((size_t)n * n), Cs((size_t)n * n);     // H: X in symmetric storage (see qld_factor_kernel)
   for (int a = 0; a < n; ++a)
     for (int b = 0; b <= a; ++b) {
-      LD s = 0;
-      for (int k = a; k < n; ++k) s += X[(size_t)k * n + a] * X[(size_t)k * n + b];
-      H[(size_t)a * n + b] = H[(size_t)b * n + a] = (double)s;
+      H[(size_t)a * n + b] = H[(size_t)b * n + a] = (double)X[(size_t)a * n + b];
       Cs[(size_t)a * n + b] = Cs[(size_t)b * n + a] = C[(size_t)b * nmax + a];
     }
   WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -544,8 +624,17 @@ int wg_qld_set_shared_hessian(wg_ctx *ctx, int n, int nmax, const double *C)
   }
   WG_CUDA(ctx, cudaMemcpy(st->d_hinv_shared, H.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
   WG_CUDA(ctx, cudaMemcpy(st->d_c_shared, Cs.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+  ctx->qld_shared_owner = nullptr;    // a generator that installs its own Hessian claims it after this call
   return WG_OK;
 }
+
+double wg_qld_diagonal_boost(int n, int nmax, const double *C, double eps)
+{
+  if (n <= 0 || nmax < n || !C) return 0.0;
+  return qld_diagonal_boost(n, nmax, C, eps);
+}
+
+double wg_qld_shared_boost(wg_ctx *ctx) { return ctx && ctx->qld ? static_cast<QldState *>(ctx->qld)->shared_boost : 0.0; }
 
 int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q)
 {
@@ -621,13 +710,13 @@ int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q)
   a.d = d.d; a.A = d.A; a.a_stride = q->a_stride; a.b = d.b; a.b_stride = q->b_stride;
   a.xl = d.xl; a.xu = d.xu; a.x = d.x; a.u = d.u; a.u_stride = q->u_stride; a.ifail = d.ifail; a.iterations = d.iterations;
   if (q->shared_hessian) {
-    a.Hinv = st->d_hinv_shared; a.h_stride = 0; a.hfail = nullptr;
+    a.S = st->d_hinv_shared; a.h_stride = 0; a.hfail = nullptr;
     a.C = st->d_c_shared; a.c_stride = 0;
   } else {
     if ((rc = ensure(ctx, reinterpret_cast<void **>(&st->d_hinv), &st->cap_hinv, sizeof(double) * nb * n * n)) != WG_OK) return rc;
     if ((rc = ensure(ctx, reinterpret_cast<void **>(&st->d_fail), &st->cap_fail, sizeof(int) * nb)) != WG_OK) return rc;
     if ((rc = hinv_launch(ctx, B, n, nmax, d.C, (long long)nmax * n, st->d_hinv, st->d_fail)) != WG_OK) return rc;
-    a.Hinv = st->d_hinv; a.h_stride = (long long)n * n; a.hfail = st->d_fail;
+    a.S = st->d_hinv; a.h_stride = (long long)n * n; a.hfail = st->d_fail;
     a.C = d.C; a.c_stride = (long long)nmax * n;
   }
   const size_t smem = qld_smem_bytes(n, mmax, a.qcap, bounds);

@@ -51,6 +51,7 @@ struct wg_ctx {
   void *dimitrov = nullptr;
   // dense QP solver (qld.cu) and the Wieber2006 generator on top of it (wieber.cu)
   void *qld = nullptr;
+  const void *qld_shared_owner = nullptr;   // which generator's Hessian wg_qld_set_shared_hessian holds (nullptr: a caller's)
   void *wieber = nullptr;
 };
 

@@ -7,6 +7,7 @@ extern void wg_herdt_mpc_release(wg_ctx *ctx);
 extern void wg_pldp_release(wg_ctx *ctx);
 extern void wg_dimitrov_release(wg_ctx *ctx);
 extern void wg_qld_release(wg_ctx *ctx);
+extern void wg_wieber_release(wg_ctx *ctx);
 
 #include <mutex>
 
@@ -66,6 +67,7 @@ int wg_ctx_destroy(wg_ctx *ctx)
   wg_herdt_mpc_release(ctx);
   wg_herdt_release(ctx);
   wg_dimitrov_release(ctx);
+  wg_wieber_release(ctx);
   wg_qld_release(ctx);
   wg_pldp_release(ctx);
   if (ctx->d_previewF) cudaFree(ctx->d_previewF);

@@ -18,32 +18,34 @@
 #include <cstring>
 #include <vector>
 #include <limits>
+#include <algorithm>
 
 namespace {
 
-struct GI {
+template <typename Rr> struct GI {
+  typedef Rr real;
   int n, m;
-  std::vector<double> J, R;  /* J n x n (columns rotate), R n x n upper triangular (q x q used) */
-  std::vector<double> x, u, s, d, z, r;
+  std::vector<real> J, R;  /* J n x n (columns rotate), R n x n upper triangular (q x q used) */
+  std::vector<real> x, u, s, d, z, r;
   std::vector<int> act;      /* active constraint indices, size q */
   std::vector<char> is_act;
   int q = 0;
 
-  double &Jm(int i, int j) { return J[(size_t)i * n + j]; }
-  double &Rm(int i, int j) { return R[(size_t)i * n + j]; }
+  real &Jm(int i, int j) { return J[(size_t)i * n + j]; }
+  real &Rm(int i, int j) { return R[(size_t)i * n + j]; }
 
-  static void givens(double a, double b, double &c, double &s)
+  static void givens(real a, real b, real &c, real &s)
   {
     if (b == 0.0) { c = 1.0; s = 0.0; return; }
-    double h = std::hypot(a, b);
+    real h = std::sqrt(a * a + b * b);
     c = a / h; s = b / h;
   }
 
   /* d = J' a ; z = J2 d2 ; r = R^-1 d1 */
-  void compute_d(const double *a)
+  void compute_d(const real *a)
   {
     for (int j = 0; j < n; ++j) {
-      double t = 0;
+      real t = 0;
       for (int i = 0; i < n; ++i) t += Jm(i, j) * a[i];
       d[j] = t;
     }
@@ -51,7 +53,7 @@ struct GI {
   void update_z()
   {
     for (int i = 0; i < n; ++i) {
-      double t = 0;
+      real t = 0;
       for (int j = q; j < n; ++j) t += Jm(i, j) * d[j];
       z[i] = t;
     }
@@ -59,7 +61,7 @@ struct GI {
   void update_r()
   {
     for (int i = q - 1; i >= 0; --i) {
-      double t = d[i];
+      real t = d[i];
       for (int j = i + 1; j < q; ++j) t -= Rm(i, j) * r[j];
       r[i] = t / Rm(i, i);
     }
@@ -68,20 +70,20 @@ struct GI {
   {
     /* rotate d[q+1..n-1] into d[q] */
     for (int j = n - 1; j > q; --j) {
-      double c, s;
+      real c, s;
       givens(d[j - 1], d[j], c, s);
       if (s == 0.0 && c == 1.0) continue;
-      double dj1 = c * d[j - 1] + s * d[j];
+      real dj1 = c * d[j - 1] + s * d[j];
       d[j] = 0.0;
       d[j - 1] = dj1;
       for (int i = 0; i < n; ++i) {
-        double a = Jm(i, j - 1), b = Jm(i, j);
+        real a = Jm(i, j - 1), b = Jm(i, j);
         Jm(i, j - 1) = c * a + s * b;
         Jm(i, j) = -s * a + c * b;
       }
     }
     for (int i = 0; i <= q; ++i) Rm(i, q) = d[i];
-    if (std::fabs(d[q]) <= 1e-14 * std::fabs(Rm(0, 0) == 0 ? 1.0 : Rm(0, 0))) return false;
+    if (std::fabs(d[q]) <= (sizeof(real) > 8 ? 1e-17 : 1e-14) * std::fabs(Rm(0, 0) == 0 ? real(1.0) : Rm(0, 0))) return false;
     ++q;
     return true;
   }
@@ -96,15 +98,15 @@ struct GI {
     --q;
     for (int i = 0; i <= q; ++i) Rm(i, q) = 0.0;
     for (int j = l; j < q; ++j) {
-      double c, s;
+      real c, s;
       givens(Rm(j, j), Rm(j + 1, j), c, s);
       for (int k = j; k < q; ++k) {
-        double a = Rm(j, k), b = Rm(j + 1, k);
+        real a = Rm(j, k), b = Rm(j + 1, k);
         Rm(j, k) = c * a + s * b;
         Rm(j + 1, k) = -s * a + c * b;
       }
       for (int i = 0; i < n; ++i) {
-        double a = Jm(i, j), b = Jm(i, j + 1);
+        real a = Jm(i, j), b = Jm(i, j + 1);
         Jm(i, j) = c * a + s * b;
         Jm(i, j + 1) = -s * a + c * b;
       }
@@ -114,15 +116,15 @@ struct GI {
 
 } // namespace
 
-extern "C" {
-
 /* Returns 0 on success, 1 if the iteration limit was hit, 2 if C is not positive definite,
  * 3 if the constraints are inconsistent.  x[n]; u[m] multipliers (0 for inactive rows);
- * iterations (may be NULL) counts constraint additions + removals. */
-int oracle_qp_solve(int n, int m, const double *C, const double *dvec, const double *A, const double *b,
-                    double *x_out, double *u_out, int *iterations)
+ * iterations (may be NULL) counts constraint additions + removals.  real: the arithmetic (double, or long double for the
+ * extended-precision oracle of badly conditioned problems). */
+template <typename real>
+int qp_solve_t(int n, int m, const double *C, const double *dvec, const double *A, const double *b,
+               double *x_out, double *u_out, int *iterations)
 {
-  GI g;
+  GI<real> g;
   g.n = n; g.m = m;
   g.J.assign((size_t)n * n, 0.0); g.R.assign((size_t)n * n, 0.0);
   g.x.assign(n, 0.0); g.u.assign(n + 1, 0.0); g.s.assign(m, 0.0);
@@ -130,14 +132,14 @@ int oracle_qp_solve(int n, int m, const double *C, const double *dvec, const dou
   g.act.assign(n + 1, -1); g.is_act.assign(m, 0);
 
   /* Cholesky C = L L' */
-  std::vector<double> L((size_t)n * n, 0.0);
+  std::vector<real> L((size_t)n * n, 0.0);
   for (int j = 0; j < n; ++j) {
-    double t = C[(size_t)j * n + j];
+    real t = C[(size_t)j * n + j];
     for (int k = 0; k < j; ++k) t -= L[(size_t)j * n + k] * L[(size_t)j * n + k];
     if (!(t > 0.0)) return 2;
     L[(size_t)j * n + j] = std::sqrt(t);
     for (int i = j + 1; i < n; ++i) {
-      double v = C[(size_t)i * n + j];
+      real v = C[(size_t)i * n + j];
       for (int k = 0; k < j; ++k) v -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
       L[(size_t)i * n + j] = v / L[(size_t)j * n + j];
     }
@@ -145,66 +147,70 @@ int oracle_qp_solve(int n, int m, const double *C, const double *dvec, const dou
   /* J = L^-T : column j of J solves L' J(:,j) = e_j */
   for (int j = 0; j < n; ++j) {
     for (int i = n - 1; i >= 0; --i) {
-      double t = (i == j) ? 1.0 : 0.0;
+      real t = (i == j) ? 1.0 : 0.0;
       for (int k = i + 1; k < n; ++k) t -= L[(size_t)k * n + i] * g.Jm(k, j);
       g.Jm(i, j) = t / L[(size_t)i * n + i];
     }
   }
   /* x = -C^-1 d = -J J' d */
   {
-    std::vector<double> t(n);
+    std::vector<real> t(n);
     for (int j = 0; j < n; ++j) {
-      double v = 0;
+      real v = 0;
       for (int i = 0; i < n; ++i) v += g.Jm(i, j) * dvec[i];
       t[j] = v;
     }
     for (int i = 0; i < n; ++i) {
-      double v = 0;
+      real v = 0;
       for (int j = 0; j < n; ++j) v += g.Jm(i, j) * t[j];
       g.x[i] = -v;
     }
   }
-  double scale = 0.0;
+  real scale = 0.0;
+  std::vector<real> rown(m, 1.0);
   for (int i = 0; i < m; ++i) {
-    double nr = 0;
+    real nr = 0;
     for (int j = 0; j < n; ++j) nr += A[(size_t)i * n + j] * A[(size_t)i * n + j];
-    scale = std::fmax(scale, std::sqrt(nr));
+    scale = std::max(scale, std::sqrt(nr));
+    rown[i] = nr > 0 ? std::sqrt(nr) : real(1.0);
   }
-  const double tol = 1e-12 * (scale > 0 ? scale : 1.0);
+  const real tol = (sizeof(real) > 8 ? 1e-15 : 1e-12) * (scale > 0 ? scale : real(1.0));
   int iters = 0;
   const int maxit = 40 * (m + n);
-  const double inf = std::numeric_limits<double>::infinity();
+  const real inf = std::numeric_limits<real>::infinity();
+  std::vector<real> apv(n);
 
   for (;;) {
     /* most violated constraint */
     int p = -1;
-    double smin = -tol;
+    real smin = -tol;
     for (int i = 0; i < m; ++i) {
       if (g.is_act[i]) continue;
-      double v = b[i];
-      for (int j = 0; j < n; ++j) v += A[(size_t)i * n + j] * g.x[j];
+      real v = b[i];
+      for (int j = 0; j < n; ++j) v += (real)A[(size_t)i * n + j] * g.x[j];
       g.s[i] = v;
       if (v < smin) { smin = v; p = i; }
     }
     if (p < 0) break;
-    const double *ap = A + (size_t)p * n;
-    double up = 0.0;
-    double sp = g.s[p];
+    for (int j = 0; j < n; ++j) apv[j] = A[(size_t)p * n + j];
+    const real *ap = apv.data();
+    real up = 0.0;
+    real sp = g.s[p];
     for (;;) {
       if (++iters > maxit) return 1;
       g.compute_d(ap);
       g.update_z();
       g.update_r();
-      double t1 = inf; int l = -1;
+      real t1 = inf; int l = -1;
       for (int k = 0; k < g.q; ++k)
         if (g.r[k] > 0.0) {
-          double v = g.u[k] / g.r[k];
+          real v = g.u[k] / g.r[k];
           if (v < t1) { t1 = v; l = k; }
         }
-      double zz = 0, za = 0;
+      real zz = 0, za = 0;
       for (int i = 0; i < n; ++i) { zz += g.z[i] * g.z[i]; za += g.z[i] * ap[i]; }
-      double t2 = (zz <= 1e-28 * scale * scale || za <= 0.0) ? inf : -sp / za;
-      double t = std::fmin(t1, t2);
+      real t2 = (zz <= (sizeof(real) > 8 ? 1e-34 : 1e-28) * scale * scale || za <= 0.0) ? inf : -sp / za;
+      real t = std::min(t1, t2);
       if (t == inf) return 3;
       if (t2 == inf) { /* dual step only */
         for (int k = 0; k < g.q; ++k) g.u[k] -= t * g.r[k];
@@ -231,13 +237,28 @@ int oracle_qp_solve(int n, int m, const double *C, const double *dvec, const dou
       for (int j = 0; j < n; ++j) sp += ap[j] * g.x[j];
     }
   }
-  std::memcpy(x_out, g.x.data(), sizeof(double) * n);
+  for (int i = 0; i < n; ++i) x_out[i] = (double)g.x[i];
   if (u_out) {
     for (int i = 0; i < m; ++i) u_out[i] = 0.0;
-    for (int k = 0; k < g.q; ++k) u_out[g.act[k]] = g.u[k];
+    for (int k = 0; k < g.q; ++k) u_out[g.act[k]] = (double)g.u[k];
   }
   if (iterations) *iterations = iters;
   return 0;
+}
+
+extern "C" {
+
+int oracle_qp_solve(int n, int m, const double *C, const double *dvec, const double *A, const double *b,
+                    double *x_out, double *u_out, int *iterations)
+{
+  return qp_solve_t<double>(n, m, C, dvec, A, b, x_out, u_out, iterations);
+}
+/* the same method in x87 extended precision (64-bit mantissa): the reference point for problems whose conditioning
+ * (cond(C) ~ 5e11 for Wieber2006) puts a double-precision solution - the reference's ql0001_ included - 1e-4 off */
+int oracle_qp_solve_ld(int n, int m, const double *C, const double *dvec, const double *A, const double *b,
+                       double *x_out, double *u_out, int *iterations)
+{
+  return qp_solve_t<long double>(n, m, C, dvec, A, b, x_out, u_out, iterations);
 }
 
 } /* extern "C" */

@@ -171,6 +171,25 @@ template <typename T> vector<T> prod(const matrix<T> &A, const vector<T> &x)
   return y;
 }
 
+/* compound assignments and vector sums used by ZMPQPWithConstraint.cpp (:968, :1064, :1252): element by element */
+template <typename T> matrix<T> &operator+=(matrix<T> &A, const matrix<T> &B)
+{
+  for (std::size_t i = 0; i < A.size1(); ++i)
+    for (std::size_t j = 0; j < A.size2(); ++j) A(i, j) += B(i, j);
+  return A;
+}
+template <typename T> vector<T> &operator-=(vector<T> &a, const vector<T> &b)
+{
+  for (std::size_t i = 0; i < a.size(); ++i) a(i) -= b(i);
+  return a;
+}
+template <typename T> vector<T> operator+(const vector<T> &a, const vector<T> &b)
+{
+  vector<T> r(a.size());
+  for (std::size_t i = 0; i < a.size(); ++i) r(i) = a(i) + b(i);
+  return r;
+}
+
 /* jrl-mal's "small" fixed-size types (matrixabstractlayersmall*.hh): a 3-vector and a 4x4 matrix, only element access
  * and assignment are used by the sources compiled here (ZMPPreviewControlWithMultiBodyZMP.cpp) */
 template <typename T> struct vec3 {
@@ -206,6 +225,7 @@ template <typename T> struct mat4 {
 #define MAL_MATRIX_NB_ROWS(name) name.size1()
 #define MAL_MATRIX_NB_COLS(name) name.size2()
 #define MAL_RET_A_by_B(A, B) oracle_mal::prod(A, B)
+#define MAL_C_eq_A_by_B(C, A, B) (C) = oracle_mal::prod(A, B)   /* uBLAS: C = prod(A, B) through a temporary (aliasing safe) */
 #define MAL_MATRIX_TYPE(type) oracle_mal::matrix<type>
 #define MAL_MATRIX_FILL(name, v) name.fill(v)
 #define MAL_VECTOR_FILL(name, v) name.fill(v)
