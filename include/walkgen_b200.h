@@ -467,8 +467,8 @@ int wg_optcholesky_full_batch(wg_ctx *ctx, int mem, int B, int n, const double *
  * Arrays are laid out as ql0001_ wants them: C column-major with leading dimension nmax, A column-major with leading
  * dimension mmax (row j of QP k at A + k a_stride + j, its element i at + i mmax), multipliers u = m rows, then n lower
  * bounds, then n upper bounds (qld.cpp:520-536).  One CTA per QP; dual active-set method in range-space form (qld.cu).
- * ifail: 0 ok; 1 iteration limit 40 (m + n) (QLD :459); 2 C not positive definite (QLD would boost the diagonal, :809-854:
- * this solver refuses); 3 more than n active rows; 5 bad dimensions; 10 + j: constraint j (1-based) cannot be satisfied
+ * ifail: 0 ok; 1 iteration limit 40 (m + n) (QLD :459); 2 C not positive definite and eps = 0 (with eps > 0 the diagonal is
+ * boosted as QLD does, :809-918); 3 more than n active rows; 5 bad dimensions; 10 + j: constraint j (1-based) cannot be satisfied
  * together with the active ones (QLD's ifail > 10).  On failure x is the unconstrained minimiser.
  * ---------------------------------------------------------------------------------------------- */
 #define WG_QLD_MAX_N 160
@@ -492,6 +492,9 @@ typedef struct wg_qld_batch {
   long long u_stride;         /* >= mmax (+ 2 n when bounds are given)                                           */
   int32_t *ifail;             /* [B]           out                                                               */
   int32_t *iterations;        /* [B]           out (active-set changes), or NULL                                 */
+  double eps;                 /* per-QP Hessians: > 0 applies QLD's diagonal boost rule with vsmall = eps (the accuracy
+                                 argument of ql0001_; see wg_qld_set_shared_hessian) instead of refusing a Hessian whose
+                                 pivots fall below it; 0: factorise C as given, ifail 2 when it is not positive definite */
 } wg_qld_batch;
 
 /* The Hessian shared by every QP of later wg_qld_solve_batch(shared_hessian = 1) calls (both reference generators have a

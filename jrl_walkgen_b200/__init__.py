@@ -248,7 +248,7 @@ class Context:
         self._check(self.lib.wg_qld_set_shared_hessian(self.h, n, n, Cmat.ctypes.data, float(eps)))
         return self.lib.wg_qld_shared_boost(self.h)
 
-    def qld_solve(self, d, A, b, m, C_=None, me=None, xl=None, xu=None, want_u=True):
+    def qld_solve(self, d, A, b, m, C_=None, me=None, xl=None, xu=None, want_u=True, eps=0.0):
         """wg_qld_solve_batch on host arrays.  d [B][n]; A [B][mmax][n] (row r of QP k = A[k, r]; converted here to the
         column-major layout of ql0001_); b [B][mmax]; m [B]; C_ [B][n][n] symmetric, or None for the shared Hessian.
         Returns x [B][n], u [B][mmax (+ 2n)], ifail [B], iterations [B]."""
@@ -262,6 +262,7 @@ class Context:
         q = _capi.QldBatch()
         q.n = n; q.nmax = n; q.mmax = mmax
         q.shared_hessian = 1 if C_ is None else 0
+        q.eps = float(eps)
         keep = [d, Acm, b, m]
         q.m = m.ctypes.data; q.d = d.ctypes.data; q.A = Acm.ctypes.data; q.a_stride = mmax * n
         q.b = b.ctypes.data; q.b_stride = mmax

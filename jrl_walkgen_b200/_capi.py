@@ -87,7 +87,7 @@ class QldBatch(C.Structure):
                 ("m", C.c_void_p), ("me", C.c_void_p), ("C", C.c_void_p), ("d", C.c_void_p), ("A", C.c_void_p),
                 ("a_stride", C.c_longlong), ("b", C.c_void_p), ("b_stride", C.c_longlong), ("xl", C.c_void_p),
                 ("xu", C.c_void_p), ("x", C.c_void_p), ("u", C.c_void_p), ("u_stride", C.c_longlong),
-                ("ifail", C.c_void_p), ("iterations", C.c_void_p)]
+                ("ifail", C.c_void_p), ("iterations", C.c_void_p), ("eps", C.c_double)]
 
 
 class WieberParams(C.Structure):

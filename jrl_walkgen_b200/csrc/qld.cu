@@ -106,40 +106,96 @@ __device__ void block_argmin(double &v, int &idx, double *red, int *redi)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QT)
 qld_factor_kernel(int count, int n, int nmax, const double *__restrict__ C, long long c_stride, double *__restrict__ Sout,
-                  int *__restrict__ fail)
+                  int *__restrict__ fail, double vsmall)
 {
   extern __shared__ double sm[];
-  double *dinv = sm;
-  __shared__ int bad;
+  double *dinv = sm, *wv = sm + n;
+  __shared__ double red[QW];
+  __shared__ int redi[QW];
+  __shared__ int bad, jfail;
+  __shared__ double s_diag;
   const int t = threadIdx.x;
   for (int b = blockIdx.x; b < count; b += gridDim.x) {
     const double *Cb = C + (size_t)b * c_stride;
     double *W = Sout + (size_t)b * n * n;
-    if (t == 0) bad = 0;
-    for (int e = t; e < n * n; e += QT) {
-      const int i = e / n, j = e - i * n;
-      W[e] = (j <= i) ? Cb[(size_t)j * nmax + i] : 0.0;      // lower triangle of the column-major C
-    }
-    __syncthreads();
-    for (int j = 0; j < n; ++j) {
-      if (t == 0) {
-        const double p = W[j * n + j];
-        if (!(p > 0.0)) { bad = 1; W[j * n + j] = 1.0; dinv[j] = 1.0; }
-        else { const double l = sqrt(p); W[j * n + j] = l; dinv[j] = 1.0 / l; }
-      }
-      __syncthreads();
-      const double il = dinv[j];
-      for (int i = j + 1 + t; i < n; i += QT) W[i * n + j] *= il;
-      __syncthreads();
-      // trailing update of the lower triangle: W[i][k] -= W[i][j] W[k][j], j < k <= i
-      const int r = n - 1 - j;
-      for (int e = t; e < r * r; e += QT) {
-        const int ii = e / r, kk = e - ii * r;
-        if (kk <= ii) {
-          const int i = j + 1 + ii, k = j + 1 + kk;
-          W[i * n + k] -= W[i * n + j] * W[k * n + j];
+    // QLD's first estimate of the multiple of I to add (qld.cpp:814-843; see qld_diagonal_boost)
+    double dg = 0.0;
+    if (vsmall > 0.0) {
+      for (int e = t; e < n * n; e += QT) {
+        const int i = e / n, j = e - i * n;
+        const double gii = Cb[(size_t)i * nmax + i];
+        if (j == i) dg = fmax(dg, vsmall - gii);
+        else if (j > i) {
+          const double gjj = Cb[(size_t)j * nmax + j], gij = Cb[(size_t)j * nmax + i];
+          double ga = -fmin(gii, gjj);
+          const double gb = fabs(gii - gjj) + fabs(gij);
+          if (gb > 0.0) ga += gij * gij / gb;
+          dg = fmax(dg, ga);
         }
       }
+      int dummy = 0;
+      double neg = -dg;
+      block_argmin(neg, dummy, red, redi);
+      dg = -neg;
+    }
+    bool boosted = dg > 0.0;
+    if (t == 0) { bad = 0; s_diag = dg; }
+    __syncthreads();
+    for (int pass = 0; pass < 200; ++pass) {
+      if (t == 0) { if (boosted) s_diag = 2.0 * s_diag; jfail = -1; }
+      __syncthreads();
+      const double diag = s_diag;
+      for (int e = t; e < n * n; e += QT) {
+        const int i = e / n, j = e - i * n;
+        W[e] = (j <= i) ? Cb[(size_t)j * nmax + i] + (j == i ? diag : 0.0) : 0.0;      // lower triangle of the column-major C
+      }
+      __syncthreads();
+      for (int j = 0; j < n; ++j) {
+        if (t == 0) {
+          const double p = W[j * n + j];
+          if (vsmall > 0.0 ? (p < vsmall) : !(p > 0.0)) { jfail = j; }
+          else { const double l = sqrt(p); W[j * n + j] = l; dinv[j] = 1.0 / l; }
+        }
+        __syncthreads();
+        if (jfail >= 0) break;
+        const double il = dinv[j];
+        for (int i = j + 1 + t; i < n; i += QT) W[i * n + j] *= il;
+        __syncthreads();
+        // trailing update of the lower triangle: W[i][k] -= W[i][j] W[k][j], j < k <= i
+        const int r = n - 1 - j;
+        for (int e = t; e < r * r; e += QT) {
+          const int ii = e / r, kk = e - ii * r;
+          if (kk <= ii) {
+            const int i = j + 1 + ii, k = j + 1 + kk;
+            W[i * n + k] -= W[i * n + j] * W[k * n + j];
+          }
+        }
+        __syncthreads();
+      }
+      if (jfail < 0) break;
+      if (!(vsmall > 0.0)) {           // no QLD treatment asked for: refuse the Hessian
+        if (t == 0) { bad = 1; }
+        // finish with a harmless factor so that the kernel below reads defined memory
+        for (int e = t; e < n * n; e += QT) { const int i = e / n, j = e - i * n; W[e] = (i == j) ? 1.0 : 0.0; }
+        for (int i = t; i < n; i += QT) dinv[i] = 1.0;
+        __syncthreads();
+        break;
+      }
+      // qld.cpp:893-918: w solves R w = e_j-like with the part of the factor found so far; diag += vsmall - pivot / |w|^2
+      if (t == 0) {
+        const int j = jfail;
+        const double temp = W[j * n + j];
+        wv[j] = 1.0;
+        double sumx = 1.0;
+        for (int k = j - 1; k >= 0; --k) {
+          double sum = 0.0;
+          for (int i = k + 1; i <= j; ++i) sum -= W[i * n + k] * wv[i];     // R(k, i) = L(i, k)
+          wv[k] = sum / W[k * n + k];
+          sumx += wv[k] * wv[k];
+        }
+        s_diag = s_diag + vsmall - temp / sumx;
+      }
+      boosted = true;
       __syncthreads();
     }
     // X = L^-1, column c by forward substitution, written transposed into the strict upper triangle: X[i][c] at W[c][i]
@@ -496,10 +552,11 @@ size_t qld_smem_bytes(int n, int mmax, int qcap, bool bounds)
   return (s + 15) & ~(size_t)15;
 }
 
-int hinv_launch(wg_ctx *ctx, int count, int n, int nmax, const double *d_C, long long c_stride, double *d_hinv, int *d_fail)
+int hinv_launch(wg_ctx *ctx, int count, int n, int nmax, const double *d_C, long long c_stride, double *d_hinv, int *d_fail,
+                double vsmall)
 {
   const int blocks = std::max(1, std::min(count, ctx->sm_count * 2));
-  qld_factor_kernel<<<blocks, QT, sizeof(double) * n, ctx->stream>>>(count, n, nmax, d_C, c_stride, d_hinv, d_fail);
+  qld_factor_kernel<<<blocks, QT, sizeof(double) * 2 * n, ctx->stream>>>(count, n, nmax, d_C, c_stride, d_hinv, d_fail, vsmall);
   WG_LAUNCHED(ctx);
   return WG_OK;
 }
@@ -715,7 +772,7 @@ int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q)
   } else {
     if ((rc = ensure(ctx, reinterpret_cast<void **>(&st->d_hinv), &st->cap_hinv, sizeof(double) * nb * n * n)) != WG_OK) return rc;
     if ((rc = ensure(ctx, reinterpret_cast<void **>(&st->d_fail), &st->cap_fail, sizeof(int) * nb)) != WG_OK) return rc;
-    if ((rc = hinv_launch(ctx, B, n, nmax, d.C, (long long)nmax * n, st->d_hinv, st->d_fail)) != WG_OK) return rc;
+    if ((rc = hinv_launch(ctx, B, n, nmax, d.C, (long long)nmax * n, st->d_hinv, st->d_fail, q->eps)) != WG_OK) return rc;
     a.S = st->d_hinv; a.h_stride = (long long)n * n; a.hfail = st->d_fail;
     a.C = d.C; a.c_stride = (long long)nmax * n;
   }

@@ -188,3 +188,56 @@ def test_gpu_dense_qp_failure_codes(ctx):
     assert ifail[0] > 10 and ifail[1] == 2 and ifail[2] == 5
     xr, ur, fr = ref_qld(Cm, d[0], A[0, :2], b[0, :2])
     assert fr > 10
+
+
+@pytest.mark.gpu
+def test_gpu_dense_qp_on_wieber_qps_reproduces_ql0001_regularisation(ctx):
+    """QPs of the Wieber2006 generator (cond(C) = 5e11): with eps = 1e-8 - QLD's diagonal boost, on the host for a shared
+    Hessian and inside qld_factor_kernel for per-QP Hessians - the solver reproduces the reference's ql0001_; with eps = 0 it
+    returns the minimiser of the QP as stated, whose objective is lower than that of ql0001_'s answer."""
+    import ctypes as C
+    import dimitrov_oracle as do
+    import wieber_oracle as wo
+    from test_wieber import short_walk
+    N, T = 75, 0.02
+    Cm, OptB, OptC = wo.constants()
+    w = short_walk(4)
+    L, R, st, t, z = wo.inputs(w)
+    lci = do.fcals(w["left"], w["right"], w["types"][:, 1])
+    o = ol.oracle()
+    o.oracle_wieber_build.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_double, D, D, D, C.POINTER(C.c_int)]
+    probs = []
+    rng = np.random.default_rng(1)
+    for li in (100, 120, 150, 200, 260, 330):
+        xk = rng.normal(scale=[0.02, 0.05, 0.2, 0.02, 0.05, 0.2])
+        Px = np.zeros(8 * N + 1); Pu = np.zeros((8 * N + 1) * 2 * N); nb = C.c_int(0)
+        assert o.oracle_wieber_build(N, T, li * T, len(lci), lci.ctypes.data, 0.80, ol.dptr(xk), ol.dptr(Px), ol.dptr(Pu), C.byref(nb)) == 0
+        m = nb.value
+        A = Pu[:(m + 1) * 2 * N].reshape(2 * N, m + 1).T[:m].copy(); b = Px[:m].copy()
+        zr = np.concatenate([z[li * 4 + 4 * np.arange(N), 0], z[li * 4 + 4 * np.arange(N), 1]])
+        probs.append((OptB @ xk - OptC @ zr, A, b))
+    mmax = max(len(p[2]) for p in probs) + 1
+    B = len(probs)
+    ds = np.stack([p[0] for p in probs]); As = np.zeros((B, mmax, 2 * N)); bs = np.zeros((B, mmax))
+    for k, p in enumerate(probs):
+        As[k, :len(p[2])] = p[1]; bs[k, :len(p[2])] = p[2]
+    ms = np.array([len(p[2]) for p in probs])
+    boost = ctx.qld_set_shared_hessian(Cm, eps=1e-8)
+    assert 1e-8 < boost < 1e-7
+    shared = ctx.qld_solve(ds, As, bs, ms)
+    per_qp = ctx.qld_solve(ds, As, bs, ms, C_=np.stack([Cm] * B), eps=1e-8)
+    ctx.qld_set_shared_hessian(Cm, eps=0.0)
+    exact = ctx.qld_solve(ds, As, bs, ms)
+    f = lambda x, d: 0.5 * x @ (Cm @ x) + d @ x
+    for k, (d, A, b) in enumerate(probs):
+        xr, ur, fr = ref_qld(Cm, d, A, b)
+        assert fr == 0 and shared[2][k] == 0 and per_qp[2][k] == 0 and exact[2][k] == 0
+        sc = max(1.0, np.abs(xr).max())
+        assert np.abs(shared[0][k] - xr).max() < 1e-6 * sc, (k, np.abs(shared[0][k] - xr).max())
+        assert np.abs(per_qp[0][k] - xr).max() < 1e-5 * sc, (k, np.abs(per_qp[0][k] - xr).max())
+        act = lambda u: set(np.nonzero(u[:len(b)] > 1e-7 * max(ur.max(), 1e-12))[0])
+        assert act(shared[1][k]) == act(ur) == act(per_qp[1][k]), k
+        assert (A @ exact[0][k] + b).min() > -1e-10
+        assert f(exact[0][k], d) <= f(xr, d) + 1e-9 * abs(f(xr, d))
+    print(f"Wieber QPs: |x - x_ql0001| shared {max(np.abs(shared[0][k] - ref_qld(Cm, *probs[k])[0]).max() for k in range(B)):.2e}, "
+          f"per-QP factor {max(np.abs(per_qp[0][k] - ref_qld(Cm, *probs[k])[0]).max() for k in range(B)):.2e}; iterations {shared[3]}")
