@@ -241,3 +241,46 @@ def test_gpu_dense_qp_on_wieber_qps_reproduces_ql0001_regularisation(ctx):
         assert f(exact[0][k], d) <= f(xr, d) + 1e-9 * abs(f(xr, d))
     print(f"Wieber QPs: |x - x_ql0001| shared {max(np.abs(shared[0][k] - ref_qld(Cm, *probs[k])[0]).max() for k in range(B)):.2e}, "
           f"per-QP factor {max(np.abs(per_qp[0][k] - ref_qld(Cm, *probs[k])[0]).max() for k in range(B)):.2e}; iterations {shared[3]}")
+
+
+@pytest.mark.gpu
+def test_gpu_dense_qp_covers_the_qldandlq_call_of_the_dimitrov_generator(ctx):
+    """ZMPConstrainedQPFastFormulation.cpp:1297-1305: in QLDANDLQ mode the generator hands ql0001_ the SAME per-period problem the
+    PLDP branch solves (Hessian = identity in the variables L_Q' u, D, the dense (m + 1) x 32 matrix DPu, DPx).  The mode is
+    fixed to PLDP in the constructor (:55) and has no setter, so the branch is unreachable in the reference; the call itself is
+    covered here: the period QPs of TestKajita2003's straight walk through wg_qld_solve_batch against ql0001_, and against the
+    PLDP solution of the same problem (PLDP never drops a row: its objective can only be higher or equal)."""
+    import dimitrov_oracle as do
+    import pldp_oracle as po
+    import zmpdisc_oracle as zo
+    w = zo.run(zo.default_params(), zo.profile_steps("StraightWalking"))
+    lci = do.fcals(w["left"], w["right"], w["types"][:, 1])
+    K = do.Constants()
+    N = 16
+    rng = np.random.default_rng(2)
+    probs = []
+    for k in range(24):
+        t0 = 0.1 * int(rng.integers(5, 150))
+        xk = rng.normal(scale=[0.03, 0.1, 0.3, 0.03, 0.1, 0.3])
+        xk[0] += 0.2 * t0 / 3.0
+        pr = do.build_constraints(K, lci, t0, xk)
+        m = pr["m"]
+        A = pr["DPu"].reshape(2 * N, m + 1).T[:m].copy()
+        probs.append((pr["D"].copy(), A, pr["DPx"].copy()))
+    mmax = max(len(p[2]) for p in probs) + 1
+    B = len(probs)
+    ds = np.stack([p[0] for p in probs]); As = np.zeros((B, mmax, 2 * N)); bs = np.zeros((B, mmax))
+    for k, p in enumerate(probs):
+        As[k, :len(p[2])] = p[1]; bs[k, :len(p[2])] = p[2]
+    ctx.qld_set_shared_hessian(np.eye(2 * N), eps=1e-8)
+    x, u, ifail, it = ctx.qld_solve(ds, As, bs, np.array([len(p[2]) for p in probs]))
+    feasible = 0
+    for k, (d, A, b) in enumerate(probs):
+        xr, ur, fr = ref_qld(np.eye(2 * N), d, A, b)
+        if fr != 0:
+            assert ifail[k] != 0, k                  # random states can make a period infeasible: both must say so
+            continue
+        feasible += 1
+        compare((x, u, ifail, it), k, np.eye(2 * N), d, A, b)
+    assert feasible >= B // 2
+    print(f"Dimitrov QLDANDLQ call: {feasible} feasible period QPs identical to ql0001_ (active sets, x, KKT), iterations mean {it.mean():.1f}")
