@@ -580,6 +580,43 @@ class ZMPConstrainedQPFastFormulation : public ZMPRefTrajectoryGeneration {   /*
   int m_Status, m_Done;
 };
 
+/* src/ZMPRefTrajectoryGeneration/ZMPQPWithConstraint.hh: the Wieber2006 generator (the whole walk off line, as in the
+ * reference: ZMPDiscretization, then one 150-variable QP per 20 ms).  ":setpbwconstraint XY x y | T t | N n" as :1389-1414. */
+class ZMPQPWithConstraint : public ZMPRefTrajectoryGeneration {
+ public:
+  ZMPQPWithConstraint(SimplePluginManager *lSPM, std::string DataFile, CjrlHumanoidDynamicRobot *aHS = 0);
+  void GetZMPDiscretization(std::deque<ZMPPosition> &ZMPPositions, std::deque<COMState> &COMStates,
+                            std::deque<RelativeFootPosition> &RelativeFootPositions,
+                            std::deque<FootAbsolutePosition> &LeftFootAbsolutePositions,
+                            std::deque<FootAbsolutePosition> &RightFootAbsolutePositions, double Xmax,
+                            COMState &lStartingCOMState, MAL_S3_VECTOR_TYPE(double) &lStartingZMPPosition,
+                            FootAbsolutePosition &InitLeftFootAbsolutePosition,
+                            FootAbsolutePosition &InitRightFootAbsolutePosition);
+  void CallMethod(std::string &Method, std::istringstream &strm);
+  /* 0, or the wg_wieber_run_batch status where the reference prints and returns -1 */
+  int LastStatus() const { return m_Status; }
+  int PeriodsDone() const { return m_Done; }
+  /* 0: solve the QPs as stated instead of reproducing ql0001_'s regularised Hessian (wg_wieber_params::qld_eps) */
+  void SetQLDEps(double eps) { m_Par.qld_eps = eps; }
+  /* "To be implemented" in the reference as well (:1417-1474) */
+  int InitOnLine(std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
+                 std::deque<FootAbsolutePosition> &, FootAbsolutePosition &, FootAbsolutePosition &,
+                 std::deque<RelativeFootPosition> &, COMState &, MAL_S3_VECTOR_TYPE(double) &) { return 0; }
+  void OnLineAddFoot(RelativeFootPosition &, std::deque<ZMPPosition> &, std::deque<COMState> &,
+                     std::deque<FootAbsolutePosition> &, std::deque<FootAbsolutePosition> &, bool) {}
+  void OnLine(double, std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
+              std::deque<FootAbsolutePosition> &) {}
+  void EndPhaseOfTheWalking(std::deque<ZMPPosition> &, std::deque<COMState> &, std::deque<FootAbsolutePosition> &,
+                            std::deque<FootAbsolutePosition> &) {}
+  int OnLineFootChange(double, FootAbsolutePosition &, std::deque<ZMPPosition> &, std::deque<COMState> &,
+                       std::deque<FootAbsolutePosition> &, std::deque<FootAbsolutePosition> &, StepStackHandler *) { return -1; }
+  int ReturnOptimalTimeToRegenerateAStep() { return 0; }
+ private:
+  wg_wieber_params m_Par;
+  wg_zmpdisc_params m_Zd;
+  int m_Status, m_Done;
+};
+
 /* The PGI facade (include/jrl/walkgen/patterngeneratorinterface.hh:55-306) for the accelerated paths: command bus + the
  * 5 ms tick, for the Herdt on-line generator and for the Kajita off-line / on-line step sequences.  Whole-body inverse
  * kinematics and the multibody second preview stage are outside the accelerated path: as with the
@@ -754,5 +791,12 @@ class ZMPPreviewControlWithMultiBodyZMP : public SimplePlugin {
 PatternGeneratorInterface *patternGeneratorInterfaceFactory(CjrlHumanoidDynamicRobot *aHDR);
 
 }  // namespace PatternGeneratorJRL
+
+/* src/Mathematics/qld.hh:27-31, argument for argument (C++ linkage as in the reference): one dense QP through
+ * wg_qld_solve_batch on the process-wide context.  war / iwar are not used (iwar[0] = 0, "C holds its Cholesky factor", is
+ * not supported: ifail = 5); eps1 plays QLD's role for the Hessian (vsmall of the diagonal boost, see walkgen_b200.h). */
+int ql0001_(int *m, int *me, int *mmax, int *n, int *nmax, int *mnn, double *c, double *d, double *a, double *b, double *xl,
+            double *xu, double *x, double *u, int *iout, int *ifail, int *iprint, double *war, int *lwar, int *iwar,
+            int *liwar, double *eps1);
 
 #endif

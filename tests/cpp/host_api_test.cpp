@@ -488,6 +488,48 @@ static int test_twostage(const char *in, const char *out, int max_ticks)
   return worst < 1e-9 ? 0 : 5;
 }
 
+// ---- ZMPQPWithConstraint (Wieber2006) through its class interface, and ql0001_ with the reference's signature ---------
+static int test_wieber(const char *out)
+{
+  SimplePluginManager spm;
+  CjrlHumanoidDynamicRobot robot(0.25, 0.14, 0.105);
+  ZMPQPWithConstraint gen(&spm, "", &robot);
+  { std::string m(":setpbwconstraint"); std::istringstream s("XY 0.04 0.04"); gen.CallMethod(m, s); }
+  gen.SetSamplingPeriod(0.005); gen.SetTSingleSupport(0.78); gen.SetTDoubleSupport(0.02);
+  { std::string m(":stepheight"); std::istringstream s("0.07"); gen.CallMethod(m, s); }
+  std::deque<RelativeFootPosition> rel;
+  const double seq[6][3] = {{0.0, -0.095, 0.0}, {0.2, 0.19, 0.0}, {0.2, -0.19, 0.0}, {0.2, 0.19, 0.0}, {0.2, -0.19, 0.0}, {0.0, 0.19, 0.0}};
+  for (int i = 0; i < 6; ++i) {
+    RelativeFootPosition r; std::memset(&r, 0, sizeof r);
+    r.sx = seq[i][0]; r.sy = seq[i][1]; r.theta = seq[i][2]; r.SStime = 0.78; r.DStime = 0.02; r.stepType = 1;
+    rel.push_back(r);
+  }
+  std::deque<ZMPPosition> zmp; std::deque<COMState> com; std::deque<FootAbsolutePosition> lf, rf;
+  COMState start; S3Vector zstart;
+  FootAbsolutePosition il, ir; std::memset(&il, 0, sizeof il); std::memset(&ir, 0, sizeof ir);
+  il.x = 0.00949035; il.y = 0.095; ir.x = 0.00949035; ir.y = -0.095;
+  gen.GetZMPDiscretization(zmp, com, rel, lf, rf, 0.0, start, zstart, il, ir);
+  if (gen.LastStatus() != 0 || gen.PeriodsDone() < 100) { std::cerr << "status " << gen.LastStatus() << " periods " << gen.PeriodsDone() << std::endl; return 2; }
+  // a small QP through ql0001_: min 1/2 |x|^2 - (1,1)x  s.t. x0 + x1 <= 1  ->  x = (0.5, 0.5), u = 0.5
+  int m = 1, me = 0, mmax = 2, n = 2, nmax = 2, mnn = 5, iout = 0, ifail = -1, iprint = 0, lwar = 100, liwar = 10;
+  double c[4] = {1, 0, 0, 1}, d[2] = {-1, -1}, a[4] = {-1, 0, -1, 0}, b[2] = {1, 0}, xl[2] = {-1e8, -1e8}, xu[2] = {1e8, 1e8};
+  double x[2] = {0, 0}, u[5] = {0}, war[100], eps = 1e-8;
+  int iwar[10] = {1};
+  ql0001_(&m, &me, &mmax, &n, &nmax, &mnn, c, d, a, b, xl, xu, x, u, &iout, &ifail, &iprint, war, &lwar, iwar, &liwar, &eps);
+  if (ifail != 0 || fabs(x[0] - 0.5) > 1e-12 || fabs(x[1] - 0.5) > 1e-12 || fabs(u[0] - 0.5) > 1e-12) {
+    std::cerr << "ql0001_: ifail " << ifail << " x " << x[0] << " " << x[1] << " u " << u[0] << std::endl; return 3;
+  }
+  std::ofstream f(out, std::ios::binary);
+  const double hdr[2] = {(double)com.size(), (double)gen.PeriodsDone()};
+  f.write(reinterpret_cast<const char *>(hdr), sizeof hdr);
+  for (size_t i = 0; i < com.size(); ++i) {
+    const double r[8] = {com[i].x[0], com[i].x[1], com[i].x[2], com[i].y[0], com[i].y[1], com[i].y[2], zmp[i].px, zmp[i].py};
+    f.write(reinterpret_cast<const char *>(r), sizeof r);
+  }
+  std::cout << "wieber: " << com.size() << " samples, " << gen.PeriodsDone() << " QP periods; ql0001_ ok" << std::endl;
+  return 0;
+}
+
 int main(int argc, char **argv)
 {
   try {
@@ -497,6 +539,7 @@ int main(int argc, char **argv)
     if (what == "preview" && argc > 2) return test_preview(argv[2]);
     if (what == "kajita2003" && argc > 3) return test_kajita2003(argv[2], argv[3]);
     if (what == "preview1d" && argc > 4) return test_preview1d(argv[2], argv[3], argv[4]);
+    if (what == "wieber" && argc > 2) return test_wieber(argv[2]);
     if (what == "twostage" && argc > 4) return test_twostage(argv[2], argv[3], atoi(argv[4]));
     if (what == "pldp" && argc > 3) return test_pldp(argv[2], argv[3]);
     if (what == "dimitrov" && argc > 2) return test_dimitrov(argv[2], argc > 3 && std::string(argv[3]) == "robust");

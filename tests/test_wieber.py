@@ -132,3 +132,26 @@ def test_reference_qld_regularises_the_hessian_and_the_rule_is_restated():
     assert gap > 1e-3
     print(f"QLD adds {boost:.3e} I; reference vs exact solve of the regularised QP: ZMP {np.abs(zmp_q[:n, :2] - zmp_b[:n, :2]).max():.1e} m; "
           f"vs the QP as stated: {gap:.1e} m")
+
+
+@pytest.mark.gpu
+def test_cpp_class_mirror_zmpqpwithconstraint_and_ql0001(ref_gen, tmp_path):
+    """ZMPQPWithConstraint::GetZMPDiscretization (":setpbwconstraint", the ZMPRefTrajectoryGeneration commands) and ql0001_ with
+    the reference's signature, through the C++ class mirror (tests/cpp/host_api_test.cpp): CoM / ZMP of the whole walk against
+    the reference object within 1e-6 m."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "tests", "cpp")], check=True)
+    out = tmp_path / "wieber.bin"
+    r = subprocess.run([os.path.join(root, "tests", "cpp", "host_api_test"), "wieber", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out)
+    n, k = int(raw[0]), int(raw[1])
+    rows = raw[2:].reshape(n, 8)
+    w = short_walk(4)
+    rc, com_r, zmp_r = ref_gen.run(w)
+    assert rc == 0 and len(com_r) == n
+    e = max(np.abs(rows[:4 * k, :6] - com_r[:4 * k, :6]).max(), np.abs(rows[:, 6:] - zmp_r[:, :2]).max())
+    print(r.stdout.strip(), f"; vs reference object {e:.2e} m")
+    assert e < 1e-6
