@@ -773,6 +773,108 @@ def dimitrov_leg(ctx, wg, args, rank, want_cpu):
     return res, kern
 
 
+def _cpu_wieber_worker(args):
+    import wieber_oracle as wo
+    import zmpdisc_oracle as zo
+    walks, feet, seconds = args
+    zp = zo.default_params()
+    periods = 0
+    t0 = time.perf_counter()
+    while True:
+        for st, f in zip(walks, feet):
+            w = zo.run(zp, st.astype(zo.REL_STEP_DTYPE), f)
+            budget = max(8, int((seconds - (time.perf_counter() - t0)) / 0.004))      # ~4 ms per QP: stop inside a walk
+            k, _, _, _ = wo.run(w, max_periods=budget)
+            periods += max(int(k), 0)
+            if time.perf_counter() - t0 >= seconds:
+                return periods, time.perf_counter() - t0
+
+
+def cpu_wieber_rate(off, steps, feet, seconds=5.0, procs=None):
+    """The oracle chain of the Wieber2006 generator (bitwise the reference's ZMPQPWithConstraint object code, tests/test_wieber.py)
+    with the reference's own ql0001_ object code as the solver, one process per core (QLD is not re-entrant)."""
+    import multiprocessing as mp
+    procs = procs or host_cores()
+    B = len(off) - 1
+    jobs = []
+    for i in range(procs):
+        idx = [(i * 4 + k) % B for k in range(4)]
+        jobs.append(([steps[off[b]:off[b + 1]].copy() for b in idx], [feet[b].copy() for b in idx], seconds))
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_cpu_wieber_worker, jobs)
+    total = sum(r[0] for r in res); wall = max(r[1] for r in res)
+    return {"value": total / wall, "unit": "QP periods/s", "cores": procs, "kind": "reference",
+            "sample": f"{procs} processes, walks of the batch for {seconds:.0f} s ({total} QPs of n = 150, m = 300..304): oracle "
+                      "assembly (bitwise the reference object) + the reference's own ql0001_ object code",
+            "us_per_qp_per_core": 1e6 * wall * procs / max(1, total)}
+
+
+def wieber_leg(ctx, wg, args, rank, want_cpu, hbm_peak):
+    """BASELINE configs[3] names 'Dimitrov ZMPQPWithConstraint ...': ZMPQPWithConstraint is the Wieber2006 generator (SURVEY 8f
+    rank 3).  The straight / arc walks of configs[1] through wg_wieber_run_batch: one dense QP (n = 150, m = 300..304) per 20 ms."""
+    from jrl_walkgen_b200 import workloads
+    B = args.wieber_walks
+    off, steps, feet = workloads.kajita_steps_batch(B, seed=3000 + 1000 * rank)
+    ctx.wieber_set_params()
+    plan = ctx.kajita_plan(off, steps, feet)
+    n = plan.total_samples
+    dcom = ctx.alloc(n * 48); dzmp = ctx.alloc(n * 16)
+    dstat = ctx.alloc(B * 4); ddone = ctx.alloc(B * 4); dit = ctx.alloc(B * 8)
+
+    def run_dev():
+        ctx._check(ctx.lib.wg_wieber_run_batch(ctx.h, plan.h, wg.WG_MEM_DEVICE, dcom.ptr, dzmp.ptr, None, None, dstat.ptr,
+                                               ddone.ptr, dit.ptr))
+    run_dev()
+    ctx.sync()
+    reps = 2
+    ctx.reset_launches()
+    ctx.prof_begin(20000)
+    ctx.timer_start()
+    for _ in range(reps):
+        run_dev()
+    ms = ctx.timer_stop_ms() / reps
+    prof = ctx.prof_end()
+    launches = ctx.launches // reps
+    status = dstat.download(np.int32, (B,)); done = ddone.download(np.int32, (B,)); its = dit.download(np.int64, (B,))
+    periods = int(done.sum())
+    kern = {}
+    for kid, name in ((10, "qld_kernel"), (11, "wieber_pre_kernel + wieber_post_kernel")):
+        if kid in prof:
+            kern[name] = {"launches": int(prof[kid][0]), "avg_ms": prof[kid][1] / prof[kid][0], "total_ms": prof[kid][1]}
+    com = ctx.pinned((n, 6)); zmp = ctx.pinned((n, 2))
+    hstat = np.zeros(B, dtype=np.int32); hdone = np.zeros(B, dtype=np.int32)
+    te = time.perf_counter()
+    plan.set_steps(steps, feet)
+    ctx._check(ctx.lib.wg_wieber_run_batch(ctx.h, plan.h, wg.WG_MEM_HOST, com.ctypes.data, zmp.ctypes.data, None, None,
+                                           hstat.ctypes.data, hdone.ctypes.data, None))
+    e2e_s = time.perf_counter() - te
+    qld_ms = prof[10][1] / reps if 10 in prof else None
+    # per QP the solver streams the m x n constraint matrix once per violation scan (iterations + 1 scans) plus once for the row norms
+    m_mean, nvar = 300.0, 150
+    scans = float(its.sum()) / max(periods, 1) + 2.0
+    traffic_model = periods * m_mean * nvar * 8.0 * scans
+    res = {"workload": "wieber2006_zmpqpwithconstraint_%d_straight_and_arc_walks_N75_T20ms" % B, "walks": B, "samples": int(n),
+           "qp_periods": periods, "ms_per_pass": ms, "qp_periods_per_s": periods / (ms * 1e-3),
+           "walks_completed": int((status == 0).sum()), "walks_stopped": int((status != 0).sum()),
+           "active_set_changes_per_qp": float(its.sum()) / max(periods, 1), "launches_per_pass": int(launches),
+           "kernels": kern,
+           "roofline": None if qld_ms is None else {
+               "kernel": "qld_kernel", "bound": "hbm", "achieved": traffic_model / (qld_ms * 1e-3) / 1e9, "peak": hbm_peak,
+               "unit": "GB/s", "frac": traffic_model / (qld_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+               "note": "model: every violation scan (active-set changes + 2 per QP) streams the 300 x 150 constraint matrix "
+                       "(360 KB) of its QP; the kernel's other operands (the factor of the shared Hessian, the basis of the "
+                       "active rows) are L2 resident"},
+           "e2e": {"value": periods / e2e_s, "unit": "QP periods/s", "h2d_bytes_per_step": int(steps.nbytes + feet.nbytes),
+                   "d2h_bytes_per_step": int(com.nbytes + zmp.nbytes + hstat.nbytes + hdone.nbytes),
+                   "api": "wg_kajita_plan_set_steps + wg_wieber_run_batch(WG_MEM_HOST): step lists in, CoM/ZMP at 5 ms out"}}
+    if want_cpu:
+        res["cpu_baseline"] = cpu_wieber_rate(off, steps, feet, seconds=max(2.0, args.cpu_seconds / 2))
+    for b in (dcom, dzmp, dstat, ddone, dit):
+        b.free()
+    plan.destroy()
+    return res, kern
+
+
 def run_cuda(args):
     rank, local_rank, world = dist_env()
     import jrl_walkgen_b200 as wg
@@ -925,6 +1027,18 @@ def run_cuda(args):
             dimitrov["qp_periods_per_s"] = p_d / (t_d * 1e-3)
             dimitrov["walks_per_s"] = w_d / (t_d * 1e-3)
             dimitrov["walks"] = int(w_d)
+    wieber = None
+    if not args.no_wieber:
+        try:
+            hbm_pk2 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+        except OSError:
+            hbm_pk2 = 6650.0
+        wieber, wb_kern = wieber_leg(ctx, wg, args, rank, want_cpu=(rank == 0 and world == 1), hbm_peak=hbm_pk2)
+        herdt_kern = dict(herdt_kern or {}, **wb_kern)
+        if dist is not None:
+            (t_w,), (p_w, w_w) = reduce_over_ranks(dist, [wieber["ms_per_pass"]], [float(wieber["qp_periods"]), float(wieber["walks"])])
+            wieber["qp_periods_per_s"] = p_w / (t_w * 1e-3)
+            wieber["walks"] = int(w_w)
     sweep = None
     if not args.no_sweep:
         sweep = sweep_leg(ctx, wg, args, rank, world, dist)
@@ -976,7 +1090,7 @@ def run_cuda(args):
                            "preview_steps_per_pass_per_gpu": steps_per_pass, "passes_per_step": passes,
                            "l2": "inputs+outputs per pass (%.2f GB) exceed the 126 MB L2" % ((n * 80) / 1e9)},
                 "roofline": roof, "kernels": dict(kern, **(herdt_kern or {})), "fp64_peak_tflops_measured": fp64_peak,
-                "herdt": herdt, "pldp": pldp, "kajita_front_end": kajita, "dimitrov_front_to_back": dimitrov, "sweep": sweep,
+                "herdt": herdt, "pldp": pldp, "kajita_front_end": kajita, "dimitrov_front_to_back": dimitrov, "wieber_front_to_back": wieber, "sweep": sweep,
                 "herdt_qp_solves_per_s": None if herdt is None else herdt["qp_solves_per_s"],
                 "herdt_qp_solves_per_s_e2e": None if herdt is None else herdt["e2e"]["value"],
                 "cpu_baseline": cpu,
@@ -1009,6 +1123,8 @@ def main():
     ap.add_argument("--no-kajita", action="store_true")
     ap.add_argument("--dimitrov-walks", type=int, default=4096)
     ap.add_argument("--no-dimitrov", action="store_true")
+    ap.add_argument("--wieber-walks", type=int, default=512)
+    ap.add_argument("--no-wieber", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="(default since round 2; kept for old command lines)")
     ap.add_argument("--no-sweep", action="store_true", help="skip BASELINE configs[4]: 1M MPC instances x 100 periods")
     ap.add_argument("--passes-per-step", type=int, default=72,

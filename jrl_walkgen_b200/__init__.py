@@ -173,7 +173,7 @@ class Context:
         """-> {kernel_id: (launches, total_ms)} for the kernels that ran since prof_begin."""
         self._check(self.lib.wg_prof_end(self.h))
         out = {}
-        for kid in range(10):
+        for kid in range(12):
             n = C.c_longlong(); ms = C.c_double()
             self._check(self.lib.wg_prof_get(self.h, kid, C.byref(n), C.byref(ms)))
             if n.value:

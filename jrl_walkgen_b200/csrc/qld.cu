@@ -216,6 +216,56 @@ qld_factor_kernel(int count, int n, int nmax, const double *__restrict__ C, long
   }
 }
 
+// y = X a through the symmetric storage of X (row i of S is contiguous: S[i n + j] = X[i][j], j <= i): one warp per row, lanes
+// over the columns (coalesced, 5 loads per lane at n = 150 instead of a 150-long dependent chain per thread).
+__device__ __forceinline__ void tri_lower_mv(const double *__restrict__ S, int n, const double *a, double *y, int warp, int lane)
+{
+  for (int i = warp; i < n; i += QW) {
+    const double *row = S + (size_t)i * n;
+    double s = 0.0;
+    for (int j = lane; j <= i; j += 32) s = fma(row[j], a[j], s);
+    s = warp_sum(s);
+    if (lane == 0) y[i] = s;
+  }
+}
+// x = X'v: x_j = sum_{i >= j} X[i][j] v_i = sum_{i >= j} S[j n + i] v_i
+__device__ __forceinline__ void tri_upper_mv(const double *__restrict__ S, int n, const double *v, double *x, int warp, int lane)
+{
+  for (int j = warp; j < n; j += QW) {
+    const double *row = S + (size_t)j * n;
+    double s = 0.0;
+    for (int i = j + lane; i < n; i += 32) s = fma(row[i], v[i], s);
+    s = warp_sum(s);
+    if (lane == 0) x[j] = s;
+  }
+}
+// part[w][r] = sum over the columns j of chunk w of A(r, j) * (x ? x[j] : A(r, j)): the m x n column-major constraint matrix is
+// read once, consecutive lanes on consecutive rows (coalesced), 4 rows per lane in flight; the caller sums the QW partials.
+__device__ __forceinline__ void rows_partial(const double *__restrict__ A, int mmax, int m, int n, const double *x, double *part,
+                                             int pstride, int warp, int lane)
+{
+  constexpr int RPL = 8;                      // rows per lane in flight
+  const int chunk = (n + QW - 1) / QW, j0 = warp * chunk, j1 = min(n, j0 + chunk);
+  double *pw = part + (size_t)warp * pstride;
+  for (int base = 0; base < m; base += 32 * RPL) {
+    double s[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) s[k] = 0.0;
+    for (int j = j0; j < j1; ++j) {
+      const double *col = A + (size_t)j * mmax + base + lane;
+      const double xj = x ? x[j] : 0.0;
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) {
+        const double a = (base + lane + 32 * k < m) ? col[32 * k] : 0.0;
+        s[k] = fma(a, x ? xj : a, s[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RPL; ++k)
+      if (base + lane + 32 * k < m) pw[base + lane + 32 * k] = s[k];
+  }
+}
+
 struct QldArgs {
   int B, n, nmax, mmax, qcap;
   const int *m, *me;
@@ -251,7 +301,8 @@ qld_kernel(QldArgs P)
   double *x = reinterpret_cast<double *>(smem_raw);
   double *v = x + n, *v0 = v + n, *ap = v0 + n, *yp = ap + n, *yd = yp + n;
   double *inrm = yd + n;
-  double *u = inrm + mtot_max, *g = u + qcap, *w = g + qcap, *r = w + qcap;
+  double *part = inrm + mtot_max;                                         // QW x mmax partial row sums
+  double *u = part + (size_t)QW * mmax, *g = u + qcap, *w = g + qcap, *r = w + qcap;
   int *Wc = reinterpret_cast<int *>(r + qcap);
   int *slot = Wc + qcap, *freeslot = slot + qcap;
   signed char *sgn = reinterpret_cast<signed char *>(freeslot + qcap);   // sign of an active (equality) row
@@ -278,26 +329,24 @@ qld_kernel(QldArgs P)
     const int mtot = fail ? 0 : m + (bounds ? 2 * n : 0);
 
     // ---- unconstrained optimum v0 = -X d, x = X'v0; row norms, flags
-    for (int i = t; i < n; i += QT) {
-      double s = 0.0;
-      for (int j = 0; j <= i; ++j) s = fma(S[(size_t)j * n + i], dv[j], s);
-      v0[i] = -s; v[i] = -s;
-    }
+    for (int i = t; i < n; i += QT) ap[i] = dv[i];
     __syncthreads();
-    for (int j = t; j < n; j += QT) {
-      double s = 0.0;
-      for (int i = j; i < n; ++i) s = fma(S[(size_t)i * n + j], v[i], s);
-      x[j] = s;
-    }
+    tri_lower_mv(S, n, ap, v0, warp, lane);
+    if (!fail) rows_partial(A, mmax, m, n, nullptr, part, mmax, warp, lane);
+    __syncthreads();
+    for (int i = t; i < n; i += QT) { v0[i] = -v0[i]; v[i] = v0[i]; }
     for (int rr = t; rr < mtot; rr += QT) {
       double s = 1.0;
       if (rr < m) {
         s = 0.0;
-        for (int j = 0; j < n; ++j) { const double a = A[rr + (size_t)j * mmax]; s = fma(a, a, s); }
+#pragma unroll
+        for (int wq = 0; wq < QW; ++wq) s += part[(size_t)wq * mmax + rr];
       }
       inrm[rr] = s > 0.0 ? rsqrt(s) : 0.0;
       act[rr] = 0;
     }
+    __syncthreads();
+    tri_upper_mv(S, n, v, x, warp, lane);
     for (int k = t; k < qcap; k += QT) freeslot[k] = qcap - 1 - k;
     __syncthreads();
     int nfree = qcap;
@@ -318,12 +367,15 @@ qld_kernel(QldArgs P)
         if (sp > 0.0) { sign = -1; sp = -sp; }
       } else {
         double best = INF; int bi = 0x7fffffff;
+        rows_partial(A, mmax, m, n, x, part, mmax, warp, lane);
+        __syncthreads();
         for (int rr = t; rr < mtot; rr += QT) {
           if (act[rr] || rr < me) continue;          // equalities are all taken above
           double s, scale;
           if (rr < m) {
             s = 0.0;
-            for (int j = 0; j < n; ++j) s = fma(A[rr + (size_t)j * mmax], x[j], s);
+#pragma unroll
+            for (int wq = 0; wq < QW; ++wq) s += part[(size_t)wq * mmax + rr];
             const double bb = bv[rr];
             s += bb;
             scale = fabs(bb) * inrm[rr] + xnorm;
@@ -353,13 +405,10 @@ qld_kernel(QldArgs P)
       }
       __syncthreads();
       // y_p = X a_p, M_pp = |y_p|^2
+      tri_lower_mv(S, n, ap, yp, warp, lane);
+      __syncthreads();
       double mpp = 0.0;
-      for (int i = t; i < n; i += QT) {
-        double s = 0.0;
-        for (int j = 0; j <= i; ++j) s = fma(S[(size_t)j * n + i], ap[j], s);
-        yp[i] = s;
-        mpp = fma(s, s, mpp);
-      }
+      for (int i = t; i < n; i += QT) mpp = fma(yp[i], yp[i], mpp);
       const double Mpp = block_sum(mpp, red);
       double up = 0.0;
       bool added = false;
@@ -377,9 +426,14 @@ qld_kernel(QldArgs P)
         // yd = y_p - Q w: the part of y_p orthogonal to the active rows, with one re-orthogonalisation pass (Gram-Schmidt
         // twice: |yd| stays accurate when y_p lies almost inside the span, which is the rule for adjacent CoP rows)
         for (int i = t; i < n; i += QT) {
-          double s = yp[i];
-          for (int k = 0; k < q; ++k) s = fma(-w[k], Y[(size_t)slot[k] * n + i], s);
-          yd[i] = s;
+          double s0 = yp[i], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          int k = 0;
+          for (; k + 3 < q; k += 4) {
+            s0 = fma(-w[k], Y[(size_t)slot[k] * n + i], s0); s1 = fma(-w[k + 1], Y[(size_t)slot[k + 1] * n + i], s1);
+            s2 = fma(-w[k + 2], Y[(size_t)slot[k + 2] * n + i], s2); s3 = fma(-w[k + 3], Y[(size_t)slot[k + 3] * n + i], s3);
+          }
+          for (; k < q; ++k) s0 = fma(-w[k], Y[(size_t)slot[k] * n + i], s0);
+          yd[i] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         for (int k = warp; k < q; k += QW) {
@@ -392,8 +446,14 @@ qld_kernel(QldArgs P)
         __syncthreads();
         double dsq = 0.0;
         for (int i = t; i < n; i += QT) {
-          double s = yd[i];
-          for (int k = 0; k < q; ++k) s = fma(-g[k], Y[(size_t)slot[k] * n + i], s);
+          double s0 = yd[i], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          int k = 0;
+          for (; k + 3 < q; k += 4) {
+            s0 = fma(-g[k], Y[(size_t)slot[k] * n + i], s0); s1 = fma(-g[k + 1], Y[(size_t)slot[k + 1] * n + i], s1);
+            s2 = fma(-g[k + 2], Y[(size_t)slot[k + 2] * n + i], s2); s3 = fma(-g[k + 3], Y[(size_t)slot[k + 3] * n + i], s3);
+          }
+          for (; k < q; ++k) s0 = fma(-g[k], Y[(size_t)slot[k] * n + i], s0);
+          const double s = (s0 + s1) + (s2 + s3);
           yd[i] = s;
           dsq = fma(s, s, dsq);
         }
@@ -423,11 +483,7 @@ qld_kernel(QldArgs P)
           // step along yd in the factor's variables, x = X'v
           for (int i = t; i < n; i += QT) v[i] = fma(tt, yd[i], v[i]);
           __syncthreads();
-          for (int j = t; j < n; j += QT) {
-            double s = 0.0;
-            for (int i = j; i < n; ++i) s = fma(S[(size_t)i * n + j], v[i], s);
-            x[j] = s;
-          }
+          tri_upper_mv(S, n, v, x, warp, lane);
           sp += tt * delta;
         }
         for (int j = t; j < q; j += QT) u[j] = fma(-tt, r[j], u[j]);
@@ -518,11 +574,8 @@ qld_kernel(QldArgs P)
     // ---- results: x, multipliers in QLD's layout (m rows, n lower bounds, n upper bounds; qld.cpp:520-536)
     if (fail) {
       __syncthreads();
-      for (int j = t; j < n; j += QT) {
-        double s = 0.0;
-        for (int i = j; i < n; ++i) s = fma(S[(size_t)i * n + j], v0[i], s);
-        x[j] = s;
-      }
+      tri_upper_mv(S, n, v0, x, warp, lane);
+      __syncthreads();
     }
     for (int i = t; i < n; i += QT) P.x[(size_t)b * n + i] = x[i];
     if (P.u) {
@@ -548,7 +601,7 @@ qld_kernel(QldArgs P)
 size_t qld_smem_bytes(int n, int mmax, int qcap, bool bounds)
 {
   const size_t mtot = (size_t)mmax + (bounds ? 2 * (size_t)n : 0);
-  size_t s = sizeof(double) * (6 * (size_t)n + mtot + 4 * (size_t)qcap) + sizeof(int) * 3 * (size_t)qcap + qcap + mtot;
+  size_t s = sizeof(double) * (6 * (size_t)n + mtot + (size_t)QW * mmax + 4 * (size_t)qcap) + sizeof(int) * 3 * (size_t)qcap + qcap + mtot;
   return (s + 15) & ~(size_t)15;
 }
 

@@ -77,7 +77,7 @@ def preview_batch(B, seed=0):
     return offsets, np.ascontiguousarray(np.concatenate(walks, axis=0))
 
 
-def kajita_steps_batch(B, seed=0, ss=0.78, ds=0.02):
+def kajita_steps_batch(B, seed=0, ss=0.78, ds=0.02, straight_only=False):
     """Config 2 as FOOTSTEPS (the input of the on-GPU front end, wg_kajita_plan_create): walk b is, with equal odds,
     a straight walk (:stepseq of 8-20 steps, sx in U[0.05, 0.25], sy = -/+ U[0.19, 0.21] alternating, theta = 0, closed by
     a half step that brings the feet together) or an arc (:supportfoot 1, :arc 0 R a -1, :lastsupport with R in U[0.5, 2],
@@ -90,7 +90,7 @@ def kajita_steps_batch(B, seed=0, ss=0.78, ds=0.02):
     walks = []
     for b in range(B):
         rng = np.random.default_rng([seed, 2, b])
-        if rng.random() < 0.5:
+        if rng.random() < 0.5 or straight_only:
             n = int(rng.integers(8, 21))
             st = np.zeros(n + 2, dtype=REL_STEP_DTYPE)
             side = -1.0

@@ -237,7 +237,7 @@ def test_gpu_dense_qp_on_wieber_qps_reproduces_ql0001_regularisation(ctx):
         assert np.abs(per_qp[0][k] - xr).max() < 1e-5 * sc, (k, np.abs(per_qp[0][k] - xr).max())
         act = lambda u: set(np.nonzero(u[:len(b)] > 1e-7 * max(ur.max(), 1e-12))[0])
         assert act(shared[1][k]) == act(ur) == act(per_qp[1][k]), k
-        assert (A @ exact[0][k] + b).min() > -1e-10
+        assert (A @ exact[0][k] + b).min() > -1e-8          # the bound the reference itself checks (:1085)
         assert f(exact[0][k], d) <= f(xr, d) + 1e-9 * abs(f(xr, d))
     print(f"Wieber QPs: |x - x_ql0001| shared {max(np.abs(shared[0][k] - ref_qld(Cm, *probs[k])[0]).max() for k in range(B)):.2e}, "
           f"per-QP factor {max(np.abs(per_qp[0][k] - ref_qld(Cm, *probs[k])[0]).max() for k in range(B)):.2e}; iterations {shared[3]}")
