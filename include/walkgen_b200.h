@@ -75,6 +75,41 @@ int wg_prof_get(wg_ctx *ctx, int kernel_id, long long *launches, double *total_m
 int wg_measure_fp64_peak(wg_ctx *ctx, double *tflops);
 
 /* ------------------------------------------------------------------------------------------------
+ * Several GPUs from one process.  The instances of this path are independent: a sharded run deals instance i to
+ * device i mod G, every device runs the same kernel sequence on its share from its own host thread, no collective on the data
+ * path; the per-device statistics are all-reduced ONCE over NCCL at the end (ncclCommInitAll communicators, libnccl.so.2 bound
+ * at run time with dlopen; WG_NCCL_LIB overrides the name).  Without NCCL the statistics are summed on the host and
+ * wg_multi_stats::reduced_by_nccl is 0.  (One process per GPU over torch.distributed, as bench.py --gpus N runs it, needs none
+ * of this: every rank simply creates its own wg_ctx.)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct wg_multi wg_multi;
+int wg_multi_create(unsigned long long device_mask, wg_multi **out);   /* bit d selects device d; 0 = every visible device */
+int wg_multi_destroy(wg_multi *m);
+int wg_multi_size(const wg_multi *m);                                   /* G                                             */
+wg_ctx *wg_multi_ctx(wg_multi *m, int k);                               /* the context of the k-th selected device       */
+int wg_multi_nccl_version(const wg_multi *m);                           /* e.g. 22703, 0 when NCCL is not in use          */
+const char *wg_multi_last_error(const wg_multi *m);
+
+typedef struct wg_multi_stats {
+  long long instances, periods;
+  double seconds;                 /* CUDA-event time of the slowest device (MAX all-reduce)                               */
+  double qp_solves, failures, iterations, still_online;   /* SUM all-reduce over the devices                              */
+  int32_t devices, reduced_by_nccl, nccl_version, reserved;
+  float device_ms[16];            /* per device: time, share and kernel launches                                          */
+  long long device_instances[16], device_launches[16];
+} wg_multi_stats;
+
+/* struct wg_herdt_params / wg_herdt_mpc_params are declared further down */
+struct wg_herdt_params;
+struct wg_herdt_mpc_params;
+int wg_multi_herdt_set_params(wg_multi *m, const struct wg_herdt_params *hp, const struct wg_herdt_mpc_params *mp);
+/* BASELINE configs[4] inside the library: `instances` Herdt2010 closed loops (InitOnLine from init9, constant velocity
+ * reference vel_ref [instances][3], HOST array) advanced by `periods` QP periods in launches of `chunk` periods (<= 0: 10),
+ * sharded i -> device i mod G, states device resident from start to end. */
+int wg_multi_herdt_mpc_sweep(wg_multi *m, long long instances, int periods, int chunk, const double *vel_ref,
+                             const double *init9, wg_multi_stats *out);
+
+/* ------------------------------------------------------------------------------------------------
  * Kajita2003 preview control
  *   replaces PreviewControl::ComputeOptimalWeights        (src/PreviewControl/PreviewControl.cpp:198-322)
  *            OptimalControllerSolver::ComputeWeights       (src/PreviewControl/OptimalControllerSolver.cpp:200-352)
@@ -357,6 +392,15 @@ int wg_herdt_mpc_set_params(wg_ctx *ctx, const wg_herdt_mpc_params *params);
  * (TimeBuffer_/m_SamplingPeriod) of the deques are implied by the state. */
 int wg_herdt_mpc_init(wg_ctx *ctx, int mem, int B, const double *init9, int init_stride,
                       wg_herdt_mpc_state *states);
+
+/* The same for a start that is not at rest: init15 = {com x, dx, ddx, y, dy, ddy, z, trunk yaw (rad), trunk yaw rate,
+ * left foot x, y, theta(deg), right foot x, y, theta(deg)} - InitOnLine copies the whole lStartingCOMState into CoM_ and hands it
+ * to OrientationsPreview::CurrentTrunkState (ZMPVelocityReferencedQP.cpp:292-301). */
+int wg_herdt_mpc_init15(wg_ctx *ctx, int mem, int B, const double *init15, int init_stride, wg_herdt_mpc_state *states);
+
+/* qp_count, fail_count, iterations_total summed over B DEVICE-resident states and the number of instances still on line, into
+ * four DEVICE doubles (asynchronous on the context stream): the statistics a sharded run reduces across GPUs. */
+int wg_herdt_mpc_stats(wg_ctx *ctx, int B, const wg_herdt_mpc_state *d_states, double *d_out4);
 
 /* Advance every instance by `nsteps` QP periods.
  *   vel_ref : [B][3] or NULL   new (dx, dy, dyaw) written to new_ref before the first period

@@ -24,7 +24,7 @@ REL_STEP_DTYPE, KAJITA_FOOT_DTYPE = _capi.kajita_dtypes()
 LCI_DTYPE, DIMITROV_PERIOD_DTYPE = _capi.dimitrov_dtypes()
 DimitrovParams = _capi.DimitrovParams
 
-__all__ = ["LCI_DTYPE", "DIMITROV_PERIOD_DTYPE", "DimitrovParams", "dimitrov_default_params", "Context", "PreviewPlan", "KajitaPlan", "zmpdisc_default_params", "REL_STEP_DTYPE", "KAJITA_FOOT_DTYPE", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
+__all__ = ["MultiContext", "LCI_DTYPE", "DIMITROV_PERIOD_DTYPE", "DimitrovParams", "dimitrov_default_params", "Context", "PreviewPlan", "KajitaPlan", "zmpdisc_default_params", "REL_STEP_DTYPE", "KAJITA_FOOT_DTYPE", "preview_gains", "herdt_default_params", "herdt_mpc_default_params", "HerdtParams", "HerdtMpcParams",
            "PLDP_STATE_DTYPE", "PLDP_INFO_DTYPE", "FOOT_DTYPE", "TICK_DTYPE", "MPC_STATE_DTYPE", "MPC_STEP_DTYPE", "TICKS_PER_STEP", "QP_INPUT_DTYPE",
            "QP_OUTPUT_DTYPE", "ACTIVE_SET_DTYPE", "WalkgenError", "device_count",
            "MODE_WITH_INITIALPOS", "MODE_WITHOUT_INITIALPOS", "WG_MEM_HOST", "WG_MEM_DEVICE"]
@@ -502,6 +502,48 @@ class Context:
             plan.destroy()
         return {"com": com, "zmp": zmp, "left": left, "right": right, "status": status, "periods_done": done,
                 "period_counts": np.array(pc), "qp_iterations": its, "sample_offsets": so}
+
+
+class MultiContext:
+    """wg_multi: several GPUs from one process (instance i -> device i mod G, statistics all-reduced over NCCL)."""
+
+    def __init__(self, device_mask=0):
+        self.lib = _capi.load()
+        h = C.c_void_p()
+        rc = self.lib.wg_multi_create(int(device_mask), C.byref(h))
+        if rc != 0:
+            raise WalkgenError(rc, "wg_multi_create failed (no CUDA device?)")
+        self.h = h
+        self.size = self.lib.wg_multi_size(h)
+        self.nccl_version = self.lib.wg_multi_nccl_version(h)
+
+    def herdt_set_params(self, hp=None, mp=None):
+        self.hp = hp or herdt_default_params()
+        self.mp = mp or herdt_mpc_default_params()
+        rc = self.lib.wg_multi_herdt_set_params(self.h, C.byref(self.hp), C.byref(self.mp))
+        if rc != 0:
+            raise WalkgenError(rc, self.lib.wg_multi_last_error(self.h).decode())
+
+    def herdt_mpc_sweep(self, vel_ref, periods, chunk=10,
+                        init9=(0.0316055, 0.0, 0.7116911, 0.0, 0.09, 0.0, 0.0, -0.09, 0.0)):
+        v = np.ascontiguousarray(vel_ref, dtype=np.float64)
+        i9 = np.ascontiguousarray(init9, dtype=np.float64)
+        st = _capi.MultiStats()
+        rc = self.lib.wg_multi_herdt_mpc_sweep(self.h, len(v), int(periods), int(chunk), v.ctypes.data, i9.ctypes.data, C.byref(st))
+        if rc != 0:
+            raise WalkgenError(rc, self.lib.wg_multi_last_error(self.h).decode())
+        G = st.devices
+        return {"instances": st.instances, "periods": st.periods, "seconds": st.seconds, "qp_solves": st.qp_solves,
+                "failures": st.failures, "iterations": st.iterations, "still_online": st.still_online, "devices": G,
+                "reduced_by_nccl": bool(st.reduced_by_nccl), "nccl_version": st.nccl_version,
+                "device_ms": [float(st.device_ms[k]) for k in range(G)],
+                "device_instances": [int(st.device_instances[k]) for k in range(G)],
+                "device_launches": [int(st.device_launches[k]) for k in range(G)]}
+
+    def close(self):
+        if self.h:
+            self.lib.wg_multi_destroy(self.h)
+            self.h = None
 
 
 class KajitaPlan:

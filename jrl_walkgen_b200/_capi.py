@@ -81,6 +81,14 @@ class PldpBatch(C.Structure):
                 ("max_iterations", C.c_int32), ("info", C.c_void_p)]
 
 
+class MultiStats(C.Structure):
+    """Mirror of wg_multi_stats."""
+    _fields_ = [("instances", C.c_longlong), ("periods", C.c_longlong), ("seconds", C.c_double), ("qp_solves", C.c_double),
+                ("failures", C.c_double), ("iterations", C.c_double), ("still_online", C.c_double), ("devices", C.c_int32),
+                ("reduced_by_nccl", C.c_int32), ("nccl_version", C.c_int32), ("reserved", C.c_int32),
+                ("device_ms", C.c_float * 16), ("device_instances", C.c_longlong * 16), ("device_launches", C.c_longlong * 16)]
+
+
 class QldBatch(C.Structure):
     """Mirror of wg_qld_batch."""
     _fields_ = [("n", C.c_int32), ("nmax", C.c_int32), ("mmax", C.c_int32), ("shared_hessian", C.c_int32),
@@ -240,6 +248,15 @@ SIGNATURES = {
     "wg_prof_end": (C.c_int, [C.c_void_p]),
     "wg_prof_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), c_double_p]),
     "wg_measure_fp64_peak": (C.c_int, [C.c_void_p, c_double_p]),
+    "wg_multi_create": (C.c_int, [C.c_ulonglong, C.POINTER(C.c_void_p)]),
+    "wg_multi_destroy": (C.c_int, [C.c_void_p]),
+    "wg_multi_size": (C.c_int, [C.c_void_p]),
+    "wg_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "wg_multi_nccl_version": (C.c_int, [C.c_void_p]),
+    "wg_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "wg_multi_herdt_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtParams), C.POINTER(HerdtMpcParams)]),
+    "wg_multi_herdt_mpc_sweep": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.POINTER(MultiStats)]),
     "wg_preview_gains": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(PreviewGains)]),
     "wg_preview_gains_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_longlong]),
@@ -306,6 +323,8 @@ SIGNATURES = {
     "wg_herdt_mpc_default_params": (None, [C.POINTER(HerdtMpcParams)]),
     "wg_herdt_mpc_set_params": (C.c_int, [C.c_void_p, C.POINTER(HerdtMpcParams)]),
     "wg_herdt_mpc_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "wg_herdt_mpc_init15": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "wg_herdt_mpc_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wg_herdt_mpc_run_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
 }

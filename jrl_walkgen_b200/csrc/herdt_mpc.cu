@@ -933,7 +933,45 @@ int wg_herdt_mpc_set_params(wg_ctx *ctx, const wg_herdt_mpc_params *params)
   return WG_OK;
 }
 
+static int mpc_init_impl(wg_ctx *ctx, int mem, int B, const double *init, int init_stride, wg_herdt_mpc_state *states, bool full);
+
 int wg_herdt_mpc_init(wg_ctx *ctx, int mem, int B, const double *init9, int init_stride, wg_herdt_mpc_state *states)
+{
+  return mpc_init_impl(ctx, mem, B, init9, init_stride, states, false);
+}
+
+int wg_herdt_mpc_init15(wg_ctx *ctx, int mem, int B, const double *init15, int init_stride, wg_herdt_mpc_state *states)
+{
+  return mpc_init_impl(ctx, mem, B, init15, init_stride, states, true);
+}
+
+// qp_count, fail_count, iterations_total summed over the instances, and the number of instances still on line
+__global__ void mpc_stats_kernel(int B, const wg_herdt_mpc_state *__restrict__ states, double *__restrict__ out4)
+{
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    a0 += states[b].qp_count; a1 += states[b].fail_count; a2 += (double)states[b].iterations_total; a3 += states[b].online_mode ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out4, a0); atomicAdd(out4 + 1, a1); atomicAdd(out4 + 2, a2); atomicAdd(out4 + 3, a3); }
+}
+
+int wg_herdt_mpc_stats(wg_ctx *ctx, int B, const wg_herdt_mpc_state *d_states, double *d_out4)
+{
+  if (!ctx || B < 0 || !d_out4 || (B > 0 && !d_states)) return WG_ERR_INVALID;
+  wg_device_guard guard(ctx->device);
+  WG_CUDA(ctx, cudaMemsetAsync(d_out4, 0, sizeof(double) * 4, ctx->stream));
+  if (B == 0) return WG_OK;
+  mpc_stats_kernel<<<std::max(1, std::min((B + 255) / 256, ctx->sm_count * 4)), 256, 0, ctx->stream>>>(B, d_states, d_out4);
+  WG_LAUNCHED(ctx);
+  return WG_OK;
+}
+
+static int mpc_init_impl(wg_ctx *ctx, int mem, int B, const double *init9, int init_stride, wg_herdt_mpc_state *states, bool full)
 {
   if (!ctx || B < 0 || (B > 0 && (!init9 || !states)) || init_stride < 0) return WG_ERR_INVALID;
   MpcState *m = mpc_of(ctx);
@@ -943,7 +981,11 @@ int wg_herdt_mpc_init(wg_ctx *ctx, int mem, int B, const double *init9, int init
   // ZMPVelocityReferencedQP::InitOnLine, ZMPVelocityReferencedQP.cpp:213-319
   std::vector<wg_herdt_mpc_state> h((size_t)B);
   for (int b = 0; b < B; ++b) {
-    const double *in = init9 + (size_t)b * init_stride;
+    const double *src = init9 + (size_t)b * init_stride;
+    // init15 = {com x, dx, ddx, y, dy, ddy, z, trunk yaw, trunk yaw rate, left foot x, y, theta, right foot x, y, theta}
+    double in[9];
+    if (full) { in[0] = src[0]; in[1] = src[3]; in[2] = src[6]; for (int k = 0; k < 6; ++k) in[3 + k] = src[9 + k]; }
+    else for (int k = 0; k < 9; ++k) in[k] = src[k];
     wg_herdt_mpc_state &s = h[b];
     std::memset(&s, 0, sizeof s);
     s.online_mode = 1; s.time_to_stop = -1.0;
@@ -958,6 +1000,15 @@ int wg_herdt_mpc_init(wg_ctx *ctx, int mem, int B, const double *init9, int init
     s.sup_phase = WG_DS; s.sup_foot = WG_LEFT; s.sup_time_limit = 1000000000; s.sup_steps_left = 1;
     s.sup_x = in[3]; s.sup_y = in[4]; s.sup_yaw = in[5] * PI / 180.0;
     s.nb_steps_ssds = m->h_params.nb_steps_ssds;
+    if (full) {
+      // InitOnLine copies the whole lStartingCOMState into CoM_ and hands it to OrientPrw_->CurrentTrunkState
+      // (ZMPVelocityReferencedQP.cpp:292-301): velocity, acceleration, trunk yaw and yaw rate of a start that is not at rest
+      s.com_x[1] = src[1]; s.com_x[2] = src[2]; s.com_y[1] = src[4]; s.com_y[2] = src[5];
+      s.com_front[1] = src[1]; s.com_front[2] = src[2]; s.com_front[4] = src[4]; s.com_front[5] = src[5];
+      s.com_back[1] = src[1]; s.com_back[2] = src[2]; s.com_back[4] = src[4]; s.com_back[5] = src[5];
+      s.trunk_yaw[0] = src[7]; s.trunk_yaw[1] = src[8];
+      s.com_back[7] = src[7]; s.com_back[8] = src[8];
+    }
   }
   if (mem == WG_MEM_HOST) { std::memcpy(states, h.data(), sizeof(wg_herdt_mpc_state) * (size_t)B); return WG_OK; }
   if (mem != WG_MEM_DEVICE) return WG_ERR_INVALID;
