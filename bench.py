@@ -515,6 +515,25 @@ def sweep_leg(ctx, wg, args, rank, world, dist):
             "state_bytes_per_rank": int(B * wg.MPC_STATE_DTYPE.itemsize)}
 
 
+def library_multi_leg(wg, args, world):
+    """configs[4] through wg_multi_herdt_mpc_sweep on devices 0 .. world-1 from ONE process."""
+    total, periods = args.sweep_instances, args.sweep_periods
+    rng = np.random.default_rng(2010)
+    v_all = np.column_stack([rng.uniform(-0.2, 0.3, total), rng.uniform(-0.15, 0.15, total), rng.uniform(-0.2, 0.2, total)])
+    m = wg.MultiContext((1 << world) - 1)
+    try:
+        m.herdt_set_params()
+        m.herdt_mpc_sweep(v_all[:4096 * world], 2)                        # warm-up
+        r = m.herdt_mpc_sweep(v_all, periods, chunk=10)
+    finally:
+        m.close()
+    return {"api": "wg_multi_create + wg_multi_herdt_mpc_sweep (one process, one host thread per device)",
+            "devices": r["devices"], "seconds": r["seconds"], "qp_solves": int(r["qp_solves"]),
+            "qp_solves_per_s": r["qp_solves"] / r["seconds"], "failures": int(r["failures"]),
+            "reduced_by_nccl": r["reduced_by_nccl"], "nccl_version": r["nccl_version"], "device_ms": r["device_ms"],
+            "device_instances": r["device_instances"]}
+
+
 # ------------------------------------------------------------------------------------------------
 # Dimitrov PLDP leg (BASELINE configs[3]: 16 384 constrained CoP QPs)
 # ------------------------------------------------------------------------------------------------
@@ -885,6 +904,9 @@ def run_cuda(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side barrier for the one leg in which rank 0 drives every GPU itself: an NCCL barrier would park a spinning
+        # kernel on the other ranks' GPUs (measured: 2.2x slower sweep on the GPU whose rank waits in dist.barrier())
+        cpu_group = dist.new_group(backend="gloo")
     ctx = wg.Context(local_rank)
     gains = wg.preview_gains(0.005, 1.6, 0.814, wg.MODE_WITHOUT_INITIALPOS)
     ctx.preview_set_gains(gains)
@@ -1042,6 +1064,18 @@ def run_cuda(args):
     sweep = None
     if not args.no_sweep:
         sweep = sweep_leg(ctx, wg, args, rank, world, dist)
+        # the same sweep through the LIBRARY's own sharding driver (wg_multi: one process, a host thread per device, NCCL
+        # all-reduce of the statistics): rank 0 drives all `world` devices while the other ranks wait at the barrier below
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                sweep["library_multi_gpu"] = library_multi_leg(wg, args, world)
+            except Exception as e:                                       # noqa: BLE001 - reported, not fatal for the line
+                sweep["library_multi_gpu"] = {"error": str(e)}
+        if dist is not None:
+            dist.barrier(group=cpu_group)
 
     if rank == 0:
         # roofline of the dominant kernel (largest share of the timed region)
