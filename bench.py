@@ -515,6 +515,31 @@ def sweep_leg(ctx, wg, args, rank, world, dist):
             "state_bytes_per_rank": int(B * wg.MPC_STATE_DTYPE.itemsize)}
 
 
+def pin_to_gpu_numa_node(index):
+    """Best effort: restrict this rank to the CPUs of its GPU's NUMA node BEFORE any pinned buffer is allocated (first touch
+    then places the staging buffers next to the GPU's PCIe root).  Returns what happened, for the bench line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out            # 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"gpu_numa_node": node, "pinned": False, "why": "the platform reports no NUMA node for the GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return {"gpu_numa_node": node, "pinned": False, "allowed_cpus": len(allowed),
+                    "why": "none of the node's CPUs is in this process's cpuset"}
+        os.sched_setaffinity(0, use)
+        return {"gpu_numa_node": node, "pinned": True, "cpus": len(use)}
+    except Exception as e:                                        # noqa: BLE001
+        return {"pinned": False, "why": str(e)[:120]}
+
+
 def library_multi_leg(wg, args, world):
     """configs[4] through wg_multi_herdt_mpc_sweep on devices 0 .. world-1 from ONE process."""
     total, periods = args.sweep_instances, args.sweep_periods
@@ -907,6 +932,8 @@ def run_cuda(args):
         # host-side barrier for the one leg in which rank 0 drives every GPU itself: an NCCL barrier would park a spinning
         # kernel on the other ranks' GPUs (measured: 2.2x slower sweep on the GPU whose rank waits in dist.barrier())
         cpu_group = dist.new_group(backend="gloo")
+    numa_note = pin_to_gpu_numa_node(local_rank) if world > 1 else \
+        {"pinned": False, "why": "single rank: affinity left alone (the CPU baseline legs use every core)"}
     ctx = wg.Context(local_rank)
     gains = wg.preview_gains(0.005, 1.6, 0.814, wg.MODE_WITHOUT_INITIALPOS)
     ctx.preview_set_gains(gains)
@@ -970,6 +997,18 @@ def run_cuda(args):
         plan.run(zp, stp, comp, zmpp, True, mem=wg.WG_MEM_HOST)
     ctx.sync()
     e2e_s = time.perf_counter() - te
+    # output selection (wg_preview_run_batch_pos): a caller that only consumes the CoM position moves 16 + 16 B per step
+    posp = ctx.pinned((n, 2))
+    for _ in range(2):
+        stp[:] = 0.0
+        plan.run_pos(zp, stp, posp, True, mem=wg.WG_MEM_HOST)
+    barrier()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        stp[:] = 0.0
+        plan.run_pos(zp, stp, posp, True, mem=wg.WG_MEM_HOST)
+    ctx.sync()
+    e2e_pos_s = time.perf_counter() - te
     clocks = sampler.stop(t0, t1)
     h2d = z.nbytes + stp.nbytes
     d2h = comp.nbytes + zmpp.nbytes + stp.nbytes
@@ -997,7 +1036,7 @@ def run_cuda(args):
             "how": "4 x 256 MB pinned copies per direction per rank, all ranks at once"}
 
     # ---- max over ranks ----------------------------------------------------------------------
-    (ms_total, e2e_s), (total_steps_all,) = reduce_over_ranks(dist, [ms_total, e2e_s], [float(steps_per_pass)])
+    (ms_total, e2e_s, e2e_pos_s), (total_steps_all,) = reduce_over_ranks(dist, [ms_total, e2e_s, e2e_pos_s], [float(steps_per_pass)])
     ms_per_step = ms_total / args.steps
     value = total_steps_all * passes / (ms_per_step * 1e-3)
     e2e_value = total_steps_all * e2e_steps / e2e_s
@@ -1130,6 +1169,10 @@ def run_cuda(args):
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "passes": e2e_steps, "api": "wg_preview_run_batch(WG_MEM_HOST), pinned host buffers",
+                        "com_position_only": {"value": total_steps_all * e2e_steps / e2e_pos_s, "unit": UNIT,
+                                              "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(posp.nbytes + stp.nbytes),
+                                              "api": "wg_preview_run_batch_pos(WG_MEM_HOST): output selection, 16 B per step out"},
+                        "numa": numa_note,
                         "host_link": link,
                         "bound": "host link: %.0f B per preview step cross PCIe (16 in, 64 out); at the probed D2H rate the "
                                  "64 B/step alone cap the leg at %.2f G steps/s" % (BYTES_PER_STEP, d2h_sum / 64.0)},

@@ -176,6 +176,12 @@ int64_t wg_preview_plan_total_samples(const wg_preview_plan *plan); /* offsets[B
 int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *plan, int mem, const double *zmpref_xy,
                          double *state, double *com_out, double *zmp_out, int simulation);
 
+/* Output selection: the same run, writing only the CoM POSITION of every step, com_pos_out [total_samples][2] = (x, y) after
+ * step k (rows past a trajectory's last step as in wg_preview_run_batch's zmp_out).  16 bytes per step leave the GPU instead of
+ * 64 - the host-buffer path is bound by that traffic.  `state` still receives the full final state. */
+int wg_preview_run_batch_pos(wg_ctx *ctx, wg_preview_plan *plan, int mem, const double *zmpref_xy, double *state,
+                             double *com_pos_out, int simulation);
+
 /* Second stage of the two-stage scheme (ZMPPreviewControlWithMultiBodyZMP::EvaluateMultiBodyZMP / SecondStageOfControl,
  * src/PreviewControl/ZMPPreviewControlWithMultiBodyZMP.cpp:447-479, :317-376), for callers that own the multibody model:
  *   1. wg_preview_run_batch(simulation = 1) is the first stage: com_out row k = m_PC1x / m_PC1y after tick k;

@@ -603,6 +603,11 @@ class PreviewPlan:
         self.ctx._check(self.ctx.lib.wg_preview_run_batch(self.ctx.h, self.h, mem, _ptr(zmpref_xy), _ptr(state),
                                                           _ptr(com_out), _ptr(zmp_out), int(simulation)))
 
+    def run_pos(self, zmpref_xy, state, com_pos_out, simulation=True, mem=WG_MEM_HOST):
+        """wg_preview_run_batch_pos: only the CoM position (x, y) of every step."""
+        self.ctx._check(self.ctx.lib.wg_preview_run_batch_pos(self.ctx.h, self.h, mem, _ptr(zmpref_xy), _ptr(state),
+                                                              _ptr(com_pos_out), int(simulation)))
+
     def delta_zmp(self, zmpref_xy, zmp_multibody_xy, delta_out, mem=WG_MEM_HOST):
         """wg_preview_delta_zmp: delta[k] = zmpref[k + 1] - zmp_multibody[k] (EvaluateMultiBodyZMP)."""
         self.ctx._check(self.ctx.lib.wg_preview_delta_zmp(self.ctx.h, self.h, mem, _ptr(zmpref_xy), _ptr(zmp_multibody_xy),

@@ -395,7 +395,9 @@ __device__ __forceinline__ void scan_combine(Axis &c, const double *__restrict__
 
 // ADD: second stage of ZMPPreviewControlWithMultiBodyZMP (SecondStageOfControl, ZMPPreviewControlWithMultiBodyZMP.cpp:317-376):
 // the stream is the delta ZMP, and the CoM rows written are com_add (the first stage's CoM of the same tick) + the state.
-template <bool SIM, int FIR_THREADS, int MIN_CTAS, bool ADD = false>
+// POS: output selection for callers that only consume the CoM position (wg_preview_run_batch_pos): the (x, y) pair of a tick
+// goes out through the 16-byte path of the ZMP (zmp = the position array, com = nullptr): 16 B per step leave the GPU, not 64.
+template <bool SIM, int FIR_THREADS, int MIN_CTAS, bool ADD = false, bool POS = false>
 __global__ void __launch_bounds__(FIR_THREADS, MIN_CTAS)
 preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ offsets,
                      const double2 *__restrict__ p, double *__restrict__ state, double *__restrict__ com,
@@ -578,7 +580,7 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
             q[0] = make_double2(sx.x0, sx.x1);
             q[1] = make_double2(sx.x2, sy.x0);
             q[2] = make_double2(sy.x1, sy.x2);
-            stg_z[CHUNK_Z * lane + h] = make_double2(zx, zy);
+            stg_z[CHUNK_Z * lane + h] = POS ? make_double2(sx.x0, sy.x0) : make_double2(zx, zy);
           }
         }
         __syncwarp();
@@ -679,7 +681,7 @@ void scan_matrices(const wg_preview_gains_t &g, bool sim, double (*P)[16], doubl
 template <int THREADS, int MIN_CTAS>
 static int preview_launch_shape(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count, const double *d_zmp,
                                 double *d_state, double *d_com, double *d_zmpout, int simulation,
-                                const double *d_com_add = nullptr)
+                                const double *d_com_add = nullptr, bool pos_only = false)
 {
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
   const int span = FIR_R * THREADS + NLpad;
@@ -691,6 +693,21 @@ static int preview_launch_shape(wg_ctx *ctx, wg_preview_plan *pl, const int *d_o
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
   std::lock_guard<std::mutex> lock(g_pv_mutex);
   { const int rc = preview_bind(ctx); if (rc != WG_OK) return rc; }
+  if (pos_only) {             // CoM position only: d_zmpout is the [total][2] position array
+    if (simulation) {
+      WG_SMEM_ATTR(ctx, WG_ATTR_PREVIEW_POS_0 + 2 * (THREADS == 128 ? 0 : THREADS == 32 ? 1 : 2), (preview_fused_kernel<true, THREADS, MIN_CTAS, false, true>), smem);
+    } else {
+      WG_SMEM_ATTR(ctx, WG_ATTR_PREVIEW_POS_0 + 2 * (THREADS == 128 ? 0 : THREADS == 32 ? 1 : 2) + 1, (preview_fused_kernel<false, THREADS, MIN_CTAS, false, true>), smem);
+    }
+    wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
+    if (simulation)
+      preview_fused_kernel<true, THREADS, MIN_CTAS, false, true><<<count, THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, nullptr, d_zmpout);
+    else
+      preview_fused_kernel<false, THREADS, MIN_CTAS, false, true><<<count, THREADS, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state, nullptr, d_zmpout);
+    wg_prof_stop(ctx);
+    WG_LAUNCHED(ctx);
+    return WG_OK;
+  }
   if (d_com_add && d_com) {   // second stage: always with the integrated error (Simulation = true, :343-347)
     WG_SMEM_ATTR(ctx, WG_ATTR_PREVIEW_ADD_0 + (THREADS == 128 ? 0 : THREADS == 32 ? 1 : 2), (preview_fused_kernel<true, THREADS, MIN_CTAS, true>), smem);
     wg_prof_start(ctx, WG_K_PREVIEW_FUSED);
@@ -826,7 +843,8 @@ int64_t wg_preview_plan_total_samples(const wg_preview_plan *pl) { return pl ? p
 
 // Launch over `count` trajectories listed in d_order (device array of trajectory indices of this plan).
 int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count, const double *d_zmp,
-                            double *d_state, double *d_com, double *d_zmpout, int simulation, const double *d_com_add)
+                            double *d_state, double *d_com, double *d_zmpout, int simulation, const double *d_com_add,
+                            int pos_only)
 {
   if (pl->total_steps == 0 || count <= 0) return WG_OK;
   static int shape = -1;   // WG_PREVIEW_SHAPE: tuning knob for the CTA shape (default 64 threads x 8 CTAs/SM, 128 registers, no spills; measured 0.752 ms vs 0.778 (128 x 4) and 0.766 (32 x 16) on config 2)
@@ -835,14 +853,14 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
     shape = e ? atoi(e) : 0;
   }
   switch (shape) {
-  case 1: return preview_launch_shape<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add);
-  case 2: return preview_launch_shape<32, 16>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add);
-  default: return preview_launch_shape<64, 8>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add);
+  case 1: return preview_launch_shape<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
+  case 2: return preview_launch_shape<32, 16>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
+  default: return preview_launch_shape<64, 8>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
   }
 }
 
 static int preview_run(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *zmpref_xy, double *state,
-                       double *com_out, double *zmp_out, int simulation, const double *com_add)
+                       double *com_out, double *zmp_out, int simulation, const double *com_add, int pos_only = 0)
 {
   if (!ctx || !pl || pl->ctx != ctx || !state || (!zmpref_xy && pl->total_samples > 0)) return WG_ERR_INVALID;
   if (!ctx->preview_ready || ctx->preview_gains.NL != pl->NL)
@@ -850,7 +868,7 @@ static int preview_run(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *
   wg_device_guard guard(ctx->device);
   if (pl->B == 0) return WG_OK;
   if (mem == WG_MEM_DEVICE)
-    return wgi_preview_launch_range(ctx, pl, pl->d_order, pl->B, zmpref_xy, state, com_out, zmp_out, simulation, com_add);
+    return wgi_preview_launch_range(ctx, pl, pl->d_order, pl->B, zmpref_xy, state, com_out, zmp_out, simulation, com_add, pos_only);
   if (mem != WG_MEM_HOST) return WG_ERR_INVALID;
   const size_t ns = (size_t)pl->total_samples;
   if (com_add && !pl->d_add) WG_CUDA(ctx, cudaMalloc(&pl->d_add, sizeof(double) * 6 * std::max<size_t>(1, ns)));
@@ -879,7 +897,7 @@ static int preview_run(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *
     WG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl->ev_up[c], 0));
     int rc = wgi_preview_launch_range(ctx, pl, pl->d_order_chunked + b0, b1 - b0, pl->d_zmp, pl->d_state,
                                       com_out ? pl->d_com : nullptr, zmp_out ? pl->d_zmpout : nullptr, simulation,
-                                      com_add ? pl->d_add : nullptr);
+                                      com_add ? pl->d_add : nullptr, pos_only);
     if (rc != WG_OK) return rc;
     WG_CUDA(ctx, cudaEventRecord(pl->ev_k[c], ctx->stream));
     WG_CUDA(ctx, cudaStreamWaitEvent(pl->down_stream, pl->ev_k[c], 0));
@@ -898,6 +916,13 @@ int wg_preview_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double
                          double *com_out, double *zmp_out, int simulation)
 {
   return preview_run(ctx, pl, mem, zmpref_xy, state, com_out, zmp_out, simulation, nullptr);
+}
+
+int wg_preview_run_batch_pos(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *zmpref_xy, double *state,
+                             double *com_pos_out, int simulation)
+{
+  if (!com_pos_out) return WG_ERR_INVALID;
+  return preview_run(ctx, pl, mem, zmpref_xy, state, nullptr, com_pos_out, simulation, nullptr, 1);
 }
 
 int wg_preview_stage2_run_batch(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *delta_zmp_xy,

@@ -100,7 +100,8 @@ inline void wg_prof_stop(wg_ctx *ctx)
 // context on the same GPU must not lower it).  Slots: one per kernel instantiation that needs more than 48 KB.
 enum { WG_ATTR_PREVIEW_0 = 0, /* .. 5: {sim, nosim} x 3 CTA shapes */ WG_ATTR_HERDT_QP = 6, WG_ATTR_HERDT_MPC = 7,
        WG_ATTR_PLDP = 8, WG_ATTR_PLDP_RANKED = 9, WG_ATTR_ZMPDISC = 10, WG_ATTR_DIMITROV = 11, WG_ATTR_DENSEQP = 12,
-       WG_ATTR_PREVIEW_ADD_0 = 13, /* .. 15: second-stage variant x 3 CTA shapes */ WG_ATTR_SLOTS = 24 };
+       WG_ATTR_PREVIEW_ADD_0 = 13, /* .. 15: second-stage variant x 3 CTA shapes */
+       WG_ATTR_PREVIEW_POS_0 = 16, /* .. 21: position-only variant {sim, nosim} x 3 CTA shapes */ WG_ATTR_SLOTS = 24 };
 extern "C" int wgi_smem_attr(wg_ctx *ctx, int slot, const void *func, size_t bytes);
 #define WG_SMEM_ATTR(ctx, slot, func, bytes)                                              \
   do {                                                                                    \
@@ -112,7 +113,7 @@ extern "C" int wgi_smem_attr(wg_ctx *ctx, int slot, const void *func, size_t byt
 // trajectories listed in the device array d_order.
 extern "C" int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count,
                                         const double *d_zmp, double *d_state, double *d_com, double *d_zmpout,
-                                        int simulation, const double *d_com_add = nullptr);
+                                        int simulation, const double *d_com_add = nullptr, int pos_only = 0);
 
 // zmpdisc.cu / pldp.cu internals used by dimitrov.cu
 struct wgi_kajita_view {

@@ -276,3 +276,35 @@ def test_gpu_batched_gains_match_host_solve_and_oracle(ctx):
             assert abs(heads["Ks"][b] - og.Ks) < 1e-8 * abs(og.Ks)
             assert np.abs(F[b, :og.NL] - og.F).max() < 1e-8 * np.abs(og.F).max()
         print(f"batched gains mode {mode}: max rel deviation from the host solve {worst:.2e}")
+
+
+@pytest.mark.gpu
+def test_gpu_position_only_output_equals_the_full_run(ctx):
+    """wg_preview_run_batch_pos (output selection: 16 B per step instead of 64) writes exactly the x / y of the full run, host
+    and device memory, with and without the integrated error."""
+    import jrl_walkgen_b200 as wg
+    gains = wg.preview_gains(0.005, 1.6, 0.814, wg.MODE_WITHOUT_INITIALPOS)
+    ctx.preview_set_gains(gains)
+    rng = np.random.default_rng(31)
+    lens = [1500, 330, 4000, 320, 900]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = int(offsets[-1])
+    z = np.cumsum(rng.normal(scale=1e-3, size=(n, 2)), axis=0)
+    plan = ctx.preview_plan(offsets)
+    for sim in (True, False):
+        st_a = rng.normal(scale=0.01, size=(len(lens), 8)); st_b = st_a.copy(); st_c = st_a.copy()
+        com = np.zeros((n, 6)); zmp = np.zeros((n, 2)); pos = np.zeros((n, 2))
+        plan.run(z, st_a, com, zmp, sim)
+        plan.run_pos(z, st_b, pos, sim)
+        assert np.array_equal(pos, com[:, [0, 3]]) and np.array_equal(st_a, st_b)
+        dz = ctx.to_device(z); ds = ctx.to_device(st_c); dp = ctx.alloc(pos.nbytes)
+        plan.run_pos(dz, ds, dp, sim, mem=wg.WG_MEM_DEVICE)
+        ctx.sync()
+        got = dp.download(np.float64, (n, 2))
+        for b, L in enumerate(lens):
+            o = int(offsets[b]); steps = L - 320 + 1
+            assert np.array_equal(got[o:o + steps], pos[o:o + steps])
+        assert np.array_equal(ds.download(np.float64, (len(lens), 8)), st_a)
+        for d in (dz, ds, dp):
+            d.free()
+    plan.destroy()
