@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py - headline measurement of the B200 hot path (contract: see DESIGN.md "Measurement").
 
-Workload (BASELINE.json configs[1]): Kajita2003 preview control, 4096 random straight/circle footstep walks,
-320-tap preview window, 5 ms ticks.  A "step" of the bench is one pass of the hot path over the whole batch
+Workload (BASELINE.json configs[1]): Kajita2003 preview control, 4096 random straight/circle footstep walks turned into
+5 ms ZMP references by ZMPDiscretization (the product's kernel in the CUDA arm, the oracle's restatement in the reference
+arm; both pinned to the TestKajita2003 datrefs), 320-tap preview window.  A "step" of the bench is one pass of the hot path over the whole batch
 (every preview step of every walk); the metric unit is one preview step = one OneIterationOfPreview call for
 both axes (PreviewControl.cpp:324-374).
 
@@ -30,7 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "Kajita preview steps/s (batched; Herdt2010 QP solves/s reported under 'herdt')"
 UNIT = "preview steps/s"
-WORKLOAD = "kajita2003_preview_batched_4096_walks_320tap"
+WORKLOAD = "kajita2003_preview_batched_4096_footstep_walks_zmpdiscretization_320tap"
 FLOP_PER_STEP = 1360.0          # both axes, 2*(2*320 + 40)
 FIR_FLOP_PER_STEP = 1280.0      # the 2x320-tap window MACs, the part the FIR kernel executes
 BYTES_PER_STEP = 80.0           # streaming minimum: 16 B in, 48 B CoM + 16 B ZMP out
@@ -237,13 +238,55 @@ def herdt_cpu_inputs(n_sims=48, periods=30, seed=7):
     return np.concatenate(ins)
 
 
+def _oracle_discretize_worker(job):
+    import zmpdisc_oracle as zo
+    zp = zo.default_params()
+    out = []
+    for st, f in job:
+        o = zo.run(zp, st.astype(zo.REL_STEP_DTYPE), f)
+        out.append(np.ascontiguousarray(o["zmp"][:, :2]))
+    return out
+
+
+def headline_workload_cpu(walks, seed):
+    """configs[1] for the reference arm (no GPU there): the footstep walks of workloads.kajita_steps_batch through the ORACLE's
+    ZMPDiscretization (pinned to the four TestKajita2003 datrefs), one process per core -> (offsets, zmpref [total][2])."""
+    import multiprocessing as mp
+    from jrl_walkgen_b200 import workloads
+    off, steps, feet = workloads.kajita_steps_batch(walks, seed=seed)
+    procs = host_cores()
+    jobs = [[] for _ in range(procs)]
+    for b in range(walks):
+        jobs[b % procs].append((steps[off[b]:off[b + 1]].copy(), feet[b].copy()))
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_oracle_discretize_worker, jobs)
+    zs = [None] * walks
+    for p, r in enumerate(res):
+        for k, z in enumerate(r):
+            zs[p + k * procs] = z
+    lens = np.array([len(z) for z in zs], dtype=np.int64)
+    return np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), np.ascontiguousarray(np.concatenate(zs))
+
+
+def headline_workload_gpu(ctx, walks, seed):
+    """configs[1] for the CUDA arm: the same footstep walks through the product's own ZMPDiscretization kernel
+    (wg_zmpdisc_run_batch), downloaded once - the ZMP references the preview kernel is then timed on."""
+    from jrl_walkgen_b200 import workloads
+    off, steps, feet = workloads.kajita_steps_batch(walks, seed=seed)
+    kp = ctx.kajita_plan(off, steps, feet)
+    offsets = np.ascontiguousarray(kp.sample_offsets, dtype=np.int64).copy()
+    z = np.zeros((int(offsets[-1]), 2))
+    kp.discretize(zmpref_xy=z)
+    kp.destroy()
+    return offsets, z
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
-    from jrl_walkgen_b200 import workloads
-    offsets, z = workloads.preview_batch(args.walks, seed=0)
+    offsets, z = headline_workload_cpu(args.walks, seed=0)
     arm = ReferencePreviewArm(offsets, z)
     ms, steps = [], 0
     for it in range(args.warmup + args.steps):
@@ -937,7 +980,7 @@ def run_cuda(args):
     ctx = wg.Context(local_rank)
     gains = wg.preview_gains(0.005, 1.6, 0.814, wg.MODE_WITHOUT_INITIALPOS)
     ctx.preview_set_gains(gains)
-    offsets, z = workloads.preview_batch(args.walks, seed=1000 * rank)
+    offsets, z = headline_workload_gpu(ctx, args.walks, seed=1000 * rank)
     B = args.walks
     n = int(offsets[-1])
     plan = ctx.preview_plan(offsets)
