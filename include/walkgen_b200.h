@@ -560,6 +560,16 @@ double wg_qld_shared_boost(wg_ctx *ctx);
 double wg_qld_diagonal_boost(int n, int nmax, const double *C, double eps);
 int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *batch);
 
+/* The same solve for constraint matrices of the rank structure both QP generators of the reference build
+ * (ZMPQPWithConstraint.cpp:613-626, ZMPConstrainedQPFastFormulation.cpp:885-905): n = 2N and row r of QP k is
+ *     element (r, j + N ax) = A_ax[r] * uz[sample[r] - j]   for j <= sample[r], 0 beyond     (ax = 0, 1)
+ * i.e. a half-plane normal (A0, A1) applied to previewed sample `sample[r]` of the lower-triangular Toeplitz map uz from the
+ * jerks to the CoP.  A0, A1, sample: [B][row_stride] (row_stride >= mmax), uz_dev: N DEVICE doubles; batch->A is ignored.  The
+ * m x n matrix (360 KB per Wieber QP) is neither materialised nor streamed: the violation scan works on the N points Uz x.
+ * Device memory only (mem = WG_MEM_DEVICE).  Same results as the dense entry on the materialised matrix up to rounding. */
+int wg_qld_solve_batch_ranked(wg_ctx *ctx, int mem, int B, const wg_qld_batch *batch, const double *A0, const double *A1,
+                              const unsigned char *sample, long long row_stride, const double *uz_dev, int N);
+
 /* ------------------------------------------------------------------------------------------------
  * Kajita2003 front end: footsteps -> 5 ms ZMP reference and feet trajectories, batched
  *   replaces StepStackHandler::ReadStepSequenceAccordingToWalkMode / PrepareForSupportFoot /
@@ -763,7 +773,9 @@ typedef struct wg_wieber_params {
   double qld_eps;                     /* Eps handed to ql0001_, 1e-8 (:734): QLD regularises the Hessian with it (see
                                          wg_qld_set_shared_hessian); 0 solves the QP as stated                          */
   int32_t N;                          /* m_QP_N 75              (:72); 2N <= WG_QLD_MAX_N                               */
-  int32_t reserved;
+  int32_t materialize_pu;             /* 0 (default): the rows go to the solver as (A_r(0), A_r(1), i_r)
+                                         (wg_qld_solve_batch_ranked); 1: the dense (m + 1) x 2N matrix Pu is written out in
+                                         ql0001_'s layout and solved through wg_qld_solve_batch, as the reference does       */
 } wg_wieber_params;
 
 void wg_wieber_default_params(wg_wieber_params *p);

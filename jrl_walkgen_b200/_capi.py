@@ -103,7 +103,7 @@ class WieberParams(C.Structure):
     _fields_ = [("T", C.c_double), ("sampling_period", C.c_double), ("com_height", C.c_double), ("alpha", C.c_double),
                 ("beta", C.c_double), ("constraint_x", C.c_double), ("constraint_y", C.c_double),
                 ("sole_length", C.c_double), ("sole_width", C.c_double), ("qld_eps", C.c_double), ("N", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("materialize_pu", C.c_int32)]
 
 
 class ZmpDiscParams(C.Structure):
@@ -291,6 +291,8 @@ SIGNATURES = {
     "wg_qld_shared_boost": (C.c_double, [C.c_void_p]),
     "wg_qld_diagonal_boost": (C.c_double, [C.c_int, C.c_int, C.c_void_p, C.c_double]),
     "wg_qld_solve_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(QldBatch)]),
+    "wg_qld_solve_batch_ranked": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(QldBatch), C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_longlong, C.c_void_p, C.c_int]),
     "wg_wieber_default_params": (None, [C.POINTER(WieberParams)]),
     "wg_wieber_set_params": (C.c_int, [C.c_void_p, C.POINTER(WieberParams)]),
     "wg_wieber_period_count": (C.c_int64, [C.POINTER(WieberParams), C.c_int64]),

@@ -330,7 +330,7 @@ herdt_mpc_kernel(int B, int nsteps, const herdt::Consts *__restrict__ Cp, const 
       for (int e = lane; e < STW; e += 32) dst[e] = src[e];
     }
     __syncwarp();
-    if (vel_ref && lane < 3) st.new_ref[lane] = vel_ref[3 * (size_t)b + lane];
+    if (vel_ref && lane < 3 && st.online_mode) st.new_ref[lane] = vel_ref[3 * (size_t)b + lane];   // ended instances stay untouched
     __syncwarp();
 
     for (int step = 0; step < nsteps; ++step) {
@@ -614,7 +614,7 @@ mpc_pre_kernel(int B, int step, const herdt::Consts *__restrict__ Cp, const wg_h
       for (int e = lane; e < STW; e += 32) dst[e] = src[e];
     }
     __syncwarp();
-    if (step == 0 && vel_ref && lane < 3) st.new_ref[lane] = vel_ref[3 * (size_t)b + lane];
+    if (step == 0 && vel_ref && lane < 3 && st.online_mode) st.new_ref[lane] = vel_ref[3 * (size_t)b + lane];   // ended instances stay untouched
     __syncwarp();
     int stopped = (step == 0) ? 0 : scratch[b].stopped;
     int fire = 0;

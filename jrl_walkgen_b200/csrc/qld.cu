@@ -216,27 +216,62 @@ qld_factor_kernel(int count, int n, int nmax, const double *__restrict__ C, long
   }
 }
 
-// y = X a through the symmetric storage of X (row i of S is contiguous: S[i n + j] = X[i][j], j <= i): one warp per row, lanes
-// over the columns (coalesced, 5 loads per lane at n = 150 instead of a 150-long dependent chain per thread).
-__device__ __forceinline__ void tri_lower_mv(const double *__restrict__ S, int n, const double *a, double *y, int warp, int lane)
+// y = X a through the symmetric storage of X: y_i = sum_{j <= i} S[j n + i] a_j.  One thread per row, consecutive threads on
+// consecutive addresses, 8 independent accumulators: the dependent FMA chain is n / 8 long and the n loads of a thread are
+// independent of it.  (A warp per row with a shuffle reduction was measured slower: 19 dependent load + 5-round reductions per
+// warp and product, 34 % of the kernel's samples.)
+__device__ __forceinline__ void tri_lower_mv(const double *__restrict__ S, int n, const double *a, double *y, int t)
 {
-  for (int i = warp; i < n; i += QW) {
-    const double *row = S + (size_t)i * n;
-    double s = 0.0;
-    for (int j = lane; j <= i; j += 32) s = fma(row[j], a[j], s);
-    s = warp_sum(s);
-    if (lane == 0) y[i] = s;
+  for (int i = t; i < n; i += QT) {
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double *col = S + i;
+    int j = 0;
+    for (; j + 7 <= i; j += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] = fma(col[(size_t)(j + k) * n], a[j + k], s[k]);
+    }
+    for (; j <= i; ++j) s[0] = fma(col[(size_t)j * n], a[j], s[0]);
+    y[i] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   }
 }
-// x = X'v: x_j = sum_{i >= j} X[i][j] v_i = sum_{i >= j} S[j n + i] v_i
-__device__ __forceinline__ void tri_upper_mv(const double *__restrict__ S, int n, const double *v, double *x, int warp, int lane)
+// x = X'v: x_j = sum_{i >= j} X[i][j] v_i = sum_{i >= j} S[i n + j] v_i (same access pattern)
+__device__ __forceinline__ void tri_upper_mv(const double *__restrict__ S, int n, const double *v, double *x, int t)
 {
-  for (int j = warp; j < n; j += QW) {
-    const double *row = S + (size_t)j * n;
-    double s = 0.0;
-    for (int i = j + lane; i < n; i += 32) s = fma(row[i], v[i], s);
-    s = warp_sum(s);
-    if (lane == 0) x[j] = s;
+  for (int j = t; j < n; j += QT) {
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double *col = S + j;
+    int i = j;
+    for (; i + 7 < n; i += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] = fma(col[(size_t)(i + k) * n], v[i + k], s[k]);
+    }
+    for (; i < n; ++i) s[0] = fma(col[(size_t)i * n], v[i], s[0]);
+    x[j] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  }
+}
+// dots[k] = Q_k . y for the q active rows: a warp takes four rows at a time (four independent load / reduce chains)
+__device__ __forceinline__ void basis_dots(const double *__restrict__ Y, const int *slot, int q, int n, const double *y, double *dots,
+                                           int warp, int lane)
+{
+  for (int k0 = 4 * warp; k0 < q; k0 += 4 * QW) {
+    double s[4] = {0, 0, 0, 0};
+    const double *qk[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) qk[c] = Y + (size_t)slot[min(k0 + c, q - 1)] * n;
+    for (int j = lane; j < n; j += 32) {
+      const double yj = y[j];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] = fma(qk[c][j], yj, s[c]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (k0 + c < q) dots[k0 + c] = s[c];
+    }
   }
 }
 // part[w][r] = sum over the columns j of chunk w of A(r, j) * (x ? x[j] : A(r, j)): the m x n column-major constraint matrix is
@@ -281,12 +316,20 @@ struct QldArgs {
   int *ifail, *iterations;
   double *work; long long work_stride;      // per CTA
   int *next;
+  // rank-structured rows (RANKED kernel): row r of QP b = (A0, A1) x row `samp` of the lower-triangular Toeplitz matrix uz
+  const double *A0, *A1; const unsigned char *samp; long long row_stride;
+  const double *uz; int N;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // The solver.  Shared memory: x, v, v0, ap, yp, yd [n each]; inrm [m + 2n]; u, g, w, r [qcap each]; W, slot [qcap ints];
 // active flags [m + 2n bytes]; free-slot stack [qcap ints].  v = L'x is the iterate, x = X'v is refreshed after every step.
 // ---------------------------------------------------------------------------------------------------------------
+// RANKED: the m x n matrix is never read (nor materialised by the caller): element (r, k + N ax) = A_ax[r] uz[samp[r] - k],
+// k <= samp[r].  The violation scan then works on the N "points" P_ax = Uz x_ax (two Toeplitz products out of shared memory) and
+// costs two multiplications per row; the row handed to the factor is rebuilt from (A0, A1, samp).  Everything else is the
+// dense kernel.  (Wieber2006: 360 KB of matrix per QP and active-set change no longer cross HBM.)
+template <bool RANKED>
 __global__ void __launch_bounds__(QT, 2)
 qld_kernel(QldArgs P)
 {
@@ -307,6 +350,8 @@ qld_kernel(QldArgs P)
   int *slot = Wc + qcap, *freeslot = slot + qcap;
   signed char *sgn = reinterpret_cast<signed char *>(freeslot + qcap);   // sign of an active (equality) row
   unsigned char *act = reinterpret_cast<unsigned char *>(sgn + qcap);
+  const int N = RANKED ? P.N : 0;
+  double *pts = part, *uzs = part + 2 * N, *rn2 = part + 3 * N;          // RANKED: P_x, P_y [N each], uz [N], |uz row|^2 [N]
   double *Y = P.work + (size_t)blockIdx.x * P.work_stride;                // n x qcap, column `slot` at Y + slot * n
   double *T = Y + (size_t)n * qcap;                                       // packed lower triangle, row j at T + tri(j)
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -318,7 +363,9 @@ qld_kernel(QldArgs P)
     __syncthreads();
     if (b >= P.B) break;
     const int m = P.m[b], me = P.me ? P.me[b] : 0;
-    const double *A = P.A + (size_t)b * P.a_stride, *bv = P.b + (size_t)b * P.b_stride;
+    const double *A = RANKED ? nullptr : P.A + (size_t)b * P.a_stride, *bv = P.b + (size_t)b * P.b_stride;
+    const double *A0 = RANKED ? P.A0 + (size_t)b * P.row_stride : nullptr, *A1 = RANKED ? P.A1 + (size_t)b * P.row_stride : nullptr;
+    const unsigned char *samp = RANKED ? P.samp + (size_t)b * P.row_stride : nullptr;
     const double *dv = P.d + (size_t)b * n;
     const double *S = P.S + (size_t)b * P.h_stride;
     const double *Cm = P.C ? P.C + (size_t)b * P.c_stride : nullptr;
@@ -331,22 +378,29 @@ qld_kernel(QldArgs P)
     // ---- unconstrained optimum v0 = -X d, x = X'v0; row norms, flags
     for (int i = t; i < n; i += QT) ap[i] = dv[i];
     __syncthreads();
-    tri_lower_mv(S, n, ap, v0, warp, lane);
-    if (!fail) rows_partial(A, mmax, m, n, nullptr, part, mmax, warp, lane);
+    tri_lower_mv(S, n, ap, v0, t);
+    if (RANKED) {
+      for (int i = t; i < N; i += QT) uzs[i] = P.uz[i];
+      __syncthreads();
+      for (int i = t; i < N; i += QT) { double a = 0.0; for (int k = 0; k <= i; ++k) a = fma(uzs[k], uzs[k], a); rn2[i] = a; }
+    } else if (!fail) rows_partial(A, mmax, m, n, nullptr, part, mmax, warp, lane);
     __syncthreads();
     for (int i = t; i < n; i += QT) { v0[i] = -v0[i]; v[i] = v0[i]; }
     for (int rr = t; rr < mtot; rr += QT) {
       double s = 1.0;
       if (rr < m) {
-        s = 0.0;
+        if (RANKED) s = (A0[rr] * A0[rr] + A1[rr] * A1[rr]) * rn2[min((int)samp[rr], N - 1)];
+        else {
+          s = 0.0;
 #pragma unroll
-        for (int wq = 0; wq < QW; ++wq) s += part[(size_t)wq * mmax + rr];
+          for (int wq = 0; wq < QW; ++wq) s += part[(size_t)wq * mmax + rr];
+        }
       }
       inrm[rr] = s > 0.0 ? rsqrt(s) : 0.0;
       act[rr] = 0;
     }
     __syncthreads();
-    tri_upper_mv(S, n, v, x, warp, lane);
+    tri_upper_mv(S, n, v, x, t);
     for (int k = t; k < qcap; k += QT) freeslot[k] = qcap - 1 - k;
     __syncthreads();
     int nfree = qcap;
@@ -362,20 +416,44 @@ qld_kernel(QldArgs P)
       if (neq < me) {
         p = neq;
         double s = 0.0;
-        for (int j = t; j < n; j += QT) s = fma(A[p + (size_t)j * mmax], x[j], s);
+        if (RANKED) {
+          const int ip = min((int)samp[p], N - 1);
+          for (int j = t; j <= ip; j += QT) s = fma(uzs[ip - j], A0[p] * x[j] + A1[p] * x[j + N], s);
+        } else {
+          for (int j = t; j < n; j += QT) s = fma(A[p + (size_t)j * mmax], x[j], s);
+        }
         sp = block_sum(s, red) + bv[p];
         if (sp > 0.0) { sign = -1; sp = -sp; }
       } else {
         double best = INF; int bi = 0x7fffffff;
-        rows_partial(A, mmax, m, n, x, part, mmax, warp, lane);
+        if (RANKED) {
+          // points P_ax[i] = sum_{k <= i} uz[i - k] x[ax N + k]: warp per (axis, sample)
+          for (int e = t; e < 2 * N; e += QT) {
+            const int ax = e >= N, i = ax ? e - N : e;
+            const double *xa = x + ax * N;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = 0;
+            for (; k + 3 <= i; k += 4) {
+              a0 = fma(uzs[i - k], xa[k], a0); a1 = fma(uzs[i - k - 1], xa[k + 1], a1);
+              a2 = fma(uzs[i - k - 2], xa[k + 2], a2); a3 = fma(uzs[i - k - 3], xa[k + 3], a3);
+            }
+            for (; k <= i; ++k) a0 = fma(uzs[i - k], xa[k], a0);
+            pts[e] = (a0 + a1) + (a2 + a3);
+          }
+        } else rows_partial(A, mmax, m, n, x, part, mmax, warp, lane);
         __syncthreads();
         for (int rr = t; rr < mtot; rr += QT) {
           if (act[rr] || rr < me) continue;          // equalities are all taken above
           double s, scale;
           if (rr < m) {
-            s = 0.0;
+            if (RANKED) {
+              const int ip = min((int)samp[rr], N - 1);
+              s = A0[rr] * pts[ip] + A1[rr] * pts[N + ip];
+            } else {
+              s = 0.0;
 #pragma unroll
-            for (int wq = 0; wq < QW; ++wq) s += part[(size_t)wq * mmax + rr];
+              for (int wq = 0; wq < QW; ++wq) s += part[(size_t)wq * mmax + rr];
+            }
             const double bb = bv[rr];
             s += bb;
             scale = fabs(bb) * inrm[rr] + xnorm;
@@ -398,14 +476,19 @@ qld_kernel(QldArgs P)
       // a_p into shared memory (bounds: +- unit vector)
       for (int j = t; j < n; j += QT) {
         double a;
-        if (p < m) a = sign * A[p + (size_t)j * mmax];
+        if (p < m) {
+          if (RANKED) {
+            const int ip = min((int)samp[p], N - 1), ax = j >= N, k = ax ? j - N : j;
+            a = (k <= ip) ? sign * (ax ? A1[p] : A0[p]) * uzs[ip - k] : 0.0;
+          } else a = sign * A[p + (size_t)j * mmax];
+        }
         else if (p < m + n) a = (j == p - m) ? 1.0 : 0.0;
         else a = (j == p - m - n) ? -1.0 : 0.0;
         ap[j] = a;
       }
       __syncthreads();
       // y_p = X a_p, M_pp = |y_p|^2
-      tri_lower_mv(S, n, ap, yp, warp, lane);
+      tri_lower_mv(S, n, ap, yp, t);
       __syncthreads();
       double mpp = 0.0;
       for (int i = t; i < n; i += QT) mpp = fma(yp[i], yp[i], mpp);
@@ -415,13 +498,7 @@ qld_kernel(QldArgs P)
       while (!added && !done) {
         if (++iters > maxit) { fail = 1; done = true; break; }
         // w = Q'y_p (warp per active row): the coordinates of y_p in the orthonormal basis Q of the active rows (Y = Q R)
-        for (int k = warp; k < q; k += QW) {
-          const double *qk = Y + (size_t)slot[k] * n;
-          double s = 0.0;
-          for (int j = lane; j < n; j += 32) s = fma(qk[j], yp[j], s);
-          s = warp_sum(s);
-          if (lane == 0) w[k] = s;
-        }
+        basis_dots(Y, slot, q, n, yp, w, warp, lane);
         __syncthreads();
         // yd = y_p - Q w: the part of y_p orthogonal to the active rows, with one re-orthogonalisation pass (Gram-Schmidt
         // twice: |yd| stays accurate when y_p lies almost inside the span, which is the rule for adjacent CoP rows)
@@ -436,13 +513,7 @@ qld_kernel(QldArgs P)
           yd[i] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
-        for (int k = warp; k < q; k += QW) {
-          const double *qk = Y + (size_t)slot[k] * n;
-          double s = 0.0;
-          for (int j = lane; j < n; j += 32) s = fma(qk[j], yd[j], s);
-          s = warp_sum(s);
-          if (lane == 0) g[k] = s;
-        }
+        basis_dots(Y, slot, q, n, yd, g, warp, lane);
         __syncthreads();
         double dsq = 0.0;
         for (int i = t; i < n; i += QT) {
@@ -483,7 +554,7 @@ qld_kernel(QldArgs P)
           // step along yd in the factor's variables, x = X'v
           for (int i = t; i < n; i += QT) v[i] = fma(tt, yd[i], v[i]);
           __syncthreads();
-          tri_upper_mv(S, n, v, x, warp, lane);
+          tri_upper_mv(S, n, v, x, t);
           sp += tt * delta;
         }
         for (int j = t; j < q; j += QT) u[j] = fma(-tt, r[j], u[j]);
@@ -574,7 +645,7 @@ qld_kernel(QldArgs P)
     // ---- results: x, multipliers in QLD's layout (m rows, n lower bounds, n upper bounds; qld.cpp:520-536)
     if (fail) {
       __syncthreads();
-      tri_upper_mv(S, n, v0, x, warp, lane);
+      tri_upper_mv(S, n, v0, x, t);
       __syncthreads();
     }
     for (int i = t; i < n; i += QT) P.x[(size_t)b * n + i] = x[i];
@@ -746,15 +817,19 @@ double wg_qld_diagonal_boost(int n, int nmax, const double *C, double eps)
 
 double wg_qld_shared_boost(wg_ctx *ctx) { return ctx && ctx->qld ? static_cast<QldState *>(ctx->qld)->shared_boost : 0.0; }
 
-int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q)
+struct RankedRows { const double *A0, *A1; const unsigned char *samp; long long row_stride; const double *uz; int N; };
+
+static int qld_solve_impl(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q, const RankedRows *rk)
 {
   if (!ctx || !q || B < 0) return WG_ERR_INVALID;
   if (B == 0) return WG_OK;
   const int n = q->n, nmax = q->nmax, mmax = q->mmax;
   if (n <= 0 || n > WG_QLD_MAX_N || mmax < 0 || mmax > WG_QLD_MAX_M || !q->m || !q->d || !q->x || !q->ifail ||
-      (mmax > 0 && (!q->A || !q->b)) || (!q->shared_hessian && (!q->C || nmax < n)) || ((q->xl == nullptr) != (q->xu == nullptr)))
+      (mmax > 0 && ((!rk && !q->A) || !q->b)) || (!q->shared_hessian && (!q->C || nmax < n)) || ((q->xl == nullptr) != (q->xu == nullptr)))
     return WG_ERR_INVALID;
-  if (q->a_stride < (long long)mmax * n || q->b_stride < mmax || (q->u && q->u_stride < mmax)) return WG_ERR_INVALID;
+  if ((!rk && q->a_stride < (long long)mmax * n) || q->b_stride < mmax || (q->u && q->u_stride < mmax)) return WG_ERR_INVALID;
+  if (rk && (mem != WG_MEM_DEVICE || rk->N * 2 != n || !rk->A0 || !rk->A1 || !rk->samp || !rk->uz || rk->row_stride < mmax || rk->N > 255))
+    return WG_ERR_INVALID;
   wg_device_guard guard(ctx->device);
   QldState *st = state_of(ctx);
   if (q->shared_hessian && (st->shared_n != n || !st->d_hinv_shared))
@@ -829,9 +904,12 @@ int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q)
     a.S = st->d_hinv; a.h_stride = (long long)n * n; a.hfail = st->d_fail;
     a.C = d.C; a.c_stride = (long long)nmax * n;
   }
-  const size_t smem = qld_smem_bytes(n, mmax, a.qcap, bounds);
+  a.A0 = a.A1 = nullptr; a.samp = nullptr; a.row_stride = 0; a.uz = nullptr; a.N = 0;
+  if (rk) { a.A0 = rk->A0; a.A1 = rk->A1; a.samp = rk->samp; a.row_stride = rk->row_stride; a.uz = rk->uz; a.N = rk->N; }
+  const size_t smem = qld_smem_bytes(n, std::max(mmax, rk ? (4 * rk->N + QW - 1) / QW : 0), a.qcap, bounds);
   if (smem > 200 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "wg_qld_solve_batch: problem too large for shared memory");
-  WG_SMEM_ATTR(ctx, WG_ATTR_DENSEQP, qld_kernel, smem);
+  if (rk) WG_SMEM_ATTR(ctx, WG_ATTR_DENSEQP_RANKED, qld_kernel<true>, smem);
+  else WG_SMEM_ATTR(ctx, WG_ATTR_DENSEQP, qld_kernel<false>, smem);
   int per_sm = (int)std::min<size_t>(2, (220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   const int blocks = std::max(1, std::min(B, ctx->sm_count * per_sm));
@@ -842,13 +920,23 @@ int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q)
   a.next = st->d_next;
   WG_CUDA(ctx, cudaMemsetAsync(st->d_next, 0, sizeof(int), ctx->stream));
   wg_prof_start(ctx, WG_K_QLD);
-  qld_kernel<<<blocks, QT, smem, ctx->stream>>>(a);
+  if (rk) qld_kernel<true><<<blocks, QT, smem, ctx->stream>>>(a);
+  else qld_kernel<false><<<blocks, QT, smem, ctx->stream>>>(a);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   for (auto &dl : downloads)
     WG_CUDA(ctx, cudaMemcpyAsync(dl.first, dl.second.first, dl.second.second, cudaMemcpyDeviceToHost, ctx->stream));
   if (mem == WG_MEM_HOST) WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return WG_OK;
+}
+
+int wg_qld_solve_batch(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q) { return qld_solve_impl(ctx, mem, B, q, nullptr); }
+
+int wg_qld_solve_batch_ranked(wg_ctx *ctx, int mem, int B, const wg_qld_batch *q, const double *A0, const double *A1,
+                              const unsigned char *sample, long long row_stride, const double *uz_dev, int N)
+{
+  RankedRows rk = {A0, A1, sample, row_stride, uz_dev, N};
+  return qld_solve_impl(ctx, mem, B, q, &rk);
 }
 
 }  // extern "C"

@@ -101,7 +101,8 @@ inline void wg_prof_stop(wg_ctx *ctx)
 enum { WG_ATTR_PREVIEW_0 = 0, /* .. 5: {sim, nosim} x 3 CTA shapes */ WG_ATTR_HERDT_QP = 6, WG_ATTR_HERDT_MPC = 7,
        WG_ATTR_PLDP = 8, WG_ATTR_PLDP_RANKED = 9, WG_ATTR_ZMPDISC = 10, WG_ATTR_DIMITROV = 11, WG_ATTR_DENSEQP = 12,
        WG_ATTR_PREVIEW_ADD_0 = 13, /* .. 15: second-stage variant x 3 CTA shapes */
-       WG_ATTR_PREVIEW_POS_0 = 16, /* .. 21: position-only variant {sim, nosim} x 3 CTA shapes */ WG_ATTR_SLOTS = 24 };
+       WG_ATTR_PREVIEW_POS_0 = 16, /* .. 21: position-only variant {sim, nosim} x 3 CTA shapes */ WG_ATTR_DENSEQP_RANKED = 22,
+       WG_ATTR_SLOTS = 24 };
 extern "C" int wgi_smem_attr(wg_ctx *ctx, int slot, const void *func, size_t bytes);
 #define WG_SMEM_ATTR(ctx, slot, func, bytes)                                              \
   do {                                                                                    \

@@ -14,6 +14,7 @@
 #include "wg_common.h"
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <vector>
 
 extern "C" int wgi_fcals_launch(wg_ctx *ctx, int B, const int64_t *d_samp_off, const wg_foot_sample *left,
@@ -77,7 +78,7 @@ wieber_pre_kernel(int B, const WbConsts *__restrict__ Kp, const int64_t *__restr
                   const double *__restrict__ start_time, const int64_t *__restrict__ lci_off, const wg_lci *__restrict__ lci,
                   const int32_t *__restrict__ n_lci, const int *__restrict__ zd_status, const double *__restrict__ zmp,
                   WbWalk *__restrict__ walks, int32_t *__restrict__ m_out, double *__restrict__ Px, double *__restrict__ Pu,
-                  double *__restrict__ Dv)
+                  double *__restrict__ Dv, double *__restrict__ A0g, double *__restrict__ A1g, unsigned char *__restrict__ sampg)
 {
   __shared__ int s_poly[WB_MAXN], s_row0[WB_MAXN + 1];
   __shared__ int s_m, s_go;
@@ -148,7 +149,7 @@ wieber_pre_kernel(int B, const WbConsts *__restrict__ Kp, const int64_t *__restr
     }
     __syncthreads();
     // Px (:594-612)
-    double *Pxb = Px + (size_t)b * ld, *Pub = Pu + (size_t)b * ld * 2 * N;
+    double *Pxb = Px + (size_t)b * ld, *Pub = Pu ? Pu + (size_t)b * ld * 2 * N : nullptr;
     for (int r = t; r < m; r += WB_T) {
       const int i = s_ri[r];
       const wg_lci &P = L[s_poly[i]];
@@ -156,8 +157,11 @@ wieber_pre_kernel(int B, const WbConsts *__restrict__ Kp, const int64_t *__restr
       Pxb[r] = (s_xk[0] * K.sz[i][0] + s_xk[1] * K.sz[i][1] + s_xk[2] * K.sz[i][2]) * s_a0[r] +
                (s_xk[3] * K.sz[i][0] + s_xk[4] * K.sz[i][1] + s_xk[5] * K.sz[i][2]) * s_a1[r] + P.B[j];
     }
+    // rank-structured rows for wg_qld_solve_batch_ranked: (A_r(0), A_r(1), i_r) - 17 bytes per row instead of 2N doubles
+    if (A0g)
+      for (int r = t; r < m; r += WB_T) { A0g[(size_t)b * ld + r] = s_a0[r]; A1g[(size_t)b * ld + r] = s_a1[r]; sampg[(size_t)b * ld + r] = s_ri[r]; }
     // Pu (:613-626): element (r, k) = A_r(0) pz(i_r - k), (r, k + N) = A_r(1) pz(i_r - k), k <= i_r; zero elsewhere
-    for (int k = 0; k < N; ++k) {
+    for (int k = 0; Pu && k < N; ++k) {
       double *cx = Pub + (size_t)k * ld, *cy = Pub + (size_t)(k + N) * ld;
       for (int r = t; r < m; r += WB_T) {
         const int i = s_ri[r];
@@ -180,10 +184,11 @@ __global__ void __launch_bounds__(WB_T)
 wieber_post_kernel(int B, const WbConsts *__restrict__ Kp, const int64_t *__restrict__ samp_off,
                    const int32_t *__restrict__ m_in, const double *__restrict__ Px, const double *__restrict__ Pu,
                    const double *__restrict__ X, const int32_t *__restrict__ ifail, const int32_t *__restrict__ iters,
-                   WbWalk *__restrict__ walks, double *__restrict__ com, double *__restrict__ zmp)
+                   WbWalk *__restrict__ walks, double *__restrict__ com, double *__restrict__ zmp,
+                   const double *__restrict__ A0g, const double *__restrict__ A1g, const unsigned char *__restrict__ sampg)
 {
   __shared__ int s_bad;
-  __shared__ double s_x[2 * WB_MAXN];
+  __shared__ double s_x[2 * WB_MAXN], s_pt[2 * WB_MAXN];
   const WbConsts &K = *Kp;
   const int N = K.N, ld = K.ld, t = threadIdx.x;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -195,8 +200,22 @@ wieber_post_kernel(int B, const WbConsts *__restrict__ Kp, const int64_t *__rest
     for (int i = t; i < 2 * N; i += WB_T) s_x[i] = X[(size_t)b * 2 * N + i];
     __syncthreads();
     // vnlValConstraint = Pu X + Px >= -1e-8 (:1056-1105; a violated row makes the reference return -1)
-    const double *Pub = Pu + (size_t)b * ld * 2 * N, *Pxb = Px + (size_t)b * ld;
-    if (!s_bad)
+    const double *Pub = Pu ? Pu + (size_t)b * ld * 2 * N : nullptr, *Pxb = Px + (size_t)b * ld;
+    if (A0g) {
+      // rank-structured rows: Pu X = A_r(0) (Uz X_x)_i + A_r(1) (Uz X_y)_i
+      for (int e = t; e < 2 * N; e += WB_T) {
+        const int ax = e >= N, i = ax ? e - N : e;
+        double a = 0.0;
+        for (int k = 0; k <= i; ++k) a += K.pz[i - k] * s_x[ax * N + k];
+        s_pt[e] = a;
+      }
+      __syncthreads();
+      if (!s_bad)
+        for (int r = t; r < m; r += WB_T) {
+          const int i = sampg[(size_t)b * ld + r];
+          if (A0g[(size_t)b * ld + r] * s_pt[i] + A1g[(size_t)b * ld + r] * s_pt[N + i] + Pxb[r] < -1e-8) s_bad = 1;
+        }
+    } else if (!s_bad)
       for (int r = t; r < m; r += WB_T) {
         double s = 0.0;
         for (int j = 0; j < 2 * N; ++j) s += Pub[r + (size_t)j * ld] * s_x[j];
@@ -413,13 +432,18 @@ int wg_wieber_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *com_
   if ((rc = wb_ensure(ctx, H, 2, sizeof(int32_t) * 4 * nb)) != WG_OK) return rc;
   if ((rc = wb_ensure(ctx, H, 3, sizeof(WbWalk) * nb)) != WG_OK) return rc;
   if ((rc = wb_ensure(ctx, H, 4, sizeof(double) * nb * ld)) != WG_OK) return rc;
-  if ((rc = wb_ensure(ctx, H, 5, sizeof(double) * nb * ld * nv)) != WG_OK) return rc;
+  const bool dense = par.materialize_pu != 0;
+  if (dense) { if ((rc = wb_ensure(ctx, H, 5, sizeof(double) * nb * ld * nv)) != WG_OK) return rc; }
+  else { if ((rc = wb_ensure(ctx, H, 9, (sizeof(double) * 2 + 1) * nb * ld + 64)) != WG_OK) return rc; }
   if ((rc = wb_ensure(ctx, H, 6, sizeof(double) * nb * nv * 2)) != WG_OK) return rc;
   int64_t *d_lo = static_cast<int64_t *>(H->buf[0]);
   wg_lci *d_lci = static_cast<wg_lci *>(H->buf[1]);
   int32_t *d_nlci = static_cast<int32_t *>(H->buf[2]), *d_m = d_nlci + nb, *d_ifail = d_m + nb, *d_it = d_ifail + nb;
   WbWalk *d_walks = static_cast<WbWalk *>(H->buf[3]);
-  double *d_Px = static_cast<double *>(H->buf[4]), *d_Pu = static_cast<double *>(H->buf[5]);
+  double *d_Px = static_cast<double *>(H->buf[4]), *d_Pu = dense ? static_cast<double *>(H->buf[5]) : nullptr;
+  double *d_A0 = dense ? nullptr : static_cast<double *>(H->buf[9]), *d_A1 = dense ? nullptr : d_A0 + nb * ld;
+  unsigned char *d_samp = dense ? nullptr : reinterpret_cast<unsigned char *>(d_A1 + nb * ld);
+  const double *d_uz = reinterpret_cast<const double *>(reinterpret_cast<const char *>(H->d) + offsetof(WbConsts, pz));
   double *d_D = static_cast<double *>(H->buf[6]), *d_X = d_D + nb * nv;
   WG_CUDA(ctx, cudaMemcpyAsync(d_lo, lci_off.data(), sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, ctx->stream));
   WG_CUDA(ctx, cudaMemsetAsync(d_walks, 0, sizeof(WbWalk) * nb, ctx->stream));
@@ -436,19 +460,21 @@ int wg_wieber_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *com_
   wg_qld_batch q;
   std::memset(&q, 0, sizeof q);
   q.n = nv; q.nmax = nv; q.mmax = ld; q.shared_hessian = 1;
-  q.m = d_m; q.d = d_D; q.A = d_Pu; q.a_stride = (long long)ld * nv; q.b = d_Px; q.b_stride = ld;
+  q.m = d_m; q.d = d_D; q.A = d_Pu; q.a_stride = (long long)ld * nv; q.b = d_Px; q.b_stride = ld;   // A: dense mode only
   q.x = d_X; q.ifail = d_ifail; q.iterations = d_it;
   const int grid = std::max(1, std::min(B, ctx->sm_count * 4));
   for (int64_t li = 0; li < max_periods; ++li) {
     wg_prof_start(ctx, WG_K_WIEBER);
     wieber_pre_kernel<<<grid, WB_T, 0, ctx->stream>>>(B, H->d, V.d_samp_off, H->d_start, d_lo, d_lci, d_nlci, V.d_zd_status,
-                                                     d_zmp, d_walks, d_m, d_Px, d_Pu, d_D);
+                                                     d_zmp, d_walks, d_m, d_Px, d_Pu, d_D, d_A0, d_A1, d_samp);
     wg_prof_stop(ctx);
     WG_LAUNCHED(ctx);
-    if ((rc = wg_qld_solve_batch(ctx, WG_MEM_DEVICE, B, &q)) != WG_OK) return rc;
+    if (dense) rc = wg_qld_solve_batch(ctx, WG_MEM_DEVICE, B, &q);
+    else rc = wg_qld_solve_batch_ranked(ctx, WG_MEM_DEVICE, B, &q, d_A0, d_A1, d_samp, ld, d_uz, N);
+    if (rc != WG_OK) return rc;
     wg_prof_start(ctx, WG_K_WIEBER);
     wieber_post_kernel<<<grid, WB_T, 0, ctx->stream>>>(B, H->d, V.d_samp_off, d_m, d_Px, d_Pu, d_X, d_ifail, d_it, d_walks,
-                                                      d_com, d_zmp);
+                                                      d_com, d_zmp, d_A0, d_A1, d_samp);
     wg_prof_stop(ctx);
     WG_LAUNCHED(ctx);
   }

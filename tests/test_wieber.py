@@ -6,6 +6,8 @@ reference's).  The reference holds no golden data for this generator.
     whole CoM / ZMP output, bitwise.
   * GPU: wg_wieber_run_batch against the same object at north_star's tolerance (1e-6 m on CoM / ZMP).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -66,13 +68,19 @@ def walk_steps(nsteps=4, sx=0.2):
 
 
 @pytest.mark.gpu
-def test_gpu_wieber_generator_matches_reference_object(ctx, ref_gen):
+@pytest.mark.parametrize("materialize_pu", [0, 1])
+def test_gpu_wieber_generator_matches_reference_object(ctx, ref_gen, materialize_pu):
     """wg_wieber_run_batch (ZMPDiscretization -> polygons -> 150-variable QP per 20 ms -> LIPM, all on the device) on a ragged
     batch of walks against the reference's ZMPQPWithConstraint object code fed the feet / ZMP buffers of the restated
     ZMPDiscretization: every CoM / ZMP sample the loop writes within 1e-6 m (north_star), the same number of periods."""
     import jrl_walkgen_b200 as wg
     walks = [walk_steps(4, 0.2), walk_steps(3, 0.1), walk_steps(6, 0.25), zo.profile_steps("StraightWalking")]
     feet = np.array([zo.INIT_FEET] * len(walks), dtype=np.float64).reshape(len(walks), -1)
+    from jrl_walkgen_b200 import _capi
+    par = _capi.WieberParams()
+    ctx.lib.wg_wieber_default_params(C.byref(par))
+    par.materialize_pu = materialize_pu        # 0: rank-structured rows (default); 1: the dense Pu of the reference
+    ctx.wieber_set_params(par)
     out = ctx.wieber_run(walks, feet)
     assert (out["status"] == 0).all(), out["status"]
     so = out["sample_offsets"]
@@ -91,7 +99,7 @@ def test_gpu_wieber_generator_matches_reference_object(ctx, ref_gen):
         worst = max(worst, ec, ez)
         assert ec < 1e-6 and ez < 1e-6, (b, ec, ez)
         assert (com_r[rows:, :6] == 0).all() and (out["com"][o + rows:e] == 0).all()
-    print(f"wieber GPU vs reference object: max |CoM, ZMP| deviation {worst:.2e} m; periods {out['periods_done']}, "
+    print(f"wieber GPU ({'dense Pu' if materialize_pu else 'ranked rows'}) vs reference object: max |CoM, ZMP| deviation {worst:.2e} m; periods {out['periods_done']}, "
           f"active-set changes per QP {out['qp_iterations'].sum() / out['periods_done'].sum():.1f}")
 
 
