@@ -1024,6 +1024,26 @@ def run_cuda(args):
     barrier()
     launches = ctx.launches
     prof = ctx.prof_end()
+    sum_mode, fit_resid = ctx.preview_sum_info()
+
+    # ---- the same pass with the preview sum evaluated directly (the 320-tap FIR of preview_fused_kernel, FP64-pipe bound):
+    # the kernel the recursive evaluation replaced as the default, timed beside it on the same inputs
+    direct = None
+    if sum_mode == wg.PREVIEW_SUM_RECURSIVE:
+        ctx.preview_set_sum_mode(wg.PREVIEW_SUM_DIRECT)
+        dpasses = max(8, passes // 4)
+        for _ in range(4):
+            one_pass()
+        barrier()
+        ctx.prof_begin(dpasses * max(1, args.steps // 4) + 8)
+        ctx.timer_start()
+        for _ in range(max(1, args.steps // 4) * dpasses):
+            one_pass()
+        d_ms = ctx.timer_stop_ms()
+        dprof = ctx.prof_end()
+        barrier()
+        ctx.preview_set_sum_mode(wg.PREVIEW_SUM_AUTO)
+        direct = {"ms_total": d_ms, "passes": max(1, args.steps // 4) * dpasses, "kernel_avg_ms": dprof[6][1] / dprof[6][0]}
 
     # ---- end-to-end leg: host buffers through the C ABI (H2D + kernels + D2H inside) ---------
     zp = ctx.pinned(z.shape); zp[:] = z
@@ -1079,7 +1099,8 @@ def run_cuda(args):
             "how": "4 x 256 MB pinned copies per direction per rank, all ranks at once"}
 
     # ---- max over ranks ----------------------------------------------------------------------
-    (ms_total, e2e_s, e2e_pos_s), (total_steps_all,) = reduce_over_ranks(dist, [ms_total, e2e_s, e2e_pos_s], [float(steps_per_pass)])
+    d_ms_all = direct["ms_total"] if direct else 0.0
+    (ms_total, e2e_s, e2e_pos_s, d_ms_all), (total_steps_all,) = reduce_over_ranks(dist, [ms_total, e2e_s, e2e_pos_s, d_ms_all], [float(steps_per_pass)])
     ms_per_step = ms_total / args.steps
     value = total_steps_all * passes / (ms_per_step * 1e-3)
     e2e_value = total_steps_all * e2e_steps / e2e_s
@@ -1174,20 +1195,26 @@ def run_cuda(args):
         kern = {names.get(k, str(k)): {"launches": v[0], "avg_ms": v[1] / v[0]} for k, v in prof.items()}
         dom = max(kern.items(), key=lambda kv: kv[1]["avg_ms"] * kv[1]["launches"])
         dom_name, dom_ms = dom[0], dom[1]["avg_ms"]
-        if dom_name == "preview_recur_kernel":
-            # 4-state recursion: streams fir(16 B) + zmpref(16 B) in, CoM(48 B) + ZMP(16 B) out per step
-            ach = 96.0 * steps_per_pass / (dom_ms * 1e-3) / 1e9
+        fp64_src = ("measured live: register-resident DFMA chains on all SMs (wg_measure_fp64_peak); "
+                    "MEASURED_PEAKS.json has no FP64 entry")
+        if sum_mode == wg.PREVIEW_SUM_RECURSIVE:
+            # preview_rec_kernel: the window sum as a backward linear recurrence (~170 FMA per step for everything): the
+            # kernel streams 16 B in and 64 B out per step and is bounded by HBM, SURVEY 8(d)'s 80 B per step
+            dom_name = "preview_rec_kernel"
+            kern = {dom_name: kern.pop("preview_fused_kernel")}
+            ach = BYTES_PER_STEP * steps_per_pass / (dom_ms * 1e-3) / 1e9
             roof = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                    "algorithmic_bytes_per_step": 96.0}
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src + ", burst copy figure",
+                    "algorithmic_bytes_per_step": BYTES_PER_STEP,
+                    "fp64_frac_on_the_direct_sum_flop_model": FLOP_PER_STEP * steps_per_pass / (dom_ms * 1e-3) / 1e12 / fp64_peak,
+                    "note": "the direct-sum flop model (1360 flop per step) no longer describes the work: the recursive "
+                            "evaluation executes ~340 flop per step; see direct_sum for the FIR kernel on the same inputs"}
         else:
             fl = (FIR_FLOP_PER_STEP if dom_name == "preview_fir_kernel" else FLOP_PER_STEP)
             ach = fl * steps_per_pass / (dom_ms * 1e-3) / 1e12
             roof = {"kernel": dom_name, "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": ach / fp64_peak, "traffic": None,
-                    "peak_source": "measured live: register-resident DFMA chains on all SMs (wg_measure_fp64_peak); "
-                                   "MEASURED_PEAKS.json has no FP64 entry",
-                    "algorithmic_flop_per_step": fl}
+                    "peak_source": fp64_src, "algorithmic_flop_per_step": fl}
         roof["hbm_frac_streaming_minimum"] = BYTES_PER_STEP * steps_per_pass * passes / (ms_per_step * 1e-3) / 1e9 / hbm_peak
         roof["algorithmic_bytes_per_launch"] = BYTES_PER_STEP * steps_per_pass
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this (seeded, deterministic) workload: not
@@ -1195,6 +1222,18 @@ def run_cuda(args):
         # capture of this same command (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); null when
         # that file has no entry for this kernel and batch size.
         roof.update(ncu_traffic(dom_name, args.walks))
+        direct_line = None
+        if direct:
+            d_ms_pass = d_ms_all / direct["passes"]
+            d_ach = FLOP_PER_STEP * steps_per_pass / (direct["kernel_avg_ms"] * 1e-3) / 1e12
+            direct_line = {"kernel": "preview_fused_kernel", "value": total_steps_all / (d_ms_pass * 1e-3), "unit": UNIT,
+                           "ms_per_pass": d_ms_pass, "passes": direct["passes"],
+                           "roofline": dict({"bound": "fp64", "achieved": d_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                                             "frac": d_ach / fp64_peak, "peak_source": fp64_src,
+                                             "algorithmic_flop_per_step": FLOP_PER_STEP},
+                                            **ncu_traffic("preview_fused_kernel", args.walks)),
+                           "how": "wg_preview_set_sum_mode(WG_PREVIEW_SUM_DIRECT): the 320-tap sum as written in "
+                                  "PreviewControl.cpp:346-352, same inputs, device resident"}
         cpu = None
         if world == 1:
             subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
@@ -1205,7 +1244,9 @@ def run_cuda(args):
                 "config": {"workload": WORKLOAD, "walks_per_gpu": B, "NL": 320, "T": 0.005,
                            "preview_steps_per_pass_per_gpu": steps_per_pass, "passes_per_step": passes,
                            "l2": "inputs+outputs per pass (%.2f GB) exceed the 126 MB L2" % ((n * 80) / 1e9)},
-                "roofline": roof, "kernels": dict(kern, **(herdt_kern or {})), "fp64_peak_tflops_measured": fp64_peak,
+                "roofline": roof, "preview_sum": {"mode": "recursive" if sum_mode == wg.PREVIEW_SUM_RECURSIVE else "direct",
+                                                  "fit_residual_relative": fit_resid, "direct_sum": direct_line},
+                "kernels": dict(kern, **(herdt_kern or {})), "fp64_peak_tflops_measured": fp64_peak,
                 "herdt": herdt, "pldp": pldp, "kajita_front_end": kajita, "dimitrov_front_to_back": dimitrov, "wieber_front_to_back": wieber, "sweep": sweep,
                 "herdt_qp_solves_per_s": None if herdt is None else herdt["qp_solves_per_s"],
                 "herdt_qp_solves_per_s_e2e": None if herdt is None else herdt["e2e"]["value"],

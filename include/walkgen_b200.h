@@ -153,6 +153,22 @@ int wg_preview_gains_batch(wg_ctx *ctx, int mem, int B, const double *params, in
 /* Upload gains to the context (constant memory image used by the kernels). */
 int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *gains);
 
+/* How the batched kernels evaluate the preview sum  sum_{i<NL} F[i] p[k+i]  of OneIterationOfPreview (PreviewControl.cpp:346-352).
+ * The weights OptimalControllerSolver::ComputeWeights produces are F[i] = (1/(R+b'Pb)) b' ((A-bK)')^i P c'Q
+ * (OptimalControllerSolver.cpp:323-345), a matrix-geometric sequence, so the sum obeys a stable BACKWARD linear recurrence in k
+ * and costs ~70 flop per tick instead of 1280: the batch run becomes HBM bound instead of FP64 bound.  wg_preview_set_gains fits
+ * that structure to the table it is given (extended precision); when sum_i |F[i] - fit| <= WG_PREVIEW_REC_TOL * sum_i |F[i]| the
+ * recursive kernel is used (AUTO), otherwise - e.g. a table read from a file with few digits - the direct 320-tap sum.  The two
+ * differ by the summation order of the same products: ~1e-14 relative on the sum, < 1e-12 m on CoM / ZMP (tests/test_preview*.py).
+ *   DIRECT    always the direct sum
+ *   RECURSIVE refuse (WG_ERR_INVALID) instead of falling back when the weights do not have the structure
+ * wg_preview_sum_info: which of the two the next run uses, and the fit residual (relative; -1: no fit possible). */
+enum { WG_PREVIEW_SUM_AUTO = 0, WG_PREVIEW_SUM_DIRECT = 1, WG_PREVIEW_SUM_RECURSIVE = 2 };
+#define WG_PREVIEW_REC_TOL 1e-12
+double wg_preview_sum_fit(const wg_preview_gains_t *gains);   /* host only: the relative fit residual of a gain set, -1: none */
+int wg_preview_set_sum_mode(wg_ctx *ctx, int mode);
+int wg_preview_sum_info(wg_ctx *ctx, int *mode_in_use, double *fit_residual);
+
 /* A plan describes a ragged batch of B trajectories: trajectory b owns ZMP-reference samples
  * [offsets[b], offsets[b+1]) of a packed array of interleaved (px,py) pairs.  A trajectory of L
  * samples yields L-NL+1 preview steps (step k consumes the window [k, k+NL), exactly what

@@ -72,6 +72,9 @@ def zmpdisc_default_params() -> "_capi.ZmpDiscParams":
     return p
 
 
+PREVIEW_SUM_AUTO, PREVIEW_SUM_DIRECT, PREVIEW_SUM_RECURSIVE = 0, 1, 2   # wg_preview_set_sum_mode
+
+
 def preview_gains(T=0.005, preview_time=1.6, zc=0.814, mode=MODE_WITHOUT_INITIALPOS) -> PreviewGains:
     """Host Riccati solve: PreviewControl::ComputeOptimalWeights (PreviewControl.cpp:198-322)."""
     g = PreviewGains()
@@ -189,6 +192,16 @@ class Context:
     def preview_set_gains(self, gains: PreviewGains):
         self._check(self.lib.wg_preview_set_gains(self.h, C.byref(gains)))
         self.gains = gains
+
+    def preview_set_sum_mode(self, mode: int):
+        """wg_preview_set_sum_mode: PREVIEW_SUM_AUTO / _DIRECT / _RECURSIVE."""
+        self._check(self.lib.wg_preview_set_sum_mode(self.h, int(mode)))
+
+    def preview_sum_info(self):
+        """(mode in use, relative residual of the fit F[i] = w' L^i v) - wg_preview_sum_info."""
+        m, r = C.c_int(0), C.c_double(0.0)
+        self._check(self.lib.wg_preview_sum_info(self.h, C.byref(m), C.byref(r)))
+        return m.value, r.value
 
     def preview_plan(self, offsets) -> "PreviewPlan":
         return PreviewPlan(self, offsets)

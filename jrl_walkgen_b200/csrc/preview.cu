@@ -307,6 +307,13 @@ struct PreviewConsts {
   // One tick is X' = M X + g f + h p (f = preview sum, p = ZMP reference of the tick).  State after the FIR_R ticks
   // of a thread started from zero: sum_r G[sim][r] f_r + H[sim][r] p_r with G[r] = M^(FIR_R-1-r) g, same for H.
   double G[2][FIR_R][4], H[2][FIR_R][4];
+  // ---- recursive evaluation of the preview sum (preview_rec_kernel; see rec_setup): the window weights of
+  // OptimalControllerSolver::ComputeWeights are F[i] = w' L^i v with L = (A - b K)' (OptimalControllerSolver.cpp:323-345), so
+  // W_k = sum_{i<NL} L^i v p[k+i] obeys the BACKWARD recurrence W_k = L W_{k+1} + v p[k] - (L^NL v) p[k+NL], f_k = w' W_k.
+  double RF0[FIR_R], RFN[FIR_R];       // w' L^i v and w' L^(NL+i) v, i < FIR_R: the local triangular sums of a thread
+  double RV[FIR_R][4], RVN[FIR_R][4];  // L^r v and L^(NL+r) v: a thread's local total sum_r RV[r] p[r] - RVN[r] p[r+NL]
+  double RW[FIR_R + 1][4];             // rows w' L^j, j = 0..FIR_R: tick r of a thread adds RW[FIR_R - r] . W_in
+  double RP[SCAN_LEVELS][16];          // L^(FIR_R 2^l), row-major
 };
 __constant__ PreviewConsts c_pc;
 __constant__ double c_F[WG_PREVIEW_MAX_NL + 8];
@@ -620,6 +627,340 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// preview_rec_kernel: the same batch run with the preview sum evaluated RECURSIVELY (HBM bound instead of FP64 bound).
+//
+// The window weights of the reference are F[i] = w' L^i v (see rec_setup), so with W_k = sum_{i<NL} L^i v p[k+i]
+//     f_k = w' W_k,      W_k = L W_{k+1} + v p[k] - (L^NL v) p[k+NL]        (spectral radius of L: 0.983)
+// a stable BACKWARD linear recurrence: 1280 flop of window sum per tick become ~70.  Per tile of 8 x THREADS ticks:
+//   (1a) W at the tile's end directly from the halo samples already staged in shared memory (sum_{i<NL} E[i] p[end+i],
+//        one table row per sample, reduced over the CTA): tiles stay independent of each other and of the processing order;
+//   (1b) every thread: its 8 ticks from a zero end state - the 8-tap triangular sums with F[0..7] and -F[NL..NL+7] - and
+//        its local total sum_r L^r (v p[r] - L^NL v p[r+NL]);
+//   (1c) Kogge-Stone scan over threads, running DOWN the tile (shuffle-down, constant matrices L^(8 d)), warp totals through
+//        shared memory, the per-lane power (L^8)^(31-lane) of the state entering the warp from a 4 KB table;
+//   (1d) f of tick r += (w' L^(8-r)) . (true W at the thread's end).
+// Then phases (2a)-(2d) of preview_fused_kernel unchanged (forward scan of the cart-table state, staged stores).
+// Deviation of f from the direct sum: 1e-14 relative (it is a different summation order of the same 320 products);
+// measured on CoM / ZMP against the reference's object code: see tests/test_preview_ref.py.
+// ---------------------------------------------------------------------------------------------
+template <bool SIM, int FIR_THREADS, int MIN_CTAS, bool ADD = false, bool POS = false>
+__global__ void __launch_bounds__(FIR_THREADS, MIN_CTAS)
+preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ offsets,
+                   const double2 *__restrict__ p, double *__restrict__ state, double *__restrict__ com,
+                   double *__restrict__ zmp, const double *__restrict__ com_add, const double2 *__restrict__ Etab,
+                   const double2 *__restrict__ lanepow)
+{
+  constexpr int FIR_TILE = FIR_R * FIR_THREADS;   // ticks per tile
+  constexpr int NW = FIR_THREADS / 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ double2 sp[];             // padded tile of (px,py), then the store staging area
+  __shared__ double s_tot[NW + 1][8];         // warp totals of the forward scan (x axis 0..3, y axis 4..7)
+  __shared__ double s_totb[NW + 1][8];        // warp totals of the backward scan
+  __shared__ double s_halo[NW][8];            // per-warp partial sums of W at the tile's end
+  __shared__ double s_carry[8];
+  const int b = order[blockIdx.x];
+  const int64_t o = offsets[b];
+  const int L = (int)(offsets[b + 1] - o);
+  const int NL = c_pc.NL, NLpad = c_pc.NLpad;
+  const int nsteps = L - NL + 1;
+  if (nsteps <= 0) return;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int span = FIR_TILE + NLpad;           // samples one tile needs
+  if (t < 8) s_carry[t] = state[8 * (size_t)b + t];   // {x,dx,ddx,y,dy,ddy,sx,sy}
+  const double(*Pm)[16] = c_pc.P[SIM ? 1 : 0];
+
+  for (int start = 0; start < nsteps; start += FIR_TILE) {
+    __syncthreads();
+    const double2 *src = p + o + start;
+    const int avail = L - start;               // samples that exist from `start` on; the rest of the tile reads as zero
+    for (int e = t; e < span; e += FIR_THREADS) {
+      double2 v = make_double2(0.0, 0.0);
+      if (e < avail) v = __ldg(src + e);
+      sp[pad9(e)] = v;
+    }
+    __syncthreads();
+
+    // ---- (1a) W at the tile's end (x: h[0..3], y: h[4..7]), partial sums of this thread's halo samples
+    {
+      double h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = 0.0;
+      for (int i = t; i < NL; i += FIR_THREADS) {
+        const double2 e01 = __ldg(Etab + 2 * i), e23 = __ldg(Etab + 2 * i + 1);
+        const double2 q = sp[pad9(FIR_TILE + i)];
+        h[0] = fma(e01.x, q.x, h[0]); h[1] = fma(e01.y, q.x, h[1]); h[2] = fma(e23.x, q.x, h[2]); h[3] = fma(e23.y, q.x, h[3]);
+        h[4] = fma(e01.x, q.y, h[4]); h[5] = fma(e01.y, q.y, h[5]); h[6] = fma(e23.x, q.y, h[6]); h[7] = fma(e23.y, q.y, h[7]);
+      }
+      // warp sum of 8 values with 9 shuffles: halve the set of values a lane carries at each of the first three levels
+      double k4[4], k2[2], k1;
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double send = up ? h[j] : h[4 + j];
+          k4[j] = (up ? h[4 + j] : h[j]) + __shfl_xor_sync(FULL, send, 16);
+        }
+      }
+      {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double send = up ? k4[j] : k4[2 + j];
+          k2[j] = (up ? k4[2 + j] : k4[j]) + __shfl_xor_sync(FULL, send, 8);
+        }
+      }
+      {
+        const bool up = (lane & 4) != 0;
+        const double send = up ? k2[0] : k2[1];
+        k1 = (up ? k2[1] : k2[0]) + __shfl_xor_sync(FULL, send, 4);
+      }
+      k1 += __shfl_xor_sync(FULL, k1, 2);
+      k1 += __shfl_xor_sync(FULL, k1, 1);
+      if ((lane & 3) == 0) s_halo[w][((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0)] = k1;
+    }
+
+    // ---- (1b) local pass: ax[r], ay[r] = the part of f of tick 8t + r that comes from this thread's own 8 samples and
+    //      their partners NL further on; (bx, by) = the thread's total, W at tick 8t for a zero state at tick 8t + 8
+    double ax[FIR_R], ay[FIR_R];
+    double2 pk[FIR_R];                          // the thread's own ZMP reference (the `ZMPPositions[lindex]` of the integrator)
+    Axis bx, by;
+    bx.x0 = bx.x1 = bx.x2 = bx.s = 0.0;
+    by = bx;
+    {
+      const double2 *own = sp + pad9(FIR_R * t);
+#pragma unroll
+      for (int r = 0; r < FIR_R; ++r) { ax[r] = 0.0; ay[r] = 0.0; }
+#pragma unroll
+      for (int j = 0; j < FIR_R; ++j) {
+        const double2 a = own[j];
+        const double2 f = sp[pad9(FIR_R * t + j + NL)];
+        pk[j] = SIM ? a : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r <= j; ++r) {
+          ax[r] = fma(c_pc.RF0[j - r], a.x, ax[r]); ax[r] = fma(c_pc.RFN[j - r], f.x, ax[r]);
+          ay[r] = fma(c_pc.RF0[j - r], a.y, ay[r]); ay[r] = fma(c_pc.RFN[j - r], f.y, ay[r]);
+        }
+        bx.x0 = fma(c_pc.RV[j][0], a.x, bx.x0); bx.x0 = fma(c_pc.RVN[j][0], f.x, bx.x0);
+        bx.x1 = fma(c_pc.RV[j][1], a.x, bx.x1); bx.x1 = fma(c_pc.RVN[j][1], f.x, bx.x1);
+        bx.x2 = fma(c_pc.RV[j][2], a.x, bx.x2); bx.x2 = fma(c_pc.RVN[j][2], f.x, bx.x2);
+        bx.s = fma(c_pc.RV[j][3], a.x, bx.s); bx.s = fma(c_pc.RVN[j][3], f.x, bx.s);
+        by.x0 = fma(c_pc.RV[j][0], a.y, by.x0); by.x0 = fma(c_pc.RVN[j][0], f.y, by.x0);
+        by.x1 = fma(c_pc.RV[j][1], a.y, by.x1); by.x1 = fma(c_pc.RVN[j][1], f.y, by.x1);
+        by.x2 = fma(c_pc.RV[j][2], a.y, by.x2); by.x2 = fma(c_pc.RVN[j][2], f.y, by.x2);
+        by.s = fma(c_pc.RV[j][3], a.y, by.s); by.s = fma(c_pc.RVN[j][3], f.y, by.s);
+      }
+    }
+    // ---- (1c) Kogge-Stone scan DOWN the tile: c_t += L^(8d) c_{t+d} (segmented per warp)
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      const int d = 1 << l;
+      const double a0 = __shfl_down_sync(FULL, bx.x0, d), a1 = __shfl_down_sync(FULL, bx.x1, d);
+      const double a2 = __shfl_down_sync(FULL, bx.x2, d), a3 = __shfl_down_sync(FULL, bx.s, d);
+      const double b0 = __shfl_down_sync(FULL, by.x0, d), b1 = __shfl_down_sync(FULL, by.x1, d);
+      const double b2 = __shfl_down_sync(FULL, by.x2, d), b3 = __shfl_down_sync(FULL, by.s, d);
+      if (lane + d < 32) {
+        scan_combine(bx, c_pc.RP[l], a0, a1, a2, a3);
+        scan_combine(by, c_pc.RP[l], b0, b1, b2, b3);
+      }
+    }
+    if (lane == 0) {
+      double *n = s_totb[w];
+      n[0] = bx.x0; n[1] = bx.x1; n[2] = bx.x2; n[3] = bx.s;
+      n[4] = by.x0; n[5] = by.x1; n[6] = by.x2; n[7] = by.s;
+    }
+    __syncthreads();      // every read of the tile buffer is done: it becomes the store staging area below
+    {
+      // state entering this warp from above: V_(NW-1) = W at the tile's end, V_(u-1) = T_u + L^256 V_u
+      Axis vx, vy;
+      vx.x0 = vx.x1 = vx.x2 = vx.s = 0.0;
+      vy = vx;
+#pragma unroll
+      for (int u = 0; u < NW; ++u) {
+        vx.x0 += s_halo[u][0]; vx.x1 += s_halo[u][1]; vx.x2 += s_halo[u][2]; vx.s += s_halo[u][3];
+        vy.x0 += s_halo[u][4]; vy.x1 += s_halo[u][5]; vy.x2 += s_halo[u][6]; vy.s += s_halo[u][7];
+      }
+      for (int u = NW - 1; u > w; --u) {
+        const double *n = s_totb[u];
+        Axis nx, ny;
+        nx.x0 = n[0]; nx.x1 = n[1]; nx.x2 = n[2]; nx.s = n[3];
+        ny.x0 = n[4]; ny.x1 = n[5]; ny.x2 = n[6]; ny.s = n[7];
+        scan_combine(nx, c_pc.RP[5], vx.x0, vx.x1, vx.x2, vx.s);
+        scan_combine(ny, c_pc.RP[5], vy.x0, vy.x1, vy.x2, vy.s);
+        vx = nx; vy = ny;
+      }
+      // true W at this thread's end (tick 8t + 8) = inclusive result of lane + 1 (nothing for lane 31) + (L^8)^(31-lane) V
+      Axis ix, iy;
+      ix.x0 = __shfl_down_sync(FULL, bx.x0, 1); ix.x1 = __shfl_down_sync(FULL, bx.x1, 1);
+      ix.x2 = __shfl_down_sync(FULL, bx.x2, 1); ix.s = __shfl_down_sync(FULL, bx.s, 1);
+      iy.x0 = __shfl_down_sync(FULL, by.x0, 1); iy.x1 = __shfl_down_sync(FULL, by.x1, 1);
+      iy.x2 = __shfl_down_sync(FULL, by.x2, 1); iy.s = __shfl_down_sync(FULL, by.s, 1);
+      if (lane == 31) { ix.x0 = ix.x1 = ix.x2 = ix.s = 0.0; iy = ix; }
+      {
+        const double2 *lp = lanepow + 8 * (31 - lane);
+        double Pl[16];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const double2 q = __ldg(lp + e); Pl[2 * e] = q.x; Pl[2 * e + 1] = q.y; }
+        scan_combine(ix, Pl, vx.x0, vx.x1, vx.x2, vx.s);
+        scan_combine(iy, Pl, vy.x0, vy.x1, vy.x2, vy.s);
+      }
+      // ---- (1d) f of tick r += (w' L^(8 - r)) . W_in
+#pragma unroll
+      for (int r = 0; r < FIR_R; ++r) {
+        const double *g = c_pc.RW[FIR_R - r];
+        ax[r] = fma(g[0], ix.x0, fma(g[1], ix.x1, fma(g[2], ix.x2, fma(g[3], ix.s, ax[r]))));
+        ay[r] = fma(g[0], iy.x0, fma(g[1], iy.x1, fma(g[2], iy.x2, fma(g[3], iy.s, ay[r]))));
+      }
+    }
+
+    // ---- (2a) local aggregate of the cart-table recursion (as preview_fused_kernel)
+    Axis cx, cy, inx, iny;
+    cx.x0 = cx.x1 = cx.x2 = cx.s = 0.0;
+    cy.x0 = cy.x1 = cy.x2 = cy.s = 0.0;
+    inx = cx; iny = cy;
+    {
+      const double(*Gm)[4] = c_pc.G[SIM ? 1 : 0];
+      const double(*Hm)[4] = c_pc.H[SIM ? 1 : 0];
+#pragma unroll
+      for (int r = 0; r < FIR_R; ++r) {
+        cx.x0 = fma(Gm[r][0], ax[r], cx.x0); cx.x1 = fma(Gm[r][1], ax[r], cx.x1);
+        cx.x2 = fma(Gm[r][2], ax[r], cx.x2); cx.s = fma(Gm[r][3], ax[r], cx.s);
+        cy.x0 = fma(Gm[r][0], ay[r], cy.x0); cy.x1 = fma(Gm[r][1], ay[r], cy.x1);
+        cy.x2 = fma(Gm[r][2], ay[r], cy.x2); cy.s = fma(Gm[r][3], ay[r], cy.s);
+        if (SIM) {
+          cx.x0 = fma(Hm[r][0], pk[r].x, cx.x0); cx.x1 = fma(Hm[r][1], pk[r].x, cx.x1);
+          cx.x2 = fma(Hm[r][2], pk[r].x, cx.x2); cx.s = fma(Hm[r][3], pk[r].x, cx.s);
+          cy.x0 = fma(Hm[r][0], pk[r].y, cy.x0); cy.x1 = fma(Hm[r][1], pk[r].y, cy.x1);
+          cy.x2 = fma(Hm[r][2], pk[r].y, cy.x2); cy.s = fma(Hm[r][3], pk[r].y, cy.s);
+        }
+      }
+      if (t == 0) {
+        inx.x0 = s_carry[0]; inx.x1 = s_carry[1]; inx.x2 = s_carry[2]; inx.s = s_carry[6];
+        iny.x0 = s_carry[3]; iny.x1 = s_carry[4]; iny.x2 = s_carry[5]; iny.s = s_carry[7];
+        scan_combine(cx, Pm[0], inx.x0, inx.x1, inx.x2, inx.s);
+        scan_combine(cy, Pm[0], iny.x0, iny.x1, iny.x2, iny.s);
+      }
+    }
+    // ---- (2b) Kogge-Stone scan UP the tile: c_t += M^(8d) c_{t-d}
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      const int d = 1 << l;
+      const double a0 = __shfl_up_sync(FULL, cx.x0, d), a1 = __shfl_up_sync(FULL, cx.x1, d);
+      const double a2 = __shfl_up_sync(FULL, cx.x2, d), a3 = __shfl_up_sync(FULL, cx.s, d);
+      const double b0 = __shfl_up_sync(FULL, cy.x0, d), b1 = __shfl_up_sync(FULL, cy.x1, d);
+      const double b2 = __shfl_up_sync(FULL, cy.x2, d), b3 = __shfl_up_sync(FULL, cy.s, d);
+      if (lane >= d) {
+        scan_combine(cx, Pm[l], a0, a1, a2, a3);
+        scan_combine(cy, Pm[l], b0, b1, b2, b3);
+      }
+    }
+    if (lane == 31) {
+      double *n = s_tot[w];
+      n[0] = cx.x0; n[1] = cx.x1; n[2] = cx.x2; n[3] = cx.s;
+      n[4] = cy.x0; n[5] = cy.x1; n[6] = cy.x2; n[7] = cy.s;
+    }
+    __syncthreads();
+    // ---- (2c) true start state of this thread = inclusive result of thread t-1
+    Axis sx, sy;
+    {
+      Axis vx, vy;                         // W_w, the state entering this warp
+      vx.x0 = vx.x1 = vx.x2 = vx.s = 0.0;
+      vy.x0 = vy.x1 = vy.x2 = vy.s = 0.0;
+      for (int v = 0; v < w; ++v) {        // W_{v+1} = M^256 W_v + T_v
+        const double *n = s_tot[v];
+        Axis nx, ny;
+        nx.x0 = n[0]; nx.x1 = n[1]; nx.x2 = n[2]; nx.s = n[3];
+        ny.x0 = n[4]; ny.x1 = n[5]; ny.x2 = n[6]; ny.s = n[7];
+        scan_combine(nx, Pm[5], vx.x0, vx.x1, vx.x2, vx.s);
+        scan_combine(ny, Pm[5], vy.x0, vy.x1, vy.x2, vy.s);
+        vx = nx; vy = ny;
+      }
+      const Axis wx_in = vx, wy_in = vy;
+      if (w > 0) {
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          if (((lane + 1) >> l) & 1) {
+            Axis zx, zy;
+            zx.x0 = zx.x1 = zx.x2 = zx.s = 0.0;
+            zy.x0 = zy.x1 = zy.x2 = zy.s = 0.0;
+            scan_combine(zx, Pm[l], vx.x0, vx.x1, vx.x2, vx.s);
+            scan_combine(zy, Pm[l], vy.x0, vy.x1, vy.x2, vy.s);
+            vx = zx; vy = zy;
+          }
+        }
+        cx.x0 += vx.x0; cx.x1 += vx.x1; cx.x2 += vx.x2; cx.s += vx.s;
+        cy.x0 += vy.x0; cy.x1 += vy.x1; cy.x2 += vy.x2; cy.s += vy.s;
+      }
+      sx.x0 = __shfl_up_sync(FULL, cx.x0, 1); sx.x1 = __shfl_up_sync(FULL, cx.x1, 1);
+      sx.x2 = __shfl_up_sync(FULL, cx.x2, 1); sx.s = __shfl_up_sync(FULL, cx.s, 1);
+      sy.x0 = __shfl_up_sync(FULL, cy.x0, 1); sy.x1 = __shfl_up_sync(FULL, cy.x1, 1);
+      sy.x2 = __shfl_up_sync(FULL, cy.x2, 1); sy.s = __shfl_up_sync(FULL, cy.s, 1);
+      if (lane == 0) {
+        if (w == 0) { sx = inx; sy = iny; }
+        else { sx = wx_in; sy = wy_in; }
+      }
+    }
+    // ---- (2d) final pass and staged stores (as preview_fused_kernel)
+    const int k0 = start + FIR_R * t;
+    const int last = min(start + FIR_TILE, nsteps) - 1;   // last valid tick of this tile
+    {
+      constexpr int CHUNK_C = 7, CHUNK_Z = 3;     // double2 per lane and round: 6 (+1 pad) of CoM, 2 (+1 pad) of ZMP
+      double2 *stg_c = sp + w * (32 * (CHUNK_C + CHUNK_Z));
+      double2 *stg_z = stg_c + 32 * CHUNK_C;
+      const int kw = start + FIR_R * (t & ~31);   // first tick of this warp
+      double2 *gc = reinterpret_cast<double2 *>(com) + 3 * (o + kw);
+      double2 *gz = reinterpret_cast<double2 *>(zmp) + (o + kw);
+#pragma unroll
+      for (int j = 0; j < FIR_R / 2; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = 2 * j + h;
+          if (k0 + r <= last) {
+            const double zx = preview_tick<SIM>(sx, ax[r], pk[r].x);
+            const double zy = preview_tick<SIM>(sy, ay[r], pk[r].y);
+            double2 *q = stg_c + CHUNK_C * lane + 3 * h;
+            q[0] = make_double2(sx.x0, sx.x1);
+            q[1] = make_double2(sx.x2, sy.x0);
+            q[2] = make_double2(sy.x1, sy.x2);
+            stg_z[CHUNK_Z * lane + h] = POS ? make_double2(sx.x0, sy.x0) : make_double2(zx, zy);
+          }
+        }
+        __syncwarp();
+        if (com) {
+#pragma unroll
+          for (int it = 0; it < 6; ++it) {
+            const int idx = 32 * it + lane, c = idx / 6, part = idx - 6 * c;
+            const int row = kw + FIR_R * c + 2 * j;             // first of the two ticks of lane c in this round
+            if (row + (part >= 3) <= last) {
+              double2 v = stg_c[CHUNK_C * c + part];
+              if (ADD) {
+                const double2 a = __ldg(reinterpret_cast<const double2 *>(com_add) + 3 * (o + kw) + 3 * (FIR_R * c + 2 * j) + part);
+                v.x += a.x; v.y += a.y;
+              }
+              gc[3 * (FIR_R * c + 2 * j) + part] = v;
+            }
+          }
+        }
+        if (zmp) {
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int idx = 32 * it + lane, c = idx >> 1, part = idx & 1;
+            const int row = kw + FIR_R * c + 2 * j + part;
+            if (row <= last) gz[FIR_R * c + 2 * j + part] = stg_z[CHUNK_Z * c + part];
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (k0 <= last && last < k0 + FIR_R) {   // the thread that ran the tile's last valid tick carries the state
+      s_carry[0] = sx.x0; s_carry[1] = sx.x1; s_carry[2] = sx.x2; s_carry[6] = sx.s;
+      s_carry[3] = sy.x0; s_carry[4] = sy.x1; s_carry[5] = sy.x2; s_carry[7] = sy.s;
+    }
+  }
+  __syncthreads();
+  if (t < 8) state[8 * (size_t)b + t] = s_carry[t];
+}
+
+// ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
 namespace {
@@ -675,6 +1016,148 @@ void scan_matrices(const wg_preview_gains_t &g, bool sim, double (*P)[16], doubl
   }
 }
 
+
+// Constants of preview_rec_kernel.  The window weights are fitted as F[i] = w' L^i v in extended precision: L = (A - b K)' is
+// formed from the head of the gain set (for MODE_WITHOUT_INITIALPOS the augmented error system of PreviewControl.cpp:237-262
+// with K = (Ks, Kx)), w = b, and v is the least-squares solution of the NL x n system (column-scaled, Gram-Schmidt twice).
+// Weights that OptimalControllerSolver::ComputeWeights produced have this structure up to their own rounding (measured
+// residual 4e-15 of sum |F|); a table that does not (e.g. read from a file with few digits) keeps the direct sum.
+// Returns sum |F[i] - w' L^i v| / sum |F[i]|, or -1 when the structure cannot be formed.  tables = E [NLpad][4] (L^i v, zero
+// past NL) followed by lane powers [32][16] ((L^FIR_R)^m, row-major).
+double rec_setup(const wg_preview_gains_t &g, PreviewConsts &pc, std::vector<double> &tables)
+{
+  typedef long double LD;
+  const int NL = g.NL;
+  int n = 0;
+  LD Ax[4][4], bx[4] = {0, 0, 0, 0}, K[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Ax[i][j] = 0;
+  if (g.mode == WG_PREVIEW_MODE_WITHOUT_INITIALPOS) {
+    n = 4;
+    Ax[0][0] = 1;
+    for (int j = 0; j < 3; ++j) {
+      LD a = 0;
+      for (int l = 0; l < 3; ++l) a += (LD)g.C[l] * (LD)g.A[3 * l + j];
+      Ax[0][j + 1] = a;
+      for (int i = 0; i < 3; ++i) Ax[i + 1][j + 1] = g.A[3 * i + j];
+    }
+    for (int l = 0; l < 3; ++l) { bx[0] += (LD)g.C[l] * (LD)g.B[l]; bx[l + 1] = g.B[l]; }
+    K[0] = g.Ks;
+    for (int j = 0; j < 3; ++j) K[j + 1] = g.Kx[j];
+  } else if (g.mode == WG_PREVIEW_MODE_WITH_INITIALPOS) {
+    n = 3;
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) Ax[i][j] = g.A[3 * i + j]; bx[i] = g.B[i]; K[i] = g.Kx[i]; }
+  } else {
+    return -1.0;
+  }
+  if (NL < 2 * n) return -1.0;
+  LD L[4][4];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) L[i][j] = (i < n && j < n) ? Ax[j][i] - bx[j] * K[i] : (LD)0;
+  // rows r_i = (L')^i w: r_i . v = w' L^i v
+  std::vector<LD> M((size_t)NL * 4, 0), Q((size_t)NL * 4, 0);
+  {
+    LD r[4] = {bx[0], bx[1], bx[2], bx[3]};
+    for (int i = 0; i < NL; ++i) {
+      for (int a = 0; a < 4; ++a) M[4 * (size_t)i + a] = r[a];
+      LD nx[4] = {0, 0, 0, 0};
+      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) nx[a] += L[b][a] * r[b];
+      for (int a = 0; a < 4; ++a) r[a] = nx[a];
+    }
+  }
+  LD sc[4] = {1, 1, 1, 1}, R[4][4], y[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
+  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) R[a][b] = 0;
+  for (int a = 0; a < n; ++a) {
+    LD m = 0;
+    for (int i = 0; i < NL; ++i) m = std::max(m, fabsl(M[4 * (size_t)i + a]));
+    if (!(m > 0)) return -1.0;
+    sc[a] = m;
+  }
+  for (int j = 0; j < n; ++j) {
+    for (int i = 0; i < NL; ++i) Q[4 * (size_t)i + j] = M[4 * (size_t)i + j] / sc[j];
+    for (int rep = 0; rep < 2; ++rep)
+      for (int a = 0; a < j; ++a) {
+        LD c = 0;
+        for (int i = 0; i < NL; ++i) c += Q[4 * (size_t)i + a] * Q[4 * (size_t)i + j];
+        R[a][j] += c;
+        for (int i = 0; i < NL; ++i) Q[4 * (size_t)i + j] -= c * Q[4 * (size_t)i + a];
+      }
+    LD nn = 0;
+    for (int i = 0; i < NL; ++i) nn += Q[4 * (size_t)i + j] * Q[4 * (size_t)i + j];
+    nn = sqrtl(nn);
+    if (!(nn > 1e-12L)) return -1.0;     // the Krylov rows do not span n directions: no unique fit
+    R[j][j] = nn;
+    for (int i = 0; i < NL; ++i) Q[4 * (size_t)i + j] /= nn;
+  }
+  for (int j = 0; j < n; ++j) for (int i = 0; i < NL; ++i) y[j] += Q[4 * (size_t)i + j] * (LD)g.F[i];
+  for (int j = n - 1; j >= 0; --j) {
+    LD a = y[j];
+    for (int b = j + 1; b < n; ++b) a -= R[j][b] * v[b];
+    v[j] = a / R[j][j];
+  }
+  for (int j = 0; j < n; ++j) v[j] /= sc[j];
+  LD res = 0, tot = 0;
+  for (int i = 0; i < NL; ++i) {
+    LD fh = 0;
+    for (int a = 0; a < n; ++a) fh += M[4 * (size_t)i + a] * v[a];
+    res += fabsl((LD)g.F[i] - fh);
+    tot += fabsl((LD)g.F[i]);
+  }
+  if (!(tot > 0) || !(res == res)) return -1.0;
+  // x_i = L^i v, i <= NL + FIR_R
+  const int NLpad = (NL + FIR_R - 1) / FIR_R * FIR_R;
+  tables.assign((size_t)NLpad * 4 + 32 * 16, 0.0);
+  {
+    LD x[4] = {v[0], v[1], v[2], v[3]};
+    for (int i = 0; i < NL + FIR_R; ++i) {
+      LD f = 0;
+      for (int a = 0; a < 4; ++a) f += bx[a] * x[a];
+      if (i < NL) for (int a = 0; a < 4; ++a) tables[4 * (size_t)i + a] = (double)x[a];
+      if (i < FIR_R) { pc.RF0[i] = (double)f; for (int a = 0; a < 4; ++a) pc.RV[i][a] = (double)x[a]; }
+      if (i >= NL) { pc.RFN[i - NL] = (double)-f; for (int a = 0; a < 4; ++a) pc.RVN[i - NL][a] = (double)-x[a]; }   // negated: pure FMAs
+      LD nx[4] = {0, 0, 0, 0};
+      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) nx[a] += L[a][b] * x[b];
+      for (int a = 0; a < 4; ++a) x[a] = nx[a];
+    }
+  }
+  {
+    LD r[4] = {bx[0], bx[1], bx[2], bx[3]};          // w' L^j
+    for (int j = 0; j <= FIR_R; ++j) {
+      for (int a = 0; a < 4; ++a) pc.RW[j][a] = (double)r[a];
+      LD nx[4] = {0, 0, 0, 0};
+      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) nx[a] += r[b] * L[b][a];
+      for (int a = 0; a < 4; ++a) r[a] = nx[a];
+    }
+  }
+  auto mul = [](LD X[4][4], LD Y[4][4], LD Z[4][4]) {
+    LD T[4][4];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        LD a = 0;
+        for (int k = 0; k < 4; ++k) a += X[i][k] * Y[k][j];
+        T[i][j] = a;
+      }
+    std::memcpy(Z, T, sizeof T);
+  };
+  LD P8[4][4];
+  std::memcpy(P8, L, sizeof P8);
+  for (int r = 1; r < FIR_R; r <<= 1) mul(P8, P8, P8);            // L^FIR_R
+  {
+    LD Pl[4][4];
+    std::memcpy(Pl, P8, sizeof Pl);
+    for (int l = 0; l < SCAN_LEVELS; ++l) {
+      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) pc.RP[l][4 * i + j] = (double)Pl[i][j];
+      mul(Pl, Pl, Pl);
+    }
+    LD Pm[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Pm[i][j] = (i == j) ? 1 : 0;
+    double *lp = tables.data() + (size_t)NLpad * 4;
+    for (int m = 0; m < 32; ++m) {
+      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) lp[16 * m + 4 * i + j] = (double)Pm[i][j];
+      mul(P8, Pm, Pm);
+    }
+  }
+  return (double)(res / tot);
+}
+
 }  // namespace
 
 // One CTA shape of the fused kernel: THREADS threads (tile = 8 x THREADS ticks), at least MIN_CTAS resident per SM.
@@ -685,7 +1168,8 @@ static int preview_launch_shape(wg_ctx *ctx, wg_preview_plan *pl, const int *d_o
 {
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
   const int span = FIR_R * THREADS + NLpad;
-  const size_t smem = sizeof(double2) * (size_t)(span + (span >> 3) + 2);
+  // the tile buffer doubles as the store staging area (320 double2 per warp)
+  const size_t smem = sizeof(double2) * std::max<size_t>((size_t)(span + (span >> 3) + 2), (size_t)(THREADS / 32) * 320);
   if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the FIR tile");
   constexpr int slot = WG_ATTR_PREVIEW_0 + (THREADS == 128 ? 0 : THREADS == 32 ? 2 : 4);
   if (simulation) WG_SMEM_ATTR(ctx, slot, (preview_fused_kernel<true, THREADS, MIN_CTAS>), smem);
@@ -726,6 +1210,42 @@ static int preview_launch_shape(wg_ctx *ctx, wg_preview_plan *pl, const int *d_o
   return WG_OK;
 }
 
+// The recursive kernel in the same CTA shapes.
+template <int THREADS, int MIN_CTAS>
+static int preview_launch_rec(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count, const double *d_zmp,
+                              double *d_state, double *d_com, double *d_zmpout, int simulation,
+                              const double *d_com_add, bool pos_only)
+{
+  const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
+  const int span = FIR_R * THREADS + NLpad;
+  const size_t smem = sizeof(double2) * std::max<size_t>((size_t)(span + (span >> 3) + 2), (size_t)(THREADS / 32) * 320);
+  if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the tile");
+  constexpr int slot = WG_ATTR_PREVIEW_REC_0 + 5 * (THREADS == 128 ? 0 : THREADS == 32 ? 1 : 2);
+  const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
+  const double2 *E = reinterpret_cast<const double2 *>(ctx->preview_rec_dev);
+  const double2 *lp = E + 2 * (size_t)NLpad;
+  std::lock_guard<std::mutex> lock(g_pv_mutex);
+  { const int rc = preview_bind(ctx); if (rc != WG_OK) return rc; }
+#define WG_REC_LAUNCH(SLOT, SIMF, ADDF, POSF, COM, ADDP)                                                                \
+  do {                                                                                                                 \
+    WG_SMEM_ATTR(ctx, slot + (SLOT), (preview_rec_kernel<SIMF, THREADS, MIN_CTAS, ADDF, POSF>), smem);                   \
+    wg_prof_start(ctx, WG_K_PREVIEW_FUSED);                                                                            \
+    preview_rec_kernel<SIMF, THREADS, MIN_CTAS, ADDF, POSF><<<count, THREADS, smem, ctx->stream>>>(                     \
+        d_order, pl->d_offsets, pz, d_state, COM, d_zmpout, ADDP, E, lp);                                              \
+    wg_prof_stop(ctx);                                                                                                 \
+    WG_LAUNCHED(ctx);                                                                                                  \
+    return WG_OK;                                                                                                      \
+  } while (0)
+  if (pos_only) {
+    if (simulation) WG_REC_LAUNCH(0, true, false, true, nullptr, nullptr);
+    else WG_REC_LAUNCH(1, false, false, true, nullptr, nullptr);
+  }
+  if (d_com_add && d_com) WG_REC_LAUNCH(2, true, true, false, d_com, d_com_add);
+  if (simulation) WG_REC_LAUNCH(3, true, false, false, d_com, nullptr);
+  else WG_REC_LAUNCH(4, false, false, false, d_com, nullptr);
+#undef WG_REC_LAUNCH
+}
+
 extern "C" {
 
 int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *g)
@@ -746,9 +1266,67 @@ int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *g)
   scan_matrices(*g, false, pc.P[0], pc.G[0], pc.H[0]);
   scan_matrices(*g, true, pc.P[1], pc.G[1], pc.H[1]);
   std::copy(g->F, g->F + g->NL, im->F);          // the rest of F stays zero: the FIR runs over NLpad taps
+  // recursive evaluation of the preview sum: usable when the weights have the structure ComputeWeights gives them
+  {
+    std::vector<double> tables;
+    ctx->preview_rec_residual = rec_setup(*g, pc, tables);
+    ctx->preview_rec_ok = ctx->preview_rec_residual >= 0.0 && ctx->preview_rec_residual <= WG_PREVIEW_REC_TOL;
+    if (ctx->preview_rec_dev) { WG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->preview_rec_dev); ctx->preview_rec_dev = nullptr; }
+    if (ctx->preview_rec_ok) {
+      WG_CUDA(ctx, cudaMalloc(&ctx->preview_rec_dev, sizeof(double) * tables.size()));
+      WG_CUDA(ctx, cudaMemcpy(ctx->preview_rec_dev, tables.data(), sizeof(double) * tables.size(), cudaMemcpyHostToDevice));
+    }
+  }
   ctx->preview_gains = *g;
   ctx->preview_gen = ++g_pv_gen_counter;           // the device block is refreshed lazily by preview_bind()
   ctx->preview_ready = true;
+  return WG_OK;
+}
+
+double wg_preview_sum_fit(const wg_preview_gains_t *g)
+{
+  if (!g || g->NL <= 0 || g->NL > WG_PREVIEW_MAX_NL) return -1.0;
+  PreviewConsts pc;
+  std::vector<double> tables;
+  return rec_setup(*g, pc, tables);
+}
+
+// internal (tests): the constants of preview_rec_kernel for a gain set, flat: RF0[8] RFN[8] RV[8][4] RVN[8][4] RW[9][4] RP[6][16],
+// then E[NLpad][4] and the lane powers [32][16].  Returns the number of doubles (or -1), writes at most cap of them.
+long long wgi_preview_rec_dump(const wg_preview_gains_t *g, double *out, long long cap)
+{
+  if (!g || g->NL <= 0 || g->NL > WG_PREVIEW_MAX_NL) return -1;
+  PreviewConsts pc;
+  std::vector<double> tables;
+  if (rec_setup(*g, pc, tables) < 0.0) return -1;
+  std::vector<double> flat;
+  flat.insert(flat.end(), pc.RF0, pc.RF0 + FIR_R);
+  flat.insert(flat.end(), pc.RFN, pc.RFN + FIR_R);
+  flat.insert(flat.end(), &pc.RV[0][0], &pc.RV[0][0] + FIR_R * 4);
+  flat.insert(flat.end(), &pc.RVN[0][0], &pc.RVN[0][0] + FIR_R * 4);
+  flat.insert(flat.end(), &pc.RW[0][0], &pc.RW[0][0] + (FIR_R + 1) * 4);
+  flat.insert(flat.end(), &pc.RP[0][0], &pc.RP[0][0] + SCAN_LEVELS * 16);
+  flat.insert(flat.end(), tables.begin(), tables.end());
+  for (long long i = 0; i < (long long)flat.size() && i < cap; ++i) out[i] = flat[(size_t)i];
+  return (long long)flat.size();
+}
+
+int wg_preview_set_sum_mode(wg_ctx *ctx, int mode)
+{
+  if (!ctx || mode < WG_PREVIEW_SUM_AUTO || mode > WG_PREVIEW_SUM_RECURSIVE) return WG_ERR_INVALID;
+  if (mode == WG_PREVIEW_SUM_RECURSIVE && ctx->preview_ready && !ctx->preview_rec_ok)
+    return wg_fail(ctx, WG_ERR_INVALID, "the window weights of this context are not of the form w' L^i v");
+  ctx->preview_sum_mode = mode;
+  return WG_OK;
+}
+
+int wg_preview_sum_info(wg_ctx *ctx, int *mode_in_use, double *fit_residual)
+{
+  if (!ctx) return WG_ERR_INVALID;
+  if (!ctx->preview_ready) return wg_fail(ctx, WG_ERR_NOT_READY, "wg_preview_set_gains not called");
+  if (mode_in_use)
+    *mode_in_use = (ctx->preview_sum_mode != WG_PREVIEW_SUM_DIRECT && ctx->preview_rec_ok) ? WG_PREVIEW_SUM_RECURSIVE : WG_PREVIEW_SUM_DIRECT;
+  if (fit_residual) *fit_residual = ctx->preview_rec_residual;
   return WG_OK;
 }
 
@@ -851,6 +1429,15 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
   if (shape < 0) {
     const char *e = getenv("WG_PREVIEW_SHAPE");
     shape = e ? atoi(e) : 0;
+  }
+  if (ctx->preview_sum_mode == WG_PREVIEW_SUM_RECURSIVE && !ctx->preview_rec_ok)
+    return wg_fail(ctx, WG_ERR_INVALID, "WG_PREVIEW_SUM_RECURSIVE: the window weights of this context are not of the form w' L^i v");
+  if (ctx->preview_sum_mode != WG_PREVIEW_SUM_DIRECT && ctx->preview_rec_ok) {
+    switch (shape) {
+    case 1: return preview_launch_rec<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
+    case 2: return preview_launch_rec<32, 16>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
+    default: return preview_launch_rec<64, 8>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
+    }
   }
   switch (shape) {
   case 1: return preview_launch_shape<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
@@ -1027,6 +1614,7 @@ extern "C" {
 
 void wg_preview_release(wg_ctx *ctx)
 {
+  if (ctx && ctx->preview_rec_dev) { cudaFree(ctx->preview_rec_dev); ctx->preview_rec_dev = nullptr; }
   PreviewTickBuf *tb = static_cast<PreviewTickBuf *>(ctx->preview_tick);
   if (!tb) return;
   if (tb->h) cudaFreeHost(tb->h);

@@ -41,6 +41,10 @@ struct wg_ctx {
   std::vector<unsigned char> preview_image;   // host image of the kernels' __constant__ block (PreviewConsts + taps)
   unsigned long long preview_gen = 0;         // bumped by wg_preview_set_gains
   void *preview_tick = nullptr;               // buffers of wg_preview_one_iteration (preview.cu)
+  int preview_sum_mode = WG_PREVIEW_SUM_AUTO;  // wg_preview_set_sum_mode
+  bool preview_rec_ok = false;                // the window weights fit w' L^i v within WG_PREVIEW_REC_TOL (rec_setup, preview.cu)
+  double preview_rec_residual = -1.0;
+  void *preview_rec_dev = nullptr;            // device tables of preview_rec_kernel
   // Herdt constants (herdt_qp.cu)
   void *herdt = nullptr;
   // Herdt closed loop (herdt_mpc.cu)
@@ -102,7 +106,7 @@ enum { WG_ATTR_PREVIEW_0 = 0, /* .. 5: {sim, nosim} x 3 CTA shapes */ WG_ATTR_HE
        WG_ATTR_PLDP = 8, WG_ATTR_PLDP_RANKED = 9, WG_ATTR_ZMPDISC = 10, WG_ATTR_DIMITROV = 11, WG_ATTR_DENSEQP = 12,
        WG_ATTR_PREVIEW_ADD_0 = 13, /* .. 15: second-stage variant x 3 CTA shapes */
        WG_ATTR_PREVIEW_POS_0 = 16, /* .. 21: position-only variant {sim, nosim} x 3 CTA shapes */ WG_ATTR_DENSEQP_RANKED = 22,
-       WG_ATTR_SLOTS = 24 };
+       WG_ATTR_PREVIEW_REC_0 = 24, /* .. 38: recursive preview kernel, 5 variants x 3 CTA shapes */ WG_ATTR_SLOTS = 40 };
 extern "C" int wgi_smem_attr(wg_ctx *ctx, int slot, const void *func, size_t bytes);
 #define WG_SMEM_ATTR(ctx, slot, func, bytes)                                              \
   do {                                                                                    \

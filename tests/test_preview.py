@@ -125,6 +125,104 @@ def test_oracle_tracks_constant_reference():
 
 
 # ------------------------------------------------------------------------------------------------
+# Recursive evaluation of the preview sum (preview_rec_kernel): host logic
+# ------------------------------------------------------------------------------------------------
+def test_window_weights_are_matrix_geometric_and_tables_that_are_not_fall_back():
+    """OptimalControllerSolver.cpp:323-345 builds F[i] = la b' ((A - bK)')^i P c'Q: wg_preview_sum_fit recovers that structure
+    from a gain table to rounding (both modes, several T / preview times / heights), and refuses tables without it: one tap
+    off by 1e-9 relative, or the 5-digit precision of the reference's PreviewControlParameters.ini."""
+    import jrl_walkgen_b200 as wg
+    from jrl_walkgen_b200 import _capi
+    lib = _capi.load()
+    tol = 1e-12                                            # WG_PREVIEW_REC_TOL
+    for mode in (wg.MODE_WITHOUT_INITIALPOS, wg.MODE_WITH_INITIALPOS):
+        for T, Tp, zc in [(0.005, 1.6, 0.814), (0.005, 0.8, 0.6), (0.01, 1.6, 1.0), (0.002, 2.0, 0.814), (0.005, 0.04, 0.814)]:
+            g = wg.preview_gains(T, Tp, zc, mode)
+            r = lib.wg_preview_sum_fit(C.byref(g))
+            assert 0.0 <= r < 2e-14, (mode, T, Tp, zc, r)
+    o = ol.OracleGains(0.005, 1.6, 0.814, 1)               # another solver's weights (the oracle's Riccati fixed point)
+    g = wg.preview_gains()
+    for i in range(3):
+        g.Kx[i] = o.Kx[i]
+    g.Ks = o.Ks
+    for i in range(g.NL):
+        g.F[i] = o.F[i]
+    assert 0.0 <= lib.wg_preview_sum_fit(C.byref(g)) < 2e-14
+    g = wg.preview_gains()
+    g.F[10] *= 1 + 1e-9
+    assert lib.wg_preview_sum_fit(C.byref(g)) > tol
+    g = wg.preview_gains()
+    for i in range(g.NL):
+        g.F[i] = float(f"{g.F[i]:.5g}")
+    assert lib.wg_preview_sum_fit(C.byref(g)) > 1e-7
+
+
+@pytest.mark.parametrize("threads,NLcfg", [(64, (0.005, 1.6)), (128, (0.005, 1.6)), (32, (0.005, 0.8)), (64, (0.005, 1.595))])
+def test_recursive_sum_constants_reproduce_the_direct_sum(threads, NLcfg):
+    """The decomposition preview_rec_kernel runs per tile - W at the tile's end from the table E, the 8-tap triangular sums of a
+    thread, its local total, the scan DOWN the tile with L^(8d), the per-lane power of the state entering a warp, the
+    correction w' L^(8-r) W_in - executed here in numpy with the library's own constants (wgi_preview_rec_dump), thread by
+    thread, against the direct 320-tap sum in extended precision: 1e-13 relative."""
+    import jrl_walkgen_b200 as wg
+    from jrl_walkgen_b200 import _capi
+    lib = _capi.load()
+    lib.wgi_preview_rec_dump.restype = C.c_longlong
+    lib.wgi_preview_rec_dump.argtypes = [C.POINTER(_capi.PreviewGains), C.c_void_p, C.c_longlong]
+    g = wg.preview_gains(NLcfg[0], NLcfg[1], 0.814, 1)
+    NL = g.NL; R = 8; NLpad = (NL + 7) // 8 * 8
+    n = lib.wgi_preview_rec_dump(C.byref(g), None, 0)
+    assert n == 8 + 8 + 32 + 32 + 36 + 96 + NLpad * 4 + 512
+    flat = np.zeros(n)
+    assert lib.wgi_preview_rec_dump(C.byref(g), flat.ctypes.data, n) == n
+    o = 0
+    def take(k, shape):
+        nonlocal o
+        a = flat[o:o + k].reshape(shape); o += k
+        return a
+    RF0 = take(8, (8,)); RFN = take(8, (8,)); RV = take(32, (8, 4)); RVN = take(32, (8, 4)); RW = take(36, (9, 4))
+    RP = take(96, (6, 4, 4)); E = take(NLpad * 4, (NLpad, 4)); LP = take(512, (32, 4, 4))
+    F = np.array(g.F[:NL])
+    assert np.allclose(RF0, F[:8], rtol=1e-13) and np.array_equal(LP[0], np.eye(4)) and np.allclose(LP[1], RP[0], rtol=1e-15)
+    assert (E[NL:] == 0).all()
+    rng = np.random.default_rng(5)
+    TILE = R * threads
+    L = 2 * TILE + NL + 77                                  # three tiles, the last one ragged
+    p = synth_walk(rng, L)[:, 0] + rng.normal(scale=1e-3, size=L)
+    nsteps = L - NL + 1
+    fex = np.array([float((F.astype(np.longdouble) * p[k:k + NL].astype(np.longdouble)).sum()) for k in range(nsteps)])
+    f = np.zeros(nsteps)
+    for start in range(0, nsteps, TILE):
+        span = TILE + NLpad
+        sp = np.zeros(span); m = min(span, L - start); sp[:m] = p[start:start + m]
+        Wend = (E[:NL] * sp[TILE:TILE + NL, None]).sum(axis=0)
+        floc = np.zeros((threads, R)); c = np.zeros((threads, 4))
+        for t in range(threads):
+            own = sp[R * t:R * t + R]; far = sp[R * t + NL:R * t + NL + R]
+            for j in range(R):
+                for r in range(j + 1):
+                    floc[t, r] += RF0[j - r] * own[j] + RFN[j - r] * far[j]
+                c[t] += RV[j] * own[j] + RVN[j] * far[j]
+        for l in range(5):
+            d = 1 << l; new = c.copy()
+            for t in range(threads):
+                if (t & 31) + d < 32:
+                    new[t] = c[t] + RP[l] @ c[t + d]
+            c = new
+        nw = threads // 32
+        V = [None] * nw; V[nw - 1] = Wend
+        for w in range(nw - 2, -1, -1):
+            V[w] = c[32 * (w + 1)] + RP[5] @ V[w + 1]
+        for t in range(threads):
+            lane = t & 31
+            Win = (c[t + 1] if lane < 31 else np.zeros(4)) + LP[31 - lane] @ V[t >> 5]
+            for r in range(R):
+                k = start + R * t + r
+                if k < nsteps:
+                    f[k] = floc[t, r] + RW[R - r] @ Win
+    assert np.abs(f - fex).max() < 1e-13 * np.abs(fex).max(), np.abs(f - fex).max() / np.abs(fex).max()
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU parity
 # ------------------------------------------------------------------------------------------------
 def _run_gpu(ctx, gains, offsets, z, st0, simulation=True, mem_device=False):
@@ -308,3 +406,77 @@ def test_gpu_position_only_output_equals_the_full_run(ctx):
         for d in (dz, ds, dp):
             d.free()
     plan.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(0.005, 1.6, 0.807709, 1), (0.01, 1.6, 0.814, 0), (0.005, 0.8, 0.75, 1), (0.005, 1.595, 0.814, 1)])
+def test_gpu_recursive_and_direct_preview_sums_agree_with_the_oracle(ctx, cfg):
+    """Both evaluations of the preview sum - preview_rec_kernel (the default for weights of the reference's structure) and the
+    direct 320-tap sum of preview_fused_kernel - against the oracle on a ragged batch (tile boundaries of every CTA shape,
+    windows that are not a multiple of 8, both solver modes, with and without the integrated error), and against each other."""
+    import jrl_walkgen_b200 as wg
+    T, Tp, zc, mode = cfg
+    rng = np.random.default_rng(11)
+    gains = wg.preview_gains(T, Tp, zc, mode)
+    og = ol.OracleGains(T, Tp, zc, mode)
+    NL = gains.NL
+    lens = [NL + 4000, NL - 1, NL, NL + 1, NL + 511, NL + 512, NL + 513, NL + 1023, NL + 1024, NL + 1025, 0, 2500, 5000, 2 * NL,
+            NL + 255, NL + 256, NL + 257]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    z = np.concatenate([synth_walk(rng, L) for L in lens if L > 0])
+    st0 = rng.normal(scale=0.01, size=(len(lens), 8))
+    rows = _valid_rows(offsets, NL)
+    out = {}
+    try:
+        # MODE_WITH_INITIALPOS has no error integrator in its design (Ks is K(0,0) again): with Simulation = true the loop of
+        # the reference itself diverges (the oracle reaches 1e145 within 1000 ticks), so that mode runs without it
+        for sim in ((True, False) if mode == 1 else (False,)):
+            st_o = st0.copy()
+            com_o, zmp_o, _ = ol.oracle_preview_batch(og, offsets, z, st_o, simulation=sim)
+            for name, m in (("recursive", wg.PREVIEW_SUM_RECURSIVE), ("direct", wg.PREVIEW_SUM_DIRECT)):
+                ctx.preview_set_gains(gains)
+                ctx.preview_set_sum_mode(m)
+                used, resid = ctx.preview_sum_info()
+                assert used == m and 0 <= resid < 1e-13
+                com, zmp, st, _ = _run_gpu(ctx, gains, offsets, z, st0, sim, mem_device=(name == "recursive"))
+                out[name] = (com, zmp, st)
+                assert np.abs(com[rows] - com_o[rows])[:, [0, 3]].max() < TOL_COM, (name, sim)
+                assert np.abs(com[rows] - com_o[rows]).max() < 1e-7, (name, sim)
+                assert np.abs(zmp[rows] - zmp_o[rows]).max() < 1e-8, (name, sim)
+                assert np.allclose(st, st_o, rtol=1e-7, atol=1e-8), (name, sim)
+            d = np.abs(out["recursive"][0][rows] - out["direct"][0][rows])
+            print(f"cfg {cfg} sim {sim}: recursive vs direct sum, max |dCoM| = {d[:, [0, 3]].max():.2e} m, "
+                  f"|d ddCoM| = {d[:, [2, 5]].max():.2e} m/s^2")
+            assert d[:, [0, 3]].max() < 1e-11
+    finally:
+        ctx.preview_set_sum_mode(wg.PREVIEW_SUM_AUTO)
+
+
+@pytest.mark.gpu
+def test_gpu_weights_without_the_structure_keep_the_direct_sum(ctx):
+    """A gain table that is not matrix-geometric (here: rounded to the 5 digits of the reference's PreviewControlParameters.ini)
+    runs through the direct sum under AUTO, RECURSIVE is refused, and the result is the oracle's for THAT table."""
+    import jrl_walkgen_b200 as wg
+    gains = wg.preview_gains()
+    og = ol.OracleGains()
+    for i in range(gains.NL):
+        gains.F[i] = float(f"{gains.F[i]:.5g}")
+        og.F[i] = gains.F[i]
+    rng = np.random.default_rng(12)
+    offsets = np.array([0, 1700, 1700 + 900], dtype=np.int64)
+    z = np.concatenate([synth_walk(rng, 1700), synth_walk(rng, 900)])
+    st0 = np.zeros((2, 8))
+    try:
+        ctx.preview_set_gains(gains)
+        used, resid = ctx.preview_sum_info()
+        assert used == wg.PREVIEW_SUM_DIRECT and resid > 1e-7
+        with pytest.raises(wg.WalkgenError):
+            ctx.preview_set_sum_mode(wg.PREVIEW_SUM_RECURSIVE)
+        com, zmp, st, _ = _run_gpu(ctx, gains, offsets, z, st0)
+        st_o = st0.copy()
+        com_o, zmp_o, _ = ol.oracle_preview_batch(og, offsets, z, st_o)
+        rows = _valid_rows(offsets, 320)
+        assert np.abs(com[rows] - com_o[rows])[:, [0, 3]].max() < TOL_COM
+    finally:
+        ctx.preview_set_sum_mode(wg.PREVIEW_SUM_AUTO)
+        ctx.preview_set_gains(wg.preview_gains())

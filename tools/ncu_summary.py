@@ -34,7 +34,28 @@ def load(path):
     return recs
 
 
+def traffic(paths, walks, out):
+    """--traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch of each captured kernel -> profiles/ncu_traffic.json
+    (what bench.py reports as roofline.traffic; `walks` = the --walks of the captured command, bench.py refuses another size)."""
+    import json
+    import os
+    res = {}
+    for path in paths:
+        for rec in load(path):
+            name = rec.get("Kernel Name", ("", "?"))[1].split("(")[0].split("::")[-1].split("<")[0].replace("void ", "").strip()
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                u, v = rec[key]
+                tot += float(v.replace(",", "")) * UNIT[u] * 1e6
+            res[name] = {"dram_bytes_per_launch": tot, "walks": walks,
+                         "source": f"ncu --set full capture {os.path.basename(path)} (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"}
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 def main():
+    if sys.argv[1] == "--traffic":   # --traffic <walks> <out.json> captures...
+        return traffic(sys.argv[4:], int(sys.argv[2]), sys.argv[3])
     lines = []
     for path in sys.argv[1:]:
         for rec in load(path):
