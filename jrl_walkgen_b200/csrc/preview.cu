@@ -643,6 +643,15 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
 // Deviation of f from the direct sum: 1e-14 relative (it is a different summation order of the same 320 products);
 // measured on CoM / ZMP against the reference's object code: see tests/test_preview_ref.py.
 // ---------------------------------------------------------------------------------------------
+// cp.async (LDGSTS): 16 bytes global -> shared without a register round trip; src_size 0 writes zeros
+__device__ __forceinline__ void cp_async16(double2 *dst_smem, const double2 *src_gmem, unsigned src_size)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src_gmem), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 template <bool SIM, int FIR_THREADS, int MIN_CTAS, bool ADD = false, bool POS = false>
 __global__ void __launch_bounds__(FIR_THREADS, MIN_CTAS)
 preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ offsets,
@@ -653,7 +662,10 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
   constexpr int FIR_TILE = FIR_R * FIR_THREADS;   // ticks per tile
   constexpr int NW = FIR_THREADS / 32;
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ double2 sp[];             // padded tile of (px,py), then the store staging area
+  // Ring of 2 tiles + the window, 9/8 padded: sample e of the trajectory lives in slot pad9(e mod CAP).  While tile i is
+  // computed, the FIR_TILE new samples tile i + 1 needs arrive through cp.async in the slots tile i - 1 used for its own
+  // samples; the slots of tile i's own samples are dead after phase (1) and stage its stores.  Nothing is loaded twice.
+  extern __shared__ double2 sp[];
   __shared__ double s_tot[NW + 1][8];         // warp totals of the forward scan (x axis 0..3, y axis 4..7)
   __shared__ double s_totb[NW + 1][8];        // warp totals of the backward scan
   __shared__ double s_halo[NW][8];            // per-warp partial sums of W at the tile's end
@@ -665,20 +677,31 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
   const int nsteps = L - NL + 1;
   if (nsteps <= 0) return;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int span = FIR_TILE + NLpad;           // samples one tile needs
+  const int CAP = 2 * FIR_TILE + NLpad;        // ring capacity in samples (a multiple of 8)
   if (t < 8) s_carry[t] = state[8 * (size_t)b + t];   // {x,dx,ddx,y,dy,ddy,sx,sy}
   const double(*Pm)[16] = c_pc.P[SIM ? 1 : 0];
+  const double2 *src = p + o;
+  // first tile: samples [0, FIR_TILE + NLpad); samples past the trajectory read as zero (src-size 0 zero-fills)
+  for (int e = t; e < FIR_TILE + NLpad; e += FIR_THREADS) cp_async16(sp + pad9(e), src + (e < L ? e : 0), e < L ? 16u : 0u);
+  cp_async_commit();
+  int base = 0;                                // slot index (before padding) of sample `start`
 
   for (int start = 0; start < nsteps; start += FIR_TILE) {
-    __syncthreads();
-    const double2 *src = p + o + start;
-    const int avail = L - start;               // samples that exist from `start` on; the rest of the tile reads as zero
-    for (int e = t; e < span; e += FIR_THREADS) {
-      double2 v = make_double2(0.0, 0.0);
-      if (e < avail) v = __ldg(src + e);
-      sp[pad9(e)] = v;
+    cp_async_wait_all();
+    __syncthreads();                           // this tile's samples have landed; the previous tile's staged stores are out
+    if (start + FIR_TILE < nsteps) {           // prefetch what the next tile adds: samples [start + span, start + span + FIR_TILE)
+      const int first = start + FIR_TILE + NLpad;
+#pragma unroll
+      for (int u = 0; u < FIR_R; ++u) {
+        const int e = t + u * FIR_THREADS;
+        int ri = base + FIR_TILE + NLpad + e;
+        if (ri >= CAP) ri -= CAP;
+        const bool in = first + e < L;
+        cp_async16(sp + pad9(ri), src + (in ? first + e : 0), in ? 16u : 0u);
+      }
+      cp_async_commit();
     }
-    __syncthreads();
+    const int own0 = (base + FIR_R * t >= CAP) ? base + FIR_R * t - CAP : base + FIR_R * t;   // slot of this thread's first sample
 
     // ---- (1a) W at the tile's end (x: h[0..3], y: h[4..7]), partial sums of this thread's halo samples
     {
@@ -687,7 +710,9 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
       for (int j = 0; j < 8; ++j) h[j] = 0.0;
       for (int i = t; i < NL; i += FIR_THREADS) {
         const double2 e01 = __ldg(Etab + 2 * i), e23 = __ldg(Etab + 2 * i + 1);
-        const double2 q = sp[pad9(FIR_TILE + i)];
+        int hi = base + FIR_TILE + i;
+        if (hi >= CAP) hi -= CAP;
+        const double2 q = sp[pad9(hi)];
         h[0] = fma(e01.x, q.x, h[0]); h[1] = fma(e01.y, q.x, h[1]); h[2] = fma(e23.x, q.x, h[2]); h[3] = fma(e23.y, q.x, h[3]);
         h[4] = fma(e01.x, q.y, h[4]); h[5] = fma(e01.y, q.y, h[5]); h[6] = fma(e23.x, q.y, h[6]); h[7] = fma(e23.y, q.y, h[7]);
       }
@@ -727,13 +752,15 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
     bx.x0 = bx.x1 = bx.x2 = bx.s = 0.0;
     by = bx;
     {
-      const double2 *own = sp + pad9(FIR_R * t);
+      const double2 *own = sp + pad9(own0);
 #pragma unroll
       for (int r = 0; r < FIR_R; ++r) { ax[r] = 0.0; ay[r] = 0.0; }
 #pragma unroll
       for (int j = 0; j < FIR_R; ++j) {
         const double2 a = own[j];
-        const double2 f = sp[pad9(FIR_R * t + j + NL)];
+        int fi = own0 + j + NL;
+        if (fi >= CAP) fi -= CAP;
+        const double2 f = sp[pad9(fi)];
         pk[j] = SIM ? a : make_double2(0.0, 0.0);
 #pragma unroll
         for (int r = 0; r <= j; ++r) {
@@ -903,9 +930,14 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
     const int k0 = start + FIR_R * t;
     const int last = min(start + FIR_TILE, nsteps) - 1;   // last valid tick of this tile
     {
-      constexpr int CHUNK_C = 7, CHUNK_Z = 3;     // double2 per lane and round: 6 (+1 pad) of CoM, 2 (+1 pad) of ZMP
-      double2 *stg_c = sp + w * (32 * (CHUNK_C + CHUNK_Z));
-      double2 *stg_z = stg_c + 32 * CHUNK_C;
+      // staging chunk of lane c of this warp = the 9 slots of its 8 (dead) own samples: 6 double2 of CoM (two ticks), 2 of ZMP
+      const int wbase = base + FIR_R * (t & ~31);
+      auto chunk = [&](int c) -> double2 * {
+        int i = wbase + FIR_R * c;
+        if (i >= CAP) i -= CAP;
+        return sp + pad9(i);
+      };
+      double2 *mine = chunk(lane);
       const int kw = start + FIR_R * (t & ~31);   // first tick of this warp
       double2 *gc = reinterpret_cast<double2 *>(com) + 3 * (o + kw);
       double2 *gz = reinterpret_cast<double2 *>(zmp) + (o + kw);
@@ -917,11 +949,11 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
           if (k0 + r <= last) {
             const double zx = preview_tick<SIM>(sx, ax[r], pk[r].x);
             const double zy = preview_tick<SIM>(sy, ay[r], pk[r].y);
-            double2 *q = stg_c + CHUNK_C * lane + 3 * h;
+            double2 *q = mine + 3 * h;
             q[0] = make_double2(sx.x0, sx.x1);
             q[1] = make_double2(sx.x2, sy.x0);
             q[2] = make_double2(sy.x1, sy.x2);
-            stg_z[CHUNK_Z * lane + h] = POS ? make_double2(sx.x0, sy.x0) : make_double2(zx, zy);
+            mine[6 + h] = POS ? make_double2(sx.x0, sy.x0) : make_double2(zx, zy);
           }
         }
         __syncwarp();
@@ -931,7 +963,7 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
             const int idx = 32 * it + lane, c = idx / 6, part = idx - 6 * c;
             const int row = kw + FIR_R * c + 2 * j;             // first of the two ticks of lane c in this round
             if (row + (part >= 3) <= last) {
-              double2 v = stg_c[CHUNK_C * c + part];
+              double2 v = chunk(c)[part];
               if (ADD) {
                 const double2 a = __ldg(reinterpret_cast<const double2 *>(com_add) + 3 * (o + kw) + 3 * (FIR_R * c + 2 * j) + part);
                 v.x += a.x; v.y += a.y;
@@ -945,7 +977,7 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
           for (int it = 0; it < 2; ++it) {
             const int idx = 32 * it + lane, c = idx >> 1, part = idx & 1;
             const int row = kw + FIR_R * c + 2 * j + part;
-            if (row <= last) gz[FIR_R * c + 2 * j + part] = stg_z[CHUNK_Z * c + part];
+            if (row <= last) gz[FIR_R * c + 2 * j + part] = chunk(c)[6 + part];
           }
         }
         __syncwarp();
@@ -955,6 +987,8 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
       s_carry[0] = sx.x0; s_carry[1] = sx.x1; s_carry[2] = sx.x2; s_carry[6] = sx.s;
       s_carry[3] = sy.x0; s_carry[4] = sy.x1; s_carry[5] = sy.x2; s_carry[7] = sy.s;
     }
+    base += FIR_TILE;
+    if (base >= CAP) base -= CAP;
   }
   __syncthreads();
   if (t < 8) state[8 * (size_t)b + t] = s_carry[t];
@@ -1217,8 +1251,8 @@ static int preview_launch_rec(wg_ctx *ctx, wg_preview_plan *pl, const int *d_ord
                               const double *d_com_add, bool pos_only)
 {
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
-  const int span = FIR_R * THREADS + NLpad;
-  const size_t smem = sizeof(double2) * std::max<size_t>((size_t)(span + (span >> 3) + 2), (size_t)(THREADS / 32) * 320);
+  const int cap = 2 * FIR_R * THREADS + NLpad;     // ring of two tiles + the window
+  const size_t smem = sizeof(double2) * (size_t)(cap + (cap >> 3) + 2);
   if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the tile");
   constexpr int slot = WG_ATTR_PREVIEW_REC_0 + 5 * (THREADS == 128 ? 0 : THREADS == 32 ? 1 : 2);
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
