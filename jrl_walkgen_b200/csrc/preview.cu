@@ -643,6 +643,24 @@ preview_fused_kernel(const int *__restrict__ order, const int64_t *__restrict__ 
 // Deviation of f from the direct sum: 1e-14 relative (it is a different summation order of the same 320 products);
 // measured on CoM / ZMP against the reference's object code: see tests/test_preview_ref.py.
 // ---------------------------------------------------------------------------------------------
+// 256-bit global accesses (LDG.256 / STG.256, sm_100): one whole 32-byte sector per thread; `al32` = the address is 32-byte
+// aligned (uniform over the CTA), otherwise two 128-bit accesses
+__device__ __forceinline__ void st32g(double *p, double a, double b, double c, double d, bool al32)
+{
+  if (al32) asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+  else {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(a, b);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
+  }
+}
+__device__ __forceinline__ void ld32g(const double *p, double &a, double &b, double &c, double &d, bool al32)
+{
+  if (al32) asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];\n" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+  else {
+    const double2 u = __ldg(reinterpret_cast<const double2 *>(p)), v = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    a = u.x; b = u.y; c = v.x; d = v.y;
+  }
+}
 // cp.async (LDGSTS): 16 bytes global -> shared without a register round trip; src_size 0 writes zeros
 __device__ __forceinline__ void cp_async16(double2 *dst_smem, const double2 *src_gmem, unsigned src_size)
 {
@@ -926,61 +944,58 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
         else { sx = wx_in; sy = wy_in; }
       }
     }
-    // ---- (2d) final pass and staged stores (as preview_fused_kernel)
+    // ---- (2d) final pass.  Every thread stores its own rows straight from registers: two ticks are 96 B of CoM and 32 B of
+    //      ZMP, i.e. four whole 32-byte sectors, written with 256-bit stores (STG.256) when the rows of this trajectory start
+    //      on a 32-byte boundary and with 128-bit stores otherwise; no staging, no index arithmetic per store.
     const int k0 = start + FIR_R * t;
     const int last = min(start + FIR_TILE, nsteps) - 1;   // last valid tick of this tile
     {
-      // staging chunk of lane c of this warp = the 9 slots of its 8 (dead) own samples: 6 double2 of CoM (two ticks), 2 of ZMP
-      const int wbase = base + FIR_R * (t & ~31);
-      auto chunk = [&](int c) -> double2 * {
-        int i = wbase + FIR_R * c;
-        if (i >= CAP) i -= CAP;
-        return sp + pad9(i);
-      };
-      double2 *mine = chunk(lane);
-      const int kw = start + FIR_R * (t & ~31);   // first tick of this warp
-      double2 *gc = reinterpret_cast<double2 *>(com) + 3 * (o + kw);
-      double2 *gz = reinterpret_cast<double2 *>(zmp) + (o + kw);
+      double *gc = com ? com + 6 * (size_t)(o + k0) : nullptr;
+      double *gz = zmp ? zmp + 2 * (size_t)(o + k0) : nullptr;
+      const double *ga = ADD ? com_add + 6 * (size_t)(o + k0) : nullptr;
+      const bool c32 = ((reinterpret_cast<uintptr_t>(gc) | (ADD ? reinterpret_cast<uintptr_t>(ga) : 0)) & 31) == 0;
+      const bool z32 = (reinterpret_cast<uintptr_t>(gz) & 31) == 0;
 #pragma unroll
       for (int j = 0; j < FIR_R / 2; ++j) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int r = 2 * j + h;
-          if (k0 + r <= last) {
-            const double zx = preview_tick<SIM>(sx, ax[r], pk[r].x);
-            const double zy = preview_tick<SIM>(sy, ay[r], pk[r].y);
-            double2 *q = mine + 3 * h;
-            q[0] = make_double2(sx.x0, sx.x1);
-            q[1] = make_double2(sx.x2, sy.x0);
-            q[2] = make_double2(sy.x1, sy.x2);
-            mine[6 + h] = POS ? make_double2(sx.x0, sy.x0) : make_double2(zx, zy);
-          }
-        }
-        __syncwarp();
-        if (com) {
-#pragma unroll
-          for (int it = 0; it < 6; ++it) {
-            const int idx = 32 * it + lane, c = idx / 6, part = idx - 6 * c;
-            const int row = kw + FIR_R * c + 2 * j;             // first of the two ticks of lane c in this round
-            if (row + (part >= 3) <= last) {
-              double2 v = chunk(c)[part];
-              if (ADD) {
-                const double2 a = __ldg(reinterpret_cast<const double2 *>(com_add) + 3 * (o + kw) + 3 * (FIR_R * c + 2 * j) + part);
-                v.x += a.x; v.y += a.y;
-              }
-              gc[3 * (FIR_R * c + 2 * j) + part] = v;
+        const int r0 = 2 * j, r1 = 2 * j + 1;
+        if (k0 + r1 <= last) {                 // both ticks of the pair are valid
+          const double zx0 = preview_tick<SIM>(sx, ax[r0], pk[r0].x);
+          const double zy0 = preview_tick<SIM>(sy, ay[r0], pk[r0].y);
+          double a0 = sx.x0, a1 = sx.x1, a2 = sx.x2, a3 = sy.x0, a4 = sy.x1, a5 = sy.x2;
+          const double u0 = POS ? sx.x0 : zx0, u1 = POS ? sy.x0 : zy0;
+          const double zx1 = preview_tick<SIM>(sx, ax[r1], pk[r1].x);
+          const double zy1 = preview_tick<SIM>(sy, ay[r1], pk[r1].y);
+          if (com) {
+            double b0 = sx.x0, b1 = sx.x1, b2 = sx.x2, b3 = sy.x0, b4 = sy.x1, b5 = sy.x2;
+            if (ADD) {
+              double q[12];
+              ld32g(ga + 6 * r0, q[0], q[1], q[2], q[3], c32);
+              ld32g(ga + 6 * r0 + 4, q[4], q[5], q[6], q[7], c32);
+              ld32g(ga + 6 * r0 + 8, q[8], q[9], q[10], q[11], c32);
+              a0 += q[0]; a1 += q[1]; a2 += q[2]; a3 += q[3]; a4 += q[4]; a5 += q[5];
+              b0 += q[6]; b1 += q[7]; b2 += q[8]; b3 += q[9]; b4 += q[10]; b5 += q[11];
             }
+            st32g(gc + 6 * r0, a0, a1, a2, a3, c32);
+            st32g(gc + 6 * r0 + 4, a4, a5, b0, b1, c32);
+            st32g(gc + 6 * r0 + 8, b2, b3, b4, b5, c32);
           }
-        }
-        if (zmp) {
-#pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int idx = 32 * it + lane, c = idx >> 1, part = idx & 1;
-            const int row = kw + FIR_R * c + 2 * j + part;
-            if (row <= last) gz[FIR_R * c + 2 * j + part] = chunk(c)[6 + part];
+          if (zmp) st32g(gz + 2 * r0, u0, u1, POS ? sx.x0 : zx1, POS ? sy.x0 : zy1, z32);
+        } else if (k0 + r0 <= last) {          // the trajectory ends on the first tick of the pair
+          const double zx0 = preview_tick<SIM>(sx, ax[r0], pk[r0].x);
+          const double zy0 = preview_tick<SIM>(sy, ay[r0], pk[r0].y);
+          if (com) {
+            double a0 = sx.x0, a1 = sx.x1, a2 = sx.x2, a3 = sy.x0, a4 = sy.x1, a5 = sy.x2;
+            if (ADD) {
+              const double2 q0 = __ldg(reinterpret_cast<const double2 *>(ga + 6 * r0));
+              const double2 q1 = __ldg(reinterpret_cast<const double2 *>(ga + 6 * r0) + 1);
+              const double2 q2 = __ldg(reinterpret_cast<const double2 *>(ga + 6 * r0) + 2);
+              a0 += q0.x; a1 += q0.y; a2 += q1.x; a3 += q1.y; a4 += q2.x; a5 += q2.y;
+            }
+            double2 *g2 = reinterpret_cast<double2 *>(gc + 6 * r0);
+            g2[0] = make_double2(a0, a1); g2[1] = make_double2(a2, a3); g2[2] = make_double2(a4, a5);
           }
+          if (zmp) *reinterpret_cast<double2 *>(gz + 2 * r0) = POS ? make_double2(sx.x0, sy.x0) : make_double2(zx0, zy0);
         }
-        __syncwarp();
       }
     }
     if (k0 <= last && last < k0 + FIR_R) {   // the thread that ran the tile's last valid tick carries the state
@@ -992,6 +1007,305 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
   }
   __syncthreads();
   if (t < 8) state[8 * (size_t)b + t] = s_carry[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// preview_rec_warp_kernel: the recursive evaluation with ONE WARP per trajectory (CTA = 32 threads, tile = 256 ticks).
+// Same arithmetic as preview_rec_kernel; what a single warp changes:
+//   * no cross-warp phase, no __syncthreads: W at the tile's end (the halo sum) is folded into lane 31's local total BEFORE the
+//     downward scan (c_31 += L^8 W_end), so the scan delivers the true W of every lane and the per-lane power table is not read;
+//     the carried cart-table state enters lane 0 of the upward scan the same way;
+//   * the samples live in a ring of TILE + NLpad slots: once phase (1b) has read a lane's own 8 samples their slots are dead and
+//     receive (cp.async) the 256 samples the next tile adds while phases (1c)-(2d) run: 10.4 KB of shared memory per warp at
+//     NL = 320, 16 warps per SM (the register limit at 128) and most of the L1 left for the E table;
+//   * the E table rows of a lane's halo samples are fetched five at a time before they are used (one exposed L1/L2 latency per
+//     five samples instead of one per sample).
+// ---------------------------------------------------------------------------------------------
+constexpr int RW_TILE = FIR_R * 32;
+constexpr int RW_U = 5;                        // halo samples per lane fetched together
+
+template <bool SIM, bool ADD = false, bool POS = false>
+__global__ void __launch_bounds__(32, 16)
+preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict__ offsets,
+                        const double2 *__restrict__ p, double *__restrict__ state, double *__restrict__ com,
+                        double *__restrict__ zmp, const double *__restrict__ com_add, const double2 *__restrict__ Etab)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ double2 sp[];             // the ring, 9/8 padded
+  __shared__ double s_halo[8];                // W at the tile's end (x: 0..3, y: 4..7)
+  __shared__ double s_carry[8];
+  const int b = order[blockIdx.x];
+  const int64_t o = offsets[b];
+  const int L = (int)(offsets[b + 1] - o);
+  const int NL = c_pc.NL, NLpad = c_pc.NLpad;
+  const int nsteps = L - NL + 1;
+  if (nsteps <= 0) return;
+  const int lane = threadIdx.x;
+  const int CAP = RW_TILE + NLpad;             // ring capacity in samples (a multiple of 8)
+  if (lane < 8) s_carry[lane] = state[8 * (size_t)b + lane];   // {x,dx,ddx,y,dy,ddy,sx,sy}
+  const double(*Pm)[16] = c_pc.P[SIM ? 1 : 0];
+  const double2 *src = p + o;
+  // first tile: samples [0, TILE + NLpad) fill the whole ring; samples past the trajectory read as zero
+  for (int e = lane; e < CAP; e += 32) cp_async16(sp + pad9(e), src + (e < L ? e : 0), e < L ? 16u : 0u);
+  cp_async_commit();
+  int base = 0;                                // ring slot of sample `start`
+
+  for (int start = 0; start < nsteps; start += RW_TILE) {
+    cp_async_wait_all();
+    __syncwarp();                              // this tile's samples have landed
+    int own0 = base + FIR_R * lane;            // slot of this lane's first sample
+    if (own0 >= CAP) own0 -= CAP;
+
+    // ---- (1a) W at the tile's end, partial sums over this lane's halo samples
+    {
+      double h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = 0.0;
+      int hb = base + RW_TILE;
+      if (hb >= CAP) hb -= CAP;
+      for (int i0 = lane; i0 < NL; i0 += 32 * RW_U) {
+        double2 e01[RW_U], e23[RW_U], q[RW_U];
+#pragma unroll
+        for (int u = 0; u < RW_U; ++u) {
+          const int i = i0 + 32 * u;
+          const bool in = i < NL;
+          const int ii = in ? i : 0;
+          e01[u] = __ldg(Etab + 2 * ii);
+          e23[u] = __ldg(Etab + 2 * ii + 1);
+          int hi = hb + ii;
+          if (hi >= CAP) hi -= CAP;
+          q[u] = in ? sp[pad9(hi)] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < RW_U; ++u) {
+          h[0] = fma(e01[u].x, q[u].x, h[0]); h[1] = fma(e01[u].y, q[u].x, h[1]);
+          h[2] = fma(e23[u].x, q[u].x, h[2]); h[3] = fma(e23[u].y, q[u].x, h[3]);
+          h[4] = fma(e01[u].x, q[u].y, h[4]); h[5] = fma(e01[u].y, q[u].y, h[5]);
+          h[6] = fma(e23[u].x, q[u].y, h[6]); h[7] = fma(e23[u].y, q[u].y, h[7]);
+        }
+      }
+      // warp sum of 8 values with 9 shuffles: halve the set of values a lane carries at each of the first three levels
+      double k4[4], k2[2], k1;
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double send = up ? h[j] : h[4 + j];
+          k4[j] = (up ? h[4 + j] : h[j]) + __shfl_xor_sync(FULL, send, 16);
+        }
+      }
+      {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double send = up ? k4[j] : k4[2 + j];
+          k2[j] = (up ? k4[2 + j] : k4[j]) + __shfl_xor_sync(FULL, send, 8);
+        }
+      }
+      {
+        const bool up = (lane & 4) != 0;
+        const double send = up ? k2[0] : k2[1];
+        k1 = (up ? k2[1] : k2[0]) + __shfl_xor_sync(FULL, send, 4);
+      }
+      k1 += __shfl_xor_sync(FULL, k1, 2);
+      k1 += __shfl_xor_sync(FULL, k1, 1);
+      if ((lane & 3) == 0) s_halo[((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0)] = k1;
+    }
+
+    // ---- (1b) local pass (as preview_rec_kernel)
+    double ax[FIR_R], ay[FIR_R];
+    double2 pk[FIR_R];
+    Axis bx, by;
+    bx.x0 = bx.x1 = bx.x2 = bx.s = 0.0;
+    by = bx;
+    {
+      const double2 *own = sp + pad9(own0);
+#pragma unroll
+      for (int r = 0; r < FIR_R; ++r) { ax[r] = 0.0; ay[r] = 0.0; }
+#pragma unroll
+      for (int j = 0; j < FIR_R; ++j) {
+        const double2 a = own[j];
+        int fi = own0 + j + NL;
+        if (fi >= CAP) fi -= CAP;
+        const double2 f = sp[pad9(fi)];
+        pk[j] = SIM ? a : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r <= j; ++r) {
+          ax[r] = fma(c_pc.RF0[j - r], a.x, ax[r]); ax[r] = fma(c_pc.RFN[j - r], f.x, ax[r]);
+          ay[r] = fma(c_pc.RF0[j - r], a.y, ay[r]); ay[r] = fma(c_pc.RFN[j - r], f.y, ay[r]);
+        }
+        bx.x0 = fma(c_pc.RV[j][0], a.x, bx.x0); bx.x0 = fma(c_pc.RVN[j][0], f.x, bx.x0);
+        bx.x1 = fma(c_pc.RV[j][1], a.x, bx.x1); bx.x1 = fma(c_pc.RVN[j][1], f.x, bx.x1);
+        bx.x2 = fma(c_pc.RV[j][2], a.x, bx.x2); bx.x2 = fma(c_pc.RVN[j][2], f.x, bx.x2);
+        bx.s = fma(c_pc.RV[j][3], a.x, bx.s); bx.s = fma(c_pc.RVN[j][3], f.x, bx.s);
+        by.x0 = fma(c_pc.RV[j][0], a.y, by.x0); by.x0 = fma(c_pc.RVN[j][0], f.y, by.x0);
+        by.x1 = fma(c_pc.RV[j][1], a.y, by.x1); by.x1 = fma(c_pc.RVN[j][1], f.y, by.x1);
+        by.x2 = fma(c_pc.RV[j][2], a.y, by.x2); by.x2 = fma(c_pc.RVN[j][2], f.y, by.x2);
+        by.s = fma(c_pc.RV[j][3], a.y, by.s); by.s = fma(c_pc.RVN[j][3], f.y, by.s);
+      }
+    }
+    __syncwarp();          // every read of this tile's samples is done; s_halo is written
+    // the slots of the tile's own samples are dead: they receive what the next tile adds, samples [start + CAP, start + CAP + TILE)
+    if (start + RW_TILE < nsteps) {
+      const int first = start + CAP;
+#pragma unroll
+      for (int u = 0; u < FIR_R; ++u) {
+        const int e = lane + 32 * u;
+        int ri = base + e;
+        if (ri >= CAP) ri -= CAP;
+        const bool in = first + e < L;
+        cp_async16(sp + pad9(ri), src + (in ? first + e : 0), in ? 16u : 0u);
+      }
+      cp_async_commit();
+    }
+    // ---- (1c) lane 31 takes W at the tile's end, then Kogge-Stone DOWN the tile: c_t += L^(8d) c_{t+d}
+    Axis ix, iy;                               // W at tick 8 lane + 8 (the end of this lane's ticks)
+    ix.x0 = s_halo[0]; ix.x1 = s_halo[1]; ix.x2 = s_halo[2]; ix.s = s_halo[3];
+    iy.x0 = s_halo[4]; iy.x1 = s_halo[5]; iy.x2 = s_halo[6]; iy.s = s_halo[7];
+    if (lane == 31) {
+      scan_combine(bx, c_pc.RP[0], ix.x0, ix.x1, ix.x2, ix.s);
+      scan_combine(by, c_pc.RP[0], iy.x0, iy.x1, iy.x2, iy.s);
+    }
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      const int d = 1 << l;
+      const double a0 = __shfl_down_sync(FULL, bx.x0, d), a1 = __shfl_down_sync(FULL, bx.x1, d);
+      const double a2 = __shfl_down_sync(FULL, bx.x2, d), a3 = __shfl_down_sync(FULL, bx.s, d);
+      const double b0 = __shfl_down_sync(FULL, by.x0, d), b1 = __shfl_down_sync(FULL, by.x1, d);
+      const double b2 = __shfl_down_sync(FULL, by.x2, d), b3 = __shfl_down_sync(FULL, by.s, d);
+      if (lane + d < 32) {
+        scan_combine(bx, c_pc.RP[l], a0, a1, a2, a3);
+        scan_combine(by, c_pc.RP[l], b0, b1, b2, b3);
+      }
+    }
+    {
+      const double a0 = __shfl_down_sync(FULL, bx.x0, 1), a1 = __shfl_down_sync(FULL, bx.x1, 1);
+      const double a2 = __shfl_down_sync(FULL, bx.x2, 1), a3 = __shfl_down_sync(FULL, bx.s, 1);
+      const double b0 = __shfl_down_sync(FULL, by.x0, 1), b1 = __shfl_down_sync(FULL, by.x1, 1);
+      const double b2 = __shfl_down_sync(FULL, by.x2, 1), b3 = __shfl_down_sync(FULL, by.s, 1);
+      if (lane != 31) {
+        ix.x0 = a0; ix.x1 = a1; ix.x2 = a2; ix.s = a3;
+        iy.x0 = b0; iy.x1 = b1; iy.x2 = b2; iy.s = b3;
+      }
+    }
+    // ---- (1d) f of tick r += (w' L^(8 - r)) . W_in
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r) {
+      const double *g = c_pc.RW[FIR_R - r];
+      ax[r] = fma(g[0], ix.x0, fma(g[1], ix.x1, fma(g[2], ix.x2, fma(g[3], ix.s, ax[r]))));
+      ay[r] = fma(g[0], iy.x0, fma(g[1], iy.x1, fma(g[2], iy.x2, fma(g[3], iy.s, ay[r]))));
+    }
+
+    // ---- (2a) local aggregate of the cart-table recursion; lane 0 takes the carried state
+    Axis cx, cy, inx, iny;
+    cx.x0 = cx.x1 = cx.x2 = cx.s = 0.0;
+    cy.x0 = cy.x1 = cy.x2 = cy.s = 0.0;
+    inx = cx; iny = cy;
+    {
+      const double(*Gm)[4] = c_pc.G[SIM ? 1 : 0];
+      const double(*Hm)[4] = c_pc.H[SIM ? 1 : 0];
+#pragma unroll
+      for (int r = 0; r < FIR_R; ++r) {
+        cx.x0 = fma(Gm[r][0], ax[r], cx.x0); cx.x1 = fma(Gm[r][1], ax[r], cx.x1);
+        cx.x2 = fma(Gm[r][2], ax[r], cx.x2); cx.s = fma(Gm[r][3], ax[r], cx.s);
+        cy.x0 = fma(Gm[r][0], ay[r], cy.x0); cy.x1 = fma(Gm[r][1], ay[r], cy.x1);
+        cy.x2 = fma(Gm[r][2], ay[r], cy.x2); cy.s = fma(Gm[r][3], ay[r], cy.s);
+        if (SIM) {
+          cx.x0 = fma(Hm[r][0], pk[r].x, cx.x0); cx.x1 = fma(Hm[r][1], pk[r].x, cx.x1);
+          cx.x2 = fma(Hm[r][2], pk[r].x, cx.x2); cx.s = fma(Hm[r][3], pk[r].x, cx.s);
+          cy.x0 = fma(Hm[r][0], pk[r].y, cy.x0); cy.x1 = fma(Hm[r][1], pk[r].y, cy.x1);
+          cy.x2 = fma(Hm[r][2], pk[r].y, cy.x2); cy.s = fma(Hm[r][3], pk[r].y, cy.s);
+        }
+      }
+      if (lane == 0) {
+        inx.x0 = s_carry[0]; inx.x1 = s_carry[1]; inx.x2 = s_carry[2]; inx.s = s_carry[6];
+        iny.x0 = s_carry[3]; iny.x1 = s_carry[4]; iny.x2 = s_carry[5]; iny.s = s_carry[7];
+        scan_combine(cx, Pm[0], inx.x0, inx.x1, inx.x2, inx.s);
+        scan_combine(cy, Pm[0], iny.x0, iny.x1, iny.x2, iny.s);
+      }
+    }
+    // ---- (2b) Kogge-Stone scan UP the tile: c_t += M^(8d) c_{t-d}
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      const int d = 1 << l;
+      const double a0 = __shfl_up_sync(FULL, cx.x0, d), a1 = __shfl_up_sync(FULL, cx.x1, d);
+      const double a2 = __shfl_up_sync(FULL, cx.x2, d), a3 = __shfl_up_sync(FULL, cx.s, d);
+      const double b0 = __shfl_up_sync(FULL, cy.x0, d), b1 = __shfl_up_sync(FULL, cy.x1, d);
+      const double b2 = __shfl_up_sync(FULL, cy.x2, d), b3 = __shfl_up_sync(FULL, cy.s, d);
+      if (lane >= d) {
+        scan_combine(cx, Pm[l], a0, a1, a2, a3);
+        scan_combine(cy, Pm[l], b0, b1, b2, b3);
+      }
+    }
+    // ---- (2c) true start state of this lane = inclusive result of lane - 1
+    Axis sx, sy;
+    sx.x0 = __shfl_up_sync(FULL, cx.x0, 1); sx.x1 = __shfl_up_sync(FULL, cx.x1, 1);
+    sx.x2 = __shfl_up_sync(FULL, cx.x2, 1); sx.s = __shfl_up_sync(FULL, cx.s, 1);
+    sy.x0 = __shfl_up_sync(FULL, cy.x0, 1); sy.x1 = __shfl_up_sync(FULL, cy.x1, 1);
+    sy.x2 = __shfl_up_sync(FULL, cy.x2, 1); sy.s = __shfl_up_sync(FULL, cy.s, 1);
+    if (lane == 0) { sx = inx; sy = iny; }
+    __syncwarp();                              // s_carry and s_halo have been read
+    // ---- (2d) final pass, rows stored straight from registers (256-bit stores, see preview_rec_kernel)
+    const int k0 = start + FIR_R * lane;
+    const int last = min(start + RW_TILE, nsteps) - 1;   // last valid tick of this tile
+    {
+      double *gc = com ? com + 6 * (size_t)(o + k0) : nullptr;
+      double *gz = zmp ? zmp + 2 * (size_t)(o + k0) : nullptr;
+      const double *ga = ADD ? com_add + 6 * (size_t)(o + k0) : nullptr;
+      const bool c32 = ((reinterpret_cast<uintptr_t>(gc) | (ADD ? reinterpret_cast<uintptr_t>(ga) : 0)) & 31) == 0;
+      const bool z32 = (reinterpret_cast<uintptr_t>(gz) & 31) == 0;
+#pragma unroll
+      for (int j = 0; j < FIR_R / 2; ++j) {
+        const int r0 = 2 * j, r1 = 2 * j + 1;
+        if (k0 + r1 <= last) {                 // both ticks of the pair are valid
+          const double zx0 = preview_tick<SIM>(sx, ax[r0], pk[r0].x);
+          const double zy0 = preview_tick<SIM>(sy, ay[r0], pk[r0].y);
+          double a0 = sx.x0, a1 = sx.x1, a2 = sx.x2, a3 = sy.x0, a4 = sy.x1, a5 = sy.x2;
+          const double u0 = POS ? sx.x0 : zx0, u1 = POS ? sy.x0 : zy0;
+          const double zx1 = preview_tick<SIM>(sx, ax[r1], pk[r1].x);
+          const double zy1 = preview_tick<SIM>(sy, ay[r1], pk[r1].y);
+          if (com) {
+            double b0 = sx.x0, b1 = sx.x1, b2 = sx.x2, b3 = sy.x0, b4 = sy.x1, b5 = sy.x2;
+            if (ADD) {
+              double q[12];
+              ld32g(ga + 6 * r0, q[0], q[1], q[2], q[3], c32);
+              ld32g(ga + 6 * r0 + 4, q[4], q[5], q[6], q[7], c32);
+              ld32g(ga + 6 * r0 + 8, q[8], q[9], q[10], q[11], c32);
+              a0 += q[0]; a1 += q[1]; a2 += q[2]; a3 += q[3]; a4 += q[4]; a5 += q[5];
+              b0 += q[6]; b1 += q[7]; b2 += q[8]; b3 += q[9]; b4 += q[10]; b5 += q[11];
+            }
+            st32g(gc + 6 * r0, a0, a1, a2, a3, c32);
+            st32g(gc + 6 * r0 + 4, a4, a5, b0, b1, c32);
+            st32g(gc + 6 * r0 + 8, b2, b3, b4, b5, c32);
+          }
+          if (zmp) st32g(gz + 2 * r0, u0, u1, POS ? sx.x0 : zx1, POS ? sy.x0 : zy1, z32);
+        } else if (k0 + r0 <= last) {          // the trajectory ends on the first tick of the pair
+          const double zx0 = preview_tick<SIM>(sx, ax[r0], pk[r0].x);
+          const double zy0 = preview_tick<SIM>(sy, ay[r0], pk[r0].y);
+          if (com) {
+            double a0 = sx.x0, a1 = sx.x1, a2 = sx.x2, a3 = sy.x0, a4 = sy.x1, a5 = sy.x2;
+            if (ADD) {
+              const double2 q0 = __ldg(reinterpret_cast<const double2 *>(ga + 6 * r0));
+              const double2 q1 = __ldg(reinterpret_cast<const double2 *>(ga + 6 * r0) + 1);
+              const double2 q2 = __ldg(reinterpret_cast<const double2 *>(ga + 6 * r0) + 2);
+              a0 += q0.x; a1 += q0.y; a2 += q1.x; a3 += q1.y; a4 += q2.x; a5 += q2.y;
+            }
+            double2 *g2 = reinterpret_cast<double2 *>(gc + 6 * r0);
+            g2[0] = make_double2(a0, a1); g2[1] = make_double2(a2, a3); g2[2] = make_double2(a4, a5);
+          }
+          if (zmp) *reinterpret_cast<double2 *>(gz + 2 * r0) = POS ? make_double2(sx.x0, sy.x0) : make_double2(zx0, zy0);
+        }
+      }
+    }
+    if (k0 <= last && last < k0 + FIR_R) {   // the lane that ran the tile's last valid tick carries the state
+      s_carry[0] = sx.x0; s_carry[1] = sx.x1; s_carry[2] = sx.x2; s_carry[6] = sx.s;
+      s_carry[3] = sy.x0; s_carry[4] = sy.x1; s_carry[5] = sy.x2; s_carry[7] = sy.s;
+    }
+    base += RW_TILE;
+    if (base >= CAP) base -= CAP;
+  }
+  __syncwarp();
+  if (lane < 8) state[8 * (size_t)b + lane] = s_carry[lane];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1280,6 +1594,40 @@ static int preview_launch_rec(wg_ctx *ctx, wg_preview_plan *pl, const int *d_ord
 #undef WG_REC_LAUNCH
 }
 
+// The recursive kernel, one warp per trajectory.
+static int preview_launch_recw(wg_ctx *ctx, wg_preview_plan *pl, const int *d_order, int count, const double *d_zmp,
+                               double *d_state, double *d_com, double *d_zmpout, int simulation,
+                               const double *d_com_add, bool pos_only)
+{
+  const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
+  const int cap = RW_TILE + NLpad;
+  const size_t smem = sizeof(double2) * (size_t)(cap + (cap >> 3) + 2);
+  if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the tile");
+  constexpr int slot = WG_ATTR_PREVIEW_REC_0 + 5;
+  const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
+  const double2 *E = reinterpret_cast<const double2 *>(ctx->preview_rec_dev);
+  std::lock_guard<std::mutex> lock(g_pv_mutex);
+  { const int rc = preview_bind(ctx); if (rc != WG_OK) return rc; }
+#define WG_RECW_LAUNCH(SLOT, SIMF, ADDF, POSF, COM, ADDP)                                                               \
+  do {                                                                                                                 \
+    WG_SMEM_ATTR(ctx, slot + (SLOT), (preview_rec_warp_kernel<SIMF, ADDF, POSF>), smem);                                \
+    wg_prof_start(ctx, WG_K_PREVIEW_FUSED);                                                                            \
+    preview_rec_warp_kernel<SIMF, ADDF, POSF><<<count, 32, smem, ctx->stream>>>(d_order, pl->d_offsets, pz, d_state,    \
+                                                                                 COM, d_zmpout, ADDP, E);              \
+    wg_prof_stop(ctx);                                                                                                 \
+    WG_LAUNCHED(ctx);                                                                                                  \
+    return WG_OK;                                                                                                      \
+  } while (0)
+  if (pos_only) {
+    if (simulation) WG_RECW_LAUNCH(0, true, false, true, nullptr, nullptr);
+    else WG_RECW_LAUNCH(1, false, false, true, nullptr, nullptr);
+  }
+  if (d_com_add && d_com) WG_RECW_LAUNCH(2, true, true, false, d_com, d_com_add);
+  if (simulation) WG_RECW_LAUNCH(3, true, false, false, d_com, nullptr);
+  else WG_RECW_LAUNCH(4, false, false, false, d_com, nullptr);
+#undef WG_RECW_LAUNCH
+}
+
 extern "C" {
 
 int wg_preview_set_gains(wg_ctx *ctx, const wg_preview_gains_t *g)
@@ -1469,7 +1817,7 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
   if (ctx->preview_sum_mode != WG_PREVIEW_SUM_DIRECT && ctx->preview_rec_ok) {
     switch (shape) {
     case 1: return preview_launch_rec<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
-    case 2: return preview_launch_rec<32, 16>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
+    case 2: return preview_launch_recw(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
     default: return preview_launch_rec<64, 8>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
     }
   }
