@@ -168,6 +168,11 @@ enum { WG_PREVIEW_SUM_AUTO = 0, WG_PREVIEW_SUM_DIRECT = 1, WG_PREVIEW_SUM_RECURS
 double wg_preview_sum_fit(const wg_preview_gains_t *gains);   /* host only: the relative fit residual of a gain set, -1: none */
 int wg_preview_set_sum_mode(wg_ctx *ctx, int mode);
 int wg_preview_sum_info(wg_ctx *ctx, int *mode_in_use, double *fit_residual);
+/* Tuning knob: the CTA shape of the batch kernels.  -1 (default) = chosen per launch from the number of trajectories (the
+ * recursive sum runs one warp per trajectory once ~2000 trajectories fill the SMs, two or four warps per trajectory below that);
+ * 0 = 64 threads x 8 CTAs/SM, 1 = 128 x 4, 2 = 32 x 16.  Results do not depend on it beyond the summation order (1e-14).  The
+ * environment variable WG_PREVIEW_SHAPE, read once per process, overrides both. */
+int wg_preview_set_cta_shape(wg_ctx *ctx, int shape);
 
 /* A plan describes a ragged batch of B trajectories: trajectory b owns ZMP-reference samples
  * [offsets[b], offsets[b+1]) of a packed array of interleaved (px,py) pairs.  A trajectory of L

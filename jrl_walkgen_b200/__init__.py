@@ -197,6 +197,10 @@ class Context:
         """wg_preview_set_sum_mode: PREVIEW_SUM_AUTO / _DIRECT / _RECURSIVE."""
         self._check(self.lib.wg_preview_set_sum_mode(self.h, int(mode)))
 
+    def preview_set_cta_shape(self, shape: int):
+        """wg_preview_set_cta_shape: -1 per launch (default), 0 = 64 x 8, 1 = 128 x 4, 2 = one warp per trajectory."""
+        self._check(self.lib.wg_preview_set_cta_shape(self.h, int(shape)))
+
     def preview_sum_info(self):
         """(mode in use, relative residual of the fit F[i] = w' L^i v) - wg_preview_sum_info."""
         m, r = C.c_int(0), C.c_double(0.0)

@@ -263,6 +263,7 @@ SIGNATURES = {
     "wg_preview_set_gains": (C.c_int, [C.c_void_p, C.POINTER(PreviewGains)]),
     "wg_preview_sum_fit": (C.c_double, [C.POINTER(PreviewGains)]),
     "wg_preview_set_sum_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "wg_preview_set_cta_shape": (C.c_int, [C.c_void_p, C.c_int]),
     "wg_preview_sum_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "wg_preview_plan_create": (C.c_int, [C.c_void_p, C.c_int, c_i64_p, C.POINTER(C.c_void_p)]),
     "wg_preview_plan_destroy": (C.c_int, [C.c_void_p]),

@@ -1702,6 +1702,13 @@ int wg_preview_set_sum_mode(wg_ctx *ctx, int mode)
   return WG_OK;
 }
 
+int wg_preview_set_cta_shape(wg_ctx *ctx, int shape)
+{
+  if (!ctx || shape < -1 || shape > 2) return WG_ERR_INVALID;
+  ctx->preview_cta_shape = shape;
+  return WG_OK;
+}
+
 int wg_preview_sum_info(wg_ctx *ctx, int *mode_in_use, double *fit_residual)
 {
   if (!ctx) return WG_ERR_INVALID;
@@ -1807,14 +1814,20 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
                             int pos_only)
 {
   if (pl->total_steps == 0 || count <= 0) return WG_OK;
-  static int shape = -1;   // WG_PREVIEW_SHAPE: tuning knob for the CTA shape (default 64 threads x 8 CTAs/SM, 128 registers, no spills; measured 0.752 ms vs 0.778 (128 x 4) and 0.766 (32 x 16) on config 2)
-  if (shape < 0) {
+  // CTA shape: 0 = 64 threads x 8 CTAs/SM, 1 = 128 x 4, 2 = 32 x 16 (the recursive sum: one warp per trajectory, preview_rec_warp_kernel).
+  // WG_PREVIEW_SHAPE forces one; otherwise the recursive path takes the shape that fills the SMs with the trajectories of THIS launch
+  // (16 one-warp CTAs per SM need ~2400 trajectories on 148 SMs; measured on 4096 walks: 39.2 G steps/s one warp, 34.7 at 64 x 8,
+  // 35.4 at 128 x 4), the direct sum stays at 64 x 8 (measured 0.752 ms vs 0.778 (128 x 4) and 0.766 (32 x 16) on config 2).
+  static int forced = -2;
+  if (forced == -2) {
     const char *e = getenv("WG_PREVIEW_SHAPE");
-    shape = e ? atoi(e) : 0;
+    forced = e ? atoi(e) : -1;
   }
+  const bool recursive = ctx->preview_sum_mode != WG_PREVIEW_SUM_DIRECT && ctx->preview_rec_ok;
+  const int shape = forced >= 0 ? forced : ctx->preview_cta_shape >= 0 ? ctx->preview_cta_shape : !recursive ? 0 : count >= 2048 ? 2 : count >= 1024 ? 0 : 1;
   if (ctx->preview_sum_mode == WG_PREVIEW_SUM_RECURSIVE && !ctx->preview_rec_ok)
     return wg_fail(ctx, WG_ERR_INVALID, "WG_PREVIEW_SUM_RECURSIVE: the window weights of this context are not of the form w' L^i v");
-  if (ctx->preview_sum_mode != WG_PREVIEW_SUM_DIRECT && ctx->preview_rec_ok) {
+  if (recursive) {
     switch (shape) {
     case 1: return preview_launch_rec<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
     case 2: return preview_launch_recw(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);

@@ -42,6 +42,7 @@ struct wg_ctx {
   unsigned long long preview_gen = 0;         // bumped by wg_preview_set_gains
   void *preview_tick = nullptr;               // buffers of wg_preview_one_iteration (preview.cu)
   int preview_sum_mode = WG_PREVIEW_SUM_AUTO;  // wg_preview_set_sum_mode
+  int preview_cta_shape = -1;                 // wg_preview_set_cta_shape (-1: per launch)
   bool preview_rec_ok = false;                // the window weights fit w' L^i v within WG_PREVIEW_REC_TOL (rec_setup, preview.cu)
   double preview_rec_residual = -1.0;
   void *preview_rec_dev = nullptr;            // device tables of preview_rec_kernel

@@ -433,23 +433,29 @@ def test_gpu_recursive_and_direct_preview_sums_agree_with_the_oracle(ctx, cfg):
         for sim in ((True, False) if mode == 1 else (False,)):
             st_o = st0.copy()
             com_o, zmp_o, _ = ol.oracle_preview_batch(og, offsets, z, st_o, simulation=sim)
-            for name, m in (("recursive", wg.PREVIEW_SUM_RECURSIVE), ("direct", wg.PREVIEW_SUM_DIRECT)):
+            for name, m, shape in (("recursive", wg.PREVIEW_SUM_RECURSIVE, -1), ("recursive 64x8", wg.PREVIEW_SUM_RECURSIVE, 0),
+                                   ("recursive 128x4", wg.PREVIEW_SUM_RECURSIVE, 1), ("recursive one warp", wg.PREVIEW_SUM_RECURSIVE, 2),
+                                   ("direct", wg.PREVIEW_SUM_DIRECT, -1)):
                 ctx.preview_set_gains(gains)
                 ctx.preview_set_sum_mode(m)
+                ctx.preview_set_cta_shape(shape)
                 used, resid = ctx.preview_sum_info()
                 assert used == m and 0 <= resid < 1e-13
-                com, zmp, st, _ = _run_gpu(ctx, gains, offsets, z, st0, sim, mem_device=(name == "recursive"))
+                com, zmp, st, _ = _run_gpu(ctx, gains, offsets, z, st0, sim, mem_device=name.startswith("recursive"))
                 out[name] = (com, zmp, st)
                 assert np.abs(com[rows] - com_o[rows])[:, [0, 3]].max() < TOL_COM, (name, sim)
                 assert np.abs(com[rows] - com_o[rows]).max() < 1e-7, (name, sim)
                 assert np.abs(zmp[rows] - zmp_o[rows]).max() < 1e-8, (name, sim)
                 assert np.allclose(st, st_o, rtol=1e-7, atol=1e-8), (name, sim)
+            for name in ("recursive 64x8", "recursive 128x4", "recursive one warp"):
+                assert np.abs(out[name][0][rows] - out["direct"][0][rows])[:, [0, 3]].max() < 1e-11, name
             d = np.abs(out["recursive"][0][rows] - out["direct"][0][rows])
             print(f"cfg {cfg} sim {sim}: recursive vs direct sum, max |dCoM| = {d[:, [0, 3]].max():.2e} m, "
                   f"|d ddCoM| = {d[:, [2, 5]].max():.2e} m/s^2")
             assert d[:, [0, 3]].max() < 1e-11
     finally:
         ctx.preview_set_sum_mode(wg.PREVIEW_SUM_AUTO)
+        ctx.preview_set_cta_shape(-1)
 
 
 @pytest.mark.gpu

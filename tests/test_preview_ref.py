@@ -174,9 +174,11 @@ def _gpu_run(ctx, gains, offsets, z, st0, simulation=True):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [-1, 0, 2])
 @pytest.mark.parametrize("own_gains", [False, True])
-def test_gpu_preview_vs_reference_object(ctx, own_gains):
-    """preview_fused_kernel against PreviewControl::OneIterationOfPreview of the reference object on the StraightWalking
+def test_gpu_preview_vs_reference_object(ctx, own_gains, shape):
+    """The batch preview kernels (shape -1: the default choice for this batch size; 0: preview_rec_kernel at 64 x 8; 2:
+    preview_rec_warp_kernel, the one a batch of thousands of walks runs through) against PreviewControl::OneIterationOfPreview of the reference object on the StraightWalking
     ZMP reference and 64 random walks.  own_gains=False: both sides use the product's gains (pins the recursion);
     own_gains=True: the reference computes its own gains through dgges_ (pins gains + recursion end to end)."""
     import jrl_walkgen_b200 as wg
@@ -194,8 +196,13 @@ def test_gpu_preview_vs_reference_object(ctx, own_gains):
     offsets = np.concatenate([[0], np.cumsum([len(w) for w in walks])]).astype(np.int64)
     z = np.concatenate(walks)
     st0 = rng.normal(scale=0.01, size=(len(walks), 8)); st0[0] = 0.0
+    ctx.preview_set_cta_shape(shape)
     for simulation in (True, False):
-        com, zmp, st = _gpu_run(ctx, gains, offsets, z, st0, simulation)
+        try:
+            com, zmp, st = _gpu_run(ctx, gains, offsets, z, st0, simulation)
+        except Exception:
+            ctx.preview_set_cta_shape(-1)
+            raise
         worst = 0.0
         for b, w in enumerate(walks):
             sr = st0[b].copy()
@@ -207,6 +214,7 @@ def test_gpu_preview_vs_reference_object(ctx, own_gains):
             worst = max(worst, e)
             assert np.allclose(st[b, :6], sr[:6], atol=1e-8, rtol=0)
         assert worst < (TOL_COM if simulation else 1e-7), worst
+    ctx.preview_set_cta_shape(-1)
     rp.close()
 
 
