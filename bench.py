@@ -311,7 +311,7 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "herdt": herdt, "herdt_qp_solves_per_s": None if herdt is None else herdt["value"],
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1002,7 +1002,7 @@ def run_cuda(args):
         plan.run(dz, ds, dcom, dzmp, True, mem=wg.WG_MEM_DEVICE)
 
     # A bench "step" is `passes` passes over the 4096-walk batch (default 72: K = 20 steps time ~1.1 s of kernels, so that
-    # clocks and throttle reasons are sampled under sustained load; one pass alone is 0.77 ms).  Every pass re-reads the
+    # clocks and throttle reasons are sampled under sustained load; one pass alone is 0.39 ms).  Every pass re-reads the
     # 254 MB input and rewrites the 1.0 GB output, far above the 126 MB L2: nothing is served from cache between passes.
     passes = max(1, args.passes_per_step)
     for _ in range(max(args.warmup, 3)):
@@ -1198,9 +1198,12 @@ def run_cuda(args):
         fp64_src = ("measured live: register-resident DFMA chains on all SMs (wg_measure_fp64_peak); "
                     "MEASURED_PEAKS.json has no FP64 entry")
         if sum_mode == wg.PREVIEW_SUM_RECURSIVE:
-            # preview_rec_kernel: the window sum as a backward linear recurrence (~170 FMA per step for everything): the
-            # kernel streams 16 B in and 64 B out per step and is bounded by HBM, SURVEY 8(d)'s 80 B per step
-            dom_name = "preview_rec_kernel"
+            # the window sum as a backward linear recurrence (~170 FMA per step for everything): the kernel streams 16 B in
+            # and 64 B out per step and is bounded by HBM, SURVEY 8(d)'s 80 B per step.  A device-resident batch of >= 2048
+            # walks runs one warp per trajectory (preview_rec_warp_kernel), smaller ones preview_rec_kernel (preview.cu)
+            shape_env = os.environ.get("WG_PREVIEW_SHAPE")
+            one_warp = (int(shape_env) == 2) if shape_env is not None else args.walks >= 2048
+            dom_name = "preview_rec_warp_kernel" if one_warp else "preview_rec_kernel"
             kern = {dom_name: kern.pop("preview_fused_kernel")}
             ach = BYTES_PER_STEP * steps_per_pass / (dom_ms * 1e-3) / 1e9
             roof = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
@@ -1261,11 +1264,24 @@ def run_cuda(args):
                         "bound": "host link: %.0f B per preview step cross PCIe (16 in, 64 out); at the probed D2H rate the "
                                  "64 B/step alone cap the leg at %.2f G steps/s" % (BYTES_PER_STEP, d2h_sum / 64.0)},
                 "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     plan.destroy()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+_STDOUT_FD = None
+
+
+def emit_line(line):
+    """The bench's JSON line, on the process's real stdout."""
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+    if _STDOUT_FD is not None:
+        os.dup2(2, 1)
 
 
 def main():
@@ -1288,12 +1304,18 @@ def main():
     ap.add_argument("--no-wieber", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="(default since round 2; kept for old command lines)")
     ap.add_argument("--no-sweep", action="store_true", help="skip BASELINE configs[4]: 1M MPC instances x 100 periods")
-    ap.add_argument("--passes-per-step", type=int, default=72,
-                    help="passes over the batch per bench step (timed region = steps x passes x 0.77 ms)")
+    ap.add_argument("--passes-per-step", type=int, default=160,
+                    help="passes over the batch per bench step (timed region = steps x passes x 0.39 ms: >= 1 s at the default 20 steps)")
     ap.add_argument("--e2e-passes", type=int, default=48)
     ap.add_argument("--sweep-instances", type=int, default=1000000)
     ap.add_argument("--sweep-periods", type=int, default=100)
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that print to file descriptor 1 on their own (NCCL announces
+    # its version there when the box sets NCCL_DEBUG) are sent to stderr for the run; emit_line() puts the descriptor back
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

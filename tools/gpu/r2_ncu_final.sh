@@ -4,10 +4,10 @@ mkdir -p gpurun_out
 TAG=${TAG:-r2b}
 COMMON="--steps 2 --warmup 1 --cpu-seconds 0.5 --passes-per-step 2 --e2e-passes 2 --no-sweep"
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py $COMMON --wieber-walks 64 > gpurun_out/launches_${TAG}.log 2>&1
-for k in ${KERNELS:-preview_fused herdt_qp pldp zmpdisc fcals dimitrov qld wieber_pre}; do
+for k in ${KERNELS:-preview_rec_warp preview_fused herdt_qp pldp zmpdisc fcals dimitrov qld wieber_pre}; do
   extra=""; skip=3
   case $k in
-    preview_fused) extra="--no-herdt --no-pldp --no-kajita --no-dimitrov --no-wieber";;
+    preview_rec_warp|preview_fused) extra="--no-herdt --no-pldp --no-kajita --no-dimitrov --no-wieber";;
     herdt_qp) extra="--no-pldp --no-kajita --no-dimitrov --no-wieber";;
     pldp) extra="--no-herdt --no-kajita --no-dimitrov --no-wieber";;
     zmpdisc) extra="--no-herdt --no-pldp --no-dimitrov --no-wieber"; skip=2;;
