@@ -25,6 +25,8 @@ template <typename T> class vector {
   vector() {}
   explicit vector(std::size_t n) : d_(n, T()) {}
   void resize(std::size_t n) { d_.resize(n, T()); }
+  void resize(std::size_t n, bool) { d_.resize(n, T()); }     /* uBLAS resize(n, preserve) */
+  void clear() { fill(T()); }                                /* uBLAS clear(): zero the elements */
   std::size_t size() const { return d_.size(); }
   T &operator()(std::size_t i) { return d_[i]; }
   const T &operator()(std::size_t i) const { return d_[i]; }

@@ -145,6 +145,53 @@ def test_oracle_loop_equals_the_loop_driven_through_the_reference_pldp_object():
     ref.close()
 
 
+REF_OBJECT_CASES = ("StraightWalking", "StraightWalking@500", "StraightWalking@900", "Circle@200", "Circle@300", "Circle@640",
+                    "Circle@1000", "PbFlorentSeq1@700", "PbFlorentSeq1@1500", "PbFlorentSeq2@1200")
+
+
+@needs_ref
+@pytest.mark.parametrize("case", REF_OBJECT_CASES)
+def test_oracle_equals_the_reference_generator_object(case):
+    """The reference's OWN ZMPConstrainedQPFastFormulation object (its .cpp compiled into oracle/_ref together with
+    LinearizedInvertedPendulum2D.cpp and privatepgtypes.cpp; constructor -> InitConstants, then
+    BuildZMPTrajectoryFromFootTrajectory in PLDP mode) against the oracle:
+      * InitConstants(): Px, Pu = iLQ Pu', iLQ, OptB, OptC BITWISE (both axes' blocks; off-diagonal blocks zero); iPu is LAPACK's
+        LU inverse in the reference (MAL_INVERSE) and agrees to 1e-15 relative;
+      * the whole loop - polygon look-up by accumulated clocks, DPx / DPu / D, the PLDP solve with the real SimilarConstraints
+        flags and hot starts, jerk recovery through iLQ, LIPM interpolation - BITWISE on CoM (x, dx, ddx, y, dy, ddy) and ZMP for
+        every period up to the one at which the reference stops, once both sides hold the same iPu; and the stop falls on the
+        same period for the same reason: exit(0) after "PB ON constraint" (trapped by the glue) <-> status 2, IFAIL / return -1
+        <-> a NaN solution (status 0 with rc -1, or 3 when more than 2N rows were activated).
+    "<profile>@<k>" hands the generator the feet buffers from sample k on: every unshifted walk stops at its 18th period (the
+    m_tol drift of the hot start during the initial double support), so later phases - single support, rotated feet, the
+    duplicated half-planes of arcs - are reached this way; 10 cases, 17 + 148 + 82 + 40 + 34 + 2 + 2 + 77 + 47 + 75 periods.
+    With LAPACK's own inverse (1 ulp away) the solver's m_tol pushes (PLDPSolver.cpp:617-618) land differently: 3e-8 m over
+    the 17 periods of the unshifted walk - the reason the comparison pins the inverse.  Subprocess: see the glue's exit trap."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import preview_ref as pr
+    if not pr.lapack_available():
+        pytest.skip("no LAPACK with dgetrf_/dgetri_ in this image (the reference's MAL_INVERSE)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "dimitrov_ref_object.py"), case], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["constants_bitwise"] and d["iPu_rel"] < 1e-14 and d["iPu_Pu_identity"] < 1e-12
+    assert d["oracle_stop"] is not None and d["periods_compared"] == d["oracle_stop"]
+    if d["ref_rc"] == -100:
+        assert d["oracle_stop_status"] == 2, d            # exit(0): negative step length after an infeasible hot start
+    else:
+        assert d["ref_rc"] == -1 and d["oracle_stop_status"] in (0, 3), d
+    if d["periods_compared"]:
+        assert d["com_bitwise"] and d["com_err"] == 0.0 and d["zmp_err"] == 0.0, d
+    if case == "StraightWalking":
+        assert d["periods_compared"] == 17 and d["ref_rc_lapack_inverse"] == -100
+        assert d["com_err_lapack_inverse"] < 1e-7 and d["zmp_err_lapack_inverse"] < 1e-7
+
+
 @needs_ref
 @pytest.mark.parametrize("name", PROFILES)
 def test_oracle_loop_equals_reference_pldp_object_with_real_similar_flags_whole_walks(name):
