@@ -3,7 +3,7 @@ against the oracle: the constants InitConstants() computes, and BuildZMPTrajecto
 reachable one) on the feet buffers of one TestKajita2003 profile up to the period at which the reference stops (exit(0) on an
 infeasible hot start - caught by oracle/ref_glue_dimitrov.cc -, or IFAIL on a NaN solution).
 Run as a subprocess by tests/test_dimitrov.py.  TEST INFRASTRUCTURE ONLY.
-    python tests/dimitrov_ref_object.py <profile>   -> one JSON line ending the output."""
+    python tests/dimitrov_ref_object.py <profile> [<rows.npz> [<iPu.npy>]]  -> one JSON line ending the output."""
 import ctypes as C
 import json
 import os
@@ -56,7 +56,7 @@ class RefDimitrov:
         self.r.ref_dimitrov_delete(self.h)
 
 
-def main(name):
+def main(name, dump=None, ipu_file=None):
     assert pr.lapack_available(), "no LAPACK (dgetrf_/dgetri_) for the reference's MAL_INVERSE"
     par = do.default_params()
     ref = RefDimitrov(par)
@@ -85,7 +85,7 @@ def main(name):
     rc_l, com_l, zmp_l = ref.run(left, right, lt, par)  # the reference as built: iPu from LAPACK's LU inverse
     ref.close()
     ref = RefDimitrov(par)
-    ref.set_ipu(K.iPu)                                  # the same inverse on both sides
+    ref.set_ipu(np.load(ipu_file) if ipu_file else K.iPu)   # the same inverse on both sides
     rc, com, zmp = ref.run(left, right, lt, par)
     ref.close()
     res["ref_rc_lapack_inverse"] = int(rc_l)
@@ -106,8 +106,10 @@ def main(name):
         res["com_span"] = float(np.abs(out["com"][:rows, 0]).max())
         res["com_err_lapack_inverse"] = float(np.abs(com_l[:rows, :6] - out["com"][:rows]).max())
         res["zmp_err_lapack_inverse"] = float(np.abs(zmp_l[:rows, :2] - out["zmp"][:rows]).max())
+    if dump:      # the reference object's rows (same-inverse run) for a caller that compares something else with them
+        np.savez(dump, com=com[:rows, :6], zmp=zmp[:rows, :2], com_lapack=com_l[:rows, :6], zmp_lapack=zmp_l[:rows, :2])
     print(json.dumps(res))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else None)

@@ -391,6 +391,37 @@ def test_gpu_dimitrov_closed_loop_matches_oracle(ctx, name, cold):
 
 
 @pytest.mark.gpu
+@needs_ref
+def test_gpu_dimitrov_equals_the_reference_generator_object(ctx, tmp_path):
+    """wg_dimitrov_run_batch (defaults = the reference's semantics) against the reference's OWN ZMPConstrainedQPFastFormulation
+    object on TestKajita2003's straight walk: the reference ends the process at its 18th period (exit(0), trapped by the glue);
+    the GPU walk stops there with status 1, and the 340 rows of CoM (x, dx, ddx, y, dy, ddy) and ZMP before it are BITWISE the
+    object's when it holds the product's iPu, and within 1e-7 m when it keeps LAPACK's own inverse."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import preview_ref as pr
+    if not pr.lapack_available():
+        pytest.skip("no LAPACK with dgetrf_/dgetri_ in this image (the reference's MAL_INVERSE)")
+    G = ctx.dimitrov_set_params(_gpu_params(0))
+    np.save(tmp_path / "ipu.npy", np.ascontiguousarray(G["iPu"]))
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "dimitrov_ref_object.py"), "StraightWalking",
+                        str(tmp_path / "rows.npz"), str(tmp_path / "ipu.npy")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["ref_rc"] == -100 and d["periods_compared"] == 17
+    rows = np.load(tmp_path / "rows.npz")
+    out = ctx.dimitrov_run([zo.profile_steps("StraightWalking")], [zo.INIT_FEET])
+    assert out["status"][0] == 1 and out["periods_done"][0] in (17, 18)
+    n = 340
+    assert out["com"][:n].tobytes() == rows["com"].tobytes()
+    assert out["zmp"][:n].tobytes() == rows["zmp"].tobytes()
+    assert np.abs(out["com"][:n] - rows["com_lapack"]).max() < 1e-7 and np.abs(out["zmp"][:n] - rows["zmp_lapack"]).max() < 1e-7
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", PROFILES)
 def test_gpu_dimitrov_robust_mode_matches_oracle(ctx, name):
     """cold_restart + merge_duplicate_rows: every profile completes on the device as in the oracle."""
