@@ -988,7 +988,7 @@ def run_cuda(args):
 
     # ---- device-resident leg (value) -------------------------------------------------------
     dz = ctx.to_device(z)
-    st0 = np.zeros((B, 8))
+    st0 = ctx.pinned((B, 8)); st0[:] = 0.0     # pinned: the per-pass reset below is a true asynchronous copy on the stream
     ds = ctx.to_device(st0)
     dcom = ctx.alloc(n * 48); dzmp = ctx.alloc(n * 16)
 
@@ -1001,7 +1001,7 @@ def run_cuda(args):
         ctx._check(ctx.lib.wg_memcpy_h2d(ctx.h, ds.ptr, st0.ctypes.data, st0.nbytes))  # reset 256 KB of states
         plan.run(dz, ds, dcom, dzmp, True, mem=wg.WG_MEM_DEVICE)
 
-    # A bench "step" is `passes` passes over the 4096-walk batch (default 72: K = 20 steps time ~1.1 s of kernels, so that
+    # A bench "step" is `passes` passes over the 4096-walk batch (default 160: K = 20 steps time ~1.2 s of kernels, so that
     # clocks and throttle reasons are sampled under sustained load; one pass alone is 0.39 ms).  Every pass re-reads the
     # 254 MB input and rewrites the 1.0 GB output, far above the 126 MB L2: nothing is served from cache between passes.
     passes = max(1, args.passes_per_step)
