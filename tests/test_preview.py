@@ -459,6 +459,47 @@ def test_gpu_recursive_and_direct_preview_sums_agree_with_the_oracle(ctx, cfg):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["recursive", "direct"])
+def test_gpu_two_contexts_on_one_device_keep_their_own_gains(ctx, mode):
+    """Gains belong to a context, the kernels' constant block to the device: two contexts on cuda:0 with different gain sets
+    (different CoM height AND different window length), run alternately on plans created once, must each reproduce the oracle
+    with THEIR gains - the block is re-bound before a launch whenever it holds the other context's image."""
+    import jrl_walkgen_b200 as wg
+    rng = np.random.default_rng(5)
+    cfgs = [(0.005, 1.6, 0.814, 1), (0.005, 1.2, 0.60, 1)]
+    lens = [2100, 1400, 900]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    z = np.concatenate([synth_walk(rng, L) for L in lens])
+    st0 = rng.normal(scale=0.01, size=(len(lens), 8))
+    other = wg.Context(0)
+    try:
+        ctxs = [ctx, other]
+        plans, refs = [], []
+        for c, cfg in zip(ctxs, cfgs):
+            c.preview_set_gains(wg.preview_gains(*cfg))
+            c.preview_set_sum_mode(wg.PREVIEW_SUM_RECURSIVE if mode == "recursive" else wg.PREVIEW_SUM_DIRECT)
+            plans.append(c.preview_plan(offsets))
+            st_o = st0.copy()
+            com_o, zmp_o, _ = ol.oracle_preview_batch(ol.OracleGains(*cfg), offsets, z, st_o)
+            refs.append((com_o, zmp_o, st_o, _valid_rows(offsets, c.gains.NL)))
+        assert ctxs[0].gains.NL != ctxs[1].gains.NL
+        for _ in range(3):                       # A, B, A, B, ...: every launch finds the other context's image bound
+            for k in (0, 1):
+                st = st0.copy()
+                com = np.zeros((len(z), 6)); zmp = np.zeros((len(z), 2))
+                plans[k].run(z, st, com, zmp, True)
+                com_o, zmp_o, st_o, rows = refs[k]
+                assert np.abs(com[rows] - com_o[rows])[:, [0, 3]].max() < TOL_COM, (mode, k)
+                assert np.abs(zmp[rows] - zmp_o[rows]).max() < 1e-8, (mode, k)
+                assert np.allclose(st, st_o, rtol=1e-7, atol=1e-8), (mode, k)
+        for p in plans:
+            p.destroy()
+    finally:
+        other.close()
+        ctx.preview_set_sum_mode(wg.PREVIEW_SUM_AUTO)
+
+
+@pytest.mark.gpu
 def test_gpu_weights_without_the_structure_keep_the_direct_sum(ctx):
     """A gain table that is not matrix-geometric (here: rounded to the 5 digits of the reference's PreviewControlParameters.ini)
     runs through the direct sum under AUTO, RECURSIVE is refused, and the result is the oracle's for THAT table."""
