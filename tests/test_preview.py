@@ -409,11 +409,13 @@ def test_gpu_position_only_output_equals_the_full_run(ctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", [(0.005, 1.6, 0.807709, 1), (0.01, 1.6, 0.814, 0), (0.005, 0.8, 0.75, 1), (0.005, 1.595, 0.814, 1)])
+@pytest.mark.parametrize("cfg", [(0.005, 1.6, 0.807709, 1), (0.01, 1.6, 0.814, 0), (0.005, 0.8, 0.75, 1), (0.005, 1.595, 0.814, 1),
+                                 (0.002, 2.0, 0.814, 1), (0.005, 0.04, 0.814, 1), (0.001, 2.048, 0.814, 1)])
 def test_gpu_recursive_and_direct_preview_sums_agree_with_the_oracle(ctx, cfg):
     """Both evaluations of the preview sum - preview_rec_kernel (the default for weights of the reference's structure) and the
     direct 320-tap sum of preview_fused_kernel - against the oracle on a ragged batch (tile boundaries of every CTA shape,
-    windows that are not a multiple of 8, both solver modes, with and without the integrated error), and against each other."""
+    windows that are not a multiple of 8, windows of 8, 1000 and WG_PREVIEW_MAX_NL = 2048 samples, both solver modes, with and
+    without the integrated error), and against each other."""
     import jrl_walkgen_b200 as wg
     T, Tp, zc, mode = cfg
     rng = np.random.default_rng(11)
