@@ -7,6 +7,7 @@
  * and the ComAndFootRealization below only records which first-stage iteration was realised and the CoM it was given.
  * Everything between - the FIFOs, both preview stages, the delta ZMP, the NL-delayed sum - is the reference's code.
  */
+#include <unistd.h>
 #include <cstring>
 #include <deque>
 #include <sstream>
@@ -66,6 +67,14 @@ struct RefTwoStage {
 
 }  // namespace
 
+namespace {
+struct CwdGuard {     /* the constructor resets two debug files in the working directory (:72-74): keep them out of the repository */
+  char old[4096];
+  CwdGuard() { if (!getcwd(old, sizeof old)) old[0] = 0; if (chdir("/tmp")) {} }
+  ~CwdGuard() { if (old[0] && chdir(old)) {} }
+};
+}  // namespace
+
 extern "C" {
 
 /* ctor (:46-95) creates its own PreviewControl (MODE_WITHOUT_INITIALPOS, auto weights); the three parameters are set
@@ -73,7 +82,7 @@ extern "C" {
 void *ref_twostage_new(double T, double preview_time, double zc)
 {
   RefTwoStage *h = new RefTwoStage;
-  h->zpc = new ZMPPreviewControlWithMultiBodyZMP(&h->spm);
+  { CwdGuard g; h->zpc = new ZMPPreviewControlWithMultiBodyZMP(&h->spm); }
   PreviewControl *pc = h->zpc->m_PC;
   pc->SetSamplingPeriod(T);
   pc->SetPreviewControlTime(preview_time);
