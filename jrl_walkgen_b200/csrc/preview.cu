@@ -367,6 +367,7 @@ struct wg_preview_plan {
 };
 
 __device__ __forceinline__ int pad9(int e) { return e + (e >> 3); }
+__device__ __forceinline__ int swz8(int e) { return e ^ ((e >> 3) & 7); }   // XOR swizzle of 16-byte slots in groups of 8
 
 // One tick of OneIterationOfPreview for one axis, in the reference's statement order
 // (PreviewControl.cpp:346-367): u, x <- A x + B u, zmp = C x, s += p - zmp.
@@ -1019,7 +1020,13 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
 //     receive (cp.async) the 256 samples the next tile adds while phases (1c)-(2d) run: 10.4 KB of shared memory per warp at
 //     NL = 320, 16 warps per SM (the register limit at 128) and most of the L1 left for the E table;
 //   * the E table rows of a lane's halo samples are fetched five at a time before they are used (one exposed L1/L2 latency per
-//     five samples instead of one per sample).
+//     five samples instead of one per sample);
+//   * the ring is XOR-swizzled instead of padded (slot s lives at s ^ ((s >> 3) & 7): the stride-8 reads of the local pass and the
+//     lane-contiguous accesses are both conflict free), which leaves room for
+//   * a per-lane staging slot of 96 B behind the ring: the CoM rows of a tick pair leave through ONE cp.async.bulk request per
+//     lane (the TMA engine writes the lane's three sectors) instead of three scattered 256-bit stores - a warp-wide 256-bit
+//     store of this layout touches 32 different 128-byte lines, and the LSU tag stage, not HBM, was what the stores cost
+//     (measured: 39.2 -> 42.4 G steps/s).  The ZMP pair (one sector per lane) stays a 256-bit store.
 // ---------------------------------------------------------------------------------------------
 constexpr int RW_TILE = FIR_R * 32;
 constexpr int RW_U = 5;                        // halo samples per lane fetched together
@@ -1031,7 +1038,7 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
                         double *__restrict__ zmp, const double *__restrict__ com_add, const double2 *__restrict__ Etab)
 {
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ double2 sp[];             // the ring, 9/8 padded
+  extern __shared__ double2 sp[];             // the ring (XOR-swizzled), then 32 staging slots of 7 double2
   __shared__ double s_halo[8];                // W at the tile's end (x: 0..3, y: 4..7)
   __shared__ double s_carry[8];
   const int b = order[blockIdx.x];
@@ -1042,11 +1049,13 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
   if (nsteps <= 0) return;
   const int lane = threadIdx.x;
   const int CAP = RW_TILE + NLpad;             // ring capacity in samples (a multiple of 8)
+  // per-lane staging of the CoM rows of one tick pair (96 B, lane stride 112 B: conflict-free 128-bit stores) behind the ring
+  double2 *stage = sp + CAP + 7 * lane;
   if (lane < 8) s_carry[lane] = state[8 * (size_t)b + lane];   // {x,dx,ddx,y,dy,ddy,sx,sy}
   const double(*Pm)[16] = c_pc.P[SIM ? 1 : 0];
   const double2 *src = p + o;
   // first tile: samples [0, TILE + NLpad) fill the whole ring; samples past the trajectory read as zero
-  for (int e = lane; e < CAP; e += 32) cp_async16(sp + pad9(e), src + (e < L ? e : 0), e < L ? 16u : 0u);
+  for (int e = lane; e < CAP; e += 32) cp_async16(sp + swz8(e), src + (e < L ? e : 0), e < L ? 16u : 0u);
   cp_async_commit();
   int base = 0;                                // ring slot of sample `start`
 
@@ -1074,7 +1083,7 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
           e23[u] = __ldg(Etab + 2 * ii + 1);
           int hi = hb + ii;
           if (hi >= CAP) hi -= CAP;
-          q[u] = in ? sp[pad9(hi)] : make_double2(0.0, 0.0);
+          q[u] = in ? sp[swz8(hi)] : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int u = 0; u < RW_U; ++u) {
@@ -1119,15 +1128,16 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
     bx.x0 = bx.x1 = bx.x2 = bx.s = 0.0;
     by = bx;
     {
-      const double2 *own = sp + pad9(own0);
+      const double2 *own = sp + own0;          // own0 is a multiple of 8: sample j of the block sits at j ^ ((own0 >> 3) & 7)
+      const int osw = (own0 >> 3) & 7;
 #pragma unroll
       for (int r = 0; r < FIR_R; ++r) { ax[r] = 0.0; ay[r] = 0.0; }
 #pragma unroll
       for (int j = 0; j < FIR_R; ++j) {
-        const double2 a = own[j];
+        const double2 a = own[j ^ osw];
         int fi = own0 + j + NL;
         if (fi >= CAP) fi -= CAP;
-        const double2 f = sp[pad9(fi)];
+        const double2 f = sp[swz8(fi)];
         pk[j] = SIM ? a : make_double2(0.0, 0.0);
 #pragma unroll
         for (int r = 0; r <= j; ++r) {
@@ -1154,7 +1164,7 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
         int ri = base + e;
         if (ri >= CAP) ri -= CAP;
         const bool in = first + e < L;
-        cp_async16(sp + pad9(ri), src + (in ? first + e : 0), in ? 16u : 0u);
+        cp_async16(sp + swz8(ri), src + (in ? first + e : 0), in ? 16u : 0u);
       }
       cp_async_commit();
     }
@@ -1254,6 +1264,7 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
       const double *ga = ADD ? com_add + 6 * (size_t)(o + k0) : nullptr;
       const bool c32 = ((reinterpret_cast<uintptr_t>(gc) | (ADD ? reinterpret_cast<uintptr_t>(ga) : 0)) & 31) == 0;
       const bool z32 = (reinterpret_cast<uintptr_t>(gz) & 31) == 0;
+      const bool bulk = com != nullptr;        // CoM pairs through the bulk-copy engine (16-byte alignment is all it asks)
 #pragma unroll
       for (int j = 0; j < FIR_R / 2; ++j) {
         const int r0 = 2 * j, r1 = 2 * j + 1;
@@ -1274,9 +1285,19 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
               a0 += q[0]; a1 += q[1]; a2 += q[2]; a3 += q[3]; a4 += q[4]; a5 += q[5];
               b0 += q[6]; b1 += q[7]; b2 += q[8]; b3 += q[9]; b4 += q[10]; b5 += q[11];
             }
-            st32g(gc + 6 * r0, a0, a1, a2, a3, c32);
-            st32g(gc + 6 * r0 + 4, a4, a5, b0, b1, c32);
-            st32g(gc + 6 * r0 + 8, b2, b3, b4, b5, c32);
+            if (bulk) {
+              asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // the previous pair has left the staging slot
+              stage[0] = make_double2(a0, a1); stage[1] = make_double2(a2, a3); stage[2] = make_double2(a4, a5);
+              stage[3] = make_double2(b0, b1); stage[4] = make_double2(b2, b3); stage[5] = make_double2(b4, b5);
+              asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+              const unsigned sa = (unsigned)__cvta_generic_to_shared(stage);
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 96;\n" ::"l"(gc + 6 * r0), "r"(sa) : "memory");
+              asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            } else {
+              st32g(gc + 6 * r0, a0, a1, a2, a3, c32);
+              st32g(gc + 6 * r0 + 4, a4, a5, b0, b1, c32);
+              st32g(gc + 6 * r0 + 8, b2, b3, b4, b5, c32);
+            }
           }
           if (zmp) st32g(gz + 2 * r0, u0, u1, POS ? sx.x0 : zx1, POS ? sy.x0 : zy1, z32);
         } else if (k0 + r0 <= last) {          // the trajectory ends on the first tick of the pair
@@ -1305,6 +1326,7 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
     if (base >= CAP) base -= CAP;
   }
   __syncwarp();
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");     // every row handed to the bulk-copy engine has been written
   if (lane < 8) state[8 * (size_t)b + lane] = s_carry[lane];
 }
 
@@ -1601,7 +1623,7 @@ static int preview_launch_recw(wg_ctx *ctx, wg_preview_plan *pl, const int *d_or
 {
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
   const int cap = RW_TILE + NLpad;
-  const size_t smem = sizeof(double2) * (size_t)(cap + (cap >> 3) + 2);
+  const size_t smem = sizeof(double2) * (size_t)(cap + 7 * 32);     // swizzled ring + 32 staging slots of 112 B
   if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the tile");
   constexpr int slot = WG_ATTR_PREVIEW_REC_0 + 5;
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
