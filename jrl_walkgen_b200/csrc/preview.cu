@@ -1050,7 +1050,7 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
   const int lane = threadIdx.x;
   const int CAP = RW_TILE + NLpad;             // ring capacity in samples (a multiple of 8)
   // per-lane staging of the CoM rows of one tick pair (96 B, lane stride 112 B: conflict-free 128-bit stores) behind the ring
-  double2 *stage = sp + CAP + 7 * lane;
+  double2 *stage = sp + CAP + 13 * lane;
   if (lane < 8) s_carry[lane] = state[8 * (size_t)b + lane];   // {x,dx,ddx,y,dy,ddy,sx,sy}
   const double(*Pm)[16] = c_pc.P[SIM ? 1 : 0];
   const double2 *src = p + o;
@@ -1286,13 +1286,19 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
               b0 += q[6]; b1 += q[7]; b2 += q[8]; b3 += q[9]; b4 += q[10]; b5 += q[11];
             }
             if (bulk) {
-              asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // the previous pair has left the staging slot
-              stage[0] = make_double2(a0, a1); stage[1] = make_double2(a2, a3); stage[2] = make_double2(a4, a5);
-              stage[3] = make_double2(b0, b1); stage[4] = make_double2(b2, b3); stage[5] = make_double2(b4, b5);
-              asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-              const unsigned sa = (unsigned)__cvta_generic_to_shared(stage);
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 96;\n" ::"l"(gc + 6 * r0), "r"(sa) : "memory");
-              asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+              double2 *sg = stage + 6 * (j & 1);
+              if ((j & 1) == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the previous four ticks have left the slot
+              sg[0] = make_double2(a0, a1); sg[1] = make_double2(a2, a3); sg[2] = make_double2(a4, a5);
+              sg[3] = make_double2(b0, b1); sg[4] = make_double2(b2, b3); sg[5] = make_double2(b4, b5);
+              const bool second = (j & 1) == 1;
+              if (second || k0 + r1 + 2 > last) {      // four ticks staged, or the next pair will not be a whole pair
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(stage);
+                double *dst = gc + 6 * (second ? r0 - 2 : r0);
+                if (second) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 192;\n" ::"l"(dst), "r"(sa) : "memory");
+                else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 96;\n" ::"l"(dst), "r"(sa) : "memory");
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+              }
             } else {
               st32g(gc + 6 * r0, a0, a1, a2, a3, c32);
               st32g(gc + 6 * r0 + 4, a4, a5, b0, b1, c32);
@@ -1623,7 +1629,7 @@ static int preview_launch_recw(wg_ctx *ctx, wg_preview_plan *pl, const int *d_or
 {
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
   const int cap = RW_TILE + NLpad;
-  const size_t smem = sizeof(double2) * (size_t)(cap + 7 * 32);     // swizzled ring + 32 staging slots of 112 B
+  const size_t smem = sizeof(double2) * (size_t)(cap + 13 * 32);     // swizzled ring + 32 staging slots of 208 B
   if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the tile");
   constexpr int slot = WG_ATTR_PREVIEW_REC_0 + 5;
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
