@@ -1050,7 +1050,7 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
   const int lane = threadIdx.x;
   const int CAP = RW_TILE + NLpad;             // ring capacity in samples (a multiple of 8)
   // per-lane staging of the CoM rows of one tick pair (96 B, lane stride 112 B: conflict-free 128-bit stores) behind the ring
-  double2 *stage = sp + CAP + 13 * lane;
+  double2 *stage = sp + CAP + 25 * lane;
   if (lane < 8) s_carry[lane] = state[8 * (size_t)b + lane];   // {x,dx,ddx,y,dy,ddy,sx,sy}
   const double(*Pm)[16] = c_pc.P[SIM ? 1 : 0];
   const double2 *src = p + o;
@@ -1286,17 +1286,15 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
               b0 += q[6]; b1 += q[7]; b2 += q[8]; b3 += q[9]; b4 += q[10]; b5 += q[11];
             }
             if (bulk) {
-              double2 *sg = stage + 6 * (j & 1);
-              if ((j & 1) == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the previous four ticks have left the slot
+              double2 *sg = stage + 6 * j;
+              if (j == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the previous tile has left the slot
               sg[0] = make_double2(a0, a1); sg[1] = make_double2(a2, a3); sg[2] = make_double2(a4, a5);
               sg[3] = make_double2(b0, b1); sg[4] = make_double2(b2, b3); sg[5] = make_double2(b4, b5);
-              const bool second = (j & 1) == 1;
-              if (second || k0 + r1 + 2 > last) {      // four ticks staged, or the next pair will not be a whole pair
+              if (j == FIR_R / 2 - 1 || k0 + r1 + 2 > last) {      // all eight ticks staged, or the next pair will not be a whole pair
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                 const unsigned sa = (unsigned)__cvta_generic_to_shared(stage);
-                double *dst = gc + 6 * (second ? r0 - 2 : r0);
-                if (second) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 192;\n" ::"l"(dst), "r"(sa) : "memory");
-                else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 96;\n" ::"l"(dst), "r"(sa) : "memory");
+                const unsigned bytes = 96u * (unsigned)(j + 1);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gc), "r"(sa), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
               }
             } else {
@@ -1629,7 +1627,7 @@ static int preview_launch_recw(wg_ctx *ctx, wg_preview_plan *pl, const int *d_or
 {
   const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R;
   const int cap = RW_TILE + NLpad;
-  const size_t smem = sizeof(double2) * (size_t)(cap + 13 * 32);     // swizzled ring + 32 staging slots of 208 B
+  const size_t smem = sizeof(double2) * (size_t)(cap + 25 * 32);     // swizzled ring + 32 staging slots of 400 B
   if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the tile");
   constexpr int slot = WG_ATTR_PREVIEW_REC_0 + 5;
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
