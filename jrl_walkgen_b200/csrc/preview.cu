@@ -1032,7 +1032,7 @@ constexpr int RW_TILE = FIR_R * 32;
 constexpr int RW_U = 5;                        // halo samples per lane fetched together
 
 template <bool SIM, bool ADD = false, bool POS = false>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, 10)
 preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict__ offsets,
                         const double2 *__restrict__ p, double *__restrict__ state, double *__restrict__ com,
                         double *__restrict__ zmp, const double *__restrict__ com_add, const double2 *__restrict__ Etab)
