@@ -1079,8 +1079,7 @@ preview_rec_warp_kernel(const int *__restrict__ order, const int64_t *__restrict
           const int i = i0 + 32 * u;
           const bool in = i < NL;
           const int ii = in ? i : 0;
-          e01[u] = __ldg(Etab + 2 * ii);
-          e23[u] = __ldg(Etab + 2 * ii + 1);
+          ld32g(reinterpret_cast<const double *>(Etab + 2 * ii), e01[u].x, e01[u].y, e23[u].x, e23[u].y, true);   // one 32-byte row
           int hi = hb + ii;
           if (hi >= CAP) hi -= CAP;
           q[u] = in ? sp[swz8(hi)] : make_double2(0.0, 0.0);
