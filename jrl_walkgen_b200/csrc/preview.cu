@@ -1017,16 +1017,19 @@ preview_rec_kernel(const int *__restrict__ order, const int64_t *__restrict__ of
 //     downward scan (c_31 += L^8 W_end), so the scan delivers the true W of every lane and the per-lane power table is not read;
 //     the carried cart-table state enters lane 0 of the upward scan the same way;
 //   * the samples live in a ring of TILE + NLpad slots: once phase (1b) has read a lane's own 8 samples their slots are dead and
-//     receive (cp.async) the 256 samples the next tile adds while phases (1c)-(2d) run: 10.4 KB of shared memory per warp at
-//     NL = 320, 16 warps per SM (the register limit at 128) and most of the L1 left for the E table;
-//   * the E table rows of a lane's halo samples are fetched five at a time before they are used (one exposed L1/L2 latency per
-//     five samples instead of one per sample);
-//   * the ring is XOR-swizzled instead of padded (slot s lives at s ^ ((s >> 3) & 7): the stride-8 reads of the local pass and the
-//     lane-contiguous accesses are both conflict free), which leaves room for
-//   * a per-lane staging slot of 96 B behind the ring: the CoM rows of a tick pair leave through ONE cp.async.bulk request per
-//     lane (the TMA engine writes the lane's three sectors) instead of three scattered 256-bit stores - a warp-wide 256-bit
-//     store of this layout touches 32 different 128-byte lines, and the LSU tag stage, not HBM, was what the stores cost
-//     (measured: 39.2 -> 42.4 G steps/s).  The ZMP pair (one sector per lane) stays a 256-bit store.
+//     receive (cp.async) the 256 samples the next tile adds while phases (1c)-(2d) run; the ring is XOR-swizzled, not padded
+//     (slot s lives at s ^ ((s >> 3) & 7): the stride-8 reads of the local pass and the lane-contiguous accesses are both
+//     conflict free): 9.2 KB at NL = 320;
+//   * the E table rows of a lane's halo samples are fetched five at a time, one 256-bit load per row, before they are used (one
+//     exposed L1/L2 latency per five samples instead of one per sample);
+//   * the CoM rows leave through the bulk-copy engine: a lane stages the 384 bytes of its 8 ticks in its own slot behind the ring
+//     (400-byte stride: conflict-free 128-bit stores) and hands them over with ONE cp.async.bulk request per tile.  A warp-wide
+//     256-bit store of this row layout touches 32 different 128-byte lines, and the LSU tag stage - not HBM - was what the stores
+//     cost; measured on configs[1]: 39.2 G steps/s with direct stores, 42.4 with one request per tick pair (16 warps/SM), 43.8 per
+//     four ticks (13 warps/SM), 47.2 per tile (22 KB of shared memory per warp: 10 warps/SM, 138 registers, no spills).  The
+//     request is issued lane by lane (UBLKCP takes uniform registers: a 10-instruction loop per lane), which is why fewer, larger
+//     requests win against occupancy.  The ZMP pair (one sector per lane) stays a 256-bit store: a second request per lane costs
+//     more than it saves (measured 38.7 G steps/s at 8 warps/SM).
 // ---------------------------------------------------------------------------------------------
 constexpr int RW_TILE = FIR_R * 32;
 constexpr int RW_U = 5;                        // halo samples per lane fetched together
