@@ -1842,17 +1842,20 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
                             int pos_only)
 {
   if (pl->total_steps == 0 || count <= 0) return WG_OK;
-  // CTA shape: 0 = 64 threads x 8 CTAs/SM, 1 = 128 x 4, 2 = 32 x 16 (the recursive sum: one warp per trajectory, preview_rec_warp_kernel).
-  // WG_PREVIEW_SHAPE forces one; otherwise the recursive path takes the shape that fills the SMs with the trajectories of THIS launch
-  // (16 one-warp CTAs per SM need ~2400 trajectories on 148 SMs; measured on 4096 walks: 39.2 G steps/s one warp, 34.7 at 64 x 8,
-  // 35.4 at 128 x 4), the direct sum stays at 64 x 8 (measured 0.752 ms vs 0.778 (128 x 4) and 0.766 (32 x 16) on config 2).
+  // CTA shape: 0 = 64 threads x 8 CTAs/SM, 1 = 128 x 4, 2 = one warp per trajectory (preview_rec_warp_kernel, the recursive sum only).
+  // WG_PREVIEW_SHAPE / wg_preview_set_cta_shape force one; otherwise the recursive path takes the shape that is fastest for the
+  // number of trajectories of THIS launch, measured on walks of configs[1] (G steps/s at 64 x 8 | 128 x 4 | one warp):
+  //    256: 8.8 | 13.1 | 5.7     512: 14.8 | 19.9 | 11.2    1024: 23.9 | 27.4 | 22.0    1536: 27.5 | 31.7 | 29.8
+  //   2048: 31.2 | 32.2 | 36.9   3072: 34.2 | 34.8 | 43.6    4096: 34.7 | 35.4 | 48.7
+  // (ten one-warp CTAs per SM need 1480 trajectories to fill 148 SMs; below that four warps per trajectory finish sooner).
+  // The direct sum stays at 64 x 8 (measured 0.752 ms vs 0.778 (128 x 4) and 0.766 (32 x 16) on config 2).
   static int forced = -2;
   if (forced == -2) {
     const char *e = getenv("WG_PREVIEW_SHAPE");
     forced = e ? atoi(e) : -1;
   }
   const bool recursive = ctx->preview_sum_mode != WG_PREVIEW_SUM_DIRECT && ctx->preview_rec_ok;
-  const int shape = forced >= 0 ? forced : ctx->preview_cta_shape >= 0 ? ctx->preview_cta_shape : !recursive ? 0 : count >= 2048 ? 2 : count >= 1024 ? 0 : 1;
+  const int shape = forced >= 0 ? forced : ctx->preview_cta_shape >= 0 ? ctx->preview_cta_shape : !recursive ? 0 : count >= 1792 ? 2 : 1;
   if (ctx->preview_sum_mode == WG_PREVIEW_SUM_RECURSIVE && !ctx->preview_rec_ok)
     return wg_fail(ctx, WG_ERR_INVALID, "WG_PREVIEW_SUM_RECURSIVE: the window weights of this context are not of the form w' L^i v");
   if (recursive) {
