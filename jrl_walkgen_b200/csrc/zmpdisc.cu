@@ -161,29 +161,39 @@ __device__ __forceinline__ void put_foot(wg_foot_sample *dst, int64_t g, const F
 __device__ void filter_head(const ZdConsts &K, const double2 *u, int len, int ulen, const double2 *hist, int64_t F0,
                             double2 final0, double2 *head)
 {
+  // A tap that reads filtered history has r = i - j + 2 < 0, i.e. j >= i + 3, and then looks at head[q] with q = 2 i - j - 1
+  // <= i - 4: sample i depends on head samples at least four places back.  So the eight head samples are two rounds of four
+  // independent ones: lanes 0..3 run samples 4 round + lane, each summing its 11 taps in the reference's order (bitwise the
+  // serial loop, a quarter of its instructions).
   const int nh = min(len, ZD_HEAD);
+  const int lane = threadIdx.x & 31;
+  static_assert(ZD_HEAD == 8, "two rounds of four head samples");
 #pragma unroll 1
-  for (int i = 0; i < nh; ++i) {
-    double a0 = 0, a1 = 0;
-    const int64_t o = F0 + i - 1 - 2;
+  for (int round = 0; round < 2; ++round) {
+    const int i = 4 * round + lane;
+    if (lane < 4 && i < nh) {
+      double a0 = 0, a1 = 0;
+      const int64_t o = F0 + i - 1 - 2;
 #pragma unroll 1
-    for (int j = 0; j < K.nw; ++j) {
-      int r = i - j + 2;
-      double2 v;
-      if (r < 0) {
-        if (-r < o) {
-          const int q = 2 * i - j - 1;          // FinalZMPPositions[o + r] relative to F0
-          v = (q >= 0) ? head[q] : hist[ZD_HIST + q];
-        } else
-          v = final0;
-      } else {
-        if (r >= len) r = len - 1;
-        v = u[min(r, ulen - 1)];
+      for (int j = 0; j < K.nw; ++j) {
+        int r = i - j + 2;
+        double2 v;
+        if (r < 0) {
+          if (-r < o) {
+            const int q = 2 * i - j - 1;          // FinalZMPPositions[o + r] relative to F0
+            v = (q >= 0) ? head[q] : hist[ZD_HIST + q];
+          } else
+            v = final0;
+        } else {
+          if (r >= len) r = len - 1;
+          v = u[min(r, ulen - 1)];
+        }
+        a0 += K.window[j] * v.x;
+        a1 += K.window[j] * v.y;
       }
-      a0 += K.window[j] * v.x;
-      a1 += K.window[j] * v.y;
+      head[i] = make_double2(a0, a1);
     }
-    head[i] = make_double2(a0, a1);
+    __syncwarp();
   }
 }
 
@@ -335,8 +345,7 @@ zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ ste
         for (int k = n1; k < n1 + n2; ++k) u[k] = make_double2(u[k - 1].x + ex, u[k - 1].y + ey);
       }
       __syncwarp();
-      if (lane == 0) filter_head(K, u, add, add, hist, F0, final0, head);
-      __syncwarp();
+      filter_head(K, u, add, add, hist, F0, final0, head);     // whole warp: lanes 0..3 work, two rounds (ends on a __syncwarp)
       // swing-foot set-up (every lane, redundantly)
       const double next_theta = rel1.theta;
       const double rel_theta = next_theta + dTheta, rel_zmp_theta = next_theta + dZmpTheta;
@@ -462,9 +471,9 @@ zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ ste
         if (lane == 0) {
           u[0] = make_double2(back.x + dx, back.y + dy);
           for (int k = 1; k < n; ++k) u[k] = make_double2(u[k - 1].x + dx, u[k - 1].y + dy);
-          filter_head(K, u, len, n, hist, F0, final0, head);
         }
         __syncwarp();
+        filter_head(K, u, len, n, hist, F0, final0, head);     // whole warp (ends on a __syncwarp)
         for (int i = lane; i < len; i += 32) {
           const double2 f = (i < ZD_HEAD) ? head[i] : filter_body(K, u, len, n, i);
           const int64_t g = o + F0 + i;
