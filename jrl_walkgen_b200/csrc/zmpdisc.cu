@@ -210,11 +210,44 @@ __device__ __forceinline__ double2 filter_body(const ZdConsts &K, const double2 
   return make_double2(a0, a1);
 }
 
+// Filtered ZMP of lead-in sample i (InitOnLine: a ramp from (0, 0) to the neutral position through the 11-tap window).  It depends
+// on the parameters only, not on the walk: zmpdisc_lead_kernel tabulates it once per plan with this very code, and the front-end
+// kernel reads the table (11 FP64 divisions per sample and walk saved, same bits).
+__device__ __forceinline__ double2 lead_sample(const ZdConsts &K, int i)
+{
+  const wg_zmpdisc_params &P = K.P;
+  const int n = K.n_lead;
+  const double2 u2 = make_double2(0.0 + (P.zmp_neutral[0] - 0.0) * (2.0 / (double)n),
+                                  0.0 + (P.zmp_neutral[1] - 0.0) * (2.0 / (double)n));
+  double a0 = 0, a1 = 0;
+#pragma unroll 1
+  for (int j = 0; j < K.nw; ++j) {
+    int r = i - j + 2;
+    double2 v;
+    if (r < 0)
+      v = u2;
+    else {
+      if (r >= n) r = n - 1;
+      const double coef = (double)r / (double)n;
+      v = make_double2(0.0 + (P.zmp_neutral[0] - 0.0) * coef, 0.0 + (P.zmp_neutral[1] - 0.0) * coef);
+    }
+    a0 += K.window[j] * v.x;
+    a1 += K.window[j] * v.y;
+  }
+  return make_double2(a0, a1);
+}
+
+__global__ void zmpdisc_lead_kernel(const ZdConsts K, double2 *__restrict__ lead)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K.n_lead) lead[i] = lead_sample(K, i);
+}
+
 __global__ void __launch_bounds__(ZD_THREADS, 4)
 zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ step_off,
                const wg_rel_step *__restrict__ steps, const double *__restrict__ init_feet,
                const int64_t *__restrict__ samp_off, Out out, int *__restrict__ status,
-               const int *__restrict__ order, int *__restrict__ next_walk)
+               const int *__restrict__ order, int *__restrict__ next_walk, const double2 *__restrict__ lead_tab)
 {
   extern __shared__ double2 zd_smem[];
   __shared__ Poly s_poly[ZD_WARPS][7];
@@ -251,25 +284,10 @@ zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ ste
     // ---- lead-in: 2*NL samples ramping from the start ZMP (0,0) to the neutral position, init filter ------------
     {
       const int n = K.n_lead;
-      const double2 u2 = make_double2(0.0 + (P.zmp_neutral[0] - 0.0) * (2.0 / (double)n),
-                                      0.0 + (P.zmp_neutral[1] - 0.0) * (2.0 / (double)n));
 #pragma unroll 1
       for (int i = lane; i < n; i += 32) {
-        double a0 = 0, a1 = 0;
-#pragma unroll 1
-        for (int j = 0; j < K.nw; ++j) {
-          int r = i - j + 2;
-          double2 v;
-          if (r < 0)
-            v = u2;
-          else {
-            if (r >= n) r = n - 1;
-            const double coef = (double)r / (double)n;
-            v = make_double2(0.0 + (P.zmp_neutral[0] - 0.0) * coef, 0.0 + (P.zmp_neutral[1] - 0.0) * coef);
-          }
-          a0 += K.window[j] * v.x;
-          a1 += K.window[j] * v.y;
-        }
+        const double2 f = __ldg(lead_tab + i);      // lead_sample(K, i), tabulated once per plan
+        const double a0 = f.x, a1 = f.y;
         const int64_t g = o + i;
         if (out.zmpref) out.zmpref[g] = make_double2(a0, a1);
         if (out.ztheta) out.ztheta[g] = 0.0;
@@ -513,6 +531,7 @@ struct wg_kajita_plan {
   int *d_order;                    // walks sorted by decreasing length inside each chunk
   int *d_order_all;                // walks sorted by decreasing length over the whole batch (single-launch path)
   int *d_next;                     // work counter of the front-end kernel
+  double2 *d_lead;                 // filtered ZMP of the lead-in samples (walk independent), n_lead entries
   // device staging for WG_MEM_HOST calls and scratch for the ZMP reference
   double *d_zmpref, *d_state, *d_com, *d_zmpout, *d_ztheta;
   wg_foot_sample *d_left, *d_right;
@@ -662,7 +681,7 @@ int wg_kajita_plan_destroy(wg_kajita_plan *pl)
   if (pl->copy_stream) cudaStreamSynchronize(pl->copy_stream);
   if (pl->pv) wg_preview_plan_destroy(pl->pv);
   cudaFree(pl->d_step_off); cudaFree(pl->d_samp_off); cudaFree(pl->d_steps); cudaFree(pl->d_init_feet);
-  cudaFree(pl->d_status); cudaFree(pl->d_order); cudaFree(pl->d_order_all); cudaFree(pl->d_next);
+  cudaFree(pl->d_status); cudaFree(pl->d_order); cudaFree(pl->d_order_all); cudaFree(pl->d_next); cudaFree(pl->d_lead);
   cudaFree(pl->d_zmpref); cudaFree(pl->d_state); cudaFree(pl->d_com); cudaFree(pl->d_zmpout); cudaFree(pl->d_ztheta);
   cudaFree(pl->d_left); cudaFree(pl->d_right); cudaFree(pl->d_types);
   for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
@@ -725,6 +744,7 @@ int wg_kajita_plan_create(wg_ctx *ctx, const wg_zmpdisc_params *p, int B, const 
   cudaError_t e = cudaMalloc(&pl->d_step_off, sizeof(int64_t) * (B + 1));
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_order_all, sizeof(int) * B);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_next, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_lead, sizeof(double2) * (size_t)std::max(1, pl->K.n_lead));
   if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_order_all, order_all.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_samp_off, sizeof(int64_t) * (B + 1));
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_steps, sizeof(wg_rel_step) * pl->total_steps_in);
@@ -738,6 +758,10 @@ int wg_kajita_plan_create(wg_ctx *ctx, const wg_zmpdisc_params *p, int B, const 
   if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_init_feet, init_feet, sizeof(double) * 6 * B, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_order, order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(pl->d_status, 0, sizeof(int) * B, ctx->stream);
+  if (e == cudaSuccess && pl->K.n_lead > 0) {
+    zmpdisc_lead_kernel<<<(pl->K.n_lead + 127) / 128, 128, 0, ctx->stream>>>(pl->K, pl->d_lead);
+    e = cudaGetLastError();
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 2 * nchunks + 2 && e == cudaSuccess; ++i) {
     cudaEvent_t ev;
@@ -788,7 +812,7 @@ static int zd_launch(wg_ctx *ctx, wg_kajita_plan *pl, int b0, int b1, const Out 
   WG_CUDA(ctx, cudaMemsetAsync(pl->d_next, 0, sizeof(int), ctx->stream));
   wg_prof_start(ctx, WG_K_ZMPDISC);
   zmpdisc_kernel<<<grid, ZD_THREADS, smem, ctx->stream>>>(pl->K, b0, b1, pl->d_step_off, pl->d_steps, pl->d_init_feet,
-                                                         pl->d_samp_off, o, pl->d_status, order, pl->d_next);
+                                                         pl->d_samp_off, o, pl->d_status, order, pl->d_next, pl->d_lead);
   wg_prof_stop(ctx);
   WG_LAUNCHED(ctx);
   return WG_OK;
