@@ -243,7 +243,7 @@ fcals_kernel(int B, const DimConsts *__restrict__ Kp, const int64_t *__restrict_
     const int cap = (int)(lci_off[b + 1] - lci_off[b]);
     wg_lci *out = lci + lci_off[b];
     int carry = 3;      // State before sample 0 (:312-316: i == 0 forces State = 3 before the tests)
-    int count = 0;
+    int count = 0, over_i = -1;
     for (int c0 = 0; c0 < n; c0 += 32) {
       const int i = c0 + lane;
       const bool valid = i < n;
@@ -269,34 +269,49 @@ fcals_kernel(int B, const DimConsts *__restrict__ Kp, const int64_t *__restrict_
       const bool boundary = valid && (i == 0 || res != prev);
       const unsigned bm = __ballot_sync(0xffffffffu, boundary);
       const int idx = count + __popc(bm & ((1u << lane) - 1u));
-      if (boundary) {
-        const double t = clock[i];
-        if (idx >= 1 && idx - 1 < cap) out[idx - 1].t_end = t;
-        if (idx < cap) {
-          const wg_foot_sample L = left[s0 + i], R = right[s0 + i];
-          P2 hull[8];
-          int nh;
-          if (res == 3) {
-            P2 pts[8];
-            dv_foot_corners(L, hw, hh, pts);
-            dv_foot_corners(R, hw, hh, pts + 4);
-            nh = dv_convex_hull(pts, 8, hull);
-          } else {
-            nh = 4;
-            if (L.z < R.z) dv_foot_corners(L, hw, hh, hull);
-            else dv_foot_corners(R, hw, hh, hull);
-          }
-          dv_write_polygon(out + idx, hull, nh, t, i, res, Kp->merge_rows);
-        }
-      }
+      // phase 1 only records where the support state changes - in the polygon record itself -; the polygons are built
+      // afterwards, one per lane
+      if (boundary && idx < cap) { out[idx].first_sample = i; out[idx].state = res; }
+      const unsigned ov = __ballot_sync(0xffffffffu, boundary && idx == cap);   // the first polygon that does not fit still closes the last
+      if (ov) over_i = __shfl_sync(0xffffffffu, i, __ffs(ov) - 1);
       count += __popc(bm);
       const int last = min(31, n - 1 - c0);
       carry = __shfl_sync(0xffffffffu, res, last);
     }
-    if (lane == 0) {
-      if (count >= 1 && count - 1 < cap) out[count - 1].t_end = clock[n - 1];
-      n_lci[b] = count <= cap ? count : -count;
+    __syncwarp();
+    // ---- phase 2: polygon k of the walk by lane k mod 32 (a walk of configs[1] has ~20 support phases: one round instead of
+    //      20 single-lane constructions of ~2.7 k instructions each)
+    const int npoly = min(count, cap);
+    for (int k0 = 0; k0 < npoly; k0 += 32) {
+      const int k = k0 + lane;
+      int i = 0, res = 0, inext = -1;
+      if (k < npoly) {
+        i = out[k].first_sample; res = out[k].state;
+        if (k + 1 < npoly) inext = out[k + 1].first_sample;      // read before lane k + 1 rewrites its record
+      }
+      __syncwarp();
+      if (k < npoly) {
+        const double t = clock[i];
+        const wg_foot_sample L = left[s0 + i], R = right[s0 + i];
+        P2 hull[8];
+        int nh;
+        if (res == 3) {
+          P2 pts[8];
+          dv_foot_corners(L, hw, hh, pts);
+          dv_foot_corners(R, hw, hh, pts + 4);
+          nh = dv_convex_hull(pts, 8, hull);
+        } else {
+          nh = 4;
+          if (L.z < R.z) dv_foot_corners(L, hw, hh, hull);
+          else dv_foot_corners(R, hw, hh, hull);
+        }
+        dv_write_polygon(out + k, hull, nh, t, i, res, Kp->merge_rows);
+        // EndingTime: the clock of the sample that opens the next polygon (also when that one no longer fits), else the last sample
+        out[k].t_end = inext >= 0 ? clock[inext] : (k + 1 < count && over_i >= 0 ? clock[over_i] : clock[n - 1]);
+      }
+      __syncwarp();
     }
+    if (lane == 0) n_lci[b] = count <= cap ? count : -count;
   }
 }
 
