@@ -244,14 +244,29 @@ fcals_kernel(int B, const DimConsts *__restrict__ Kp, const int64_t *__restrict_
     wg_lci *out = lci + lci_off[b];
     int carry = 3;      // State before sample 0 (:312-316: i == 0 forces State = 3 before the tests)
     int count = 0, over_i = -1;
-    for (int c0 = 0; c0 < n; c0 += 32) {
+    // phase 1, 4 chunks of 32 samples per trip: the 12 strided loads of a trip are issued together (one exposed memory latency per
+    // 128 samples; the chunks are still processed in order - state and count carry over)
+    constexpr int FC_U = 4;
+    for (int cb = 0; cb < n; cb += 32 * FC_U) {
+      double lzv[FC_U], rzv[FC_U];
+      int tyv[FC_U];
+#pragma unroll
+      for (int u = 0; u < FC_U; ++u) {
+        const int iu = cb + 32 * u + lane;
+        lzv[u] = 0.0; rzv[u] = 0.0; tyv[u] = 0;
+        if (iu < n) { lzv[u] = left[s0 + iu].z; rzv[u] = right[s0 + iu].z; tyv[u] = types[3 * (s0 + iu) + 1]; }
+      }
+#pragma unroll
+      for (int u = 0; u < FC_U; ++u) {
+      const int c0 = cb + 32 * u;
+      if (c0 >= n) break;
       const int i = c0 + lane;
       const bool valid = i < n;
       int st = -1;
       double lz = 0.0, rz = 0.0;
       if (valid) {
-        lz = left[s0 + i].z; rz = right[s0 + i].z;
-        const int ty = types[3 * (s0 + i) + 1];
+        lz = lzv[u]; rz = rzv[u];
+        const int ty = tyv[u];
         const double thr = 0.00001;
         if (ty >= 10) st = 3;
         else if (lz > thr) st = 2;
@@ -277,6 +292,7 @@ fcals_kernel(int B, const DimConsts *__restrict__ Kp, const int64_t *__restrict_
       count += __popc(bm);
       const int last = min(31, n - 1 - c0);
       carry = __shfl_sync(0xffffffffu, res, last);
+      }
     }
     __syncwarp();
     // ---- phase 2: polygon k of the walk by lane k mod 32 (a walk of configs[1] has ~20 support phases: one round instead of
