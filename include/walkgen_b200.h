@@ -8,7 +8,8 @@
  *     (the reference LTHROWs / exit(0)s on these paths: PreviewControl.cpp:341-344, :394-399,
  *     PLDPSolver.cpp:822-828);
  *   - `mem` says where the *bulk* buffers of a call live: WG_MEM_HOST (the library stages them
- *     through the context's stream: H2D, kernels, D2H) or WG_MEM_DEVICE (used in place, no copies).
+ *     through the context's stream: H2D, kernels, D2H) or WG_MEM_DEVICE (used in place, no copies; device arrays must be
+ *     16-byte aligned - anything cudaMalloc / wg_malloc returns is -, the preview entries refuse others with WG_ERR_INVALID).
  *     Small metadata arrays documented as "host" are always host pointers;
  *   - calls are asynchronous on the context's CUDA stream when mem == WG_MEM_DEVICE; call wg_sync()
  *     before reading results.  With WG_MEM_HOST the call returns after the D2H copy completed;

@@ -1880,8 +1880,13 @@ static int preview_run(wg_ctx *ctx, wg_preview_plan *pl, int mem, const double *
     return wg_fail(ctx, WG_ERR_NOT_READY, "gains changed since the plan was created");
   wg_device_guard guard(ctx->device);
   if (pl->B == 0) return WG_OK;
-  if (mem == WG_MEM_DEVICE)
+  if (mem == WG_MEM_DEVICE) {
+    // the kernels move rows with 128-bit (and wider) accesses and hand CoM rows to the bulk-copy engine: 16-byte aligned arrays
+    if ((reinterpret_cast<uintptr_t>(zmpref_xy) | reinterpret_cast<uintptr_t>(com_out) | reinterpret_cast<uintptr_t>(zmp_out) |
+         reinterpret_cast<uintptr_t>(com_add)) & 15)
+      return wg_fail(ctx, WG_ERR_INVALID, "preview: device arrays must be 16-byte aligned");
     return wgi_preview_launch_range(ctx, pl, pl->d_order, pl->B, zmpref_xy, state, com_out, zmp_out, simulation, com_add, pos_only);
+  }
   if (mem != WG_MEM_HOST) return WG_ERR_INVALID;
   const size_t ns = (size_t)pl->total_samples;
   if (com_add && !pl->d_add) WG_CUDA(ctx, cudaMalloc(&pl->d_add, sizeof(double) * 6 * std::max<size_t>(1, ns)));

@@ -502,6 +502,36 @@ def test_gpu_two_contexts_on_one_device_keep_their_own_gains(ctx, mode):
 
 
 @pytest.mark.gpu
+def test_gpu_preview_refuses_device_arrays_that_are_not_16_byte_aligned(ctx):
+    """The batch kernels move rows with 128-bit accesses and bulk copies: a device array at an odd multiple of 8 bytes is refused
+    (WG_ERR_INVALID) instead of faulting on the device."""
+    import ctypes as C
+    import jrl_walkgen_b200 as wg
+    from jrl_walkgen_b200 import _capi
+    gains = wg.preview_gains(0.005, 1.6, 0.814, 1)
+    ctx.preview_set_gains(gains)
+    offsets = np.array([0, 1000], dtype=np.int64)
+    plan = ctx.preview_plan(offsets)
+    dz = ctx.to_device(np.zeros((1001, 2))); ds = ctx.to_device(np.zeros((1, 8)))
+    dc = ctx.to_device(np.zeros((1001, 6))); dzo = ctx.to_device(np.zeros((1001, 2)))
+    try:
+        for which in range(3):
+            ptrs = [dz.ptr, dc.ptr, dzo.ptr]
+            ptrs[which] += 8
+            rc = ctx.lib.wg_preview_run_batch(ctx.h, plan.h, wg.WG_MEM_DEVICE, C.c_void_p(ptrs[0]), C.c_void_p(ds.ptr),
+                                              C.c_void_p(ptrs[1]), C.c_void_p(ptrs[2]), 1)
+            assert rc == _capi.WG_ERR_INVALID, (which, rc)
+        rc = ctx.lib.wg_preview_run_batch(ctx.h, plan.h, wg.WG_MEM_DEVICE, C.c_void_p(dz.ptr), C.c_void_p(ds.ptr),
+                                          C.c_void_p(dc.ptr), C.c_void_p(dzo.ptr), 1)
+        assert rc == 0
+        ctx.sync()
+    finally:
+        for d in (dz, ds, dc, dzo):
+            d.free()
+        plan.destroy()
+
+
+@pytest.mark.gpu
 def test_gpu_weights_without_the_structure_keep_the_direct_sum(ctx):
     """A gain table that is not matrix-geometric (here: rounded to the 5 digits of the reference's PreviewControlParameters.ini)
     runs through the direct sum under AUTO, RECURSIVE is refused, and the result is the oracle's for THAT table."""
