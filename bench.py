@@ -1300,7 +1300,7 @@ def main():
     ap.add_argument("--no-kajita", action="store_true")
     ap.add_argument("--dimitrov-walks", type=int, default=4096)
     ap.add_argument("--no-dimitrov", action="store_true")
-    ap.add_argument("--wieber-walks", type=int, default=512)
+    ap.add_argument("--wieber-walks", type=int, default=888)   # 3 x 296 resident CTAs of the dense QP kernel
     ap.add_argument("--no-wieber", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="(default since round 2; kept for old command lines)")
     ap.add_argument("--no-sweep", action="store_true", help="skip BASELINE configs[4]: 1M MPC instances x 100 periods")
