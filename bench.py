@@ -988,7 +988,7 @@ def run_cuda(args):
 
     # ---- device-resident leg (value) -------------------------------------------------------
     dz = ctx.to_device(z)
-    st0 = ctx.pinned((B, 8)); st0[:] = 0.0     # pinned: the per-pass reset below is a true asynchronous copy on the stream
+    st0 = np.zeros((B, 8))                      # every pass starts from rest: the states are reset on the device (memset)
     ds = ctx.to_device(st0)
     dcom = ctx.alloc(n * 48); dzmp = ctx.alloc(n * 16)
 
@@ -998,7 +998,7 @@ def run_cuda(args):
             dist.barrier()
 
     def one_pass():
-        ctx._check(ctx.lib.wg_memcpy_h2d(ctx.h, ds.ptr, st0.ctypes.data, st0.nbytes))  # reset 256 KB of states
+        ctx._check(ctx.lib.wg_memset_device(ctx.h, ds.ptr, 0, st0.nbytes))  # reset 256 KB of states (all zero) on the device
         plan.run(dz, ds, dcom, dzmp, True, mem=wg.WG_MEM_DEVICE)
 
     # A bench "step" is `passes` passes over the 4096-walk batch (default 160: K = 20 steps time ~1.2 s of kernels, so that
