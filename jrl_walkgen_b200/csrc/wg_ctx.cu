@@ -1,5 +1,6 @@
 // wg_ctx.cu - context, memory and timing entry points of the C ABI (include/walkgen_b200.h).
 #include "wg_common.h"
+#include <algorithm>
 
 extern "C" void wg_preview_release(wg_ctx *ctx);
 extern void wg_herdt_release(wg_ctx *ctx);
@@ -130,10 +131,25 @@ int wg_memcpy_d2h(wg_ctx *ctx, void *dst, const void *src, size_t bytes)
   WG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return WG_OK;
 }
+// 16 bytes per thread, grid-stride: small fills (the states of a batch) stay on the SMs, in order with the kernels around them
+__global__ void __launch_bounds__(256) wg_fill_kernel(uint4 *__restrict__ p, unsigned v32, size_t n16)
+{
+  const uint4 v = make_uint4(v32, v32, v32, v32);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
 int wg_memset_device(wg_ctx *ctx, void *dst, int value, size_t bytes)
 {
   if (!ctx) return WG_ERR_INVALID;
   wg_device_guard g(ctx->device);
+  if (bytes == 0) return WG_OK;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (bytes & 15) == 0) {
+    const unsigned b = (unsigned)value & 0xffu, v32 = b | (b << 8) | (b << 16) | (b << 24);
+    const size_t n16 = bytes / 16;
+    const int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->sm_count * 8);
+    wg_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<uint4 *>(dst), v32, n16);
+    WG_CUDA(ctx, cudaGetLastError());
+    return WG_OK;
+  }
   WG_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
   return WG_OK;
 }
