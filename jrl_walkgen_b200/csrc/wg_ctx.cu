@@ -148,6 +148,7 @@ int wg_memset_device(wg_ctx *ctx, void *dst, int value, size_t bytes)
     const int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->sm_count * 8);
     wg_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<uint4 *>(dst), v32, n16);
     WG_CUDA(ctx, cudaGetLastError());
+    WG_LAUNCHED(ctx);
     return WG_OK;
   }
   WG_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
