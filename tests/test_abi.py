@@ -114,3 +114,25 @@ def test_product_does_not_reference_the_oracle():
     lib = os.path.join(pkg, "libwalkgen_b200.so")
     syms = subprocess.run(["nm", "-D", lib], capture_output=True, text=True).stdout
     assert "oracle_" not in syms
+
+
+@pytest.mark.gpu
+def test_gpu_memset_device_fill_kernel_and_fallback():
+    """wg_memset_device: 16-byte aligned fills run the library's own grid-stride kernel, anything else cudaMemsetAsync; both must
+    set exactly the bytes asked for (byte value replicated) and nothing around them."""
+    import numpy as np
+    import jrl_walkgen_b200 as wg
+    ctx = wg.Context(0)
+    try:
+        n = 1 << 20
+        buf = ctx.to_device(np.full(n, 0x11, dtype=np.uint8))
+        for off, cnt, val in ((0, n, 0), (4096, 65536, 0xAB), (16, 48, 0x7F), (8, 100, 0x01), (3, 5, 0xFF), (32, 0, 0x55)):
+            ref = np.full(n, 0x11, dtype=np.uint8)
+            buf.upload(ref)
+            ref[off:off + cnt] = val
+            ctx._check(ctx.lib.wg_memset_device(ctx.h, buf.ptr + off, val, cnt))
+            got = buf.download(np.uint8, (n,))
+            assert np.array_equal(got, ref), (off, cnt, val)
+        buf.free()
+    finally:
+        ctx.close()
