@@ -341,6 +341,42 @@ def test_gpu_preview_linearity_full_size(ctx):
 
 
 @pytest.mark.gpu
+def test_gpu_preview_full_size_device_resident_vs_oracle_and_host_path(ctx):
+    """BASELINE config-2 scale through the kernel the bench times: 4096 ragged walks in ONE device-resident launch (the launch
+    heuristic picks preview_rec_warp_kernel from 1792 trajectories up) against (i) the oracle on 32 of the walks, every valid row,
+    and (ii) the host-buffer path on ALL walks (16 chunks of 256 walks: preview_rec_kernel at 128 x 4) - two kernels, two store
+    paths (bulk-copy engine / shared-memory staging), same numbers."""
+    import jrl_walkgen_b200 as wg
+    rng = np.random.default_rng(8)
+    gains = wg.preview_gains()
+    og = ol.OracleGains(0.005, 1.6, 0.814, 1)
+    B = 4096
+    lens = rng.integers(2800, 4600, size=B)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = int(offsets[-1])
+    z = np.cumsum(rng.normal(scale=2e-3, size=(n, 2)), axis=0)
+    for b in range(B):                               # every walk starts at the origin
+        z[offsets[b]:offsets[b + 1]] -= z[offsets[b]]
+    st0 = rng.normal(scale=0.01, size=(B, 8))
+    com_d, zmp_d, st_d, steps = _run_gpu(ctx, gains, offsets, z, st0, True, mem_device=True)
+    com_h, zmp_h, st_h, _ = _run_gpu(ctx, gains, offsets, z, st0, True, mem_device=False)
+    rows = _valid_rows(offsets, 320)
+    assert steps == len(rows)
+    assert np.abs(com_d[rows] - com_h[rows])[:, [0, 3]].max() < 1e-11
+    assert np.abs(com_d[rows] - com_h[rows]).max() < 1e-8 and np.abs(zmp_d[rows] - zmp_h[rows]).max() < 1e-9
+    assert np.abs(st_d - st_h).max() < 1e-9
+    pick = rng.choice(B, size=32, replace=False)
+    for b in pick:
+        o, L = int(offsets[b]), int(lens[b])
+        so = st0[b:b + 1].copy()
+        com_o, zmp_o, _ = ol.oracle_preview_batch(og, np.array([0, L], dtype=np.int64), z[o:o + L], so)
+        k = L - 320 + 1
+        assert np.abs(com_d[o:o + k] - com_o[:k])[:, [0, 3]].max() < TOL_COM, b
+        assert np.abs(zmp_d[o:o + k] - zmp_o[:k]).max() < 1e-8, b
+        assert np.allclose(st_d[b], so[0], rtol=1e-7, atol=1e-8), b
+
+
+@pytest.mark.gpu
 def test_gpu_batched_gains_match_host_solve_and_oracle(ctx):
     """wg_preview_gains_batch (SURVEY 8f rank 4: OptimalControllerSolver::ComputeWeights for per-instance (T, preview time, zc),
     one thread per parameter set) against the host solve of wg_preview_gains on every set, and against the oracle's Riccati
