@@ -170,8 +170,8 @@ double wg_preview_sum_fit(const wg_preview_gains_t *gains);   /* host only: the 
 int wg_preview_set_sum_mode(wg_ctx *ctx, int mode);
 int wg_preview_sum_info(wg_ctx *ctx, int *mode_in_use, double *fit_residual);
 /* Tuning knob: the CTA shape of the batch kernels.  -1 (default) = chosen per launch from the number of trajectories (the
- * recursive sum runs one warp per trajectory from 1792 trajectories up, four warps per trajectory below that);
- * 0 = 64 threads x 8 CTAs/SM, 1 = 128 x 4, 2 = 32 x 16.  Results do not depend on it beyond the summation order (1e-14).  The
+ * recursive sum runs one warp per trajectory from 1792 trajectories up, four warps per trajectory below that, eight below 768);
+ * 0 = 64 threads x 8 CTAs/SM, 1 = 128 x 4, 2 = 32 x 16 (one warp per trajectory), 3 = 256 x 2 (falls back to 1 when the window does not fit).  Results do not depend on it beyond the summation order (1e-14).  The
  * environment variable WG_PREVIEW_SHAPE, read once per process, overrides both. */
 int wg_preview_set_cta_shape(wg_ctx *ctx, int shape);
 

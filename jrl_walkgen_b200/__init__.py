@@ -198,7 +198,7 @@ class Context:
         self._check(self.lib.wg_preview_set_sum_mode(self.h, int(mode)))
 
     def preview_set_cta_shape(self, shape: int):
-        """wg_preview_set_cta_shape: -1 per launch (default), 0 = 64 x 8, 1 = 128 x 4, 2 = one warp per trajectory."""
+        """wg_preview_set_cta_shape: -1 per launch (default), 0 = 64 x 8, 1 = 128 x 4, 2 = one warp per trajectory, 3 = 256 x 2."""
         self._check(self.lib.wg_preview_set_cta_shape(self.h, int(shape)))
 
     def preview_sum_info(self):

@@ -1596,7 +1596,7 @@ static int preview_launch_rec(wg_ctx *ctx, wg_preview_plan *pl, const int *d_ord
   const int cap = 2 * FIR_R * THREADS + NLpad;     // ring of two tiles + the window
   const size_t smem = sizeof(double2) * (size_t)(cap + (cap >> 3) + 2);
   if (smem > 96 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "preview window too large for the tile");
-  constexpr int slot = WG_ATTR_PREVIEW_REC_0 + 5 * (THREADS == 128 ? 0 : THREADS == 32 ? 1 : 2);
+  constexpr int slot = WG_ATTR_PREVIEW_REC_0 + 5 * (THREADS == 128 ? 0 : THREADS == 32 ? 1 : THREADS == 64 ? 2 : 3);
   const double2 *pz = reinterpret_cast<const double2 *>(d_zmp);
   const double2 *E = reinterpret_cast<const double2 *>(ctx->preview_rec_dev);
   const double2 *lp = E + 2 * (size_t)NLpad;
@@ -1732,7 +1732,7 @@ int wg_preview_set_sum_mode(wg_ctx *ctx, int mode)
 
 int wg_preview_set_cta_shape(wg_ctx *ctx, int shape)
 {
-  if (!ctx || shape < -1 || shape > 2) return WG_ERR_INVALID;
+  if (!ctx || shape < -1 || shape > 3) return WG_ERR_INVALID;
   ctx->preview_cta_shape = shape;
   return WG_OK;
 }
@@ -1842,12 +1842,15 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
                             int pos_only)
 {
   if (pl->total_steps == 0 || count <= 0) return WG_OK;
-  // CTA shape: 0 = 64 threads x 8 CTAs/SM, 1 = 128 x 4, 2 = one warp per trajectory (preview_rec_warp_kernel, the recursive sum only).
-  // WG_PREVIEW_SHAPE / wg_preview_set_cta_shape force one; otherwise the recursive path takes the shape that is fastest for the
-  // number of trajectories of THIS launch, measured on walks of configs[1] (G steps/s at 64 x 8 | 128 x 4 | one warp):
-  //    256: 8.8 | 13.1 | 5.7     512: 14.8 | 19.9 | 11.2    1024: 23.9 | 27.4 | 22.0    1536: 27.5 | 31.7 | 29.8
-  //   2048: 31.2 | 32.2 | 36.9   3072: 34.2 | 34.8 | 43.6    4096: 34.7 | 35.4 | 48.7
-  // (ten one-warp CTAs per SM need 1480 trajectories to fill 148 SMs; below that four warps per trajectory finish sooner).
+  // CTA shape: 0 = 64 threads x 8 CTAs/SM, 1 = 128 x 4, 2 = one warp per trajectory (preview_rec_warp_kernel), 3 = 256 x 2 (2 and 3:
+  // the recursive sum only).  WG_PREVIEW_SHAPE / wg_preview_set_cta_shape force one; otherwise the recursive path takes the shape
+  // that is fastest for the number of trajectories of THIS launch, measured on walks of configs[1] (G steps/s):
+  //   walks     32    64    128    256    512   1024   1536   2048   3072   4096
+  //   64 x 8     -     -      -    8.8   14.8   23.9   27.5   31.2   34.2   34.7
+  //   128 x 4   2.2   4.2    8.0  14.1   21.3   27.4   31.7   32.2   34.8   35.4
+  //   256 x 2   2.7   5.1    9.7  16.4   23.8     -      -      -      -      -
+  //   one warp   -     -      -    5.7   11.2   22.0   29.8   36.9   43.6   48.7
+  // (ten one-warp CTAs per SM need 1480 trajectories to fill 148 SMs; below that more warps per trajectory finish sooner).
   // The direct sum stays at 64 x 8 (measured 0.752 ms vs 0.778 (128 x 4) and 0.766 (32 x 16) on config 2).
   static int forced = -2;
   if (forced == -2) {
@@ -1855,13 +1858,18 @@ int wgi_preview_launch_range(wg_ctx *ctx, wg_preview_plan *pl, const int *d_orde
     forced = e ? atoi(e) : -1;
   }
   const bool recursive = ctx->preview_sum_mode != WG_PREVIEW_SUM_DIRECT && ctx->preview_rec_ok;
-  const int shape = forced >= 0 ? forced : ctx->preview_cta_shape >= 0 ? ctx->preview_cta_shape : !recursive ? 0 : count >= 1792 ? 2 : 1;
+  int shape = forced >= 0 ? forced : ctx->preview_cta_shape >= 0 ? ctx->preview_cta_shape : !recursive ? 0 : count >= 1792 ? 2 : count >= 768 ? 1 : 3;
+  if (shape == 3) {      // eight warps per trajectory (tiles of 2048 ticks): the ring of two tiles + the window must fit 96 KB
+    const int NLpad = (pl->NL + FIR_R - 1) / FIR_R * FIR_R, cap = 2 * FIR_R * 256 + NLpad;
+    if (!recursive || sizeof(double2) * (size_t)(cap + (cap >> 3) + 2) > 96 * 1024) shape = 1;
+  }
   if (ctx->preview_sum_mode == WG_PREVIEW_SUM_RECURSIVE && !ctx->preview_rec_ok)
     return wg_fail(ctx, WG_ERR_INVALID, "WG_PREVIEW_SUM_RECURSIVE: the window weights of this context are not of the form w' L^i v");
   if (recursive) {
     switch (shape) {
     case 1: return preview_launch_rec<128, 4>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
     case 2: return preview_launch_recw(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
+    case 3: return preview_launch_rec<256, 2>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
     default: return preview_launch_rec<64, 8>(ctx, pl, d_order, count, d_zmp, d_state, d_com, d_zmpout, simulation, d_com_add, pos_only != 0);
     }
   }

@@ -107,7 +107,7 @@ enum { WG_ATTR_PREVIEW_0 = 0, /* .. 5: {sim, nosim} x 3 CTA shapes */ WG_ATTR_HE
        WG_ATTR_PLDP = 8, WG_ATTR_PLDP_RANKED = 9, WG_ATTR_ZMPDISC = 10, WG_ATTR_DIMITROV = 11, WG_ATTR_DENSEQP = 12,
        WG_ATTR_PREVIEW_ADD_0 = 13, /* .. 15: second-stage variant x 3 CTA shapes */
        WG_ATTR_PREVIEW_POS_0 = 16, /* .. 21: position-only variant {sim, nosim} x 3 CTA shapes */ WG_ATTR_DENSEQP_RANKED = 22,
-       WG_ATTR_PREVIEW_REC_0 = 24, /* .. 38: recursive preview kernel, 5 variants x 3 CTA shapes */ WG_ATTR_SLOTS = 40 };
+       WG_ATTR_PREVIEW_REC_0 = 24, /* .. 43: recursive preview kernel, 5 variants x 4 CTA shapes */ WG_ATTR_SLOTS = 48 };
 extern "C" int wgi_smem_attr(wg_ctx *ctx, int slot, const void *func, size_t bytes);
 #define WG_SMEM_ATTR(ctx, slot, func, bytes)                                              \
   do {                                                                                    \

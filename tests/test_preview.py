@@ -473,6 +473,7 @@ def test_gpu_recursive_and_direct_preview_sums_agree_with_the_oracle(ctx, cfg):
             com_o, zmp_o, _ = ol.oracle_preview_batch(og, offsets, z, st_o, simulation=sim)
             for name, m, shape in (("recursive", wg.PREVIEW_SUM_RECURSIVE, -1), ("recursive 64x8", wg.PREVIEW_SUM_RECURSIVE, 0),
                                    ("recursive 128x4", wg.PREVIEW_SUM_RECURSIVE, 1), ("recursive one warp", wg.PREVIEW_SUM_RECURSIVE, 2),
+                                   ("recursive 256x2", wg.PREVIEW_SUM_RECURSIVE, 3),
                                    ("direct", wg.PREVIEW_SUM_DIRECT, -1)):
                 ctx.preview_set_gains(gains)
                 ctx.preview_set_sum_mode(m)
@@ -485,7 +486,7 @@ def test_gpu_recursive_and_direct_preview_sums_agree_with_the_oracle(ctx, cfg):
                 assert np.abs(com[rows] - com_o[rows]).max() < 1e-7, (name, sim)
                 assert np.abs(zmp[rows] - zmp_o[rows]).max() < 1e-8, (name, sim)
                 assert np.allclose(st, st_o, rtol=1e-7, atol=1e-8), (name, sim)
-            for name in ("recursive 64x8", "recursive 128x4", "recursive one warp"):
+            for name in ("recursive 64x8", "recursive 128x4", "recursive one warp", "recursive 256x2"):
                 assert np.abs(out[name][0][rows] - out["direct"][0][rows])[:, [0, 3]].max() < 1e-11, name
             d = np.abs(out["recursive"][0][rows] - out["direct"][0][rows])
             print(f"cfg {cfg} sim {sim}: recursive vs direct sum, max |dCoM| = {d[:, [0, 3]].max():.2e} m, "

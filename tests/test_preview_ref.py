@@ -174,11 +174,11 @@ def _gpu_run(ctx, gains, offsets, z, st0, simulation=True):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [-1, 0, 2])
+@pytest.mark.parametrize("shape", [-1, 0, 2, 3])
 @pytest.mark.parametrize("own_gains", [False, True])
 def test_gpu_preview_vs_reference_object(ctx, own_gains, shape):
     """The batch preview kernels (shape -1: the default choice for this batch size; 0: preview_rec_kernel at 64 x 8; 2:
-    preview_rec_warp_kernel, the one a batch of thousands of walks runs through) against PreviewControl::OneIterationOfPreview of the reference object on the StraightWalking
+    preview_rec_warp_kernel, the one a batch of thousands of walks runs through; 3: 256 x 2, small batches) against PreviewControl::OneIterationOfPreview of the reference object on the StraightWalking
     ZMP reference and 64 random walks.  own_gains=False: both sides use the product's gains (pins the recursion);
     own_gains=True: the reference computes its own gains through dgges_ (pins gains + recursion end to end)."""
     import jrl_walkgen_b200 as wg
