@@ -3,12 +3,13 @@
 
 Workload (BASELINE.json configs[1]): Kajita2003 preview control, 4096 random straight/circle footstep walks turned into
 5 ms ZMP references by ZMPDiscretization (the product's kernel in the CUDA arm, the oracle's restatement in the reference
-arm; both pinned to the TestKajita2003 datrefs), 320-tap preview window.  A "step" of the bench is one pass of the hot path over the whole batch
-(every preview step of every walk); the metric unit is one preview step = one OneIterationOfPreview call for
-both axes (PreviewControl.cpp:324-374).
+arm; both pinned to the TestKajita2003 datrefs), 320-tap preview window.  A "step" of the bench is --passes-per-step passes (default
+160, so that 20 steps time >= 1 s) of the hot path over the whole batch (every preview step of every walk); the metric unit is
+one preview step = one OneIterationOfPreview call for both axes (PreviewControl.cpp:324-374).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            the CUDA path through the C ABI
-  python bench.py --impl reference [...]                         the reference's CPU path (oracle port) on host cores
+  python bench.py --impl reference [...]                         the reference's CPU path on the host cores: its own
+                                                                 PreviewControl object code (oracle/_ref), one process per core
 
 With N > 1 (torchrun) every rank runs the same 4096-walk batch shape on its own GPU with its own seed
 (instances are independent: weak scaling, no data-path collective); value = all steps of all ranks / max time.
