@@ -243,7 +243,8 @@ __global__ void zmpdisc_lead_kernel(const ZdConsts K, double2 *__restrict__ lead
   if (i < K.n_lead) lead[i] = lead_sample(K, i);
 }
 
-__global__ void __launch_bounds__(ZD_THREADS, 4)
+// 3 CTAs per SM: 168 registers, no spills (measured 0.72 ms per 4096 walks against 0.77 at 4 CTAs / 128 registers / 56 B of spills, 1.03 at 5)
+__global__ void __launch_bounds__(ZD_THREADS, 3)
 zmpdisc_kernel(const ZdConsts K, int b0, int b1, const int64_t *__restrict__ step_off,
                const wg_rel_step *__restrict__ steps, const double *__restrict__ init_feet,
                const int64_t *__restrict__ samp_off, Out out, int *__restrict__ status,
@@ -805,7 +806,7 @@ static int zd_launch(wg_ctx *ctx, wg_kajita_plan *pl, int b0, int b1, const Out 
   if (smem > 200 * 1024) return wg_fail(ctx, WG_ERR_INVALID, "step segment too long for the shared-memory buffer");
   WG_SMEM_ATTR(ctx, WG_ATTR_ZMPDISC, zmpdisc_kernel, smem);
   const int walks = b1 - b0;
-  const int grid = std::max(1, std::min((walks + ZD_WARPS - 1) / ZD_WARPS, ctx->sm_count * 4));
+  const int grid = std::max(1, std::min((walks + ZD_WARPS - 1) / ZD_WARPS, ctx->sm_count * 3));
   // the whole batch uses the global longest-first order, a chunk [b0, b1) the per-chunk one (both are permutations of
   // their range stored at positions b0 .. b1-1)
   const int *order = (b0 == 0 && b1 == pl->B) ? pl->d_order_all : pl->d_order;
