@@ -347,7 +347,7 @@ struct DimWarp {
 // 4 CTAs/SM (128 registers) measured best at both batch sizes tried: 4096 walks 36.1 ms (3 CTAs/SM at 161 registers: 38 ms, 5
 // CTAs/SM at 96 registers: 47.8 ms, 6 at 80 registers with spills: 58 ms); 16 384 walks 111 ms (3: 122 ms, 5: 121 ms).  A walk is
 // a serial chain of some hundred periods: per-warp speed (registers, few warps per scheduler) counts as much as residency.
-__global__ void __launch_bounds__(DM_WARPS * 32, 4)
+__global__ void __launch_bounds__(DM_WARPS * 32, 3)   // 168 registers, no spills: 32.2 ms per 4096 walks against 33.8 at 4 CTAs / 128 registers
 dimitrov_kernel(int B, const DimConsts *__restrict__ Kp, const PldpConsts *__restrict__ Cp,
                 const int64_t *__restrict__ samp_off, const double *__restrict__ clock,
                 const int64_t *__restrict__ lci_off, const wg_lci *__restrict__ lci, const int32_t *__restrict__ n_lci,
@@ -922,7 +922,7 @@ int wg_dimitrov_run_batch(wg_ctx *ctx, wg_kajita_plan *plan, int mem, double *co
   // ---- FootConstraintsAsLinearSystem
   if ((rc = launch_fcals(ctx, H, B, V.d_samp_off, d_left, d_right, d_types, d_lo, d_lci, d_nlci)) != WG_OK) return rc;
   // ---- the loop
-  const int grid = std::max(1, std::min((B + DM_WARPS - 1) / DM_WARPS, ctx->sm_count * 4));
+  const int grid = std::max(1, std::min((B + DM_WARPS - 1) / DM_WARPS, ctx->sm_count * 3));
   if ((rc = dm_ensure(ctx, H, 11, 64)) != WG_OK) return rc;
   int *d_next = static_cast<int *>(H->buf[11]);
   WG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(int), ctx->stream));
